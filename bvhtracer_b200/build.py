@@ -1,0 +1,86 @@
+"""Build libbvht_cuda.so (the C-ABI library of include/bvht.h) in-tree with nvcc for sm_100a.
+
+    python -m bvhtracer_b200.build [--force]
+
+The trace kernels are compiled twice from the same source with different floating-point flags:
+strict (--fmad=false, IEEE div/sqrt, no FTZ) and fast (--fmad=true).  nvcc cross-compiles without a GPU.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, "csrc")
+LIB_DIR = os.path.join(PKG, "lib")
+OBJ_DIR = os.path.join(PKG, "build")
+LIB_PATH = os.path.join(LIB_DIR, "libbvht_cuda.so")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+          "-Xcompiler", "-fno-fast-math", "-Xcompiler", "-ffp-contract=off"]
+IEEE = ["-prec-div=true", "-prec-sqrt=true", "-ftz=false"]
+STRICT = ["--fmad=false"] + IEEE
+FAST = ["--fmad=true"] + IEEE
+
+UNITS = [
+    # source,             extra flags
+    ("trace_strict.cu", STRICT),
+    ("trace_fast.cu", FAST),
+    ("upload_kernels.cu", STRICT),
+    ("refit_kernels.cu", STRICT),
+    ("bvht_api.cu", STRICT),
+    ("leaf_accel.cpp", []),
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _deps():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(os.path.dirname(PKG), "include", "bvht.h")]
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(d) > t for d in _deps())
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = _nvcc()
+    os.makedirs(LIB_DIR, exist_ok=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    objs = []
+    procs = []
+    for src, extra in UNITS:
+        obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    failed = False
+    for src, cmd, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(f"[bvht build] {src} FAILED\n{' '.join(cmd)}\n{out}\n")
+        elif verbose and out.strip():
+            sys.stderr.write(f"[bvht build] {src}\n{out}\n")
+    if failed:
+        raise RuntimeError("nvcc compilation failed")
+    tmp = LIB_PATH + ".tmp"
+    cmd = [nvcc] + ARCH + ["-shared", "-o", tmp] + objs
+    subprocess.check_call(cmd)
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,765 @@
+// bvht_api.cu -- the C ABI of include/bvht.h: context, uploads, refit, trace launches.
+//
+// Host-side runtime only (no device code here).  One bvht_ctx owns one device, one stream, every device
+// allocation and a small pinned staging buffer.  Nothing throws across the ABI; every CUDA error is turned
+// into a status code + message.  There is deliberately NO CPU fallback.
+#include "../../include/bvht.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "device_types.cuh"
+#include "launchers.hpp"
+#include "leaf_accel.hpp"
+
+using namespace bvht;
+
+namespace {
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr uint32_t kRefitChunkTris = 512;
+constexpr int kTraceBlock = 128;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct Blas {
+    bool alive = false;
+    uint32_t n_tris = 0, nodes_used = 0;
+    std::vector<bvht_bvh_node> h_nodes;     // host copy of the uploaded node pool (topology for validation / accel)
+    std::vector<float> h_tris;              // host copy of the vertices (needed to rebuild the leaf accelerator)
+    DevBuf tris_aos, nodes, v0, e1, e2;
+    // refit plan
+    DevBuf chunk_leaf, chunk_first, chunk_count, leaf_chunks, parent, scratch, counters;
+    uint32_t n_chunks = 0;
+    // leaf accelerator
+    DevBuf sub_nodes, sub_order, sv0, se1, se2, leaf_sub_root;
+    uint32_t n_sub = 0;
+    float d_max = 0.0f, o_max = 0.0f;
+};
+
+} // namespace
+
+struct bvht_ctx {
+    int device = 0;
+    uint32_t flags = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;       // trace timing
+    cudaEvent_t ev_c = nullptr, ev_d = nullptr;       // refit timing
+    cudaEvent_t ev_e = nullptr, ev_f = nullptr;       // upload timing
+    bool trace_timed = false, refit_timed = false;
+    std::vector<Blas> blas;
+    DevBuf blas_desc;                                 // BlasDesc[blas.size()]
+    bool blas_desc_dirty = true;
+    DevBuf tlas, inst_cols, inst_blas;
+    uint32_t tlas_nodes_used = 0, n_inst = 0;
+    DevBuf work_counter;
+    DevBuf out_buf, rays_buf;                         // device staging for the host-pointer entry points
+    void* pinned = nullptr; size_t pinned_bytes = 0;  // pinned staging for small uploads
+    int sm_count = 0;
+    bvht_stats stats;
+    std::string err;
+};
+
+namespace {
+
+int fail(bvht_ctx* ctx, int status, const char* fmt, ...) {
+    if (ctx) {
+        char buf[512];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        ctx->err = buf;
+    }
+    return status;
+}
+
+#define CU(ctx, call)                                                                                     \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? BVHT_ERR_OUT_OF_MEMORY : BVHT_ERR_CUDA,   \
+                        "%s failed: %s", #call, cudaGetErrorString(e__));                                 \
+    } while (0)
+
+int ensure(bvht_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.bytes && b.p) return BVHT_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+    if (bytes == 0) bytes = 16;
+    CU(ctx, cudaMalloc(&b.p, bytes));
+    b.bytes = bytes;
+    return BVHT_OK;
+}
+
+void release(DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+
+int ensure_pinned(bvht_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_bytes) return BVHT_OK;
+    if (ctx->pinned) { cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
+    size_t want = std::max<size_t>(bytes, 1 << 16);
+    CU(ctx, cudaMallocHost(&ctx->pinned, want));
+    ctx->pinned_bytes = want;
+    return BVHT_OK;
+}
+
+int h2d(bvht_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return BVHT_OK;
+    CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += bytes;
+    return BVHT_OK;
+}
+
+// Upload a small host array through the pinned staging buffer (safe to return before the copy has run).
+int h2d_staged(bvht_ctx* ctx, void* dst, const void* src, size_t bytes, size_t& staging_off) {
+    if (bytes == 0) return BVHT_OK;
+    memcpy((char*)ctx->pinned + staging_off, src, bytes);
+    int rc = h2d(ctx, dst, (char*)ctx->pinned + staging_off, bytes);
+    staging_off += (bytes + 255) & ~size_t(255);
+    return rc;
+}
+
+void free_blas(Blas& b) {
+    for (DevBuf* d : { &b.tris_aos, &b.nodes, &b.v0, &b.e1, &b.e2, &b.chunk_leaf, &b.chunk_first, &b.chunk_count,
+                       &b.leaf_chunks, &b.parent, &b.scratch, &b.counters, &b.sub_nodes, &b.sub_order, &b.sv0, &b.se1,
+                       &b.se2, &b.leaf_sub_root })
+        release(*d);
+    b = Blas();
+}
+
+// Walk the uploaded tree: bounds-check every index, reject cycles / shared nodes, bound the traversal stack.
+int validate_bvh(bvht_ctx* ctx, const bvht_bvh_node* nodes, uint32_t nodes_used, uint32_t n_tris,
+                 std::vector<uint32_t>& parent, uint32_t& max_depth) {
+    if (nodes_used < 1) return fail(ctx, BVHT_ERR_MALFORMED_BVH, "BVH has no nodes");
+    parent.assign(nodes_used, kNone);
+    std::vector<uint8_t> seen(nodes_used, 0);
+    std::vector<std::pair<uint32_t, uint32_t>> stack;   // node, depth
+    stack.push_back({ 0u, 1u });
+    seen[0] = 1;
+    max_depth = 0;
+    uint64_t covered = 0;
+    while (!stack.empty()) {
+        auto [ni, depth] = stack.back(); stack.pop_back();
+        max_depth = std::max(max_depth, depth);
+        const bvht_bvh_node& n = nodes[ni];
+        if (n.prim_count > 0) {
+            if ((uint64_t)n.left_first + n.prim_count > n_tris)
+                return fail(ctx, BVHT_ERR_MALFORMED_BVH, "leaf %u covers primitives [%u, %u) beyond n_tris = %u", ni,
+                            n.left_first, n.left_first + n.prim_count, n_tris);
+            covered += n.prim_count;
+        } else {
+            uint32_t l = n.left_first;
+            if (l == 0 || (uint64_t)l + 1 >= nodes_used)
+                return fail(ctx, BVHT_ERR_MALFORMED_BVH, "branch %u has children %u,%u outside [1, %u)", ni, l, l + 1, nodes_used);
+            for (uint32_t c = l; c <= l + 1; ++c) {
+                if (seen[c]) return fail(ctx, BVHT_ERR_MALFORMED_BVH, "node %u is reachable twice", c);
+                seen[c] = 1; parent[c] = ni;
+                stack.push_back({ c, depth + 1 });
+            }
+        }
+    }
+    (void)covered;
+    if (max_depth > (uint32_t)kBlasStack)
+        return fail(ctx, BVHT_ERR_MALFORMED_BVH, "BVH depth %u exceeds the traversal stack bound %d", max_depth, kBlasStack);
+    return BVHT_OK;
+}
+
+int upload_u32(bvht_ctx* ctx, DevBuf& d, const std::vector<uint32_t>& v) {
+    int rc = ensure(ctx, d, v.size() * 4);
+    if (rc) return rc;
+    // pageable source: cudaMemcpyAsync stages it before returning, so the vector may die afterwards
+    return h2d(ctx, d.p, v.data(), v.size() * 4);
+}
+
+int build_and_upload_accel(bvht_ctx* ctx, Blas& b) {
+    LeafAccelConfig cfg;
+    LeafAccelHost acc;
+    if (!build_leaf_accel(b.h_tris.data(), b.n_tris, b.h_nodes.data(), b.nodes_used, cfg, acc))
+        return fail(ctx, BVHT_ERR_MALFORMED_BVH, "leaf accelerator build failed");
+    if (acc.max_depth + 2 > (uint32_t)kSubStack)
+        return fail(ctx, BVHT_ERR_MALFORMED_BVH, "leaf accelerator depth %u exceeds the stack bound %d", acc.max_depth, kSubStack);
+    b.n_sub = (uint32_t)acc.order.size();
+    b.d_max = acc.d_max; b.o_max = acc.o_max;
+    int rc;
+    if ((rc = ensure(ctx, b.sub_nodes, acc.sub_nodes.size() * 4))) return rc;
+    if ((rc = h2d(ctx, b.sub_nodes.p, acc.sub_nodes.data(), acc.sub_nodes.size() * 4))) return rc;
+    if ((rc = upload_u32(ctx, b.sub_order, acc.order))) return rc;
+    if ((rc = upload_u32(ctx, b.leaf_sub_root, acc.leaf_sub_root))) return rc;
+    if ((rc = ensure(ctx, b.sv0, (size_t)b.n_sub * 16))) return rc;
+    if ((rc = ensure(ctx, b.se1, (size_t)b.n_sub * 16))) return rc;
+    if ((rc = ensure(ctx, b.se2, (size_t)b.n_sub * 16))) return rc;
+    CU(ctx, launch_repack_sub_triangles((const float*)b.tris_aos.p, (const uint32_t*)b.sub_order.p, b.n_sub,
+                                        (float4*)b.sv0.p, (float4*)b.se1.p, (float4*)b.se2.p, ctx->stream));
+    if (b.n_sub) ctx->stats.kernel_launches += 1;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));     // host vectors of `acc` die here
+    return BVHT_OK;
+}
+
+int upload_vertices(bvht_ctx* ctx, Blas& b, const float* tris) {
+    int rc;
+    size_t bytes = (size_t)b.n_tris * 36;
+    if ((rc = ensure(ctx, b.tris_aos, bytes))) return rc;
+    if ((rc = ensure(ctx, b.v0, (size_t)b.n_tris * 16))) return rc;
+    if ((rc = ensure(ctx, b.e1, (size_t)b.n_tris * 16))) return rc;
+    if ((rc = ensure(ctx, b.e2, (size_t)b.n_tris * 16))) return rc;
+    b.h_tris.assign(tris, tris + (size_t)b.n_tris * 9);
+    if ((rc = h2d(ctx, b.tris_aos.p, b.h_tris.data(), bytes))) return rc;
+    CU(ctx, launch_repack_triangles((const float*)b.tris_aos.p, b.n_tris, (float4*)b.v0.p, (float4*)b.e1.p, (float4*)b.e2.p,
+                                    ctx->stream));
+    if (b.n_tris) ctx->stats.kernel_launches += 1;
+    return BVHT_OK;
+}
+
+int refresh_blas_desc(bvht_ctx* ctx) {
+    if (!ctx->blas_desc_dirty) return BVHT_OK;
+    std::vector<BlasDesc> d(std::max<size_t>(ctx->blas.size(), 1));
+    memset(d.data(), 0, d.size() * sizeof(BlasDesc));
+    for (size_t i = 0; i < ctx->blas.size(); ++i) {
+        const Blas& b = ctx->blas[i];
+        if (!b.alive) continue;
+        BlasDesc& o = d[i];
+        o.nodes = (const float4*)b.nodes.p;
+        o.v0 = (const float4*)b.v0.p; o.e1 = (const float4*)b.e1.p; o.e2 = (const float4*)b.e2.p;
+        o.sub_nodes = (const float4*)b.sub_nodes.p;
+        o.sv0 = (const float4*)b.sv0.p; o.se1 = (const float4*)b.se1.p; o.se2 = (const float4*)b.se2.p;
+        o.leaf_sub_root = (const uint32_t*)b.leaf_sub_root.p;
+        o.n_tris = b.n_tris; o.nodes_used = b.nodes_used;
+        o.accel_d_max = b.d_max; o.accel_o_max = b.o_max;
+    }
+    int rc = ensure(ctx, ctx->blas_desc, d.size() * sizeof(BlasDesc));
+    if (rc) return rc;
+    if ((rc = h2d(ctx, ctx->blas_desc.p, d.data(), d.size() * sizeof(BlasDesc)))) return rc;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->blas_desc_dirty = false;
+    return BVHT_OK;
+}
+
+bool accel_on(const bvht_ctx* ctx) { return (ctx->flags & BVHT_FLAG_LEAF_ACCEL) != 0; }
+bool fast_on(const bvht_ctx* ctx) { return (ctx->flags & BVHT_FLAG_FAST) != 0; }
+
+int fill_scene(bvht_ctx* ctx, SceneDev& s) {
+    if (ctx->tlas_nodes_used == 0 || !ctx->tlas.p)
+        return fail(ctx, BVHT_ERR_NOT_READY, "bvht_tlas_set has not been called");
+    int rc = refresh_blas_desc(ctx);
+    if (rc) return rc;
+    s.tlas = (const float4*)ctx->tlas.p;
+    s.inst_cols = (const float4*)ctx->inst_cols.p;
+    s.inst_blas = (const uint32_t*)ctx->inst_blas.p;
+    s.blas = (const BlasDesc*)ctx->blas_desc.p;
+    s.n_inst = ctx->n_inst;
+    s.flags = ctx->flags;
+    return BVHT_OK;
+}
+
+int persistent_grid(bvht_ctx* ctx, bool primary, uint64_t n_items) {
+    bool accel = accel_on(ctx);
+    int per_sm;
+    if (fast_on(ctx)) per_sm = primary ? blocks_per_sm_primary_fast(accel, kTraceBlock) : blocks_per_sm_rays_fast(accel, kTraceBlock);
+    else              per_sm = primary ? blocks_per_sm_primary_strict(accel, kTraceBlock) : blocks_per_sm_rays_strict(accel, kTraceBlock);
+    if (per_sm < 1) per_sm = 1;
+    uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)per_sm;          // a whole number of resident waves
+    uint64_t warps_needed = n_items;
+    uint64_t ctas_needed = (warps_needed + (kTraceBlock / 32) - 1) / (kTraceBlock / 32);
+    if (ctas_needed < grid) grid = std::max<uint64_t>(ctas_needed, 1);
+    return (int)grid;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------------
+#pragma GCC visibility push(default)
+extern "C" {
+
+int bvht_abi_version(void) { return BVHT_ABI_VERSION; }
+
+int bvht_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* bvht_status_string(int status) {
+    switch (status) {
+        case BVHT_OK: return "ok";
+        case BVHT_ERR_INVALID_ARG: return "invalid argument";
+        case BVHT_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+        case BVHT_ERR_CUDA: return "CUDA error";
+        case BVHT_ERR_OUT_OF_MEMORY: return "out of device memory";
+        case BVHT_ERR_BAD_HANDLE: return "bad handle";
+        case BVHT_ERR_MALFORMED_BVH: return "malformed BVH/TLAS";
+        case BVHT_ERR_NOT_READY: return "not ready";
+        default: return "unknown status";
+    }
+}
+
+int bvht_create(int device, uint32_t flags, bvht_ctx** out) {
+    if (!out) return BVHT_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); return BVHT_ERR_NO_DEVICE; }
+    if (device < 0 || device >= n) return BVHT_ERR_INVALID_ARG;
+    bvht_ctx* ctx = new (std::nothrow) bvht_ctx();
+    if (!ctx) return BVHT_ERR_OUT_OF_MEMORY;
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    ctx->device = device;
+    ctx->flags = flags;
+    bool ok = cudaSetDevice(device) == cudaSuccess
+           && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess
+           && cudaEventCreate(&ctx->ev_a) == cudaSuccess && cudaEventCreate(&ctx->ev_b) == cudaSuccess
+           && cudaEventCreate(&ctx->ev_c) == cudaSuccess && cudaEventCreate(&ctx->ev_d) == cudaSuccess
+           && cudaEventCreate(&ctx->ev_e) == cudaSuccess && cudaEventCreate(&ctx->ev_f) == cudaSuccess
+           && cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
+    if (ok) {
+        ctx->stream = ctx->own_stream;
+        ok = ensure(ctx, ctx->work_counter, 256) == BVHT_OK && ensure_pinned(ctx, 1 << 16) == BVHT_OK;
+    }
+    if (!ok) { cudaGetLastError(); bvht_destroy(ctx); return BVHT_ERR_CUDA; }
+    ctx->stats.sm_count = (uint32_t)ctx->sm_count;
+    ctx->stats.flags = flags;
+    ctx->stats.trace_block = kTraceBlock;
+    *out = ctx;
+    return BVHT_OK;
+}
+
+void bvht_destroy(bvht_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (Blas& b : ctx->blas) free_blas(b);
+    for (DevBuf* d : { &ctx->blas_desc, &ctx->tlas, &ctx->inst_cols, &ctx->inst_blas, &ctx->work_counter, &ctx->out_buf, &ctx->rays_buf })
+        release(*d);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (cudaEvent_t ev : { ctx->ev_a, ctx->ev_b, ctx->ev_c, ctx->ev_d, ctx->ev_e, ctx->ev_f }) if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* bvht_last_error(const bvht_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int bvht_set_stream(bvht_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    cudaSetDevice(ctx->device);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return BVHT_OK;
+}
+
+int bvht_sync(bvht_ctx* ctx) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    cudaSetDevice(ctx->device);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return BVHT_OK;
+}
+
+int bvht_blas_create(bvht_ctx* ctx, const float* tris, uint32_t n_tris, const bvht_bvh_node* nodes, uint32_t nodes_used,
+                     uint32_t* out_blas_id) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (!nodes || !out_blas_id || (n_tris > 0 && !tris)) return fail(ctx, BVHT_ERR_INVALID_ARG, "null pointer argument");
+    if (n_tris == 0) return fail(ctx, BVHT_ERR_INVALID_ARG, "empty model (the reference indexes nodes[0] of an empty pool and panics)");
+    if (n_tris > 0x000FFFFFu + 1u)
+        return fail(ctx, BVHT_ERR_INVALID_ARG, "n_tris = %u exceeds the 20-bit primitive index of InstancePrimitiveIndex", n_tris);
+    cudaSetDevice(ctx->device);
+    std::vector<uint32_t> parent;
+    uint32_t depth = 0;
+    int rc = validate_bvh(ctx, nodes, nodes_used, n_tris, parent, depth);
+    if (rc) return rc;
+
+    cudaEventRecord(ctx->ev_e, ctx->stream);
+    Blas b;
+    b.alive = true; b.n_tris = n_tris; b.nodes_used = nodes_used;
+    b.h_nodes.assign(nodes, nodes + nodes_used);
+
+    // node pool: 2 float4 per node = {min.xyz, left_first}, {max.xyz, prim_count}
+    std::vector<float> flat((size_t)nodes_used * 8);
+    for (uint32_t i = 0; i < nodes_used; ++i) {
+        float* f = &flat[(size_t)i * 8];
+        memcpy(f + 0, nodes[i].aabb_min, 12); memcpy(f + 3, &nodes[i].left_first, 4);
+        memcpy(f + 4, nodes[i].aabb_max, 12); memcpy(f + 7, &nodes[i].prim_count, 4);
+    }
+    auto bail = [&](int code) { free_blas(b); return code; };
+    if ((rc = ensure(ctx, b.nodes, flat.size() * 4))) return bail(rc);
+    if ((rc = h2d(ctx, b.nodes.p, flat.data(), flat.size() * 4))) return bail(rc);
+    if ((rc = upload_vertices(ctx, b, tris))) return bail(rc);
+
+    // refit plan: leaves cut into chunks, parent links, arrival counters
+    std::vector<uint32_t> chunk_leaf, chunk_first, chunk_count, leaf_chunks(nodes_used, 0);
+    for (uint32_t i = 0; i < nodes_used; ++i) {
+        if (i == 1 || nodes[i].prim_count == 0) continue;
+        if (i != 0 && parent[i] == kNone) continue;                  // unreachable node
+        uint32_t first = nodes[i].left_first, left = nodes[i].prim_count;
+        while (left > 0) {
+            uint32_t c = std::min(left, kRefitChunkTris);
+            chunk_leaf.push_back(i); chunk_first.push_back(first); chunk_count.push_back(c);
+            leaf_chunks[i]++; first += c; left -= c;
+        }
+    }
+    b.n_chunks = (uint32_t)chunk_leaf.size();
+    if ((rc = upload_u32(ctx, b.chunk_leaf, chunk_leaf))) return bail(rc);
+    if ((rc = upload_u32(ctx, b.chunk_first, chunk_first))) return bail(rc);
+    if ((rc = upload_u32(ctx, b.chunk_count, chunk_count))) return bail(rc);
+    if ((rc = upload_u32(ctx, b.leaf_chunks, leaf_chunks))) return bail(rc);
+    if ((rc = upload_u32(ctx, b.parent, parent))) return bail(rc);
+    if ((rc = ensure(ctx, b.scratch, (size_t)nodes_used * 24))) return bail(rc);
+    if ((rc = ensure(ctx, b.counters, (size_t)nodes_used * 4))) return bail(rc);
+
+    if (accel_on(ctx)) { if ((rc = build_and_upload_accel(ctx, b))) return bail(rc); }
+
+    cudaEventRecord(ctx->ev_f, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { fail(ctx, BVHT_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e)); return bail(BVHT_ERR_CUDA); }
+    cudaEventElapsedTime(&ctx->stats.last_upload_ms, ctx->ev_e, ctx->ev_f);
+
+    uint32_t id = kNone;
+    for (uint32_t i = 0; i < ctx->blas.size(); ++i) if (!ctx->blas[i].alive) { id = i; break; }
+    if (id == kNone) { id = (uint32_t)ctx->blas.size(); ctx->blas.emplace_back(); }
+    ctx->blas[id] = std::move(b);
+    ctx->blas_desc_dirty = true;
+    *out_blas_id = id;
+    return BVHT_OK;
+}
+
+int bvht_blas_destroy(bvht_ctx* ctx, uint32_t blas_id) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (blas_id >= ctx->blas.size() || !ctx->blas[blas_id].alive) return fail(ctx, BVHT_ERR_BAD_HANDLE, "unknown blas id %u", blas_id);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_blas(ctx->blas[blas_id]);
+    ctx->blas_desc_dirty = true;
+    return BVHT_OK;
+}
+
+int bvht_blas_update_vertices(bvht_ctx* ctx, uint32_t blas_id, const float* tris, uint32_t n_tris) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (blas_id >= ctx->blas.size() || !ctx->blas[blas_id].alive) return fail(ctx, BVHT_ERR_BAD_HANDLE, "unknown blas id %u", blas_id);
+    Blas& b = ctx->blas[blas_id];
+    if (!tris && n_tris) return fail(ctx, BVHT_ERR_INVALID_ARG, "null vertex pointer");
+    if (n_tris != b.n_tris) return fail(ctx, BVHT_ERR_INVALID_ARG, "vertex update with %u triangles, model has %u", n_tris, b.n_tris);
+    cudaSetDevice(ctx->device);
+    cudaEventRecord(ctx->ev_e, ctx->stream);
+    int rc = upload_vertices(ctx, b, tris);
+    if (rc) return rc;
+    if (accel_on(ctx)) {
+        if ((rc = build_and_upload_accel(ctx, b))) return rc;
+        ctx->blas_desc_dirty = true;
+    }
+    cudaEventRecord(ctx->ev_f, ctx->stream);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->stats.last_upload_ms, ctx->ev_e, ctx->ev_f);
+    return BVHT_OK;
+}
+
+int bvht_blas_refit(bvht_ctx* ctx, uint32_t blas_id) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (blas_id >= ctx->blas.size() || !ctx->blas[blas_id].alive) return fail(ctx, BVHT_ERR_BAD_HANDLE, "unknown blas id %u", blas_id);
+    Blas& b = ctx->blas[blas_id];
+    cudaSetDevice(ctx->device);
+    RefitPlan p;
+    p.nodes = (float4*)b.nodes.p;
+    p.tris_aos = (const float*)b.tris_aos.p;
+    p.chunk_leaf = (const uint32_t*)b.chunk_leaf.p;
+    p.chunk_first = (const uint32_t*)b.chunk_first.p;
+    p.chunk_count = (const uint32_t*)b.chunk_count.p;
+    p.leaf_chunks = (const uint32_t*)b.leaf_chunks.p;
+    p.parent = (const uint32_t*)b.parent.p;
+    p.scratch = (float*)b.scratch.p;
+    p.counters = (unsigned int*)b.counters.p;
+    p.n_chunks = b.n_chunks;
+    p.nodes_used = b.nodes_used;
+    cudaEventRecord(ctx->ev_c, ctx->stream);
+    CU(ctx, launch_refit(p, ctx->stream));
+    cudaEventRecord(ctx->ev_d, ctx->stream);
+    ctx->refit_timed = true;
+    ctx->stats.kernel_launches += (b.n_chunks ? 2 : 1);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return BVHT_OK;
+}
+
+int bvht_blas_read_nodes(bvht_ctx* ctx, uint32_t blas_id, bvht_bvh_node* out, uint32_t max_nodes) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (blas_id >= ctx->blas.size() || !ctx->blas[blas_id].alive) return fail(ctx, BVHT_ERR_BAD_HANDLE, "unknown blas id %u", blas_id);
+    if (!out) return fail(ctx, BVHT_ERR_INVALID_ARG, "null output pointer");
+    Blas& b = ctx->blas[blas_id];
+    cudaSetDevice(ctx->device);
+    uint32_t n = std::min(max_nodes, b.nodes_used);
+    std::vector<float> flat((size_t)n * 8);
+    CU(ctx, cudaMemcpyAsync(flat.data(), b.nodes.p, flat.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += flat.size() * 4;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* f = &flat[(size_t)i * 8];
+        memcpy(out[i].aabb_min, f + 0, 12); memcpy(&out[i].left_first, f + 3, 4);
+        memcpy(out[i].aabb_max, f + 4, 12); memcpy(&out[i].prim_count, f + 7, 4);
+    }
+    return BVHT_OK;
+}
+
+int bvht_tlas_set(bvht_ctx* ctx, const bvht_tlas_node* nodes, uint32_t nodes_used, const bvht_instance* instances,
+                  uint32_t n_instances) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (!nodes || nodes_used == 0 || (n_instances && !instances)) return fail(ctx, BVHT_ERR_INVALID_ARG, "null/empty TLAS");
+    if (n_instances > 0xFFFu + 1u) return fail(ctx, BVHT_ERR_INVALID_ARG, "more than 4096 instances (12-bit instance index)");
+    cudaSetDevice(ctx->device);
+    // validate: indices in range, bounded depth, no cycles (node 0 is a COPY of the last merged node, tlas.rs:248)
+    {
+        std::vector<std::pair<uint32_t, uint32_t>> stack;
+        stack.push_back({ 0u, 1u });
+        uint64_t visited = 0;
+        while (!stack.empty()) {
+            auto [ni, depth] = stack.back(); stack.pop_back();
+            if (++visited > 4ull * nodes_used + 4)
+                return fail(ctx, BVHT_ERR_MALFORMED_BVH, "TLAS walk does not terminate (cycle)");
+            if (depth > (uint32_t)kTlasStack)
+                return fail(ctx, BVHT_ERR_MALFORMED_BVH, "TLAS depth exceeds the traversal stack bound %d", kTlasStack);
+            const bvht_tlas_node& n = nodes[ni];
+            if (n.left_right == 0) {
+                if (n_instances == 0) continue;                       // empty scene: the root leaf is never resolved
+                if (n.blas >= n_instances)
+                    return fail(ctx, BVHT_ERR_MALFORMED_BVH, "TLAS leaf %u refers to instance %u of %u", ni, n.blas, n_instances);
+            } else {
+                uint32_t a = n.left_right >> 16, c = n.left_right & 0xFFFFu;
+                if (a >= nodes_used || c >= nodes_used)
+                    return fail(ctx, BVHT_ERR_MALFORMED_BVH, "TLAS node %u has children %u,%u outside [0, %u)", ni, a, c, nodes_used);
+                stack.push_back({ a, depth + 1 }); stack.push_back({ c, depth + 1 });
+            }
+        }
+    }
+    for (uint32_t i = 0; i < n_instances; ++i) {
+        uint32_t id = instances[i].blas_id;
+        if (id >= ctx->blas.size() || !ctx->blas[id].alive)
+            return fail(ctx, BVHT_ERR_BAD_HANDLE, "instance %u refers to unknown blas id %u", i, id);
+    }
+    size_t tl_bytes = (size_t)nodes_used * 32, ic_bytes = (size_t)std::max(n_instances, 1u) * 64, ib_bytes = (size_t)std::max(n_instances, 1u) * 4;
+    int rc;
+    if ((rc = ensure(ctx, ctx->tlas, tl_bytes))) return rc;
+    if ((rc = ensure(ctx, ctx->inst_cols, ic_bytes))) return rc;
+    if ((rc = ensure(ctx, ctx->inst_blas, ib_bytes))) return rc;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));       // previous frame may still read the staging buffer
+    if ((rc = ensure_pinned(ctx, tl_bytes + ic_bytes + ib_bytes + 1024))) return rc;
+    // flatten into the device layouts inside the pinned buffer
+    char* st = (char*)ctx->pinned;
+    float* tl = (float*)st;
+    for (uint32_t i = 0; i < nodes_used; ++i) {
+        float* f = tl + (size_t)i * 8;
+        memcpy(f + 0, nodes[i].aabb_min, 12); memcpy(f + 3, &nodes[i].left_right, 4);
+        memcpy(f + 4, nodes[i].aabb_max, 12); memcpy(f + 7, &nodes[i].blas, 4);
+    }
+    size_t off = (tl_bytes + 255) & ~size_t(255);
+    float* ic = (float*)(st + off);
+    for (uint32_t i = 0; i < n_instances; ++i) memcpy(ic + (size_t)i * 16, instances[i].transform_inv, 64);
+    size_t off2 = off + ((ic_bytes + 255) & ~size_t(255));
+    uint32_t* ib = (uint32_t*)(st + off2);
+    for (uint32_t i = 0; i < n_instances; ++i) ib[i] = instances[i].blas_id;
+    if ((rc = h2d(ctx, ctx->tlas.p, tl, tl_bytes))) return rc;
+    if (n_instances) {
+        if ((rc = h2d(ctx, ctx->inst_cols.p, ic, (size_t)n_instances * 64))) return rc;
+        if ((rc = h2d(ctx, ctx->inst_blas.p, ib, (size_t)n_instances * 4))) return rc;
+    }
+    ctx->tlas_nodes_used = nodes_used;
+    ctx->n_inst = n_instances;
+    return BVHT_OK;
+}
+
+int bvht_trace_primary_device(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height, uint32_t tile,
+                              bvht_rect region, void* out_device) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (!camera || !out_device) return fail(ctx, BVHT_ERR_INVALID_ARG, "null pointer argument");
+    if (tile == 0) tile = 8;
+    if (width == 0 || height == 0 || width > (1u << 24) || height > (1u << 24))
+        return fail(ctx, BVHT_ERR_INVALID_ARG, "image size %ux%u outside (0, 2^24]", width, height);
+    if (tile > 1024) return fail(ctx, BVHT_ERR_INVALID_ARG, "tile %u too large", tile);
+    region.x1 = std::min(region.x1, width); region.y1 = std::min(region.y1, height);
+    cudaSetDevice(ctx->device);
+    PrimaryParams p;
+    memset(&p, 0, sizeof p);
+    int rc = fill_scene(ctx, p.scene);
+    if (rc) return rc;
+    ctx->stats.last_trace_rays = 0;
+    if (region.x0 >= region.x1 || region.y0 >= region.y1) return BVHT_OK;     // empty region: nothing to do
+    memcpy(p.cam.tl, camera->top_left_eye, 12);
+    memcpy(p.cam.tr, camera->top_right_eye, 12);
+    memcpy(p.cam.bl, camera->bottom_left_eye, 12);
+    memcpy(p.cam.vinv, camera->view_matrix_inv, 64);
+    p.width = width; p.height = height; p.tile = tile;
+    p.x0 = region.x0; p.y0 = region.y0; p.x1 = region.x1; p.y1 = region.y1;
+    p.tx0 = region.x0 / tile; p.ty0 = region.y0 / tile;
+    p.ntx = (region.x1 + tile - 1) / tile - p.tx0;
+    p.nty = (region.y1 + tile - 1) / tile - p.ty0;
+    p.items_per_tile = (tile * tile + 31u) / 32u;
+    uint64_t n_items = (uint64_t)p.ntx * p.nty * p.items_per_tile;
+    if (n_items >= 0xFFFFFFFFull - (1ull << 20)) return fail(ctx, BVHT_ERR_INVALID_ARG, "too many work items");
+    p.n_items = (uint32_t)n_items;
+    p.out = (uint4*)out_device;
+    p.work_counter = (unsigned int*)ctx->work_counter.p;
+    int grid = persistent_grid(ctx, true, n_items);
+    CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, 4, ctx->stream));
+    cudaEventRecord(ctx->ev_a, ctx->stream);
+    cudaError_t e = fast_on(ctx) ? launch_primary_fast(p, accel_on(ctx), grid, kTraceBlock, ctx->stream)
+                                 : launch_primary_strict(p, accel_on(ctx), grid, kTraceBlock, ctx->stream);
+    cudaEventRecord(ctx->ev_b, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, BVHT_ERR_CUDA, "trace_primary launch failed: %s", cudaGetErrorString(e));
+    ctx->trace_timed = true;
+    ctx->stats.kernel_launches += 1;
+    ctx->stats.trace_grid = (uint32_t)grid;
+    ctx->stats.last_trace_rays = (uint64_t)(region.x1 - region.x0) * (region.y1 - region.y0);
+    return BVHT_OK;
+}
+
+int bvht_trace_primary(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height, uint32_t tile,
+                       bvht_rect region, bvht_hit* out_host) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (!out_host) return fail(ctx, BVHT_ERR_INVALID_ARG, "null output pointer");
+    cudaSetDevice(ctx->device);
+    size_t bytes = (size_t)width * height * sizeof(bvht_hit);
+    int rc = ensure(ctx, ctx->out_buf, bytes);
+    if (rc) return rc;
+    rc = bvht_trace_primary_device(ctx, camera, width, height, tile, region, ctx->out_buf.p);
+    if (rc) return rc;
+    region.x1 = std::min(region.x1, width); region.y1 = std::min(region.y1, height);
+    if (region.x0 < region.x1 && region.y0 < region.y1) {
+        // only the region's rows travel back (full rows when the region spans the width, else a 2-D copy)
+        size_t row = (size_t)width * sizeof(bvht_hit);
+        if (region.x0 == 0 && region.x1 == width) {
+            size_t off = (size_t)region.y0 * row, len = (size_t)(region.y1 - region.y0) * row;
+            CU(ctx, cudaMemcpyAsync((char*)out_host + off, (char*)ctx->out_buf.p + off, len, cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->stats.d2h_bytes += len;
+        } else {
+            size_t off = (size_t)region.y0 * row + (size_t)region.x0 * sizeof(bvht_hit);
+            size_t wbytes = (size_t)(region.x1 - region.x0) * sizeof(bvht_hit);
+            CU(ctx, cudaMemcpy2DAsync((char*)out_host + off, row, (char*)ctx->out_buf.p + off, row, wbytes,
+                                      region.y1 - region.y0, cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->stats.d2h_bytes += wbytes * (region.y1 - region.y0);
+        }
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return BVHT_OK;
+}
+
+int bvht_trace_rays_device(bvht_ctx* ctx, const void* rays_device, uint64_t n, void* out_device) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (n == 0) { ctx->stats.last_trace_rays = 0; return BVHT_OK; }
+    if (!rays_device || !out_device) return fail(ctx, BVHT_ERR_INVALID_ARG, "null pointer argument");
+    if (n > 0xFFFFFFFFull * 16) return fail(ctx, BVHT_ERR_INVALID_ARG, "too many rays");
+    cudaSetDevice(ctx->device);
+    RaysParams p;
+    memset(&p, 0, sizeof p);
+    int rc = fill_scene(ctx, p.scene);
+    if (rc) return rc;
+    p.rays = (const float*)rays_device; p.n = n; p.out = (uint4*)out_device;
+    p.work_counter = (unsigned int*)ctx->work_counter.p;
+    int grid = persistent_grid(ctx, false, (n + 31) / 32);
+    CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, 4, ctx->stream));
+    cudaEventRecord(ctx->ev_a, ctx->stream);
+    cudaError_t e = fast_on(ctx) ? launch_rays_fast(p, accel_on(ctx), grid, kTraceBlock, ctx->stream)
+                                 : launch_rays_strict(p, accel_on(ctx), grid, kTraceBlock, ctx->stream);
+    cudaEventRecord(ctx->ev_b, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, BVHT_ERR_CUDA, "trace_rays launch failed: %s", cudaGetErrorString(e));
+    ctx->trace_timed = true;
+    ctx->stats.kernel_launches += 1;
+    ctx->stats.trace_grid = (uint32_t)grid;
+    ctx->stats.last_trace_rays = n;
+    return BVHT_OK;
+}
+
+int bvht_trace_rays(bvht_ctx* ctx, const bvht_ray* rays, uint64_t n, bvht_hit* out_host) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (n == 0) { ctx->stats.last_trace_rays = 0; return BVHT_OK; }
+    if (!rays || !out_host) return fail(ctx, BVHT_ERR_INVALID_ARG, "null pointer argument");
+    cudaSetDevice(ctx->device);
+    int rc;
+    if ((rc = ensure(ctx, ctx->rays_buf, n * sizeof(bvht_ray)))) return rc;
+    if ((rc = ensure(ctx, ctx->out_buf, n * sizeof(bvht_hit)))) return rc;
+    if ((rc = h2d(ctx, ctx->rays_buf.p, rays, n * sizeof(bvht_ray)))) return rc;
+    if ((rc = bvht_trace_rays_device(ctx, ctx->rays_buf.p, n, ctx->out_buf.p))) return rc;
+    CU(ctx, cudaMemcpyAsync(out_host, ctx->out_buf.p, n * sizeof(bvht_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.d2h_bytes += n * sizeof(bvht_hit);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return BVHT_OK;
+}
+
+int bvht_device_alloc(bvht_ctx* ctx, size_t bytes, void** out_device) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (!out_device) return fail(ctx, BVHT_ERR_INVALID_ARG, "null pointer argument");
+    cudaSetDevice(ctx->device);
+    CU(ctx, cudaMalloc(out_device, bytes ? bytes : 16));
+    return BVHT_OK;
+}
+
+int bvht_device_free(bvht_ctx* ctx, void* device_ptr) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    CU(ctx, cudaFree(device_ptr));
+    return BVHT_OK;
+}
+
+int bvht_memcpy_h2d(bvht_ctx* ctx, void* dst_device, const void* src_host, size_t bytes) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    cudaSetDevice(ctx->device);
+    int rc = h2d(ctx, dst_device, src_host, bytes);
+    if (rc) return rc;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return BVHT_OK;
+}
+
+int bvht_memcpy_d2h(bvht_ctx* ctx, void* dst_host, const void* src_device, size_t bytes) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    cudaSetDevice(ctx->device);
+    CU(ctx, cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += bytes;
+    return BVHT_OK;
+}
+
+int bvht_ipc_export(bvht_ctx* ctx, void* device_ptr, uint8_t handle_out[64]) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaSetDevice(ctx->device);
+    cudaIpcMemHandle_t h;
+    CU(ctx, cudaIpcGetMemHandle(&h, device_ptr));
+    memcpy(handle_out, &h, 64);
+    return BVHT_OK;
+}
+
+int bvht_ipc_open(bvht_ctx* ctx, const uint8_t handle[64], void** out_device) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    cudaSetDevice(ctx->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(ctx, cudaIpcOpenMemHandle(out_device, h, cudaIpcMemLazyEnablePeerAccess));
+    return BVHT_OK;
+}
+
+int bvht_ipc_close(bvht_ctx* ctx, void* device_ptr) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    CU(ctx, cudaIpcCloseMemHandle(device_ptr));
+    return BVHT_OK;
+}
+
+int bvht_get_stats(const bvht_ctx* cctx, bvht_stats* out) {
+    if (!cctx || !out) return BVHT_ERR_BAD_HANDLE;
+    bvht_ctx* ctx = const_cast<bvht_ctx*>(cctx);
+    cudaSetDevice(ctx->device);
+    if (ctx->trace_timed) {
+        if (cudaEventSynchronize(ctx->ev_b) == cudaSuccess) cudaEventElapsedTime(&ctx->stats.last_trace_ms, ctx->ev_a, ctx->ev_b);
+    }
+    if (ctx->refit_timed) {
+        if (cudaEventSynchronize(ctx->ev_d) == cudaSuccess) cudaEventElapsedTime(&ctx->stats.last_refit_ms, ctx->ev_c, ctx->ev_d);
+    }
+    cudaGetLastError();
+    *out = ctx->stats;
+    return BVHT_OK;
+}
+
+} // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,71 @@
+// device_types.cuh -- HBM-resident layouts shared by the upload, refit and trace kernels.
+//
+// Everything here is the UPLOADED form of the reference's in-memory objects (DESIGN.md "Data layout"):
+//   BvhNode  (bvh.rs:88-134, 32 B)  -> 2 x float4 : {min.xyz, left_first}, {max.xyz, prim_count}
+//   Triangle (triangle.rs:9-16, 36 B AoS) -> three float4 streams v0 | e1 = v1 - v0 | e2 = v2 - v0
+//            (one IEEE subtraction each, exactly what Triangle::intersect computes first, triangle.rs:43-44)
+//   TlasNode (tlas.rs:41-46, 32 B)  -> 2 x float4 : {min.xyz, left_right}, {max.xyz, blas}
+//   SceneObject inverse transform (scene_object.rs:78-89) -> 4 x float4 columns
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bvht {
+
+constexpr int kTlasStack = 32;   // validated at bvht_tlas_set (depth of the uploaded tree)
+constexpr int kBlasStack = 32;   // validated at bvht_blas_create
+constexpr int kSubStack  = 48;   // leaf sub-BVH (built by us, depth bounded at build)
+
+// One per uploaded model.  Pointers are device addresses.
+struct BlasDesc {
+    const float4* nodes;      // 2 float4 per reference node
+    const float4* v0;         // triangle streams in REFERENCE primitive order (brute-force leaves, refit source)
+    const float4* e1;
+    const float4* e2;
+    // leaf accelerator (BVHT_FLAG_LEAF_ACCEL), see leaf_accel.hpp
+    const float4* sub_nodes;  // 4 float4 per sub node (two child boxes + two child refs)
+    const float4* sv0;        // triangle streams in sub-BVH order; v0.w carries the reference primitive index
+    const float4* se1;
+    const float4* se2;
+    const uint32_t* leaf_sub_root;  // per reference node: sub-BVH root ref for leaves (0xFFFFFFFF = brute force)
+    uint32_t n_tris;
+    uint32_t nodes_used;
+    float    accel_d_max;     // model-space limits |d| <= d_max, |o| <= o_max under which the pre-inflated
+    float    accel_o_max;     //   sub boxes are conservative (leaf_accel.hpp); other rays use brute-force leaves
+};
+
+struct SceneDev {
+    const float4*   tlas;        // 2 float4 per TLAS node
+    const float4*   inst_cols;   // 4 float4 per instance: columns of the inverse transform
+    const uint32_t* inst_blas;   // blas id per instance
+    const BlasDesc* blas;
+    uint32_t        n_inst;
+    uint32_t        flags;
+};
+
+struct CameraDev {
+    float tl[3], tr[3], bl[3];
+    float vinv[16];              // column-major
+};
+
+struct PrimaryParams {
+    SceneDev  scene;
+    CameraDev cam;
+    uint32_t  width, height, tile;
+    uint32_t  x0, y0, x1, y1;            // pixel region
+    uint32_t  tx0, ty0, ntx, nty;        // tile range covering the region
+    uint32_t  items_per_tile;            // ceil(tile*tile / 32)
+    uint32_t  n_items;                   // ntx * nty * items_per_tile
+    uint4*    out;                       // width*height hit records (16 B each)
+    unsigned int* work_counter;          // persistent-thread work cursor
+};
+
+struct RaysParams {
+    SceneDev     scene;
+    const float* rays;                   // n x 7 floats (o, d, t)
+    uint64_t     n;
+    uint4*       out;
+    unsigned int* work_counter;
+};
+
+} // namespace bvht

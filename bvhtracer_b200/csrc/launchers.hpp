@@ -1,0 +1,38 @@
+// launchers.hpp -- host-callable entry points of the separately compiled kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include "device_types.cuh"
+
+namespace bvht {
+
+#define BVHT_DECLARE_MODE(sfx)                                                                                   \
+    cudaError_t launch_primary_##sfx(const PrimaryParams& p, bool accel, int grid, int block, cudaStream_t s);   \
+    cudaError_t launch_rays_##sfx(const RaysParams& p, bool accel, int grid, int block, cudaStream_t s);         \
+    int blocks_per_sm_primary_##sfx(bool accel, int block);                                                      \
+    int blocks_per_sm_rays_##sfx(bool accel, int block);
+BVHT_DECLARE_MODE(strict)
+BVHT_DECLARE_MODE(fast)
+#undef BVHT_DECLARE_MODE
+
+// upload_kernels.cu
+cudaError_t launch_repack_triangles(const float* tris_aos, uint32_t n_tris, float4* v0, float4* e1, float4* e2, cudaStream_t s);
+cudaError_t launch_repack_sub_triangles(const float* tris_aos, const uint32_t* sub_order, uint32_t n,
+                                        float4* sv0, float4* se1, float4* se2, cudaStream_t s);
+
+// refit_kernels.cu
+struct RefitPlan {
+    float4*         nodes;          // device node pool (2 float4 per node)
+    const float*    tris_aos;       // n_tris x 9 floats (reference layout)
+    const uint32_t* chunk_leaf;     // per chunk: leaf node index
+    const uint32_t* chunk_first;    // per chunk: first triangle
+    const uint32_t* chunk_count;    // per chunk: triangle count
+    const uint32_t* leaf_chunks;    // per node: number of chunks (leaves only)
+    const uint32_t* parent;         // per node: parent index (root: 0xFFFFFFFF)
+    float*          scratch;        // per node: 6 floats of running min/max
+    unsigned int*   counters;       // per node: chunk / child arrival counters
+    uint32_t        n_chunks;
+    uint32_t        nodes_used;
+};
+cudaError_t launch_refit(const RefitPlan& plan, cudaStream_t s);
+
+} // namespace bvht

@@ -1,0 +1,395 @@
+// trace_kernels.cuh -- the closest-hit kernels (K1 primary rays, K1b arbitrary rays).
+//
+// This file is compiled TWICE (trace_strict.cu / trace_fast.cu) with different floating-point flags:
+//   strict: --fmad=false -prec-div=true -prec-sqrt=true -ftz=false   (rustc's arithmetic model: no contraction)
+//   fast  : --fmad=true  (FMA contraction; results within the fast-mode tolerance of BASELINE.json)
+// BVHT_MODE_NS names the namespace of the instantiation.
+//
+// What it replaces in the reference (bvhtracer/src/...):
+//   renderer.rs:345-368   PathTracer::evaluate, first loop (tiles of 8x8 pixels, one primary ray per pixel)
+//   camera.rs:994-1010    Camera::get_ray_eye / get_ray_world
+//   query/ray.rs:23-35    Ray::new / from_origin_dir (three IEEE divides)
+//   scene/tlas.rs:123-177 Tlas::intersect (ordered near-first walk, root box never tested, swapped accessors)
+//   scene/scene_object.rs:78-89  SceneObject::intersect (world -> model ray, t shared)
+//   model/bvh.rs:242-305  Bvh::intersect_subtree (leaf triangles against the ENTRY ray, boxes against the
+//                         shrinking ray, ties / double-miss descend RIGHT first)
+//   geometry/aabb.rs:65-84       Aabb::intersect (slab)
+//   geometry/triangle.rs:41-72   Triangle::intersect (Moeller-Trumbore, thresholds 1e-4, no culling)
+//
+// Design (DESIGN.md "Kernels"): persistent CTAs, one per SM slot; each WARP pulls a 32-pixel slice of an
+// 8x8 tile with one atomicAdd (lane 0) + shuffle broadcast, generates its 32 primary rays in registers,
+// walks TLAS -> instance -> BLAS with two short per-thread stacks, and writes one 16-byte record per pixel.
+#pragma once
+#include <cfloat>
+#include "device_types.cuh"
+
+#ifndef BVHT_MODE_NS
+#error "define BVHT_MODE_NS (strict|fast) before including trace_kernels.cuh"
+#endif
+
+namespace bvht {
+namespace BVHT_MODE_NS {
+
+struct RayM {            // a ray in some space with its cached reciprocal (query/ray.rs:9-17)
+    float ox, oy, oz;
+    float dx, dy, dz;
+    float rdx, rdy, rdz;
+};
+
+struct HitRec { float t, u, v; uint32_t id; };
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+// geometry/aabb.rs:65-84.  `tcl` is the ray's current t.
+__device__ __forceinline__ bool slab_test(const float4 lo, const float4 hi, const RayM& r, float tcl, float& tmin_out) {
+    float t_x1 = (lo.x - r.ox) * r.rdx;
+    float t_x2 = (hi.x - r.ox) * r.rdx;
+    float t_min = fminf(t_x1, t_x2);
+    float t_max = fmaxf(t_x1, t_x2);
+    float t_y1 = (lo.y - r.oy) * r.rdy;
+    float t_y2 = (hi.y - r.oy) * r.rdy;
+    t_min = fmaxf(t_min, fminf(t_y1, t_y2));
+    t_max = fminf(t_max, fmaxf(t_y1, t_y2));
+    float t_z1 = (lo.z - r.oz) * r.rdz;
+    float t_z2 = (hi.z - r.oz) * r.rdz;
+    t_min = fmaxf(t_min, fminf(t_z1, t_z2));
+    t_max = fminf(t_max, fmaxf(t_z1, t_z2));
+    tmin_out = t_min;
+    return (t_max >= t_min) && (t_min < tcl) && (t_max > 0.0f);
+}
+
+// Slab test for OUR sub-BVH boxes (not a reference function): inclusive on every bound so that it is never
+// stricter than needed; the boxes themselves carry the conservative inflation.
+__device__ __forceinline__ bool slab_test_sub(const float4 lo, const float4 hi, const RayM& r, float tcl, float& tmin_out) {
+    float t_x1 = (lo.x - r.ox) * r.rdx;
+    float t_x2 = (hi.x - r.ox) * r.rdx;
+    float t_min = fminf(t_x1, t_x2);
+    float t_max = fmaxf(t_x1, t_x2);
+    float t_y1 = (lo.y - r.oy) * r.rdy;
+    float t_y2 = (hi.y - r.oy) * r.rdy;
+    t_min = fmaxf(t_min, fminf(t_y1, t_y2));
+    t_max = fminf(t_max, fmaxf(t_y1, t_y2));
+    float t_z1 = (lo.z - r.oz) * r.rdz;
+    float t_z2 = (hi.z - r.oz) * r.rdz;
+    t_min = fmaxf(t_min, fminf(t_z1, t_z2));
+    t_max = fminf(t_max, fmaxf(t_z1, t_z2));
+    tmin_out = t_min;
+    return (t_max >= t_min) && (t_min <= tcl) && (t_max >= 0.0f);
+}
+
+// geometry/triangle.rs:41-72 on the repacked triangle (v0, e1 = v1 - v0, e2 = v2 - v0).
+// Returns true when the reference would return Some(SurfaceInteraction{min(entry_t, t), u, v}).
+__device__ __forceinline__ bool moller_trumbore(const float4 v0, const float4 e1, const float4 e2, const RayM& r,
+                                                float entry_t, float& t_out, float& u_out, float& v_out) {
+    const float threshold = 0.0001f;
+    float nx = r.dy * e2.z - r.dz * e2.y;
+    float ny = r.dz * e2.x - r.dx * e2.z;
+    float nz = r.dx * e2.y - r.dy * e2.x;
+    float area = (e1.x * nx + e1.y * ny) + e1.z * nz;
+    if (fabsf(area) < threshold) return false;
+    float f = 1.0f / area;
+    float sx = r.ox - v0.x, sy = r.oy - v0.y, sz = r.oz - v0.z;
+    float u = f * ((sx * nx + sy * ny) + sz * nz);
+    if (u < 0.0f || u > 1.0f) return false;
+    float qx = sy * e1.z - sz * e1.y;
+    float qy = sz * e1.x - sx * e1.z;
+    float qz = sx * e1.y - sy * e1.x;
+    float v = f * ((r.dx * qx + r.dy * qy) + r.dz * qz);
+    if (v < 0.0f || u + v > 1.0f) return false;
+    float t = f * ((e2.x * qx + e2.y * qy) + e2.z * qz);
+    if (!(t > threshold)) return false;
+    t_out = fminf(entry_t, t);
+    u_out = u;
+    v_out = v;
+    return true;
+}
+
+// Brute-force leaf: primitives base .. base+count ascending, strict '<' against the shrinking closest t
+// (bvh.rs:250-258).  Triangles are tested against the ENTRY ray.
+__device__ __forceinline__ void leaf_brute(const BlasDesc& B, uint32_t base, uint32_t count, const RayM& r, float entry_t,
+                                           float& best_t, float& best_u, float& best_v, uint32_t& best_prim, bool& found) {
+    for (uint32_t k = 0; k < count; ++k) {
+        uint32_t pi = base + k;
+        float4 v0 = ldg4(B.v0 + pi);
+        float4 e1 = ldg4(B.e1 + pi);
+        float4 e2 = ldg4(B.e2 + pi);
+        float t, u, v;
+        if (moller_trumbore(v0, e1, e2, r, entry_t, t, u, v)) {
+            if (t < best_t) { best_t = t; best_u = u; best_v = v; best_prim = pi; found = true; }
+        }
+    }
+}
+
+// Leaf accelerator: conservative sub-BVH built by us over the triangles of one oversized reference leaf
+// (leaf_accel.hpp).  The reference's result for a leaf is the lexicographic minimum (t, primitive index)
+// over the triangles that Triangle::intersect accepts with t < closest-at-entry, because the leaf loop
+// tests against the ENTRY ray (bvh.rs:251) and accepts with strict '<' in ascending index order.  Any
+// visiting order gives that same answer as long as no accepting triangle is skipped, which the
+// pre-inflated boxes guarantee under the bound checked by the caller (DESIGN.md "Leaf accelerator").
+__device__ __forceinline__ void leaf_accel(const BlasDesc& B, uint32_t sub_root, const RayM& r, float entry_t,
+                                           float& best_t, float& best_u, float& best_v, uint32_t& best_prim, bool& found) {
+    // within this leaf: lt/lu/lv/lp = lexicographic-min candidate; ties with the entry value are rejected
+    // because lp starts at 0 (no index is < 0) while lt starts at the closest-at-entry value.
+    float lt = best_t, lu = 0.0f, lv = 0.0f;
+    uint32_t lp = 0u;
+    bool lfound = false;
+    uint32_t stack[kSubStack];
+    int sp = 0;
+    uint32_t ref = sub_root;
+    for (;;) {
+        if (ref & 0x80000000u) {
+            // leaf ref: [30:28] = count-1, [27:0] = first triangle in sub order
+            uint32_t first = ref & 0x0FFFFFFFu;
+            uint32_t cnt = ((ref >> 28) & 7u) + 1u;
+            for (uint32_t k = 0; k < cnt; ++k) {
+                float4 v0 = ldg4(B.sv0 + first + k);
+                float4 e1 = ldg4(B.se1 + first + k);
+                float4 e2 = ldg4(B.se2 + first + k);
+                float t, u, v;
+                if (moller_trumbore(v0, e1, e2, r, entry_t, t, u, v)) {
+                    uint32_t pi = __float_as_uint(v0.w);
+                    if (t < lt || (t == lt && pi < lp)) { lt = t; lu = u; lv = v; lp = pi; lfound = true; }
+                }
+            }
+            if (sp == 0) break;
+            ref = stack[--sp];
+        } else {
+            const float4* n = B.sub_nodes + (size_t)ref * 4;
+            float4 a = ldg4(n + 0);   // child0 lo.xyz, child0 ref
+            float4 b = ldg4(n + 1);   // child0 hi.xyz, child1 ref
+            float4 c = ldg4(n + 2);   // child1 lo.xyz
+            float4 d = ldg4(n + 3);   // child1 hi.xyz
+            float t0, t1;
+            // inclusive comparisons: a node holding a triangle with t == lt but a lower index must be visited
+            bool h0 = slab_test_sub(a, b, r, lt, t0);
+            bool h1 = slab_test_sub(c, d, r, lt, t1);
+            uint32_t r0 = __float_as_uint(a.w), r1 = __float_as_uint(b.w);
+            if (h0 && h1) {
+                bool swap = t1 < t0;
+                uint32_t nearr = swap ? r1 : r0, farr = swap ? r0 : r1;
+                stack[sp++] = farr;
+                ref = nearr;
+            } else if (h0) {
+                ref = r0;
+            } else if (h1) {
+                ref = r1;
+            } else {
+                if (sp == 0) break;
+                ref = stack[--sp];
+            }
+        }
+    }
+    if (lfound) { best_t = lt; best_u = lu; best_v = lv; best_prim = lp; found = true; }
+}
+
+// model/bvh.rs:242-305 for one instance.  `r` is the MODEL-space ray, entry_t its t at entry (= the world
+// ray's current closest, scene_object.rs:87).  On return `found` says whether a strictly closer hit exists.
+template <bool ACCEL>
+__device__ __forceinline__ void blas_intersect(const BlasDesc& B, const RayM& r, float entry_t, bool use_accel,
+                                               float& best_t, float& best_u, float& best_v, uint32_t& best_prim, bool& found) {
+    uint32_t stack[kBlasStack];
+    int sp = 0;
+    uint32_t ni = 0;                       // root: its AABB is never tested (bvh.rs:243)
+    best_t = entry_t;
+    found = false;
+    float4 n0 = ldg4(B.nodes + 0);
+    float4 n1 = ldg4(B.nodes + 1);
+    for (;;) {
+        uint32_t count = __float_as_uint(n1.w);
+        uint32_t lf = __float_as_uint(n0.w);
+        if (count > 0) {
+            bool done = false;
+            if (ACCEL) {
+                if (use_accel) {
+                    uint32_t sr = __ldg(B.leaf_sub_root + ni);
+                    if (sr != 0xFFFFFFFFu) { leaf_accel(B, sr, r, entry_t, best_t, best_u, best_v, best_prim, found); done = true; }
+                }
+            }
+            if (!done) leaf_brute(B, lf, count, r, entry_t, best_t, best_u, best_v, best_prim, found);
+            if (sp == 0) break;
+            ni = stack[--sp];
+            n0 = ldg4(B.nodes + 2 * (size_t)ni);
+            n1 = ldg4(B.nodes + 2 * (size_t)ni + 1);
+        } else {
+            // children are adjacent: 4 float4 = 64 contiguous, 64-byte aligned bytes (left index is even)
+            const float4* c = B.nodes + 2 * (size_t)lf;
+            float4 l0 = ldg4(c + 0), l1 = ldg4(c + 1), r0 = ldg4(c + 2), r1 = ldg4(c + 3);
+            float ld, rd;
+            bool lh = slab_test(l0, l1, r, best_t, ld);
+            bool rh = slab_test(r0, r1, r, best_t, rd);
+            float lkey = lh ? ld : FLT_MAX;
+            float rkey = rh ? rd : FLT_MAX;
+            bool left_first = lkey < rkey;         // ties and double-miss: right first (bvh.rs:271-275)
+            bool near_hit = left_first ? lh : rh;
+            bool far_hit = left_first ? rh : lh;
+            if (near_hit) {
+                if (far_hit) stack[sp++] = left_first ? lf + 1 : lf;
+                if (left_first) { ni = lf; n0 = l0; n1 = l1; } else { ni = lf + 1; n0 = r0; n1 = r1; }
+                continue;
+            }
+            if (sp == 0) break;
+            ni = stack[--sp];
+            n0 = ldg4(B.nodes + 2 * (size_t)ni);
+            n1 = ldg4(B.nodes + 2 * (size_t)ni + 1);
+        }
+    }
+}
+
+// scene/tlas.rs:123-177 + scene_object.rs:78-89.  World ray (ox..dz, recip), initial t = tmax.
+template <bool ACCEL>
+__device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM& w, float tmax) {
+    HitRec best;
+    best.t = FLT_MAX; best.u = 0.0f; best.v = 0.0f; best.id = 0xFFFFFFFFu;
+    float closest = tmax;
+    bool have = false;
+    uint32_t stack[kTlasStack];
+    int sp = 0;
+    float4 n0 = ldg4(S.tlas + 0);
+    float4 n1 = ldg4(S.tlas + 1);
+    for (;;) {
+        uint32_t lr = __float_as_uint(n0.w);
+        if (lr == 0u) {
+            uint32_t inst = __float_as_uint(n1.w);
+            const float4* m = S.inst_cols + 4 * (size_t)inst;
+            float4 c0 = ldg4(m + 0), c1 = ldg4(m + 1), c2 = ldg4(m + 2), c3 = ldg4(m + 3);
+            RayM r;
+            // transform.rs:219-234 over cglinalg Matrix4x4 * Vector4: ((c0*x + c1*y) + c2*z) + c3*w
+            r.ox = ((c0.x * w.ox + c1.x * w.oy) + c2.x * w.oz) + c3.x * 1.0f;
+            r.oy = ((c0.y * w.ox + c1.y * w.oy) + c2.y * w.oz) + c3.y * 1.0f;
+            r.oz = ((c0.z * w.ox + c1.z * w.oy) + c2.z * w.oz) + c3.z * 1.0f;
+            r.dx = ((c0.x * w.dx + c1.x * w.dy) + c2.x * w.dz) + c3.x * 0.0f;
+            r.dy = ((c0.y * w.dx + c1.y * w.dy) + c2.y * w.dz) + c3.y * 0.0f;
+            r.dz = ((c0.z * w.dx + c1.z * w.dy) + c2.z * w.dz) + c3.z * 0.0f;
+            r.rdx = 1.0f / r.dx; r.rdy = 1.0f / r.dy; r.rdz = 1.0f / r.dz;   // Ray::new, ray.rs:23-31
+            const BlasDesc& B = S.blas[__ldg(S.inst_blas + inst)];
+            bool use_accel = false;
+            if (ACCEL) {
+                // the sub boxes were inflated for model-space rays with |d| <= d_max and |o| <= o_max; anything
+                // else takes the brute-force leaves (still exact)
+                float dn2 = (r.dx * r.dx + r.dy * r.dy) + r.dz * r.dz;
+                float on2 = (r.ox * r.ox + r.oy * r.oy) + r.oz * r.oz;
+                use_accel = (dn2 <= B.accel_d_max * B.accel_d_max) && (on2 <= B.accel_o_max * B.accel_o_max);
+            }
+            float bt, bu, bv; uint32_t bp; bool found;
+            blas_intersect<ACCEL>(B, r, closest, use_accel, bt, bu, bv, bp, found);
+            if (found && bt < closest) {                                     // tlas.rs:131
+                closest = bt;
+                best.t = bt; best.u = bu; best.v = bv;
+                // InstancePrimitiveIndex::from_primitive: instance bits are 0 in the reference (bvh.rs:296)
+                best.id = (bp & 0x000FFFFFu) | ((S.flags & 0x4u) ? ((inst & 0xFFFu) << 20) : 0u);
+                have = true;
+            }
+            if (sp == 0) break;
+            uint32_t ni = stack[--sp];
+            n0 = ldg4(S.tlas + 2 * (size_t)ni);
+            n1 = ldg4(S.tlas + 2 * (size_t)ni + 1);
+        } else {
+            uint32_t li = (lr & 0xFFFF0000u) >> 16;    // left_blas()  = upper half (tlas.rs:25-27)
+            uint32_t ri = lr & 0x0000FFFFu;            // right_blas() = lower half (tlas.rs:30-32)
+            float4 l0 = ldg4(S.tlas + 2 * (size_t)li), l1 = ldg4(S.tlas + 2 * (size_t)li + 1);
+            float4 r0 = ldg4(S.tlas + 2 * (size_t)ri), r1 = ldg4(S.tlas + 2 * (size_t)ri + 1);
+            float ld, rd;
+            bool lh = slab_test(l0, l1, w, closest, ld);
+            bool rh = slab_test(r0, r1, w, closest, rd);
+            float lkey = lh ? ld : FLT_MAX;
+            float rkey = rh ? rd : FLT_MAX;
+            bool left_first = lkey < rkey;
+            bool near_hit = left_first ? lh : rh;
+            bool far_hit = left_first ? rh : lh;
+            if (near_hit) {
+                if (far_hit) stack[sp++] = left_first ? ri : li;
+                if (left_first) { n0 = l0; n1 = l1; } else { n0 = r0; n1 = r1; }
+                continue;
+            }
+            if (sp == 0) break;
+            uint32_t ni = stack[--sp];
+            n0 = ldg4(S.tlas + 2 * (size_t)ni);
+            n1 = ldg4(S.tlas + 2 * (size_t)ni + 1);
+        }
+    }
+    if (!((closest < FLT_MAX) && have)) { best.t = FLT_MAX; best.u = 0.0f; best.v = 0.0f; best.id = 0xFFFFFFFFu; }
+    return best;
+}
+
+// camera.rs:994-1010 with u, v from renderer.rs:358-361
+__device__ __forceinline__ RayM primary_ray(const CameraDev& C, uint32_t px, uint32_t py, uint32_t width, uint32_t height) {
+    float u = (float)px / (float)width;
+    float v = (float)py / (float)height;
+    float p[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float origin = 0.0f;
+        p[k] = ((origin + C.tl[k]) + (C.tr[k] - C.tl[k]) * u) + (C.bl[k] - C.tl[k]) * v;
+        p[k] = p[k] - origin;
+    }
+    float m = sqrtf((p[0] * p[0] + p[1] * p[1]) + p[2] * p[2]);   // normalize = v / |v| (pinned, test_tri_mesh.rs:57-59)
+    float ex = p[0] / m, ey = p[1] / m, ez = p[2] / m;
+    RayM w;
+    const float* M = C.vinv;
+    w.ox = ((M[0] * 0.0f + M[4] * 0.0f) + M[8] * 0.0f) + M[12] * 1.0f;
+    w.oy = ((M[1] * 0.0f + M[5] * 0.0f) + M[9] * 0.0f) + M[13] * 1.0f;
+    w.oz = ((M[2] * 0.0f + M[6] * 0.0f) + M[10] * 0.0f) + M[14] * 1.0f;
+    w.dx = ((M[0] * ex + M[4] * ey) + M[8] * ez) + M[12] * 0.0f;
+    w.dy = ((M[1] * ex + M[5] * ey) + M[9] * ez) + M[13] * 0.0f;
+    w.dz = ((M[2] * ex + M[6] * ey) + M[10] * ez) + M[14] * 0.0f;
+    w.rdx = 1.0f / w.dx; w.rdy = 1.0f / w.dy; w.rdz = 1.0f / w.dz;
+    return w;
+}
+
+// K1: persistent, tile-pulling primary closest-hit kernel.
+template <bool ACCEL>
+__global__ void __launch_bounds__(256)
+trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
+    const unsigned lane = threadIdx.x & 31u;
+    for (;;) {
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(P.work_counter, 1u);
+        item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        if (item >= P.n_items) break;
+        uint32_t tile_idx = item / P.items_per_tile;
+        uint32_t sub = item - tile_idx * P.items_per_tile;
+        uint32_t tx = P.tx0 + tile_idx % P.ntx;
+        uint32_t ty = P.ty0 + tile_idx / P.ntx;
+        uint32_t p = sub * 32u + lane;                 // pixel within the tile, row-major (renderer.rs:356-357)
+        uint32_t iu = p % P.tile, iv = p / P.tile;
+        uint32_t px = tx * P.tile + iu, py = ty * P.tile + iv;
+        bool active = (iv < P.tile) && px >= P.x0 && px < P.x1 && py >= P.y0 && py < P.y1;
+        if (active) {
+            RayM w = primary_ray(P.cam, px, py, P.width, P.height);
+            HitRec h = scene_intersect<ACCEL>(P.scene, w, FLT_MAX);
+            uint4 o;
+            o.x = __float_as_uint(h.t); o.y = __float_as_uint(h.u); o.z = __float_as_uint(h.v); o.w = h.id;
+            P.out[(size_t)py * P.width + px] = o;
+        }
+    }
+}
+
+// K1b: Scene::intersect(&Ray) for an arbitrary ray buffer; warps pull 32 rays at a time.
+template <bool ACCEL>
+__global__ void __launch_bounds__(256)
+trace_rays_kernel(const __grid_constant__ RaysParams P) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t n_items = (P.n + 31u) / 32u;
+    for (;;) {
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(P.work_counter, 1u);
+        item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        if (item >= n_items) break;
+        uint64_t i = (uint64_t)item * 32u + lane;
+        if (i < P.n) {
+            const float* rp = P.rays + i * 7;
+            RayM w;
+            w.ox = __ldg(rp + 0); w.oy = __ldg(rp + 1); w.oz = __ldg(rp + 2);
+            w.dx = __ldg(rp + 3); w.dy = __ldg(rp + 4); w.dz = __ldg(rp + 5);
+            float t = __ldg(rp + 6);
+            w.rdx = 1.0f / w.dx; w.rdy = 1.0f / w.dy; w.rdz = 1.0f / w.dz;
+            HitRec h = scene_intersect<ACCEL>(P.scene, w, t);
+            uint4 o;
+            o.x = __float_as_uint(h.t); o.y = __float_as_uint(h.u); o.z = __float_as_uint(h.v); o.w = h.id;
+            P.out[i] = o;
+        }
+    }
+}
+
+} // namespace BVHT_MODE_NS
+} // namespace bvht

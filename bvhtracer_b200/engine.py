@@ -1,0 +1,145 @@
+"""Engine: a thin object wrapper over one bvht_ctx (include/bvht.h).  All work happens in libbvht_cuda.so."""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import BVH_NODE, CAMERA, HIT, INSTANCE, RAY, TLAS_NODE, BvhtError, Rect, Stats, ptr
+
+
+class Engine:
+    def __init__(self, device=0, flags=_ffi.FLAG_STRICT):
+        self._lib = _ffi.load()
+        self._ctx = C.c_void_p()
+        rc = self._lib.bvht_create(int(device), int(flags), C.byref(self._ctx))
+        if rc != _ffi.OK:
+            raise BvhtError(rc, self._lib.bvht_status_string(rc).decode())
+        self.flags = int(flags)
+        self.device = int(device)
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.bvht_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != _ffi.OK:
+            raise BvhtError(rc, self._lib.bvht_last_error(self._ctx).decode(errors="replace"))
+
+    def set_stream(self, cuda_stream_handle):
+        self._check(self._lib.bvht_set_stream(self._ctx, C.c_void_p(cuda_stream_handle or 0)))
+
+    def sync(self):
+        self._check(self._lib.bvht_sync(self._ctx))
+
+    def stats(self):
+        s = Stats()
+        self._check(self._lib.bvht_get_stats(self._ctx, C.byref(s)))
+        return s.as_dict()
+
+    # ------------------------------------------------------------------ scene state
+    def blas_create(self, tris, nodes, nodes_used=None):
+        tris = np.ascontiguousarray(np.asarray(tris, dtype="<f4").reshape(-1, 9))
+        nodes = np.ascontiguousarray(nodes)
+        assert nodes.dtype.itemsize == 32
+        if nodes_used is None:
+            nodes_used = len(nodes)
+        out = C.c_uint32()
+        self._check(self._lib.bvht_blas_create(self._ctx, ptr(tris), tris.shape[0], ptr(nodes), int(nodes_used), C.byref(out)))
+        return int(out.value)
+
+    def blas_destroy(self, blas_id):
+        self._check(self._lib.bvht_blas_destroy(self._ctx, int(blas_id)))
+
+    def blas_update_vertices(self, blas_id, tris):
+        tris = np.ascontiguousarray(np.asarray(tris, dtype="<f4").reshape(-1, 9))
+        self._check(self._lib.bvht_blas_update_vertices(self._ctx, int(blas_id), ptr(tris), tris.shape[0]))
+
+    def blas_refit(self, blas_id):
+        self._check(self._lib.bvht_blas_refit(self._ctx, int(blas_id)))
+
+    def blas_read_nodes(self, blas_id, n):
+        out = np.zeros(int(n), BVH_NODE)
+        self._check(self._lib.bvht_blas_read_nodes(self._ctx, int(blas_id), ptr(out), int(n)))
+        return out
+
+    def tlas_set(self, nodes, nodes_used, instances):
+        nodes = np.ascontiguousarray(nodes)
+        instances = np.ascontiguousarray(instances)
+        assert nodes.dtype.itemsize == 32 and instances.dtype.itemsize == 68
+        self._check(self._lib.bvht_tlas_set(self._ctx, ptr(nodes), int(nodes_used), ptr(instances), len(instances)))
+
+    # ------------------------------------------------------------------ tracing
+    def trace_primary(self, camera, width, height, tile=8, region=None, out=None):
+        camera = np.ascontiguousarray(camera)
+        assert camera.dtype.itemsize == 100
+        if out is None:
+            out = np.zeros(width * height, HIT)
+            out["t"] = _ffi.FLT_MAX
+            out["id"] = _ffi.MISS_ID
+        x0, y0, x1, y1 = region if region is not None else (0, 0, width, height)
+        self._check(self._lib.bvht_trace_primary(self._ctx, ptr(camera), int(width), int(height), int(tile),
+                                                 Rect(x0, y0, x1, y1), ptr(out)))
+        return out
+
+    def trace_primary_device(self, camera, width, height, tile, region, out_device_ptr):
+        camera = np.ascontiguousarray(camera)
+        x0, y0, x1, y1 = region if region is not None else (0, 0, width, height)
+        self._check(self._lib.bvht_trace_primary_device(self._ctx, ptr(camera), int(width), int(height), int(tile),
+                                                        Rect(x0, y0, x1, y1), C.c_void_p(out_device_ptr)))
+
+    def trace_rays(self, rays):
+        rays = np.ascontiguousarray(rays)
+        if rays.dtype != RAY:
+            rays = np.ascontiguousarray(np.asarray(rays, "<f4").reshape(-1, 7)).view(RAY).reshape(-1)
+        out = np.zeros(len(rays), HIT)
+        self._check(self._lib.bvht_trace_rays(self._ctx, ptr(rays), len(rays), ptr(out)))
+        return out
+
+    def trace_rays_device(self, rays_device_ptr, n, out_device_ptr):
+        self._check(self._lib.bvht_trace_rays_device(self._ctx, C.c_void_p(rays_device_ptr), int(n), C.c_void_p(out_device_ptr)))
+
+    # ------------------------------------------------------------------ device memory
+    def device_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(self._lib.bvht_device_alloc(self._ctx, int(nbytes), C.byref(p)))
+        return int(p.value)
+
+    def device_free(self, dptr):
+        self._check(self._lib.bvht_device_free(self._ctx, C.c_void_p(dptr)))
+
+    def memcpy_h2d(self, dptr, host_array):
+        host_array = np.ascontiguousarray(host_array)
+        self._check(self._lib.bvht_memcpy_h2d(self._ctx, C.c_void_p(dptr), ptr(host_array), host_array.nbytes))
+
+    def memcpy_d2h(self, host_array, dptr, nbytes=None):
+        assert host_array.flags["C_CONTIGUOUS"]
+        self._check(self._lib.bvht_memcpy_d2h(self._ctx, ptr(host_array), C.c_void_p(dptr), int(nbytes or host_array.nbytes)))
+        return host_array
+
+    def ipc_export(self, dptr):
+        h = (C.c_uint8 * 64)()
+        self._check(self._lib.bvht_ipc_export(self._ctx, C.c_void_p(dptr), h))
+        return bytes(h)
+
+    def ipc_open(self, handle_bytes):
+        h = (C.c_uint8 * 64).from_buffer_copy(handle_bytes)
+        p = C.c_void_p()
+        self._check(self._lib.bvht_ipc_open(self._ctx, h, C.byref(p)))
+        return int(p.value)
+
+    def ipc_close(self, dptr):
+        self._check(self._lib.bvht_ipc_close(self._ctx, C.c_void_p(dptr)))

@@ -1,0 +1,194 @@
+/*
+ * bvht.h -- C ABI of the B200-native closest-hit engine for bvhtracer's hot path.
+ *
+ * The reference (lambdaxymox/bvhtracer, pure Rust) has no FFI today; its plugin seam is the trait
+ * `Integrator::evaluate(&mut self, &mut RendererState, &Scene) -> usize` (bvhtracer/src/renderer.rs:104-106)
+ * plus `Scene::intersect(&self, &Ray<f32>) -> Option<Intersection<f32>>` (bvhtracer/src/scene/scene.rs:32-34).
+ * This header is what a `CudaPathTracer: Integrator` inside the Rust crate binds with `extern "C"`
+ * (INTEGRATION.md shows the binding).  Every entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all structs are POD with the layouts documented here
+ *   - return value: BVHT_OK (0) or a negative bvht_status; bvht_last_error(ctx) gives the text.
+ *     Nothing aborts, throws or unwinds across this boundary.  There is NO CPU fallback: with no
+ *     CUDA device bvht_create fails with BVHT_ERR_NO_DEVICE.
+ *   - the caller owns host buffers; the library copies during the call and never retains host pointers
+ *   - one ctx <-> one device <-> one host thread at a time.  Calls are synchronous at return unless the
+ *     name ends in _async / _device (then ordered on the ctx stream; bvht_sync waits).
+ *   - miss is encoded in-band: t = FLT_MAX, u = v = 0, id = 0xFFFFFFFF
+ */
+#ifndef BVHT_H
+#define BVHT_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BVHT_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define BVHT_API __attribute__((visibility("default")))
+#else
+#define BVHT_API
+#endif
+
+typedef enum {
+    BVHT_OK = 0,
+    BVHT_ERR_INVALID_ARG = -1,
+    BVHT_ERR_NO_DEVICE = -2,
+    BVHT_ERR_CUDA = -3,
+    BVHT_ERR_OUT_OF_MEMORY = -4,
+    BVHT_ERR_BAD_HANDLE = -5,
+    BVHT_ERR_MALFORMED_BVH = -6,     /* child index out of range, cycle, stack bound exceeded, ... */
+    BVHT_ERR_NOT_READY = -7          /* trace before tlas_set, refit before vertices, ... */
+} bvht_status;
+
+/* bvht_create flags */
+#define BVHT_FLAG_STRICT       0x0u  /* default: kernels built with --fmad=false, IEEE div/sqrt, no FTZ:
+                                        hit ids bit-exact, t/u/v bit-exact vs the reference CPU path */
+#define BVHT_FLAG_FAST         0x1u  /* FMA-contracted kernels: >= 99.99 % identical ids, t within 1e-5 rel. */
+#define BVHT_FLAG_LEAF_ACCEL   0x2u  /* conservative sub-BVH inside each oversized reference leaf:
+                                        same results, far fewer triangle tests */
+#define BVHT_FLAG_STAMP_INSTANCE 0x4u /* EXTENSION (off by default): put the instance index in id bits 31..20.
+                                        The reference always reports instance 0 (bvh.rs:296, intersection.rs:64-66) */
+
+typedef struct bvht_ctx bvht_ctx;
+
+/* model/bvh.rs:88-134  BvhLeafNode / BvhBranchNode (both #[repr(C)]): 32 bytes.
+ * prim_count > 0  => leaf, left_first = first primitive index
+ * prim_count == 0 => branch, children at left_first and left_first + 1.  Node 1 is the unused dummy. */
+typedef struct {
+    float    aabb_min[3];
+    float    aabb_max[3];
+    uint32_t prim_count;
+    uint32_t left_first;
+} bvht_bvh_node;
+
+/* scene/tlas.rs:11-46  TlasNode: 32 bytes.  left_right == 0 => leaf (blas = instance index).
+ * left_right keeps the reference's packing (LeftRightIndex::new(l, r) = l + (r << 16), tlas.rs:18-22)
+ * and the engine reads it back exactly like the reference accessors do (upper half first, tlas.rs:25-32). */
+typedef struct {
+    float    aabb_min[3];
+    float    aabb_max[3];
+    uint32_t left_right;
+    uint32_t blas;
+} bvht_tlas_node;
+
+/* scene/scene_object.rs:16-21 + transform_component.rs:8-11: cached INVERSE transform, column-major
+ * (cglinalg Matrix4x4 storage), and the BLAS this instance refers to. */
+typedef struct {
+    float    transform_inv[16];
+    uint32_t blas_id;
+} bvht_instance;
+
+/* camera/camera.rs:199-216 (eye-space corner points of the near plane) and :871-873 (view_matrix_inv,
+ * column-major).  Ray for (u, v): camera.rs:994-1010. */
+typedef struct {
+    float top_left_eye[3];
+    float top_right_eye[3];
+    float bottom_left_eye[3];
+    float view_matrix_inv[16];
+} bvht_camera;
+
+/* query/ray.rs:9-17 without the cached reciprocal (Ray::new recomputes it, ray.rs:23-31). */
+typedef struct {
+    float origin[3];
+    float direction[3];
+    float t;                         /* initial closest distance (f32::MAX for Ray::from_origin_dir) */
+} bvht_ray;
+
+/* query/intersection.rs:10-17, 33-67, 77-92: the 16-byte record {t, u, v, InstancePrimitiveIndex}. */
+typedef struct {
+    float    t;
+    float    u;
+    float    v;
+    uint32_t id;                     /* ((instance & 0xFFF) << 20) | (primitive & 0xFFFFF); miss: 0xFFFFFFFF */
+} bvht_hit;
+
+typedef struct { uint32_t x0, y0, x1, y1; } bvht_rect;   /* pixels [x0,x1) x [y0,y1) */
+
+typedef struct {
+    float    last_trace_ms;          /* device time of the last trace kernel (CUDA events on the ctx stream) */
+    float    last_refit_ms;
+    float    last_upload_ms;
+    uint64_t last_trace_rays;
+    uint64_t kernel_launches;        /* total launches of this library's own kernels since bvht_create */
+    uint64_t h2d_bytes;              /* totals since bvht_create */
+    uint64_t d2h_bytes;
+    uint32_t sm_count;
+    uint32_t trace_grid;             /* CTAs of the last persistent trace launch */
+    uint32_t trace_block;
+    uint32_t flags;
+} bvht_stats;
+
+/* ---------------------------------------------------------------------------------------------- */
+BVHT_API int         bvht_abi_version(void);
+BVHT_API int         bvht_device_count(void);
+
+/* Create a context on `device`.  Replaces nothing in the reference (it has no device). */
+BVHT_API int         bvht_create(int device, uint32_t flags, bvht_ctx** out);
+BVHT_API void        bvht_destroy(bvht_ctx* ctx);
+BVHT_API const char* bvht_last_error(const bvht_ctx* ctx);
+BVHT_API const char* bvht_status_string(int status);
+
+/* Use an existing CUDA stream (cudaStream_t as void*) for all work of this ctx; NULL = the ctx's own. */
+BVHT_API int         bvht_set_stream(bvht_ctx* ctx, void* cuda_stream);
+BVHT_API int         bvht_sync(bvht_ctx* ctx);
+
+/* Upload one model: the BVH-reordered triangle buffer `Mesh::primitives()` (mesh.rs:126-134; n_tris x 9 f32,
+ * 36-byte stride) and the used prefix of `Bvh.nodes` (bvh.rs:228-233).  Replaces what
+ * ModelBuilder::build leaves in memory for Model::intersect (model.rs:66-68, 140-144).  On upload the
+ * node pool is flattened to 2 x float4 per node and the triangles are repacked SoA (v0, e1, e2). */
+BVHT_API int         bvht_blas_create(bvht_ctx* ctx, const float* tris, uint32_t n_tris,
+                             const bvht_bvh_node* nodes, uint32_t nodes_used, uint32_t* out_blas_id);
+BVHT_API int         bvht_blas_destroy(bvht_ctx* ctx, uint32_t blas_id);
+
+/* New vertex positions for an existing model (examples/big_ben_clock.rs:67-96 `animate`); same count. */
+BVHT_API int         bvht_blas_update_vertices(bvht_ctx* ctx, uint32_t blas_id, const float* tris, uint32_t n_tris);
+
+/* Bvh::refit (bvh.rs:469-493) + update_node_bounds (bvh.rs:317-330), bottom-up on the device. */
+BVHT_API int         bvht_blas_refit(bvht_ctx* ctx, uint32_t blas_id);
+
+/* Read the device node pool back in reference layout (parity checks of refit). */
+BVHT_API int         bvht_blas_read_nodes(bvht_ctx* ctx, uint32_t blas_id, bvht_bvh_node* out, uint32_t max_nodes);
+
+/* Per-frame scene state: `Tlas.nodes[0..nodes_used]` after Tlas::rebuild (tlas.rs:204-250) and one
+ * bvht_instance per SceneObject, in `Scene.objects` order (scene.rs:10-15). */
+BVHT_API int         bvht_tlas_set(bvht_ctx* ctx, const bvht_tlas_node* nodes, uint32_t nodes_used,
+                          const bvht_instance* instances, uint32_t n_instances);
+
+/* PathTracer::evaluate, first loop (renderer.rs:345-368): one primary ray per pixel of `region` of a
+ * width x height image through Camera::get_ray_world, Scene::intersect for each, tiles of `tile` x `tile`
+ * pixels (8 in the reference).  out_host: width*height records, row-major (pixel_address =
+ * x + y * width, renderer.rs:362); only the region's pixels are written.  Returns when out_host is filled. */
+BVHT_API int         bvht_trace_primary(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height,
+                               uint32_t tile, bvht_rect region, bvht_hit* out_host);
+
+/* Same, result left in device memory (a device pointer obtained from bvht_device_alloc, from another
+ * library, or a peer-mapped pointer of another GPU: the kernel stores straight into it).  Asynchronous. */
+BVHT_API int         bvht_trace_primary_device(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height,
+                                      uint32_t tile, bvht_rect region, void* out_device);
+
+/* Scene::intersect(&Ray) for n arbitrary rays (scene.rs:32-34). */
+BVHT_API int         bvht_trace_rays(bvht_ctx* ctx, const bvht_ray* rays, uint64_t n, bvht_hit* out_host);
+BVHT_API int         bvht_trace_rays_device(bvht_ctx* ctx, const void* rays_device, uint64_t n, void* out_device);
+
+/* Device memory helpers (multi-GPU gather, resident benchmarks). */
+BVHT_API int         bvht_device_alloc(bvht_ctx* ctx, size_t bytes, void** out_device);
+BVHT_API int         bvht_device_free(bvht_ctx* ctx, void* device_ptr);
+BVHT_API int         bvht_memcpy_h2d(bvht_ctx* ctx, void* dst_device, const void* src_host, size_t bytes);
+BVHT_API int         bvht_memcpy_d2h(bvht_ctx* ctx, void* dst_host, const void* src_device, size_t bytes);
+/* CUDA IPC: export a device allocation so another process (one rank per GPU) can map it over NVLink P2P */
+BVHT_API int         bvht_ipc_export(bvht_ctx* ctx, void* device_ptr, uint8_t handle_out[64]);
+BVHT_API int         bvht_ipc_open(bvht_ctx* ctx, const uint8_t handle[64], void** out_device);
+BVHT_API int         bvht_ipc_close(bvht_ctx* ctx, void* device_ptr);
+
+BVHT_API int         bvht_get_stats(const bvht_ctx* ctx, bvht_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BVHT_H */

@@ -1,0 +1,58 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol that
+include/bvht.h declares; without a device it reports BVHT_ERR_NO_DEVICE (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import bvhtracer_b200
+from bvhtracer_b200 import _ffi, build as bvht_build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "bvht.h")).read()
+    return sorted(set(re.findall(r"^BVHT_API\s+[\w\s\*]+?\b(bvht_\w+)\s*\(", text, flags=re.M)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = bvht_build.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/bvht.h but not exported"
+    assert sorted(n for n, _, _ in _ffi.SYMBOLS) == names          # the Python binding covers the whole header
+
+
+def test_abi_version_and_struct_sizes():
+    lib = _ffi.load()
+    assert lib.bvht_abi_version() == 1
+    assert _ffi.BVH_NODE.itemsize == 32          # bvh.rs:720-723
+    assert _ffi.TLAS_NODE.itemsize == 32
+    assert _ffi.HIT.itemsize == 16               # intersection.rs:77-83
+    assert _ffi.INSTANCE.itemsize == 68 and _ffi.CAMERA.itemsize == 100 and _ffi.RAY.itemsize == 28
+    assert lib.bvht_status_string(-2).decode().startswith("no CUDA device")
+
+
+def test_no_device_is_an_error_not_a_fallback():
+    lib = _ffi.load()
+    if lib.bvht_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(bvhtracer_b200.BvhtError) as e:
+        bvhtracer_b200.Engine()
+    assert e.value.status == _ffi.ERR_NO_DEVICE
+
+
+def test_product_never_imports_the_oracle():
+    # the oracle is test infrastructure: nothing under bvhtracer_b200/ may reference it
+    pkg = os.path.join(ROOT, "bvhtracer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".inc")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle_lib" not in text and "liboracle" not in text and "bvht_oracle" not in text, f

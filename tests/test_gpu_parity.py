@@ -1,0 +1,312 @@
+"""GPU parity tests: the CUDA path (through the C ABI of include/bvht.h) against the CPU oracle.
+
+Bar (BASELINE.json north_star): strict mode -- hit ids bit-exact, t within 1 ulp (we require bit-identical
+records); fast mode -- >= 99.99 % identical ids, t within 1e-5 relative.
+Sizes are chosen so the oracle finishes in seconds; full-size runs compare the leaf accelerator against the
+brute-force leaves on the GPU itself (both strict), which is size-independent evidence of equivalence.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import scene_build as SB
+from bvhtracer_b200 import Engine, BvhtError, _ffi, examples
+from bvhtracer_b200 import FLAG_FAST, FLAG_LEAF_ACCEL, FLAG_STRICT
+
+pytestmark = pytest.mark.gpu
+
+F = np.float32
+NTHREADS = max(1, O.max_threads())
+
+STRICT_MODES = [FLAG_STRICT, FLAG_STRICT | FLAG_LEAF_ACCEL]
+MODE_IDS = ["strict-brute", "strict-accel"]
+
+
+def render_both(spec, w, h, flags, tile=8):
+    scene, cam = SB.oracle_scene(spec)
+    ref = scene.render(cam, w, h, tile=tile, threads=NTHREADS)
+    with Engine(flags=flags) as eng:
+        SB.upload_scene(eng, scene)
+        got = eng.trace_primary(SB.to_ffi_camera(cam), w, h, tile=tile)
+    return got, ref
+
+
+def assert_strict(got, ref):
+    r = SB.compare_hits(got, ref)
+    assert r["id_mismatch"] == 0, r
+    assert r["max_ulp_t"] == 0 and r["max_ulp_u"] == 0 and r["max_ulp_v"] == 0, r
+    assert r["bit_identical"], r
+
+
+def assert_fast(got, ref):
+    r = SB.compare_hits(got, ref)
+    assert r["id_mismatch"] <= 1e-4 * r["n"], r
+    assert r["max_rel_t"] <= 1e-5, r
+
+
+# ------------------------------------------------------------------------------------------ C1 / quad
+@pytest.mark.parametrize("flags", STRICT_MODES, ids=MODE_IDS)
+def test_cube_640_bit_exact(flags):
+    got, ref = render_both(examples.cube(), 640, 640, flags)
+    assert (ref["id"] != O.MISS_ID).sum() > 1000
+    assert_strict(got, ref)
+
+
+@pytest.mark.parametrize("flags", STRICT_MODES, ids=MODE_IDS)
+def test_cube_golden_ids_through_abi(flags):
+    # bvhtracer/tests/test_scene_cube.rs:97-136, 188-227 through bvht_trace_rays
+    scene, _ = SB.oracle_scene(examples.cube())
+    o = np.array([0, 4, 0], F)
+    rays = []
+    for target in ([0.5, 1.0, -0.5], [-0.5, 1.0, 0.5]):
+        d = O.normalize(np.array(target, F) - o)
+        rays.append(list(o) + list(d) + [O.FLT_MAX])
+    with Engine(flags=flags) as eng:
+        SB.upload_scene(eng, scene)
+        hits = eng.trace_rays(np.array(rays, F))
+    assert [int(h) & 0xFFFFF for h in hits["id"]] == [6, 9]
+    assert [int(h) >> 20 for h in hits["id"]] == [0, 0]
+    exp = np.sqrt(F(19) / F(2))
+    assert all(abs(float(t) - float(exp)) <= float(exp) * float(np.finfo(F).eps) for t in hits["t"])
+
+
+@pytest.mark.parametrize("flags", STRICT_MODES, ids=MODE_IDS)
+def test_quad_viewport_640(flags):
+    # bvhtracer/tests/test_scene_quad.rs:355-377 (see tests/test_oracle_kat.py for the 16 exact-edge pixels)
+    got, ref = render_both(examples.quad(), 640, 640, flags)
+    assert_strict(got, ref)
+    g = got.reshape(640, 640)
+    assert F(g["t"][320, 320]).tobytes() == F(2).tobytes()          # test_scene_quad.rs:201-209
+    inside = np.zeros((640, 640), bool)
+    inside[161:481, 160:480] = True                                  # interior of the quad's solid angle
+    assert (g["id"][inside] != O.MISS_ID).all()
+    outside = np.ones((640, 640), bool)
+    outside[160:481, 160:481] = False
+    assert (g["id"][outside] == O.MISS_ID).all()
+
+
+def test_triangle_and_aabb_kats_through_abi():
+    # bvhtracer/tests/test_bvh_one_triangle.rs:82-139 (bit-exact t), test_triangle_intersection.rs:126-166 (misses)
+    s3 = np.sqrt(F(3))
+    tri = np.array([[0, 0.5, 0, -F(1) / s3, -0.5, 0, F(1) / s3, -0.5, 0]], F)
+    blas = O.Blas(tri)
+    scene = O.Scene([blas], [(0, O.mat4_identity())])
+    o = np.array([0, 0, 5], F)
+    targets = [[0, 0, 0], tri[0, 0:3], tri[0, 3:6], tri[0, 6:9],
+               tri[0, 0:3] + np.array([0, 0.5, 0], F), tri[0, 3:6] + np.array([0, -0.5, 0], F)]
+    rays = np.array([list(o) + list(O.normalize(np.array(t, F) - o)) + [O.FLT_MAX] for t in targets], F)
+    with Engine() as eng:
+        SB.upload_scene(eng, scene)
+        hits = eng.trace_rays(rays)
+    exp = [F(5), np.sqrt(F(101) / F(4)), np.sqrt(F(307) / F(12)), np.sqrt(F(307) / F(12))]
+    for h, e in zip(hits[:4], exp):
+        assert F(h["t"]).tobytes() == F(e).tobytes() and h["id"] == 0
+    assert all(h["id"] == O.MISS_ID and h["t"] == O.FLT_MAX for h in hits[4:])
+
+
+# ------------------------------------------------------------------------------------------ C2
+@pytest.mark.parametrize("flags", STRICT_MODES, ids=MODE_IDS)
+@pytest.mark.parametrize("frame", ["canonical", "initial"])
+def test_two_armadillos_bit_exact(frame, flags):
+    # "initial" has both instances coincident: every hit is an exact tie between instances (order matters)
+    got, ref = render_both(examples.two_armadillos(frame), 384, 216, flags)
+    assert (ref["id"] != O.MISS_ID).mean() > 0.05
+    assert_strict(got, ref)
+
+
+# ------------------------------------------------------------------------------------------ C3 / C4
+@pytest.mark.parametrize("flags", STRICT_MODES, ids=MODE_IDS)
+@pytest.mark.parametrize("frame", [0, 1, 37])
+def test_sixteen_armadillos_bit_exact(frame, flags):
+    got, ref = render_both(examples.sixteen_armadillos(frame), 320, 180, flags)
+    assert (ref["id"] != O.MISS_ID).mean() > 0.05
+    assert_strict(got, ref)
+
+
+@pytest.mark.parametrize("flags", STRICT_MODES, ids=MODE_IDS)
+@pytest.mark.parametrize("frame", [0, 25])
+def test_trippy_teapots_bit_exact(frame, flags):
+    got, ref = render_both(examples.trippy_teapots(frame), 960, 540, flags)
+    assert (ref["id"] != O.MISS_ID).mean() > 0.02
+    assert_strict(got, ref)
+
+
+# ------------------------------------------------------------------------------------------ C5: refit
+@pytest.mark.parametrize("flags", STRICT_MODES, ids=MODE_IDS)
+def test_big_ben_animate_refit_trace(flags):
+    spec = examples.big_ben_clock()
+    scene, cam = SB.oracle_scene(spec)
+    blas = O.Blas(O.load_asset("bigben.tri"))              # private copy: vertices get animated
+    scene = O.Scene([blas], [(0, O.mat4_identity())], with_transform=False)
+    anim = examples.BigBenAnimation(blas.tris)
+    with Engine(flags=flags) as eng:
+        ids = SB.upload_scene(eng, scene)
+        for frame in range(3):
+            verts = anim.animate()
+            blas.tris[:] = verts
+            blas.refit()                                   # oracle: Bvh::refit
+            scene.refresh_blas()
+            eng.blas_update_vertices(ids[0], verts)
+            eng.blas_refit(ids[0])                         # device: K2
+            nodes = eng.blas_read_nodes(ids[0], blas.nodes_used)
+            ref_nodes = blas.nodes[:blas.nodes_used]
+            assert np.array_equal(nodes["aabb_min"], ref_nodes["min"])
+            assert np.array_equal(nodes["aabb_max"], ref_nodes["max"])
+            assert np.array_equal(nodes["prim_count"], ref_nodes["prim_count"])
+            assert np.array_equal(nodes["left_first"], ref_nodes["left_first"])
+            ref = scene.render(cam, 256, 144, threads=NTHREADS)
+            got = eng.trace_primary(SB.to_ffi_camera(cam), 256, 144)
+            assert_strict(got, ref)
+
+
+def test_refit_identity_and_idempotent_on_device():
+    # bvhtracer/tests/test_bvh_refit.rs:47-65 through the C ABI
+    s3 = np.sqrt(F(3))
+    t0 = np.array([[0, 0.5, 0], [-F(1) / s3, -0.5, 0], [F(1) / s3, -0.5, 0]], F)
+    tris = np.stack([((t0 + F(i) * np.array([5, 0, 0], F)) + F(i) * np.array([0, 5, 0], F)).reshape(9) for i in range(-100, 100)])
+    blas = O.Blas(tris.astype(F))
+    with Engine() as eng:
+        bid = eng.blas_create(blas.tris, blas.nodes.view(_ffi.BVH_NODE), blas.nodes_used)
+        eng.blas_refit(bid)
+        n1 = eng.blas_read_nodes(bid, blas.nodes_used)
+        assert n1.tobytes() == blas.nodes[:blas.nodes_used].tobytes()       # unchanged on the same mesh
+        moved = blas.tris.copy()
+        moved[:, 0] += F(0.3); moved[:, 4] += F(0.3); moved[:, 8] += F(0.3)
+        eng.blas_update_vertices(bid, moved)
+        eng.blas_refit(bid)
+        a = eng.blas_read_nodes(bid, blas.nodes_used)
+        eng.blas_refit(bid)
+        b = eng.blas_read_nodes(bid, blas.nodes_used)
+        assert a.tobytes() == b.tobytes()                                    # idempotent
+        blas.tris[:] = moved
+        blas.refit()
+        assert np.array_equal(a["aabb_min"], blas.nodes["min"][:blas.nodes_used])
+        assert np.array_equal(a["aabb_max"], blas.nodes["max"][:blas.nodes_used])
+        assert a[1].tobytes() == bytes(32)                                   # node 1 untouched (bvh.rs:635-642)
+
+
+# ------------------------------------------------------------------------------------------ arbitrary rays
+@pytest.mark.parametrize("flags", STRICT_MODES, ids=MODE_IDS)
+def test_random_rays_sixteen_armadillos(flags):
+    scene, _ = SB.oracle_scene(examples.sixteen_armadillos(12))
+    rng = np.random.default_rng(1234)
+    n = 20000
+    o = rng.uniform(-8, 8, (n, 3)).astype(F)
+    target = rng.uniform(-4, 4, (n, 3)).astype(F)
+    d = target - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(F)
+    t = np.where(rng.random(n) < 0.2, rng.uniform(0.5, 12.0, n), O.FLT_MAX).astype(F)
+    rays = np.concatenate([o, d.astype(F), t[:, None]], axis=1).astype(F)
+    # axis-aligned directions: zero components -> +-inf reciprocals (aabb.rs KATs rely on this)
+    rays[:60, 3:6] = 0
+    for i in range(60):
+        rays[i, 3 + (i % 3)] = 1.0 if (i // 3) % 2 == 0 else -1.0
+    ref = scene.trace_rays(rays, threads=NTHREADS)
+    with Engine(flags=flags) as eng:
+        SB.upload_scene(eng, scene)
+        got = eng.trace_rays(rays)
+    assert (ref["id"] != O.MISS_ID).sum() > 500
+    assert_strict(got, ref)
+
+
+def test_empty_and_ragged_inputs():
+    scene, cam = SB.oracle_scene(examples.cube())
+    with Engine() as eng:
+        SB.upload_scene(eng, scene)
+        assert len(eng.trace_rays(np.zeros((0, 7), F))) == 0                # empty ray list
+        # ragged image: not a multiple of the tile, odd tile, sub-rectangle region
+        w, h = 101, 67
+        ref = scene.render(cam, w, h, tile=8)
+        for tile in (8, 5, 16):
+            got = eng.trace_primary(SB.to_ffi_camera(cam), w, h, tile=tile)
+            assert got.tobytes() == ref.tobytes()
+        region = (13, 9, 77, 50)
+        got = eng.trace_primary(SB.to_ffi_camera(cam), w, h, region=region)
+        exp = np.zeros(w * h, _ffi.HIT); exp["t"] = O.FLT_MAX; exp["id"] = O.MISS_ID
+        e2 = exp.reshape(h, w); r2 = ref.reshape(h, w)
+        e2[9:50, 13:77] = r2[9:50, 13:77]
+        assert got.tobytes() == exp.tobytes()
+        # empty region is a no-op
+        got = eng.trace_primary(SB.to_ffi_camera(cam), w, h, region=(5, 5, 5, 9))
+        assert (got["id"] == O.MISS_ID).all()
+
+
+def test_tile_bands_reassemble_full_frame():
+    # multi-GPU sharding contract: disjoint regions written into one buffer == full frame
+    scene, cam = SB.oracle_scene(examples.trippy_teapots(3))
+    w, h = 640, 360
+    with Engine(flags=FLAG_LEAF_ACCEL) as eng:
+        SB.upload_scene(eng, scene)
+        full = eng.trace_primary(SB.to_ffi_camera(cam), w, h)
+        out = None
+        for r in range(4):
+            y0, y1 = r * 88, min(h, (r + 1) * 88)
+            out = eng.trace_primary(SB.to_ffi_camera(cam), w, h, region=(0, y0, w, y1), out=out)
+        out = eng.trace_primary(SB.to_ffi_camera(cam), w, h, region=(0, 352, w, h), out=out)
+    assert out.tobytes() == full.tobytes()
+
+
+# ------------------------------------------------------------------------------------------ accel == brute at full size
+@pytest.mark.parametrize("name,frame,size", [
+    ("two_armadillos", "canonical", (1920, 1080)),
+    ("two_armadillos", "initial", (1920, 1080)),
+    ("sixteen_armadillos", 0, (3840, 2160)),
+    ("sixteen_armadillos", 45, (1920, 1080)),
+    ("trippy_teapots", 10, (3840, 2160)),
+    ("big_ben_clock", None, (1920, 1080)),
+])
+def test_leaf_accel_equals_brute_force_full_size(name, frame, size):
+    spec = examples.CONFIGS[name]() if frame is None else examples.CONFIGS[name](frame)
+    scene, cam = SB.oracle_scene(spec)
+    w, h = size
+    res = []
+    for flags in STRICT_MODES:
+        with Engine(flags=flags) as eng:
+            SB.upload_scene(eng, scene)
+            res.append(eng.trace_primary(SB.to_ffi_camera(cam), w, h))
+    assert (res[0]["id"] != O.MISS_ID).sum() > 1000
+    assert res[0].tobytes() == res[1].tobytes()
+
+
+# ------------------------------------------------------------------------------------------ fast mode
+@pytest.mark.parametrize("flags", [FLAG_FAST, FLAG_FAST | FLAG_LEAF_ACCEL], ids=["fast-brute", "fast-accel"])
+@pytest.mark.parametrize("name,frame,size", [("two_armadillos", "canonical", (384, 216)),
+                                             ("sixteen_armadillos", 5, (320, 180)),
+                                             ("trippy_teapots", 8, (640, 360))])
+def test_fast_mode_tolerance(name, frame, size, flags):
+    got, ref = render_both(examples.CONFIGS[name](frame), size[0], size[1], flags)
+    assert_fast(got, ref)
+
+
+# ------------------------------------------------------------------------------------------ error behaviour
+def test_errors_are_codes_not_crashes():
+    scene, cam = SB.oracle_scene(examples.cube())
+    blas = scene.blases[0]
+    with Engine() as eng:
+        with pytest.raises(BvhtError) as e:                       # trace before tlas_set
+            eng.trace_primary(SB.to_ffi_camera(cam), 8, 8)
+        assert e.value.status == _ffi.ERR_NOT_READY
+        bad = blas.nodes[:blas.nodes_used].copy().view(_ffi.BVH_NODE)
+        bad["left_first"][0] = 1000                               # child out of range
+        with pytest.raises(BvhtError) as e:
+            eng.blas_create(blas.tris, bad, blas.nodes_used)
+        assert e.value.status == _ffi.ERR_MALFORMED_BVH
+        bad = blas.nodes[:blas.nodes_used].copy().view(_ffi.BVH_NODE)
+        leaf = int(np.argmax(bad["prim_count"] > 0))
+        bad["prim_count"][leaf] = 10 ** 6                         # leaf beyond the triangle buffer
+        with pytest.raises(BvhtError) as e:
+            eng.blas_create(blas.tris, bad, blas.nodes_used)
+        assert e.value.status == _ffi.ERR_MALFORMED_BVH
+        with pytest.raises(BvhtError) as e:                       # empty model
+            eng.blas_create(np.zeros((0, 9), F), blas.nodes.view(_ffi.BVH_NODE), 2)
+        assert e.value.status == _ffi.ERR_INVALID_ARG
+        ids = SB.upload_scene(eng, scene)
+        inst = np.zeros(1, _ffi.INSTANCE); inst["blas_id"] = 77  # unknown blas
+        with pytest.raises(BvhtError) as e:
+            eng.tlas_set(scene.tlas.view(_ffi.TLAS_NODE), scene.tlas_used, inst)
+        assert e.value.status == _ffi.ERR_BAD_HANDLE
+        with pytest.raises(BvhtError):
+            eng.blas_update_vertices(ids[0], np.zeros((5, 9), F))  # wrong triangle count
+        # the context is still usable after every error
+        got = eng.trace_primary(SB.to_ffi_camera(cam), 64, 64)
+        assert got.tobytes() == scene.render(cam, 64, 64).tobytes()
