@@ -35,6 +35,14 @@ class Rect(C.Structure):
     _fields_ = [("x0", C.c_uint32), ("y0", C.c_uint32), ("x1", C.c_uint32), ("y1", C.c_uint32)]
 
 
+class ShadeParams(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("depth_scale", C.c_float), ("depth_offset", C.c_float),
+                ("hit_rgba", C.c_uint8 * 4), ("miss_rgba", C.c_uint8 * 4)]
+
+
+SHADE_NONE, SHADE_DEPTH, SHADE_INTERSECTION, SHADE_UV = 0, 1, 2, 3
+
+
 class Stats(C.Structure):
     _fields_ = [("last_trace_ms", C.c_float), ("last_refit_ms", C.c_float), ("last_upload_ms", C.c_float),
                 ("last_trace_rays", C.c_uint64), ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64),
@@ -64,10 +72,16 @@ SYMBOLS = [
     ("bvht_tlas_set", C.c_int, [_P, _P, C.c_uint32, _P, C.c_uint32]),
     ("bvht_trace_primary", C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, Rect, _P]),
     ("bvht_trace_primary_device", C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, Rect, _P]),
+    ("bvht_render_frame", C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, Rect, C.POINTER(ShadeParams), _P, _P]),
+    ("bvht_render_frame_device", C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, Rect, C.POINTER(ShadeParams), _P, _P]),
+    ("bvht_set_shard", C.c_int, [_P, C.c_uint32, C.c_uint32]),
+    ("bvht_shard_tile_rows", C.c_int, [Rect, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     ("bvht_trace_rays", C.c_int, [_P, _P, C.c_uint64, _P]),
     ("bvht_trace_rays_device", C.c_int, [_P, _P, C.c_uint64, _P]),
     ("bvht_device_alloc", C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     ("bvht_device_free", C.c_int, [_P, _P]),
+    ("bvht_host_alloc", C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
+    ("bvht_host_free", C.c_int, [_P, _P]),
     ("bvht_memcpy_h2d", C.c_int, [_P, _P, _P, C.c_size_t]),
     ("bvht_memcpy_d2h", C.c_int, [_P, _P, _P, C.c_size_t]),
     ("bvht_ipc_export", C.c_int, [_P, _P, _P]),
@@ -103,3 +117,12 @@ def load():
 
 def ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def shard_tile_rows(region, tile, index, count):
+    """bvht_shard_tile_rows: -> list of the tile rows shard `index` of `count` owns inside `region` (x0, y0, x1, y1)."""
+    first, n = C.c_uint32(), C.c_uint32()
+    rc = load().bvht_shard_tile_rows(Rect(*region), int(tile), int(index), int(count), C.byref(first), C.byref(n))
+    if rc != OK:
+        raise BvhtError(rc, "bvht_shard_tile_rows")
+    return [first.value + k * int(count) for k in range(n.value)]

@@ -82,5 +82,33 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+HOST_DIR = os.path.join(PKG, "host")
+HOST_LIB = os.path.join(LIB_DIR, "libbvht_host.so")
+
+
+def build_host(force=False):
+    """C++ host mirror (bvhtracer_b200/host): g++ with rustc's arithmetic model, linked against libbvht_cuda.so."""
+    srcs = [os.path.join(HOST_DIR, f) for f in ("capi.cpp", "bvhtracer.hpp")] + [os.path.join(os.path.dirname(PKG), "include", "bvht.h")]
+    if not force and os.path.exists(HOST_LIB) and all(os.path.getmtime(s) <= os.path.getmtime(HOST_LIB) for s in srcs) \
+            and os.path.getmtime(LIB_PATH) <= os.path.getmtime(HOST_LIB):
+        return HOST_LIB
+    cxx = shutil.which("g++") or "g++"
+    tmp = HOST_LIB + ".tmp"
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-fvisibility=hidden", "-Wall",
+           os.path.join(HOST_DIR, "capi.cpp"), "-o", tmp, "-L" + LIB_DIR, "-lbvht_cuda", "-Wl,-rpath,$ORIGIN"]
+    subprocess.check_call(cmd)
+    os.replace(tmp, HOST_LIB)
+    return HOST_LIB
+
+
+def build_all(force=False, verbose=False):
+    build(force=force, verbose=verbose)
+    build_host(force=force)
+    return LIB_PATH, HOST_LIB
+
+
 if __name__ == "__main__":
+    print(build_all(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    sys.exit(0)
+
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

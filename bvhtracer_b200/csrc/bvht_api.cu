@@ -65,9 +65,14 @@ struct bvht_ctx {
     DevBuf tlas, inst_cols, inst_blas;
     uint32_t tlas_nodes_used = 0, n_inst = 0;
     DevBuf work_counter;
-    DevBuf out_buf, rays_buf;                         // device staging for the host-pointer entry points
+    DevBuf out_buf, rays_buf, rgba_buf;               // device staging for the host-pointer entry points
+    cudaStream_t aux[2] = { nullptr, nullptr };       // band pipelining: two compute streams + one copy stream
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_band[64] = {};
     void* pinned = nullptr; size_t pinned_bytes = 0;  // pinned staging for small uploads
     int sm_count = 0;
+    uint32_t shard_index = 0, shard_count = 1;
     bvht_stats stats;
     std::string err;
 };
@@ -322,6 +327,14 @@ int bvht_create(int device, uint32_t flags, bvht_ctx** out) {
         ctx->stream = ctx->own_stream;
         ok = ensure(ctx, ctx->work_counter, 256) == BVHT_OK && ensure_pinned(ctx, 1 << 16) == BVHT_OK;
     }
+    if (ok) {
+        ok = cudaStreamCreateWithFlags(&ctx->aux[0], cudaStreamNonBlocking) == cudaSuccess
+          && cudaStreamCreateWithFlags(&ctx->aux[1], cudaStreamNonBlocking) == cudaSuccess
+          && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess
+          && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess
+          && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; ok && i < 64; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_band[i], cudaEventDisableTiming) == cudaSuccess;
+    }
     if (!ok) { cudaGetLastError(); bvht_destroy(ctx); return BVHT_ERR_CUDA; }
     ctx->stats.sm_count = (uint32_t)ctx->sm_count;
     ctx->stats.flags = flags;
@@ -335,8 +348,12 @@ void bvht_destroy(bvht_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (Blas& b : ctx->blas) free_blas(b);
-    for (DevBuf* d : { &ctx->blas_desc, &ctx->tlas, &ctx->inst_cols, &ctx->inst_blas, &ctx->work_counter, &ctx->out_buf, &ctx->rays_buf })
+    for (DevBuf* d : { &ctx->blas_desc, &ctx->tlas, &ctx->inst_cols, &ctx->inst_blas, &ctx->work_counter, &ctx->out_buf, &ctx->rays_buf,
+                       &ctx->rgba_buf })
         release(*d);
+    for (cudaStream_t st : { ctx->aux[0], ctx->aux[1], ctx->copy_stream }) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (cudaEvent_t ev : { ctx->ev_fork, ctx->ev_join }) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ctx->ev_band) if (ev) cudaEventDestroy(ev);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (cudaEvent_t ev : { ctx->ev_a, ctx->ev_b, ctx->ev_c, ctx->ev_d, ctx->ev_e, ctx->ev_f }) if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -568,22 +585,13 @@ int bvht_tlas_set(bvht_ctx* ctx, const bvht_tlas_node* nodes, uint32_t nodes_use
     return BVHT_OK;
 }
 
-int bvht_trace_primary_device(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height, uint32_t tile,
-                              bvht_rect region, void* out_device) {
-    if (!ctx) return BVHT_ERR_BAD_HANDLE;
-    if (!camera || !out_device) return fail(ctx, BVHT_ERR_INVALID_ARG, "null pointer argument");
-    if (tile == 0) tile = 8;
-    if (width == 0 || height == 0 || width > (1u << 24) || height > (1u << 24))
-        return fail(ctx, BVHT_ERR_INVALID_ARG, "image size %ux%u outside (0, 2^24]", width, height);
-    if (tile > 1024) return fail(ctx, BVHT_ERR_INVALID_ARG, "tile %u too large", tile);
-    region.x1 = std::min(region.x1, width); region.y1 = std::min(region.y1, height);
-    cudaSetDevice(ctx->device);
+// One persistent launch of K1 over `region` on `stream`, using work counter slot `slot`.
+static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvht_camera* camera, uint32_t width, uint32_t height,
+                                 uint32_t tile, bvht_rect region, const bvht_shade_params* shade, void* hits_device,
+                                 void* rgba_device, cudaStream_t stream, int slot, uint32_t shard_index = 0, uint32_t shard_count = 1) {
     PrimaryParams p;
     memset(&p, 0, sizeof p);
-    int rc = fill_scene(ctx, p.scene);
-    if (rc) return rc;
-    ctx->stats.last_trace_rays = 0;
-    if (region.x0 >= region.x1 || region.y0 >= region.y1) return BVHT_OK;     // empty region: nothing to do
+    p.scene = scene;
     memcpy(p.cam.tl, camera->top_left_eye, 12);
     memcpy(p.cam.tr, camera->top_right_eye, 12);
     memcpy(p.cam.bl, camera->bottom_left_eye, 12);
@@ -593,23 +601,158 @@ int bvht_trace_primary_device(bvht_ctx* ctx, const bvht_camera* camera, uint32_t
     p.tx0 = region.x0 / tile; p.ty0 = region.y0 / tile;
     p.ntx = (region.x1 + tile - 1) / tile - p.tx0;
     p.nty = (region.y1 + tile - 1) / tile - p.ty0;
+    p.row_stride = 1;
+    if (shard_count > 1) {
+        bvht_shard_tile_rows(region, tile, shard_index, shard_count, &p.ty0, &p.nty);
+        p.row_stride = shard_count;
+    }
     p.items_per_tile = (tile * tile + 31u) / 32u;
     uint64_t n_items = (uint64_t)p.ntx * p.nty * p.items_per_tile;
     if (n_items >= 0xFFFFFFFFull - (1ull << 20)) return fail(ctx, BVHT_ERR_INVALID_ARG, "too many work items");
+    if (n_items == 0) return BVHT_OK;
     p.n_items = (uint32_t)n_items;
-    p.out = (uint4*)out_device;
-    p.work_counter = (unsigned int*)ctx->work_counter.p;
+    p.out = (uint4*)hits_device;
+    p.out_rgba = (uint32_t*)rgba_device;
+    if (shade && rgba_device) {
+        p.shade_kind = shade->kind;
+        p.shade_scale = shade->depth_scale; p.shade_offset = shade->depth_offset;
+        memcpy(&p.hit_rgba, shade->hit_rgba, 4); memcpy(&p.miss_rgba, shade->miss_rgba, 4);
+    }
+    p.work_counter = (unsigned int*)ctx->work_counter.p + slot;
     int grid = persistent_grid(ctx, true, n_items);
-    CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, 4, ctx->stream));
-    cudaEventRecord(ctx->ev_a, ctx->stream);
-    cudaError_t e = fast_on(ctx) ? launch_primary_fast(p, accel_on(ctx), grid, kTraceBlock, ctx->stream)
-                                 : launch_primary_strict(p, accel_on(ctx), grid, kTraceBlock, ctx->stream);
-    cudaEventRecord(ctx->ev_b, ctx->stream);
+    cudaError_t e = fast_on(ctx) ? launch_primary_fast(p, accel_on(ctx), grid, kTraceBlock, stream)
+                                 : launch_primary_strict(p, accel_on(ctx), grid, kTraceBlock, stream);
     if (e != cudaSuccess) return fail(ctx, BVHT_ERR_CUDA, "trace_primary launch failed: %s", cudaGetErrorString(e));
-    ctx->trace_timed = true;
     ctx->stats.kernel_launches += 1;
     ctx->stats.trace_grid = (uint32_t)grid;
-    ctx->stats.last_trace_rays = (uint64_t)(region.x1 - region.x0) * (region.y1 - region.y0);
+    return BVHT_OK;
+}
+
+static int check_frame_args(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height, uint32_t& tile,
+                            bvht_rect& region) {
+    if (!camera) return fail(ctx, BVHT_ERR_INVALID_ARG, "null camera");
+    if (tile == 0) tile = 8;
+    if (width == 0 || height == 0 || width > (1u << 24) || height > (1u << 24))
+        return fail(ctx, BVHT_ERR_INVALID_ARG, "image size %ux%u outside (0, 2^24]", width, height);
+    if (tile > 1024) return fail(ctx, BVHT_ERR_INVALID_ARG, "tile %u too large", tile);
+    region.x1 = std::min(region.x1, width); region.y1 = std::min(region.y1, height);
+    return BVHT_OK;
+}
+
+int bvht_render_frame_device(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height, uint32_t tile,
+                             bvht_rect region, const bvht_shade_params* shade, void* frame_out_device, void* hits_out_device) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (!frame_out_device && !hits_out_device) return fail(ctx, BVHT_ERR_INVALID_ARG, "no output buffer");
+    if (frame_out_device && (!shade || shade->kind == BVHT_SHADE_NONE || shade->kind > BVHT_SHADE_UV))
+        return fail(ctx, BVHT_ERR_INVALID_ARG, "frame output requested without a valid shade kind");
+    int rc = check_frame_args(ctx, camera, width, height, tile, region);
+    if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    SceneDev scene;
+    if ((rc = fill_scene(ctx, scene))) return rc;
+    ctx->stats.last_trace_rays = 0;
+    if (region.x0 >= region.x1 || region.y0 >= region.y1) return BVHT_OK;     // empty region: nothing to do
+    CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, 4, ctx->stream));
+    cudaEventRecord(ctx->ev_a, ctx->stream);
+    rc = launch_primary_region(ctx, scene, camera, width, height, tile, region, shade, hits_out_device, frame_out_device,
+                               ctx->stream, 0, ctx->shard_index, ctx->shard_count);
+    cudaEventRecord(ctx->ev_b, ctx->stream);
+    if (rc) return rc;
+    ctx->trace_timed = true;
+    ctx->stats.last_trace_rays = (uint64_t)(region.x1 - region.x0) * (region.y1 - region.y0) / ctx->shard_count;
+    return BVHT_OK;
+}
+
+int bvht_shard_tile_rows(bvht_rect region, uint32_t tile, uint32_t shard_index, uint32_t shard_count, uint32_t* first_row,
+                         uint32_t* n_rows) {
+    if (!first_row || !n_rows || tile == 0 || shard_count == 0 || shard_index >= shard_count) return BVHT_ERR_INVALID_ARG;
+    // own the tile rows r with r % shard_count == shard_index (global tile-row numbering)
+    uint32_t ty0 = region.y0 / tile, ty_end = region.y1 > region.y0 ? (region.y1 + tile - 1) / tile : ty0;
+    uint32_t first = ty0 + ((shard_index + shard_count - ty0 % shard_count) % shard_count);
+    *first_row = first;
+    *n_rows = first < ty_end ? (ty_end - first + shard_count - 1) / shard_count : 0;
+    return BVHT_OK;
+}
+
+int bvht_set_shard(bvht_ctx* ctx, uint32_t shard_index, uint32_t shard_count) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (shard_count == 0 || shard_index >= shard_count) return fail(ctx, BVHT_ERR_INVALID_ARG, "shard %u of %u", shard_index, shard_count);
+    ctx->shard_index = shard_index; ctx->shard_count = shard_count;
+    return BVHT_OK;
+}
+
+int bvht_trace_primary_device(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height, uint32_t tile,
+                              bvht_rect region, void* out_device) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (!out_device) return fail(ctx, BVHT_ERR_INVALID_ARG, "null pointer argument");
+    return bvht_render_frame_device(ctx, camera, width, height, tile, region, nullptr, nullptr, out_device);
+}
+
+// D2H of the rows [y0, y1) x [x0, x1) of a width-pitched buffer of `elem` byte pixels.
+static int copy_rows_d2h(bvht_ctx* ctx, void* host, const void* dev, uint32_t width, bvht_rect r, size_t elem, cudaStream_t st) {
+    size_t row = (size_t)width * elem;
+    if (r.x0 == 0 && r.x1 == width) {
+        size_t off = (size_t)r.y0 * row, len = (size_t)(r.y1 - r.y0) * row;
+        CU(ctx, cudaMemcpyAsync((char*)host + off, (const char*)dev + off, len, cudaMemcpyDeviceToHost, st));
+        ctx->stats.d2h_bytes += len;
+    } else {
+        size_t off = (size_t)r.y0 * row + (size_t)r.x0 * elem;
+        size_t wbytes = (size_t)(r.x1 - r.x0) * elem;
+        CU(ctx, cudaMemcpy2DAsync((char*)host + off, row, (const char*)dev + off, row, wbytes, r.y1 - r.y0,
+                                  cudaMemcpyDeviceToHost, st));
+        ctx->stats.d2h_bytes += wbytes * (r.y1 - r.y0);
+    }
+    return BVHT_OK;
+}
+
+int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height, uint32_t tile,
+                      bvht_rect region, const bvht_shade_params* shade, uint32_t* frame_out_host, bvht_hit* hits_out_host) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (!frame_out_host && !hits_out_host) return fail(ctx, BVHT_ERR_INVALID_ARG, "no output buffer");
+    if (frame_out_host && (!shade || shade->kind == BVHT_SHADE_NONE || shade->kind > BVHT_SHADE_UV))
+        return fail(ctx, BVHT_ERR_INVALID_ARG, "frame output requested without a valid shade kind");
+    int rc = check_frame_args(ctx, camera, width, height, tile, region);
+    if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    SceneDev scene;
+    if ((rc = fill_scene(ctx, scene))) return rc;
+    ctx->stats.last_trace_rays = 0;
+    if (region.x0 >= region.x1 || region.y0 >= region.y1) return BVHT_OK;
+    size_t npix = (size_t)width * height;
+    if (frame_out_host && (rc = ensure(ctx, ctx->rgba_buf, npix * 4))) return rc;
+    if (hits_out_host && (rc = ensure(ctx, ctx->out_buf, npix * sizeof(bvht_hit)))) return rc;
+    void* d_rgba = frame_out_host ? ctx->rgba_buf.p : nullptr;
+    void* d_hits = hits_out_host ? ctx->out_buf.p : nullptr;
+
+    // bands of whole tile rows, ~1 M rays each, at most 16 (and at most 64 counter slots)
+    uint32_t ty0 = region.y0 / tile, ty1 = (region.y1 + tile - 1) / tile;
+    uint32_t tile_rows = ty1 - ty0;
+    uint64_t rays = (uint64_t)(region.x1 - region.x0) * (region.y1 - region.y0);
+    uint32_t n_bands = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(rays / (1u << 20), 1), 16);
+    n_bands = std::min(n_bands, tile_rows);
+    CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, 256, ctx->stream));
+    cudaEventRecord(ctx->ev_a, ctx->stream);
+    CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    for (int i = 0; i < 2; ++i) CU(ctx, cudaStreamWaitEvent(ctx->aux[i], ctx->ev_fork, 0));
+    CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
+    for (uint32_t b = 0; b < n_bands; ++b) {
+        uint32_t r0 = ty0 + (uint32_t)((uint64_t)tile_rows * b / n_bands);
+        uint32_t r1 = ty0 + (uint32_t)((uint64_t)tile_rows * (b + 1) / n_bands);
+        bvht_rect band = { region.x0, std::max(region.y0, r0 * tile), region.x1, std::min(region.y1, r1 * tile) };
+        if (band.y0 >= band.y1) continue;
+        cudaStream_t cs = ctx->aux[b & 1];
+        if ((rc = launch_primary_region(ctx, scene, camera, width, height, tile, band, shade, d_hits, d_rgba, cs, (int)b))) return rc;
+        CU(ctx, cudaEventRecord(ctx->ev_band[b], cs));
+        CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[b], 0));
+        if (frame_out_host && (rc = copy_rows_d2h(ctx, frame_out_host, d_rgba, width, band, 4, ctx->copy_stream))) return rc;
+        if (hits_out_host && (rc = copy_rows_d2h(ctx, hits_out_host, d_hits, width, band, sizeof(bvht_hit), ctx->copy_stream))) return rc;
+    }
+    CU(ctx, cudaEventRecord(ctx->ev_join, ctx->copy_stream));
+    CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    cudaEventRecord(ctx->ev_b, ctx->stream);
+    ctx->trace_timed = true;
+    ctx->stats.last_trace_rays = rays;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
     return BVHT_OK;
 }
 
@@ -617,30 +760,7 @@ int bvht_trace_primary(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width,
                        bvht_rect region, bvht_hit* out_host) {
     if (!ctx) return BVHT_ERR_BAD_HANDLE;
     if (!out_host) return fail(ctx, BVHT_ERR_INVALID_ARG, "null output pointer");
-    cudaSetDevice(ctx->device);
-    size_t bytes = (size_t)width * height * sizeof(bvht_hit);
-    int rc = ensure(ctx, ctx->out_buf, bytes);
-    if (rc) return rc;
-    rc = bvht_trace_primary_device(ctx, camera, width, height, tile, region, ctx->out_buf.p);
-    if (rc) return rc;
-    region.x1 = std::min(region.x1, width); region.y1 = std::min(region.y1, height);
-    if (region.x0 < region.x1 && region.y0 < region.y1) {
-        // only the region's rows travel back (full rows when the region spans the width, else a 2-D copy)
-        size_t row = (size_t)width * sizeof(bvht_hit);
-        if (region.x0 == 0 && region.x1 == width) {
-            size_t off = (size_t)region.y0 * row, len = (size_t)(region.y1 - region.y0) * row;
-            CU(ctx, cudaMemcpyAsync((char*)out_host + off, (char*)ctx->out_buf.p + off, len, cudaMemcpyDeviceToHost, ctx->stream));
-            ctx->stats.d2h_bytes += len;
-        } else {
-            size_t off = (size_t)region.y0 * row + (size_t)region.x0 * sizeof(bvht_hit);
-            size_t wbytes = (size_t)(region.x1 - region.x0) * sizeof(bvht_hit);
-            CU(ctx, cudaMemcpy2DAsync((char*)out_host + off, row, (char*)ctx->out_buf.p + off, row, wbytes,
-                                      region.y1 - region.y0, cudaMemcpyDeviceToHost, ctx->stream));
-            ctx->stats.d2h_bytes += wbytes * (region.y1 - region.y0);
-        }
-    }
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    return BVHT_OK;
+    return bvht_render_frame(ctx, camera, width, height, tile, region, nullptr, nullptr, out_host);
 }
 
 int bvht_trace_rays_device(bvht_ctx* ctx, const void* rays_device, uint64_t n, void* out_device) {
@@ -698,6 +818,22 @@ int bvht_device_free(bvht_ctx* ctx, void* device_ptr) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     CU(ctx, cudaFree(device_ptr));
+    return BVHT_OK;
+}
+
+int bvht_host_alloc(bvht_ctx* ctx, size_t bytes, void** out_host) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (!out_host) return fail(ctx, BVHT_ERR_INVALID_ARG, "null pointer argument");
+    cudaSetDevice(ctx->device);
+    CU(ctx, cudaMallocHost(out_host, bytes ? bytes : 16));
+    return BVHT_OK;
+}
+
+int bvht_host_free(bvht_ctx* ctx, void* host_ptr) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    CU(ctx, cudaFreeHost(host_ptr));
     return BVHT_OK;
 }
 

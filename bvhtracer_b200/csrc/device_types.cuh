@@ -53,10 +53,15 @@ struct PrimaryParams {
     CameraDev cam;
     uint32_t  width, height, tile;
     uint32_t  x0, y0, x1, y1;            // pixel region
-    uint32_t  tx0, ty0, ntx, nty;        // tile range covering the region
+    uint32_t  tx0, ty0, ntx, nty;        // tile range covering the region (nty counts only this shard's tile rows)
+    uint32_t  row_stride;                // tile-row interleave across GPUs: this launch owns rows ty0 + k * row_stride
     uint32_t  items_per_tile;            // ceil(tile*tile / 32)
     uint32_t  n_items;                   // ntx * nty * items_per_tile
-    uint4*    out;                       // width*height hit records (16 B each)
+    uint4*    out;                       // width*height hit records (16 B each); may be null when out_rgba is set
+    uint32_t* out_rgba;                  // width*height Rgba<u8> pixels (fused accumulator + pixel shader); may be null
+    uint32_t  shade_kind;                // bvht_shade_kind
+    float     shade_scale, shade_offset; // DepthMappingShader::new(scale, offset)
+    uint32_t  hit_rgba, miss_rgba;       // IntersectionShader::new(hit, miss), packed r | g<<8 | b<<16 | a<<24
     unsigned int* work_counter;          // persistent-thread work cursor
 };
 

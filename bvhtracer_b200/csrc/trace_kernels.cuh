@@ -336,6 +336,35 @@ __device__ __forceinline__ RayM primary_ray(const CameraDev& C, uint32_t px, uin
     return w;
 }
 
+// Fused accumulator + pixel shader (renderer.rs:116-245): what the examples turn a hit into.
+//   kind 1: DepthAccumulator (:184-194) + DepthMappingShader (:207-222)   two/sixteen_armadillos
+//   kind 2: IntersectionAccumulator (:145-153) + IntersectionShader (:166-174)   big_ben_clock
+//   kind 3: UvMappingAccumulator (:233-245) + RadianceToRgbShader (:124-132)
+// Integer tricks are kept: `as i32` / `as u8` are saturating casts (NaN -> 0), u32 arithmetic wraps.
+__device__ __forceinline__ uint32_t shade_pixel(const PrimaryParams& P, const HitRec& h) {
+    const bool hit = h.id != 0xFFFFFFFFu;
+    if (P.shade_kind == 1u) {
+        float nearest_t = hit ? h.t : FLT_MAX;
+        if (nearest_t < FLT_MAX) {
+            int xi = __float2int_rz((nearest_t - P.shade_offset) * P.shade_scale);   // `as i32`
+            uint32_t color = 255u - (uint32_t)xi;
+            uint32_t c = color * 0x010101u;
+            uint32_t r = (c & 0x00FF0000u) >> 16, g = (c & 0x0000FF00u) >> 8, b = c & 0x000000FFu;
+            return r | (g << 8) | (b << 16) | 0xFF000000u;
+        }
+        return 0xFF000000u;                                                          // Rgba::new(0, 0, 0, 255)
+    }
+    if (P.shade_kind == 2u) return hit ? P.hit_rgba : P.miss_rgba;
+    if (P.shade_kind == 3u) {
+        float rx = hit ? h.u : 0.0f, ry = hit ? h.v : 0.0f, rz = hit ? 1.0f - (h.u + h.v) : 0.0f;
+        uint32_t r = min(255u, __float2uint_rz(255.0f * rx));
+        uint32_t g = min(255u, __float2uint_rz(255.0f * ry));
+        uint32_t b = min(255u, __float2uint_rz(255.0f * rz));
+        return r | (g << 8) | (b << 16) | 0xFF000000u;
+    }
+    return 0u;
+}
+
 // K1: persistent, tile-pulling primary closest-hit kernel.
 template <bool ACCEL>
 __global__ void __launch_bounds__(256)
@@ -349,7 +378,7 @@ trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
         uint32_t tile_idx = item / P.items_per_tile;
         uint32_t sub = item - tile_idx * P.items_per_tile;
         uint32_t tx = P.tx0 + tile_idx % P.ntx;
-        uint32_t ty = P.ty0 + tile_idx / P.ntx;
+        uint32_t ty = P.ty0 + (tile_idx / P.ntx) * P.row_stride;
         uint32_t p = sub * 32u + lane;                 // pixel within the tile, row-major (renderer.rs:356-357)
         uint32_t iu = p % P.tile, iv = p / P.tile;
         uint32_t px = tx * P.tile + iu, py = ty * P.tile + iv;
@@ -357,9 +386,12 @@ trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
         if (active) {
             RayM w = primary_ray(P.cam, px, py, P.width, P.height);
             HitRec h = scene_intersect<ACCEL>(P.scene, w, FLT_MAX);
-            uint4 o;
-            o.x = __float_as_uint(h.t); o.y = __float_as_uint(h.u); o.z = __float_as_uint(h.v); o.w = h.id;
-            P.out[(size_t)py * P.width + px] = o;
+            if (P.out) {
+                uint4 o;
+                o.x = __float_as_uint(h.t); o.y = __float_as_uint(h.u); o.z = __float_as_uint(h.v); o.w = h.id;
+                P.out[(size_t)py * P.width + px] = o;
+            }
+            if (P.out_rgba) P.out_rgba[(size_t)py * P.width + px] = shade_pixel(P, h);
         }
     }
 }

@@ -4,7 +4,7 @@ import ctypes as C
 import numpy as np
 
 from . import _ffi
-from ._ffi import BVH_NODE, CAMERA, HIT, INSTANCE, RAY, TLAS_NODE, BvhtError, Rect, Stats, ptr
+from ._ffi import BVH_NODE, CAMERA, HIT, INSTANCE, RAY, TLAS_NODE, BvhtError, Rect, ShadeParams, Stats, ptr
 
 
 class Engine:
@@ -17,10 +17,21 @@ class Engine:
         self.flags = int(flags)
         self.device = int(device)
 
+    @classmethod
+    def from_handle(cls, ctx_handle, flags=0, device=0):
+        """Non-owning view of a bvht_ctx created elsewhere (e.g. by the C++ CudaPathTracer)."""
+        self = cls.__new__(cls)
+        self._lib = _ffi.load()
+        self._ctx = C.c_void_p(ctx_handle)
+        self._borrowed = True
+        self.flags, self.device = int(flags), int(device)
+        return self
+
     # ------------------------------------------------------------------ lifecycle
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx:
-            self._lib.bvht_destroy(self._ctx)
+            if not getattr(self, "_borrowed", False):
+                self._lib.bvht_destroy(self._ctx)
             self._ctx = None
 
     def __del__(self):
@@ -41,6 +52,10 @@ class Engine:
 
     def set_stream(self, cuda_stream_handle):
         self._check(self._lib.bvht_set_stream(self._ctx, C.c_void_p(cuda_stream_handle or 0)))
+
+    def set_shard(self, index, count):
+        """Only tile rows r with r % count == index are traced by the *_device entry points (multi-GPU)."""
+        self._check(self._lib.bvht_set_shard(self._ctx, int(index), int(count)))
 
     def sync(self):
         self._check(self._lib.bvht_sync(self._ctx))
@@ -101,6 +116,42 @@ class Engine:
         self._check(self._lib.bvht_trace_primary_device(self._ctx, ptr(camera), int(width), int(height), int(tile),
                                                         Rect(x0, y0, x1, y1), C.c_void_p(out_device_ptr)))
 
+    @staticmethod
+    def shade_depth(scale=80.0, offset=3.0):
+        """DepthAccumulator + DepthMappingShader::new(scale, offset) (two/sixteen_armadillos.rs main)."""
+        return ShadeParams(_ffi.SHADE_DEPTH, scale, offset, (C.c_uint8 * 4)(0, 0, 0, 0), (C.c_uint8 * 4)(0, 0, 0, 0))
+
+    @staticmethod
+    def shade_intersection(hit=(255, 255, 255, 255), miss=(0, 0, 0, 255)):
+        """IntersectionAccumulator + IntersectionShader::new(hit, miss) (big_ben_clock.rs main)."""
+        return ShadeParams(_ffi.SHADE_INTERSECTION, 0.0, 0.0, (C.c_uint8 * 4)(*hit), (C.c_uint8 * 4)(*miss))
+
+    @staticmethod
+    def shade_uv():
+        """UvMappingAccumulator + RadianceToRgbShader."""
+        return ShadeParams(_ffi.SHADE_UV, 0.0, 0.0, (C.c_uint8 * 4)(0, 0, 0, 0), (C.c_uint8 * 4)(0, 0, 0, 0))
+
+    def render_frame(self, camera, width, height, shade, tile=8, region=None, frame_out=None, hits_out=None, want_hits=False):
+        """Integrator::evaluate: -> (frame u32[w*h] Rgba<u8>, hits or None); host buffers (pinned ones overlap copies)."""
+        camera = np.ascontiguousarray(camera)
+        if frame_out is None and shade is not None:
+            frame_out = np.zeros(width * height, "<u4")
+        if hits_out is None and want_hits:
+            hits_out = np.zeros(width * height, HIT)
+        x0, y0, x1, y1 = region if region is not None else (0, 0, width, height)
+        self._check(self._lib.bvht_render_frame(
+            self._ctx, ptr(camera), int(width), int(height), int(tile), Rect(x0, y0, x1, y1),
+            C.byref(shade) if shade is not None else None,
+            ptr(frame_out) if frame_out is not None else None, ptr(hits_out) if hits_out is not None else None))
+        return frame_out, hits_out
+
+    def render_frame_device(self, camera, width, height, shade, tile, region, frame_dptr, hits_dptr):
+        camera = np.ascontiguousarray(camera)
+        x0, y0, x1, y1 = region if region is not None else (0, 0, width, height)
+        self._check(self._lib.bvht_render_frame_device(
+            self._ctx, ptr(camera), int(width), int(height), int(tile), Rect(x0, y0, x1, y1),
+            C.byref(shade) if shade is not None else None, C.c_void_p(frame_dptr or 0), C.c_void_p(hits_dptr or 0)))
+
     def trace_rays(self, rays):
         rays = np.ascontiguousarray(rays)
         if rays.dtype != RAY:
@@ -120,6 +171,22 @@ class Engine:
 
     def device_free(self, dptr):
         self._check(self._lib.bvht_device_free(self._ctx, C.c_void_p(dptr)))
+
+    def pinned_array(self, shape, dtype):
+        """numpy array over page-locked host memory (bvht_host_alloc); freed with free_pinned(array)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        self._check(self._lib.bvht_host_alloc(self._ctx, max(n, 16), C.byref(p)))
+        buf = (C.c_uint8 * max(n, 16)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.uint8, count=n).view(dtype).reshape(shape)
+        self._pinned = getattr(self, "_pinned", {})
+        self._pinned[arr.ctypes.data] = p.value
+        return arr
+
+    def free_pinned(self, arr):
+        p = self._pinned.pop(arr.ctypes.data)
+        self._check(self._lib.bvht_host_free(self._ctx, C.c_void_p(p)))
 
     def memcpy_h2d(self, dptr, host_array):
         host_array = np.ascontiguousarray(host_array)

@@ -110,6 +110,23 @@ typedef struct {
 
 typedef struct { uint32_t x0, y0, x1, y1; } bvht_rect;   /* pixels [x0,x1) x [y0,y1) */
 
+/* Accumulator + PixelShader pairs of the reference (renderer.rs:116-245), evaluated on the device right
+ * after the closest hit is known, producing `Rgba<u8>` pixels (r, g, b, a bytes; 4 B/pixel). */
+typedef enum {
+    BVHT_SHADE_NONE = 0,
+    BVHT_SHADE_DEPTH = 1,          /* DepthAccumulator (:184-194) + DepthMappingShader::new(scale, offset) (:207-222) */
+    BVHT_SHADE_INTERSECTION = 2,   /* IntersectionAccumulator (:145-153) + IntersectionShader::new(hit, miss) (:166-174) */
+    BVHT_SHADE_UV = 3              /* UvMappingAccumulator (:233-245) + RadianceToRgbShader (:124-132) */
+} bvht_shade_kind;
+
+typedef struct {
+    uint32_t kind;                 /* bvht_shade_kind */
+    float    depth_scale;          /* DepthMappingShader.scale  (80 in the armadillo examples) */
+    float    depth_offset;         /* DepthMappingShader.offset ( 3 in the armadillo examples) */
+    uint8_t  hit_rgba[4];          /* IntersectionShader.hit_value  */
+    uint8_t  miss_rgba[4];         /* IntersectionShader.miss_value */
+} bvht_shade_params;
+
 typedef struct {
     float    last_trace_ms;          /* device time of the last trace kernel (CUDA events on the ctx stream) */
     float    last_refit_ms;
@@ -172,6 +189,30 @@ BVHT_API int         bvht_trace_primary(bvht_ctx* ctx, const bvht_camera* camera
 BVHT_API int         bvht_trace_primary_device(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height,
                                       uint32_t tile, bvht_rect region, void* out_device);
 
+/* Integrator::evaluate as a whole (renderer.rs:345-384): trace the region AND run the accumulator + pixel
+ * shader pair on the device, returning the `FrameBuffer<Rgba<u8>>` pixels (frame_out_host: width*height
+ * u32, row-major, NOT vertically flipped -- the flip for GL is done by the caller, bvhtracer_demos lib.rs:114)
+ * and, when hits_out_host is not NULL, the 16-byte hit records as well.  The region is cut into bands of
+ * tile rows; each band's device->host copy overlaps the tracing of the next band (give pinned host memory,
+ * e.g. from bvht_host_alloc, for the overlap to be real).  Returns when the host buffers are filled. */
+BVHT_API int         bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height,
+                               uint32_t tile, bvht_rect region, const bvht_shade_params* shade,
+                               uint32_t* frame_out_host, bvht_hit* hits_out_host);
+/* Same, everything left in device memory (either output may be NULL).  Asynchronous, single launch. */
+BVHT_API int         bvht_render_frame_device(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height,
+                                      uint32_t tile, bvht_rect region, const bvht_shade_params* shade,
+                                      void* frame_out_device, void* hits_out_device);
+
+/* Multi-GPU sharding (scene replicated per GPU, image tiles sharded): after bvht_set_shard(ctx, i, n) the
+ * *_device entry points above only trace the tile rows r with r % n == i (interleaved for load balance) and
+ * leave every other pixel untouched, so n contexts on n GPUs writing into ONE frame buffer (rank 0's, mapped
+ * on the peers with bvht_ipc_open) assemble the frame over NVLink with no copy.  (0, 1) restores the default. */
+BVHT_API int         bvht_set_shard(bvht_ctx* ctx, uint32_t shard_index, uint32_t shard_count);
+/* Pure host helper (no device needed): which tile rows of `region` shard i of n owns -- rows
+ * first_row, first_row + n, ... (n_rows of them).  The same function the launches use. */
+BVHT_API int         bvht_shard_tile_rows(bvht_rect region, uint32_t tile, uint32_t shard_index, uint32_t shard_count,
+                                  uint32_t* first_row, uint32_t* n_rows);
+
 /* Scene::intersect(&Ray) for n arbitrary rays (scene.rs:32-34). */
 BVHT_API int         bvht_trace_rays(bvht_ctx* ctx, const bvht_ray* rays, uint64_t n, bvht_hit* out_host);
 BVHT_API int         bvht_trace_rays_device(bvht_ctx* ctx, const void* rays_device, uint64_t n, void* out_device);
@@ -179,6 +220,9 @@ BVHT_API int         bvht_trace_rays_device(bvht_ctx* ctx, const void* rays_devi
 /* Device memory helpers (multi-GPU gather, resident benchmarks). */
 BVHT_API int         bvht_device_alloc(bvht_ctx* ctx, size_t bytes, void** out_device);
 BVHT_API int         bvht_device_free(bvht_ctx* ctx, void* device_ptr);
+/* Page-locked host memory (so that copies overlap with kernels). */
+BVHT_API int         bvht_host_alloc(bvht_ctx* ctx, size_t bytes, void** out_host);
+BVHT_API int         bvht_host_free(bvht_ctx* ctx, void* host_ptr);
 BVHT_API int         bvht_memcpy_h2d(bvht_ctx* ctx, void* dst_device, const void* src_host, size_t bytes);
 BVHT_API int         bvht_memcpy_d2h(bvht_ctx* ctx, void* dst_host, const void* src_device, size_t bytes);
 /* CUDA IPC: export a device allocation so another process (one rank per GPU) can map it over NVLink P2P */

@@ -916,3 +916,52 @@ void orc_trace_rays(const orc_scene* s, const float* odt, uint64_t n, orc_hit* h
     j.s = s; j.odt = odt; j.hits = hits; j.n_items = (int64_t)n; j.chunk = 256;
     job_execute(&j, n_threads, counters);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * accumulators + pixel shaders (renderer.rs:116-245)
+ * ------------------------------------------------------------------------------------------ */
+/* Rust `f32 as i32`: saturating, NaN -> 0 */
+static int32_t f32_as_i32(float x) {
+    if (x != x) return 0;
+    if (x >= 2147483648.0f) return INT32_MAX;
+    if (x <= -2147483648.0f) return INT32_MIN;
+    return (int32_t)x;
+}
+/* Rust `f32 as u8`: saturating, NaN -> 0 */
+static uint32_t f32_as_u8(float x) {
+    if (x != x) return 0;
+    if (x >= 255.0f) return 255;
+    if (x <= 0.0f) return 0;
+    return (uint32_t)x;
+}
+
+void orc_shade(uint32_t kind, float scale, float offset, uint32_t hit_rgba, uint32_t miss_rgba,
+               const orc_hit* hits, uint64_t n, uint32_t* rgba_out) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const orc_hit* h = &hits[i];
+        int hit = h->id != 0xFFFFFFFFu;
+        uint32_t px = 0;
+        if (kind == 1) {
+            /* DepthAccumulator: radiance = from_fill(t or f32::MAX) (:184-194); DepthMappingShader (:207-222) */
+            float nearest_t = hit ? h->t : FLT_MAX;
+            if (nearest_t < FLT_MAX) {
+                uint32_t color = 255u - (uint32_t)f32_as_i32((nearest_t - offset) * scale);   /* wrapping u32 */
+                uint32_t c = color * 0x010101u;
+                uint32_t r = (c & 0x00FF0000u) >> 16, g = (c & 0x0000FF00u) >> 8, b = c & 0x000000FFu;
+                px = r | (g << 8) | (b << 16) | 0xFF000000u;
+            } else {
+                px = 0xFF000000u;
+            }
+        } else if (kind == 2) {
+            /* IntersectionAccumulator (:145-153) + IntersectionShader (:166-174), hit/miss radiance non-zero/zero */
+            px = hit ? hit_rgba : miss_rgba;
+        } else if (kind == 3) {
+            /* UvMappingAccumulator (:233-245) + RadianceToRgbShader (:124-132) */
+            float rx = hit ? h->u : 0.0f, ry = hit ? h->v : 0.0f, rz = hit ? 1.0f - (h->u + h->v) : 0.0f;
+            uint32_t r = f32_as_u8(255.0f * rx), g = f32_as_u8(255.0f * ry), b = f32_as_u8(255.0f * rz);
+            if (r > 255) r = 255; if (g > 255) g = 255; if (b > 255) b = 255;
+            px = r | (g << 8) | (b << 16) | 0xFF000000u;
+        }
+        rgba_out[i] = px;
+    }
+}

@@ -154,6 +154,12 @@ void orc_render(const orc_scene* s, const orc_camera* cam, uint32_t width, uint3
 void orc_trace_rays(const orc_scene* s, const float* o_d_t /* n x 7 */, uint64_t n, orc_hit* hits,
                     orc_counters* counters, int n_threads);
 
+/* ---- accumulator + pixel shader pairs (renderer.rs:116-245) applied to hit records.
+ * kind 1: DepthAccumulator + DepthMappingShader(scale, offset); 2: IntersectionAccumulator + IntersectionShader(hit, miss);
+ * 3: UvMappingAccumulator + RadianceToRgbShader.  rgba_out: r | g<<8 | b<<16 | a<<24 (Rgba<u8> byte order). */
+void orc_shade(uint32_t kind, float scale, float offset, uint32_t hit_rgba, uint32_t miss_rgba,
+               const orc_hit* hits, uint64_t n, uint32_t* rgba_out);
+
 int  orc_max_threads(void);
 
 #ifdef __cplusplus

@@ -312,3 +312,12 @@ class Scene:
 
 def max_threads():
     return int(lib().orc_max_threads())
+
+
+def shade(kind, hits, scale=80.0, offset=3.0, hit_rgba=0xFFFFFFFF, miss_rgba=0xFF000000):
+    """Accumulator + PixelShader pair applied to hit records -> u32 Rgba<u8> pixels (renderer.rs:116-245)."""
+    hits = np.ascontiguousarray(hits)
+    out = np.zeros(hits.size, "<u4")
+    lib().orc_shade(C.c_uint32(kind), C.c_float(scale), C.c_float(offset), C.c_uint32(hit_rgba), C.c_uint32(miss_rgba),
+                    _p(hits), C.c_uint64(hits.size), _p(out))
+    return out

@@ -310,3 +310,133 @@ def test_errors_are_codes_not_crashes():
         # the context is still usable after every error
         got = eng.trace_primary(SB.to_ffi_camera(cam), 64, 64)
         assert got.tobytes() == scene.render(cam, 64, 64).tobytes()
+
+
+# ------------------------------------------------------------------------------------------ f1: fused shading
+@pytest.mark.parametrize("kind", ["depth", "intersection", "uv"])
+def test_render_frame_shaders_match_oracle(kind):
+    # renderer.rs:116-245 accumulator + pixel shader pairs, fused into the trace kernel's epilogue
+    scene, cam = SB.oracle_scene(examples.sixteen_armadillos(9))
+    w, h = 320, 184
+    ref_hits = scene.render(cam, w, h, threads=NTHREADS)
+    with Engine(flags=FLAG_LEAF_ACCEL) as eng:
+        SB.upload_scene(eng, scene)
+        if kind == "depth":
+            shade, ref = eng.shade_depth(80.0, 3.0), O.shade(1, ref_hits, 80.0, 3.0)
+        elif kind == "intersection":
+            shade, ref = eng.shade_intersection((255, 200, 10, 255), (1, 2, 3, 255)), \
+                O.shade(2, ref_hits, hit_rgba=0xFF0AC8FF, miss_rgba=0xFF030201)
+        else:
+            shade, ref = eng.shade_uv(), O.shade(3, ref_hits)
+        frame, hits = eng.render_frame(SB.to_ffi_camera(cam), w, h, shade, want_hits=True)
+        assert hits.tobytes() == ref_hits.tobytes()
+        assert frame.tobytes() == ref.tobytes()
+        assert len(np.unique(frame)) > 2
+        # frame only (no hit records travel), pinned destination, sub-region
+        pinned = eng.pinned_array(w * h, "<u4")
+        pinned[:] = 0
+        eng.render_frame(SB.to_ffi_camera(cam), w, h, shade, frame_out=pinned, region=(0, 8, w, 96))
+        exp = np.zeros(w * h, "<u4")
+        exp.reshape(h, w)[8:96] = ref.reshape(h, w)[8:96]
+        assert pinned.tobytes() == exp.tobytes()
+        eng.free_pinned(pinned)
+
+
+def test_render_frame_bands_full_size_equal_single_launch():
+    # 4K frame: the banded, copy-overlapped host path must equal the single-launch device path
+    scene, cam = SB.oracle_scene(examples.sixteen_armadillos(2))
+    w, h = 3840, 2160
+    with Engine(flags=FLAG_LEAF_ACCEL) as eng:
+        SB.upload_scene(eng, scene)
+        shade = eng.shade_depth()
+        frame, hits = eng.render_frame(SB.to_ffi_camera(cam), w, h, shade, want_hits=True)
+        dh = eng.device_alloc(w * h * 16)
+        df = eng.device_alloc(w * h * 4)
+        eng.render_frame_device(SB.to_ffi_camera(cam), w, h, shade, 8, None, df, dh)
+        eng.sync()
+        h2 = eng.memcpy_d2h(np.zeros(w * h, _ffi.HIT), dh)
+        f2 = eng.memcpy_d2h(np.zeros(w * h, "<u4"), df)
+        eng.device_free(dh); eng.device_free(df)
+    assert hits.tobytes() == h2.tobytes() and frame.tobytes() == f2.tobytes()
+    assert np.array_equal(frame, O.shade(1, hits))
+
+
+# ------------------------------------------------------------------------------------------ through the host mirror
+def test_host_mirror_renderer_animated_frames():
+    # Renderer::new(Box::new(CudaPathTracer::new())) + AppState::update loop of sixteen_armadillos.rs:132-163
+    from bvhtracer_b200 import host
+    anim = examples.GridAnimation()
+    scene, models = host.build_scene(examples.sixteen_armadillos(0))
+    renderer = host.Renderer(flags=FLAG_STRICT | FLAG_LEAF_ACCEL)
+    w, h = 320, 176
+    state = host.RendererState(host.depth_pipeline(80.0, 3.0), w, h, keep_hits=True)
+    for frame in range(4):
+        if frame > 0:
+            anim.update()
+            for i, o in enumerate(anim.objects()):
+                scene.set_transform(i, host.object_transform(o))
+            scene.rebuild()
+        assert renderer.render(state, scene) == w * h                 # rays traced, like PathTracer::evaluate
+        ref_scene, ref_cam = SB.oracle_scene(examples.sixteen_armadillos(frame))
+        ref = ref_scene.render(ref_cam, w, h, threads=NTHREADS)
+        assert state.hits().tobytes() == ref.tobytes()
+        assert state.frame_buffer().tobytes() == O.shade(1, ref).tobytes()
+
+
+def test_host_mirror_big_ben_refit_and_scene_intersect():
+    # big_ben_clock.rs:67-103: animate() + ModelInstance::refit(), IntersectionAccumulator + IntersectionShader
+    from bvhtracer_b200 import host
+    scene, models = host.build_scene(examples.big_ben_clock())
+    ref_blas = O.Blas(O.load_asset("bigben.tri"))
+    ref_scene = O.Scene([ref_blas], [(0, O.mat4_identity())], with_transform=False)
+    _, ref_cam = SB.oracle_scene(examples.big_ben_clock())
+    anim = examples.BigBenAnimation(models[0].primitives())
+    renderer = host.Renderer(flags=FLAG_STRICT | FLAG_LEAF_ACCEL)
+    w, h = 256, 144
+    state = host.RendererState(host.intersection_pipeline((255, 255, 255, 255), (0, 0, 0, 255)), w, h, keep_hits=True)
+    for frame in range(3):
+        verts = anim.animate()
+        models[0].set_primitives(verts)
+        models[0].refit()
+        ref_blas.tris[:] = verts
+        ref_blas.refit()
+        ref_scene.refresh_blas()
+        renderer.render(state, scene)
+        nodes, used = models[0].nodes()                               # refitted boxes read back into the host Bvh
+        assert np.array_equal(nodes["aabb_min"][:used], ref_blas.nodes["min"][:used])
+        assert np.array_equal(nodes["aabb_max"][:used], ref_blas.nodes["max"][:used])
+        ref = ref_scene.render(ref_cam, w, h, threads=NTHREADS)
+        assert state.hits().tobytes() == ref.tobytes()
+        assert state.frame_buffer().tobytes() == O.shade(2, ref, hit_rgba=0xFFFFFFFF, miss_rgba=0xFF000000).tobytes()
+    # Scene::intersect(&Ray) through the integrator
+    rays = np.array([[0, 2.75, -2.5, 0, 0, 1, O.FLT_MAX], [0, 2.75, -2.5, 0, 1, 0, O.FLT_MAX]], F)
+    got = renderer.intersect(scene, rays)
+    assert got.tobytes() == ref_scene.trace_rays(rays).tobytes()
+
+
+def test_sharded_launches_assemble_in_one_buffer():
+    # the multi-GPU contract on one device: n contexts, shard i of n each, all writing into ONE device buffer
+    scene, cam = SB.oracle_scene(examples.sixteen_armadillos(4))
+    w, h, n = 512, 296, 3
+    with Engine(flags=FLAG_LEAF_ACCEL) as e0:
+        SB.upload_scene(e0, scene)
+        full = e0.trace_primary(SB.to_ffi_camera(cam), w, h)
+        buf = e0.device_alloc(w * h * 16)
+        e0.memcpy_h2d(buf, np.zeros(w * h, _ffi.HIT))
+        for i in range(n):
+            with Engine(flags=FLAG_LEAF_ACCEL) as ei:
+                SB.upload_scene(ei, scene)
+                ei.set_shard(i, n)
+                ei.trace_primary_device(SB.to_ffi_camera(cam), w, h, 8, None, buf)
+                ei.sync()
+                if i == 0:                                            # after one shard only its rows are filled
+                    part = e0.memcpy_d2h(np.zeros(w * h, _ffi.HIT), buf).reshape(h, w)
+                    rows = _ffi.shard_tile_rows((0, 0, w, h), 8, 0, n)
+                    own = np.zeros(h, bool)
+                    for r in rows:
+                        own[r * 8:(r + 1) * 8] = True
+                    assert part[own].tobytes() == full.reshape(h, w)[own].tobytes()
+                    assert not part[~own].view(np.uint8).any()
+        got = e0.memcpy_d2h(np.zeros(w * h, _ffi.HIT), buf)
+        e0.device_free(buf)
+    assert got.tobytes() == full.tobytes()
