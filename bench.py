@@ -53,49 +53,65 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML every 2 ms; nvidia-smi as fallback)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
+    def __init__(self, uuid=None, index=0):
+        self.uuid, self.index = uuid, index
+        self.sm, self.mask, self.sm_max = [], 0, None
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.error = None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if self.uuid:
+                for cand in (self.uuid, self.uuid.encode()):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(cand)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self.stop_flag.is_set():
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                except Exception:
+                    pass
+                time.sleep(0.002)
+        except Exception as e:                                   # pragma: no cover
+            self.error = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.sm:
+            return self._smi_once()
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.sm_max, "samples": len(self.sm),
+                "reasons": sorted(n for b, n in self.REASONS.items() if self.mask & b), "source": "nvml, 2 ms period, whole timed region"}
+
+    def _smi_once(self):
         try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); smax.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "samples": 1,
+                    "reasons": [n for n, v in zip(names, out[2:6]) if v.strip().lower().startswith("active")],
+                    "source": f"nvidia-smi after the timed region (nvml failed: {self.error})"}
+        except Exception as e:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": [f"unavailable: {e!r}"]}
 
 
 # ------------------------------------------------------------------------------------------ CPU oracle legs
@@ -194,7 +210,8 @@ def run_ours(args, rank, local_rank, world):
     spec = examples.sixteen_armadillos(0)
     scene, models = host.build_scene(spec)
     renderer = host.Renderer(flags=flags, device=local_rank, tile=tile)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()                         # a real (non-NULL) stream: the library launches on it, so
+    torch.cuda.set_stream(stream)                        # torch.cuda.Event sees exactly the kernels we time
     renderer.set_stream(stream.cuda_stream)
     eng = renderer.engine()
     cam = scene.camera()
@@ -243,7 +260,11 @@ def run_ours(args, rank, local_rank, world):
     barrier()
 
     # ---- timed: resident (value)
-    sampler = ClockSampler(local_rank)
+    try:
+        gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(gpu_uuid, local_rank)
     sampler.start()
     launches0 = renderer.stats()["kernel_launches"]
     barrier()

@@ -27,6 +27,7 @@ UNITS = [
     # source,             extra flags
     ("trace_strict.cu", STRICT),
     ("trace_fast.cu", FAST),
+    ("trace_stats.cu", STRICT),
     ("upload_kernels.cu", STRICT),
     ("refit_kernels.cu", STRICT),
     ("bvht_api.cu", STRICT),

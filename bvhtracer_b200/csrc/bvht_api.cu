@@ -882,6 +882,45 @@ int bvht_ipc_close(bvht_ctx* ctx, void* device_ptr) {
     return BVHT_OK;
 }
 
+int bvht_debug_trace_stats(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height, uint32_t tile,
+                           bvht_rect region, uint64_t counters_out[16]) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (!counters_out) return fail(ctx, BVHT_ERR_INVALID_ARG, "null pointer argument");
+    int rc = check_frame_args(ctx, camera, width, height, tile, region);
+    if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    memset(counters_out, 0, 16 * sizeof(uint64_t));
+    if (region.x0 >= region.x1 || region.y0 >= region.y1) return BVHT_OK;
+    PrimaryParams p;
+    memset(&p, 0, sizeof p);
+    if ((rc = fill_scene(ctx, p.scene))) return rc;
+    if ((rc = ensure(ctx, ctx->out_buf, (size_t)width * height * sizeof(bvht_hit)))) return rc;
+    DevBuf cnt;
+    if ((rc = ensure(ctx, cnt, 16 * sizeof(uint64_t)))) return rc;
+    memcpy(p.cam.tl, camera->top_left_eye, 12); memcpy(p.cam.tr, camera->top_right_eye, 12);
+    memcpy(p.cam.bl, camera->bottom_left_eye, 12); memcpy(p.cam.vinv, camera->view_matrix_inv, 64);
+    p.width = width; p.height = height; p.tile = tile;
+    p.x0 = region.x0; p.y0 = region.y0; p.x1 = region.x1; p.y1 = region.y1;
+    p.tx0 = region.x0 / tile; p.ty0 = region.y0 / tile;
+    p.ntx = (region.x1 + tile - 1) / tile - p.tx0; p.nty = (region.y1 + tile - 1) / tile - p.ty0;
+    p.row_stride = 1;
+    p.items_per_tile = (tile * tile + 31u) / 32u;
+    p.n_items = p.ntx * p.nty * p.items_per_tile;
+    p.out = (uint4*)ctx->out_buf.p;
+    p.work_counter = (unsigned int*)ctx->work_counter.p;
+    p.stats = (unsigned long long*)cnt.p;
+    cudaMemsetAsync(cnt.p, 0, 16 * sizeof(uint64_t), ctx->stream);
+    cudaMemsetAsync(ctx->work_counter.p, 0, 4, ctx->stream);
+    int per_sm = std::max(1, blocks_per_sm_primary_stats(accel_on(ctx), kTraceBlock));
+    cudaError_t e = launch_primary_stats(p, accel_on(ctx), ctx->sm_count * per_sm, kTraceBlock, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(counters_out, cnt.p, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    release(cnt);
+    if (e != cudaSuccess) return fail(ctx, BVHT_ERR_CUDA, "debug stats launch failed: %s", cudaGetErrorString(e));
+    ctx->stats.kernel_launches += 1;
+    return BVHT_OK;
+}
+
 int bvht_get_stats(const bvht_ctx* cctx, bvht_stats* out) {
     if (!cctx || !out) return BVHT_ERR_BAD_HANDLE;
     bvht_ctx* ctx = const_cast<bvht_ctx*>(cctx);

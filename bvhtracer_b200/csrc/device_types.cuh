@@ -63,6 +63,7 @@ struct PrimaryParams {
     float     shade_scale, shade_offset; // DepthMappingShader::new(scale, offset)
     uint32_t  hit_rgba, miss_rgba;       // IntersectionShader::new(hit, miss), packed r | g<<8 | b<<16 | a<<24
     unsigned int* work_counter;          // persistent-thread work cursor
+    unsigned long long* stats;           // debug counters (stats build only)
 };
 
 struct RaysParams {

@@ -12,6 +12,7 @@ namespace bvht {
     int blocks_per_sm_rays_##sfx(bool accel, int block);
 BVHT_DECLARE_MODE(strict)
 BVHT_DECLARE_MODE(fast)
+BVHT_DECLARE_MODE(stats)
 #undef BVHT_DECLARE_MODE
 
 // upload_kernels.cu

@@ -38,6 +38,22 @@ struct RayM {            // a ray in some space with its cached reciprocal (quer
 
 struct HitRec { float t, u, v; uint32_t id; };
 
+// Per-thread work counters, compiled in only for the debug entry point (BVHT_STATS); otherwise an empty type
+// whose calls vanish.  Slots: 0 rays, 1 tlas pair tests, 2 instance entries, 3 reference BLAS pair tests,
+// 4 reference leaves visited, 5 brute-force triangle tests, 6 sub-BVH pair tests, 7 sub-BVH triangle tests,
+// 8 accel fallbacks (ray outside the inflation limits), 9 hits
+#ifdef BVHT_STATS
+struct Stat {
+    unsigned long long c[10];
+    __device__ __forceinline__ Stat() { for (int i = 0; i < 10; ++i) c[i] = 0; }
+    __device__ __forceinline__ void add(int i, unsigned n = 1) { c[i] += n; }
+};
+#else
+struct Stat {
+    __device__ __forceinline__ void add(int, unsigned = 1) {}
+};
+#endif
+
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
 // geometry/aabb.rs:65-84.  `tcl` is the ray's current t.
@@ -107,7 +123,8 @@ __device__ __forceinline__ bool moller_trumbore(const float4 v0, const float4 e1
 // Brute-force leaf: primitives base .. base+count ascending, strict '<' against the shrinking closest t
 // (bvh.rs:250-258).  Triangles are tested against the ENTRY ray.
 __device__ __forceinline__ void leaf_brute(const BlasDesc& B, uint32_t base, uint32_t count, const RayM& r, float entry_t,
-                                           float& best_t, float& best_u, float& best_v, uint32_t& best_prim, bool& found) {
+                                           float& best_t, float& best_u, float& best_v, uint32_t& best_prim, bool& found, Stat& st) {
+    st.add(5, count);
     for (uint32_t k = 0; k < count; ++k) {
         uint32_t pi = base + k;
         float4 v0 = ldg4(B.v0 + pi);
@@ -127,7 +144,7 @@ __device__ __forceinline__ void leaf_brute(const BlasDesc& B, uint32_t base, uin
 // visiting order gives that same answer as long as no accepting triangle is skipped, which the
 // pre-inflated boxes guarantee under the bound checked by the caller (DESIGN.md "Leaf accelerator").
 __device__ __forceinline__ void leaf_accel(const BlasDesc& B, uint32_t sub_root, const RayM& r, float entry_t,
-                                           float& best_t, float& best_u, float& best_v, uint32_t& best_prim, bool& found) {
+                                           float& best_t, float& best_u, float& best_v, uint32_t& best_prim, bool& found, Stat& st) {
     // within this leaf: lt/lu/lv/lp = lexicographic-min candidate; ties with the entry value are rejected
     // because lp starts at 0 (no index is < 0) while lt starts at the closest-at-entry value.
     float lt = best_t, lu = 0.0f, lv = 0.0f;
@@ -141,6 +158,7 @@ __device__ __forceinline__ void leaf_accel(const BlasDesc& B, uint32_t sub_root,
             // leaf ref: [30:28] = count-1, [27:0] = first triangle in sub order
             uint32_t first = ref & 0x0FFFFFFFu;
             uint32_t cnt = ((ref >> 28) & 7u) + 1u;
+            st.add(7, cnt);
             for (uint32_t k = 0; k < cnt; ++k) {
                 float4 v0 = ldg4(B.sv0 + first + k);
                 float4 e1 = ldg4(B.se1 + first + k);
@@ -154,6 +172,7 @@ __device__ __forceinline__ void leaf_accel(const BlasDesc& B, uint32_t sub_root,
             if (sp == 0) break;
             ref = stack[--sp];
         } else {
+            st.add(6);
             const float4* n = B.sub_nodes + (size_t)ref * 4;
             float4 a = ldg4(n + 0);   // child0 lo.xyz, child0 ref
             float4 b = ldg4(n + 1);   // child0 hi.xyz, child1 ref
@@ -186,7 +205,7 @@ __device__ __forceinline__ void leaf_accel(const BlasDesc& B, uint32_t sub_root,
 // ray's current closest, scene_object.rs:87).  On return `found` says whether a strictly closer hit exists.
 template <bool ACCEL>
 __device__ __forceinline__ void blas_intersect(const BlasDesc& B, const RayM& r, float entry_t, bool use_accel,
-                                               float& best_t, float& best_u, float& best_v, uint32_t& best_prim, bool& found) {
+                                               float& best_t, float& best_u, float& best_v, uint32_t& best_prim, bool& found, Stat& st) {
     uint32_t stack[kBlasStack];
     int sp = 0;
     uint32_t ni = 0;                       // root: its AABB is never tested (bvh.rs:243)
@@ -199,19 +218,21 @@ __device__ __forceinline__ void blas_intersect(const BlasDesc& B, const RayM& r,
         uint32_t lf = __float_as_uint(n0.w);
         if (count > 0) {
             bool done = false;
+            st.add(4);
             if (ACCEL) {
                 if (use_accel) {
                     uint32_t sr = __ldg(B.leaf_sub_root + ni);
-                    if (sr != 0xFFFFFFFFu) { leaf_accel(B, sr, r, entry_t, best_t, best_u, best_v, best_prim, found); done = true; }
+                    if (sr != 0xFFFFFFFFu) { leaf_accel(B, sr, r, entry_t, best_t, best_u, best_v, best_prim, found, st); done = true; }
                 }
             }
-            if (!done) leaf_brute(B, lf, count, r, entry_t, best_t, best_u, best_v, best_prim, found);
+            if (!done) leaf_brute(B, lf, count, r, entry_t, best_t, best_u, best_v, best_prim, found, st);
             if (sp == 0) break;
             ni = stack[--sp];
             n0 = ldg4(B.nodes + 2 * (size_t)ni);
             n1 = ldg4(B.nodes + 2 * (size_t)ni + 1);
         } else {
             // children are adjacent: 4 float4 = 64 contiguous, 64-byte aligned bytes (left index is even)
+            st.add(3);
             const float4* c = B.nodes + 2 * (size_t)lf;
             float4 l0 = ldg4(c + 0), l1 = ldg4(c + 1), r0 = ldg4(c + 2), r1 = ldg4(c + 3);
             float ld, rd;
@@ -237,7 +258,8 @@ __device__ __forceinline__ void blas_intersect(const BlasDesc& B, const RayM& r,
 
 // scene/tlas.rs:123-177 + scene_object.rs:78-89.  World ray (ox..dz, recip), initial t = tmax.
 template <bool ACCEL>
-__device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM& w, float tmax) {
+__device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM& w, float tmax, Stat& st) {
+    st.add(0);
     HitRec best;
     best.t = FLT_MAX; best.u = 0.0f; best.v = 0.0f; best.id = 0xFFFFFFFFu;
     float closest = tmax;
@@ -269,9 +291,11 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
                 float dn2 = (r.dx * r.dx + r.dy * r.dy) + r.dz * r.dz;
                 float on2 = (r.ox * r.ox + r.oy * r.oy) + r.oz * r.oz;
                 use_accel = (dn2 <= B.accel_d_max * B.accel_d_max) && (on2 <= B.accel_o_max * B.accel_o_max);
+                if (!use_accel) st.add(8);
             }
+            st.add(2);
             float bt, bu, bv; uint32_t bp; bool found;
-            blas_intersect<ACCEL>(B, r, closest, use_accel, bt, bu, bv, bp, found);
+            blas_intersect<ACCEL>(B, r, closest, use_accel, bt, bu, bv, bp, found, st);
             if (found && bt < closest) {                                     // tlas.rs:131
                 closest = bt;
                 best.t = bt; best.u = bu; best.v = bv;
@@ -284,6 +308,7 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
             n0 = ldg4(S.tlas + 2 * (size_t)ni);
             n1 = ldg4(S.tlas + 2 * (size_t)ni + 1);
         } else {
+            st.add(1);
             uint32_t li = (lr & 0xFFFF0000u) >> 16;    // left_blas()  = upper half (tlas.rs:25-27)
             uint32_t ri = lr & 0x0000FFFFu;            // right_blas() = lower half (tlas.rs:30-32)
             float4 l0 = ldg4(S.tlas + 2 * (size_t)li), l1 = ldg4(S.tlas + 2 * (size_t)li + 1);
@@ -308,6 +333,7 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
         }
     }
     if (!((closest < FLT_MAX) && have)) { best.t = FLT_MAX; best.u = 0.0f; best.v = 0.0f; best.id = 0xFFFFFFFFu; }
+    else st.add(9);
     return best;
 }
 
@@ -370,6 +396,7 @@ template <bool ACCEL>
 __global__ void __launch_bounds__(256)
 trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
     const unsigned lane = threadIdx.x & 31u;
+    Stat st;
     for (;;) {
         unsigned item = 0;
         if (lane == 0) item = atomicAdd(P.work_counter, 1u);
@@ -385,7 +412,7 @@ trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
         bool active = (iv < P.tile) && px >= P.x0 && px < P.x1 && py >= P.y0 && py < P.y1;
         if (active) {
             RayM w = primary_ray(P.cam, px, py, P.width, P.height);
-            HitRec h = scene_intersect<ACCEL>(P.scene, w, FLT_MAX);
+            HitRec h = scene_intersect<ACCEL>(P.scene, w, FLT_MAX, st);
             if (P.out) {
                 uint4 o;
                 o.x = __float_as_uint(h.t); o.y = __float_as_uint(h.u); o.z = __float_as_uint(h.v); o.w = h.id;
@@ -394,6 +421,13 @@ trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
             if (P.out_rgba) P.out_rgba[(size_t)py * P.width + px] = shade_pixel(P, h);
         }
     }
+#ifdef BVHT_STATS
+    for (int i = 0; i < 10; ++i) {
+        unsigned long long v = st.c[i];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
+        if (lane == 0 && v) atomicAdd(P.stats + i, v);
+    }
+#endif
 }
 
 // K1b: Scene::intersect(&Ray) for an arbitrary ray buffer; warps pull 32 rays at a time.
@@ -401,6 +435,7 @@ template <bool ACCEL>
 __global__ void __launch_bounds__(256)
 trace_rays_kernel(const __grid_constant__ RaysParams P) {
     const unsigned lane = threadIdx.x & 31u;
+    Stat st;
     const uint64_t n_items = (P.n + 31u) / 32u;
     for (;;) {
         unsigned item = 0;
@@ -415,7 +450,7 @@ trace_rays_kernel(const __grid_constant__ RaysParams P) {
             w.dx = __ldg(rp + 3); w.dy = __ldg(rp + 4); w.dz = __ldg(rp + 5);
             float t = __ldg(rp + 6);
             w.rdx = 1.0f / w.dx; w.rdy = 1.0f / w.dy; w.rdz = 1.0f / w.dz;
-            HitRec h = scene_intersect<ACCEL>(P.scene, w, t);
+            HitRec h = scene_intersect<ACCEL>(P.scene, w, t, st);
             uint4 o;
             o.x = __float_as_uint(h.t); o.y = __float_as_uint(h.u); o.z = __float_as_uint(h.v); o.w = h.id;
             P.out[i] = o;

@@ -163,6 +163,18 @@ class Engine:
     def trace_rays_device(self, rays_device_ptr, n, out_device_ptr):
         self._check(self._lib.bvht_trace_rays_device(self._ctx, C.c_void_p(rays_device_ptr), int(n), C.c_void_p(out_device_ptr)))
 
+    COUNTER_NAMES = ["rays", "tlas_pairs", "instance_entries", "blas_pairs", "ref_leaves", "brute_tris", "sub_pairs", "sub_tris",
+                     "accel_fallbacks", "hits"]
+
+    def debug_trace_stats(self, camera, width, height, tile=8, region=None):
+        """Per-frame work counters of an instrumented strict kernel (not a product path)."""
+        camera = np.ascontiguousarray(camera)
+        out = np.zeros(16, "<u8")
+        x0, y0, x1, y1 = region if region is not None else (0, 0, width, height)
+        self._check(self._lib.bvht_debug_trace_stats(self._ctx, ptr(camera), int(width), int(height), int(tile),
+                                                     Rect(x0, y0, x1, y1), ptr(out)))
+        return {n: int(out[i]) for i, n in enumerate(self.COUNTER_NAMES)}
+
     # ------------------------------------------------------------------ device memory
     def device_alloc(self, nbytes):
         p = C.c_void_p()

@@ -232,6 +232,13 @@ BVHT_API int         bvht_ipc_close(bvht_ctx* ctx, void* device_ptr);
 
 BVHT_API int         bvht_get_stats(const bvht_ctx* ctx, bvht_stats* out);
 
+/* Debug: trace `region` once with an instrumented strict kernel and return per-frame work counters:
+ * [0] rays, [1] TLAS pair tests, [2] instance entries, [3] reference BLAS pair tests, [4] reference leaves
+ * visited, [5] brute-force triangle tests, [6] sub-BVH pair tests, [7] sub-BVH triangle tests,
+ * [8] accel fallbacks, [9] hits, [10..15] reserved.  Not a product path. */
+BVHT_API int         bvht_debug_trace_stats(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height,
+                                    uint32_t tile, bvht_rect region, uint64_t counters_out[16]);
+
 #ifdef __cplusplus
 }
 #endif
