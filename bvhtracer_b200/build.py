@@ -57,13 +57,16 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH
     nvcc = _nvcc()
+    extra_defs = []
+    if os.environ.get("BVHT_MIN_BLOCKS"):            # tuning knob: register budget of the trace kernels
+        extra_defs.append("-DBVHT_MIN_BLOCKS=" + os.environ["BVHT_MIN_BLOCKS"])
     os.makedirs(LIB_DIR, exist_ok=True)
     os.makedirs(OBJ_DIR, exist_ok=True)
     objs = []
     procs = []
     for src, extra in UNITS:
         obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
-        cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + ARCH + COMMON + extra + extra_defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -46,6 +47,8 @@ struct Blas {
     DevBuf sub_nodes, sub_order, sv0, se1, se2, leaf_sub_root;
     uint32_t n_sub = 0;
     float d_max = 0.0f, o_max = 0.0f;
+    float tight_lo[3] = { 0, 0, 0 }, tight_hi[3] = { 0, 0, 0 };
+    bool tight_valid = false;
 };
 
 } // namespace
@@ -62,7 +65,7 @@ struct bvht_ctx {
     std::vector<Blas> blas;
     DevBuf blas_desc;                                 // BlasDesc[blas.size()]
     bool blas_desc_dirty = true;
-    DevBuf tlas, inst_cols, inst_blas;
+    DevBuf tlas, inst_cols, inst_blas, tlas_tight;
     uint32_t tlas_nodes_used = 0, n_inst = 0;
     DevBuf work_counter;
     DevBuf out_buf, rays_buf, rgba_buf;               // device staging for the host-pointer entry points
@@ -193,6 +196,7 @@ int build_and_upload_accel(bvht_ctx* ctx, Blas& b) {
         return fail(ctx, BVHT_ERR_MALFORMED_BVH, "leaf accelerator depth %u exceeds the stack bound %d", acc.max_depth, kSubStack);
     b.n_sub = (uint32_t)acc.order.size();
     b.d_max = acc.d_max; b.o_max = acc.o_max;
+    memcpy(b.tight_lo, acc.tight_lo, 12); memcpy(b.tight_hi, acc.tight_hi, 12); b.tight_valid = acc.tight_valid;
     int rc;
     if ((rc = ensure(ctx, b.sub_nodes, acc.sub_nodes.size() * 4))) return rc;
     if ((rc = h2d(ctx, b.sub_nodes.p, acc.sub_nodes.data(), acc.sub_nodes.size() * 4))) return rc;
@@ -248,6 +252,102 @@ int refresh_blas_desc(bvht_ctx* ctx) {
 }
 
 bool accel_on(const bvht_ctx* ctx) { return (ctx->flags & BVHT_FLAG_LEAF_ACCEL) != 0; }
+
+// 4x4 inverse in double (column-major), for the world-space tight boxes only (never for traced arithmetic)
+bool invert_d(const double* m, double* out) {
+    double a[4][8];
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) { a[r][c] = m[c * 4 + r]; a[r][4 + c] = (r == c) ? 1.0 : 0.0; }
+    for (int col = 0; col < 4; ++col) {
+        int piv = col; double best = std::fabs(a[col][col]);
+        for (int r = col + 1; r < 4; ++r) if (std::fabs(a[r][col]) > best) { best = std::fabs(a[r][col]); piv = r; }
+        if (!(best > 1e-300)) return false;
+        if (piv != col) for (int c = 0; c < 8; ++c) std::swap(a[piv][c], a[col][c]);
+        double inv = 1.0 / a[col][col];
+        for (int c = 0; c < 8; ++c) a[col][c] *= inv;
+        for (int r = 0; r < 4; ++r) if (r != col) { double f = a[r][col]; if (f != 0.0) for (int c = 0; c < 8; ++c) a[r][c] -= f * a[col][c]; }
+    }
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) out[c * 4 + r] = a[r][4 + c];
+    return true;
+}
+
+struct TightBox { float lo[3], hi[3]; float d2_max, o2_max; };      // d2_max < 0: unusable (always visit)
+
+// Conservative WORLD-space box of the real (non-degenerate) geometry of one instance, with the world-space ray limits
+// under which the model-space limits of the leaf accelerator are implied (DESIGN.md "Tight TLAS boxes").
+TightBox instance_tight_box(const Blas& b, const float* inv_f) {
+    TightBox t; t.d2_max = -1.0f; t.o2_max = -1.0f;
+    for (int k = 0; k < 3; ++k) { t.lo[k] = -FLT_MAX; t.hi[k] = FLT_MAX; }
+    if (!b.tight_valid) return t;
+    double inv[16], fwd[16];
+    for (int i = 0; i < 16; ++i) { inv[i] = inv_f[i]; if (!std::isfinite(inv[i])) return t; }
+    // affine only: bottom row must be (0, 0, 0, 1)
+    if (inv[3] != 0.0 || inv[7] != 0.0 || inv[11] != 0.0 || inv[15] != 1.0) return t;
+    if (!invert_d(inv, fwd)) return t;
+    double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 }, maxabs = 0.0;
+    for (int i = 0; i < 8; ++i) {
+        double p[3] = { (i & 1) ? b.tight_hi[0] : b.tight_lo[0], (i & 2) ? b.tight_hi[1] : b.tight_lo[1], (i & 4) ? b.tight_hi[2] : b.tight_lo[2] };
+        for (int r = 0; r < 3; ++r) {
+            double q = fwd[0 + r] * p[0] + fwd[4 + r] * p[1] + fwd[8 + r] * p[2] + fwd[12 + r];
+            lo[r] = std::min(lo[r], q); hi[r] = std::max(hi[r], q); maxabs = std::max(maxabs, std::fabs(q));
+        }
+    }
+    // slack for: f32 evaluation of M^-1 * (o, d) in the kernel, the f32 slab test, f32 storage of the box
+    double ext = std::max({ hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2], 1e-3 });
+    double slack = 1e-4 * (ext + maxabs);
+    // |d'| <= s |d_w|, |o'| <= s |o_w| + |t'| with s >= largest singular value of the 3x3 part A of M^-1:
+    // power iteration on A^T A (converges from below, hence the 1 % safety), capped by the Frobenius norm
+    double ata[3][3], fro = 0.0;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+        ata[i][j] = 0.0;
+        for (int r = 0; r < 3; ++r) ata[i][j] += inv[i * 4 + r] * inv[j * 4 + r];
+    }
+    for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) fro += inv[c * 4 + r] * inv[c * 4 + r];
+    double v[3] = { 0.57, 0.58, 0.59 }, lam = 0.0;
+    for (int it = 0; it < 200; ++it) {
+        double w[3] = { 0, 0, 0 };
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) w[i] += ata[i][j] * v[j];
+        double n = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+        if (!(n > 0.0)) break;
+        lam = n / std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        for (int i = 0; i < 3; ++i) v[i] = w[i] / n;
+    }
+    double sgm = std::min(std::sqrt(lam) * 1.01, std::sqrt(fro) * (1.0 + 1e-6));
+    if (!(lam > 0.0)) sgm = std::sqrt(fro) * (1.0 + 1e-6);
+    double tn = std::sqrt(inv[12] * inv[12] + inv[13] * inv[13] + inv[14] * inv[14]);
+    if (!(sgm > 0.0)) return t;
+    double dw = (double)b.d_max / sgm * (1.0 - 1e-5);
+    double ow = ((double)b.o_max - tn) / sgm * (1.0 - 1e-5);
+    if (!(dw > 0.0) || !(ow > 0.0)) return t;
+    for (int k = 0; k < 3; ++k) {
+        double l = lo[k] - slack, h = hi[k] + slack;
+        float fl = (float)l; if ((double)fl > l) fl = std::nextafterf(fl, -FLT_MAX);
+        float fh = (float)h; if ((double)fh < h) fh = std::nextafterf(fh, FLT_MAX);
+        t.lo[k] = fl; t.hi[k] = fh;
+    }
+    t.d2_max = (float)(dw * dw * (1.0 - 1e-6));
+    t.o2_max = (float)(ow * ow * (1.0 - 1e-6));
+    return t;
+}
+
+TightBox tight_union(const TightBox& a, const TightBox& b) {
+    TightBox t;
+    for (int k = 0; k < 3; ++k) { t.lo[k] = std::min(a.lo[k], b.lo[k]); t.hi[k] = std::max(a.hi[k], b.hi[k]); }
+    t.d2_max = std::min(a.d2_max, b.d2_max);        // negative (unusable) wins
+    t.o2_max = std::min(a.o2_max, b.o2_max);
+    return t;
+}
+
+// Per TLAS node: union over the instances below it.  Depth and indices were validated by the caller.
+TightBox tlas_tight_rec(const bvht_tlas_node* nodes, uint32_t ni, const std::vector<TightBox>& inst, std::vector<TightBox>& out,
+                        std::vector<uint8_t>& done) {
+    if (done[ni]) return out[ni];
+    const bvht_tlas_node& n = nodes[ni];
+    TightBox t;
+    if (n.left_right == 0) t = inst[n.blas];
+    else t = tight_union(tlas_tight_rec(nodes, n.left_right >> 16, inst, out, done), tlas_tight_rec(nodes, n.left_right & 0xFFFFu, inst, out, done));
+    out[ni] = t; done[ni] = 1;
+    return t;
+}
 bool fast_on(const bvht_ctx* ctx) { return (ctx->flags & BVHT_FLAG_FAST) != 0; }
 
 int fill_scene(bvht_ctx* ctx, SceneDev& s) {
@@ -256,6 +356,7 @@ int fill_scene(bvht_ctx* ctx, SceneDev& s) {
     int rc = refresh_blas_desc(ctx);
     if (rc) return rc;
     s.tlas = (const float4*)ctx->tlas.p;
+    s.tlas_tight = (const float4*)ctx->tlas_tight.p;
     s.inst_cols = (const float4*)ctx->inst_cols.p;
     s.inst_blas = (const uint32_t*)ctx->inst_blas.p;
     s.blas = (const BlasDesc*)ctx->blas_desc.p;
@@ -349,7 +450,7 @@ void bvht_destroy(bvht_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (Blas& b : ctx->blas) free_blas(b);
     for (DevBuf* d : { &ctx->blas_desc, &ctx->tlas, &ctx->inst_cols, &ctx->inst_blas, &ctx->work_counter, &ctx->out_buf, &ctx->rays_buf,
-                       &ctx->rgba_buf })
+                       &ctx->rgba_buf, &ctx->tlas_tight })
         release(*d);
     for (cudaStream_t st : { ctx->aux[0], ctx->aux[1], ctx->copy_stream }) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     for (cudaEvent_t ev : { ctx->ev_fork, ctx->ev_join }) if (ev) cudaEventDestroy(ev);
@@ -579,6 +680,23 @@ int bvht_tlas_set(bvht_ctx* ctx, const bvht_tlas_node* nodes, uint32_t nodes_use
     if (n_instances) {
         if ((rc = h2d(ctx, ctx->inst_cols.p, ic, (size_t)n_instances * 64))) return rc;
         if ((rc = h2d(ctx, ctx->inst_blas.p, ib, (size_t)n_instances * 4))) return rc;
+    }
+    if (accel_on(ctx) && n_instances > 0) {
+        std::vector<TightBox> inst_t(n_instances);
+        for (uint32_t i = 0; i < n_instances; ++i) inst_t[i] = instance_tight_box(ctx->blas[instances[i].blas_id], instances[i].transform_inv);
+        TightBox unusable; unusable.d2_max = unusable.o2_max = -1.0f;
+        for (int k = 0; k < 3; ++k) { unusable.lo[k] = -FLT_MAX; unusable.hi[k] = FLT_MAX; }
+        std::vector<TightBox> node_t(nodes_used, unusable);
+        std::vector<uint8_t> done(nodes_used, 0);
+        tlas_tight_rec(nodes, 0, inst_t, node_t, done);                     // unreachable nodes keep `unusable`
+        std::vector<float> flat((size_t)nodes_used * 8);
+        for (uint32_t i = 0; i < nodes_used; ++i) {
+            float* f = &flat[(size_t)i * 8];
+            memcpy(f + 0, node_t[i].lo, 12); f[3] = node_t[i].d2_max;
+            memcpy(f + 4, node_t[i].hi, 12); f[7] = node_t[i].o2_max;
+        }
+        if ((rc = ensure(ctx, ctx->tlas_tight, flat.size() * 4))) return rc;
+        if ((rc = h2d(ctx, ctx->tlas_tight.p, flat.data(), flat.size() * 4))) return rc;   // pageable: staged before return
     }
     ctx->tlas_nodes_used = nodes_used;
     ctx->n_inst = n_instances;
@@ -822,18 +940,18 @@ int bvht_device_free(bvht_ctx* ctx, void* device_ptr) {
 }
 
 int bvht_host_alloc(bvht_ctx* ctx, size_t bytes, void** out_host) {
-    if (!ctx) return BVHT_ERR_BAD_HANDLE;
-    if (!out_host) return fail(ctx, BVHT_ERR_INVALID_ARG, "null pointer argument");
-    cudaSetDevice(ctx->device);
-    CU(ctx, cudaMallocHost(out_host, bytes ? bytes : 16));
+    // ctx may be NULL: page-locked host memory does not belong to a context
+    if (!out_host) return ctx ? fail(ctx, BVHT_ERR_INVALID_ARG, "null pointer argument") : BVHT_ERR_INVALID_ARG;
+    if (ctx) cudaSetDevice(ctx->device);
+    cudaError_t e = cudaMallocHost(out_host, bytes ? bytes : 16);
+    if (e != cudaSuccess) { cudaGetLastError(); return ctx ? fail(ctx, BVHT_ERR_OUT_OF_MEMORY, "cudaMallocHost: %s", cudaGetErrorString(e)) : BVHT_ERR_OUT_OF_MEMORY; }
     return BVHT_OK;
 }
 
 int bvht_host_free(bvht_ctx* ctx, void* host_ptr) {
-    if (!ctx) return BVHT_ERR_BAD_HANDLE;
-    cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    CU(ctx, cudaFreeHost(host_ptr));
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    cudaError_t e = cudaFreeHost(host_ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return ctx ? fail(ctx, BVHT_ERR_CUDA, "cudaFreeHost: %s", cudaGetErrorString(e)) : BVHT_ERR_CUDA; }
     return BVHT_OK;
 }
 

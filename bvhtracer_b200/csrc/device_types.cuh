@@ -35,6 +35,8 @@ struct BlasDesc {
 };
 
 struct SceneDev {
+    const float4*   tlas_tight;  // accel only, 2 float4 per TLAS node: conservative world box of the REAL geometry below the
+                                 //   node {lo.xyz, max |d|^2} {hi.xyz, max |o|^2} (limits under which it may be used)
     const float4*   tlas;        // 2 float4 per TLAS node
     const float4*   inst_cols;   // 4 float4 per instance: columns of the inverse transform
     const uint32_t* inst_blas;   // blas id per instance

@@ -181,6 +181,15 @@ bool build_leaf_accel(const float* tris, uint32_t n_tris, const void* nodes_v, u
     bld.delta_scale = cfg.c_mt * eps * cfg.d_max * s_max / 1e-4;     // residual of Triangle::intersect at |det| = 1e-4
     bld.delta_abs = 16.0 * eps * s_max;                               // rounding of s = o - v0 and of the slab test
 
+    {   // whole-model tight box
+        Box mb; mb.reset(); double kmax = 0.0; bool any = false;
+        for (uint32_t i = 0; i < n_tris; ++i) {
+            if (!(bld.info[i].kappa > 0.0)) continue;
+            mb.grow(bld.info[i].box); kmax = std::max(kmax, bld.info[i].kappa); any = true;
+        }
+        if (any) { bld.write_box(out.tight_lo, out.tight_hi, mb, kmax); out.tight_valid = true; }
+    }
+
     std::vector<uint32_t> idx;
     for (uint32_t ni = 0; ni < nodes_used; ++ni) {
         if (ni == 1) continue;

@@ -29,6 +29,10 @@ struct LeafAccelHost {
     float d_max = 0.0f;                   // limits under which the inflation is valid
     float o_max = 0.0f;
     uint32_t max_depth = 0;
+    // box of the NON-degenerate triangles of the whole model, inflated like the sub boxes: under the same limits no
+    // triangle can be accepted by a ray that misses it (the 999-sentinel is degenerate and never accepted)
+    float tight_lo[3] = { 0, 0, 0 }, tight_hi[3] = { 0, 0, 0 };
+    bool  tight_valid = false;
 };
 
 struct LeafAccelConfig {

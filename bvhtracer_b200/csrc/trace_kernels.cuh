@@ -27,6 +27,10 @@
 #error "define BVHT_MODE_NS (strict|fast) before including trace_kernels.cuh"
 #endif
 
+#ifndef BVHT_MIN_BLOCKS
+#define BVHT_MIN_BLOCKS 6      // CTAs of 128 threads per SM the register allocation must allow (tuned on B200)
+#endif
+
 namespace bvht {
 namespace BVHT_MODE_NS {
 
@@ -34,7 +38,18 @@ struct RayM {            // a ray in some space with its cached reciprocal (quer
     float ox, oy, oz;
     float dx, dy, dz;
     float rdx, rdy, rdz;
+    // For the FMA-form slab test of OUR conservative boxes only (never reference boxes): reciprocal clamped to
+    // +-1e30 (so that a zero / denormal direction component cannot produce inf - inf = NaN) and -(o * that).
+    float fx, fy, fz;
+    float nx, ny, nz;
 };
+
+__device__ __forceinline__ void ray_prepare_fma(RayM& r) {
+    r.fx = fminf(fmaxf(r.rdx, -1e30f), 1e30f);
+    r.fy = fminf(fmaxf(r.rdy, -1e30f), 1e30f);
+    r.fz = fminf(fmaxf(r.rdz, -1e30f), 1e30f);
+    r.nx = -(r.ox * r.fx); r.ny = -(r.oy * r.fy); r.nz = -(r.oz * r.fz);
+}
 
 struct HitRec { float t, u, v; uint32_t id; };
 
@@ -74,21 +89,20 @@ __device__ __forceinline__ bool slab_test(const float4 lo, const float4 hi, cons
     return (t_max >= t_min) && (t_min < tcl) && (t_max > 0.0f);
 }
 
-// Slab test for OUR sub-BVH boxes (not a reference function): inclusive on every bound so that it is never
-// stricter than needed; the boxes themselves carry the conservative inflation.
+// Slab test for OUR conservative boxes (sub-BVH nodes, tight TLAS boxes) -- not a reference function.  One FMA per
+// plane, t = lo * rd - o * rd (explicit __fmaf_rn, so identical in the strict and fast builds), inclusive on every
+// bound.  Its rounding differs from (lo - o) * rd by at most ~eps * |o * rd|, i.e. a plane shift of eps * |o|, which
+// the box inflation (leaf_accel.cpp delta_abs) covers.  The reciprocal is clamped to +-1e30 (ray_prepare_fma): an axis
+// with d == 0 then yields t = +-(huge) with the right signs (inside the slab: [-huge, +huge]; outside: both on one side).
 __device__ __forceinline__ bool slab_test_sub(const float4 lo, const float4 hi, const RayM& r, float tcl, float& tmin_out) {
-    float t_x1 = (lo.x - r.ox) * r.rdx;
-    float t_x2 = (hi.x - r.ox) * r.rdx;
-    float t_min = fminf(t_x1, t_x2);
-    float t_max = fmaxf(t_x1, t_x2);
-    float t_y1 = (lo.y - r.oy) * r.rdy;
-    float t_y2 = (hi.y - r.oy) * r.rdy;
-    t_min = fmaxf(t_min, fminf(t_y1, t_y2));
-    t_max = fminf(t_max, fmaxf(t_y1, t_y2));
-    float t_z1 = (lo.z - r.oz) * r.rdz;
-    float t_z2 = (hi.z - r.oz) * r.rdz;
-    t_min = fmaxf(t_min, fminf(t_z1, t_z2));
-    t_max = fminf(t_max, fmaxf(t_z1, t_z2));
+    float t_x1 = __fmaf_rn(lo.x, r.fx, r.nx);
+    float t_x2 = __fmaf_rn(hi.x, r.fx, r.nx);
+    float t_y1 = __fmaf_rn(lo.y, r.fy, r.ny);
+    float t_y2 = __fmaf_rn(hi.y, r.fy, r.ny);
+    float t_z1 = __fmaf_rn(lo.z, r.fz, r.nz);
+    float t_z2 = __fmaf_rn(hi.z, r.fz, r.nz);
+    float t_min = fmaxf(fmaxf(fminf(t_x1, t_x2), fminf(t_y1, t_y2)), fminf(t_z1, t_z2));
+    float t_max = fminf(fminf(fmaxf(t_x1, t_x2), fmaxf(t_y1, t_y2)), fmaxf(t_z1, t_z2));
     tmin_out = t_min;
     return (t_max >= t_min) && (t_min <= tcl) && (t_max >= 0.0f);
 }
@@ -268,6 +282,21 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
     int sp = 0;
     float4 n0 = ldg4(S.tlas + 0);
     float4 n1 = ldg4(S.tlas + 1);
+    // ACCEL: conservative world-space boxes of the REAL geometry under each TLAS node ("tight" boxes).  The reference's
+    // instance boxes are inflated to +999 by the sentinel triangle of every .tri asset, so most rays enter most
+    // instances only to find nothing.  A subtree whose tight box the ray misses cannot produce a hit, and entering it
+    // has no side effect in the reference (closest is only updated by hits), so skipping it leaves the rest of the
+    // reference's ordered walk -- and therefore the result -- unchanged.
+    float wd2 = 0.0f, wo2 = 0.0f;
+    RayM wf = w;
+    if (ACCEL) {
+        wd2 = (w.dx * w.dx + w.dy * w.dy) + w.dz * w.dz;
+        wo2 = (w.ox * w.ox + w.oy * w.oy) + w.oz * w.oz;
+        ray_prepare_fma(wf);
+        float4 t0 = ldg4(S.tlas_tight + 0), t1 = ldg4(S.tlas_tight + 1);
+        float tt;
+        if (wd2 <= t0.w && wo2 <= t1.w && !slab_test_sub(t0, t1, wf, closest, tt)) return best;   // nothing reachable at all
+    }
     for (;;) {
         uint32_t lr = __float_as_uint(n0.w);
         if (lr == 0u) {
@@ -292,6 +321,7 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
                 float on2 = (r.ox * r.ox + r.oy * r.oy) + r.oz * r.oz;
                 use_accel = (dn2 <= B.accel_d_max * B.accel_d_max) && (on2 <= B.accel_o_max * B.accel_o_max);
                 if (!use_accel) st.add(8);
+                ray_prepare_fma(r);
             }
             st.add(2);
             float bt, bu, bv; uint32_t bp; bool found;
@@ -319,12 +349,31 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
             float lkey = lh ? ld : FLT_MAX;
             float rkey = rh ? rd : FLT_MAX;
             bool left_first = lkey < rkey;
+            if (ACCEL) {
+                // drop children whose tight box cannot contain an accepted hit closer than `closest`
+                if (lh) {
+                    float4 t0 = ldg4(S.tlas_tight + 2 * (size_t)li), t1 = ldg4(S.tlas_tight + 2 * (size_t)li + 1);
+                    float tt;
+                    if (wd2 <= t0.w && wo2 <= t1.w) lh = slab_test_sub(t0, t1, wf, closest, tt);
+                }
+                if (rh) {
+                    float4 t0 = ldg4(S.tlas_tight + 2 * (size_t)ri), t1 = ldg4(S.tlas_tight + 2 * (size_t)ri + 1);
+                    float tt;
+                    if (wd2 <= t0.w && wo2 <= t1.w) rh = slab_test_sub(t0, t1, wf, closest, tt);
+                }
+            }
             bool near_hit = left_first ? lh : rh;
             bool far_hit = left_first ? rh : lh;
             if (near_hit) {
                 if (far_hit) stack[sp++] = left_first ? ri : li;
                 if (left_first) { n0 = l0; n1 = l1; } else { n0 = r0; n1 = r1; }
                 continue;
+            }
+            if (ACCEL) {
+                if (far_hit) {             // near child dropped (or missed): the far child is next in the reference's order
+                    if (left_first) { n0 = r0; n1 = r1; } else { n0 = l0; n1 = l1; }
+                    continue;
+                }
             }
             if (sp == 0) break;
             uint32_t ni = stack[--sp];
@@ -393,7 +442,7 @@ __device__ __forceinline__ uint32_t shade_pixel(const PrimaryParams& P, const Hi
 
 // K1: persistent, tile-pulling primary closest-hit kernel.
 template <bool ACCEL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, BVHT_MIN_BLOCKS)
 trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
     const unsigned lane = threadIdx.x & 31u;
     Stat st;
@@ -432,7 +481,7 @@ trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
 
 // K1b: Scene::intersect(&Ray) for an arbitrary ray buffer; warps pull 32 rays at a time.
 template <bool ACCEL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, BVHT_MIN_BLOCKS)
 trace_rays_kernel(const __grid_constant__ RaysParams P) {
     const unsigned lane = threadIdx.x & 31u;
     Stat st;

@@ -587,17 +587,15 @@ public:
     const bvht_hit* hits() const { return hits_; }
     const ShadingPipeline& shading() const { return shading_; }
     bool keep_hits() const { return keep_hits_; }
-    // buffers are page-locked host memory owned by the integrator's device context
-    void bind(bvht_ctx* ctx) {
-        if (ctx_ == ctx && frame_) return;
-        release();
-        ctx_ = ctx;
+    // buffers are page-locked host memory (not tied to the integrator's context: a state may outlive it)
+    void bind(bvht_ctx*) {
+        if (frame_) return;
         void* p = nullptr;
-        if (bvht_host_alloc(ctx, width_ * height_ * 4, &p) != BVHT_OK) throw std::runtime_error(bvht_last_error(ctx));
+        if (bvht_host_alloc(nullptr, width_ * height_ * 4, &p) != BVHT_OK) throw std::runtime_error("bvht_host_alloc failed (frame buffer)");
         frame_ = (uint32_t*)p;
         for (size_t i = 0; i < width_ * height_; ++i) frame_[i] = 0xFF000000u;        // Rgba::from([0, 0, 0, 255]), renderer.rs:87-91
         if (keep_hits_) {
-            if (bvht_host_alloc(ctx, width_ * height_ * sizeof(bvht_hit), &p) != BVHT_OK) throw std::runtime_error(bvht_last_error(ctx));
+            if (bvht_host_alloc(nullptr, width_ * height_ * sizeof(bvht_hit), &p) != BVHT_OK) throw std::runtime_error("bvht_host_alloc failed (hit records)");
             hits_ = (bvht_hit*)p;
         }
     }
@@ -605,13 +603,13 @@ public:
     bvht_hit* hits_mut() { return hits_; }
 private:
     void release() {
-        if (ctx_) { if (frame_) bvht_host_free(ctx_, frame_); if (hits_) bvht_host_free(ctx_, hits_); }
-        frame_ = nullptr; hits_ = nullptr; ctx_ = nullptr;
+        if (frame_) bvht_host_free(nullptr, frame_);
+        if (hits_) bvht_host_free(nullptr, hits_);
+        frame_ = nullptr; hits_ = nullptr;
     }
     ShadingPipeline shading_;
     size_t width_, height_;
     bool keep_hits_;
-    bvht_ctx* ctx_ = nullptr;
     uint32_t* frame_ = nullptr;
     bvht_hit* hits_ = nullptr;
 };

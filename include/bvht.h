@@ -220,7 +220,7 @@ BVHT_API int         bvht_trace_rays_device(bvht_ctx* ctx, const void* rays_devi
 /* Device memory helpers (multi-GPU gather, resident benchmarks). */
 BVHT_API int         bvht_device_alloc(bvht_ctx* ctx, size_t bytes, void** out_device);
 BVHT_API int         bvht_device_free(bvht_ctx* ctx, void* device_ptr);
-/* Page-locked host memory (so that copies overlap with kernels). */
+/* Page-locked host memory (so that copies overlap with kernels).  ctx may be NULL for both calls. */
 BVHT_API int         bvht_host_alloc(bvht_ctx* ctx, size_t bytes, void** out_host);
 BVHT_API int         bvht_host_free(bvht_ctx* ctx, void* host_ptr);
 BVHT_API int         bvht_memcpy_h2d(bvht_ctx* ctx, void* dst_device, const void* src_host, size_t bytes);

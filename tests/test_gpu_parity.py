@@ -440,3 +440,31 @@ def test_sharded_launches_assemble_in_one_buffer():
         got = e0.memcpy_d2h(np.zeros(w * h, _ffi.HIT), buf)
         e0.device_free(buf)
     assert got.tobytes() == full.tobytes()
+
+
+@pytest.mark.parametrize("flags", STRICT_MODES, ids=MODE_IDS)
+@pytest.mark.parametrize("name,arg", [("two_armadillos", "canonical"), ("sixteen_armadillos", 7), ("big_ben_clock", None)])
+def test_axis_parallel_rays_zero_direction_components(name, arg, flags):
+    # d has exact zeros -> +-inf reciprocals (Ray::new, ray.rs:23-31).  The reference slab test handles them
+    # (aabb KATs); OUR conservative boxes (sub-BVH, tight TLAS boxes) must stay conservative for them too.
+    spec = examples.CONFIGS[name]() if arg is None else examples.CONFIGS[name](arg)
+    scene, _ = SB.oracle_scene(spec)
+    g = np.linspace(-3.0, 3.0, 97, dtype=F)
+    rays = []
+    for axis, sign in ((2, 1.0), (2, -1.0), (0, 1.0), (1, -1.0)):
+        a, b = np.meshgrid(g, g + F(1.0))
+        o = np.zeros((a.size, 3), F)
+        other = [k for k in range(3) if k != axis]
+        o[:, other[0]] = a.ravel()
+        o[:, other[1]] = b.ravel()
+        o[:, axis] = -8.0 * sign
+        d = np.zeros((a.size, 3), F)
+        d[:, axis] = sign
+        rays.append(np.concatenate([o, d, np.full((a.size, 1), O.FLT_MAX, F)], axis=1))
+    rays = np.concatenate(rays).astype(F)
+    ref = scene.trace_rays(rays, threads=NTHREADS)
+    with Engine(flags=flags) as eng:
+        SB.upload_scene(eng, scene)
+        got = eng.trace_rays(rays)
+    assert (ref["id"] != O.MISS_ID).sum() > 200
+    assert_strict(got, ref)
