@@ -44,11 +44,16 @@ struct Blas {
     DevBuf chunk_leaf, chunk_first, chunk_count, leaf_chunks, parent, scratch, counters;
     uint32_t n_chunks = 0;
     // leaf accelerator
-    DevBuf sub_nodes, sub_order, sv0, se1, se2, leaf_sub_root;
-    uint32_t n_sub = 0;
+    DevBuf sub_nodes, sub_raw, sub_order, sv0, se1, se2, leaf_sub_root;
+    uint32_t n_sub = 0, n_sub_nodes = 0;
+    // current bake: model-space ray limits and the whole-model tight box inflated for them
     float d_max = 0.0f, o_max = 0.0f;
     float tight_lo[3] = { 0, 0, 0 }, tight_hi[3] = { 0, 0, 0 };
     bool tight_valid = false;
+    // what the bake is computed from
+    double radius = 1.0, max_edge = 0.0, model_kappa = 0.0;
+    float model_lo[3] = { 0, 0, 0 }, model_hi[3] = { 0, 0, 0 };
+    bool model_valid = false;
 };
 
 } // namespace
@@ -67,6 +72,9 @@ struct bvht_ctx {
     bool blas_desc_dirty = true;
     DevBuf tlas, inst_cols, inst_blas, tlas_tight;
     uint32_t tlas_nodes_used = 0, n_inst = 0;
+    std::vector<bvht_tlas_node> h_tlas;               // host copies (tight boxes are recomputed when a bake changes)
+    std::vector<bvht_instance> h_inst;
+    double bake_center[3] = { 0.0, 0.0, 0.0 };        // camera origin the tight TLAS boxes' origin limit is centred on
     DevBuf work_counter;
     DevBuf out_buf, rays_buf, rgba_buf;               // device staging for the host-pointer entry points
     cudaStream_t aux[2] = { nullptr, nullptr };       // band pipelining: two compute streams + one copy stream
@@ -137,7 +145,7 @@ int h2d_staged(bvht_ctx* ctx, void* dst, const void* src, size_t bytes, size_t& 
 
 void free_blas(Blas& b) {
     for (DevBuf* d : { &b.tris_aos, &b.nodes, &b.v0, &b.e1, &b.e2, &b.chunk_leaf, &b.chunk_first, &b.chunk_count,
-                       &b.leaf_chunks, &b.parent, &b.scratch, &b.counters, &b.sub_nodes, &b.sub_order, &b.sv0, &b.se1,
+                       &b.leaf_chunks, &b.parent, &b.scratch, &b.counters, &b.sub_nodes, &b.sub_raw, &b.sub_order, &b.sv0, &b.se1,
                        &b.se2, &b.leaf_sub_root })
         release(*d);
     b = Blas();
@@ -187,6 +195,33 @@ int upload_u32(bvht_ctx* ctx, DevBuf& d, const std::vector<uint32_t>& v) {
     return h2d(ctx, d.p, v.data(), v.size() * 4);
 }
 
+// (Re)inflate the sub-BVH of one model for model-space rays with |d| <= d_max, |o| <= o_max (device kernel) and
+// recompute its whole-model tight box (host, rounded outwards).
+int bake_accel(bvht_ctx* ctx, Blas& b, double d_max, double o_max) {
+    LeafAccelConfig cfg;
+    double scale, abs_;
+    accel_deltas(cfg, d_max, o_max, b.radius, b.max_edge, scale, abs_);
+    float fs = (float)scale; if ((double)fs < scale) fs = std::nextafterf(fs, FLT_MAX);
+    float fa = (float)abs_; if ((double)fa < abs_) fa = std::nextafterf(fa, FLT_MAX);
+    CU(ctx, launch_inflate_sub_nodes((const float4*)b.sub_raw.p, (float4*)b.sub_nodes.p, b.n_sub_nodes, fs, fa, ctx->stream));
+    if (b.n_sub_nodes) ctx->stats.kernel_launches += 1;
+    b.d_max = (float)d_max; if ((double)b.d_max > d_max) b.d_max = std::nextafterf(b.d_max, 0.0f);
+    b.o_max = (float)o_max; if ((double)b.o_max > o_max) b.o_max = std::nextafterf(b.o_max, 0.0f);
+    b.tight_valid = b.model_valid;
+    if (b.model_valid) {
+        double delta = (double)fs * b.model_kappa + (double)fa;
+        for (int k = 0; k < 3; ++k) {
+            double lo = (double)b.model_lo[k] - delta - std::fabs((double)b.model_lo[k]) * 1e-6;
+            double hi = (double)b.model_hi[k] + delta + std::fabs((double)b.model_hi[k]) * 1e-6;
+            float flo = (float)lo; if ((double)flo > lo) flo = std::nextafterf(flo, -FLT_MAX);
+            float fhi = (float)hi; if ((double)fhi < hi) fhi = std::nextafterf(fhi, FLT_MAX);
+            b.tight_lo[k] = flo; b.tight_hi[k] = fhi;
+        }
+    }
+    ctx->blas_desc_dirty = true;
+    return BVHT_OK;
+}
+
 int build_and_upload_accel(bvht_ctx* ctx, Blas& b) {
     LeafAccelConfig cfg;
     LeafAccelHost acc;
@@ -195,11 +230,13 @@ int build_and_upload_accel(bvht_ctx* ctx, Blas& b) {
     if (acc.max_depth + 2 > (uint32_t)kSubStack)
         return fail(ctx, BVHT_ERR_MALFORMED_BVH, "leaf accelerator depth %u exceeds the stack bound %d", acc.max_depth, kSubStack);
     b.n_sub = (uint32_t)acc.order.size();
-    b.d_max = acc.d_max; b.o_max = acc.o_max;
-    memcpy(b.tight_lo, acc.tight_lo, 12); memcpy(b.tight_hi, acc.tight_hi, 12); b.tight_valid = acc.tight_valid;
+    b.n_sub_nodes = (uint32_t)(acc.sub_raw.size() / 16);
+    b.radius = acc.radius; b.max_edge = acc.max_edge; b.model_kappa = acc.model_kappa; b.model_valid = acc.model_valid;
+    memcpy(b.model_lo, acc.model_lo, 12); memcpy(b.model_hi, acc.model_hi, 12);
     int rc;
-    if ((rc = ensure(ctx, b.sub_nodes, acc.sub_nodes.size() * 4))) return rc;
-    if ((rc = h2d(ctx, b.sub_nodes.p, acc.sub_nodes.data(), acc.sub_nodes.size() * 4))) return rc;
+    if ((rc = ensure(ctx, b.sub_raw, acc.sub_raw.size() * 4))) return rc;
+    if ((rc = ensure(ctx, b.sub_nodes, acc.sub_raw.size() * 4))) return rc;
+    if ((rc = h2d(ctx, b.sub_raw.p, acc.sub_raw.data(), acc.sub_raw.size() * 4))) return rc;
     if ((rc = upload_u32(ctx, b.sub_order, acc.order))) return rc;
     if ((rc = upload_u32(ctx, b.leaf_sub_root, acc.leaf_sub_root))) return rc;
     if ((rc = ensure(ctx, b.sv0, (size_t)b.n_sub * 16))) return rc;
@@ -208,6 +245,10 @@ int build_and_upload_accel(bvht_ctx* ctx, Blas& b) {
     CU(ctx, launch_repack_sub_triangles((const float*)b.tris_aos.p, (const uint32_t*)b.sub_order.p, b.n_sub,
                                         (float4*)b.sv0.p, (float4*)b.se1.p, (float4*)b.se2.p, ctx->stream));
     if (b.n_sub) ctx->stats.kernel_launches += 1;
+    // keep the limits of the previous bake across vertex updates; first bake: generic limits
+    double d_max = b.d_max > 0.0f ? (double)b.d_max : (double)cfg.d_max;
+    double o_max = b.o_max > 0.0f ? (double)b.o_max : (double)cfg.o_max_radii * b.radius;
+    if ((rc = bake_accel(ctx, b, d_max, o_max))) return rc;
     CU(ctx, cudaStreamSynchronize(ctx->stream));     // host vectors of `acc` die here
     return BVHT_OK;
 }
@@ -270,11 +311,12 @@ bool invert_d(const double* m, double* out) {
     return true;
 }
 
-struct TightBox { float lo[3], hi[3]; float d2_max, o2_max; };      // d2_max < 0: unusable (always visit)
+// d2_max: limit on |d_w|^2; o2_max: limit on |o_w - center|^2; negative: unusable (always visit)
+struct TightBox { float lo[3], hi[3]; float d2_max, o2_max; };
 
 // Conservative WORLD-space box of the real (non-degenerate) geometry of one instance, with the world-space ray limits
 // under which the model-space limits of the leaf accelerator are implied (DESIGN.md "Tight TLAS boxes").
-TightBox instance_tight_box(const Blas& b, const float* inv_f) {
+TightBox instance_tight_box(const Blas& b, const float* inv_f, const double center[3]) {
     TightBox t; t.d2_max = -1.0f; t.o2_max = -1.0f;
     for (int k = 0; k < 3; ++k) { t.lo[k] = -FLT_MAX; t.hi[k] = FLT_MAX; }
     if (!b.tight_valid) return t;
@@ -313,7 +355,11 @@ TightBox instance_tight_box(const Blas& b, const float* inv_f) {
     }
     double sgm = std::min(std::sqrt(lam) * 1.01, std::sqrt(fro) * (1.0 + 1e-6));
     if (!(lam > 0.0)) sgm = std::sqrt(fro) * (1.0 + 1e-6);
-    double tn = std::sqrt(inv[12] * inv[12] + inv[13] * inv[13] + inv[14] * inv[14]);
+    // ray origins are limited to a ball around `center` (the camera of the last bake): for |o_w - c| <= rho,
+    // |o'| = |A o_w + t'| <= |A c + t'| + s * rho, which must stay <= o_max
+    double oc[3];
+    for (int r = 0; r < 3; ++r) oc[r] = inv[0 + r] * center[0] + inv[4 + r] * center[1] + inv[8 + r] * center[2] + inv[12 + r];
+    double tn = std::sqrt(oc[0] * oc[0] + oc[1] * oc[1] + oc[2] * oc[2]) * (1.0 + 1e-4) + 1e-6;
     if (!(sgm > 0.0)) return t;
     double dw = (double)b.d_max / sgm * (1.0 - 1e-5);
     double ow = ((double)b.o_max - tn) / sgm * (1.0 - 1e-5);
@@ -348,6 +394,94 @@ TightBox tlas_tight_rec(const bvht_tlas_node* nodes, uint32_t ni, const std::vec
     out[ni] = t; done[ni] = 1;
     return t;
 }
+
+// World-space tight boxes of every TLAS node from the host copies kept by bvht_tlas_set (accel only).
+int recompute_tlas_tight(bvht_ctx* ctx) {
+    uint32_t nodes_used = (uint32_t)ctx->h_tlas.size(), n_inst = (uint32_t)ctx->h_inst.size();
+    if (nodes_used == 0 || n_inst == 0) return BVHT_OK;
+    std::vector<TightBox> inst_t(n_inst);
+    for (uint32_t i = 0; i < n_inst; ++i)
+        inst_t[i] = instance_tight_box(ctx->blas[ctx->h_inst[i].blas_id], ctx->h_inst[i].transform_inv, ctx->bake_center);
+    TightBox unusable; unusable.d2_max = unusable.o2_max = -1.0f;
+    for (int k = 0; k < 3; ++k) { unusable.lo[k] = -FLT_MAX; unusable.hi[k] = FLT_MAX; }
+    std::vector<TightBox> node_t(nodes_used, unusable);
+    std::vector<uint8_t> done(nodes_used, 0);
+    tlas_tight_rec(ctx->h_tlas.data(), 0, inst_t, node_t, done);            // unreachable nodes keep `unusable`
+    std::vector<float> flat((size_t)nodes_used * 8);
+    for (uint32_t i = 0; i < nodes_used; ++i) {
+        float* f = &flat[(size_t)i * 8];
+        memcpy(f + 0, node_t[i].lo, 12); f[3] = node_t[i].d2_max;
+        memcpy(f + 4, node_t[i].hi, 12); f[7] = node_t[i].o2_max;
+    }
+    int rc = ensure(ctx, ctx->tlas_tight, flat.size() * 4);
+    if (rc) return rc;
+    return h2d(ctx, ctx->tlas_tight.p, flat.data(), flat.size() * 4);       // pageable: staged before return
+}
+
+double sigma_max_3x3(const double* m /* column-major 4x4, upper-left 3x3 */) {
+    double ata[3][3], fro = 0.0;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+        ata[i][j] = 0.0;
+        for (int r = 0; r < 3; ++r) ata[i][j] += m[i * 4 + r] * m[j * 4 + r];
+    }
+    for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) fro += m[c * 4 + r] * m[c * 4 + r];
+    double v[3] = { 0.57, 0.58, 0.59 }, lam = 0.0;
+    for (int it = 0; it < 200; ++it) {
+        double w[3] = { 0, 0, 0 };
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) w[i] += ata[i][j] * v[j];
+        double n = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+        if (!(n > 0.0)) break;
+        lam = n / std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        for (int i = 0; i < 3; ++i) v[i] = w[i] / n;
+    }
+    double s = std::sqrt(fro) * (1.0 + 1e-6);
+    if (lam > 0.0) s = std::min(std::sqrt(lam) * 1.01, s);
+    return s;
+}
+
+// Primary rays all start at the camera position with |d_w| <= sigma_max(view_inv): the limits each model's bake must
+// cover are therefore known before the launch.  Re-bake (a 64 B/node streaming kernel + a few host boxes) when the
+// current bake does not cover them or is more than 2.5x looser than needed; the tighter the limits, the smaller
+// the conservative inflation of every sub box (leaf_accel.hpp accel_deltas).
+int ensure_bake(bvht_ctx* ctx, const bvht_camera* cam) {
+    if (!accel_on(ctx) || ctx->h_inst.empty()) return BVHT_OK;
+    double vinv[16];
+    for (int i = 0; i < 16; ++i) { vinv[i] = cam->view_matrix_inv[i]; if (!std::isfinite(vinv[i])) return BVHT_OK; }
+    double dw = sigma_max_3x3(vinv) * (1.0 + 1e-4);            // eye directions are normalised (camera.rs:999)
+    const double ow[3] = { vinv[12], vinv[13], vinv[14] };     // world origin = view_inv * (0,0,0,1)
+    std::vector<double> need_d(ctx->blas.size(), 0.0), need_o(ctx->blas.size(), 0.0);
+    for (const bvht_instance& in : ctx->h_inst) {
+        double inv[16]; bool finite = true;
+        for (int i = 0; i < 16; ++i) { inv[i] = in.transform_inv[i]; finite = finite && std::isfinite(inv[i]); }
+        if (!finite) continue;
+        double o[3];
+        for (int r = 0; r < 3; ++r) o[r] = inv[0 + r] * ow[0] + inv[4 + r] * ow[1] + inv[8 + r] * ow[2] + inv[12 + r];
+        double on = std::sqrt(o[0] * o[0] + o[1] * o[1] + o[2] * o[2]) * (1.0 + 1e-4) + 1e-6;
+        double dn = sigma_max_3x3(inv) * dw;
+        need_d[in.blas_id] = std::max(need_d[in.blas_id], dn);
+        need_o[in.blas_id] = std::max(need_o[in.blas_id], on);
+    }
+    bool changed = false;
+    for (size_t i = 0; i < ctx->blas.size(); ++i) {
+        Blas& b = ctx->blas[i];
+        if (!b.alive || b.n_sub_nodes == 0 || !(need_d[i] > 0.0)) continue;
+        bool too_small = need_d[i] > 0.98 * (double)b.d_max || need_o[i] > 0.98 * (double)b.o_max;
+        // the inflation is proportional to d_max * (o_max + radius + max_edge)
+        double cur = (double)b.d_max * ((double)b.o_max + b.radius + b.max_edge);
+        double want = need_d[i] * 1.05 * (need_o[i] * 1.25 + b.radius + b.max_edge);
+        if (too_small || cur > 2.5 * want) {
+            int rc = bake_accel(ctx, b, need_d[i] * 1.05, need_o[i] * 1.25 + 1e-3 * b.radius);
+            if (rc) return rc;
+            changed = true;
+        }
+    }
+    if (ow[0] != ctx->bake_center[0] || ow[1] != ctx->bake_center[1] || ow[2] != ctx->bake_center[2]) {
+        ctx->bake_center[0] = ow[0]; ctx->bake_center[1] = ow[1]; ctx->bake_center[2] = ow[2];
+        changed = true;
+    }
+    if (changed) return recompute_tlas_tight(ctx);
+    return BVHT_OK;
+}
 bool fast_on(const bvht_ctx* ctx) { return (ctx->flags & BVHT_FLAG_FAST) != 0; }
 
 int fill_scene(bvht_ctx* ctx, SceneDev& s) {
@@ -357,6 +491,7 @@ int fill_scene(bvht_ctx* ctx, SceneDev& s) {
     if (rc) return rc;
     s.tlas = (const float4*)ctx->tlas.p;
     s.tlas_tight = (const float4*)ctx->tlas_tight.p;
+    s.tight_center[0] = (float)ctx->bake_center[0]; s.tight_center[1] = (float)ctx->bake_center[1]; s.tight_center[2] = (float)ctx->bake_center[2];
     s.inst_cols = (const float4*)ctx->inst_cols.p;
     s.inst_blas = (const uint32_t*)ctx->inst_blas.p;
     s.blas = (const BlasDesc*)ctx->blas_desc.p;
@@ -681,23 +816,11 @@ int bvht_tlas_set(bvht_ctx* ctx, const bvht_tlas_node* nodes, uint32_t nodes_use
         if ((rc = h2d(ctx, ctx->inst_cols.p, ic, (size_t)n_instances * 64))) return rc;
         if ((rc = h2d(ctx, ctx->inst_blas.p, ib, (size_t)n_instances * 4))) return rc;
     }
-    if (accel_on(ctx) && n_instances > 0) {
-        std::vector<TightBox> inst_t(n_instances);
-        for (uint32_t i = 0; i < n_instances; ++i) inst_t[i] = instance_tight_box(ctx->blas[instances[i].blas_id], instances[i].transform_inv);
-        TightBox unusable; unusable.d2_max = unusable.o2_max = -1.0f;
-        for (int k = 0; k < 3; ++k) { unusable.lo[k] = -FLT_MAX; unusable.hi[k] = FLT_MAX; }
-        std::vector<TightBox> node_t(nodes_used, unusable);
-        std::vector<uint8_t> done(nodes_used, 0);
-        tlas_tight_rec(nodes, 0, inst_t, node_t, done);                     // unreachable nodes keep `unusable`
-        std::vector<float> flat((size_t)nodes_used * 8);
-        for (uint32_t i = 0; i < nodes_used; ++i) {
-            float* f = &flat[(size_t)i * 8];
-            memcpy(f + 0, node_t[i].lo, 12); f[3] = node_t[i].d2_max;
-            memcpy(f + 4, node_t[i].hi, 12); f[7] = node_t[i].o2_max;
-        }
-        if ((rc = ensure(ctx, ctx->tlas_tight, flat.size() * 4))) return rc;
-        if ((rc = h2d(ctx, ctx->tlas_tight.p, flat.data(), flat.size() * 4))) return rc;   // pageable: staged before return
-    }
+    ctx->h_tlas.assign(nodes, nodes + nodes_used);
+    ctx->h_inst.assign(instances, instances + n_instances);
+    ctx->tlas_nodes_used = nodes_used;
+    ctx->n_inst = n_instances;
+    if (accel_on(ctx) && n_instances > 0) { if ((rc = recompute_tlas_tight(ctx))) return rc; }
     ctx->tlas_nodes_used = nodes_used;
     ctx->n_inst = n_instances;
     return BVHT_OK;
@@ -766,6 +889,7 @@ int bvht_render_frame_device(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
     int rc = check_frame_args(ctx, camera, width, height, tile, region);
     if (rc) return rc;
     cudaSetDevice(ctx->device);
+    if ((rc = ensure_bake(ctx, camera))) return rc;
     SceneDev scene;
     if ((rc = fill_scene(ctx, scene))) return rc;
     ctx->stats.last_trace_rays = 0;
@@ -832,6 +956,7 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
     int rc = check_frame_args(ctx, camera, width, height, tile, region);
     if (rc) return rc;
     cudaSetDevice(ctx->device);
+    if ((rc = ensure_bake(ctx, camera))) return rc;
     SceneDev scene;
     if ((rc = fill_scene(ctx, scene))) return rc;
     ctx->stats.last_trace_rays = 0;
@@ -1009,6 +1134,7 @@ int bvht_debug_trace_stats(bvht_ctx* ctx, const bvht_camera* camera, uint32_t wi
     cudaSetDevice(ctx->device);
     memset(counters_out, 0, 16 * sizeof(uint64_t));
     if (region.x0 >= region.x1 || region.y0 >= region.y1) return BVHT_OK;
+    if ((rc = ensure_bake(ctx, camera))) return rc;
     PrimaryParams p;
     memset(&p, 0, sizeof p);
     if ((rc = fill_scene(ctx, p.scene))) return rc;

@@ -36,13 +36,14 @@ struct BlasDesc {
 
 struct SceneDev {
     const float4*   tlas_tight;  // accel only, 2 float4 per TLAS node: conservative world box of the REAL geometry below the
-                                 //   node {lo.xyz, max |d|^2} {hi.xyz, max |o|^2} (limits under which it may be used)
+                                 //   node {lo.xyz, max |d_w|^2} {hi.xyz, max |o_w - tight_center|^2} (limits under which it may be used)
     const float4*   tlas;        // 2 float4 per TLAS node
     const float4*   inst_cols;   // 4 float4 per instance: columns of the inverse transform
     const uint32_t* inst_blas;   // blas id per instance
     const BlasDesc* blas;
     uint32_t        n_inst;
     uint32_t        flags;
+    float           tight_center[3];   // the tight boxes' origin limit is |o_w - tight_center|^2 <= hi.w
 };
 
 struct CameraDev {

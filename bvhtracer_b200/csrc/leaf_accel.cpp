@@ -30,8 +30,6 @@ struct Builder {
     const LeafAccelConfig& cfg;
     LeafAccelHost& out;
     std::vector<TriInfo> info;       // per reference primitive
-    double delta_scale = 0.0;        // delta = delta_scale * kappa + delta_abs
-    double delta_abs = 0.0;
     uint32_t depth_limit = 28;      // SAH splits up to here, balanced median splits below: depth <= 28 + log2(n)
 
     Builder(const float* t, const LeafAccelConfig& c, LeafAccelHost& o) : tris(t), cfg(c), out(o) {}
@@ -41,18 +39,6 @@ struct Builder {
     void range_box(const std::vector<uint32_t>& idx, uint32_t b, uint32_t e, Box& box, double& kappa) const {
         box.reset(); kappa = 0.0;
         for (uint32_t i = b; i < e; ++i) { box.grow(info[idx[i]].box); kappa = std::max(kappa, info[idx[i]].kappa); }
-    }
-
-    // conservative outward inflation, rounded away from the box
-    void write_box(float* lo_dst, float* hi_dst, const Box& box, double kappa) const {
-        double delta = delta_scale * kappa + delta_abs;
-        for (int k = 0; k < 3; ++k) {
-            double lo = (double)box.lo[k] - delta - std::fabs((double)box.lo[k]) * 1e-6;
-            double hi = (double)box.hi[k] + delta + std::fabs((double)box.hi[k]) * 1e-6;
-            float flo = (float)lo; if ((double)flo > lo) flo = std::nextafterf(flo, -FLT_MAX);
-            float fhi = (float)hi; if ((double)fhi < hi) fhi = std::nextafterf(fhi, FLT_MAX);
-            lo_dst[k] = flo; hi_dst[k] = fhi;
-        }
     }
 
     // Partition idx[b,e) into two non-empty halves; binned SAH (16 bins) with a median fallback.
@@ -112,8 +98,8 @@ struct Builder {
     // `base` = sub position of idx[0] in the BLAS-wide order array.
     uint32_t build(std::vector<uint32_t>& idx, uint32_t b, uint32_t e, uint32_t base, uint32_t depth) {
         out.max_depth = std::max(out.max_depth, depth + 1);
-        uint32_t node = (uint32_t)(out.sub_nodes.size() / 16);
-        out.sub_nodes.resize(out.sub_nodes.size() + 16, 0.0f);
+        uint32_t node = (uint32_t)(out.sub_raw.size() / 16);
+        out.sub_raw.resize(out.sub_raw.size() + 16, 0.0f);
         uint32_t mid = split(idx, b, e, depth);
         uint32_t refs[2];
         uint32_t rb[2] = { b, mid }, re[2] = { mid, e };
@@ -130,12 +116,12 @@ struct Builder {
         for (int c = 0; c < 2; ++c) {
             Box box; double kappa;
             range_box(idx, rb[c], re[c], box, kappa);
-            write_box(rec + 8 * c, rec + 8 * c + 4, box, kappa);
+            float kf = (float)kappa; if ((double)kf < kappa) kf = std::nextafterf(kf, FLT_MAX);
+            for (int k = 0; k < 3; ++k) { rec[8 * c + k] = box.lo[k]; rec[8 * c + 4 + k] = box.hi[k]; }
+            rec[8 * c + 3] = kf;
+            std::memcpy(&rec[8 * c + 7], &refs[c], 4);
         }
-        std::memcpy(&rec[3], &refs[0], 4);
-        std::memcpy(&rec[7], &refs[1], 4);
-        rec[11] = 0.0f; rec[15] = 0.0f;
-        std::memcpy(&out.sub_nodes[(size_t)node * 16], rec, sizeof rec);
+        std::memcpy(&out.sub_raw[(size_t)node * 16], rec, sizeof rec);
         return node;
     }
 };
@@ -174,20 +160,18 @@ bool build_leaf_accel(const float* tris, uint32_t n_tris, const void* nodes_v, u
         }
     }
     if (!(radius > 0.0)) radius = 1.0;
-    const double eps = 5.9604644775390625e-08;      // 2^-24
-    out.d_max = cfg.d_max;
-    out.o_max = (float)(cfg.o_max_radii * radius);
-    double s_max = (double)out.o_max + radius + max_edge;
-    bld.delta_scale = cfg.c_mt * eps * cfg.d_max * s_max / 1e-4;     // residual of Triangle::intersect at |det| = 1e-4
-    bld.delta_abs = 16.0 * eps * s_max;                               // rounding of s = o - v0 and of the slab test
-
-    {   // whole-model tight box
+    out.radius = radius;
+    out.max_edge = max_edge;
+    {   // whole-model raw box over the non-degenerate triangles
         Box mb; mb.reset(); double kmax = 0.0; bool any = false;
         for (uint32_t i = 0; i < n_tris; ++i) {
             if (!(bld.info[i].kappa > 0.0)) continue;
             mb.grow(bld.info[i].box); kmax = std::max(kmax, bld.info[i].kappa); any = true;
         }
-        if (any) { bld.write_box(out.tight_lo, out.tight_hi, mb, kmax); out.tight_valid = true; }
+        if (any) {
+            for (int k = 0; k < 3; ++k) { out.model_lo[k] = mb.lo[k]; out.model_hi[k] = mb.hi[k]; }
+            out.model_kappa = kmax; out.model_valid = true;
+        }
     }
 
     std::vector<uint32_t> idx;

@@ -23,25 +23,41 @@
 namespace bvht {
 
 struct LeafAccelHost {
-    std::vector<float>    sub_nodes;      // 16 floats per sub node: c0.lo.xyz, ref0 | c0.hi.xyz, ref1 | c1.lo.xyz, 0 | c1.hi.xyz, 0
+    // RAW (un-inflated) sub nodes, 16 floats each: c0.lo.xyz, kappa0 | c0.hi.xyz, ref0 | c1.lo.xyz, kappa1 | c1.hi.xyz, ref1
+    // kappa = max |e1| |e2| over the child's triangles.  The device inflates them for the current ray limits
+    // (inflate_sub_nodes kernel), see accel_deltas().
+    std::vector<float>    sub_raw;
     std::vector<uint32_t> order;          // sub position -> reference primitive index
     std::vector<uint32_t> leaf_sub_root;  // per reference node: sub root node index, 0xFFFFFFFF = brute force
-    float d_max = 0.0f;                   // limits under which the inflation is valid
-    float o_max = 0.0f;
     uint32_t max_depth = 0;
-    // box of the NON-degenerate triangles of the whole model, inflated like the sub boxes: under the same limits no
-    // triangle can be accepted by a ray that misses it (the 999-sentinel is degenerate and never accepted)
-    float tight_lo[3] = { 0, 0, 0 }, tight_hi[3] = { 0, 0, 0 };
-    bool  tight_valid = false;
+    double radius = 1.0;                  // max vertex norm over non-degenerate triangles
+    double max_edge = 0.0;
+    // raw box of the NON-degenerate triangles of the whole model (the 999-sentinel is degenerate: never accepted)
+    float  model_lo[3] = { 0, 0, 0 }, model_hi[3] = { 0, 0, 0 };
+    double model_kappa = 0.0;
+    bool   model_valid = false;
 };
 
 struct LeafAccelConfig {
     uint32_t min_leaf_tris = 12;   // reference leaves smaller than this stay brute force
     uint32_t max_sub_leaf = 4;     // triangles per sub leaf (<= 8: 3-bit count field)
-    float    d_max = 2.0f;         // |d| limit in model space (instance scale >= 0.5)
-    float    o_max_radii = 16.0f;  // |o| limit as a multiple of the model radius
+    float    d_max = 2.0f;         // default |d| limit in model space (instance scale >= 0.5)
+    float    o_max_radii = 16.0f;  // default |o| limit as a multiple of the model radius
     float    c_mt = 80.0f;         // safety constant of the Moeller-Trumbore residual bound (first-order estimate ~40)
 };
+
+// Inflation of a box whose triangles have edge product <= kappa, valid for model-space rays with |d| <= d_max and
+// |o| <= o_max:  delta = scale * kappa + abs.
+//   scale * kappa : residual |o + t d - (v0 + u e1 + v e2)| of Triangle::intersect in f32 at its |det| >= 1e-4 cut-off,
+//                   c_mt * eps * d_max * (o_max + radius + max_edge) * kappa / 1e-4
+//   abs           : rounding of s = o - v0 and of the slab test itself, 16 * eps * (o_max + radius + max_edge)
+inline void accel_deltas(const LeafAccelConfig& cfg, double d_max, double o_max, double radius, double max_edge,
+                         double& scale, double& abs_) {
+    const double eps = 5.9604644775390625e-08;      // 2^-24
+    double s_max = o_max + radius + max_edge;
+    scale = cfg.c_mt * eps * d_max * s_max / 1e-4;
+    abs_ = 16.0 * eps * s_max;
+}
 
 // tris: n_tris x 9 floats in reference order; nodes: reference nodes (bvht_bvh_node layout: min[3], max[3], count, left_first)
 bool build_leaf_accel(const float* tris, uint32_t n_tris, const void* nodes, uint32_t nodes_used,

@@ -117,9 +117,23 @@ __device__ __forceinline__ bool moller_trumbore(const float4 v0, const float4 e1
     float nz = r.dx * e2.y - r.dy * e2.x;
     float area = (e1.x * nx + e1.y * ny) + e1.z * nz;
     if (fabsf(area) < threshold) return false;
-    float f = 1.0f / area;
     float sx = r.ox - v0.x, sy = r.oy - v0.y, sz = r.oz - v0.z;
-    float u = f * ((sx * nx + sy * ny) + sz * nz);
+    float X = (sx * nx + sy * ny) + sz * nz;
+    // Exact early outs for the reference's `u = (1 / area) * X; if u < 0 || u > 1 { return None }` WITHOUT the IEEE
+    // divide (85 % of all tests leave here).  With a = |area| in [1e-4, 2^59] and x = |X|:
+    //  * signs differ and x >= 2^-60: f = fl(1/area) has |f| >= 2^-60, so fl(f * X) is a negative NORMAL number: u < 0.
+    //    (Smaller x could round to -0.0, which the reference does not reject: those take the full path.)
+    //  * signs equal and x > fl(a * (1 + 2^-20)): then x > a (1 + 2^-21), fl(1/a) >= (1 - 2^-24) / a, so
+    //    fl(1/a) * x > 1 + 2^-22 and its rounding is still > 1: u > 1.
+    // Everything else (including NaNs, for which every comparison below is false) computes f and u exactly as written.
+    {
+        float a = fabsf(area), x = fabsf(X);
+        bool opposite = (__float_as_int(area) ^ __float_as_int(X)) < 0;
+        if (opposite) { if (x >= 8.673617379884035e-19f && a <= 5.764607523034235e17f) return false; }
+        else if (x > a * 1.00000095367431640625f) return false;
+    }
+    float f = 1.0f / area;
+    float u = f * X;
     if (u < 0.0f || u > 1.0f) return false;
     float qx = sy * e1.z - sz * e1.y;
     float qy = sz * e1.x - sx * e1.z;
@@ -291,7 +305,10 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
     RayM wf = w;
     if (ACCEL) {
         wd2 = (w.dx * w.dx + w.dy * w.dy) + w.dz * w.dz;
-        wo2 = (w.ox * w.ox + w.oy * w.oy) + w.oz * w.oz;
+        {
+            float cx = w.ox - S.tight_center[0], cy = w.oy - S.tight_center[1], cz = w.oz - S.tight_center[2];
+            wo2 = (cx * cx + cy * cy) + cz * cz;
+        }
         ray_prepare_fma(wf);
         float4 t0 = ldg4(S.tlas_tight + 0), t1 = ldg4(S.tlas_tight + 1);
         float tt;
@@ -341,27 +358,25 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
             st.add(1);
             uint32_t li = (lr & 0xFFFF0000u) >> 16;    // left_blas()  = upper half (tlas.rs:25-27)
             uint32_t ri = lr & 0x0000FFFFu;            // right_blas() = lower half (tlas.rs:30-32)
-            float4 l0 = ldg4(S.tlas + 2 * (size_t)li), l1 = ldg4(S.tlas + 2 * (size_t)li + 1);
-            float4 r0 = ldg4(S.tlas + 2 * (size_t)ri), r1 = ldg4(S.tlas + 2 * (size_t)ri + 1);
-            float ld, rd;
-            bool lh = slab_test(l0, l1, w, closest, ld);
-            bool rh = slab_test(r0, r1, w, closest, rd);
+            bool lt = true, rt = true;
+            if (ACCEL) {
+                // tight boxes first (one FMA per plane): a child whose real geometry the ray cannot reach closer than
+                // `closest` is dropped without evaluating the reference's box test for it
+                float4 a0 = ldg4(S.tlas_tight + 2 * (size_t)li), a1 = ldg4(S.tlas_tight + 2 * (size_t)li + 1);
+                float4 b0 = ldg4(S.tlas_tight + 2 * (size_t)ri), b1 = ldg4(S.tlas_tight + 2 * (size_t)ri + 1);
+                float tt;
+                if (wd2 <= a0.w && wo2 <= a1.w) lt = slab_test_sub(a0, a1, wf, closest, tt);
+                if (wd2 <= b0.w && wo2 <= b1.w) rt = slab_test_sub(b0, b1, wf, closest, tt);
+            }
+            float4 l0 = n0, l1 = n1, r0 = n0, r1 = n1;
+            float ld = 0.0f, rd = 0.0f;
+            bool lh = false, rh = false;
+            if (lt) { l0 = ldg4(S.tlas + 2 * (size_t)li); l1 = ldg4(S.tlas + 2 * (size_t)li + 1); lh = slab_test(l0, l1, w, closest, ld); }
+            if (rt) { r0 = ldg4(S.tlas + 2 * (size_t)ri); r1 = ldg4(S.tlas + 2 * (size_t)ri + 1); rh = slab_test(r0, r1, w, closest, rd); }
             float lkey = lh ? ld : FLT_MAX;
             float rkey = rh ? rd : FLT_MAX;
+            // the order between two children only matters when both are entered, and then both keys are the reference's
             bool left_first = lkey < rkey;
-            if (ACCEL) {
-                // drop children whose tight box cannot contain an accepted hit closer than `closest`
-                if (lh) {
-                    float4 t0 = ldg4(S.tlas_tight + 2 * (size_t)li), t1 = ldg4(S.tlas_tight + 2 * (size_t)li + 1);
-                    float tt;
-                    if (wd2 <= t0.w && wo2 <= t1.w) lh = slab_test_sub(t0, t1, wf, closest, tt);
-                }
-                if (rh) {
-                    float4 t0 = ldg4(S.tlas_tight + 2 * (size_t)ri), t1 = ldg4(S.tlas_tight + 2 * (size_t)ri + 1);
-                    float tt;
-                    if (wd2 <= t0.w && wo2 <= t1.w) rh = slab_test_sub(t0, t1, wf, closest, tt);
-                }
-            }
             bool near_hit = left_first ? lh : rh;
             bool far_hit = left_first ? rh : lh;
             if (near_hit) {

@@ -44,7 +44,44 @@ repack_sub_triangles_kernel(const float* __restrict__ tris, const uint32_t* __re
     se2[i] = make_float4(__ldg(t + 6) - ax, __ldg(t + 7) - ay, __ldg(t + 8) - az, 0.0f);
 }
 
+// Bake the sub-BVH for the current ray limits: out = raw boxes grown by delta = scale * kappa + abs (leaf_accel.hpp
+// accel_deltas), every operation rounded AWAY from the box (directed-rounding intrinsics), plus a relative 1e-6.
+// 64 B read + 64 B written per sub node; runs at upload and whenever the limits change (bvht_api.cu ensure_bake).
+__global__ void __launch_bounds__(kRepackBlock)
+inflate_sub_nodes_kernel(const float4* __restrict__ raw, float4* __restrict__ out, uint32_t n_nodes, float scale, float abs_) {
+    uint32_t i = blockIdx.x * kRepackBlock + threadIdx.x;
+    if (i >= n_nodes) return;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        float4 lo = __ldg(raw + 4 * (size_t)i + 2 * c);        // lo.xyz, kappa
+        float4 hi = __ldg(raw + 4 * (size_t)i + 2 * c + 1);    // hi.xyz, ref
+        float d = __fmaf_ru(scale, lo.w, abs_);
+        float4 olo, ohi;
+        olo.x = __fsub_rd(__fsub_rd(lo.x, d), __fmul_ru(fabsf(lo.x), 1e-6f));
+        olo.y = __fsub_rd(__fsub_rd(lo.y, d), __fmul_ru(fabsf(lo.y), 1e-6f));
+        olo.z = __fsub_rd(__fsub_rd(lo.z, d), __fmul_ru(fabsf(lo.z), 1e-6f));
+        ohi.x = __fadd_ru(__fadd_ru(hi.x, d), __fmul_ru(fabsf(hi.x), 1e-6f));
+        ohi.y = __fadd_ru(__fadd_ru(hi.y, d), __fmul_ru(fabsf(hi.y), 1e-6f));
+        ohi.z = __fadd_ru(__fadd_ru(hi.z, d), __fmul_ru(fabsf(hi.z), 1e-6f));
+        // trace layout: n[0] = c0.lo | ref0, n[1] = c0.hi | ref1, n[2] = c1.lo | 0, n[3] = c1.hi | 0
+        olo.w = 0.0f; ohi.w = 0.0f;
+        out[4 * (size_t)i + 2 * c] = olo;
+        out[4 * (size_t)i + 2 * c + 1] = ohi;
+    }
+    // child references live in the .w of the first two float4s
+    float r0 = __ldg(raw + 4 * (size_t)i + 1).w, r1 = __ldg(raw + 4 * (size_t)i + 3).w;
+    reinterpret_cast<float*>(out + 4 * (size_t)i)[3] = r0;
+    reinterpret_cast<float*>(out + 4 * (size_t)i + 1)[3] = r1;
+}
+
 } // namespace
+
+cudaError_t launch_inflate_sub_nodes(const float4* raw, float4* out, uint32_t n_nodes, float scale, float abs_, cudaStream_t s) {
+    if (n_nodes == 0) return cudaSuccess;
+    int grid = (int)((n_nodes + kRepackBlock - 1) / kRepackBlock);
+    inflate_sub_nodes_kernel<<<grid, kRepackBlock, 0, s>>>(raw, out, n_nodes, scale, abs_);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_repack_triangles(const float* tris_aos, uint32_t n_tris, float4* v0, float4* e1, float4* e2, cudaStream_t s) {
     if (n_tris == 0) return cudaSuccess;

@@ -468,3 +468,29 @@ def test_axis_parallel_rays_zero_direction_components(name, arg, flags):
         got = eng.trace_rays(rays)
     assert (ref["id"] != O.MISS_ID).sum() > 200
     assert_strict(got, ref)
+
+
+def test_accel_rebake_across_camera_distances():
+    # The conservative inflation of the sub-BVH is baked for the current camera (ensure_bake): move the camera far away,
+    # back, and very close; every frame must stay bit-identical to the oracle, and arbitrary rays traced afterwards
+    # (outside the baked limits -> brute-force leaves) must too.
+    spec = examples.two_armadillos("canonical")
+    scene, _ = SB.oracle_scene(spec)
+    w, h = 192, 108
+    with Engine(flags=FLAG_STRICT | FLAG_LEAF_ACCEL) as eng:
+        SB.upload_scene(eng, scene)
+        for z, near in ((-2.5, 2.0), (-60.0, 60.0), (-2.5, 2.0), (-1.3, 0.5), (-400.0, 900.0), (-2.5, 2.0)):
+            cam = O.camera_symmetric_fov(90.0, 1.0, near, [0, 1, z], [0, 0, 1], [1, 0, 0], [0, 1, 0])
+            ref = scene.render(cam, w, h, threads=NTHREADS)
+            got = eng.trace_primary(SB.to_ffi_camera(cam), w, h)
+            assert_strict(got, ref)
+        rng = np.random.default_rng(7)
+        n = 3000
+        o = (rng.normal(size=(n, 3)) * 300).astype(F)             # far outside any baked |o| limit
+        d = (-o / np.linalg.norm(o, axis=1, keepdims=True)).astype(F)
+        d += (rng.normal(size=(n, 3)) * 0.004).astype(F)
+        rays = np.concatenate([o, d, np.full((n, 1), O.FLT_MAX, F)], axis=1).astype(F)
+        ref = scene.trace_rays(rays, threads=NTHREADS)
+        got = eng.trace_rays(rays)
+        assert (ref["id"] != O.MISS_ID).sum() > 50
+        assert_strict(got, ref)
