@@ -39,12 +39,12 @@ struct Blas {
     uint32_t n_tris = 0, nodes_used = 0;
     std::vector<bvht_bvh_node> h_nodes;     // host copy of the uploaded node pool (topology for validation / accel)
     std::vector<float> h_tris;              // host copy of the vertices (needed to rebuild the leaf accelerator)
-    DevBuf tris_aos, nodes, v0, e1, e2;
+    DevBuf tris_aos, nodes, tri;
     // refit plan
     DevBuf chunk_leaf, chunk_first, chunk_count, leaf_chunks, parent, scratch, counters;
     uint32_t n_chunks = 0;
     // leaf accelerator
-    DevBuf sub_nodes, sub_raw, sub_order, sv0, se1, se2, leaf_sub_root;
+    DevBuf sub_nodes, sub_raw, sub_order, stri, leaf_sub_root;
     uint32_t n_sub = 0, n_sub_nodes = 0;
     // current bake: model-space ray limits and the whole-model tight box inflated for them
     float d_max = 0.0f, o_max = 0.0f;
@@ -144,9 +144,9 @@ int h2d_staged(bvht_ctx* ctx, void* dst, const void* src, size_t bytes, size_t& 
 }
 
 void free_blas(Blas& b) {
-    for (DevBuf* d : { &b.tris_aos, &b.nodes, &b.v0, &b.e1, &b.e2, &b.chunk_leaf, &b.chunk_first, &b.chunk_count,
-                       &b.leaf_chunks, &b.parent, &b.scratch, &b.counters, &b.sub_nodes, &b.sub_raw, &b.sub_order, &b.sv0, &b.se1,
-                       &b.se2, &b.leaf_sub_root })
+    for (DevBuf* d : { &b.tris_aos, &b.nodes, &b.tri, &b.chunk_leaf, &b.chunk_first, &b.chunk_count,
+                       &b.leaf_chunks, &b.parent, &b.scratch, &b.counters, &b.sub_nodes, &b.sub_raw, &b.sub_order, &b.stri,
+                       &b.leaf_sub_root })
         release(*d);
     b = Blas();
 }
@@ -239,11 +239,9 @@ int build_and_upload_accel(bvht_ctx* ctx, Blas& b) {
     if ((rc = h2d(ctx, b.sub_raw.p, acc.sub_raw.data(), acc.sub_raw.size() * 4))) return rc;
     if ((rc = upload_u32(ctx, b.sub_order, acc.order))) return rc;
     if ((rc = upload_u32(ctx, b.leaf_sub_root, acc.leaf_sub_root))) return rc;
-    if ((rc = ensure(ctx, b.sv0, (size_t)b.n_sub * 16))) return rc;
-    if ((rc = ensure(ctx, b.se1, (size_t)b.n_sub * 16))) return rc;
-    if ((rc = ensure(ctx, b.se2, (size_t)b.n_sub * 16))) return rc;
-    CU(ctx, launch_repack_sub_triangles((const float*)b.tris_aos.p, (const uint32_t*)b.sub_order.p, b.n_sub,
-                                        (float4*)b.sv0.p, (float4*)b.se1.p, (float4*)b.se2.p, ctx->stream));
+    if ((rc = ensure(ctx, b.stri, (size_t)b.n_sub * 48))) return rc;
+    CU(ctx, launch_repack_sub_triangles((const float*)b.tris_aos.p, (const uint32_t*)b.sub_order.p, b.n_sub, (float4*)b.stri.p,
+                                        ctx->stream));
     if (b.n_sub) ctx->stats.kernel_launches += 1;
     // keep the limits of the previous bake across vertex updates; first bake: generic limits
     double d_max = b.d_max > 0.0f ? (double)b.d_max : (double)cfg.d_max;
@@ -257,13 +255,10 @@ int upload_vertices(bvht_ctx* ctx, Blas& b, const float* tris) {
     int rc;
     size_t bytes = (size_t)b.n_tris * 36;
     if ((rc = ensure(ctx, b.tris_aos, bytes))) return rc;
-    if ((rc = ensure(ctx, b.v0, (size_t)b.n_tris * 16))) return rc;
-    if ((rc = ensure(ctx, b.e1, (size_t)b.n_tris * 16))) return rc;
-    if ((rc = ensure(ctx, b.e2, (size_t)b.n_tris * 16))) return rc;
+    if ((rc = ensure(ctx, b.tri, (size_t)b.n_tris * 48))) return rc;
     b.h_tris.assign(tris, tris + (size_t)b.n_tris * 9);
     if ((rc = h2d(ctx, b.tris_aos.p, b.h_tris.data(), bytes))) return rc;
-    CU(ctx, launch_repack_triangles((const float*)b.tris_aos.p, b.n_tris, (float4*)b.v0.p, (float4*)b.e1.p, (float4*)b.e2.p,
-                                    ctx->stream));
+    CU(ctx, launch_repack_triangles((const float*)b.tris_aos.p, b.n_tris, (float4*)b.tri.p, ctx->stream));
     if (b.n_tris) ctx->stats.kernel_launches += 1;
     return BVHT_OK;
 }
@@ -277,9 +272,9 @@ int refresh_blas_desc(bvht_ctx* ctx) {
         if (!b.alive) continue;
         BlasDesc& o = d[i];
         o.nodes = (const float4*)b.nodes.p;
-        o.v0 = (const float4*)b.v0.p; o.e1 = (const float4*)b.e1.p; o.e2 = (const float4*)b.e2.p;
+        o.tri = (const float4*)b.tri.p;
         o.sub_nodes = (const float4*)b.sub_nodes.p;
-        o.sv0 = (const float4*)b.sv0.p; o.se1 = (const float4*)b.se1.p; o.se2 = (const float4*)b.se2.p;
+        o.stri = (const float4*)b.stri.p;
         o.leaf_sub_root = (const uint32_t*)b.leaf_sub_root.p;
         o.n_tris = b.n_tris; o.nodes_used = b.nodes_used;
         o.accel_d_max = b.d_max; o.accel_o_max = b.o_max;

@@ -2,7 +2,7 @@
 //
 // Everything here is the UPLOADED form of the reference's in-memory objects (DESIGN.md "Data layout"):
 //   BvhNode  (bvh.rs:88-134, 32 B)  -> 2 x float4 : {min.xyz, left_first}, {max.xyz, prim_count}
-//   Triangle (triangle.rs:9-16, 36 B AoS) -> three float4 streams v0 | e1 = v1 - v0 | e2 = v2 - v0
+//   Triangle (triangle.rs:9-16, 36 B) -> 3 float4 per triangle: v0 | e1 = v1 - v0 | e2 = v2 - v0  (48 B, 16 B aligned)
 //            (one IEEE subtraction each, exactly what Triangle::intersect computes first, triangle.rs:43-44)
 //   TlasNode (tlas.rs:41-46, 32 B)  -> 2 x float4 : {min.xyz, left_right}, {max.xyz, blas}
 //   SceneObject inverse transform (scene_object.rs:78-89) -> 4 x float4 columns
@@ -19,18 +19,15 @@ constexpr int kSubStack  = 48;   // leaf sub-BVH (built by us, depth bounded at 
 // One per uploaded model.  Pointers are device addresses.
 struct BlasDesc {
     const float4* nodes;      // 2 float4 per reference node
-    const float4* v0;         // triangle streams in REFERENCE primitive order (brute-force leaves, refit source)
-    const float4* e1;
-    const float4* e2;
+    const float4* tri;        // 3 float4 per triangle, REFERENCE primitive order: {v0, prim}, {e1, 0}, {e2, 0}   (48 B, one
+                              //   base address + immediate offsets per test; brute-force leaves and refit source)
     // leaf accelerator (BVHT_FLAG_LEAF_ACCEL), see leaf_accel.hpp
-    const float4* sub_nodes;  // 4 float4 per sub node (two child boxes + two child refs)
-    const float4* sv0;        // triangle streams in sub-BVH order; v0.w carries the reference primitive index
-    const float4* se1;
-    const float4* se2;
+    const float4* sub_nodes;  // 4 float4 per sub node (two child boxes + two child refs), inflated for the current bake
+    const float4* stri;       // 3 float4 per triangle in sub-BVH order; v0.w carries the reference primitive index
     const uint32_t* leaf_sub_root;  // per reference node: sub-BVH root ref for leaves (0xFFFFFFFF = brute force)
     uint32_t n_tris;
     uint32_t nodes_used;
-    float    accel_d_max;     // model-space limits |d| <= d_max, |o| <= o_max under which the pre-inflated
+    float    accel_d_max;     // model-space limits |d| <= d_max, |o| <= o_max under which the inflated
     float    accel_o_max;     //   sub boxes are conservative (leaf_accel.hpp); other rays use brute-force leaves
 };
 

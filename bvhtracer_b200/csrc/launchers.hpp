@@ -16,9 +16,8 @@ BVHT_DECLARE_MODE(stats)
 #undef BVHT_DECLARE_MODE
 
 // upload_kernels.cu
-cudaError_t launch_repack_triangles(const float* tris_aos, uint32_t n_tris, float4* v0, float4* e1, float4* e2, cudaStream_t s);
-cudaError_t launch_repack_sub_triangles(const float* tris_aos, const uint32_t* sub_order, uint32_t n,
-                                        float4* sv0, float4* se1, float4* se2, cudaStream_t s);
+cudaError_t launch_repack_triangles(const float* tris_aos, uint32_t n_tris, float4* out, cudaStream_t s);
+cudaError_t launch_repack_sub_triangles(const float* tris_aos, const uint32_t* sub_order, uint32_t n, float4* out, cudaStream_t s);
 
 cudaError_t launch_inflate_sub_nodes(const float4* raw, float4* out, uint32_t n_nodes, float scale, float abs_, cudaStream_t s);
 

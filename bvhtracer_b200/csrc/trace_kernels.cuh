@@ -107,37 +107,46 @@ __device__ __forceinline__ bool slab_test_sub(const float4 lo, const float4 hi, 
     return (t_max >= t_min) && (t_min <= tcl) && (t_max >= 0.0f);
 }
 
-// geometry/triangle.rs:41-72 on the repacked triangle (v0, e1 = v1 - v0, e2 = v2 - v0).
-// Returns true when the reference would return Some(SurfaceInteraction{min(entry_t, t), u, v}).
-__device__ __forceinline__ bool moller_trumbore(const float4 v0, const float4 e1, const float4 e2, const RayM& r,
-                                                float entry_t, float& t_out, float& u_out, float& v_out) {
+// geometry/triangle.rs:41-72 on the repacked triangle (v0, e1 = v1 - v0, e2 = v2 - v0), split in two so that the
+// hot loop is straight-line code with ONE rarely taken branch:
+//
+//  mt_filter  evaluates, with exactly the reference's operations, normal = d x e2, area = e1 . normal, s = o - v0,
+//             X = s . normal, and decides -- exactly -- whether the reference would already have returned None at
+//             `|area| < 1e-4` or at `u = (1 / area) * X; u < 0 || u > 1`, WITHOUT the IEEE divide (98 % of all tests
+//             end here).  With a = |area| in [1e-4, 2^59] and x = |X|:
+//              * signs differ and x >= 2^-60: f = fl(1/area) has |f| >= 2^-60, so fl(f * X) is a negative NORMAL
+//                number: u < 0.  (A smaller x could round to -0.0, which the reference does not reject: undecided.)
+//              * signs equal and x > fl(a * (1 + 2^-20)): then x > a (1 + 2^-21), fl(1/a) >= (1 - 2^-24) / a, so
+//                fl(1/a) * x > 1 + 2^-22 and its rounding is still > 1: u > 1.
+//             Anything undecided (including NaNs: every comparison is false) goes to mt_finish.
+//  mt_finish  is the rest of Triangle::intersect verbatim (f, u, the u test again, q, v, t, thresholds).
+struct MtPartial { float nx, ny, nz, area, sx, sy, sz, X; };
+
+__device__ __forceinline__ bool mt_filter(const float4 v0, const float4 e1, const float4 e2, const RayM& r, MtPartial& p) {
+    p.nx = r.dy * e2.z - r.dz * e2.y;
+    p.ny = r.dz * e2.x - r.dx * e2.z;
+    p.nz = r.dx * e2.y - r.dy * e2.x;
+    p.area = (e1.x * p.nx + e1.y * p.ny) + e1.z * p.nz;
+    p.sx = r.ox - v0.x; p.sy = r.oy - v0.y; p.sz = r.oz - v0.z;
+    p.X = (p.sx * p.nx + p.sy * p.ny) + p.sz * p.nz;
+    float a = fabsf(p.area), x = fabsf(p.X);
+    bool opposite = (__float_as_int(p.area) ^ __float_as_int(p.X)) < 0;
+    bool rej_area = a < 0.0001f;
+    bool rej_neg = opposite & (x >= 8.673617379884035e-19f) & (a <= 5.764607523034235e17f);
+    bool rej_big = (!opposite) & (x > a * 1.00000095367431640625f);
+    return !(rej_area | rej_neg | rej_big);
+}
+
+__device__ __forceinline__ bool mt_finish(const float4 e1, const float4 e2, const RayM& r, const MtPartial& p, float entry_t,
+                                          float& t_out, float& u_out, float& v_out) {
     const float threshold = 0.0001f;
-    float nx = r.dy * e2.z - r.dz * e2.y;
-    float ny = r.dz * e2.x - r.dx * e2.z;
-    float nz = r.dx * e2.y - r.dy * e2.x;
-    float area = (e1.x * nx + e1.y * ny) + e1.z * nz;
-    if (fabsf(area) < threshold) return false;
-    float sx = r.ox - v0.x, sy = r.oy - v0.y, sz = r.oz - v0.z;
-    float X = (sx * nx + sy * ny) + sz * nz;
-    // Exact early outs for the reference's `u = (1 / area) * X; if u < 0 || u > 1 { return None }` WITHOUT the IEEE
-    // divide (85 % of all tests leave here).  With a = |area| in [1e-4, 2^59] and x = |X|:
-    //  * signs differ and x >= 2^-60: f = fl(1/area) has |f| >= 2^-60, so fl(f * X) is a negative NORMAL number: u < 0.
-    //    (Smaller x could round to -0.0, which the reference does not reject: those take the full path.)
-    //  * signs equal and x > fl(a * (1 + 2^-20)): then x > a (1 + 2^-21), fl(1/a) >= (1 - 2^-24) / a, so
-    //    fl(1/a) * x > 1 + 2^-22 and its rounding is still > 1: u > 1.
-    // Everything else (including NaNs, for which every comparison below is false) computes f and u exactly as written.
-    {
-        float a = fabsf(area), x = fabsf(X);
-        bool opposite = (__float_as_int(area) ^ __float_as_int(X)) < 0;
-        if (opposite) { if (x >= 8.673617379884035e-19f && a <= 5.764607523034235e17f) return false; }
-        else if (x > a * 1.00000095367431640625f) return false;
-    }
-    float f = 1.0f / area;
-    float u = f * X;
+    if (fabsf(p.area) < threshold) return false;
+    float f = 1.0f / p.area;
+    float u = f * p.X;
     if (u < 0.0f || u > 1.0f) return false;
-    float qx = sy * e1.z - sz * e1.y;
-    float qy = sz * e1.x - sx * e1.z;
-    float qz = sx * e1.y - sy * e1.x;
+    float qx = p.sy * e1.z - p.sz * e1.y;
+    float qy = p.sz * e1.x - p.sx * e1.z;
+    float qz = p.sx * e1.y - p.sy * e1.x;
     float v = f * ((r.dx * qx + r.dy * qy) + r.dz * qz);
     if (v < 0.0f || u + v > 1.0f) return false;
     float t = f * ((e2.x * qx + e2.y * qy) + e2.z * qz);
@@ -153,14 +162,18 @@ __device__ __forceinline__ bool moller_trumbore(const float4 v0, const float4 e1
 __device__ __forceinline__ void leaf_brute(const BlasDesc& B, uint32_t base, uint32_t count, const RayM& r, float entry_t,
                                            float& best_t, float& best_u, float& best_v, uint32_t& best_prim, bool& found, Stat& st) {
     st.add(5, count);
-    for (uint32_t k = 0; k < count; ++k) {
+    const float4* tp = B.tri + 3 * (size_t)base;
+    for (uint32_t k = 0; k < count; ++k, tp += 3) {
         uint32_t pi = base + k;
-        float4 v0 = ldg4(B.v0 + pi);
-        float4 e1 = ldg4(B.e1 + pi);
-        float4 e2 = ldg4(B.e2 + pi);
-        float t, u, v;
-        if (moller_trumbore(v0, e1, e2, r, entry_t, t, u, v)) {
-            if (t < best_t) { best_t = t; best_u = u; best_v = v; best_prim = pi; found = true; }
+        float4 v0 = ldg4(tp + 0);
+        float4 e1 = ldg4(tp + 1);
+        float4 e2 = ldg4(tp + 2);
+        MtPartial mp;
+        if (mt_filter(v0, e1, e2, r, mp)) {
+            float t, u, v;
+            if (mt_finish(e1, e2, r, mp, entry_t, t, u, v)) {
+                if (t < best_t) { best_t = t; best_u = u; best_v = v; best_prim = pi; found = true; }
+            }
         }
     }
 }
@@ -187,14 +200,18 @@ __device__ __forceinline__ void leaf_accel(const BlasDesc& B, uint32_t sub_root,
             uint32_t first = ref & 0x0FFFFFFFu;
             uint32_t cnt = ((ref >> 28) & 7u) + 1u;
             st.add(7, cnt);
-            for (uint32_t k = 0; k < cnt; ++k) {
-                float4 v0 = ldg4(B.sv0 + first + k);
-                float4 e1 = ldg4(B.se1 + first + k);
-                float4 e2 = ldg4(B.se2 + first + k);
-                float t, u, v;
-                if (moller_trumbore(v0, e1, e2, r, entry_t, t, u, v)) {
-                    uint32_t pi = __float_as_uint(v0.w);
-                    if (t < lt || (t == lt && pi < lp)) { lt = t; lu = u; lv = v; lp = pi; lfound = true; }
+            const float4* tp = B.stri + 3 * (size_t)first;
+            for (uint32_t k = 0; k < cnt; ++k, tp += 3) {
+                float4 v0 = ldg4(tp + 0);
+                float4 e1 = ldg4(tp + 1);
+                float4 e2 = ldg4(tp + 2);
+                MtPartial mp;
+                if (mt_filter(v0, e1, e2, r, mp)) {
+                    float t, u, v;
+                    if (mt_finish(e1, e2, r, mp, entry_t, t, u, v)) {
+                        uint32_t pi = __float_as_uint(v0.w);
+                        if (t < lt || (t == lt && pi < lp)) { lt = t; lu = u; lv = v; lp = pi; lfound = true; }
+                    }
                 }
             }
             if (sp == 0) break;
@@ -329,7 +346,14 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
             r.dy = ((c0.y * w.dx + c1.y * w.dy) + c2.y * w.dz) + c3.y * 0.0f;
             r.dz = ((c0.z * w.dx + c1.z * w.dy) + c2.z * w.dz) + c3.z * 0.0f;
             r.rdx = 1.0f / r.dx; r.rdy = 1.0f / r.dy; r.rdz = 1.0f / r.dz;   // Ray::new, ray.rs:23-31
-            const BlasDesc& B = S.blas[__ldg(S.inst_blas + inst)];
+            // descriptor copied into registers once per instance entry (the loops below must not re-read it from memory)
+            const BlasDesc* Bp = S.blas + __ldg(S.inst_blas + inst);
+            BlasDesc B;
+            B.nodes = Bp->nodes; B.tri = Bp->tri;
+            if (ACCEL) {
+                B.sub_nodes = Bp->sub_nodes; B.stri = Bp->stri; B.leaf_sub_root = Bp->leaf_sub_root;
+                B.accel_d_max = Bp->accel_d_max; B.accel_o_max = Bp->accel_o_max;
+            }
             bool use_accel = false;
             if (ACCEL) {
                 // the sub boxes were inflated for model-space rays with |d| <= d_max and |o| <= o_max; anything

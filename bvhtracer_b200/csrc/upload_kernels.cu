@@ -1,6 +1,6 @@
-// upload_kernels.cu -- K3: repack the reference's AoS triangle buffer (Triangle<f32> = 3 x Vector3, 36 B,
-// geometry/triangle.rs:9-16 viewed through Mesh::primitives, mesh.rs:126-134) into three float4 streams
-//   v0 | e1 = v1 - v0 | e2 = v2 - v0
+// upload_kernels.cu -- K3: repack the reference's triangle buffer (Triangle<f32> = 3 x Vector3, 36 B,
+// geometry/triangle.rs:9-16 viewed through Mesh::primitives, mesh.rs:126-134) into 3 aligned float4 per triangle
+//   {v0, prim} | {e1 = v1 - v0, 0} | {e2 = v2 - v0, 0}
 // The two edge subtractions are the first two operations of Triangle::intersect (triangle.rs:43-44); doing
 // them once on upload is bit-identical (one IEEE subtraction either way; no FMA can form here).
 // HBM-bound streaming kernel: 36 B read + 48 B written per triangle, loads coalesced through shared memory.
@@ -12,8 +12,7 @@ namespace {
 constexpr int kRepackBlock = 256;
 
 __global__ void __launch_bounds__(kRepackBlock)
-repack_triangles_kernel(const float* __restrict__ tris, uint32_t n_tris,
-                        float4* __restrict__ v0, float4* __restrict__ e1, float4* __restrict__ e2) {
+repack_triangles_kernel(const float* __restrict__ tris, uint32_t n_tris, float4* __restrict__ out) {
     __shared__ float stage[kRepackBlock * 9];
     const uint32_t first = blockIdx.x * kRepackBlock;
     const uint32_t count = min((uint32_t)kRepackBlock, n_tris - first);
@@ -24,24 +23,24 @@ repack_triangles_kernel(const float* __restrict__ tris, uint32_t n_tris,
         const float* t = stage + threadIdx.x * 9;      // stride 9 words: conflict-free (gcd(9, 32) = 1)
         uint32_t i = first + threadIdx.x;
         float ax = t[0], ay = t[1], az = t[2];
-        v0[i] = make_float4(ax, ay, az, __uint_as_float(i));
-        e1[i] = make_float4(t[3] - ax, t[4] - ay, t[5] - az, 0.0f);
-        e2[i] = make_float4(t[6] - ax, t[7] - ay, t[8] - az, 0.0f);
+        out[3 * (size_t)i + 0] = make_float4(ax, ay, az, __uint_as_float(i));
+        out[3 * (size_t)i + 1] = make_float4(t[3] - ax, t[4] - ay, t[5] - az, 0.0f);
+        out[3 * (size_t)i + 2] = make_float4(t[6] - ax, t[7] - ay, t[8] - az, 0.0f);
     }
 }
 
 // Same repack, gathered through the sub-BVH order (leaf_accel.hpp); v0.w carries the REFERENCE primitive index.
 __global__ void __launch_bounds__(kRepackBlock)
 repack_sub_triangles_kernel(const float* __restrict__ tris, const uint32_t* __restrict__ order, uint32_t n,
-                            float4* __restrict__ sv0, float4* __restrict__ se1, float4* __restrict__ se2) {
+                            float4* __restrict__ out) {
     uint32_t i = blockIdx.x * kRepackBlock + threadIdx.x;
     if (i >= n) return;
     uint32_t p = __ldg(order + i);
     const float* t = tris + (size_t)p * 9;
     float ax = __ldg(t + 0), ay = __ldg(t + 1), az = __ldg(t + 2);
-    sv0[i] = make_float4(ax, ay, az, __uint_as_float(p));
-    se1[i] = make_float4(__ldg(t + 3) - ax, __ldg(t + 4) - ay, __ldg(t + 5) - az, 0.0f);
-    se2[i] = make_float4(__ldg(t + 6) - ax, __ldg(t + 7) - ay, __ldg(t + 8) - az, 0.0f);
+    out[3 * (size_t)i + 0] = make_float4(ax, ay, az, __uint_as_float(p));
+    out[3 * (size_t)i + 1] = make_float4(__ldg(t + 3) - ax, __ldg(t + 4) - ay, __ldg(t + 5) - az, 0.0f);
+    out[3 * (size_t)i + 2] = make_float4(__ldg(t + 6) - ax, __ldg(t + 7) - ay, __ldg(t + 8) - az, 0.0f);
 }
 
 // Bake the sub-BVH for the current ray limits: out = raw boxes grown by delta = scale * kappa + abs (leaf_accel.hpp
@@ -83,18 +82,17 @@ cudaError_t launch_inflate_sub_nodes(const float4* raw, float4* out, uint32_t n_
     return cudaGetLastError();
 }
 
-cudaError_t launch_repack_triangles(const float* tris_aos, uint32_t n_tris, float4* v0, float4* e1, float4* e2, cudaStream_t s) {
+cudaError_t launch_repack_triangles(const float* tris_aos, uint32_t n_tris, float4* out, cudaStream_t s) {
     if (n_tris == 0) return cudaSuccess;
     int grid = (int)((n_tris + kRepackBlock - 1) / kRepackBlock);
-    repack_triangles_kernel<<<grid, kRepackBlock, 0, s>>>(tris_aos, n_tris, v0, e1, e2);
+    repack_triangles_kernel<<<grid, kRepackBlock, 0, s>>>(tris_aos, n_tris, out);
     return cudaGetLastError();
 }
 
-cudaError_t launch_repack_sub_triangles(const float* tris_aos, const uint32_t* sub_order, uint32_t n,
-                                        float4* sv0, float4* se1, float4* se2, cudaStream_t s) {
+cudaError_t launch_repack_sub_triangles(const float* tris_aos, const uint32_t* sub_order, uint32_t n, float4* out, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     int grid = (int)((n + kRepackBlock - 1) / kRepackBlock);
-    repack_sub_triangles_kernel<<<grid, kRepackBlock, 0, s>>>(tris_aos, sub_order, n, sv0, se1, se2);
+    repack_sub_triangles_kernel<<<grid, kRepackBlock, 0, s>>>(tris_aos, sub_order, n, out);
     return cudaGetLastError();
 }
 
