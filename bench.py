@@ -354,6 +354,19 @@ def run_ours(args, rank, local_rank, world):
                "call": "per rank: bvht_tlas_set + bvht_render_frame_device (tile-row shard) into rank 0's frame buffer over NVLink P2P; "
                        "rank 0: barrier + D2H of the Rgba<u8> frame (host wall clock, includes the host-side scene update)"}
         frame_checksum = int(np.bitwise_xor.reduce(host_frame)) if rank == 0 else 0
+        # the assembled frame must equal the same frame rendered by rank 0 alone (outside every timed region)
+        sharded_ok = None
+        barrier()
+        if rank == 0:
+            eng.set_shard(0, 1)
+            d_single = eng.device_alloc(npix * 4)
+            eng.render_frame_device(cam, width, height, shade, tile, None, d_single, None)
+            eng.sync()
+            single = eng.memcpy_d2h(np.zeros(npix, "<u4"), d_single)
+            eng.device_free(d_single)
+            eng.set_shard(rank, world)
+            sharded_ok = bool(np.array_equal(single, host_frame))
+        barrier()
     clocks = sampler.stop()
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle on the box's host cores, bounded sample of the same frame
@@ -366,11 +379,11 @@ def run_ours(args, rank, local_rank, world):
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import oracle_lib as O
             threads = O.max_threads()
-            rows = oracle_sample_rows(height, tile, args.cpu_fraction)
+            rows = oracle_sample_rows(height, tile, args.cpu_baseline_fraction)      # ~10 s of CPU work on 16 cores
             r, s, counters = oracle_time_frame(args.warmup + 1, width, height, rows, threads)
-            r1, s1, _ = oracle_time_frame(args.warmup + 1, width, height, rows[::8], 1)
+            r1, s1, _ = oracle_time_frame(args.warmup + 1, width, height, rows[::16], 1)
             cpu = {"value": r / s / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
-                   "sample": f"frame {args.warmup + 1}: every {max(1, int(round(1.0 / args.cpu_fraction)))}th 8-pixel tile row ({len(rows)} rows, {r} rays, {s:.1f} s)",
+                   "sample": f"frame {args.warmup + 1}: every {max(1, int(round(1.0 / args.cpu_baseline_fraction)))}th 8-pixel tile row ({len(rows)} rows, {r} rays, {s:.1f} s)",
                    "single_thread": {"value": r1 / s1 / 1e6, "unit": "Mrays/s", "rays": r1, "seconds": s1,
                                      "note": "the reference itself is single-threaded (renderer.rs:353-368)"}}
         # roofline of the dominant kernel (trace_primary_kernel): algorithmic bytes per launch / launch duration
@@ -412,6 +425,7 @@ def run_ours(args, rank, local_rank, world):
                        "parity": "strict modes are bit-identical to the CPU oracle (tests/test_gpu_parity.py)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "frame_checksum": frame_checksum, "wall_s_resident_loop": wall_resident,
+            "sharded_frame_equals_single_gpu": (sharded_ok if world > 1 else None),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -432,6 +446,7 @@ def main():
     ap.add_argument("--mode", default="strict-accel", choices=sorted(MODES))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cpu-fraction", type=float, default=0.05, help="fraction of tile rows the CPU oracle renders per frame")
+    ap.add_argument("--cpu-baseline-fraction", type=float, default=0.5, help="fraction of tile rows of ONE frame for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

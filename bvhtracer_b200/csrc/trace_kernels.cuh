@@ -157,6 +157,28 @@ __device__ __forceinline__ bool mt_finish(const float4 e1, const float4 e2, cons
     return true;
 }
 
+#ifdef BVHT_FAST_MODE
+// Fast build only: (t, u, v) of the WINNING triangle re-evaluated with round-to-nearest intrinsics, which nvcc never
+// contracts into FMAs -- i.e. with the reference's arithmetic.  FMA contraction may pick a different winner in a
+// near-tie (allowed: >= 99.99 % identical ids), but for the triangle it reports, t/u/v are then the reference's.
+__device__ __forceinline__ void mt_exact_rn(const float4 v0, const float4 e1, const float4 e2, const RayM& r, float entry_t,
+                                            float& t, float& u, float& v) {
+    float nx = __fsub_rn(__fmul_rn(r.dy, e2.z), __fmul_rn(r.dz, e2.y));
+    float ny = __fsub_rn(__fmul_rn(r.dz, e2.x), __fmul_rn(r.dx, e2.z));
+    float nz = __fsub_rn(__fmul_rn(r.dx, e2.y), __fmul_rn(r.dy, e2.x));
+    float area = __fadd_rn(__fadd_rn(__fmul_rn(e1.x, nx), __fmul_rn(e1.y, ny)), __fmul_rn(e1.z, nz));
+    float f = __fdiv_rn(1.0f, area);
+    float sx = __fsub_rn(r.ox, v0.x), sy = __fsub_rn(r.oy, v0.y), sz = __fsub_rn(r.oz, v0.z);
+    float uu = __fmul_rn(f, __fadd_rn(__fadd_rn(__fmul_rn(sx, nx), __fmul_rn(sy, ny)), __fmul_rn(sz, nz)));
+    float qx = __fsub_rn(__fmul_rn(sy, e1.z), __fmul_rn(sz, e1.y));
+    float qy = __fsub_rn(__fmul_rn(sz, e1.x), __fmul_rn(sx, e1.z));
+    float qz = __fsub_rn(__fmul_rn(sx, e1.y), __fmul_rn(sy, e1.x));
+    float vv = __fmul_rn(f, __fadd_rn(__fadd_rn(__fmul_rn(r.dx, qx), __fmul_rn(r.dy, qy)), __fmul_rn(r.dz, qz)));
+    float tt = __fmul_rn(f, __fadd_rn(__fadd_rn(__fmul_rn(e2.x, qx), __fmul_rn(e2.y, qy)), __fmul_rn(e2.z, qz)));
+    if (isfinite(tt) && isfinite(uu) && isfinite(vv)) { t = fminf(entry_t, tt); u = uu; v = vv; }
+}
+#endif
+
 // Brute-force leaf: primitives base .. base+count ascending, strict '<' against the shrinking closest t
 // (bvh.rs:250-258).  Triangles are tested against the ENTRY ray.
 __device__ __forceinline__ void leaf_brute(const BlasDesc& B, uint32_t base, uint32_t count, const RayM& r, float entry_t,
@@ -299,6 +321,14 @@ __device__ __forceinline__ void blas_intersect(const BlasDesc& B, const RayM& r,
             n1 = ldg4(B.nodes + 2 * (size_t)ni + 1);
         }
     }
+#ifdef BVHT_FAST_MODE
+    if (found) {
+        const float4* tp = B.tri + 3 * (size_t)best_prim;
+        float t = best_t, u = best_u, v = best_v;
+        mt_exact_rn(ldg4(tp + 0), ldg4(tp + 1), ldg4(tp + 2), r, entry_t, t, u, v);
+        if (t < entry_t) { best_t = t; best_u = u; best_v = v; }      // keep the strict '<' contract of the caller
+    }
+#endif
 }
 
 // scene/tlas.rs:123-177 + scene_object.rs:78-89.  World ray (ox..dz, recip), initial t = tmax.

@@ -494,3 +494,23 @@ def test_accel_rebake_across_camera_distances():
         got = eng.trace_rays(rays)
         assert (ref["id"] != O.MISS_ID).sum() > 50
         assert_strict(got, ref)
+
+
+@pytest.mark.parametrize("name,arg,size", [("trippy_teapots", 10, (3840, 2160)), ("sixteen_armadillos", 30, (1920, 1080)),
+                                           ("big_ben_clock", None, (3840, 2160))])
+def test_fast_mode_full_size_against_strict_gpu(name, arg, size):
+    # fast (FMA) build vs the strict build on the GPU itself at full size: >= 99.99 % identical ids and, because the
+    # winning triangle's (t, u, v) are re-evaluated without contraction, t within 1e-5 relative on identical ids
+    spec = examples.CONFIGS[name]() if arg is None else examples.CONFIGS[name](arg)
+    scene, cam = SB.oracle_scene(spec)
+    w, h = size
+    res = {}
+    for label, flags in (("strict", FLAG_STRICT | FLAG_LEAF_ACCEL), ("fast", FLAG_FAST | FLAG_LEAF_ACCEL), ("fast-brute", FLAG_FAST)):
+        if label == "fast-brute" and name != "trippy_teapots":
+            continue
+        with Engine(flags=flags) as eng:
+            SB.upload_scene(eng, scene)
+            res[label] = eng.trace_primary(SB.to_ffi_camera(cam), w, h)
+    for label in res:
+        if label != "strict":
+            assert_fast(res[label], res["strict"])
