@@ -307,6 +307,8 @@ bool invert_d(const double* m, double* out) {
 }
 
 // d2_max: limit on |d_w|^2; o2_max: limit on |o_w - center|^2; negative: unusable (always visit)
+double sigma_max_3x3(const double* m);
+
 struct TightBox { float lo[3], hi[3]; float d2_max, o2_max; };
 
 // Conservative WORLD-space box of the real (non-degenerate) geometry of one instance, with the world-space ray limits
@@ -331,25 +333,8 @@ TightBox instance_tight_box(const Blas& b, const float* inv_f, const double cent
     // slack for: f32 evaluation of M^-1 * (o, d) in the kernel, the f32 slab test, f32 storage of the box
     double ext = std::max({ hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2], 1e-3 });
     double slack = 1e-4 * (ext + maxabs);
-    // |d'| <= s |d_w|, |o'| <= s |o_w| + |t'| with s >= largest singular value of the 3x3 part A of M^-1:
-    // power iteration on A^T A (converges from below, hence the 1 % safety), capped by the Frobenius norm
-    double ata[3][3], fro = 0.0;
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
-        ata[i][j] = 0.0;
-        for (int r = 0; r < 3; ++r) ata[i][j] += inv[i * 4 + r] * inv[j * 4 + r];
-    }
-    for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) fro += inv[c * 4 + r] * inv[c * 4 + r];
-    double v[3] = { 0.57, 0.58, 0.59 }, lam = 0.0;
-    for (int it = 0; it < 200; ++it) {
-        double w[3] = { 0, 0, 0 };
-        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) w[i] += ata[i][j] * v[j];
-        double n = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
-        if (!(n > 0.0)) break;
-        lam = n / std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-        for (int i = 0; i < 3; ++i) v[i] = w[i] / n;
-    }
-    double sgm = std::min(std::sqrt(lam) * 1.01, std::sqrt(fro) * (1.0 + 1e-6));
-    if (!(lam > 0.0)) sgm = std::sqrt(fro) * (1.0 + 1e-6);
+    // |d'| <= s |d_w| and |o'| grows by at most s per unit of |o_w| with s >= largest singular value of the 3x3 part of M^-1
+    double sgm = sigma_max_3x3(inv);
     // ray origins are limited to a ball around `center` (the camera of the last bake): for |o_w - c| <= rho,
     // |o'| = |A o_w + t'| <= |A c + t'| + s * rho, which must stay <= o_max
     double oc[3];
@@ -413,25 +398,20 @@ int recompute_tlas_tight(bvht_ctx* ctx) {
     return h2d(ctx, ctx->tlas_tight.p, flat.data(), flat.size() * 4);       // pageable: staged before return
 }
 
-double sigma_max_3x3(const double* m /* column-major 4x4, upper-left 3x3 */) {
-    double ata[3][3], fro = 0.0;
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
-        ata[i][j] = 0.0;
-        for (int r = 0; r < 3; ++r) ata[i][j] += m[i * 4 + r] * m[j * 4 + r];
+// Upper bound of the largest singular value of the upper-left 3x3 block A of a column-major 4x4:
+// sigma_max^2 = lambda_max(A^T A) <= max row sum of |A^T A| (exact for a scaled rotation, never an underestimate).
+double sigma_max_3x3(const double* m) {
+    double best = 0.0;
+    for (int i = 0; i < 3; ++i) {
+        double row = 0.0;
+        for (int j = 0; j < 3; ++j) {
+            double e = 0.0;
+            for (int r = 0; r < 3; ++r) e += m[i * 4 + r] * m[j * 4 + r];
+            row += std::fabs(e);
+        }
+        best = std::max(best, row);
     }
-    for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) fro += m[c * 4 + r] * m[c * 4 + r];
-    double v[3] = { 0.57, 0.58, 0.59 }, lam = 0.0;
-    for (int it = 0; it < 200; ++it) {
-        double w[3] = { 0, 0, 0 };
-        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) w[i] += ata[i][j] * v[j];
-        double n = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
-        if (!(n > 0.0)) break;
-        lam = n / std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-        for (int i = 0; i < 3; ++i) v[i] = w[i] / n;
-    }
-    double s = std::sqrt(fro) * (1.0 + 1e-6);
-    if (lam > 0.0) s = std::min(std::sqrt(lam) * 1.01, s);
-    return s;
+    return std::sqrt(best) * (1.0 + 1e-9);
 }
 
 // Primary rays all start at the camera position with |d_w| <= sigma_max(view_inv): the limits each model's bake must

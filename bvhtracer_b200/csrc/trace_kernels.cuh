@@ -369,13 +369,16 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
             float4 c0 = ldg4(m + 0), c1 = ldg4(m + 1), c2 = ldg4(m + 2), c3 = ldg4(m + 3);
             RayM r;
             // transform.rs:219-234 over cglinalg Matrix4x4 * Vector4: ((c0*x + c1*y) + c2*z) + c3*w
-            r.ox = ((c0.x * w.ox + c1.x * w.oy) + c2.x * w.oz) + c3.x * 1.0f;
-            r.oy = ((c0.y * w.ox + c1.y * w.oy) + c2.y * w.oz) + c3.y * 1.0f;
-            r.oz = ((c0.z * w.ox + c1.z * w.oy) + c2.z * w.oz) + c3.z * 1.0f;
-            r.dx = ((c0.x * w.dx + c1.x * w.dy) + c2.x * w.dz) + c3.x * 0.0f;
-            r.dy = ((c0.y * w.dx + c1.y * w.dy) + c2.y * w.dz) + c3.y * 0.0f;
-            r.dz = ((c0.z * w.dx + c1.z * w.dy) + c2.z * w.dz) + c3.z * 0.0f;
-            r.rdx = 1.0f / r.dx; r.rdy = 1.0f / r.dy; r.rdz = 1.0f / r.dz;   // Ray::new, ray.rs:23-31
+            // (round-to-nearest intrinsics: never contracted, so the model-space ray is the reference's in BOTH builds)
+#define BVHT_MV4(cx0, cx1, cx2, cx3, x, y, z, wv) \
+    __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx0, x), __fmul_rn(cx1, y)), __fmul_rn(cx2, z)), __fmul_rn(cx3, wv))
+            r.ox = BVHT_MV4(c0.x, c1.x, c2.x, c3.x, w.ox, w.oy, w.oz, 1.0f);
+            r.oy = BVHT_MV4(c0.y, c1.y, c2.y, c3.y, w.ox, w.oy, w.oz, 1.0f);
+            r.oz = BVHT_MV4(c0.z, c1.z, c2.z, c3.z, w.ox, w.oy, w.oz, 1.0f);
+            r.dx = BVHT_MV4(c0.x, c1.x, c2.x, c3.x, w.dx, w.dy, w.dz, 0.0f);
+            r.dy = BVHT_MV4(c0.y, c1.y, c2.y, c3.y, w.dx, w.dy, w.dz, 0.0f);
+            r.dz = BVHT_MV4(c0.z, c1.z, c2.z, c3.z, w.dx, w.dy, w.dz, 0.0f);
+            r.rdx = __fdiv_rn(1.0f, r.dx); r.rdy = __fdiv_rn(1.0f, r.dy); r.rdz = __fdiv_rn(1.0f, r.dz);   // Ray::new, ray.rs:23-31
             // descriptor copied into registers once per instance entry (the loops below must not re-read it from memory)
             const BlasDesc* Bp = S.blas + __ldg(S.inst_blas + inst);
             BlasDesc B;
@@ -457,26 +460,28 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
 
 // camera.rs:994-1010 with u, v from renderer.rs:358-361
 __device__ __forceinline__ RayM primary_ray(const CameraDev& C, uint32_t px, uint32_t py, uint32_t width, uint32_t height) {
-    float u = (float)px / (float)width;
-    float v = (float)py / (float)height;
+    float u = __fdiv_rn((float)px, (float)width);
+    float v = __fdiv_rn((float)py, (float)height);
     float p[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         float origin = 0.0f;
-        p[k] = ((origin + C.tl[k]) + (C.tr[k] - C.tl[k]) * u) + (C.bl[k] - C.tl[k]) * v;
-        p[k] = p[k] - origin;
+        p[k] = __fadd_rn(__fadd_rn(__fadd_rn(origin, C.tl[k]), __fmul_rn(__fsub_rn(C.tr[k], C.tl[k]), u)),
+                         __fmul_rn(__fsub_rn(C.bl[k], C.tl[k]), v));
+        p[k] = __fsub_rn(p[k], origin);
     }
-    float m = sqrtf((p[0] * p[0] + p[1] * p[1]) + p[2] * p[2]);   // normalize = v / |v| (pinned, test_tri_mesh.rs:57-59)
-    float ex = p[0] / m, ey = p[1] / m, ez = p[2] / m;
+    // normalize = v / |v| (pinned, test_tri_mesh.rs:57-59)
+    float m = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(p[0], p[0]), __fmul_rn(p[1], p[1])), __fmul_rn(p[2], p[2])));
+    float ex = __fdiv_rn(p[0], m), ey = __fdiv_rn(p[1], m), ez = __fdiv_rn(p[2], m);
     RayM w;
     const float* M = C.vinv;
-    w.ox = ((M[0] * 0.0f + M[4] * 0.0f) + M[8] * 0.0f) + M[12] * 1.0f;
-    w.oy = ((M[1] * 0.0f + M[5] * 0.0f) + M[9] * 0.0f) + M[13] * 1.0f;
-    w.oz = ((M[2] * 0.0f + M[6] * 0.0f) + M[10] * 0.0f) + M[14] * 1.0f;
-    w.dx = ((M[0] * ex + M[4] * ey) + M[8] * ez) + M[12] * 0.0f;
-    w.dy = ((M[1] * ex + M[5] * ey) + M[9] * ez) + M[13] * 0.0f;
-    w.dz = ((M[2] * ex + M[6] * ey) + M[10] * ez) + M[14] * 0.0f;
-    w.rdx = 1.0f / w.dx; w.rdy = 1.0f / w.dy; w.rdz = 1.0f / w.dz;
+    w.ox = BVHT_MV4(M[0], M[4], M[8], M[12], 0.0f, 0.0f, 0.0f, 1.0f);
+    w.oy = BVHT_MV4(M[1], M[5], M[9], M[13], 0.0f, 0.0f, 0.0f, 1.0f);
+    w.oz = BVHT_MV4(M[2], M[6], M[10], M[14], 0.0f, 0.0f, 0.0f, 1.0f);
+    w.dx = BVHT_MV4(M[0], M[4], M[8], M[12], ex, ey, ez, 0.0f);
+    w.dy = BVHT_MV4(M[1], M[5], M[9], M[13], ex, ey, ez, 0.0f);
+    w.dz = BVHT_MV4(M[2], M[6], M[10], M[14], ex, ey, ez, 0.0f);
+    w.rdx = __fdiv_rn(1.0f, w.dx); w.rdy = __fdiv_rn(1.0f, w.dy); w.rdz = __fdiv_rn(1.0f, w.dz);
     return w;
 }
 
@@ -567,7 +572,7 @@ trace_rays_kernel(const __grid_constant__ RaysParams P) {
             w.ox = __ldg(rp + 0); w.oy = __ldg(rp + 1); w.oz = __ldg(rp + 2);
             w.dx = __ldg(rp + 3); w.dy = __ldg(rp + 4); w.dz = __ldg(rp + 5);
             float t = __ldg(rp + 6);
-            w.rdx = 1.0f / w.dx; w.rdy = 1.0f / w.dy; w.rdz = 1.0f / w.dz;
+            w.rdx = __fdiv_rn(1.0f, w.dx); w.rdy = __fdiv_rn(1.0f, w.dy); w.rdz = __fdiv_rn(1.0f, w.dz);
             HitRec h = scene_intersect<ACCEL>(P.scene, w, t, st);
             uint4 o;
             o.x = __float_as_uint(h.t); o.y = __float_as_uint(h.u); o.z = __float_as_uint(h.v); o.w = h.id;
