@@ -70,10 +70,11 @@ struct bvht_ctx {
     std::vector<Blas> blas;
     DevBuf blas_desc;                                 // BlasDesc[blas.size()]
     bool blas_desc_dirty = true;
-    DevBuf tlas, inst_cols, inst_blas, tlas_tight;
+    DevBuf tlas, inst_cols, inst_blas, tlas_tight, tlas_mask;
     uint32_t tlas_nodes_used = 0, n_inst = 0;
     std::vector<bvht_tlas_node> h_tlas;               // host copies (tight boxes are recomputed when a bake changes)
     std::vector<bvht_instance> h_inst;
+    std::vector<float> inst_tight;                    // 6 floats per instance (world lo/hi) or lo > hi when unusable
     double bake_center[3] = { 0.0, 0.0, 0.0 };        // camera origin the tight TLAS boxes' origin limit is centred on
     DevBuf work_counter;
     DevBuf out_buf, rays_buf, rgba_buf;               // device staging for the host-pointer entry points
@@ -393,9 +394,76 @@ int recompute_tlas_tight(bvht_ctx* ctx) {
         memcpy(f + 0, node_t[i].lo, 12); f[3] = node_t[i].d2_max;
         memcpy(f + 4, node_t[i].hi, 12); f[7] = node_t[i].o2_max;
     }
+    ctx->inst_tight.assign((size_t)n_inst * 6, 0.0f);
+    for (uint32_t i = 0; i < n_inst; ++i) {
+        float* f = &ctx->inst_tight[(size_t)i * 6];
+        if (inst_t[i].d2_max >= 0.0f && inst_t[i].o2_max >= 0.0f) { memcpy(f, inst_t[i].lo, 12); memcpy(f + 3, inst_t[i].hi, 12); }
+        else { f[0] = f[1] = f[2] = 1.0f; f[3] = f[4] = f[5] = -1.0f; }       // unusable: lo > hi
+    }
+    // instance masks per node (only meaningful for n_inst <= 32; the kernel ignores them otherwise)
+    std::vector<uint32_t> mask(nodes_used, 0xFFFFFFFFu);
+    if (n_inst <= 32) {
+        std::vector<uint8_t> mdone(nodes_used, 0);
+        struct Rec { static uint32_t go(const bvht_tlas_node* n, uint32_t i, std::vector<uint32_t>& m, std::vector<uint8_t>& d) {
+            if (d[i]) return m[i];
+            uint32_t v = n[i].left_right == 0 ? (1u << (n[i].blas & 31u)) : (go(n, n[i].left_right >> 16, m, d) | go(n, n[i].left_right & 0xFFFFu, m, d));
+            m[i] = v; d[i] = 1; return v; } };
+        Rec::go(ctx->h_tlas.data(), 0, mask, mdone);
+    }
     int rc = ensure(ctx, ctx->tlas_tight, flat.size() * 4);
     if (rc) return rc;
+    if ((rc = ensure(ctx, ctx->tlas_mask, mask.size() * 4))) return rc;
+    if ((rc = h2d(ctx, ctx->tlas_mask.p, mask.data(), mask.size() * 4))) return rc;
     return h2d(ctx, ctx->tlas_tight.p, flat.data(), flat.size() * 4);       // pageable: staged before return
+}
+
+// Conservative screen-space rectangle (inclusive pixel bounds) of every instance's tight world box for this camera.
+// Exact geometry: a ray from the eye through the near-plane point P(u, v) can only reach a convex box whose projection
+// onto the near plane contains P; the projection is inside the bounding rectangle of the 8 projected corners.  Computed
+// in double with a 2-pixel margin (the kernel's f32 ray directions differ from the exact ones by ~1e-7 relative, a
+// pixel is > 1e-4 of the image).  Any corner at or behind the eye plane, an unusable tight box, or a frustum that is not
+// the reference's axis-aligned one (camera.rs:199-211) makes the rectangle the full image.  Returns false = no masks.
+bool compute_instance_rects(const bvht_ctx* ctx, const bvht_camera* cam, uint32_t width, uint32_t height, int4* rects, uint32_t& n) {
+    n = 0;
+    uint32_t n_inst = (uint32_t)ctx->h_inst.size();
+    if (n_inst == 0 || n_inst > 32 || ctx->inst_tight.size() != (size_t)n_inst * 6) return false;
+    const float* tl = cam->top_left_eye; const float* tr = cam->top_right_eye; const float* bl = cam->bottom_left_eye;
+    if (!(tl[2] < 0.0f) || tr[2] != tl[2] || bl[2] != tl[2] || tr[1] != tl[1] || bl[0] != tl[0]) return false;
+    double ex = (double)tr[0] - tl[0], ey = (double)bl[1] - tl[1];
+    if (ex == 0.0 || ey == 0.0) return false;
+    double vinv[16], view[16];
+    for (int i = 0; i < 16; ++i) { vinv[i] = cam->view_matrix_inv[i]; if (!std::isfinite(vinv[i])) return false; }
+    if (vinv[3] != 0.0 || vinv[7] != 0.0 || vinv[11] != 0.0 || vinv[15] != 1.0) return false;
+    if (!invert_d(vinv, view)) return false;
+    double near_ = -(double)tl[2];
+    for (uint32_t i = 0; i < n_inst; ++i) {
+        const float* b = &ctx->inst_tight[(size_t)i * 6];
+        int4 full = make_int4(0, 0, (int)width - 1, (int)height - 1);
+        rects[i] = full;
+        if (b[0] > b[3]) continue;                                    // unusable tight box
+        double umin = 1e300, umax = -1e300, vmin = 1e300, vmax = -1e300;
+        bool behind = false;
+        double scale = 0.0;
+        for (int k = 0; k < 6; ++k) scale = std::max(scale, std::fabs((double)b[k]));
+        for (int c = 0; c < 8 && !behind; ++c) {
+            double p[3] = { (c & 1) ? b[3] : b[0], (c & 2) ? b[4] : b[1], (c & 4) ? b[5] : b[2] };
+            double e[3];
+            for (int r = 0; r < 3; ++r) e[r] = view[0 + r] * p[0] + view[4 + r] * p[1] + view[8 + r] * p[2] + view[12 + r];
+            if (!(e[2] < -1e-6 * (1.0 + scale))) { behind = true; break; }
+            double s = near_ / -e[2];
+            double u = (e[0] * s - tl[0]) / ex, v = (e[1] * s - tl[1]) / ey;
+            umin = std::min(umin, u); umax = std::max(umax, u); vmin = std::min(vmin, v); vmax = std::max(vmax, v);
+        }
+        if (behind || !std::isfinite(umin) || !std::isfinite(umax) || !std::isfinite(vmin) || !std::isfinite(vmax)) continue;
+        // pixel px has u = px / W: px in [u_min * W - 2, u_max * W + 2]
+        double x0 = std::floor(umin * width) - 2.0, x1 = std::ceil(umax * width) + 2.0;
+        double y0 = std::floor(vmin * height) - 2.0, y1 = std::ceil(vmax * height) + 2.0;
+        auto clampi = [](double v, double lo, double hi) { return (int)std::max(lo, std::min(hi, v)); };
+        rects[i] = make_int4(clampi(x0, -1.0, (double)width), clampi(y0, -1.0, (double)height),
+                             clampi(x1, -1.0, (double)width), clampi(y1, -1.0, (double)height));
+    }
+    n = n_inst;
+    return true;
 }
 
 // Upper bound of the largest singular value of the upper-left 3x3 block A of a column-major 4x4:
@@ -466,6 +534,7 @@ int fill_scene(bvht_ctx* ctx, SceneDev& s) {
     if (rc) return rc;
     s.tlas = (const float4*)ctx->tlas.p;
     s.tlas_tight = (const float4*)ctx->tlas_tight.p;
+    s.tlas_mask = (const uint32_t*)ctx->tlas_mask.p;
     s.tight_center[0] = (float)ctx->bake_center[0]; s.tight_center[1] = (float)ctx->bake_center[1]; s.tight_center[2] = (float)ctx->bake_center[2];
     s.inst_cols = (const float4*)ctx->inst_cols.p;
     s.inst_blas = (const uint32_t*)ctx->inst_blas.p;
@@ -560,7 +629,7 @@ void bvht_destroy(bvht_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (Blas& b : ctx->blas) free_blas(b);
     for (DevBuf* d : { &ctx->blas_desc, &ctx->tlas, &ctx->inst_cols, &ctx->inst_blas, &ctx->work_counter, &ctx->out_buf, &ctx->rays_buf,
-                       &ctx->rgba_buf, &ctx->tlas_tight })
+                       &ctx->rgba_buf, &ctx->tlas_tight, &ctx->tlas_mask })
         release(*d);
     for (cudaStream_t st : { ctx->aux[0], ctx->aux[1], ctx->copy_stream }) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     for (cudaEvent_t ev : { ctx->ev_fork, ctx->ev_join }) if (ev) cudaEventDestroy(ev);
@@ -835,6 +904,8 @@ static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvh
         memcpy(&p.hit_rgba, shade->hit_rgba, 4); memcpy(&p.miss_rgba, shade->miss_rgba, 4);
     }
     p.work_counter = (unsigned int*)ctx->work_counter.p + slot;
+    p.n_rect = 0;
+    if (accel_on(ctx)) { uint32_t nr = 0; if (compute_instance_rects(ctx, camera, width, height, p.inst_rect, nr)) p.n_rect = nr; }
     int grid = persistent_grid(ctx, true, n_items);
     cudaError_t e = fast_on(ctx) ? launch_primary_fast(p, accel_on(ctx), grid, kTraceBlock, stream)
                                  : launch_primary_strict(p, accel_on(ctx), grid, kTraceBlock, stream);
@@ -1128,6 +1199,7 @@ int bvht_debug_trace_stats(bvht_ctx* ctx, const bvht_camera* camera, uint32_t wi
     p.out = (uint4*)ctx->out_buf.p;
     p.work_counter = (unsigned int*)ctx->work_counter.p;
     p.stats = (unsigned long long*)cnt.p;
+    if (accel_on(ctx)) { uint32_t nr = 0; if (compute_instance_rects(ctx, camera, width, height, p.inst_rect, nr)) p.n_rect = nr; }
     cudaMemsetAsync(cnt.p, 0, 16 * sizeof(uint64_t), ctx->stream);
     cudaMemsetAsync(ctx->work_counter.p, 0, 4, ctx->stream);
     int per_sm = std::max(1, blocks_per_sm_primary_stats(accel_on(ctx), kTraceBlock));

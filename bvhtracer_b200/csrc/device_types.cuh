@@ -34,6 +34,7 @@ struct BlasDesc {
 struct SceneDev {
     const float4*   tlas_tight;  // accel only, 2 float4 per TLAS node: conservative world box of the REAL geometry below the
                                  //   node {lo.xyz, max |d_w|^2} {hi.xyz, max |o_w - tight_center|^2} (limits under which it may be used)
+    const uint32_t* tlas_mask;   // accel only, n_inst <= 32: bit i set when instance i is below the node
     const float4*   tlas;        // 2 float4 per TLAS node
     const float4*   inst_cols;   // 4 float4 per instance: columns of the inverse transform
     const uint32_t* inst_blas;   // blas id per instance
@@ -64,6 +65,10 @@ struct PrimaryParams {
     uint32_t  hit_rgba, miss_rgba;       // IntersectionShader::new(hit, miss), packed r | g<<8 | b<<16 | a<<24
     unsigned int* work_counter;          // persistent-thread work cursor
     unsigned long long* stats;           // debug counters (stats build only)
+    // accel only: conservative screen-space rectangle (pixels, inclusive) of each instance's tight box for THIS camera;
+    // n_rect == 0 disables the tile-level candidate masks
+    uint32_t  n_rect;
+    int4      inst_rect[32];
 };
 
 struct RaysParams {

@@ -333,7 +333,8 @@ __device__ __forceinline__ void blas_intersect(const BlasDesc& B, const RayM& r,
 
 // scene/tlas.rs:123-177 + scene_object.rs:78-89.  World ray (ox..dz, recip), initial t = tmax.
 template <bool ACCEL>
-__device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM& w, float tmax, Stat& st) {
+__device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM& w, float tmax, uint32_t cand, Stat& st) {
+    // cand (ACCEL): bit i clear = instance i cannot be hit by this ray (tile-level screen rectangles); all ones = unknown
     st.add(0);
     HitRec best;
     best.t = FLT_MAX; best.u = 0.0f; best.v = 0.0f; best.id = 0xFFFFFFFFu;
@@ -360,6 +361,7 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
         float4 t0 = ldg4(S.tlas_tight + 0), t1 = ldg4(S.tlas_tight + 1);
         float tt;
         if (wd2 <= t0.w && wo2 <= t1.w && !slab_test_sub(t0, t1, wf, closest, tt)) return best;   // nothing reachable at all
+        if (cand != 0xFFFFFFFFu && (__ldg(S.tlas_mask + 0) & cand) == 0u) return best;
     }
     for (;;) {
         uint32_t lr = __float_as_uint(n0.w);
@@ -417,13 +419,27 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
             uint32_t ri = lr & 0x0000FFFFu;            // right_blas() = lower half (tlas.rs:30-32)
             bool lt = true, rt = true;
             if (ACCEL) {
-                // tight boxes first (one FMA per plane): a child whose real geometry the ray cannot reach closer than
-                // `closest` is dropped without evaluating the reference's box test for it
-                float4 a0 = ldg4(S.tlas_tight + 2 * (size_t)li), a1 = ldg4(S.tlas_tight + 2 * (size_t)li + 1);
-                float4 b0 = ldg4(S.tlas_tight + 2 * (size_t)ri), b1 = ldg4(S.tlas_tight + 2 * (size_t)ri + 1);
+                // candidate masks first (no memory traffic beyond one word per child), then the tight boxes (one FMA per
+                // plane): a child whose real geometry the ray cannot reach closer than `closest` is dropped without
+                // evaluating the reference's box test for it
+                bool l_tight = true, r_tight = true;
+                if (cand != 0xFFFFFFFFu) {
+                    uint32_t ml = __ldg(S.tlas_mask + li), mr = __ldg(S.tlas_mask + ri);
+                    lt = (ml & cand) != 0u;
+                    rt = (mr & cand) != 0u;
+                    // with candidate masks active the interior tight boxes add little: test them at the leaves only
+                    l_tight = __popc(ml) == 1;
+                    r_tight = __popc(mr) == 1;
+                }
                 float tt;
-                if (wd2 <= a0.w && wo2 <= a1.w) lt = slab_test_sub(a0, a1, wf, closest, tt);
-                if (wd2 <= b0.w && wo2 <= b1.w) rt = slab_test_sub(b0, b1, wf, closest, tt);
+                if (lt && l_tight) {
+                    float4 a0 = ldg4(S.tlas_tight + 2 * (size_t)li), a1 = ldg4(S.tlas_tight + 2 * (size_t)li + 1);
+                    if (wd2 <= a0.w && wo2 <= a1.w) lt = slab_test_sub(a0, a1, wf, closest, tt);
+                }
+                if (rt && r_tight) {
+                    float4 b0 = ldg4(S.tlas_tight + 2 * (size_t)ri), b1 = ldg4(S.tlas_tight + 2 * (size_t)ri + 1);
+                    if (wd2 <= b0.w && wo2 <= b1.w) rt = slab_test_sub(b0, b1, wf, closest, tt);
+                }
             }
             float4 l0 = n0, l1 = n1, r0 = n0, r1 = n1;
             float ld = 0.0f, rd = 0.0f;
@@ -533,9 +549,29 @@ trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
         uint32_t iu = p % P.tile, iv = p / P.tile;
         uint32_t px = tx * P.tile + iu, py = ty * P.tile + iv;
         bool active = (iv < P.tile) && px >= P.x0 && px < P.x1 && py >= P.y0 && py < P.y1;
+        uint32_t cand = 0xFFFFFFFFu;
+        if (ACCEL) {
+            if (P.n_rect) {
+                // which instances can this warp's pixel block see at all?  lane i tests instance i's screen rectangle
+                int bx0 = (int)(tx * P.tile), bx1 = bx0 + (int)P.tile - 1;
+                int by0 = (int)(ty * P.tile + (sub * 32u) / P.tile), by1 = (int)(ty * P.tile + (sub * 32u + 31u) / P.tile);
+                bool ov = false;
+                if (lane < P.n_rect) {
+                    int4 rc = P.inst_rect[lane];
+                    ov = !(rc.z < bx0 || rc.x > bx1 || rc.w < by0 || rc.y > by1);
+                }
+                cand = __ballot_sync(0xFFFFFFFFu, ov);
+            }
+        }
         if (active) {
-            RayM w = primary_ray(P.cam, px, py, P.width, P.height);
-            HitRec h = scene_intersect<ACCEL>(P.scene, w, FLT_MAX, st);
+            HitRec h;
+            if (ACCEL && cand == 0u) {
+                h.t = FLT_MAX; h.u = 0.0f; h.v = 0.0f; h.id = 0xFFFFFFFFu;      // no instance can be seen from this block
+                st.add(0);
+            } else {
+                RayM w = primary_ray(P.cam, px, py, P.width, P.height);
+                h = scene_intersect<ACCEL>(P.scene, w, FLT_MAX, cand, st);
+            }
             if (P.out) {
                 uint4 o;
                 o.x = __float_as_uint(h.t); o.y = __float_as_uint(h.u); o.z = __float_as_uint(h.v); o.w = h.id;
@@ -573,7 +609,7 @@ trace_rays_kernel(const __grid_constant__ RaysParams P) {
             w.dx = __ldg(rp + 3); w.dy = __ldg(rp + 4); w.dz = __ldg(rp + 5);
             float t = __ldg(rp + 6);
             w.rdx = __fdiv_rn(1.0f, w.dx); w.rdy = __fdiv_rn(1.0f, w.dy); w.rdz = __fdiv_rn(1.0f, w.dz);
-            HitRec h = scene_intersect<ACCEL>(P.scene, w, t, st);
+            HitRec h = scene_intersect<ACCEL>(P.scene, w, t, 0xFFFFFFFFu, st);
             uint4 o;
             o.x = __float_as_uint(h.t); o.y = __float_as_uint(h.u); o.z = __float_as_uint(h.v); o.w = h.id;
             P.out[i] = o;
