@@ -37,10 +37,10 @@ class Rect(C.Structure):
 
 class ShadeParams(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("depth_scale", C.c_float), ("depth_offset", C.c_float),
-                ("hit_rgba", C.c_uint8 * 4), ("miss_rgba", C.c_uint8 * 4)]
+                ("hit_rgba", C.c_uint8 * 4), ("miss_rgba", C.c_uint8 * 4), ("object0_transform", C.c_float * 16)]
 
 
-SHADE_NONE, SHADE_DEPTH, SHADE_INTERSECTION, SHADE_UV = 0, 1, 2, 3
+SHADE_NONE, SHADE_DEPTH, SHADE_INTERSECTION, SHADE_UV, SHADE_NORMAL = 0, 1, 2, 3, 4
 
 
 class Stats(C.Structure):
@@ -66,6 +66,7 @@ SYMBOLS = [
     ("bvht_sync", C.c_int, [_P]),
     ("bvht_blas_create", C.c_int, [_P, _P, C.c_uint32, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     ("bvht_blas_destroy", C.c_int, [_P, C.c_uint32]),
+    ("bvht_blas_set_normals", C.c_int, [_P, C.c_uint32, _P, C.c_uint32]),
     ("bvht_blas_update_vertices", C.c_int, [_P, C.c_uint32, _P, C.c_uint32]),
     ("bvht_blas_refit", C.c_int, [_P, C.c_uint32]),
     ("bvht_blas_read_nodes", C.c_int, [_P, C.c_uint32, _P, C.c_uint32]),

@@ -39,7 +39,7 @@ struct Blas {
     uint32_t n_tris = 0, nodes_used = 0;
     std::vector<bvht_bvh_node> h_nodes;     // host copy of the uploaded node pool (topology for validation / accel)
     std::vector<float> h_tris;              // host copy of the vertices (needed to rebuild the leaf accelerator)
-    DevBuf tris_aos, nodes, tri;
+    DevBuf tris_aos, nodes, tri, normals;      // normals: 3 float4 per primitive, ORIGINAL primitive order
     // refit plan
     DevBuf chunk_leaf, chunk_first, chunk_count, leaf_chunks, parent, scratch, counters;
     uint32_t n_chunks = 0;
@@ -145,7 +145,7 @@ int h2d_staged(bvht_ctx* ctx, void* dst, const void* src, size_t bytes, size_t& 
 }
 
 void free_blas(Blas& b) {
-    for (DevBuf* d : { &b.tris_aos, &b.nodes, &b.tri, &b.chunk_leaf, &b.chunk_first, &b.chunk_count,
+    for (DevBuf* d : { &b.tris_aos, &b.nodes, &b.tri, &b.normals, &b.chunk_leaf, &b.chunk_first, &b.chunk_count,
                        &b.leaf_chunks, &b.parent, &b.scratch, &b.counters, &b.sub_nodes, &b.sub_raw, &b.sub_order, &b.stri,
                        &b.leaf_sub_root })
         release(*d);
@@ -734,6 +734,23 @@ int bvht_blas_destroy(bvht_ctx* ctx, uint32_t blas_id) {
     return BVHT_OK;
 }
 
+int bvht_blas_set_normals(bvht_ctx* ctx, uint32_t blas_id, const float* normals, uint32_t n_tris) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (blas_id >= ctx->blas.size() || !ctx->blas[blas_id].alive) return fail(ctx, BVHT_ERR_BAD_HANDLE, "unknown blas id %u", blas_id);
+    Blas& b = ctx->blas[blas_id];
+    if (!normals) return fail(ctx, BVHT_ERR_INVALID_ARG, "null normals pointer");
+    if (n_tris != b.n_tris) return fail(ctx, BVHT_ERR_INVALID_ARG, "normals for %u primitives, model has %u", n_tris, b.n_tris);
+    cudaSetDevice(ctx->device);
+    std::vector<float> padded((size_t)n_tris * 12, 0.0f);          // 3 x float4 per primitive
+    for (uint32_t i = 0; i < n_tris; ++i)
+        for (int v = 0; v < 3; ++v) memcpy(&padded[(size_t)i * 12 + v * 4], normals + (size_t)i * 9 + v * 3, 12);
+    int rc = ensure(ctx, b.normals, padded.size() * 4);
+    if (rc) return rc;
+    if ((rc = h2d(ctx, b.normals.p, padded.data(), padded.size() * 4))) return rc;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return BVHT_OK;
+}
+
 int bvht_blas_update_vertices(bvht_ctx* ctx, uint32_t blas_id, const float* tris, uint32_t n_tris) {
     if (!ctx) return BVHT_ERR_BAD_HANDLE;
     if (blas_id >= ctx->blas.size() || !ctx->blas[blas_id].alive) return fail(ctx, BVHT_ERR_BAD_HANDLE, "unknown blas id %u", blas_id);
@@ -902,6 +919,16 @@ static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvh
         p.shade_kind = shade->kind;
         p.shade_scale = shade->depth_scale; p.shade_offset = shade->depth_offset;
         memcpy(&p.hit_rgba, shade->hit_rgba, 4); memcpy(&p.miss_rgba, shade->miss_rgba, 4);
+        if (shade->kind == BVHT_SHADE_NORMAL) {
+            // the reference's instance index is always 0: scene object 0's model supplies the normals (renderer.rs:258-266)
+            if (ctx->h_inst.empty()) return fail(ctx, BVHT_ERR_NOT_READY, "BVHT_SHADE_NORMAL needs at least one instance");
+            const Blas& b0 = ctx->blas[ctx->h_inst[0].blas_id];
+            if (!b0.normals.p) return fail(ctx, BVHT_ERR_NOT_READY, "BVHT_SHADE_NORMAL: bvht_blas_set_normals was not called for the model of scene object 0");
+            p.shade_normals = (const float4*)b0.normals.p;
+            p.shade_n_prims = b0.n_tris;
+            const float* m = shade->object0_transform;
+            for (int c = 0; c < 4; ++c) for (int r = 0; r < 3; ++r) p.shade_m[c * 3 + r] = m[c * 4 + r];
+        }
     }
     p.work_counter = (unsigned int*)ctx->work_counter.p + slot;
     p.n_rect = 0;
@@ -930,7 +957,7 @@ int bvht_render_frame_device(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
                              bvht_rect region, const bvht_shade_params* shade, void* frame_out_device, void* hits_out_device) {
     if (!ctx) return BVHT_ERR_BAD_HANDLE;
     if (!frame_out_device && !hits_out_device) return fail(ctx, BVHT_ERR_INVALID_ARG, "no output buffer");
-    if (frame_out_device && (!shade || shade->kind == BVHT_SHADE_NONE || shade->kind > BVHT_SHADE_UV))
+    if (frame_out_device && (!shade || shade->kind == BVHT_SHADE_NONE || shade->kind > BVHT_SHADE_NORMAL))
         return fail(ctx, BVHT_ERR_INVALID_ARG, "frame output requested without a valid shade kind");
     int rc = check_frame_args(ctx, camera, width, height, tile, region);
     if (rc) return rc;
@@ -997,7 +1024,7 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
                       bvht_rect region, const bvht_shade_params* shade, uint32_t* frame_out_host, bvht_hit* hits_out_host) {
     if (!ctx) return BVHT_ERR_BAD_HANDLE;
     if (!frame_out_host && !hits_out_host) return fail(ctx, BVHT_ERR_INVALID_ARG, "no output buffer");
-    if (frame_out_host && (!shade || shade->kind == BVHT_SHADE_NONE || shade->kind > BVHT_SHADE_UV))
+    if (frame_out_host && (!shade || shade->kind == BVHT_SHADE_NONE || shade->kind > BVHT_SHADE_NORMAL))
         return fail(ctx, BVHT_ERR_INVALID_ARG, "frame output requested without a valid shade kind");
     int rc = check_frame_args(ctx, camera, width, height, tile, region);
     if (rc) return rc;

@@ -63,6 +63,9 @@ struct PrimaryParams {
     uint32_t  shade_kind;                // bvht_shade_kind
     float     shade_scale, shade_offset; // DepthMappingShader::new(scale, offset)
     uint32_t  hit_rgba, miss_rgba;       // IntersectionShader::new(hit, miss), packed r | g<<8 | b<<16 | a<<24
+    const float4* shade_normals;         // kind 4: 3 float4 per primitive of scene object 0's model (un-reordered normals)
+    uint32_t  shade_n_prims;
+    float     shade_m[12];               // kind 4: columns 0..2 (xyz) + column 3 (xyz) of object 0's forward transform
     unsigned int* work_counter;          // persistent-thread work cursor
     unsigned long long* stats;           // debug counters (stats build only)
     // accel only: conservative screen-space rectangle (pixels, inclusive) of each instance's tight box for THIS camera;

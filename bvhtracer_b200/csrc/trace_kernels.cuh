@@ -71,6 +71,10 @@ struct Stat {
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
+// cglinalg Matrix4x4 * Vector4, one row: ((c0*x + c1*y) + c2*z) + c3*w with round-to-nearest intrinsics (never contracted)
+#define BVHT_MV4(cx0, cx1, cx2, cx3, x, y, z, wv) \
+    __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx0, x), __fmul_rn(cx1, y)), __fmul_rn(cx2, z)), __fmul_rn(cx3, wv))
+
 // geometry/aabb.rs:65-84.  `tcl` is the ray's current t.
 __device__ __forceinline__ bool slab_test(const float4 lo, const float4 hi, const RayM& r, float tcl, float& tmin_out) {
     float t_x1 = (lo.x - r.ox) * r.rdx;
@@ -372,8 +376,6 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
             RayM r;
             // transform.rs:219-234 over cglinalg Matrix4x4 * Vector4: ((c0*x + c1*y) + c2*z) + c3*w
             // (round-to-nearest intrinsics: never contracted, so the model-space ray is the reference's in BOTH builds)
-#define BVHT_MV4(cx0, cx1, cx2, cx3, x, y, z, wv) \
-    __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx0, x), __fmul_rn(cx1, y)), __fmul_rn(cx2, z)), __fmul_rn(cx3, wv))
             r.ox = BVHT_MV4(c0.x, c1.x, c2.x, c3.x, w.ox, w.oy, w.oz, 1.0f);
             r.oy = BVHT_MV4(c0.y, c1.y, c2.y, c3.y, w.ox, w.oy, w.oz, 1.0f);
             r.oz = BVHT_MV4(c0.z, c1.z, c2.z, c3.z, w.ox, w.oy, w.oz, 1.0f);
@@ -525,6 +527,32 @@ __device__ __forceinline__ uint32_t shade_pixel(const PrimaryParams& P, const Hi
         uint32_t r = min(255u, __float2uint_rz(255.0f * rx));
         uint32_t g = min(255u, __float2uint_rz(255.0f * ry));
         uint32_t b = min(255u, __float2uint_rz(255.0f * rz));
+        return r | (g << 8) | (b << 16) | 0xFF000000u;
+    }
+    if (P.shade_kind == 4u) {
+        // NormalMappingAccumulator (renderer.rs:256-286): normals[prim] of object 0's model (instance index is always 0),
+        // n = n0 * (1 - u - v) + n1 * u + n2 * v, object 0's transform_vector, normalize, (n + 1) * 0.5
+        float rx = 0.0f, ry = 0.0f, rz = 0.0f;
+        uint32_t prim = h.id & 0x000FFFFFu;
+        if (hit && prim < P.shade_n_prims) {
+            const float4* np = P.shade_normals + 3 * (size_t)prim;
+            float4 a = __ldg(np + 0), b = __ldg(np + 1), c = __ldg(np + 2);
+            float w0 = __fsub_rn(__fsub_rn(1.0f, h.u), h.v);
+            float mx = __fadd_rn(__fadd_rn(__fmul_rn(a.x, w0), __fmul_rn(b.x, h.u)), __fmul_rn(c.x, h.v));
+            float my = __fadd_rn(__fadd_rn(__fmul_rn(a.y, w0), __fmul_rn(b.y, h.u)), __fmul_rn(c.y, h.v));
+            float mz = __fadd_rn(__fadd_rn(__fmul_rn(a.z, w0), __fmul_rn(b.z, h.u)), __fmul_rn(c.z, h.v));
+            const float* M = P.shade_m;     // c0 = M[0..2], c1 = M[3..5], c2 = M[6..8], c3 = M[9..11]
+            float wx = BVHT_MV4(M[0], M[3], M[6], M[9], mx, my, mz, 0.0f);
+            float wy = BVHT_MV4(M[1], M[4], M[7], M[10], mx, my, mz, 0.0f);
+            float wz = BVHT_MV4(M[2], M[5], M[8], M[11], mx, my, mz, 0.0f);
+            float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(wx, wx), __fmul_rn(wy, wy)), __fmul_rn(wz, wz)));
+            rx = __fmul_rn(__fadd_rn(__fdiv_rn(wx, len), 1.0f), 0.5f);
+            ry = __fmul_rn(__fadd_rn(__fdiv_rn(wy, len), 1.0f), 0.5f);
+            rz = __fmul_rn(__fadd_rn(__fdiv_rn(wz, len), 1.0f), 0.5f);
+        }
+        uint32_t r = min(255u, __float2uint_rz(__fmul_rn(255.0f, rx)));
+        uint32_t g = min(255u, __float2uint_rz(__fmul_rn(255.0f, ry)));
+        uint32_t b = min(255u, __float2uint_rz(__fmul_rn(255.0f, rz)));
         return r | (g << 8) | (b << 16) | 0xFF000000u;
     }
     return 0u;

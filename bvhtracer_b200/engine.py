@@ -79,6 +79,10 @@ class Engine:
     def blas_destroy(self, blas_id):
         self._check(self._lib.bvht_blas_destroy(self._ctx, int(blas_id)))
 
+    def blas_set_normals(self, blas_id, normals):
+        normals = np.ascontiguousarray(np.asarray(normals, dtype="<f4").reshape(-1, 9))
+        self._check(self._lib.bvht_blas_set_normals(self._ctx, int(blas_id), ptr(normals), normals.shape[0]))
+
     def blas_update_vertices(self, blas_id, tris):
         tris = np.ascontiguousarray(np.asarray(tris, dtype="<f4").reshape(-1, 9))
         self._check(self._lib.bvht_blas_update_vertices(self._ctx, int(blas_id), ptr(tris), tris.shape[0]))
@@ -120,6 +124,12 @@ class Engine:
     def shade_depth(scale=80.0, offset=3.0):
         """DepthAccumulator + DepthMappingShader::new(scale, offset) (two/sixteen_armadillos.rs main)."""
         return ShadeParams(_ffi.SHADE_DEPTH, scale, offset, (C.c_uint8 * 4)(0, 0, 0, 0), (C.c_uint8 * 4)(0, 0, 0, 0))
+
+    @staticmethod
+    def shade_normal(object0_transform):
+        """NormalMappingAccumulator + RadianceToRgbShader (cube.rs / trippy_teapots.rs main); needs blas_set_normals."""
+        m = np.asarray(object0_transform, "<f4").reshape(16)
+        return ShadeParams(_ffi.SHADE_NORMAL, 0.0, 0.0, (C.c_uint8 * 4)(0, 0, 0, 0), (C.c_uint8 * 4)(0, 0, 0, 0), (C.c_float * 16)(*m))
 
     @staticmethod
     def shade_intersection(hit=(255, 255, 255, 255), miss=(0, 0, 0, 255)):

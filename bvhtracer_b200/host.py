@@ -34,7 +34,8 @@ def lib():
         L = C.CDLL(HOST_LIB)
         sig = {
             "bvhx_last_error": (C.c_char_p, []),
-            "bvhx_mesh_from_triangles": (_P, [_P, C.c_uint32]),
+            "bvhx_mesh_from_triangles": (_P, [_P, _P, C.c_uint32]),
+            "bvhx_mesh_normals": (_P, [_P]),
             "bvhx_mesh_from_tri_text": (_P, [C.c_char_p, C.c_size_t]),
             "bvhx_mesh_from_obj_text": (_P, [C.c_char_p, C.c_size_t]),
             "bvhx_mesh_len": (C.c_uint32, [_P]),
@@ -99,9 +100,17 @@ class Mesh:
         self._h = _nn(handle)
 
     @classmethod
-    def from_triangles(cls, tris):
+    def from_triangles(cls, tris, normals=None):
         tris = np.ascontiguousarray(np.asarray(tris, "<f4").reshape(-1, 9))
-        return cls(lib().bvhx_mesh_from_triangles(_ffi.ptr(tris), tris.shape[0]))
+        if normals is not None:
+            normals = np.ascontiguousarray(np.asarray(normals, "<f4").reshape(-1, 9))
+            assert normals.shape == tris.shape
+        return cls(lib().bvhx_mesh_from_triangles(_ffi.ptr(tris), _ffi.ptr(normals) if normals is not None else None, tris.shape[0]))
+
+    def normals(self):
+        n = lib().bvhx_mesh_len(self._h)
+        p = lib().bvhx_mesh_normals(self._h)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(max(n, 1), 9))[:n].copy()
 
     def primitives(self):
         n = lib().bvhx_mesh_len(self._h)
@@ -344,6 +353,11 @@ def intersection_pipeline(hit=(255, 255, 255, 255), miss=(0, 0, 0, 255)):
     return (_ffi.SHADE_INTERSECTION, 0.0, 0.0, tuple(hit), tuple(miss))
 
 
+def normal_pipeline():
+    """NormalMappingAccumulator + RadianceToRgbShader (cube.rs, trippy_teapots.rs)"""
+    return (_ffi.SHADE_NORMAL, 0.0, 0.0, (0, 0, 0, 0), (0, 0, 0, 0))
+
+
 def uv_pipeline():
     """UvMappingAccumulator + RadianceToRgbShader"""
     return (_ffi.SHADE_UV, 0.0, 0.0, (0, 0, 0, 0), (0, 0, 0, 0))
@@ -404,7 +418,18 @@ def load_asset_mesh(name, asset_dir=None):
     """Packed triangle soup (assets/<name>.f32; decoded from the reference's .tri/.obj by oracle/tools/pack_assets.py)."""
     asset_dir = asset_dir or os.path.join(os.path.dirname(_ffi.PKG), "assets")
     tris = np.fromfile(os.path.join(asset_dir, name + ".f32"), dtype="<f4").reshape(-1, 9)
+    npath = os.path.join(asset_dir, name + ".normals.f32")
+    if os.path.exists(npath):                      # OBJ models: the `vn` normals of each face corner
+        return Mesh.from_triangles(tris, np.fromfile(npath, dtype="<f4").reshape(-1, 9))
+    if name.endswith(".tri"):                      # .tri models: face normals derived by the decoder (mesh/decoders.rs:120-124)
+        return Mesh.from_triangles(tris, tri_face_normals(tris))
     return Mesh.from_triangles(tris)
+
+
+def tri_face_normals(tris):
+    """TriMeshDecoder's normals through the C++ decoder itself (text round trip is exact for f32 -> %.9g -> f32)."""
+    text = "\n".join(" ".join(repr(float(np.float32(x))) for x in t) for t in np.asarray(tris, "<f4").reshape(-1, 9))
+    return TriMeshDecoder(text).read_mesh().normals()
 
 
 def object_transform(o):

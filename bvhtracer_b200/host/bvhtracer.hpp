@@ -156,14 +156,19 @@ struct Intersection {
 
 // ------------------------------------------------------------------------------------------ mesh + decoders
 // mesh/mesh.rs:100-206 (positions only: tex coords / normals are not on the traced path)
+// Normals<f32, 3> (mesh.rs:55-96) has the layout of a Triangle: three Vector3
+using Normals = Triangle;
+
 struct Mesh {
     std::vector<Triangle> primitives;
+    std::vector<Normals> normals;             // per-vertex normals, NEVER reordered by the BVH build (bvh.rs:426 swaps positions only)
     size_t len_primitives() const { return primitives.size(); }
 };
 
 struct MeshBuilder {
     Mesh mesh;
-    MeshBuilder& with_primitive(const Triangle& t) { mesh.primitives.push_back(t); return *this; }
+    MeshBuilder& with_primitive(const Triangle& t) { mesh.primitives.push_back(t); mesh.normals.push_back(Normals()); return *this; }
+    MeshBuilder& with_primitive(const Triangle& t, const Normals& n) { mesh.primitives.push_back(t); mesh.normals.push_back(n); return *this; }
     Mesh build() { return std::move(mesh); }
 };
 
@@ -190,7 +195,12 @@ struct TriMeshDecoder {
         for (size_t k = 0; k + 8 < vals.size(); k += 9) {
             Triangle t;
             for (int v = 0; v < 3; ++v) t.vertices[v] = Vector3(vals[k + 3 * v], vals[k + 3 * v + 1], vals[k + 3 * v + 2]);
-            b.with_primitive(t);
+            // mesh/decoders.rs:120-124: one face normal on all three vertices
+            Vector3 v0v2 = (t.vertices[2] - t.vertices[0]).normalize();
+            Vector3 v0v1 = (t.vertices[1] - t.vertices[0]).normalize();
+            Vector3 normal = v0v2.cross(v0v1).normalize();
+            Normals n; n.vertices[0] = n.vertices[1] = n.vertices[2] = normal;
+            b.with_primitive(t, n);
         }
         return b.build();
     }
@@ -199,7 +209,7 @@ struct TriMeshDecoder {
 // mesh/decoders.rs:150-216 over cgwavefront_obj: positions f64 -> f32, faces of the first object, fan-triangulated
 struct ObjMeshDecoder {
     static Mesh read_mesh(const char* text, size_t len) {
-        std::vector<Vector3> pos;
+        std::vector<Vector3> pos, nrm;
         MeshBuilder b;
         size_t i = 0; int objects = 0;
         while (i < len) {
@@ -210,25 +220,40 @@ struct ObjMeshDecoder {
             line = line.substr(p);
             if (line.size() < 2) continue;
             if (line[0] == 'o' && (line[1] == ' ' || line[1] == '\t')) { if (++objects > 1 && !b.mesh.primitives.empty()) break; continue; }
-            if (line[0] == 'v' && (line[1] == ' ' || line[1] == '\t')) {
-                const char* c = line.c_str() + 1; char* e = nullptr; float v[3];
+            bool is_v = line[0] == 'v' && (line[1] == ' ' || line[1] == '\t');
+            bool is_vn = line.size() > 2 && line[0] == 'v' && line[1] == 'n' && (line[2] == ' ' || line[2] == '\t');
+            if (is_v || is_vn) {
+                const char* c = line.c_str() + (is_v ? 1 : 2); char* e = nullptr; float v[3];
                 for (int k = 0; k < 3; ++k) { double d = std::strtod(c, &e); if (e == c) throw std::runtime_error("bad vertex"); v[k] = (float)d; c = e; }
-                pos.push_back(Vector3(v[0], v[1], v[2]));
+                (is_v ? pos : nrm).push_back(Vector3(v[0], v[1], v[2]));
             } else if (line[0] == 'f' && (line[1] == ' ' || line[1] == '\t')) {
-                std::vector<long> idx; const char* c = line.c_str() + 1;
+                std::vector<long> idx, nidx; const char* c = line.c_str() + 1;
                 while (*c) {
                     while (*c == ' ' || *c == '\t' || *c == '\r') ++c;
                     if (!*c) break;
                     char* e = nullptr; long vi = std::strtol(c, &e, 10); if (e == c) break;
                     if (vi < 0) vi = (long)pos.size() + vi + 1;
-                    idx.push_back(vi - 1); c = e;
+                    c = e;
+                    long ni = 0; bool have = false;
+                    if (*c == '/') {                      // v/vt/vn, v//vn or v/vt
+                        ++c;
+                        if (*c != '/') { std::strtol(c, &e, 10); c = e; }
+                        if (*c == '/') { ++c; char* e2 = nullptr; ni = std::strtol(c, &e2, 10); if (e2 != c) { have = true; c = e2; } }
+                    }
+                    if (have && ni < 0) ni = (long)nrm.size() + ni + 1;
+                    idx.push_back(vi - 1); nidx.push_back(have ? ni - 1 : -1);
                     while (*c && *c != ' ' && *c != '\t') ++c;
                 }
                 for (size_t k = 1; k + 1 < idx.size(); ++k) {
-                    long tri[3] = { idx[0], idx[k], idx[k + 1] };
-                    Triangle t;
-                    for (int v = 0; v < 3; ++v) { if (tri[v] < 0 || (size_t)tri[v] >= pos.size()) throw std::runtime_error("face index out of range"); t.vertices[v] = pos[tri[v]]; }
-                    b.with_primitive(t);
+                    size_t tri[3] = { 0, k, k + 1 };
+                    Triangle t; Normals n;
+                    for (int v = 0; v < 3; ++v) {
+                        long pi = idx[tri[v]], ni = nidx[tri[v]];
+                        if (pi < 0 || (size_t)pi >= pos.size()) throw std::runtime_error("face index out of range");
+                        t.vertices[v] = pos[pi];
+                        n.vertices[v] = (ni >= 0 && (size_t)ni < nrm.size()) ? nrm[ni] : Vector3::zero();   // decoders.rs:182-203
+                    }
+                    b.with_primitive(t, n);
                 }
             }
         }
@@ -347,6 +372,7 @@ struct Model {
     Aabb bounds() const { return bvh.bounds(); }
     std::vector<Triangle>& primitives_mut() { geometry_version++; return mesh.primitives; }
     const std::vector<Triangle>& primitives() const { return mesh.primitives; }
+    const std::vector<Normals>& normals() const { return mesh.normals; }
     void refit() { refit_requested = true; }
 };
 using ModelInstance = std::shared_ptr<Model>;
@@ -571,6 +597,7 @@ struct ShadingPipeline {
         ShadingPipeline s{}; s.params.kind = BVHT_SHADE_INTERSECTION; std::memcpy(s.params.hit_rgba, hit, 4); std::memcpy(s.params.miss_rgba, miss, 4); return s;
     }
     static ShadingPipeline uv() { ShadingPipeline s{}; s.params.kind = BVHT_SHADE_UV; return s; }
+    static ShadingPipeline normal() { ShadingPipeline s{}; s.params.kind = BVHT_SHADE_NORMAL; return s; }   // object0_transform is filled per frame
 };
 
 // renderer.rs:76-102: frame buffer (Rgba<u8>, 4 B/px) + the per-pixel hit records (the GPU's "accumulation buffer")
@@ -648,6 +675,8 @@ public:
                 check(bvht_blas_create(ctx_, (const float*)m->primitives().data(), (uint32_t)m->primitives().size(),
                                        (const bvht_bvh_node*)m->bvh.nodes.data(), m->bvh.nodes_used, &u->blas_id));
                 u->version = m->geometry_version;
+                if (m->normals().size() == m->primitives().size())
+                    check(bvht_blas_set_normals(ctx_, u->blas_id, (const float*)m->normals().data(), (uint32_t)m->normals().size()));
             } else if (u->version != m->geometry_version || m->refit_requested) {
                 if (u->version != m->geometry_version)
                     check(bvht_blas_update_vertices(ctx_, u->blas_id, (const float*)m->primitives().data(), (uint32_t)m->primitives().size()));
@@ -678,7 +707,10 @@ public:
         state.bind(ctx_);
         bvht_camera cam = scene.active_camera().to_ffi();
         bvht_rect region = { 0, 0, (uint32_t)state.width(), (uint32_t)state.height() };
-        check(bvht_render_frame(ctx_, &cam, (uint32_t)state.width(), (uint32_t)state.height(), tile_, region, &state.shading().params,
+        bvht_shade_params shade = state.shading().params;
+        if (shade.kind == BVHT_SHADE_NORMAL && !scene.objects().empty())     // scene.get_unchecked(0).get_transform(), renderer.rs:275-278
+            std::memcpy(shade.object0_transform, scene.objects()[0].get_transform().matrix.m, 64);
+        check(bvht_render_frame(ctx_, &cam, (uint32_t)state.width(), (uint32_t)state.height(), tile_, region, &shade,
                                 state.frame_mut(), state.keep_hits() ? state.hits_mut() : nullptr));
         return state.width() * state.height();
     }

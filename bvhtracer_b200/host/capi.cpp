@@ -18,14 +18,17 @@ struct SceneBuilderHandle { Camera camera; std::vector<SceneObject> objects; };
 BVHX_API const char* bvhx_last_error() { return g_err.c_str(); }
 
 // ---- meshes
-BVHX_API void* bvhx_mesh_from_triangles(const float* tris, uint32_t n) {
+BVHX_API void* bvhx_mesh_from_triangles(const float* tris, const float* normals_or_null, uint32_t n) {
     return guard([&]() -> void* {
         Mesh* m = new Mesh();
         m->primitives.resize(n);
+        m->normals.resize(n);
         if (n) std::memcpy((void*)m->primitives.data(), tris, (size_t)n * sizeof(Triangle));
+        if (n && normals_or_null) std::memcpy((void*)m->normals.data(), normals_or_null, (size_t)n * sizeof(Normals));
         return m;
     }, nullptr);
 }
+BVHX_API const float* bvhx_mesh_normals(void* mesh) { return (const float*)((Mesh*)mesh)->normals.data(); }
 BVHX_API void* bvhx_mesh_from_tri_text(const char* text, size_t len) {
     return guard([&]() -> void* { return new Mesh(TriMeshDecoder::read_mesh(text, len)); }, nullptr);
 }
@@ -146,7 +149,8 @@ BVHX_API void* bvhx_state_new(uint32_t kind, float scale, float offset, const ui
                               uint32_t height, int keep_hits) {
     return guard([&]() -> void* {
         ShadingPipeline s = kind == BVHT_SHADE_DEPTH ? ShadingPipeline::depth(scale, offset)
-                          : kind == BVHT_SHADE_INTERSECTION ? ShadingPipeline::intersection(hit, miss) : ShadingPipeline::uv();
+                          : kind == BVHT_SHADE_INTERSECTION ? ShadingPipeline::intersection(hit, miss)
+                          : kind == BVHT_SHADE_NORMAL ? ShadingPipeline::normal() : ShadingPipeline::uv();
         return new RendererState(s, width, height, keep_hits != 0);
     }, nullptr);
 }

@@ -116,7 +116,10 @@ typedef enum {
     BVHT_SHADE_NONE = 0,
     BVHT_SHADE_DEPTH = 1,          /* DepthAccumulator (:184-194) + DepthMappingShader::new(scale, offset) (:207-222) */
     BVHT_SHADE_INTERSECTION = 2,   /* IntersectionAccumulator (:145-153) + IntersectionShader::new(hit, miss) (:166-174) */
-    BVHT_SHADE_UV = 3              /* UvMappingAccumulator (:233-245) + RadianceToRgbShader (:124-132) */
+    BVHT_SHADE_UV = 3,             /* UvMappingAccumulator (:233-245) + RadianceToRgbShader (:124-132) */
+    BVHT_SHADE_NORMAL = 4          /* NormalMappingAccumulator (:256-286) + RadianceToRgbShader; needs bvht_blas_set_normals for
+                                      the model of scene object 0 and object0_transform (the reference's instance index is
+                                      always 0, so it always looks up object 0's model and transform, :258-276) */
 } bvht_shade_kind;
 
 typedef struct {
@@ -125,6 +128,7 @@ typedef struct {
     float    depth_offset;         /* DepthMappingShader.offset ( 3 in the armadillo examples) */
     uint8_t  hit_rgba[4];          /* IntersectionShader.hit_value  */
     uint8_t  miss_rgba[4];         /* IntersectionShader.miss_value */
+    float    object0_transform[16];/* BVHT_SHADE_NORMAL: forward transform of scene object 0, column-major */
 } bvht_shade_params;
 
 typedef struct {
@@ -162,6 +166,11 @@ BVHT_API int         bvht_sync(bvht_ctx* ctx);
 BVHT_API int         bvht_blas_create(bvht_ctx* ctx, const float* tris, uint32_t n_tris,
                              const bvht_bvh_node* nodes, uint32_t nodes_used, uint32_t* out_blas_id);
 BVHT_API int         bvht_blas_destroy(bvht_ctx* ctx, uint32_t blas_id);
+
+/* Per-vertex normals of a model, `Mesh::normals()` (mesh.rs:158-166): n_tris x 9 f32 in the mesh's ORIGINAL primitive
+ * order -- the reference reorders only the positions when it builds the BVH (bvh.rs:426), and indexes this array with
+ * the reordered primitive index (renderer.rs:259-266); that behaviour is kept. */
+BVHT_API int         bvht_blas_set_normals(bvht_ctx* ctx, uint32_t blas_id, const float* normals, uint32_t n_tris);
 
 /* New vertex positions for an existing model (examples/big_ben_clock.rs:67-96 `animate`); same count. */
 BVHT_API int         bvht_blas_update_vertices(bvht_ctx* ctx, uint32_t blas_id, const float* tris, uint32_t n_tris);

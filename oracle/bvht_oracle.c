@@ -965,3 +965,106 @@ void orc_shade(uint32_t kind, float scale, float offset, uint32_t hit_rgba, uint
         rgba_out[i] = px;
     }
 }
+
+/* mesh/decoders.rs:120-124 (TriMeshDecoder): one face normal replicated on the three vertices */
+void orc_tri_normals(const float* tris, uint64_t n, float* out) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const float* t = tris + i * 9;
+        float a[3], b[3], an[3], bn[3], c[3], nn[3];
+        sub3(t + 6, t, a);              /* v0v2 = (v2 - v0).normalize() */
+        sub3(t + 3, t, b);              /* v0v1 = (v1 - v0).normalize() */
+        orc_vec3_normalize(a, an);
+        orc_vec3_normalize(b, bn);
+        cross3(an, bn, c);
+        orc_vec3_normalize(c, nn);
+        for (int v = 0; v < 3; ++v) for (int k = 0; k < 3; ++k) out[i * 9 + v * 3 + k] = nn[k];
+    }
+}
+
+/* mesh/decoders.rs:174-203: normals[i] = vn of the face corner (f64 -> f32), zero when absent; fan-triangulated like the faces */
+int64_t orc_parse_obj_normals(const char* text, size_t len, float** out) {
+    fvec vn = {0, 0, 0};
+    fvec res = {0, 0, 0};
+    size_t i = 0;
+    int objects_seen = 0;
+    size_t n_pos = 0;
+    while (i < len) {
+        size_t ls = i;
+        while (i < len && text[i] != '\n') ++i;
+        size_t le = i; if (i < len) ++i;
+        while (ls < le && (text[ls] == ' ' || text[ls] == '\t')) ++ls;
+        if (ls >= le) continue;
+        char line[512];
+        size_t ll = le - ls; if (ll >= sizeof line) ll = sizeof line - 1;
+        memcpy(line, text + ls, ll); line[ll] = 0;
+        if (line[0] == 'o' && (line[1] == ' ' || line[1] == '\t')) { if (++objects_seen > 1 && res.n > 0) break; continue; }
+        if (line[0] == 'v' && (line[1] == ' ' || line[1] == '\t')) { n_pos++; continue; }
+        if (line[0] == 'v' && line[1] == 'n' && (line[2] == ' ' || line[2] == '\t')) {
+            char* p = line + 2;
+            for (int k = 0; k < 3; ++k) {
+                char* e = NULL; double d = strtod(p, &e);
+                if (e == p) { free(vn.v); free(res.v); return -3; }
+                p = e;
+                if (fvec_push(&vn, (float)d)) { free(vn.v); free(res.v); return -4; }
+            }
+        } else if (line[0] == 'f' && (line[1] == ' ' || line[1] == '\t')) {
+            long nidx[64]; int nv = 0;
+            char* p = line + 1;
+            while (*p && nv < 64) {
+                while (*p == ' ' || *p == '\t' || *p == '\r') ++p;
+                if (!*p) break;
+                char* e = NULL;
+                long vi = strtol(p, &e, 10);
+                if (e == p) break;
+                (void)vi;
+                p = e;
+                long ni = 0; int have = 0;
+                if (*p == '/') {               /* v/vt/vn or v//vn or v/vt */
+                    ++p;
+                    if (*p != '/') { strtol(p, &e, 10); p = e; }
+                    if (*p == '/') { ++p; char* e2 = NULL; ni = strtol(p, &e2, 10); if (e2 != p) { have = 1; p = e2; } }
+                }
+                long count = (long)(vn.n / 3);
+                if (have && ni < 0) ni = count + ni + 1;
+                nidx[nv++] = have ? ni - 1 : -1;
+                while (*p && *p != ' ' && *p != '\t') ++p;
+            }
+            for (int k = 1; k + 1 < nv; ++k) {
+                long tri_idx[3] = { nidx[0], nidx[k], nidx[k + 1] };
+                for (int c = 0; c < 3; ++c) {
+                    long ni = tri_idx[c];
+                    for (int d = 0; d < 3; ++d) {
+                        float val = (ni >= 0 && (size_t)ni * 3 + 2 < vn.n) ? vn.v[ni * 3 + d] : 0.0f;
+                        if (fvec_push(&res, val)) { free(vn.v); free(res.v); return -4; }
+                    }
+                }
+            }
+        }
+    }
+    (void)n_pos;
+    free(vn.v);
+    *out = res.v;
+    return (int64_t)(res.n / 9);
+}
+
+void orc_shade_normal(const float* normals, uint64_t n_prims, const float m[16], const orc_hit* hits, uint64_t n, uint32_t* rgba_out) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const orc_hit* h = &hits[i];
+        float r[3] = { 0.0f, 0.0f, 0.0f };
+        if (h->id != 0xFFFFFFFFu) {
+            uint32_t prim = h->id & 0x000FFFFFu;            /* instance index is always 0 */
+            if (prim < n_prims) {
+                const float* nm = normals + (size_t)prim * 9;
+                float w0 = (1.0f - h->u) - h->v;             /* 1_f32 - u - v */
+                float ms[3], ws[3], nn[3];
+                for (int k = 0; k < 3; ++k) ms[k] = (nm[k] * w0 + nm[3 + k] * h->u) + nm[6 + k] * h->v;
+                orc_transform_vector(m, ms, ws);
+                orc_vec3_normalize(ws, nn);
+                for (int k = 0; k < 3; ++k) r[k] = (nn[k] + 1.0f) * 0.5f;
+            }
+        }
+        uint32_t c[3];
+        for (int k = 0; k < 3; ++k) { c[k] = f32_as_u8(255.0f * r[k]); if (c[k] > 255) c[k] = 255; }
+        rgba_out[i] = c[0] | (c[1] << 8) | (c[2] << 16) | 0xFF000000u;
+    }
+}

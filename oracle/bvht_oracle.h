@@ -107,6 +107,11 @@ void  orc_triangle_centroid(const float tri[9], float out[3]);
 int64_t orc_parse_tri(const char* text, size_t len, float** out);
 int64_t orc_parse_obj(const char* text, size_t len, float** out);
 int64_t orc_load_mesh_file(const char* path, float** out);   /* by extension .tri/.obj */
+/* per-vertex normals in FILE order (n x 9 floats), as the decoders build them:
+ *  .tri: normal = normalize(cross(normalize(v2-v0), normalize(v1-v0))) for all three vertices (mesh/decoders.rs:120-124)
+ *  .obj: the `vn` referenced by each face corner (f64 -> f32), zero when the corner has none (mesh/decoders.rs:174-203) */
+void    orc_tri_normals(const float* tris, uint64_t n, float* normals_out);
+int64_t orc_parse_obj_normals(const char* text, size_t len, float** out);
 void    orc_free(void* p);
 
 /* ---- BLAS build / refit (model/bvh.rs:317-541) ---- */
@@ -159,6 +164,11 @@ void orc_trace_rays(const orc_scene* s, const float* o_d_t /* n x 7 */, uint64_t
  * 3: UvMappingAccumulator + RadianceToRgbShader.  rgba_out: r | g<<8 | b<<16 | a<<24 (Rgba<u8> byte order). */
 void orc_shade(uint32_t kind, float scale, float offset, uint32_t hit_rgba, uint32_t miss_rgba,
                const orc_hit* hits, uint64_t n, uint32_t* rgba_out);
+/* kind 4: NormalMappingAccumulator (renderer.rs:256-286) + RadianceToRgbShader (:124-132).  normals = the UN-reordered
+ * per-vertex normals of scene object 0's model indexed with the (BVH-reordered) primitive index, object0_transform =
+ * scene object 0's forward transform -- both exactly what the reference looks up (its instance index is always 0). */
+void orc_shade_normal(const float* normals, uint64_t n_prims, const float object0_transform[16],
+                      const orc_hit* hits, uint64_t n, uint32_t* rgba_out);
 
 int  orc_max_threads(void);
 

@@ -46,6 +46,18 @@ def main():
         lib.orc_free(p)
         arr.tofile(os.path.join(ROOT, "assets", out_name))
         print(f"{out_name}: {n} triangles, {arr.nbytes} bytes")
+        if rel.endswith(".obj"):
+            # per-vertex normals of the OBJ models (NormalMappingAccumulator needs them; .tri normals are derived from positions)
+            text = open(os.path.join(ref, rel), "rb").read()
+            q = ctypes.POINTER(ctypes.c_float)()
+            lib.orc_parse_obj_normals.restype = ctypes.c_int64
+            lib.orc_parse_obj_normals.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.POINTER(ctypes.c_float))]
+            m = lib.orc_parse_obj_normals(text, len(text), ctypes.byref(q))
+            assert m == n, (m, n)
+            nrm = np.ctypeslib.as_array(q, shape=(m, 9)).astype("<f4").copy()
+            lib.orc_free(q)
+            nrm.tofile(os.path.join(ROOT, "assets", out_name.replace(".f32", ".normals.f32")))
+            print(f"{out_name.replace('.f32', '.normals.f32')}: {m} x 9 normals")
 
 
 if __name__ == "__main__":

@@ -321,3 +321,38 @@ def shade(kind, hits, scale=80.0, offset=3.0, hit_rgba=0xFFFFFFFF, miss_rgba=0xF
     lib().orc_shade(C.c_uint32(kind), C.c_float(scale), C.c_float(offset), C.c_uint32(hit_rgba), C.c_uint32(miss_rgba),
                     _p(hits), C.c_uint64(hits.size), _p(out))
     return out
+
+
+def tri_normals(tris):
+    """TriMeshDecoder normals (mesh/decoders.rs:120-124) for file-order triangles -> n x 9."""
+    tris = np.ascontiguousarray(np.asarray(tris, np.float32).reshape(-1, 9))
+    out = np.zeros_like(tris)
+    lib().orc_tri_normals(_p(tris), C.c_uint64(tris.shape[0]), _p(out))
+    return out
+
+
+def parse_obj_normals(text):
+    b = text.encode() if isinstance(text, str) else text
+    p = C.POINTER(C.c_float)()
+    lib().orc_parse_obj_normals.restype = C.c_int64
+    n = lib().orc_parse_obj_normals(b, C.c_size_t(len(b)), C.byref(p))
+    if n < 0:
+        raise ValueError(f"orc_parse_obj_normals failed: {n}")
+    arr = np.ctypeslib.as_array(p, shape=(max(n, 1), 9))[:n].copy() if n else np.zeros((0, 9), np.float32)
+    lib().orc_free(p)
+    return arr
+
+
+def load_asset_normals(name):
+    """Packed per-vertex normals (assets/<name>.normals.f32, file order)."""
+    return np.fromfile(os.path.join(ASSET_DIR, name + ".normals.f32"), dtype="<f4").reshape(-1, 9).copy()
+
+
+def shade_normal(normals, object0_transform, hits):
+    """NormalMappingAccumulator + RadianceToRgbShader (renderer.rs:256-286, 124-132)."""
+    normals = np.ascontiguousarray(np.asarray(normals, np.float32).reshape(-1, 9))
+    m = np.ascontiguousarray(np.asarray(object0_transform, np.float32).reshape(16))
+    hits = np.ascontiguousarray(hits)
+    out = np.zeros(hits.size, "<u4")
+    lib().orc_shade_normal(_p(normals), C.c_uint64(normals.shape[0]), _p(m), _p(hits), C.c_uint64(hits.size), _p(out))
+    return out

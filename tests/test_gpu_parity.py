@@ -514,3 +514,42 @@ def test_fast_mode_full_size_against_strict_gpu(name, arg, size):
     for label in res:
         if label != "strict":
             assert_fast(res[label], res["strict"])
+
+
+# ------------------------------------------------------------------------------------------ NormalMappingAccumulator
+@pytest.mark.parametrize("name,arg,asset", [("trippy_teapots", 6, "teapot.obj"), ("cube", None, "cube.obj")])
+def test_normal_mapping_shader_matches_oracle(name, arg, asset):
+    # renderer.rs:256-286: normals[prim] of object 0's model (UN-reordered array, reordered index; instance always 0),
+    # object 0's transform, normalize, (n + 1) / 2, then RadianceToRgbShader -- what cube.rs and trippy_teapots.rs display
+    spec = examples.CONFIGS[name]() if arg is None else examples.CONFIGS[name](arg)
+    scene, cam = SB.oracle_scene(spec)
+    normals = O.load_asset_normals(asset)
+    m0 = SB.object_matrix(spec.objects[0])
+    w, h = 480, 272
+    ref_hits = scene.render(cam, w, h, threads=NTHREADS)
+    ref = O.shade_normal(normals, m0, ref_hits)
+    with Engine(flags=FLAG_STRICT | FLAG_LEAF_ACCEL) as eng:
+        ids = SB.upload_scene(eng, scene)
+        with pytest.raises(BvhtError):                               # normals not uploaded yet
+            eng.render_frame(SB.to_ffi_camera(cam), w, h, eng.shade_normal(m0))
+        eng.blas_set_normals(ids[0], normals)
+        frame, hits = eng.render_frame(SB.to_ffi_camera(cam), w, h, eng.shade_normal(m0), want_hits=True)
+    assert hits.tobytes() == ref_hits.tobytes()
+    assert frame.tobytes() == ref.tobytes()
+    assert len(np.unique(frame)) > 4
+
+
+def test_host_mirror_normal_mapping_example():
+    # trippy_teapots.rs main: NormalMappingAccumulator + RadianceToRgbShader through Renderer::render
+    from bvhtracer_b200 import host
+    spec = examples.trippy_teapots(3)
+    scene, models = host.build_scene(spec)
+    renderer = host.Renderer(flags=FLAG_STRICT | FLAG_LEAF_ACCEL)
+    w, h = 400, 224
+    state = host.RendererState(host.normal_pipeline(), w, h, keep_hits=True)
+    renderer.render(state, scene)
+    ref_scene, ref_cam = SB.oracle_scene(spec)
+    ref_hits = ref_scene.render(ref_cam, w, h, threads=NTHREADS)
+    assert state.hits().tobytes() == ref_hits.tobytes()
+    ref = O.shade_normal(O.load_asset_normals("teapot.obj"), SB.object_matrix(spec.objects[0]), ref_hits)
+    assert state.frame_buffer().tobytes() == ref.tobytes()

@@ -81,3 +81,14 @@ def test_transform_matches_oracle():
         b = O.transform_new_rot_xz(s, t, ax, az)
         assert a.matrix.tobytes() == b.tobytes()
         assert a.inverse().matrix.tobytes() == O.mat4_inverse(b).tobytes()
+
+
+def test_decoder_normals_match_oracle():
+    tris = O.load_asset("unity.tri")[:800]
+    assert host.tri_face_normals(tris).tobytes() == O.tri_normals(tris).tobytes()
+    obj = "g q\nv 0.1 0 0\nv 1 0 0.25\nv 1 1 0\nv 0 1 0\nvn 0 0 1\nvn 0.6 0 0.8\nf 1//1 2//2 3//1\nf 1/1/2 3/1/1 4/1/2\nf 1 2 3 4\n"
+    m = host.ObjMeshDecoder(obj).read_mesh()
+    assert m.normals().tobytes() == O.parse_obj_normals(obj).tobytes()
+    assert m.primitives().tobytes() == O.parse_obj(obj).tobytes()
+    assert m.normals()[0].tolist() == [0, 0, 1, np.float32(0.6), 0, np.float32(0.8), 0, 0, 1]
+    assert not m.normals()[2:].any()                     # faces without vn get zero normals (decoders.rs:176-181)

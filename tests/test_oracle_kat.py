@@ -388,3 +388,14 @@ def test_render_threads_and_regions_agree():
     c = scene.render(cam, 64, 48, region=(0, 0, 64, 24))
     c = scene.render(cam, 64, 48, region=(0, 24, 64, 48), out=c)
     assert a.tobytes() == c.tobytes()
+
+
+def test_tri_decoder_normals_kat():
+    # tests/test_tri_mesh.rs:24-72: the decoder's per-vertex normals of the two-triangle case, bit-exact
+    tris = np.array([[0.577350, -0.5, -0.1, 0.577350, -0.5, 0.1, -0.577350, -0.5, 0.1],
+                     [-0.577350, -0.5, -0.1, 0.0, 0.5, -0.1, 0.0, 0.5, 0.1]], np.float32)
+    n = O.tri_normals(tris)
+    assert n[0].reshape(3, 3).tolist() == [[0.0, 1.0, 0.0]] * 3
+    expected = np.array([-0.86602545, 0.49999988, -1.7462564e-7], np.float32)
+    for v in range(3):
+        assert n[1, 3 * v:3 * v + 3].tobytes() == expected.tobytes()
