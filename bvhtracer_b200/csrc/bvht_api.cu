@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -135,15 +136,6 @@ int h2d(bvht_ctx* ctx, void* dst, const void* src, size_t bytes) {
     return BVHT_OK;
 }
 
-// Upload a small host array through the pinned staging buffer (safe to return before the copy has run).
-int h2d_staged(bvht_ctx* ctx, void* dst, const void* src, size_t bytes, size_t& staging_off) {
-    if (bytes == 0) return BVHT_OK;
-    memcpy((char*)ctx->pinned + staging_off, src, bytes);
-    int rc = h2d(ctx, dst, (char*)ctx->pinned + staging_off, bytes);
-    staging_off += (bytes + 255) & ~size_t(255);
-    return rc;
-}
-
 void free_blas(Blas& b) {
     for (DevBuf* d : { &b.tris_aos, &b.nodes, &b.tri, &b.normals, &b.chunk_leaf, &b.chunk_first, &b.chunk_count,
                        &b.leaf_chunks, &b.parent, &b.scratch, &b.counters, &b.sub_nodes, &b.sub_raw, &b.sub_order, &b.stri,
@@ -225,6 +217,7 @@ int bake_accel(bvht_ctx* ctx, Blas& b, double d_max, double o_max) {
 
 int build_and_upload_accel(bvht_ctx* ctx, Blas& b) {
     LeafAccelConfig cfg;
+    if (const char* e = getenv("BVHT_SUB_LEAF")) { int v = atoi(e); if (v >= 1 && v <= 8) cfg.max_sub_leaf = (uint32_t)v; }   // tuning knob
     LeafAccelHost acc;
     if (!build_leaf_accel(b.h_tris.data(), b.n_tris, b.h_nodes.data(), b.nodes_used, cfg, acc))
         return fail(ctx, BVHT_ERR_MALFORMED_BVH, "leaf accelerator build failed");
