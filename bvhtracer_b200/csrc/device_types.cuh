@@ -12,8 +12,8 @@
 
 namespace bvht {
 
-constexpr int kTlasStack = 32;   // validated at bvht_tlas_set (depth of the uploaded tree)
-constexpr int kBlasStack = 32;   // validated at bvht_blas_create
+constexpr int kTlasStack = 64;   // validated at bvht_tlas_set (depth of the uploaded tree)
+constexpr int kBlasStack = 64;   // validated at bvht_blas_create
 constexpr int kSubStack  = 48;   // leaf sub-BVH (built by us, depth bounded at build)
 
 // One per uploaded model.  Pointers are device addresses.

@@ -553,3 +553,25 @@ def test_host_mirror_normal_mapping_example():
     assert state.hits().tobytes() == ref_hits.tobytes()
     ref = O.shade_normal(O.load_asset_normals("teapot.obj"), SB.object_matrix(spec.objects[0]), ref_hits)
     assert state.frame_buffer().tobytes() == ref.tobytes()
+
+
+@pytest.mark.parametrize("flags", STRICT_MODES, ids=MODE_IDS)
+def test_many_instances_deep_tlas(flags):
+    # 150 randomly placed/rotated/scaled teapots + cubes: more than 32 instances (no tile masks), a deep agglomerative
+    # TLAS, two BLASes, overlapping instances.  No reference test covers multi-instance scenes; parity is vs the oracle.
+    rng = np.random.default_rng(99)
+    blases = [SB.oracle_blas("teapot.obj"), SB.oracle_blas("cube.obj")]
+    objs = []
+    for i in range(150):
+        s = float(rng.uniform(0.3, 1.2))
+        m = O.transform_new_rot_xz([s, s, s], rng.uniform(-7, 7, 3), float(rng.uniform(-3, 3)), float(rng.uniform(-3, 3)))
+        objs.append((i % 2, m))
+    scene = O.Scene(blases, objs)
+    cam = O.camera_symmetric_fov(90.0, 1.0, 1.0, [0, 0, -14], [0, 0, 1], [1, 0, 0], [0, 1, 0])
+    w, h = 512, 288
+    ref = scene.render(cam, w, h, threads=NTHREADS)
+    assert (ref["id"] != O.MISS_ID).mean() > 0.1
+    with Engine(flags=flags) as eng:
+        SB.upload_scene(eng, scene)
+        got = eng.trace_primary(SB.to_ffi_camera(cam), w, h)
+    assert_strict(got, ref)
