@@ -45,7 +45,7 @@ struct Blas {
     DevBuf chunk_leaf, chunk_first, chunk_count, leaf_chunks, parent, scratch, counters;
     uint32_t n_chunks = 0;
     // leaf accelerator
-    DevBuf sub_nodes, sub_raw, sub_order, stri, leaf_sub_root;
+    DevBuf sub_nodes, sub_raw, sub_order, stri, leaf_sub_root, sub_parent, sub_counters;
     uint32_t n_sub = 0, n_sub_nodes = 0;
     // current bake: model-space ray limits and the whole-model tight box inflated for them
     float d_max = 0.0f, o_max = 0.0f;
@@ -139,7 +139,7 @@ int h2d(bvht_ctx* ctx, void* dst, const void* src, size_t bytes) {
 void free_blas(Blas& b) {
     for (DevBuf* d : { &b.tris_aos, &b.nodes, &b.tri, &b.normals, &b.chunk_leaf, &b.chunk_first, &b.chunk_count,
                        &b.leaf_chunks, &b.parent, &b.scratch, &b.counters, &b.sub_nodes, &b.sub_raw, &b.sub_order, &b.stri,
-                       &b.leaf_sub_root })
+                       &b.leaf_sub_root, &b.sub_parent, &b.sub_counters })
         release(*d);
     b = Blas();
 }
@@ -233,6 +233,8 @@ int build_and_upload_accel(bvht_ctx* ctx, Blas& b) {
     if ((rc = h2d(ctx, b.sub_raw.p, acc.sub_raw.data(), acc.sub_raw.size() * 4))) return rc;
     if ((rc = upload_u32(ctx, b.sub_order, acc.order))) return rc;
     if ((rc = upload_u32(ctx, b.leaf_sub_root, acc.leaf_sub_root))) return rc;
+    if ((rc = upload_u32(ctx, b.sub_parent, acc.sub_parent))) return rc;
+    if ((rc = ensure(ctx, b.sub_counters, (size_t)std::max<uint32_t>(b.n_sub_nodes, 1) * 4))) return rc;
     if ((rc = ensure(ctx, b.stri, (size_t)b.n_sub * 48))) return rc;
     CU(ctx, launch_repack_sub_triangles((const float*)b.tris_aos.p, (const uint32_t*)b.sub_order.p, b.n_sub, (float4*)b.stri.p,
                                         ctx->stream));
@@ -243,6 +245,21 @@ int build_and_upload_accel(bvht_ctx* ctx, Blas& b) {
     if ((rc = bake_accel(ctx, b, d_max, o_max))) return rc;
     CU(ctx, cudaStreamSynchronize(ctx->stream));     // host vectors of `acc` die here
     return BVHT_OK;
+}
+
+// Vertex update with the leaf accelerator on: keep the sub-BVH topology, refit it on the device (raw boxes + kappa,
+// bottom-up), recompute the whole-model statistics on the host (one O(n) pass) and re-bake the inflation.
+int refit_accel(bvht_ctx* ctx, Blas& b) {
+    if (b.n_sub_nodes == 0 || !b.sub_parent.p || getenv("BVHT_ACCEL_REBUILD")) return build_and_upload_accel(ctx, b);
+    CU(ctx, launch_repack_sub_triangles((const float*)b.tris_aos.p, (const uint32_t*)b.sub_order.p, b.n_sub, (float4*)b.stri.p,
+                                        ctx->stream));
+    CU(ctx, launch_refit_sub_nodes((float4*)b.sub_raw.p, (const uint32_t*)b.sub_parent.p, (unsigned int*)b.sub_counters.p,
+                                   (const float*)b.tris_aos.p, (const uint32_t*)b.sub_order.p, b.n_sub_nodes, ctx->stream));
+    ctx->stats.kernel_launches += 2;
+    ModelStats ms = compute_model_stats(b.h_tris.data(), b.n_tris);
+    b.radius = ms.radius; b.max_edge = ms.max_edge; b.model_kappa = ms.model_kappa; b.model_valid = ms.model_valid;
+    memcpy(b.model_lo, ms.model_lo, 12); memcpy(b.model_hi, ms.model_hi, 12);
+    return bake_accel(ctx, b, (double)b.d_max, (double)b.o_max);
 }
 
 int upload_vertices(bvht_ctx* ctx, Blas& b, const float* tris) {
@@ -755,8 +772,9 @@ int bvht_blas_update_vertices(bvht_ctx* ctx, uint32_t blas_id, const float* tris
     int rc = upload_vertices(ctx, b, tris);
     if (rc) return rc;
     if (accel_on(ctx)) {
-        if ((rc = build_and_upload_accel(ctx, b))) return rc;
+        if ((rc = refit_accel(ctx, b))) return rc;
         ctx->blas_desc_dirty = true;
+        if (!ctx->h_inst.empty() && (rc = recompute_tlas_tight(ctx))) return rc;     // the model's tight box moved
     }
     cudaEventRecord(ctx->ev_f, ctx->stream);
     CU(ctx, cudaStreamSynchronize(ctx->stream));

@@ -100,6 +100,7 @@ struct Builder {
         out.max_depth = std::max(out.max_depth, depth + 1);
         uint32_t node = (uint32_t)(out.sub_raw.size() / 16);
         out.sub_raw.resize(out.sub_raw.size() + 16, 0.0f);
+        out.sub_parent.push_back(0xFFFFFFFFu);
         uint32_t mid = split(idx, b, e, depth);
         uint32_t refs[2];
         uint32_t rb[2] = { b, mid }, re[2] = { mid, e };
@@ -110,6 +111,7 @@ struct Builder {
                 refs[c] = leaf_ref(base + rb[c], cnt);
             } else {
                 refs[c] = build(idx, rb[c], re[c], base, depth + 1);
+                out.sub_parent[refs[c]] = (node << 1) | (uint32_t)c;
             }
         }
         float rec[16];
@@ -127,6 +129,33 @@ struct Builder {
 };
 
 } // namespace
+
+ModelStats compute_model_stats(const float* tris, uint32_t n_tris) {
+    ModelStats m;
+    double radius = 0.0, max_edge = 0.0, kmax = 0.0;
+    Box mb; mb.reset(); bool any = false;
+    for (uint32_t i = 0; i < n_tris; ++i) {
+        const float* t = tris + (size_t)i * 9;
+        double e1[3], e2[3], e3[3];
+        for (int k = 0; k < 3; ++k) { e1[k] = (double)t[3 + k] - t[k]; e2[k] = (double)t[6 + k] - t[k]; e3[k] = (double)t[6 + k] - t[3 + k]; }
+        double l1 = std::sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+        double l2 = std::sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
+        double l3 = std::sqrt(e3[0] * e3[0] + e3[1] * e3[1] + e3[2] * e3[2]);
+        double kappa = l1 * l2;
+        if (!(kappa > 0.0)) continue;           // degenerate (e.g. the 999 sentinel): area == 0 exactly, never accepted
+        for (int v = 0; v < 3; ++v) {
+            double n = std::sqrt((double)t[3 * v] * t[3 * v] + (double)t[3 * v + 1] * t[3 * v + 1] + (double)t[3 * v + 2] * t[3 * v + 2]);
+            radius = std::max(radius, n);
+        }
+        max_edge = std::max(max_edge, std::max(l1, std::max(l2, l3)));
+        kmax = std::max(kmax, kappa);
+        mb.grow(t); mb.grow(t + 3); mb.grow(t + 6); any = true;
+    }
+    m.radius = radius > 0.0 ? radius : 1.0;
+    m.max_edge = max_edge; m.model_kappa = kmax; m.model_valid = any;
+    if (any) for (int k = 0; k < 3; ++k) { m.model_lo[k] = mb.lo[k]; m.model_hi[k] = mb.hi[k]; }
+    return m;
+}
 
 bool build_leaf_accel(const float* tris, uint32_t n_tris, const void* nodes_v, uint32_t nodes_used,
                       const LeafAccelConfig& cfg, LeafAccelHost& out) {

@@ -27,6 +27,7 @@ struct LeafAccelHost {
     // kappa = max |e1| |e2| over the child's triangles.  The device inflates them for the current ray limits
     // (inflate_sub_nodes kernel), see accel_deltas().
     std::vector<float>    sub_raw;
+    std::vector<uint32_t> sub_parent;     // per sub node: (parent << 1) | child slot, 0xFFFFFFFF for the root of a leaf's tree
     std::vector<uint32_t> order;          // sub position -> reference primitive index
     std::vector<uint32_t> leaf_sub_root;  // per reference node: sub root node index, 0xFFFFFFFF = brute force
     uint32_t max_depth = 0;
@@ -58,6 +59,14 @@ inline void accel_deltas(const LeafAccelConfig& cfg, double d_max, double o_max,
     scale = cfg.c_mt * eps * d_max * s_max / 1e-4;
     abs_ = 16.0 * eps * s_max;
 }
+
+// Whole-model statistics the inflation depends on (recomputed on the host after every vertex update: one O(n) pass).
+struct ModelStats {
+    double radius = 1.0, max_edge = 0.0, model_kappa = 0.0;
+    float  model_lo[3] = { 0, 0, 0 }, model_hi[3] = { 0, 0, 0 };
+    bool   model_valid = false;
+};
+ModelStats compute_model_stats(const float* tris, uint32_t n_tris);
 
 // tris: n_tris x 9 floats in reference order; nodes: reference nodes (bvht_bvh_node layout: min[3], max[3], count, left_first)
 bool build_leaf_accel(const float* tris, uint32_t n_tris, const void* nodes, uint32_t nodes_used,

@@ -73,7 +73,83 @@ inflate_sub_nodes_kernel(const float4* __restrict__ raw, float4* __restrict__ ou
     reinterpret_cast<float*>(out + 4 * (size_t)i + 1)[3] = r1;
 }
 
+// Refit of the sub-BVHs after a vertex update (topology kept, raw boxes and kappa recomputed bottom-up): one thread per
+// sub node computes its LEAF children from the new vertices, then nodes complete when both children have arrived
+// (atomic arrival counters) and the completing thread climbs, writing the node's box into its slot of the parent.
+// Any topology is valid for the conservative search; only its quality degrades with deformation.  HBM/L2-bound:
+// 36 B per triangle + 64 B per node.
+__device__ __forceinline__ void leaf_child_box(const float* __restrict__ tris, const uint32_t* __restrict__ order, uint32_t ref,
+                                               float lo[3], float hi[3], float& kappa) {
+    uint32_t first = ref & 0x0FFFFFFFu, cnt = ((ref >> 28) & 7u) + 1u;
+    lo[0] = lo[1] = lo[2] = 3.402823466e38f; hi[0] = hi[1] = hi[2] = -3.402823466e38f;
+    double kmax = 0.0;
+    for (uint32_t k = 0; k < cnt; ++k) {
+        const float* t = tris + (size_t)__ldg(order + first + k) * 9;
+        float v[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) v[j] = __ldg(t + j);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) { lo[j % 3] = fminf(lo[j % 3], v[j]); hi[j % 3] = fmaxf(hi[j % 3], v[j]); }
+        double e1x = (double)v[3] - v[0], e1y = (double)v[4] - v[1], e1z = (double)v[5] - v[2];
+        double e2x = (double)v[6] - v[0], e2y = (double)v[7] - v[1], e2z = (double)v[8] - v[2];
+        double kp = sqrt(e1x * e1x + e1y * e1y + e1z * e1z) * sqrt(e2x * e2x + e2y * e2y + e2z * e2z);
+        kmax = fmax(kmax, kp);
+    }
+    kappa = __double2float_ru(kmax * (1.0 + 1e-12));
+}
+
+__global__ void __launch_bounds__(kRepackBlock)
+refit_sub_nodes_kernel(float4* __restrict__ raw, const uint32_t* __restrict__ parent, unsigned int* __restrict__ counters,
+                       const float* __restrict__ tris, const uint32_t* __restrict__ order, uint32_t n_nodes) {
+    uint32_t node = blockIdx.x * kRepackBlock + threadIdx.x;
+    if (node >= n_nodes) return;
+    unsigned int arrivals = 0;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint32_t ref = __float_as_uint(__ldcg(reinterpret_cast<const float*>(raw + 4 * (size_t)node + 2 * c + 1) + 3));
+        if (ref & 0x80000000u) {
+            float lo[3], hi[3], kp;
+            leaf_child_box(tris, order, ref, lo, hi, kp);
+            __stcg(raw + 4 * (size_t)node + 2 * c, make_float4(lo[0], lo[1], lo[2], kp));
+            __stcg(raw + 4 * (size_t)node + 2 * c + 1, make_float4(hi[0], hi[1], hi[2], __uint_as_float(ref)));
+            arrivals++;
+        }
+    }
+    if (arrivals == 0) return;                       // both children are inner nodes: whoever completes them climbs through here
+    __threadfence();
+    unsigned int old = atomicAdd(counters + node, arrivals);
+    if (old + arrivals != 2u) return;
+    // this thread completed `node`: climb
+    for (;;) {
+        __threadfence();
+        uint32_t pp = __ldg(parent + node);
+        if (pp == 0xFFFFFFFFu) break;                // root of a leaf's sub tree: its children ARE what the trace kernel tests
+        float4 a = __ldcg(raw + 4 * (size_t)node + 0), b = __ldcg(raw + 4 * (size_t)node + 1);
+        float4 c = __ldcg(raw + 4 * (size_t)node + 2), d = __ldcg(raw + 4 * (size_t)node + 3);
+        uint32_t p = pp >> 1, slot = pp & 1u;
+        float4 plo = make_float4(fminf(a.x, c.x), fminf(a.y, c.y), fminf(a.z, c.z), fmaxf(a.w, c.w));
+        float keep = __ldcg(reinterpret_cast<const float*>(raw + 4 * (size_t)p + 2 * slot + 1) + 3);   // the child reference (= node)
+        float4 phi = make_float4(fmaxf(b.x, d.x), fmaxf(b.y, d.y), fmaxf(b.z, d.z), keep);
+        __stcg(raw + 4 * (size_t)p + 2 * slot, plo);
+        __stcg(raw + 4 * (size_t)p + 2 * slot + 1, phi);
+        __threadfence();
+        unsigned int o = atomicAdd(counters + p, 1u);
+        if (o + 1u != 2u) break;
+        node = p;
+    }
+}
+
 } // namespace
+
+cudaError_t launch_refit_sub_nodes(float4* raw, const uint32_t* parent, unsigned int* counters, const float* tris_aos,
+                                   const uint32_t* order, uint32_t n_nodes, cudaStream_t s) {
+    if (n_nodes == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(counters, 0, (size_t)n_nodes * 4, s);
+    if (e != cudaSuccess) return e;
+    int grid = (int)((n_nodes + kRepackBlock - 1) / kRepackBlock);
+    refit_sub_nodes_kernel<<<grid, kRepackBlock, 0, s>>>(raw, parent, counters, tris_aos, order, n_nodes);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_inflate_sub_nodes(const float4* raw, float4* out, uint32_t n_nodes, float scale, float abs_, cudaStream_t s) {
     if (n_nodes == 0) return cudaSuccess;

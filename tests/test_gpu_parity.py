@@ -575,3 +575,36 @@ def test_many_instances_deep_tlas(flags):
         SB.upload_scene(eng, scene)
         got = eng.trace_primary(SB.to_ffi_camera(cam), w, h)
     assert_strict(got, ref)
+
+
+@pytest.mark.parametrize("flags", STRICT_MODES, ids=MODE_IDS)
+def test_large_deformation_refit_multi_instance(flags):
+    # A shared BLAS deformed far beyond its original bounds (the sub-BVH keeps its topology and is refitted on the
+    # device; tight TLAS boxes and the bake follow), 16 instances, several steps; then back to the original shape.
+    spec = examples.trippy_teapots(4)
+    base = O.load_asset("teapot.obj")
+    blas = O.Blas(base)
+    objs = [(0, SB.object_matrix(o)) for o in spec.objects]
+    scene = O.Scene([blas], objs)
+    cam = SB.oracle_camera(spec.camera)
+    orig = blas.tris.copy()
+    w, h = 480, 272
+    with Engine(flags=flags) as eng:
+        ids = SB.upload_scene(eng, scene)
+        for step, (sx, sy, shear, off) in enumerate([(1.6, 0.7, 0.5, 0.4), (0.5, 2.2, -0.8, -0.6), (1.0, 1.0, 0.0, 0.0)]):
+            v = orig.reshape(-1, 3, 3).copy()
+            v[:, :, 0] = orig.reshape(-1, 3, 3)[:, :, 0] * F(sx) + orig.reshape(-1, 3, 3)[:, :, 1] * F(shear)
+            v[:, :, 1] = orig.reshape(-1, 3, 3)[:, :, 1] * F(sy) + F(off)
+            blas.tris[:] = v.reshape(-1, 9)
+            blas.refit()
+            scene.rebuild()                                   # instance world bounds + TLAS from the refitted model bounds
+            eng.blas_update_vertices(ids[0], blas.tris)
+            eng.blas_refit(ids[0])
+            nodes = eng.blas_read_nodes(ids[0], blas.nodes_used)
+            assert np.array_equal(nodes["aabb_min"], blas.nodes["min"][:blas.nodes_used])
+            assert np.array_equal(nodes["aabb_max"], blas.nodes["max"][:blas.nodes_used])
+            SB.upload_scene(eng, scene, blas_ids=ids)
+            ref = scene.render(cam, w, h, threads=NTHREADS)
+            got = eng.trace_primary(SB.to_ffi_camera(cam), w, h)
+            assert (ref["id"] != O.MISS_ID).mean() > 0.03
+            assert_strict(got, ref)
