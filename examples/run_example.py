@@ -5,8 +5,7 @@ through the B200 backend and save the frame, as the reference's App would displa
     python examples/run_example.py sixteen_armadillos --frames 30 --size 640 640 --out frame.png
 
 Each example keeps its own scene, camera, accumulator and pixel shader (examples/*.rs `main`); only the integrator is
-`CudaPathTracer` instead of `PathTracer`.  The frame is flipped vertically for display like bvhtracer_demos does
-(bvhtracer_demos/src/lib.rs:114).
+`CudaPathTracer` instead of `PathTracer`.
 """
 import argparse
 import os
@@ -59,7 +58,9 @@ def main():
             models[0].refit()
         rays += renderer.render(state, scene)
     dt = time.perf_counter() - t0
-    frame = state.frame_buffer().reshape(h, w).copy()[::-1]              # flip_vertical for display
+    # row 0 is the TOP of the image (v = 0, renderer.rs:358-361); bvhtracer_demos flips it only because GL textures start at
+    # the bottom (lib.rs:114) -- an image file wants it as is
+    frame = state.frame_buffer().reshape(h, w).copy()
     print(f"{args.name}: {args.frames + 1} frames of {w}x{h}, {rays} rays in {dt * 1e3:.1f} ms "
           f"({rays / dt / 1e6:.0f} Mrays/s incl. host updates), last trace {renderer.stats()['last_trace_ms']:.3f} ms")
     if args.out:
