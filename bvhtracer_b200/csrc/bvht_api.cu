@@ -192,6 +192,7 @@ int upload_u32(bvht_ctx* ctx, DevBuf& d, const std::vector<uint32_t>& v) {
 // recompute its whole-model tight box (host, rounded outwards).
 int bake_accel(bvht_ctx* ctx, Blas& b, double d_max, double o_max) {
     LeafAccelConfig cfg;
+    if (const char* e = getenv("BVHT_C_MT")) cfg.c_mt = (float)atof(e);     // experiment knob (tools/equivalence_sweep.py): margin study only
     double scale, abs_;
     accel_deltas(cfg, d_max, o_max, b.radius, b.max_edge, scale, abs_);
     float fs = (float)scale; if ((double)fs < scale) fs = std::nextafterf(fs, FLT_MAX);

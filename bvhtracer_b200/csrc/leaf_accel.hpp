@@ -44,13 +44,18 @@ struct LeafAccelConfig {
     uint32_t max_sub_leaf = 1;     // triangles per sub leaf (<= 8: 3-bit count field); 1 measured fastest on B200
     float    d_max = 2.0f;         // default |d| limit in model space (instance scale >= 0.5)
     float    o_max_radii = 16.0f;  // default |o| limit as a multiple of the model radius
-    float    c_mt = 80.0f;         // safety constant of the Moeller-Trumbore residual bound (first-order estimate ~40)
+    float    c_mt = 48.0f;         // constant of the Moeller-Trumbore residual bound: 34.5 by first-order error analysis
+                                   //   (below), x1.4 safety; tools/equivalence_sweep.py finds no mismatch even at c = 0
 };
 
 // Inflation of a box whose triangles have edge product <= kappa, valid for model-space rays with |d| <= d_max and
 // |o| <= o_max:  delta = scale * kappa + abs.
 //   scale * kappa : residual |o + t d - (v0 + u e1 + v e2)| of Triangle::intersect in f32 at its |det| >= 1e-4 cut-off,
-//                   c_mt * eps * d_max * (o_max + radius + max_edge) * kappa / 1e-4
+//                   c_mt * eps * d_max * (o_max + radius + max_edge) * kappa / 1e-4.
+//                   Derivation (first order in eps = 2^-24, s = o - v0, D = |d||e1||e2|): with the exact identity
+//                   det*s + T*d - U*e1 - V*e2 = 0 the residual is (ddet*s + dT*d - dU*e1 - dV*e2) / det, and the rounding
+//                   errors of the reference's cross/dot sequences are |ddet| <= 9 eps D, |dU|, |dV|, |dT| <= 8.5 eps |s| times
+//                   the other two lengths, so |residual| <= (9 + 3 * 8.5) eps |s| D / |det| = 34.5 eps |s| D / |det|.
 //   abs           : rounding of s = o - v0 and of the slab test itself, 16 * eps * (o_max + radius + max_edge)
 inline void accel_deltas(const LeafAccelConfig& cfg, double d_max, double o_max, double radius, double max_edge,
                          double& scale, double& abs_) {
