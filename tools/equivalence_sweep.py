@@ -95,5 +95,5 @@ with Engine(flags=FLAG_STRICT) as brute, Engine(flags=FLAG_STRICT | FLAG_LEAF_AC
             eng.blas_refit(bid)
         compare(f"big_ben frame {f}", brute, accel, scene.camera(), 3840, 2160)
     print(f"big_ben animated done, rays so far {total:,}, mismatches {mism}", flush=True)
-print(f"TOTAL rays {total:,}  mismatching records {mism}  c_mt={os.environ.get('BVHT_C_MT', '80 (shipped)')}  "
+print(f"TOTAL rays {total:,}  mismatching records {mism}  c_mt={os.environ.get('BVHT_C_MT', 'shipped value (leaf_accel.hpp)')}  "
       f"wall {time.time() - t_start:.0f} s")
