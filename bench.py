@@ -324,18 +324,24 @@ def run_ours(args, rank, local_rank, world):
         e2e["with_hit_records"] = {"value": npix / (float(np.mean(hm)) * 1e-3) / 1e6, "unit": "Mrays/s", "d2h_bytes_per_step": npix * 20}
         del state_h
     else:
-        # every rank renders its tile rows (shaded frame) into rank 0's device frame buffer; rank 0 copies it to the host
+        # every rank renders its tile rows (shaded frame) and copies them, over ITS OWN PCIe link, into one page-locked
+        # host frame buffer in POSIX shared memory; the frame is complete on the host after the closing barrier
+        from multiprocessing import shared_memory
+        name = [None]
         if rank == 0:
-            d_frame = eng.device_alloc(npix * 4)
-            fh = eng.ipc_export(d_frame)
-            host_frame = eng.pinned_array(npix, "<u4")
-        hb2 = torch.zeros(64, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            hb2.copy_(torch.frombuffer(bytearray(fh), dtype=torch.uint8))
-        dist.broadcast(hb2, 0)
+            shm = shared_memory.SharedMemory(create=True, size=npix * 4)
+            name = [shm.name]
+        dist.broadcast_object_list(name, 0)
         if rank != 0:
-            d_frame = eng.ipc_open(bytes(hb2.cpu().numpy().tobytes()))
-        h2d0 = renderer.stats()["h2d_bytes"]
+            shm = shared_memory.SharedMemory(name=name[0])
+        host_frame = np.ndarray(npix, dtype="<u4", buffer=shm.buf)
+        eng.host_register(host_frame)
+        h2d0, d2h0 = renderer.stats()["h2d_bytes"], renderer.stats()["d2h_bytes"]
+        for _ in range(2):
+            advance_frame()
+            renderer.sync_scene(scene)
+            eng.render_frame(cam, width, height, shade, tile, None, frame_out=host_frame)
+        h2d0, d2h0 = renderer.stats()["h2d_bytes"], renderer.stats()["d2h_bytes"]
         barrier()
         e2e_s = 0.0
         for _ in range(args.steps):
@@ -343,19 +349,18 @@ def run_ours(args, rank, local_rank, world):
             barrier()
             t0 = time.perf_counter()
             renderer.sync_scene(scene)                   # per-frame H2D (TLAS + instances)
-            eng.render_frame_device(cam, width, height, shade, tile, None, d_frame, None)
-            barrier()                                    # all shards landed in rank 0's HBM
-            if rank == 0:
-                eng.memcpy_d2h(host_frame, d_frame)
+            eng.render_frame(cam, width, height, shade, tile, None, frame_out=host_frame)   # trace + shade + D2H of the owned rows
+            barrier()                                    # every rank's rows are in the shared host frame
             e2e_s += time.perf_counter() - t0
         barrier()
         e2e_wall = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(e2e_wall, op=dist.ReduceOp.MAX)
+        st_ = renderer.stats()
         e2e = {"value": npix * args.steps / float(e2e_wall.item()) / 1e6, "unit": "Mrays/s",
-               "h2d_bytes_per_step": (renderer.stats()["h2d_bytes"] - h2d0) // args.steps, "d2h_bytes_per_step": npix * 4,
+               "h2d_bytes_per_step": (st_["h2d_bytes"] - h2d0) // args.steps, "d2h_bytes_per_step": (st_["d2h_bytes"] - d2h0) // args.steps * world,
                "ms_per_step": float(e2e_wall.item()) / args.steps * 1e3,
-               "call": "per rank: bvht_tlas_set + bvht_render_frame_device (tile-row shard) into rank 0's frame buffer over NVLink P2P; "
-                       "rank 0: barrier + D2H of the whole Rgba<u8> frame over its one PCIe link (host wall clock between barriers, max over ranks)"}
+               "call": "per rank: bvht_tlas_set + bvht_render_frame (tile-row shard; trace + shade + D2H of the owned rows over the rank's own "
+                       "PCIe link into ONE page-locked frame buffer in POSIX shared memory); host wall clock between barriers, max over ranks"}
         frame_checksum = int(np.bitwise_xor.reduce(host_frame)) if rank == 0 else 0
         # the assembled frame must equal the same frame rendered by rank 0 alone (outside every timed region)
         sharded_ok = None
@@ -433,9 +438,16 @@ def run_ours(args, rank, local_rank, world):
         print(json.dumps(line), flush=True)
     if world > 1:
         barrier()
+        eng.host_unregister(host_frame)
+        del host_frame
+        try:
+            shm.close()
+            if rank == 0:
+                shm.unlink()
+        except Exception:
+            pass
         if rank != 0:
             eng.ipc_close(d_hits)
-            eng.ipc_close(d_frame)
         barrier()
         dist.destroy_process_group()
 

@@ -83,6 +83,8 @@ SYMBOLS = [
     ("bvht_device_free", C.c_int, [_P, _P]),
     ("bvht_host_alloc", C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     ("bvht_host_free", C.c_int, [_P, _P]),
+    ("bvht_host_register", C.c_int, [_P, _P, C.c_size_t]),
+    ("bvht_host_unregister", C.c_int, [_P, _P]),
     ("bvht_memcpy_h2d", C.c_int, [_P, _P, _P, C.c_size_t]),
     ("bvht_memcpy_d2h", C.c_int, [_P, _P, _P, C.c_size_t]),
     ("bvht_ipc_export", C.c_int, [_P, _P, _P]),

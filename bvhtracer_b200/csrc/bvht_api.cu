@@ -1069,17 +1069,46 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
         bvht_rect band = { region.x0, std::max(region.y0, r0 * tile), region.x1, std::min(region.y1, r1 * tile) };
         if (band.y0 >= band.y1) continue;
         cudaStream_t cs = ctx->aux[b & 1];
-        if ((rc = launch_primary_region(ctx, scene, camera, width, height, tile, band, shade, d_hits, d_rgba, cs, (int)b))) return rc;
+        if ((rc = launch_primary_region(ctx, scene, camera, width, height, tile, band, shade, d_hits, d_rgba, cs, (int)b,
+                                        ctx->shard_index, ctx->shard_count))) return rc;
         CU(ctx, cudaEventRecord(ctx->ev_band[b], cs));
         CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[b], 0));
-        if (frame_out_host && (rc = copy_rows_d2h(ctx, frame_out_host, d_rgba, width, band, 4, ctx->copy_stream))) return rc;
-        if (hits_out_host && (rc = copy_rows_d2h(ctx, hits_out_host, d_hits, width, band, sizeof(bvht_hit), ctx->copy_stream))) return rc;
+        if (ctx->shard_count == 1) {
+            if (frame_out_host && (rc = copy_rows_d2h(ctx, frame_out_host, d_rgba, width, band, 4, ctx->copy_stream))) return rc;
+            if (hits_out_host && (rc = copy_rows_d2h(ctx, hits_out_host, d_hits, width, band, sizeof(bvht_hit), ctx->copy_stream))) return rc;
+        } else {
+            // sharded: only this rank's tile rows travel, and only they are written on the host (another rank fills the
+            // others, e.g. through a shared pinned mapping).  Owned rows are `tile` image rows every shard_count * tile rows:
+            // one strided 2-D copy per band (full-width regions), or one copy per owned tile row otherwise.
+            uint32_t first = 0, n_rows = 0;
+            bvht_shard_tile_rows(band, tile, ctx->shard_index, ctx->shard_count, &first, &n_rows);
+            for (int which = 0; which < 2; ++which) {
+                void* host = which == 0 ? (void*)frame_out_host : (void*)hits_out_host;
+                const void* dev = which == 0 ? d_rgba : d_hits;
+                size_t elem = which == 0 ? 4 : sizeof(bvht_hit);
+                if (!host || n_rows == 0) continue;
+                bool aligned = band.x0 == 0 && band.x1 == width && band.y0 % tile == 0 && (band.y1 % tile == 0 || band.y1 == height);
+                uint32_t last_row_end = std::min(height, (first + (n_rows - 1) * ctx->shard_count + 1) * tile);
+                if (aligned && last_row_end == (first + (n_rows - 1) * ctx->shard_count + 1) * tile) {
+                    size_t chunk = (size_t)tile * width * elem, pitch = chunk * ctx->shard_count, off = (size_t)first * tile * width * elem;
+                    CU(ctx, cudaMemcpy2DAsync((char*)host + off, pitch, (const char*)dev + off, pitch, chunk, n_rows, cudaMemcpyDeviceToHost,
+                                              ctx->copy_stream));
+                    ctx->stats.d2h_bytes += chunk * n_rows;
+                } else {
+                    for (uint32_t k = 0; k < n_rows; ++k) {
+                        uint32_t tr = first + k * ctx->shard_count;
+                        bvht_rect rr = { band.x0, std::max(band.y0, tr * tile), band.x1, std::min(band.y1, (tr + 1) * tile) };
+                        if (rr.y0 < rr.y1 && (rc = copy_rows_d2h(ctx, host, dev, width, rr, elem, ctx->copy_stream))) return rc;
+                    }
+                }
+            }
+        }
     }
     CU(ctx, cudaEventRecord(ctx->ev_join, ctx->copy_stream));
     CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     cudaEventRecord(ctx->ev_b, ctx->stream);
     ctx->trace_timed = true;
-    ctx->stats.last_trace_rays = rays;
+    ctx->stats.last_trace_rays = rays / ctx->shard_count;
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return BVHT_OK;
 }
@@ -1162,6 +1191,21 @@ int bvht_host_free(bvht_ctx* ctx, void* host_ptr) {
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     cudaError_t e = cudaFreeHost(host_ptr);
     if (e != cudaSuccess) { cudaGetLastError(); return ctx ? fail(ctx, BVHT_ERR_CUDA, "cudaFreeHost: %s", cudaGetErrorString(e)) : BVHT_ERR_CUDA; }
+    return BVHT_OK;
+}
+
+int bvht_host_register(bvht_ctx* ctx, void* host_ptr, size_t bytes) {
+    if (!host_ptr || bytes == 0) return ctx ? fail(ctx, BVHT_ERR_INVALID_ARG, "null/empty host range") : BVHT_ERR_INVALID_ARG;
+    if (ctx) cudaSetDevice(ctx->device);
+    cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return ctx ? fail(ctx, BVHT_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e)) : BVHT_ERR_CUDA; }
+    return BVHT_OK;
+}
+
+int bvht_host_unregister(bvht_ctx* ctx, void* host_ptr) {
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    cudaError_t e = cudaHostUnregister(host_ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return ctx ? fail(ctx, BVHT_ERR_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(e)) : BVHT_ERR_CUDA; }
     return BVHT_OK;
 }
 

@@ -210,6 +210,13 @@ class Engine:
         p = self._pinned.pop(arr.ctypes.data)
         self._check(self._lib.bvht_host_free(self._ctx, C.c_void_p(p)))
 
+    def host_register(self, arr):
+        """Page-lock an existing numpy buffer (e.g. over multiprocessing.shared_memory)."""
+        self._check(self._lib.bvht_host_register(self._ctx, ptr(arr), arr.nbytes))
+
+    def host_unregister(self, arr):
+        self._check(self._lib.bvht_host_unregister(self._ctx, ptr(arr)))
+
     def memcpy_h2d(self, dptr, host_array):
         host_array = np.ascontiguousarray(host_array)
         self._check(self._lib.bvht_memcpy_h2d(self._ctx, C.c_void_p(dptr), ptr(host_array), host_array.nbytes))

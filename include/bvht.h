@@ -213,9 +213,11 @@ BVHT_API int         bvht_render_frame_device(bvht_ctx* ctx, const bvht_camera* 
                                       void* frame_out_device, void* hits_out_device);
 
 /* Multi-GPU sharding (scene replicated per GPU, image tiles sharded): after bvht_set_shard(ctx, i, n) the
- * *_device entry points above only trace the tile rows r with r % n == i (interleaved for load balance) and
+ * trace / render entry points only trace the tile rows r with r % n == i (interleaved for load balance) and
  * leave every other pixel untouched, so n contexts on n GPUs writing into ONE frame buffer (rank 0's, mapped
- * on the peers with bvht_ipc_open) assemble the frame over NVLink with no copy.  (0, 1) restores the default. */
+ * on the peers with bvht_ipc_open) assemble the frame over NVLink with no copy; the host-output calls copy
+ * back (and write) only the owned rows, so n ranks can likewise fill ONE shared pinned host frame buffer,
+ * each over its own PCIe link.  (0, 1) restores the default. */
 BVHT_API int         bvht_set_shard(bvht_ctx* ctx, uint32_t shard_index, uint32_t shard_count);
 /* Pure host helper (no device needed): which tile rows of `region` shard i of n owns -- rows
  * first_row, first_row + n, ... (n_rows of them).  The same function the launches use. */
@@ -232,6 +234,9 @@ BVHT_API int         bvht_device_free(bvht_ctx* ctx, void* device_ptr);
 /* Page-locked host memory (so that copies overlap with kernels).  ctx may be NULL for both calls. */
 BVHT_API int         bvht_host_alloc(bvht_ctx* ctx, size_t bytes, void** out_host);
 BVHT_API int         bvht_host_free(bvht_ctx* ctx, void* host_ptr);
+/* Page-lock an existing host range (e.g. a POSIX shared-memory frame buffer that several ranks fill). */
+BVHT_API int         bvht_host_register(bvht_ctx* ctx, void* host_ptr, size_t bytes);
+BVHT_API int         bvht_host_unregister(bvht_ctx* ctx, void* host_ptr);
 BVHT_API int         bvht_memcpy_h2d(bvht_ctx* ctx, void* dst_device, const void* src_host, size_t bytes);
 BVHT_API int         bvht_memcpy_d2h(bvht_ctx* ctx, void* dst_host, const void* src_device, size_t bytes);
 /* CUDA IPC: export a device allocation so another process (one rank per GPU) can map it over NVLink P2P */

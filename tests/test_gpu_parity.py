@@ -608,3 +608,32 @@ def test_large_deformation_refit_multi_instance(flags):
             got = eng.trace_primary(SB.to_ffi_camera(cam), w, h)
             assert (ref["id"] != O.MISS_ID).mean() > 0.03
             assert_strict(got, ref)
+
+
+def test_sharded_host_renders_fill_one_shared_frame():
+    # multi-GPU e2e contract on one device: n contexts, shard i of n each, every one copying ONLY its tile rows into the
+    # same page-locked host frame (ragged height: the last tile row is partial)
+    scene, cam = SB.oracle_scene(examples.sixteen_armadillos(8))
+    w, h, n = 448, 250, 3
+    with Engine(flags=FLAG_LEAF_ACCEL) as e0:
+        SB.upload_scene(e0, scene)
+        shade = e0.shade_depth()
+        full_frame, full_hits = e0.render_frame(SB.to_ffi_camera(cam), w, h, shade, want_hits=True)
+        frame = e0.pinned_array(w * h, "<u4"); frame[:] = 0xDEADBEEF
+        hits = np.zeros(w * h, _ffi.HIT)
+        for i in range(n):
+            with Engine(flags=FLAG_LEAF_ACCEL) as ei:
+                SB.upload_scene(ei, scene)
+                ei.set_shard(i, n)
+                ei.render_frame(SB.to_ffi_camera(cam), w, h, shade, frame_out=frame, hits_out=hits)
+                if i == 0:
+                    rows = _ffi.shard_tile_rows((0, 0, w, h), 8, 0, n)
+                    own = np.zeros(h, bool)
+                    for r in rows:
+                        own[r * 8:(r + 1) * 8] = True
+                    f2 = frame.reshape(h, w)
+                    assert np.array_equal(f2[own], full_frame.reshape(h, w)[own])
+                    assert (f2[~own] == 0xDEADBEEF).all()              # rows of other shards are not touched
+        assert frame.tobytes() == full_frame.tobytes()
+        assert hits.tobytes() == full_hits.tobytes()
+        e0.free_pinned(frame)
