@@ -334,6 +334,11 @@ def run_ours(args, rank, local_rank, world):
         dist.broadcast_object_list(name, 0)
         if rank != 0:
             shm = shared_memory.SharedMemory(name=name[0])
+            try:                                         # attaching ranks must not let their resource tracker unlink the segment
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(shm._name, "shared_memory")
+            except Exception:
+                pass
         host_frame = np.ndarray(npix, dtype="<u4", buffer=shm.buf)
         eng.host_register(host_frame)
         h2d0, d2h0 = renderer.stats()["h2d_bytes"], renderer.stats()["d2h_bytes"]
@@ -435,7 +440,6 @@ def run_ours(args, rank, local_rank, world):
             "frame_checksum": frame_checksum, "wall_s_resident_loop": wall_resident,
             "sharded_frame_equals_single_gpu": (sharded_ok if world > 1 else None),
         }
-        print(json.dumps(line), flush=True)
     if world > 1:
         barrier()
         eng.host_unregister(host_frame)
@@ -450,6 +454,9 @@ def run_ours(args, rank, local_rank, world):
             eng.ipc_close(d_hits)
         barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        sys.stderr.flush()
+        print(json.dumps(line), flush=True)              # the ONE JSON line, last thing on stdout
 
 
 def main():
