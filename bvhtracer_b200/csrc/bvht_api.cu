@@ -831,7 +831,9 @@ int bvht_blas_read_nodes(bvht_ctx* ctx, uint32_t blas_id, bvht_bvh_node* out, ui
 int bvht_tlas_set(bvht_ctx* ctx, const bvht_tlas_node* nodes, uint32_t nodes_used, const bvht_instance* instances,
                   uint32_t n_instances) {
     if (!ctx) return BVHT_ERR_BAD_HANDLE;
-    if (!nodes || nodes_used == 0 || (n_instances && !instances)) return fail(ctx, BVHT_ERR_INVALID_ARG, "null/empty TLAS");
+    if (!nodes || nodes_used == 0 || !instances) return fail(ctx, BVHT_ERR_INVALID_ARG, "null/empty TLAS");
+    if (n_instances == 0)
+        return fail(ctx, BVHT_ERR_INVALID_ARG, "scene without objects (the reference's Tlas::intersect indexes blas[0] and panics, tlas.rs:130)");
     if (n_instances > 0xFFFu + 1u) return fail(ctx, BVHT_ERR_INVALID_ARG, "more than 4096 instances (12-bit instance index)");
     cudaSetDevice(ctx->device);
     // validate: indices in range, bounded depth, no cycles (node 0 is a COPY of the last merged node, tlas.rs:248)
@@ -847,7 +849,6 @@ int bvht_tlas_set(bvht_ctx* ctx, const bvht_tlas_node* nodes, uint32_t nodes_use
                 return fail(ctx, BVHT_ERR_MALFORMED_BVH, "TLAS depth exceeds the traversal stack bound %d", kTlasStack);
             const bvht_tlas_node& n = nodes[ni];
             if (n.left_right == 0) {
-                if (n_instances == 0) continue;                       // empty scene: the root leaf is never resolved
                 if (n.blas >= n_instances)
                     return fail(ctx, BVHT_ERR_MALFORMED_BVH, "TLAS leaf %u refers to instance %u of %u", ni, n.blas, n_instances);
             } else {

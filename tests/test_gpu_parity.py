@@ -307,6 +307,14 @@ def test_errors_are_codes_not_crashes():
         assert e.value.status == _ffi.ERR_BAD_HANDLE
         with pytest.raises(BvhtError):
             eng.blas_update_vertices(ids[0], np.zeros((5, 9), F))  # wrong triangle count
+        with pytest.raises(BvhtError) as e:                       # scene without objects
+            eng.tlas_set(scene.tlas.view(_ffi.TLAS_NODE), scene.tlas_used, np.zeros(0, _ffi.INSTANCE))
+        assert e.value.status == _ffi.ERR_INVALID_ARG
+        cyc = scene.tlas[:scene.tlas_used].copy().view(_ffi.TLAS_NODE)
+        cyc["left_right"][0] = (0 << 16) | 0 | 1                  # node 0 -> children (0, 1): a cycle through the root
+        with pytest.raises(BvhtError) as e:
+            eng.tlas_set(cyc, scene.tlas_used, np.zeros(1, _ffi.INSTANCE))
+        assert e.value.status == _ffi.ERR_MALFORMED_BVH
         # the context is still usable after every error
         got = eng.trace_primary(SB.to_ffi_camera(cam), 64, 64)
         assert got.tobytes() == scene.render(cam, 64, 64).tobytes()
