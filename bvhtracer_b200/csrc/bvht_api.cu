@@ -53,6 +53,8 @@ struct Blas {
     bool tight_valid = false;
     // what the bake is computed from
     double radius = 1.0, max_edge = 0.0, model_kappa = 0.0;
+    double useful_product = 1e300;                // cap on d_max * (o_max + radius + max_edge): beyond it the inflated sub boxes
+                                                  //   are many triangle-edges wide and the brute-force leaf is faster
     float model_lo[3] = { 0, 0, 0 }, model_hi[3] = { 0, 0, 0 };
     bool model_valid = false;
 };
@@ -216,6 +218,16 @@ int bake_accel(bvht_ctx* ctx, Blas& b, double d_max, double o_max) {
     return BVHT_OK;
 }
 
+// The inflation of a typical sub box is scale * mean_kappa (leaf_accel.hpp accel_deltas).  Measured on B200 (tools/rays_bench.py):
+// at ~3.5 mean edges of inflation the accelerated leaf is still 2x faster than brute force, at ~100 it is 3x slower; cap at 6.
+void set_useful_product(Blas& b, const ModelStats& ms, const LeafAccelConfig& cfg) {
+    const double eps = 5.9604644775390625e-08;
+    if (ms.mean_kappa > 0.0 && ms.mean_edge > 0.0 && cfg.c_mt > 0.0f)
+        b.useful_product = 6.0 * ms.mean_edge * 1e-4 / ((double)cfg.c_mt * eps * ms.mean_kappa);
+    else
+        b.useful_product = 1e300;
+}
+
 int build_and_upload_accel(bvht_ctx* ctx, Blas& b) {
     LeafAccelConfig cfg;
     if (const char* e = getenv("BVHT_SUB_LEAF")) { int v = atoi(e); if (v >= 1 && v <= 8) cfg.max_sub_leaf = (uint32_t)v; }   // tuning knob
@@ -228,6 +240,7 @@ int build_and_upload_accel(bvht_ctx* ctx, Blas& b) {
     b.n_sub_nodes = (uint32_t)(acc.sub_raw.size() / 16);
     b.radius = acc.radius; b.max_edge = acc.max_edge; b.model_kappa = acc.model_kappa; b.model_valid = acc.model_valid;
     memcpy(b.model_lo, acc.model_lo, 12); memcpy(b.model_hi, acc.model_hi, 12);
+    set_useful_product(b, compute_model_stats(b.h_tris.data(), b.n_tris), cfg);
     int rc;
     if ((rc = ensure(ctx, b.sub_raw, acc.sub_raw.size() * 4))) return rc;
     if ((rc = ensure(ctx, b.sub_nodes, acc.sub_raw.size() * 4))) return rc;
@@ -260,6 +273,7 @@ int refit_accel(bvht_ctx* ctx, Blas& b) {
     ModelStats ms = compute_model_stats(b.h_tris.data(), b.n_tris);
     b.radius = ms.radius; b.max_edge = ms.max_edge; b.model_kappa = ms.model_kappa; b.model_valid = ms.model_valid;
     memcpy(b.model_lo, ms.model_lo, 12); memcpy(b.model_hi, ms.model_hi, 12);
+    set_useful_product(b, ms, LeafAccelConfig());
     return bake_accel(ctx, b, (double)b.d_max, (double)b.o_max);
 }
 
@@ -497,21 +511,19 @@ double sigma_max_3x3(const double* m) {
 // cover are therefore known before the launch.  Re-bake (a 64 B/node streaming kernel + a few host boxes) when the
 // current bake does not cover them or is more than 2.5x looser than needed; the tighter the limits, the smaller
 // the conservative inflation of every sub box (leaf_accel.hpp accel_deltas).
-int ensure_bake(bvht_ctx* ctx, const bvht_camera* cam) {
-    if (!accel_on(ctx) || ctx->h_inst.empty()) return BVHT_OK;
-    double vinv[16];
-    for (int i = 0; i < 16; ++i) { vinv[i] = cam->view_matrix_inv[i]; if (!std::isfinite(vinv[i])) return BVHT_OK; }
-    double dw = sigma_max_3x3(vinv) * (1.0 + 1e-4);            // eye directions are normalised (camera.rs:999)
-    const double ow[3] = { vinv[12], vinv[13], vinv[14] };     // world origin = view_inv * (0,0,0,1)
-    std::vector<double> need_d(ctx->blas.size(), 0.0), need_o(ctx->blas.size(), 0.0);
+// Core: rays start within `rho` of `center` (world space) and have |d_w| <= dw.
+int ensure_bake_for(bvht_ctx* ctx, const double center[3], double rho, double dw) {
+    std::vector<double> need_d(ctx->blas.size(), 0.0), need_o(ctx->blas.size(), 0.0), need_sg(ctx->blas.size(), 0.0);
     for (const bvht_instance& in : ctx->h_inst) {
         double inv[16]; bool finite = true;
         for (int i = 0; i < 16; ++i) { inv[i] = in.transform_inv[i]; finite = finite && std::isfinite(inv[i]); }
         if (!finite) continue;
+        need_sg[in.blas_id] = std::max(need_sg[in.blas_id], sigma_max_3x3(inv) * (1.0 + 1e-4));
         double o[3];
-        for (int r = 0; r < 3; ++r) o[r] = inv[0 + r] * ow[0] + inv[4 + r] * ow[1] + inv[8 + r] * ow[2] + inv[12 + r];
-        double on = std::sqrt(o[0] * o[0] + o[1] * o[1] + o[2] * o[2]) * (1.0 + 1e-4) + 1e-6;
-        double dn = sigma_max_3x3(inv) * dw;
+        for (int r = 0; r < 3; ++r) o[r] = inv[0 + r] * center[0] + inv[4 + r] * center[1] + inv[8 + r] * center[2] + inv[12 + r];
+        double sg = sigma_max_3x3(inv);
+        double on = (std::sqrt(o[0] * o[0] + o[1] * o[1] + o[2] * o[2]) + sg * rho) * (1.0 + 1e-4) + 1e-6;
+        double dn = sg * dw;
         need_d[in.blas_id] = std::max(need_d[in.blas_id], dn);
         need_o[in.blas_id] = std::max(need_o[in.blas_id], on);
     }
@@ -519,6 +531,18 @@ int ensure_bake(bvht_ctx* ctx, const bvht_camera* cam) {
     for (size_t i = 0; i < ctx->blas.size(); ++i) {
         Blas& b = ctx->blas[i];
         if (!b.alive || b.n_sub_nodes == 0 || !(need_d[i] > 0.0)) continue;
+        if (!(need_d[i] < 1e15) || !(need_o[i] < 1e15)) continue;   // absurd limits: keep the bake, those rays take brute-force leaves
+        // Usefulness cap: cover the origins first and as much of the direction range as stays useful, but never less than
+        // unit world directions (need_sg); rays outside the baked limits take the brute-force leaf, which is always exact.
+        {
+            double s_need = need_o[i] * 1.25 + b.radius + b.max_edge;
+            if (need_d[i] * 1.05 * s_need > b.useful_product) {
+                double d_lim = std::max(b.useful_product / s_need / 1.05, std::min(need_d[i], need_sg[i]));
+                need_d[i] = std::min(need_d[i], d_lim);
+                if (need_d[i] * 1.05 * s_need > b.useful_product)
+                    need_o[i] = std::max((b.useful_product / (need_d[i] * 1.05) - b.radius - b.max_edge) / 1.25, 0.0);
+            }
+        }
         bool too_small = need_d[i] > 0.98 * (double)b.d_max || need_o[i] > 0.98 * (double)b.o_max;
         // the inflation is proportional to d_max * (o_max + radius + max_edge)
         double cur = (double)b.d_max * ((double)b.o_max + b.radius + b.max_edge);
@@ -529,12 +553,36 @@ int ensure_bake(bvht_ctx* ctx, const bvht_camera* cam) {
             changed = true;
         }
     }
-    if (ow[0] != ctx->bake_center[0] || ow[1] != ctx->bake_center[1] || ow[2] != ctx->bake_center[2]) {
-        ctx->bake_center[0] = ow[0]; ctx->bake_center[1] = ow[1]; ctx->bake_center[2] = ow[2];
+    if (center[0] != ctx->bake_center[0] || center[1] != ctx->bake_center[1] || center[2] != ctx->bake_center[2]) {
+        ctx->bake_center[0] = center[0]; ctx->bake_center[1] = center[1]; ctx->bake_center[2] = center[2];
         changed = true;
     }
     if (changed) return recompute_tlas_tight(ctx);
     return BVHT_OK;
+}
+
+int ensure_bake(bvht_ctx* ctx, const bvht_camera* cam) {
+    if (!accel_on(ctx) || ctx->h_inst.empty()) return BVHT_OK;
+    double vinv[16];
+    for (int i = 0; i < 16; ++i) { vinv[i] = cam->view_matrix_inv[i]; if (!std::isfinite(vinv[i])) return BVHT_OK; }
+    double dw = sigma_max_3x3(vinv) * (1.0 + 1e-4);            // eye directions are normalised (camera.rs:999)
+    const double ow[3] = { vinv[12], vinv[13], vinv[14] };     // world origin = view_inv * (0,0,0,1): shared by all primary rays
+    return ensure_bake_for(ctx, ow, 0.0, dw);
+}
+
+// Arbitrary ray batch: one small reduction kernel gives max |o_w| and max |d_w|; bake for a ball around the world origin.
+int ensure_bake_rays(bvht_ctx* ctx, const void* rays_device, uint64_t n) {
+    if (!accel_on(ctx) || ctx->h_inst.empty() || n == 0) return BVHT_OK;
+    unsigned int* scratch = (unsigned int*)ctx->work_counter.p + 64;      // two words after the 64 band counters
+    CU(ctx, launch_ray_bounds((const float*)rays_device, n, scratch, ctx->stream));
+    ctx->stats.kernel_launches += 1;
+    float m[2] = { 0.0f, 0.0f };
+    CU(ctx, cudaMemcpyAsync(m, scratch, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    const double zero[3] = { 0.0, 0.0, 0.0 };
+    double rho = std::sqrt((double)m[0]) * (1.0 + 1e-6), dw = std::sqrt((double)m[1]) * (1.0 + 1e-6);
+    if (!(dw > 0.0)) return BVHT_OK;
+    return ensure_bake_for(ctx, zero, rho, dw);
 }
 bool fast_on(const bvht_ctx* ctx) { return (ctx->flags & BVHT_FLAG_FAST) != 0; }
 
@@ -616,7 +664,7 @@ int bvht_create(int device, uint32_t flags, bvht_ctx** out) {
            && cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
     if (ok) {
         ctx->stream = ctx->own_stream;
-        ok = ensure(ctx, ctx->work_counter, 256) == BVHT_OK && ensure_pinned(ctx, 1 << 16) == BVHT_OK;
+        ok = ensure(ctx, ctx->work_counter, 512) == BVHT_OK && ensure_pinned(ctx, 1 << 16) == BVHT_OK;
     }
     if (ok) {
         ok = cudaStreamCreateWithFlags(&ctx->aux[0], cudaStreamNonBlocking) == cudaSuccess
@@ -1129,8 +1177,9 @@ int bvht_trace_rays_device(bvht_ctx* ctx, const void* rays_device, uint64_t n, v
     cudaSetDevice(ctx->device);
     RaysParams p;
     memset(&p, 0, sizeof p);
-    int rc = fill_scene(ctx, p.scene);
+    int rc = ensure_bake_rays(ctx, rays_device, n);
     if (rc) return rc;
+    if ((rc = fill_scene(ctx, p.scene))) return rc;
     p.rays = (const float*)rays_device; p.n = n; p.out = (uint4*)out_device;
     p.work_counter = (unsigned int*)ctx->work_counter.p;
     int grid = persistent_grid(ctx, false, (n + 31) / 32);

@@ -132,7 +132,8 @@ struct Builder {
 
 ModelStats compute_model_stats(const float* tris, uint32_t n_tris) {
     ModelStats m;
-    double radius = 0.0, max_edge = 0.0, kmax = 0.0;
+    double radius = 0.0, max_edge = 0.0, kmax = 0.0, sum_edge = 0.0, sum_kappa = 0.0;
+    uint64_t n_good = 0;
     Box mb; mb.reset(); bool any = false;
     for (uint32_t i = 0; i < n_tris; ++i) {
         const float* t = tris + (size_t)i * 9;
@@ -149,8 +150,10 @@ ModelStats compute_model_stats(const float* tris, uint32_t n_tris) {
         }
         max_edge = std::max(max_edge, std::max(l1, std::max(l2, l3)));
         kmax = std::max(kmax, kappa);
+        sum_edge += l1; sum_kappa += kappa; ++n_good;
         mb.grow(t); mb.grow(t + 3); mb.grow(t + 6); any = true;
     }
+    if (n_good) { m.mean_edge = sum_edge / (double)n_good; m.mean_kappa = sum_kappa / (double)n_good; }
     m.radius = radius > 0.0 ? radius : 1.0;
     m.max_edge = max_edge; m.model_kappa = kmax; m.model_valid = any;
     if (any) for (int k = 0; k < 3; ++k) { m.model_lo[k] = mb.lo[k]; m.model_hi[k] = mb.hi[k]; }

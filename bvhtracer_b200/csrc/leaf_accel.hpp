@@ -68,6 +68,7 @@ inline void accel_deltas(const LeafAccelConfig& cfg, double d_max, double o_max,
 // Whole-model statistics the inflation depends on (recomputed on the host after every vertex update: one O(n) pass).
 struct ModelStats {
     double radius = 1.0, max_edge = 0.0, model_kappa = 0.0;
+    double mean_edge = 0.0, mean_kappa = 0.0;     // over the non-degenerate triangles: "typical" size for the usefulness cap
     float  model_lo[3] = { 0, 0, 0 }, model_hi[3] = { 0, 0, 0 };
     bool   model_valid = false;
 };

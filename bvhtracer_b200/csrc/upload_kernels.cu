@@ -4,6 +4,7 @@
 // The two edge subtractions are the first two operations of Triangle::intersect (triangle.rs:43-44); doing
 // them once on upload is bit-identical (one IEEE subtraction either way; no FMA can form here).
 // HBM-bound streaming kernel: 36 B read + 48 B written per triangle, loads coalesced through shared memory.
+#include <algorithm>
 #include "launchers.hpp"
 
 namespace bvht {
@@ -139,7 +140,35 @@ refit_sub_nodes_kernel(float4* __restrict__ raw, const uint32_t* __restrict__ pa
     }
 }
 
+// max |o|^2 and max |d|^2 over a ray buffer (7 floats per ray): lets the leaf accelerator be baked for an arbitrary
+// batch of rays before it is traced.  Non-negative floats order like their bit patterns, so atomicMax on uint works.
+__global__ void __launch_bounds__(kRepackBlock)
+ray_bounds_kernel(const float* __restrict__ rays, unsigned long long n, unsigned int* __restrict__ out) {
+    float mo = 0.0f, md = 0.0f;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)kRepackBlock + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * kRepackBlock) {
+        const float* r = rays + i * 7;
+        float ox = __ldg(r), oy = __ldg(r + 1), oz = __ldg(r + 2), dx = __ldg(r + 3), dy = __ldg(r + 4), dz = __ldg(r + 5);
+        float o2 = ox * ox + oy * oy + oz * oz, d2 = dx * dx + dy * dy + dz * dz;
+        if (!(o2 <= 3.0e38f)) o2 = 3.0e38f;          // NaN / inf: make the limits unreachable -> brute-force leaves
+        if (!(d2 <= 3.0e38f)) d2 = 3.0e38f;
+        mo = fmaxf(mo, o2); md = fmaxf(md, d2);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        mo = fmaxf(mo, __shfl_xor_sync(0xFFFFFFFFu, mo, off));
+        md = fmaxf(md, __shfl_xor_sync(0xFFFFFFFFu, md, off));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMax(out + 0, __float_as_uint(mo)); atomicMax(out + 1, __float_as_uint(md)); }
+}
+
 } // namespace
+
+cudaError_t launch_ray_bounds(const float* rays, unsigned long long n, unsigned int* out2, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(out2, 0, 8, s);
+    if (e != cudaSuccess || n == 0) return e;
+    int grid = (int)std::min<unsigned long long>((n + kRepackBlock - 1) / kRepackBlock, 148ull * 8);
+    ray_bounds_kernel<<<grid, kRepackBlock, 0, s>>>(rays, n, out2);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_refit_sub_nodes(float4* raw, const uint32_t* parent, unsigned int* counters, const float* tris_aos,
                                    const uint32_t* order, uint32_t n_nodes, cudaStream_t s) {

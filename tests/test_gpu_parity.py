@@ -209,6 +209,38 @@ def test_random_rays_sixteen_armadillos(flags):
     assert_strict(got, ref)
 
 
+def test_ray_batches_rebake_the_leaf_accelerator():
+    # Ray batches far outside the default |o| / |d| limits, with un-normalised directions: the accelerator is re-baked for
+    # the batch (one reduction kernel), results stay bit-identical, and alternating with primary frames stays exact too.
+    scene, cam = SB.oracle_scene(examples.sixteen_armadillos(5))
+    rng = np.random.default_rng(99)
+    n = 6000
+    o = (rng.normal(size=(n, 3)) * 300.0).astype(F)
+    target = rng.uniform(-4, 4, (n, 3)).astype(F)
+    d = ((target - o) * rng.uniform(0.01, 40.0, (n, 1))).astype(F)
+    rays = np.concatenate([o, d, np.full((n, 1), O.FLT_MAX, F)], axis=1).astype(F)
+    near = rays.copy()
+    near[:, :3] = rng.uniform(-6, 6, (n, 3)).astype(F)
+    near[:, 3:6] = (target - near[:, :3]).astype(F)
+    ref_far = scene.trace_rays(rays, threads=NTHREADS)
+    ref_near = scene.trace_rays(near, threads=NTHREADS)
+    ref_img = scene.render(cam, 96, 64, tile=8)
+    assert (ref_far["id"] != O.MISS_ID).sum() > 100
+    with Engine(flags=_ffi.FLAG_STRICT | _ffi.FLAG_LEAF_ACCEL) as eng:
+        SB.upload_scene(eng, scene)
+        for _ in range(2):
+            assert_strict(eng.trace_rays(rays), ref_far)
+            assert eng.trace_primary(SB.to_ffi_camera(cam), 96, 64, tile=8).tobytes() == ref_img.tobytes()
+            assert_strict(eng.trace_rays(near), ref_near)
+        # NaN / inf rays must not poison the bake for the finite ones in the same batch
+        bad = near.copy()
+        bad[0, 0] = np.inf; bad[1, 4] = np.nan
+        got = eng.trace_rays(bad)
+        ref_bad = scene.trace_rays(bad, threads=NTHREADS)
+        assert np.array_equal(got["id"][2:], ref_bad["id"][2:])
+        assert got["t"][2:].tobytes() == ref_bad["t"][2:].tobytes()
+
+
 def test_empty_and_ragged_inputs():
     scene, cam = SB.oracle_scene(examples.cube())
     with Engine() as eng:
