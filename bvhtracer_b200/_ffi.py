@@ -40,7 +40,7 @@ class ShadeParams(C.Structure):
                 ("hit_rgba", C.c_uint8 * 4), ("miss_rgba", C.c_uint8 * 4), ("object0_transform", C.c_float * 16)]
 
 
-SHADE_NONE, SHADE_DEPTH, SHADE_INTERSECTION, SHADE_UV, SHADE_NORMAL = 0, 1, 2, 3, 4
+SHADE_NONE, SHADE_DEPTH, SHADE_INTERSECTION, SHADE_UV, SHADE_NORMAL, SHADE_TEXTURE = 0, 1, 2, 3, 4, 5
 
 
 class Stats(C.Structure):
@@ -67,6 +67,8 @@ SYMBOLS = [
     ("bvht_blas_create", C.c_int, [_P, _P, C.c_uint32, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     ("bvht_blas_destroy", C.c_int, [_P, C.c_uint32]),
     ("bvht_blas_set_normals", C.c_int, [_P, C.c_uint32, _P, C.c_uint32]),
+    ("bvht_blas_set_tex_coords", C.c_int, [_P, C.c_uint32, _P, C.c_uint32]),
+    ("bvht_blas_set_texture", C.c_int, [_P, C.c_uint32, _P, C.c_uint32, C.c_uint32]),
     ("bvht_blas_update_vertices", C.c_int, [_P, C.c_uint32, _P, C.c_uint32]),
     ("bvht_blas_refit", C.c_int, [_P, C.c_uint32]),
     ("bvht_blas_read_nodes", C.c_int, [_P, C.c_uint32, _P, C.c_uint32]),

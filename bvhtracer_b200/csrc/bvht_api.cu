@@ -41,6 +41,8 @@ struct Blas {
     std::vector<bvht_bvh_node> h_nodes;     // host copy of the uploaded node pool (topology for validation / accel)
     std::vector<float> h_tris;              // host copy of the vertices (needed to rebuild the leaf accelerator)
     DevBuf tris_aos, nodes, tri, normals;      // normals: 3 float4 per primitive, ORIGINAL primitive order
+    DevBuf tex_coords, texels;                 // 3 float2 per primitive (ORIGINAL order); Rgb<u8> texture, row-major
+    uint32_t tex_w = 0, tex_h = 0;
     // refit plan
     DevBuf chunk_leaf, chunk_first, chunk_count, leaf_chunks, parent, scratch, counters;
     uint32_t n_chunks = 0;
@@ -139,7 +141,7 @@ int h2d(bvht_ctx* ctx, void* dst, const void* src, size_t bytes) {
 }
 
 void free_blas(Blas& b) {
-    for (DevBuf* d : { &b.tris_aos, &b.nodes, &b.tri, &b.normals, &b.chunk_leaf, &b.chunk_first, &b.chunk_count,
+    for (DevBuf* d : { &b.tris_aos, &b.nodes, &b.tri, &b.normals, &b.tex_coords, &b.texels, &b.chunk_leaf, &b.chunk_first, &b.chunk_count,
                        &b.leaf_chunks, &b.parent, &b.scratch, &b.counters, &b.sub_nodes, &b.sub_raw, &b.sub_order, &b.stri,
                        &b.leaf_sub_root, &b.sub_parent, &b.sub_counters })
         release(*d);
@@ -810,6 +812,37 @@ int bvht_blas_set_normals(bvht_ctx* ctx, uint32_t blas_id, const float* normals,
     return BVHT_OK;
 }
 
+int bvht_blas_set_tex_coords(bvht_ctx* ctx, uint32_t blas_id, const float* tex_coords, uint32_t n_tris) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (blas_id >= ctx->blas.size() || !ctx->blas[blas_id].alive) return fail(ctx, BVHT_ERR_BAD_HANDLE, "unknown blas id %u", blas_id);
+    Blas& b = ctx->blas[blas_id];
+    if (!tex_coords) return fail(ctx, BVHT_ERR_INVALID_ARG, "null texture coordinate pointer");
+    if (n_tris != b.n_tris) return fail(ctx, BVHT_ERR_INVALID_ARG, "texture coordinates for %u primitives, model has %u", n_tris, b.n_tris);
+    cudaSetDevice(ctx->device);
+    int rc = ensure(ctx, b.tex_coords, (size_t)n_tris * 24);
+    if (rc) return rc;
+    if ((rc = h2d(ctx, b.tex_coords.p, tex_coords, (size_t)n_tris * 24))) return rc;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return BVHT_OK;
+}
+
+int bvht_blas_set_texture(bvht_ctx* ctx, uint32_t blas_id, const uint8_t* rgb, uint32_t width, uint32_t height) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (blas_id >= ctx->blas.size() || !ctx->blas[blas_id].alive) return fail(ctx, BVHT_ERR_BAD_HANDLE, "unknown blas id %u", blas_id);
+    Blas& b = ctx->blas[blas_id];
+    if (!rgb) return fail(ctx, BVHT_ERR_INVALID_ARG, "null texel pointer");
+    // the reference takes `% width` / `% height` (material.rs:47-48): an empty texture divides by zero there
+    if (width == 0 || height == 0) return fail(ctx, BVHT_ERR_INVALID_ARG, "empty texture (%u x %u)", width, height);
+    cudaSetDevice(ctx->device);
+    size_t bytes = (size_t)width * height * 3;
+    int rc = ensure(ctx, b.texels, bytes);
+    if (rc) return rc;
+    if ((rc = h2d(ctx, b.texels.p, rgb, bytes))) return rc;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    b.tex_w = width; b.tex_h = height;
+    return BVHT_OK;
+}
+
 int bvht_blas_update_vertices(bvht_ctx* ctx, uint32_t blas_id, const float* tris, uint32_t n_tris) {
     if (!ctx) return BVHT_ERR_BAD_HANDLE;
     if (blas_id >= ctx->blas.size() || !ctx->blas[blas_id].alive) return fail(ctx, BVHT_ERR_BAD_HANDLE, "unknown blas id %u", blas_id);
@@ -990,6 +1023,17 @@ static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvh
             const float* m = shade->object0_transform;
             for (int c = 0; c < 4; ++c) for (int r = 0; r < 3; ++r) p.shade_m[c * 3 + r] = m[c * 4 + r];
         }
+        if (shade->kind == BVHT_SHADE_TEXTURE) {
+            // instance index always 0 again: object 0's model supplies the coordinates and the texture (renderer.rs:309-327)
+            if (ctx->h_inst.empty()) return fail(ctx, BVHT_ERR_NOT_READY, "BVHT_SHADE_TEXTURE needs at least one instance");
+            const Blas& b0 = ctx->blas[ctx->h_inst[0].blas_id];
+            if (!b0.tex_coords.p || !b0.texels.p || b0.tex_w == 0)
+                return fail(ctx, BVHT_ERR_NOT_READY, "BVHT_SHADE_TEXTURE: bvht_blas_set_tex_coords / bvht_blas_set_texture were not called for the model of scene object 0");
+            p.shade_tex = (const float2*)b0.tex_coords.p;
+            p.shade_texels = (const uint8_t*)b0.texels.p;
+            p.tex_w = b0.tex_w; p.tex_h = b0.tex_h;
+            p.shade_n_prims = b0.n_tris;
+        }
     }
     p.work_counter = (unsigned int*)ctx->work_counter.p + slot;
     p.n_rect = 0;
@@ -1018,7 +1062,7 @@ int bvht_render_frame_device(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
                              bvht_rect region, const bvht_shade_params* shade, void* frame_out_device, void* hits_out_device) {
     if (!ctx) return BVHT_ERR_BAD_HANDLE;
     if (!frame_out_device && !hits_out_device) return fail(ctx, BVHT_ERR_INVALID_ARG, "no output buffer");
-    if (frame_out_device && (!shade || shade->kind == BVHT_SHADE_NONE || shade->kind > BVHT_SHADE_NORMAL))
+    if (frame_out_device && (!shade || shade->kind == BVHT_SHADE_NONE || shade->kind > BVHT_SHADE_TEXTURE))
         return fail(ctx, BVHT_ERR_INVALID_ARG, "frame output requested without a valid shade kind");
     int rc = check_frame_args(ctx, camera, width, height, tile, region);
     if (rc) return rc;
@@ -1085,7 +1129,7 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
                       bvht_rect region, const bvht_shade_params* shade, uint32_t* frame_out_host, bvht_hit* hits_out_host) {
     if (!ctx) return BVHT_ERR_BAD_HANDLE;
     if (!frame_out_host && !hits_out_host) return fail(ctx, BVHT_ERR_INVALID_ARG, "no output buffer");
-    if (frame_out_host && (!shade || shade->kind == BVHT_SHADE_NONE || shade->kind > BVHT_SHADE_NORMAL))
+    if (frame_out_host && (!shade || shade->kind == BVHT_SHADE_NONE || shade->kind > BVHT_SHADE_TEXTURE))
         return fail(ctx, BVHT_ERR_INVALID_ARG, "frame output requested without a valid shade kind");
     int rc = check_frame_args(ctx, camera, width, height, tile, region);
     if (rc) return rc;

@@ -65,6 +65,9 @@ struct PrimaryParams {
     uint32_t  hit_rgba, miss_rgba;       // IntersectionShader::new(hit, miss), packed r | g<<8 | b<<16 | a<<24
     const float4* shade_normals;         // kind 4: 3 float4 per primitive of scene object 0's model (un-reordered normals)
     uint32_t  shade_n_prims;
+    const float2* shade_tex;             // kind 5: 3 float2 per primitive of scene object 0's model (un-reordered tex coords)
+    const uint8_t* shade_texels;         // kind 5: object 0's texture, Rgb<u8>, texel (x, y) at (y * tex_w + x) * 3
+    uint32_t  tex_w, tex_h;
     float     shade_m[12];               // kind 4: columns 0..2 (xyz) + column 3 (xyz) of object 0's forward transform
     unsigned int* work_counter;          // persistent-thread work cursor
     unsigned long long* stats;           // debug counters (stats build only)

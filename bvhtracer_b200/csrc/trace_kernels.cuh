@@ -503,10 +503,20 @@ __device__ __forceinline__ RayM primary_ray(const CameraDev& C, uint32_t px, uin
     return w;
 }
 
+// Rust's saturating `f32 as usize` (negative and NaN -> 0, >= 2^64 -> usize::MAX) followed by `% n` (material.rs:47-48).
+__device__ __forceinline__ uint32_t texel_index(float x, uint32_t n) {
+    if (!(x >= 1.0f)) return 0u;
+    if (x < 4294967296.0f) return __float2uint_rz(x) % n;
+    unsigned long long v = x >= 18446744073709551616.0f ? ~0ull : __float2ull_rz(x);
+    return (uint32_t)(v % (unsigned long long)n);
+}
+
 // Fused accumulator + pixel shader (renderer.rs:116-245): what the examples turn a hit into.
 //   kind 1: DepthAccumulator (:184-194) + DepthMappingShader (:207-222)   two/sixteen_armadillos
 //   kind 2: IntersectionAccumulator (:145-153) + IntersectionShader (:166-174)   big_ben_clock
 //   kind 3: UvMappingAccumulator (:233-245) + RadianceToRgbShader (:124-132)
+//   kind 4: NormalMappingAccumulator (:256-286) + RadianceToRgbShader   cube, trippy_teapots
+//   kind 5: TextureMaterialAccumulator (:289-334) + RadianceToRgbShader   quad
 // Integer tricks are kept: `as i32` / `as u8` are saturating casts (NaN -> 0), u32 arithmetic wraps.
 __device__ __forceinline__ uint32_t shade_pixel(const PrimaryParams& P, const HitRec& h) {
     const bool hit = h.id != 0xFFFFFFFFu;
@@ -549,6 +559,28 @@ __device__ __forceinline__ uint32_t shade_pixel(const PrimaryParams& P, const Hi
             rx = __fmul_rn(__fadd_rn(__fdiv_rn(wx, len), 1.0f), 0.5f);
             ry = __fmul_rn(__fadd_rn(__fdiv_rn(wy, len), 1.0f), 0.5f);
             rz = __fmul_rn(__fadd_rn(__fdiv_rn(wz, len), 1.0f), 0.5f);
+        }
+        uint32_t r = min(255u, __float2uint_rz(__fmul_rn(255.0f, rx)));
+        uint32_t g = min(255u, __float2uint_rz(__fmul_rn(255.0f, ry)));
+        uint32_t b = min(255u, __float2uint_rz(__fmul_rn(255.0f, rz)));
+        return r | (g << 8) | (b << 16) | 0xFF000000u;
+    }
+    if (P.shade_kind == 5u) {
+        // TextureMaterialAccumulator (renderer.rs:297-333): tex_coords[prim] of object 0's model, uv = t0 * (1 - u - v) +
+        // t1 * u + t2 * v, nearest texel of object 0's texture (material.rs:44-52), texel * (1 / 256).
+        float rx = 0.0f, ry = 0.0f, rz = 0.0f;
+        uint32_t prim = h.id & 0x000FFFFFu;
+        if (hit && prim < P.shade_n_prims) {
+            const float2* tp = P.shade_tex + 3 * (size_t)prim;
+            float2 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+            float w0 = __fsub_rn(__fsub_rn(1.0f, h.u), h.v);
+            float tu = __fadd_rn(__fadd_rn(__fmul_rn(a.x, w0), __fmul_rn(b.x, h.u)), __fmul_rn(c.x, h.v));
+            float tv = __fadd_rn(__fadd_rn(__fmul_rn(a.y, w0), __fmul_rn(b.y, h.u)), __fmul_rn(c.y, h.v));
+            uint32_t iu = texel_index(__fmul_rn(tu, (float)P.tex_w), P.tex_w);
+            uint32_t iv = texel_index(__fmul_rn(tv, (float)P.tex_h), P.tex_h);
+            const uint8_t* px = P.shade_texels + ((size_t)iv * P.tex_w + iu) * 3;
+            const float s = 1.0f / 256.0f;
+            rx = __fmul_rn((float)__ldg(px + 0), s); ry = __fmul_rn((float)__ldg(px + 1), s); rz = __fmul_rn((float)__ldg(px + 2), s);
         }
         uint32_t r = min(255u, __float2uint_rz(__fmul_rn(255.0f, rx)));
         uint32_t g = min(255u, __float2uint_rz(__fmul_rn(255.0f, ry)));

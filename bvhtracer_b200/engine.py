@@ -83,6 +83,17 @@ class Engine:
         normals = np.ascontiguousarray(np.asarray(normals, dtype="<f4").reshape(-1, 9))
         self._check(self._lib.bvht_blas_set_normals(self._ctx, int(blas_id), ptr(normals), normals.shape[0]))
 
+    def blas_set_tex_coords(self, blas_id, tex_coords):
+        """Mesh::tex_coords() (mesh.rs:146-154): n_tris x 6 f32, original primitive order."""
+        tex_coords = np.ascontiguousarray(np.asarray(tex_coords, "<f4").reshape(-1, 6))
+        self._check(self._lib.bvht_blas_set_tex_coords(self._ctx, int(blas_id), ptr(tex_coords), tex_coords.shape[0]))
+
+    def blas_set_texture(self, blas_id, texels):
+        """TextureMaterial<Rgb<u8>> (materials/material.rs:14-53): texels[height, width, 3] u8, already decoded."""
+        texels = np.ascontiguousarray(np.asarray(texels, np.uint8))
+        assert texels.ndim == 3 and texels.shape[2] == 3
+        self._check(self._lib.bvht_blas_set_texture(self._ctx, int(blas_id), ptr(texels), texels.shape[1], texels.shape[0]))
+
     def blas_update_vertices(self, blas_id, tris):
         tris = np.ascontiguousarray(np.asarray(tris, dtype="<f4").reshape(-1, 9))
         self._check(self._lib.bvht_blas_update_vertices(self._ctx, int(blas_id), ptr(tris), tris.shape[0]))
@@ -130,6 +141,11 @@ class Engine:
         """NormalMappingAccumulator + RadianceToRgbShader (cube.rs / trippy_teapots.rs main); needs blas_set_normals."""
         m = np.asarray(object0_transform, "<f4").reshape(16)
         return ShadeParams(_ffi.SHADE_NORMAL, 0.0, 0.0, (C.c_uint8 * 4)(0, 0, 0, 0), (C.c_uint8 * 4)(0, 0, 0, 0), (C.c_float * 16)(*m))
+
+    @staticmethod
+    def shade_texture():
+        """TextureMaterialAccumulator + RadianceToRgbShader (quad.rs main); needs blas_set_tex_coords + blas_set_texture."""
+        return ShadeParams(_ffi.SHADE_TEXTURE, 0.0, 0.0, (C.c_uint8 * 4)(0, 0, 0, 0), (C.c_uint8 * 4)(0, 0, 0, 0))
 
     @staticmethod
     def shade_intersection(hit=(255, 255, 255, 255), miss=(0, 0, 0, 255)):

@@ -199,6 +199,36 @@ def quad():
 
 
 QUAD_TRIS = np.array([[-1, -1, 0, 1, 1, 0, -1, 1, 0], [-1, -1, 0, 1, -1, 0, 1, 1, 0]], F)
+# examples/quad.rs:45-77: TextureCoordinates / Normals given to MeshBuilder::with_primitive, per triangle
+QUAD_TEX_COORDS = np.array([[0, 0, 1, 1, 0, 1], [0, 0, 1, 0, 1, 1]], F)
+QUAD_NORMALS = np.tile(np.array([0, 0, 1], F), (2, 3))
+
+
+def quad_example(frame=0, elapsed=1.0 / 60.0):
+    """examples/quad.rs:28-113: the textured quad, SymmetricFov camera at (0, 0, 2), spinning about z.
+
+    The spin comes from the reference's rigid-body integrator (angular velocity (0, 0, 2), out of scope here); the
+    stand-in is angle_z = 2 * elapsed * frame.  The texture (bricks_rgb.png, PNG decoding is host-side and out of
+    scope) is replaced by `brick_texture` below."""
+    cam = CameraSpec(position=(0, 0, 2), forward=(0, 0, -1), right=(1, 0, 0), up=(0, 1, 0), near=1.0)
+    angle = float(F(2.0) * F(elapsed) * F(frame))
+    return SceneSpec("quad_example", ["<quad>"], cam, [ObjectSpec(0, angle_z=angle)])
+
+
+def brick_texture(width=256, height=256, seed=7):
+    """Procedural Rgb<u8> stand-in for examples/assets/bricks_rgb.png: texels[height, width, 3]."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:height, 0:width]
+    bh, bw = max(height // 8, 1), max(width // 4, 1)
+    row = y // bh
+    xs = x + (row % 2) * (bw // 2)
+    mortar = ((y % bh) < max(bh // 8, 1)) | ((xs % bw) < max(bw // 16, 1))
+    tone = rng.integers(-20, 20, (height // bh + 2, width // bw + 3))[row, xs // bw]
+    tex = np.zeros((height, width, 3), np.int32)
+    tex[..., 0] = 170 + tone; tex[..., 1] = 70 + tone // 2; tex[..., 2] = 50 + tone // 3
+    tex[mortar] = (200, 200, 190)
+    tex += rng.integers(-6, 7, tex.shape)
+    return np.clip(tex, 0, 255).astype(np.uint8)
 
 CONFIGS = {
     "cube": cube,

@@ -36,6 +36,9 @@ def lib():
             "bvhx_last_error": (C.c_char_p, []),
             "bvhx_mesh_from_triangles": (_P, [_P, _P, C.c_uint32]),
             "bvhx_mesh_normals": (_P, [_P]),
+            "bvhx_mesh_set_tex_coords": (C.c_int, [_P, _P, C.c_uint32]),
+            "bvhx_mesh_tex_coords": (_P, [_P, C.POINTER(C.c_uint32)]),
+            "bvhx_model_build_textured": (_P, [_P, _P, C.c_uint32, C.c_uint32]),
             "bvhx_mesh_from_tri_text": (_P, [C.c_char_p, C.c_size_t]),
             "bvhx_mesh_from_obj_text": (_P, [C.c_char_p, C.c_size_t]),
             "bvhx_mesh_len": (C.c_uint32, [_P]),
@@ -112,6 +115,20 @@ class Mesh:
         p = lib().bvhx_mesh_normals(self._h)
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(max(n, 1), 9))[:n].copy()
 
+    def set_tex_coords(self, tex_coords):
+        """TextureCoordinates<f32, 3> per primitive (mesh.rs:8-51): n x 6 floats"""
+        tc = np.ascontiguousarray(np.asarray(tex_coords, "<f4").reshape(-1, 6))
+        if lib().bvhx_mesh_set_tex_coords(self._h, _ffi.ptr(tc), tc.shape[0]) != 0:
+            raise _err()
+        return self
+
+    def tex_coords(self):
+        n = C.c_uint32()
+        p = lib().bvhx_mesh_tex_coords(self._h, C.byref(n))
+        if n.value == 0:
+            return np.zeros((0, 6), "<f4")
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n.value, 6)).copy()
+
     def primitives(self):
         n = lib().bvhx_mesh_len(self._h)
         p = lib().bvhx_mesh_data(self._h)
@@ -179,12 +196,23 @@ class ModelBuilder:
 
     def __init__(self):
         self._mesh = None
+        self._texture = None
 
     def with_mesh(self, mesh):
         self._mesh = mesh
         return self
 
+    def with_texture(self, texels):
+        """TextureMaterial::new(texture) (materials/material.rs:22-24): decoded Rgb<u8> texels[height, width, 3]"""
+        texels = np.ascontiguousarray(np.asarray(texels, np.uint8))
+        assert texels.ndim == 3 and texels.shape[2] == 3
+        self._texture = texels
+        return self
+
     def build(self):
+        if self._texture is not None:
+            t = self._texture
+            return ModelInstance(lib().bvhx_model_build_textured(self._mesh._h, _ffi.ptr(t), t.shape[1], t.shape[0]))
         return ModelInstance(lib().bvhx_model_build(self._mesh._h))
 
 
@@ -356,6 +384,11 @@ def intersection_pipeline(hit=(255, 255, 255, 255), miss=(0, 0, 0, 255)):
 def normal_pipeline():
     """NormalMappingAccumulator + RadianceToRgbShader (cube.rs, trippy_teapots.rs)"""
     return (_ffi.SHADE_NORMAL, 0.0, 0.0, (0, 0, 0, 0), (0, 0, 0, 0))
+
+
+def texture_pipeline():
+    """TextureMaterialAccumulator + RadianceToRgbShader (quad.rs)"""
+    return (_ffi.SHADE_TEXTURE, 0.0, 0.0, (0, 0, 0, 0), (0, 0, 0, 0))
 
 
 def uv_pipeline():

@@ -159,17 +159,37 @@ struct Intersection {
 // Normals<f32, 3> (mesh.rs:55-96) has the layout of a Triangle: three Vector3
 using Normals = Triangle;
 
+// TextureCoordinates<f32, 3> (mesh.rs:8-51): three Vector2
+struct Vector2 { float x = 0, y = 0; };
+struct TextureCoordinates { Vector2 uv[3]; };
+
 struct Mesh {
     std::vector<Triangle> primitives;
     std::vector<Normals> normals;             // per-vertex normals, NEVER reordered by the BVH build (bvh.rs:426 swaps positions only)
+    std::vector<TextureCoordinates> tex_coords;   // likewise never reordered
     size_t len_primitives() const { return primitives.size(); }
 };
 
 struct MeshBuilder {
     Mesh mesh;
-    MeshBuilder& with_primitive(const Triangle& t) { mesh.primitives.push_back(t); mesh.normals.push_back(Normals()); return *this; }
-    MeshBuilder& with_primitive(const Triangle& t, const Normals& n) { mesh.primitives.push_back(t); mesh.normals.push_back(n); return *this; }
+    MeshBuilder& with_primitive(const Triangle& t) { return with_primitive(t, TextureCoordinates(), Normals()); }
+    MeshBuilder& with_primitive(const Triangle& t, const Normals& n) { return with_primitive(t, TextureCoordinates(), n); }
+    MeshBuilder& with_primitive(const Triangle& t, const TextureCoordinates& tc, const Normals& n) {     // mesh.rs:189-198
+        mesh.primitives.push_back(t); mesh.tex_coords.push_back(tc); mesh.normals.push_back(n); return *this;
+    }
     Mesh build() { return std::move(mesh); }
+};
+
+// materials/material.rs:14-53 over texture_buffer.rs: a decoded Rgb<u8> image, texel (x, y) at (y * width + x) * 3.
+// Decoding (PNG/JPEG, materials/decoders.rs) stays with the caller; evaluation runs on the device (BVHT_SHADE_TEXTURE).
+struct TextureMaterial {
+    uint32_t width = 0, height = 0;
+    std::vector<uint8_t> rgb;
+    TextureMaterial() = default;
+    TextureMaterial(uint32_t w, uint32_t h, std::vector<uint8_t> texels) : width(w), height(h), rgb(std::move(texels)) {
+        if (rgb.size() != (size_t)w * h * 3) throw std::invalid_argument("TextureMaterial: texel buffer does not match width x height x 3");
+    }
+    bool empty() const { return width == 0 || height == 0; }
 };
 
 // tri_loader/src/{lexer,loader}.rs + mesh/decoders.rs:102-134: nine f32 per triangle, ' ' '\\' '\t' are
@@ -210,6 +230,7 @@ struct TriMeshDecoder {
 struct ObjMeshDecoder {
     static Mesh read_mesh(const char* text, size_t len) {
         std::vector<Vector3> pos, nrm;
+        std::vector<Vector2> tex;
         MeshBuilder b;
         size_t i = 0; int objects = 0;
         while (i < len) {
@@ -222,38 +243,46 @@ struct ObjMeshDecoder {
             if (line[0] == 'o' && (line[1] == ' ' || line[1] == '\t')) { if (++objects > 1 && !b.mesh.primitives.empty()) break; continue; }
             bool is_v = line[0] == 'v' && (line[1] == ' ' || line[1] == '\t');
             bool is_vn = line.size() > 2 && line[0] == 'v' && line[1] == 'n' && (line[2] == ' ' || line[2] == '\t');
-            if (is_v || is_vn) {
+            bool is_vt = line.size() > 2 && line[0] == 'v' && line[1] == 't' && (line[2] == ' ' || line[2] == '\t');
+            if (is_vt) {                                  // vt u v [w]: (u, v) kept, f64 -> f32 (decoders.rs:190)
+                const char* c = line.c_str() + 2; char* e = nullptr; Vector2 t;
+                double u = std::strtod(c, &e); if (e == c) throw std::runtime_error("bad texture vertex"); c = e;
+                double v = std::strtod(c, &e); if (e == c) v = 0.0;
+                t.x = (float)u; t.y = (float)v; tex.push_back(t);
+            } else if (is_v || is_vn) {
                 const char* c = line.c_str() + (is_v ? 1 : 2); char* e = nullptr; float v[3];
                 for (int k = 0; k < 3; ++k) { double d = std::strtod(c, &e); if (e == c) throw std::runtime_error("bad vertex"); v[k] = (float)d; c = e; }
                 (is_v ? pos : nrm).push_back(Vector3(v[0], v[1], v[2]));
             } else if (line[0] == 'f' && (line[1] == ' ' || line[1] == '\t')) {
-                std::vector<long> idx, nidx; const char* c = line.c_str() + 1;
+                std::vector<long> idx, nidx, tidx; const char* c = line.c_str() + 1;
                 while (*c) {
                     while (*c == ' ' || *c == '\t' || *c == '\r') ++c;
                     if (!*c) break;
                     char* e = nullptr; long vi = std::strtol(c, &e, 10); if (e == c) break;
                     if (vi < 0) vi = (long)pos.size() + vi + 1;
                     c = e;
-                    long ni = 0; bool have = false;
+                    long ni = 0, ti = 0; bool have = false, have_t = false;
                     if (*c == '/') {                      // v/vt/vn, v//vn or v/vt
                         ++c;
-                        if (*c != '/') { std::strtol(c, &e, 10); c = e; }
+                        if (*c != '/') { char* e1 = nullptr; ti = std::strtol(c, &e1, 10); if (e1 != c) { have_t = true; c = e1; } }
                         if (*c == '/') { ++c; char* e2 = nullptr; ni = std::strtol(c, &e2, 10); if (e2 != c) { have = true; c = e2; } }
                     }
                     if (have && ni < 0) ni = (long)nrm.size() + ni + 1;
-                    idx.push_back(vi - 1); nidx.push_back(have ? ni - 1 : -1);
+                    if (have_t && ti < 0) ti = (long)tex.size() + ti + 1;
+                    idx.push_back(vi - 1); nidx.push_back(have ? ni - 1 : -1); tidx.push_back(have_t ? ti - 1 : -1);
                     while (*c && *c != ' ' && *c != '\t') ++c;
                 }
                 for (size_t k = 1; k + 1 < idx.size(); ++k) {
                     size_t tri[3] = { 0, k, k + 1 };
-                    Triangle t; Normals n;
+                    Triangle t; Normals n; TextureCoordinates tc;
                     for (int v = 0; v < 3; ++v) {
-                        long pi = idx[tri[v]], ni = nidx[tri[v]];
+                        long pi = idx[tri[v]], ni = nidx[tri[v]], ti = tidx[tri[v]];
+                        if (ti >= 0 && (size_t)ti < tex.size()) tc.uv[v] = tex[ti];
                         if (pi < 0 || (size_t)pi >= pos.size()) throw std::runtime_error("face index out of range");
                         t.vertices[v] = pos[pi];
                         n.vertices[v] = (ni >= 0 && (size_t)ni < nrm.size()) ? nrm[ni] : Vector3::zero();   // decoders.rs:182-203
                     }
-                    b.with_primitive(t, n);
+                    b.with_primitive(t, tc, n);
                 }
             }
         }
@@ -366,23 +395,27 @@ private:
 // model/model.rs:16-146.  `refit()` marks the model: the refit itself (bvh.rs:469-493) runs on the device the
 // next time an integrator renders, and the refitted node boxes are read back into `bvh.nodes`.
 struct Model {
-    Mesh mesh; Bvh bvh;
+    Mesh mesh; Bvh bvh; TextureMaterial texture_;
+    const TextureMaterial& texture() const { return texture_; }
     uint64_t geometry_version = 1;     // bumped when vertices change
     bool refit_requested = false;
     Aabb bounds() const { return bvh.bounds(); }
     std::vector<Triangle>& primitives_mut() { geometry_version++; return mesh.primitives; }
     const std::vector<Triangle>& primitives() const { return mesh.primitives; }
     const std::vector<Normals>& normals() const { return mesh.normals; }
+    const std::vector<TextureCoordinates>& tex_coords() const { return mesh.tex_coords; }
     void refit() { refit_requested = true; }
 };
 using ModelInstance = std::shared_ptr<Model>;
 
 struct ModelBuilder {
-    Mesh mesh;
+    Mesh mesh; TextureMaterial texture;
     ModelBuilder& with_mesh(Mesh m) { mesh = std::move(m); return *this; }
+    ModelBuilder& with_texture(TextureMaterial t) { texture = std::move(t); return *this; }   // model.rs:128-132
     ModelInstance build() {                                             // model.rs:140-144
         auto model = std::make_shared<Model>();
         model->mesh = std::move(mesh);
+        model->texture_ = std::move(texture);
         model->bvh = BvhBuilder().build_for(model->mesh.primitives);
         return model;
     }
@@ -598,6 +631,7 @@ struct ShadingPipeline {
     }
     static ShadingPipeline uv() { ShadingPipeline s{}; s.params.kind = BVHT_SHADE_UV; return s; }
     static ShadingPipeline normal() { ShadingPipeline s{}; s.params.kind = BVHT_SHADE_NORMAL; return s; }   // object0_transform is filled per frame
+    static ShadingPipeline texture() { ShadingPipeline s{}; s.params.kind = BVHT_SHADE_TEXTURE; return s; }  // TextureMaterialAccumulator + RadianceToRgbShader
 };
 
 // renderer.rs:76-102: frame buffer (Rgba<u8>, 4 B/px) + the per-pixel hit records (the GPU's "accumulation buffer")
@@ -677,6 +711,10 @@ public:
                 u->version = m->geometry_version;
                 if (m->normals().size() == m->primitives().size())
                     check(bvht_blas_set_normals(ctx_, u->blas_id, (const float*)m->normals().data(), (uint32_t)m->normals().size()));
+                if (m->tex_coords().size() == m->primitives().size())
+                    check(bvht_blas_set_tex_coords(ctx_, u->blas_id, (const float*)m->tex_coords().data(), (uint32_t)m->tex_coords().size()));
+                if (!m->texture().empty())
+                    check(bvht_blas_set_texture(ctx_, u->blas_id, m->texture().rgb.data(), m->texture().width, m->texture().height));
             } else if (u->version != m->geometry_version || m->refit_requested) {
                 if (u->version != m->geometry_version)
                     check(bvht_blas_update_vertices(ctx_, u->blas_id, (const float*)m->primitives().data(), (uint32_t)m->primitives().size()));

@@ -29,6 +29,20 @@ BVHX_API void* bvhx_mesh_from_triangles(const float* tris, const float* normals_
     }, nullptr);
 }
 BVHX_API const float* bvhx_mesh_normals(void* mesh) { return (const float*)((Mesh*)mesh)->normals.data(); }
+BVHX_API int bvhx_mesh_set_tex_coords(void* mesh, const float* tex_coords, uint32_t n) {
+    return guard([&]() -> int {
+        Mesh* m = (Mesh*)mesh;
+        if (n != m->primitives.size()) throw std::invalid_argument("texture coordinate count differs from the primitive count");
+        m->tex_coords.resize(n);
+        if (n) std::memcpy((void*)m->tex_coords.data(), tex_coords, (size_t)n * sizeof(TextureCoordinates));
+        return 0;
+    }, -1);
+}
+BVHX_API const float* bvhx_mesh_tex_coords(void* mesh, uint32_t* n) {
+    Mesh* m = (Mesh*)mesh;
+    if (n) *n = (uint32_t)m->tex_coords.size();
+    return (const float*)m->tex_coords.data();
+}
 BVHX_API void* bvhx_mesh_from_tri_text(const char* text, size_t len) {
     return guard([&]() -> void* { return new Mesh(TriMeshDecoder::read_mesh(text, len)); }, nullptr);
 }
@@ -42,6 +56,12 @@ BVHX_API void bvhx_mesh_free(void* mesh) { delete (Mesh*)mesh; }
 // ---- models (ModelBuilder::build: BVH build + in-place reorder)
 BVHX_API void* bvhx_model_build(void* mesh) {
     return guard([&]() -> void* { return new ModelInstance(ModelBuilder().with_mesh(*(Mesh*)mesh).build()); }, nullptr);
+}
+BVHX_API void* bvhx_model_build_textured(void* mesh, const uint8_t* rgb, uint32_t width, uint32_t height) {
+    return guard([&]() -> void* {
+        TextureMaterial t(width, height, std::vector<uint8_t>(rgb, rgb + (size_t)width * height * 3));
+        return new ModelInstance(ModelBuilder().with_mesh(*(Mesh*)mesh).with_texture(std::move(t)).build());
+    }, nullptr);
 }
 BVHX_API const void* bvhx_model_nodes(void* model, uint32_t* nodes_used, uint32_t* nodes_len) {
     Model* m = ((ModelInstance*)model)->get();
@@ -150,7 +170,8 @@ BVHX_API void* bvhx_state_new(uint32_t kind, float scale, float offset, const ui
     return guard([&]() -> void* {
         ShadingPipeline s = kind == BVHT_SHADE_DEPTH ? ShadingPipeline::depth(scale, offset)
                           : kind == BVHT_SHADE_INTERSECTION ? ShadingPipeline::intersection(hit, miss)
-                          : kind == BVHT_SHADE_NORMAL ? ShadingPipeline::normal() : ShadingPipeline::uv();
+                          : kind == BVHT_SHADE_NORMAL ? ShadingPipeline::normal()
+                          : kind == BVHT_SHADE_TEXTURE ? ShadingPipeline::texture() : ShadingPipeline::uv();
         return new RendererState(s, width, height, keep_hits != 0);
     }, nullptr);
 }

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BVHT_ABI_VERSION 1
+#define BVHT_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define BVHT_API __attribute__((visibility("default")))
@@ -117,9 +117,11 @@ typedef enum {
     BVHT_SHADE_DEPTH = 1,          /* DepthAccumulator (:184-194) + DepthMappingShader::new(scale, offset) (:207-222) */
     BVHT_SHADE_INTERSECTION = 2,   /* IntersectionAccumulator (:145-153) + IntersectionShader::new(hit, miss) (:166-174) */
     BVHT_SHADE_UV = 3,             /* UvMappingAccumulator (:233-245) + RadianceToRgbShader (:124-132) */
-    BVHT_SHADE_NORMAL = 4          /* NormalMappingAccumulator (:256-286) + RadianceToRgbShader; needs bvht_blas_set_normals for
+    BVHT_SHADE_NORMAL = 4,         /* NormalMappingAccumulator (:256-286) + RadianceToRgbShader; needs bvht_blas_set_normals for
                                       the model of scene object 0 and object0_transform (the reference's instance index is
                                       always 0, so it always looks up object 0's model and transform, :258-276) */
+    BVHT_SHADE_TEXTURE = 5         /* TextureMaterialAccumulator (:289-334) + RadianceToRgbShader; needs bvht_blas_set_tex_coords
+                                      and bvht_blas_set_texture for the model of scene object 0 (instance index always 0) */
 } bvht_shade_kind;
 
 typedef struct {
@@ -171,6 +173,15 @@ BVHT_API int         bvht_blas_destroy(bvht_ctx* ctx, uint32_t blas_id);
  * order -- the reference reorders only the positions when it builds the BVH (bvh.rs:426), and indexes this array with
  * the reordered primitive index (renderer.rs:259-266); that behaviour is kept. */
 BVHT_API int         bvht_blas_set_normals(bvht_ctx* ctx, uint32_t blas_id, const float* normals, uint32_t n_tris);
+
+/* Per-vertex texture coordinates, `Mesh::tex_coords()` (mesh.rs:146-154): n_tris x 6 f32 (three Vector2), ORIGINAL
+ * primitive order like the normals (renderer.rs:311-316 indexes them with the reordered primitive index). */
+BVHT_API int         bvht_blas_set_tex_coords(bvht_ctx* ctx, uint32_t blas_id, const float* tex_coords, uint32_t n_tris);
+
+/* The model's `TextureMaterial<Rgb<u8>>` (materials/material.rs:14-53): width x height texels, 3 bytes each, row-major
+ * with texel (x, y) at (y * width + x) * 3 (texture_buffer.rs:211), already decoded (PNG decoding stays on the host).
+ * Sampling is the reference's nearest-texel rule: ((uv.x * width) as usize) % width, likewise for y (material.rs:44-52). */
+BVHT_API int         bvht_blas_set_texture(bvht_ctx* ctx, uint32_t blas_id, const uint8_t* rgb, uint32_t width, uint32_t height);
 
 /* New vertex positions for an existing model (examples/big_ben_clock.rs:67-96 `animate`); same count. */
 BVHT_API int         bvht_blas_update_vertices(bvht_ctx* ctx, uint32_t blas_id, const float* tris, uint32_t n_tris);

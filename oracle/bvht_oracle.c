@@ -1047,6 +1047,38 @@ int64_t orc_parse_obj_normals(const char* text, size_t len, float** out) {
     return (int64_t)(res.n / 9);
 }
 
+/* Rust `f32 as usize` on a 64-bit target: saturating, NaN -> 0 */
+static uint64_t f32_as_usize(float x) {
+    if (!(x > 0.0f)) return 0u;
+    if (x >= 18446744073709551616.0f) return UINT64_MAX;
+    return (uint64_t)x;
+}
+
+void orc_shade_texture(const float* tex_coords, uint64_t n_prims, const uint8_t* texels, uint32_t tex_w, uint32_t tex_h,
+                       const orc_hit* hits, uint64_t n, uint32_t* rgba_out) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const orc_hit* h = &hits[i];
+        float r[3] = { 0.0f, 0.0f, 0.0f };                  /* miss: Vector3::zero() (renderer.rs:331) */
+        if (h->id != 0xFFFFFFFFu) {
+            uint32_t prim = h->id & 0x000FFFFFu;            /* instance index is always 0: object 0's model (renderer.rs:309-316) */
+            if (prim < n_prims && tex_w && tex_h) {
+                const float* tc = tex_coords + (size_t)prim * 6;
+                float w0 = (1.0f - h->u) - h->v;
+                float uvx = (tc[0] * w0 + tc[2] * h->u) + tc[4] * h->v;      /* renderer.rs:320 */
+                float uvy = (tc[1] * w0 + tc[3] * h->u) + tc[5] * h->v;
+                uint64_t iu = f32_as_usize(uvx * (float)tex_w) % tex_w;      /* material.rs:45-48 */
+                uint64_t iv = f32_as_usize(uvy * (float)tex_h) % tex_h;
+                const uint8_t* px = texels + ((size_t)iv * tex_w + iu) * 3;
+                const float s = 1.0f / 256.0f;                               /* renderer.rs:299-306 */
+                for (int k = 0; k < 3; ++k) r[k] = (float)px[k] * s;
+            }
+        }
+        uint32_t c[3];
+        for (int k = 0; k < 3; ++k) { c[k] = f32_as_u8(255.0f * r[k]); if (c[k] > 255) c[k] = 255; }
+        rgba_out[i] = c[0] | (c[1] << 8) | (c[2] << 16) | 0xFF000000u;
+    }
+}
+
 void orc_shade_normal(const float* normals, uint64_t n_prims, const float m[16], const orc_hit* hits, uint64_t n, uint32_t* rgba_out) {
     for (uint64_t i = 0; i < n; ++i) {
         const orc_hit* h = &hits[i];

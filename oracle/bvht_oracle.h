@@ -170,6 +170,12 @@ void orc_shade(uint32_t kind, float scale, float offset, uint32_t hit_rgba, uint
 void orc_shade_normal(const float* normals, uint64_t n_prims, const float object0_transform[16],
                       const orc_hit* hits, uint64_t n, uint32_t* rgba_out);
 
+/* kind 5: TextureMaterialAccumulator (renderer.rs:289-334) + TextureMaterial::evaluate (materials/material.rs:44-52) +
+ * RadianceToRgbShader (:124-132).  tex_coords = UN-reordered per-vertex coordinates of scene object 0's model (n_prims x 6
+ * floats), texels = that model's Rgb<u8> texture (texel (x, y) at (y * width + x) * 3, texture_buffer.rs:211). */
+void orc_shade_texture(const float* tex_coords, uint64_t n_prims, const uint8_t* texels, uint32_t tex_w, uint32_t tex_h,
+                       const orc_hit* hits, uint64_t n, uint32_t* rgba_out);
+
 int  orc_max_threads(void);
 
 #ifdef __cplusplus

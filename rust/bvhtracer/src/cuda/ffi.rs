@@ -12,6 +12,7 @@ pub const BVHT_SHADE_DEPTH: u32 = 1;
 pub const BVHT_SHADE_INTERSECTION: u32 = 2;
 pub const BVHT_SHADE_UV: u32 = 3;
 pub const BVHT_SHADE_NORMAL: u32 = 4;
+pub const BVHT_SHADE_TEXTURE: u32 = 5;
 
 pub enum BvhtCtx {}
 
@@ -47,6 +48,8 @@ impl BvhtShade {
     pub fn uv() -> Self { Self::base(BVHT_SHADE_UV) }
     /// `NormalMappingAccumulator` + `RadianceToRgbShader` (object0_transform is filled per frame)
     pub fn normal() -> Self { Self::base(BVHT_SHADE_NORMAL) }
+    /// `TextureMaterialAccumulator` + `RadianceToRgbShader` (needs tex coords + texture of scene object 0's model)
+    pub fn texture() -> Self { Self::base(BVHT_SHADE_TEXTURE) }
 }
 
 extern "C" {
@@ -57,6 +60,8 @@ extern "C" {
     pub fn bvht_status_string(status: c_int) -> *const c_char;
     pub fn bvht_blas_create(ctx: *mut BvhtCtx, tris: *const f32, n_tris: u32, nodes: *const BvhtBvhNode, nodes_used: u32, out_id: *mut u32) -> c_int;
     pub fn bvht_blas_set_normals(ctx: *mut BvhtCtx, id: u32, normals: *const f32, n_tris: u32) -> c_int;
+    pub fn bvht_blas_set_tex_coords(ctx: *mut BvhtCtx, id: u32, tex_coords: *const f32, n_tris: u32) -> c_int;
+    pub fn bvht_blas_set_texture(ctx: *mut BvhtCtx, id: u32, rgb: *const u8, width: u32, height: u32) -> c_int;
     pub fn bvht_blas_update_vertices(ctx: *mut BvhtCtx, id: u32, tris: *const f32, n_tris: u32) -> c_int;
     pub fn bvht_blas_refit(ctx: *mut BvhtCtx, id: u32) -> c_int;
     pub fn bvht_blas_read_nodes(ctx: *mut BvhtCtx, id: u32, out: *mut BvhtBvhNode, max_nodes: u32) -> c_int;

@@ -61,6 +61,14 @@ impl CudaPathTracer {
         if normals.len() == tris.len() {
             self.check(unsafe { bvht_blas_set_normals(self.ctx, id, normals.as_ptr() as *const f32, normals.len() as u32) });
         }
+        let tex_coords = model.mesh().tex_coords();            // &[TextureCoordinates<f32, 3>], 24 B each, never reordered
+        if tex_coords.len() == tris.len() {
+            self.check(unsafe { bvht_blas_set_tex_coords(self.ctx, id, tex_coords.as_ptr() as *const f32, tex_coords.len() as u32) });
+        }
+        let texture = model.texture().texture();               // TextureBuffer2D<Rgb<u8>, Vec<u8>> (needs a read accessor, material.rs:14-16)
+        if texture.width() > 0 && texture.height() > 0 {
+            self.check(unsafe { bvht_blas_set_texture(self.ctx, id, texture.as_bytes().as_ptr(), texture.width() as u32, texture.height() as u32) });
+        }
         self.uploaded.push(Uploaded { model: key, blas_id: id, vertex_version: 0 });
         id
     }

@@ -356,3 +356,14 @@ def shade_normal(normals, object0_transform, hits):
     out = np.zeros(hits.size, "<u4")
     lib().orc_shade_normal(_p(normals), C.c_uint64(normals.shape[0]), _p(m), _p(hits), C.c_uint64(hits.size), _p(out))
     return out
+
+
+def shade_texture(tex_coords, texels, hits):
+    """TextureMaterialAccumulator + RadianceToRgbShader (renderer.rs:289-334, 124-132); texels[height, width, 3] u8."""
+    tex_coords = np.ascontiguousarray(np.asarray(tex_coords, np.float32).reshape(-1, 6))
+    texels = np.ascontiguousarray(np.asarray(texels, np.uint8))
+    hits = np.ascontiguousarray(hits)
+    out = np.zeros(hits.size, "<u4")
+    lib().orc_shade_texture(_p(tex_coords), C.c_uint64(tex_coords.shape[0]), _p(texels), C.c_uint32(texels.shape[1]),
+                            C.c_uint32(texels.shape[0]), _p(hits), C.c_uint64(hits.size), _p(out))
+    return out

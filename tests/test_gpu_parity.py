@@ -579,6 +579,86 @@ def test_normal_mapping_shader_matches_oracle(name, arg, asset):
     assert len(np.unique(frame)) >= 2
 
 
+def test_texture_material_shader_matches_oracle():
+    # quad.rs main: TextureMaterialAccumulator + RadianceToRgbShader.  Nearest-texel lookup with Rust's saturating
+    # `as usize` and `% size` (material.rs:44-52), instance index always 0 (renderer.rs:309-327).
+    w, h = 320, 320
+    tex = examples.brick_texture(96, 64)
+    for frame in (0, 17):
+        spec = examples.quad_example(frame)
+        scene, cam = SB.oracle_scene(spec)
+        ref_hits = scene.render(cam, w, h, threads=NTHREADS)
+        for tc in (examples.QUAD_TEX_COORDS, (examples.QUAD_TEX_COORDS * F(3.7) - F(1.2)).astype(F)):   # also wrap + negative
+            ref = O.shade_texture(tc, tex, ref_hits)
+            with Engine(flags=FLAG_STRICT | FLAG_LEAF_ACCEL) as eng:
+                ids = SB.upload_scene(eng, scene)
+                with pytest.raises(BvhtError):                           # nothing uploaded yet
+                    eng.render_frame(SB.to_ffi_camera(cam), w, h, eng.shade_texture())
+                eng.blas_set_tex_coords(ids[0], tc)
+                with pytest.raises(BvhtError):                           # coordinates but no texture
+                    eng.render_frame(SB.to_ffi_camera(cam), w, h, eng.shade_texture())
+                with pytest.raises(BvhtError):                           # `% 0` in the reference
+                    eng.blas_set_texture(ids[0], np.zeros((0, 4, 3), np.uint8))
+                eng.blas_set_texture(ids[0], tex)
+                frame_px, hits = eng.render_frame(SB.to_ffi_camera(cam), w, h, eng.shade_texture(), want_hits=True)
+            assert hits.tobytes() == ref_hits.tobytes()
+            assert frame_px.tobytes() == ref.tobytes()
+            assert len(np.unique(frame_px)) > 50
+
+
+@pytest.mark.parametrize("flags", [FLAG_STRICT | FLAG_LEAF_ACCEL, FLAG_FAST | FLAG_LEAF_ACCEL], ids=["strict", "fast"])
+def test_texture_material_many_instances_use_object0(flags):
+    # sixteen teapots, random per-vertex coordinates incl. huge ones (usize saturation): every instance's hits index object 0's
+    # coordinate array and texture.  Fast mode: pixels are identical wherever the hit record is.
+    spec = examples.trippy_teapots(4)
+    scene, cam = SB.oracle_scene(spec)
+    rng = np.random.default_rng(11)
+    n_tris = scene.blases[0].tris.shape[0]
+    tc = rng.uniform(-2, 5, (n_tris, 6)).astype(F)
+    tc[::37] *= F(1e24)
+    tex = rng.integers(0, 256, (33, 129, 3)).astype(np.uint8)
+    w, h = 400, 224
+    ref_hits = scene.render(cam, w, h, threads=NTHREADS)
+    with Engine(flags=flags) as eng:
+        ids = SB.upload_scene(eng, scene)
+        eng.blas_set_tex_coords(ids[0], tc)
+        eng.blas_set_texture(ids[0], tex)
+        frame_px, hits = eng.render_frame(SB.to_ffi_camera(cam), w, h, eng.shade_texture(), want_hits=True)
+    if flags & FLAG_FAST:
+        assert frame_px.tobytes() == O.shade_texture(tc, tex, hits).tobytes()        # shading is exact given the record
+        assert (hits["id"] == ref_hits["id"]).mean() >= 0.9999
+    else:
+        assert hits.tobytes() == ref_hits.tobytes()
+        assert frame_px.tobytes() == O.shade_texture(tc, tex, ref_hits).tobytes()
+    assert (ref_hits["id"] != O.MISS_ID).mean() > 0.05
+
+
+def test_host_mirror_textured_quad_example():
+    # quad.rs: MeshBuilder::with_primitive(tri, tex_coords, normals), ModelBuilder::with_texture, TextureMaterialAccumulator +
+    # RadianceToRgbShader through Renderer::render, several frames of the spinning quad
+    from bvhtracer_b200 import host
+    tex = examples.brick_texture(128, 128)
+    mesh = host.Mesh.from_triangles(examples.QUAD_TRIS, examples.QUAD_NORMALS).set_tex_coords(examples.QUAD_TEX_COORDS)
+    model = host.ModelBuilder().with_mesh(mesh).with_texture(tex).build()
+    renderer = host.Renderer(flags=FLAG_STRICT | FLAG_LEAF_ACCEL)
+    w, h = 256, 256
+    state = host.RendererState(host.texture_pipeline(), w, h, keep_hits=True)
+    scene = None
+    for frame in (0, 3, 41):
+        spec = examples.quad_example(frame)
+        if scene is None:
+            scene, _ = host.build_scene(spec, models=[model])
+        else:
+            scene.set_transform(0, host.object_transform(spec.objects[0]))
+            scene.rebuild()
+        renderer.render(state, scene)
+        ref_scene, ref_cam = SB.oracle_scene(spec)
+        ref_hits = ref_scene.render(ref_cam, w, h, threads=NTHREADS)
+        assert state.hits().tobytes() == ref_hits.tobytes()
+        assert state.frame_buffer().tobytes() == O.shade_texture(examples.QUAD_TEX_COORDS, tex, ref_hits).tobytes()
+        assert (ref_hits["id"] != O.MISS_ID).mean() > 0.2
+
+
 def test_host_mirror_normal_mapping_example():
     # trippy_teapots.rs main: NormalMappingAccumulator + RadianceToRgbShader through Renderer::render
     from bvhtracer_b200 import host

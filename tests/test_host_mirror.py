@@ -92,3 +92,24 @@ def test_decoder_normals_match_oracle():
     assert m.primitives().tobytes() == O.parse_obj(obj).tobytes()
     assert m.normals()[0].tolist() == [0, 0, 1, np.float32(0.6), 0, np.float32(0.8), 0, 0, 1]
     assert not m.normals()[2:].any()                     # faces without vn get zero normals (decoders.rs:176-181)
+
+
+def test_decoder_texture_coordinates_and_mesh_builder():
+    # decoders.rs:182-203: v/vt/vn and v/vt corners carry (vt.u, vt.v) as f32, the others Vector2::zero(); a fan keeps them
+    obj = ("g q\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0.25 0.75\nvt 1 0.3333333333 0\nvt -2 5\nvn 0 0 1\n"
+           "f 1/1/1 2/2/1 3/3/1\nf 1/3 3/1 4/2\nf 1//1 2//1 3//1\nf 1/1 2/2 3/3 4/-1\n")
+    m = host.ObjMeshDecoder(obj).read_mesh()
+    tc = m.tex_coords()
+    third = np.float32(0.3333333333)
+    assert tc.shape == (5, 6)
+    assert tc[0].tolist() == [0.25, 0.75, 1, third, -2, 5]
+    assert tc[1].tolist() == [-2, 5, 0.25, 0.75, 1, third]
+    assert not tc[2].any()
+    assert tc[3].tolist() == [0.25, 0.75, 1, third, -2, 5] and tc[4].tolist() == [0.25, 0.75, -2, 5, -2, 5]
+    # MeshBuilder::with_primitive(triangle, tex_coords, normals) (mesh.rs:189-198) through the flat API
+    mesh = host.Mesh.from_triangles(examples.QUAD_TRIS, examples.QUAD_NORMALS).set_tex_coords(examples.QUAD_TEX_COORDS)
+    assert mesh.tex_coords().tobytes() == examples.QUAD_TEX_COORDS.tobytes()
+    with pytest.raises(host.HostError):
+        host.Mesh.from_triangles(examples.QUAD_TRIS).set_tex_coords(np.zeros((3, 6), np.float32))
+    model = host.ModelBuilder().with_mesh(mesh).with_texture(examples.brick_texture(8, 4)).build()
+    assert model.primitives().shape == (2, 9)

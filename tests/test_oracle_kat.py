@@ -399,3 +399,47 @@ def test_tri_decoder_normals_kat():
     expected = np.array([-0.86602545, 0.49999988, -1.7462564e-7], np.float32)
     for v in range(3):
         assert n[1, 3 * v:3 * v + 3].tobytes() == expected.tobytes()
+
+
+def test_texture_accumulator_restatement():
+    # renderer.rs:297-333 + materials/material.rs:44-52, restated independently in numpy: barycentric mix of the three
+    # coordinates, `as usize` (saturating; negative -> 0) then `% size`, texel * (1 / 256), RadianceToRgbShader.
+    rng = np.random.default_rng(3)
+    n_prims, tw, th = 5, 7, 4
+    tc = rng.uniform(-1.5, 3.0, (n_prims, 6)).astype(np.float32)
+    tc[4] = [1e25, 0.5, 1e25, 0.5, 1e25, 0.5]                     # uv.x * width >= 2^64: usize::MAX % width
+    tex = rng.integers(0, 256, (th, tw, 3)).astype(np.uint8)
+    n = 400
+    hits = np.zeros(n, O.HIT)
+    hits["u"] = rng.uniform(0, 1, n).astype(np.float32)
+    hits["v"] = (rng.uniform(0, 1, n) * (1 - hits["u"])).astype(np.float32)
+    hits["t"] = 1.0
+    hits["id"] = rng.integers(0, n_prims, n).astype(np.uint32) | (rng.integers(0, 3, n).astype(np.uint32) << 20)
+    hits["id"][::9] = O.MISS_ID
+    hits["id"][5] = 77                                            # primitive index past object 0's mesh: black here, a panic there
+    got = O.shade_texture(tc, tex, hits)
+    F = np.float32
+    for i in range(n):
+        rgb = (0, 0, 0)
+        prim = int(hits["id"][i]) & 0xFFFFF
+        if hits["id"][i] != O.MISS_ID and prim < n_prims:
+            u, v = F(hits["u"][i]), F(hits["v"][i])
+            w0 = F(F(1) - u) - v
+            idx = []
+            for k, size in ((0, tw), (1, th)):
+                with np.errstate(over="ignore"):
+                    c = F(F(F(tc[prim, k] * w0) + F(tc[prim, 2 + k] * u)) + F(tc[prim, 4 + k] * v))
+                    x = float(F(c * F(size)))
+                xi = 0 if not x > 0 else (2 ** 64 - 1 if x >= 2.0 ** 64 else int(x))
+                idx.append(xi % size)
+            px = tex[idx[1], idx[0]]
+            rgb = tuple(int(F(255) * F(F(p) * F(1 / 256))) for p in px)
+        exp = rgb[0] | (rgb[1] << 8) | (rgb[2] << 16) | 0xFF000000
+        assert got[i] == exp, (i, hex(got[i]), hex(exp))
+    assert len(np.unique(got)) > 10
+    # whole-texel identity: a quad with uv == barycentric position reads texel (x, y) back as floor(255 * p / 256)
+    one = np.zeros(1, O.HIT); one["u"] = 0.0; one["v"] = 0.0; one["id"] = 0; one["t"] = 1.0
+    tc0 = np.zeros((1, 6), np.float32); tc0[0, 0:2] = [(3 + 0.5) / tw, (2 + 0.5) / th]
+    px = tex[2, 3].astype(int)
+    exp = sum(int(255 * p / 256) << (8 * k) for k, p in enumerate(px)) | 0xFF000000
+    assert O.shade_texture(tc0, tex, one)[0] == exp
