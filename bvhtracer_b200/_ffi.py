@@ -47,7 +47,7 @@ class Stats(C.Structure):
     _fields_ = [("last_trace_ms", C.c_float), ("last_refit_ms", C.c_float), ("last_upload_ms", C.c_float),
                 ("last_trace_rays", C.c_uint64), ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("sm_count", C.c_uint32), ("trace_grid", C.c_uint32),
-                ("trace_block", C.c_uint32), ("flags", C.c_uint32)]
+                ("trace_block", C.c_uint32), ("flags", C.c_uint32), ("last_build_ms", C.c_float), ("last_build_levels", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -66,6 +66,11 @@ SYMBOLS = [
     ("bvht_sync", C.c_int, [_P]),
     ("bvht_blas_create", C.c_int, [_P, _P, C.c_uint32, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     ("bvht_blas_destroy", C.c_int, [_P, C.c_uint32]),
+    ("bvht_blas_build", C.c_int, [_P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
+    ("bvht_blas_rebuild", C.c_int, [_P, C.c_uint32]),
+    ("bvht_blas_info", C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    ("bvht_blas_read_triangles", C.c_int, [_P, C.c_uint32, _P, C.c_uint32]),
+    ("bvht_blas_read_permutation", C.c_int, [_P, C.c_uint32, _P, C.c_uint32]),
     ("bvht_blas_set_normals", C.c_int, [_P, C.c_uint32, _P, C.c_uint32]),
     ("bvht_blas_set_tex_coords", C.c_int, [_P, C.c_uint32, _P, C.c_uint32]),
     ("bvht_blas_set_texture", C.c_int, [_P, C.c_uint32, _P, C.c_uint32, C.c_uint32]),

@@ -21,6 +21,7 @@
 #include "device_types.cuh"
 #include "launchers.hpp"
 #include "leaf_accel.hpp"
+#include "build_device.hpp"
 
 using namespace bvht;
 
@@ -40,6 +41,7 @@ struct Blas {
     uint32_t n_tris = 0, nodes_used = 0;
     std::vector<bvht_bvh_node> h_nodes;     // host copy of the uploaded node pool (topology for validation / accel)
     std::vector<float> h_tris;              // host copy of the vertices (needed to rebuild the leaf accelerator)
+    std::vector<uint32_t> perm;             // device-built models: perm[i] = index, in the caller's array, of the triangle at i
     DevBuf tris_aos, nodes, tri, normals;      // normals: 3 float4 per primitive, ORIGINAL primitive order
     DevBuf tex_coords, texels;                 // 3 float2 per primitive (ORIGINAL order); Rgb<u8> texture, row-major
     uint32_t tex_w = 0, tex_h = 0;
@@ -82,6 +84,8 @@ struct bvht_ctx {
     std::vector<float> inst_tight;                    // 6 floats per instance (world lo/hi) or lo > hi when unusable
     double bake_center[3] = { 0.0, 0.0, 0.0 };        // camera origin the tight TLAS boxes' origin limit is centred on
     DevBuf work_counter;
+    BuildWorkspace build_ws;                   // K3 scratch (grow-only)
+    DevBuf build_tris, build_perm;             // K3 input/output: triangles reordered in place + the permutation
     DevBuf out_buf, rays_buf, rgba_buf;               // device staging for the host-pointer entry points
     cudaStream_t aux[2] = { nullptr, nullptr };       // band pipelining: two compute streams + one copy stream
     cudaStream_t copy_stream = nullptr;
@@ -618,6 +622,110 @@ int persistent_grid(bvht_ctx* ctx, bool primary, uint64_t n_items) {
     return (int)grid;
 }
 
+// Shared by bvht_blas_create (host-built tree) and bvht_blas_build / bvht_blas_rebuild (device-built tree).
+int make_blas(bvht_ctx* ctx, const float* tris, uint32_t n_tris, const bvht_bvh_node* nodes, uint32_t nodes_used, Blas& b) {
+    if (n_tris == 0) return fail(ctx, BVHT_ERR_INVALID_ARG, "empty model (the reference indexes nodes[0] of an empty pool and panics)");
+    if (n_tris > 0x000FFFFFu + 1u)
+        return fail(ctx, BVHT_ERR_INVALID_ARG, "n_tris = %u exceeds the 20-bit primitive index of InstancePrimitiveIndex", n_tris);
+    cudaSetDevice(ctx->device);
+    std::vector<uint32_t> parent;
+    uint32_t depth = 0;
+    int rc = validate_bvh(ctx, nodes, nodes_used, n_tris, parent, depth);
+    if (rc) return rc;
+
+    cudaEventRecord(ctx->ev_e, ctx->stream);
+    b = Blas();
+    b.alive = true; b.n_tris = n_tris; b.nodes_used = nodes_used;
+    b.h_nodes.assign(nodes, nodes + nodes_used);
+
+    // node pool: 2 float4 per node = {min.xyz, left_first}, {max.xyz, prim_count}
+    std::vector<float> flat((size_t)nodes_used * 8);
+    for (uint32_t i = 0; i < nodes_used; ++i) {
+        float* f = &flat[(size_t)i * 8];
+        memcpy(f + 0, nodes[i].aabb_min, 12); memcpy(f + 3, &nodes[i].left_first, 4);
+        memcpy(f + 4, nodes[i].aabb_max, 12); memcpy(f + 7, &nodes[i].prim_count, 4);
+    }
+    auto bail = [&](int code) { free_blas(b); return code; };
+    if ((rc = ensure(ctx, b.nodes, flat.size() * 4))) return bail(rc);
+    if ((rc = h2d(ctx, b.nodes.p, flat.data(), flat.size() * 4))) return bail(rc);
+    if ((rc = upload_vertices(ctx, b, tris))) return bail(rc);
+
+    // refit plan: leaves cut into chunks, parent links, arrival counters
+    std::vector<uint32_t> chunk_leaf, chunk_first, chunk_count, leaf_chunks(nodes_used, 0);
+    for (uint32_t i = 0; i < nodes_used; ++i) {
+        if (i == 1 || nodes[i].prim_count == 0) continue;
+        if (i != 0 && parent[i] == kNone) continue;                  // unreachable node
+        uint32_t first = nodes[i].left_first, left = nodes[i].prim_count;
+        while (left > 0) {
+            uint32_t c = std::min(left, kRefitChunkTris);
+            chunk_leaf.push_back(i); chunk_first.push_back(first); chunk_count.push_back(c);
+            leaf_chunks[i]++; first += c; left -= c;
+        }
+    }
+    b.n_chunks = (uint32_t)chunk_leaf.size();
+    if ((rc = upload_u32(ctx, b.chunk_leaf, chunk_leaf))) return bail(rc);
+    if ((rc = upload_u32(ctx, b.chunk_first, chunk_first))) return bail(rc);
+    if ((rc = upload_u32(ctx, b.chunk_count, chunk_count))) return bail(rc);
+    if ((rc = upload_u32(ctx, b.leaf_chunks, leaf_chunks))) return bail(rc);
+    if ((rc = upload_u32(ctx, b.parent, parent))) return bail(rc);
+    if ((rc = ensure(ctx, b.scratch, (size_t)nodes_used * 24))) return bail(rc);
+    if ((rc = ensure(ctx, b.counters, (size_t)nodes_used * 4))) return bail(rc);
+
+    if (accel_on(ctx)) { if ((rc = build_and_upload_accel(ctx, b))) return bail(rc); }
+
+    cudaEventRecord(ctx->ev_f, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { fail(ctx, BVHT_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e)); return bail(BVHT_ERR_CUDA); }
+    cudaEventElapsedTime(&ctx->stats.last_upload_ms, ctx->ev_e, ctx->ev_f);
+
+    return BVHT_OK;
+}
+
+
+uint32_t store_blas(bvht_ctx* ctx, Blas&& b) {
+    uint32_t id = kNone;
+    for (uint32_t i = 0; i < ctx->blas.size(); ++i) if (!ctx->blas[i].alive) { id = i; break; }
+    if (id == kNone) { id = (uint32_t)ctx->blas.size(); ctx->blas.emplace_back(); }
+    ctx->blas[id] = std::move(b);
+    ctx->blas_desc_dirty = true;
+    return id;
+}
+
+// BvhBuilder::build_for on the device (build_kernels.cu): upload, build, bring the small results back.
+int device_build(bvht_ctx* ctx, const float* tris_host, uint32_t n_tris, std::vector<float>& tris_out, std::vector<bvht_bvh_node>& nodes_out,
+                 std::vector<uint32_t>* perm_out) {
+    if (n_tris == 0) return fail(ctx, BVHT_ERR_INVALID_ARG, "empty model (the reference indexes nodes[0] of an empty pool and panics)");
+    if (n_tris > 0x000FFFFFu + 1u)
+        return fail(ctx, BVHT_ERR_INVALID_ARG, "n_tris = %u exceeds the 20-bit primitive index of InstancePrimitiveIndex", n_tris);
+    cudaSetDevice(ctx->device);
+    int rc;
+    if ((rc = ensure(ctx, ctx->build_tris, (size_t)n_tris * 36))) return rc;
+    if ((rc = ensure(ctx, ctx->build_perm, (size_t)n_tris * 4))) return rc;
+    cudaEventRecord(ctx->ev_e, ctx->stream);
+    if ((rc = h2d(ctx, ctx->build_tris.p, tris_host, (size_t)n_tris * 36))) return rc;
+    std::vector<BuildNodeHost> nodes;
+    DeviceBuildStats bs;
+    cudaError_t e = device_build_reference_bvh(ctx->build_ws, (float*)ctx->build_tris.p, (uint32_t*)ctx->build_perm.p, n_tris, ctx->stream,
+                                               nodes, &bs);
+    if (e != cudaSuccess) return fail(ctx, BVHT_ERR_CUDA, "device BVH build failed: %s", cudaGetErrorString(e));
+    ctx->stats.kernel_launches += bs.launches;
+    tris_out.resize((size_t)n_tris * 9);
+    CU(ctx, cudaMemcpyAsync(tris_out.data(), ctx->build_tris.p, (size_t)n_tris * 36, cudaMemcpyDeviceToHost, ctx->stream));
+    if (perm_out) {
+        perm_out->resize(n_tris);
+        CU(ctx, cudaMemcpyAsync(perm_out->data(), ctx->build_perm.p, (size_t)n_tris * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    cudaEventRecord(ctx->ev_f, ctx->stream);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += (uint64_t)n_tris * (perm_out ? 40 : 36);
+    cudaEventElapsedTime(&ctx->stats.last_build_ms, ctx->ev_e, ctx->ev_f);
+    ctx->stats.last_build_levels = bs.levels;
+    nodes_out.resize(nodes.size());
+    static_assert(sizeof(BuildNodeHost) == sizeof(bvht_bvh_node), "node layouts must agree");
+    memcpy(nodes_out.data(), nodes.data(), nodes.size() * sizeof(bvht_bvh_node));
+    return BVHT_OK;
+}
+
 } // namespace
 
 // ------------------------------------------------------------------------------------------------------
@@ -722,66 +830,66 @@ int bvht_blas_create(bvht_ctx* ctx, const float* tris, uint32_t n_tris, const bv
                      uint32_t* out_blas_id) {
     if (!ctx) return BVHT_ERR_BAD_HANDLE;
     if (!nodes || !out_blas_id || (n_tris > 0 && !tris)) return fail(ctx, BVHT_ERR_INVALID_ARG, "null pointer argument");
-    if (n_tris == 0) return fail(ctx, BVHT_ERR_INVALID_ARG, "empty model (the reference indexes nodes[0] of an empty pool and panics)");
-    if (n_tris > 0x000FFFFFu + 1u)
-        return fail(ctx, BVHT_ERR_INVALID_ARG, "n_tris = %u exceeds the 20-bit primitive index of InstancePrimitiveIndex", n_tris);
-    cudaSetDevice(ctx->device);
-    std::vector<uint32_t> parent;
-    uint32_t depth = 0;
-    int rc = validate_bvh(ctx, nodes, nodes_used, n_tris, parent, depth);
-    if (rc) return rc;
-
-    cudaEventRecord(ctx->ev_e, ctx->stream);
     Blas b;
-    b.alive = true; b.n_tris = n_tris; b.nodes_used = nodes_used;
-    b.h_nodes.assign(nodes, nodes + nodes_used);
+    int rc = make_blas(ctx, tris, n_tris, nodes, nodes_used, b);
+    if (rc) return rc;
+    *out_blas_id = store_blas(ctx, std::move(b));
+    return BVHT_OK;
+}
 
-    // node pool: 2 float4 per node = {min.xyz, left_first}, {max.xyz, prim_count}
-    std::vector<float> flat((size_t)nodes_used * 8);
-    for (uint32_t i = 0; i < nodes_used; ++i) {
-        float* f = &flat[(size_t)i * 8];
-        memcpy(f + 0, nodes[i].aabb_min, 12); memcpy(f + 3, &nodes[i].left_first, 4);
-        memcpy(f + 4, nodes[i].aabb_max, 12); memcpy(f + 7, &nodes[i].prim_count, 4);
-    }
-    auto bail = [&](int code) { free_blas(b); return code; };
-    if ((rc = ensure(ctx, b.nodes, flat.size() * 4))) return bail(rc);
-    if ((rc = h2d(ctx, b.nodes.p, flat.data(), flat.size() * 4))) return bail(rc);
-    if ((rc = upload_vertices(ctx, b, tris))) return bail(rc);
+int bvht_blas_build(bvht_ctx* ctx, const float* tris, uint32_t n_tris, uint32_t* out_blas_id) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (!out_blas_id || (n_tris > 0 && !tris)) return fail(ctx, BVHT_ERR_INVALID_ARG, "null pointer argument");
+    std::vector<float> reordered; std::vector<bvht_bvh_node> nodes; std::vector<uint32_t> perm;
+    int rc = device_build(ctx, tris, n_tris, reordered, nodes, &perm);
+    if (rc) return rc;
+    Blas b;
+    if ((rc = make_blas(ctx, reordered.data(), n_tris, nodes.data(), (uint32_t)nodes.size(), b))) return rc;
+    b.perm = std::move(perm);
+    *out_blas_id = store_blas(ctx, std::move(b));
+    return BVHT_OK;
+}
 
-    // refit plan: leaves cut into chunks, parent links, arrival counters
-    std::vector<uint32_t> chunk_leaf, chunk_first, chunk_count, leaf_chunks(nodes_used, 0);
-    for (uint32_t i = 0; i < nodes_used; ++i) {
-        if (i == 1 || nodes[i].prim_count == 0) continue;
-        if (i != 0 && parent[i] == kNone) continue;                  // unreachable node
-        uint32_t first = nodes[i].left_first, left = nodes[i].prim_count;
-        while (left > 0) {
-            uint32_t c = std::min(left, kRefitChunkTris);
-            chunk_leaf.push_back(i); chunk_first.push_back(first); chunk_count.push_back(c);
-            leaf_chunks[i]++; first += c; left -= c;
-        }
-    }
-    b.n_chunks = (uint32_t)chunk_leaf.size();
-    if ((rc = upload_u32(ctx, b.chunk_leaf, chunk_leaf))) return bail(rc);
-    if ((rc = upload_u32(ctx, b.chunk_first, chunk_first))) return bail(rc);
-    if ((rc = upload_u32(ctx, b.chunk_count, chunk_count))) return bail(rc);
-    if ((rc = upload_u32(ctx, b.leaf_chunks, leaf_chunks))) return bail(rc);
-    if ((rc = upload_u32(ctx, b.parent, parent))) return bail(rc);
-    if ((rc = ensure(ctx, b.scratch, (size_t)nodes_used * 24))) return bail(rc);
-    if ((rc = ensure(ctx, b.counters, (size_t)nodes_used * 4))) return bail(rc);
-
-    if (accel_on(ctx)) { if ((rc = build_and_upload_accel(ctx, b))) return bail(rc); }
-
-    cudaEventRecord(ctx->ev_f, ctx->stream);
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) { fail(ctx, BVHT_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e)); return bail(BVHT_ERR_CUDA); }
-    cudaEventElapsedTime(&ctx->stats.last_upload_ms, ctx->ev_e, ctx->ev_f);
-
-    uint32_t id = kNone;
-    for (uint32_t i = 0; i < ctx->blas.size(); ++i) if (!ctx->blas[i].alive) { id = i; break; }
-    if (id == kNone) { id = (uint32_t)ctx->blas.size(); ctx->blas.emplace_back(); }
-    ctx->blas[id] = std::move(b);
+int bvht_blas_rebuild(bvht_ctx* ctx, uint32_t blas_id) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (blas_id >= ctx->blas.size() || !ctx->blas[blas_id].alive) return fail(ctx, BVHT_ERR_BAD_HANDLE, "unknown blas id %u", blas_id);
+    Blas& old = ctx->blas[blas_id];
+    std::vector<float> reordered; std::vector<bvht_bvh_node> nodes; std::vector<uint32_t> perm;
+    int rc = device_build(ctx, old.h_tris.data(), old.n_tris, reordered, nodes, &perm);
+    if (rc) return rc;
+    Blas b;
+    if ((rc = make_blas(ctx, reordered.data(), old.n_tris, nodes.data(), (uint32_t)nodes.size(), b))) return rc;
+    // positions were permuted again; normals / texture coordinates / texture are never reordered (bvh.rs:426) and stay
+    std::swap(b.normals, old.normals); std::swap(b.tex_coords, old.tex_coords); std::swap(b.texels, old.texels);
+    b.tex_w = old.tex_w; b.tex_h = old.tex_h;
+    if (!old.perm.empty()) { for (uint32_t& p : perm) p = old.perm[p]; }       // compose with the earlier permutation
+    b.perm = std::move(perm);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    free_blas(old);
+    ctx->blas[blas_id] = std::move(b);
     ctx->blas_desc_dirty = true;
-    *out_blas_id = id;
+    if (accel_on(ctx) && !ctx->h_inst.empty()) return recompute_tlas_tight(ctx);
+    return BVHT_OK;
+}
+
+int bvht_blas_read_triangles(bvht_ctx* ctx, uint32_t blas_id, float* out, uint32_t n_tris) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (blas_id >= ctx->blas.size() || !ctx->blas[blas_id].alive) return fail(ctx, BVHT_ERR_BAD_HANDLE, "unknown blas id %u", blas_id);
+    const Blas& b = ctx->blas[blas_id];
+    if (!out) return fail(ctx, BVHT_ERR_INVALID_ARG, "null output pointer");
+    if (n_tris != b.n_tris) return fail(ctx, BVHT_ERR_INVALID_ARG, "buffer for %u triangles, model has %u", n_tris, b.n_tris);
+    memcpy(out, b.h_tris.data(), (size_t)n_tris * 36);
+    return BVHT_OK;
+}
+
+int bvht_blas_read_permutation(bvht_ctx* ctx, uint32_t blas_id, uint32_t* out, uint32_t n_tris) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (blas_id >= ctx->blas.size() || !ctx->blas[blas_id].alive) return fail(ctx, BVHT_ERR_BAD_HANDLE, "unknown blas id %u", blas_id);
+    const Blas& b = ctx->blas[blas_id];
+    if (!out) return fail(ctx, BVHT_ERR_INVALID_ARG, "null output pointer");
+    if (n_tris != b.n_tris) return fail(ctx, BVHT_ERR_INVALID_ARG, "buffer for %u triangles, model has %u", n_tris, b.n_tris);
+    if (b.perm.empty()) { for (uint32_t i = 0; i < n_tris; ++i) out[i] = i; }   // host-built model: uploaded in its final order
+    else memcpy(out, b.perm.data(), (size_t)n_tris * 4);
     return BVHT_OK;
 }
 
@@ -887,6 +995,14 @@ int bvht_blas_refit(bvht_ctx* ctx, uint32_t blas_id) {
     ctx->refit_timed = true;
     ctx->stats.kernel_launches += (b.n_chunks ? 2 : 1);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return BVHT_OK;
+}
+
+int bvht_blas_info(bvht_ctx* ctx, uint32_t blas_id, uint32_t* n_tris, uint32_t* nodes_used) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (blas_id >= ctx->blas.size() || !ctx->blas[blas_id].alive) return fail(ctx, BVHT_ERR_BAD_HANDLE, "unknown blas id %u", blas_id);
+    if (n_tris) *n_tris = ctx->blas[blas_id].n_tris;
+    if (nodes_used) *nodes_used = ctx->blas[blas_id].nodes_used;
     return BVHT_OK;
 }
 

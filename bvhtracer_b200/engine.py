@@ -79,6 +79,33 @@ class Engine:
     def blas_destroy(self, blas_id):
         self._check(self._lib.bvht_blas_destroy(self._ctx, int(blas_id)))
 
+    def blas_build(self, tris):
+        """BvhBuilder::build_for on the device: tris in the mesh's own order -> blas id (tree + reordering as the reference's)."""
+        tris = np.ascontiguousarray(np.asarray(tris, dtype="<f4").reshape(-1, 9))
+        out = C.c_uint32()
+        self._check(self._lib.bvht_blas_build(self._ctx, ptr(tris), tris.shape[0], C.byref(out)))
+        return int(out.value)
+
+    def blas_rebuild(self, blas_id):
+        """Rebuild from the current vertices (the alternative to blas_refit)."""
+        self._check(self._lib.bvht_blas_rebuild(self._ctx, int(blas_id)))
+
+    def blas_info(self, blas_id):
+        """-> (n_tris, nodes_used)"""
+        n, u = C.c_uint32(), C.c_uint32()
+        self._check(self._lib.bvht_blas_info(self._ctx, int(blas_id), C.byref(n), C.byref(u)))
+        return int(n.value), int(u.value)
+
+    def blas_read_triangles(self, blas_id, n_tris):
+        out = np.zeros((int(n_tris), 9), "<f4")
+        self._check(self._lib.bvht_blas_read_triangles(self._ctx, int(blas_id), ptr(out), int(n_tris)))
+        return out
+
+    def blas_read_permutation(self, blas_id, n_tris):
+        out = np.zeros(int(n_tris), "<u4")
+        self._check(self._lib.bvht_blas_read_permutation(self._ctx, int(blas_id), ptr(out), int(n_tris)))
+        return out
+
     def blas_set_normals(self, blas_id, normals):
         normals = np.ascontiguousarray(np.asarray(normals, dtype="<f4").reshape(-1, 9))
         self._check(self._lib.bvht_blas_set_normals(self._ctx, int(blas_id), ptr(normals), normals.shape[0]))

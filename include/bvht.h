@@ -145,6 +145,8 @@ typedef struct {
     uint32_t trace_grid;             /* CTAs of the last persistent trace launch */
     uint32_t trace_block;
     uint32_t flags;
+    float    last_build_ms;          /* bvht_blas_build / bvht_blas_rebuild: upload + device build + read-back */
+    uint32_t last_build_levels;      /* levels of the level-synchronous device build */
 } bvht_stats;
 
 /* ---------------------------------------------------------------------------------------------- */
@@ -168,6 +170,23 @@ BVHT_API int         bvht_sync(bvht_ctx* ctx);
 BVHT_API int         bvht_blas_create(bvht_ctx* ctx, const float* tris, uint32_t n_tris,
                              const bvht_bvh_node* nodes, uint32_t nodes_used, uint32_t* out_blas_id);
 BVHT_API int         bvht_blas_destroy(bvht_ctx* ctx, uint32_t blas_id);
+
+/* `BvhBuilder::build_for(&mut mesh)` (bvh.rs:524-541, subdivide :396-467, find_best_split_plane :333-394) ON THE DEVICE:
+ * `tris` is the mesh in ITS OWN order (n_tris x 9 f32); the binned-SAH tree, the in-place reordering of the triangles
+ * and the node numbering come out bit-identical to the reference's host build (tests compare them with the oracle).
+ * Read the results back with bvht_blas_read_nodes / bvht_blas_read_triangles -- the reference reorders `Mesh.vertices`
+ * in place, so its host copy must be replaced by the reordered triangles. */
+BVHT_API int         bvht_blas_build(bvht_ctx* ctx, const float* tris, uint32_t n_tris, uint32_t* out_blas_id);
+
+/* Rebuild the tree of an existing model from its CURRENT vertices (after bvht_blas_update_vertices): the "rebuild" arm of
+ * bvhtracer/benches/bench_bvh_refit_rebuild.rs, where bvht_blas_refit is the "refit" arm.  Triangles are reordered again. */
+BVHT_API int         bvht_blas_rebuild(bvht_ctx* ctx, uint32_t blas_id);
+
+/* The model's triangles in their current (BVH) order, n_tris x 9 f32; and, for device-built models, the permutation
+ * that produced it: out[i] = index in the array given to bvht_blas_build of the triangle now at position i. */
+BVHT_API int         bvht_blas_info(bvht_ctx* ctx, uint32_t blas_id, uint32_t* n_tris, uint32_t* nodes_used);   /* Bvh.nodes_used (bvh.rs:232) */
+BVHT_API int         bvht_blas_read_triangles(bvht_ctx* ctx, uint32_t blas_id, float* out, uint32_t n_tris);
+BVHT_API int         bvht_blas_read_permutation(bvht_ctx* ctx, uint32_t blas_id, uint32_t* out, uint32_t n_tris);
 
 /* Per-vertex normals of a model, `Mesh::normals()` (mesh.rs:158-166): n_tris x 9 f32 in the mesh's ORIGINAL primitive
  * order -- the reference reorders only the positions when it builds the BVH (bvh.rs:426), and indexes this array with
