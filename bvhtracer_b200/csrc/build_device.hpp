@@ -45,4 +45,15 @@ public:
 cudaError_t device_build_reference_bvh(BuildWorkspace& ws, float* tris, uint32_t* perm, uint32_t n_tris, cudaStream_t s,
                                        std::vector<BuildNodeHost>& out_nodes, DeviceBuildStats* stats);
 
+// ---- leaf accelerator (leaf_accel.hpp) on the device
+struct SubRoot { uint32_t first_prim, count, base; };     // one accelerated reference leaf: its primitives, its slice of the index array
+struct DeviceSubResult { uint32_t n_nodes = 0, max_depth = 0, levels = 0, launches = 0; };
+
+// tris: the model's triangles on the device in the reference's (BVH) order; roots_host: the accelerated leaves (root r becomes
+// sub node r); n_sub = sum of the counts.  Outputs (device): order[n_sub] (sub position -> primitive index), sub_raw (4 float4 per sub
+// node, only the child references are set: run refit_sub_nodes next), sub_parent.  Capacity of sub_raw / sub_parent: n_sub nodes.
+cudaError_t device_build_leaf_accel(BuildWorkspace& ws, const float* tris, const SubRoot* roots_host, uint32_t n_roots, uint32_t n_sub,
+                                    float4* sub_raw, uint32_t* sub_parent, uint32_t* order, uint32_t max_sub_leaf, uint32_t sah_depth_limit,
+                                    cudaStream_t s, DeviceSubResult* res);
+
 } // namespace bvht

@@ -44,10 +44,12 @@ constexpr int kBinWords = 3 * kBins * 7;       // per node: axis x bin x {min.xy
 constexpr uint32_t kNoNode = 0xFFFFFFFFu;
 
 struct Split {                                 // per ACTIVE node of the current level
-    int      axis; float pos;
+    int      axis; float pos;                  // reference policy: left <=> centroid[axis] < pos
     uint32_t split;                            // 1: partition this node
     uint32_t n_left, q, q_is_right, left_before_q;
     uint32_t chunk0, n_chunks;
+    float    lo, scale; int bin;               // leaf-accelerator policy: left <=> bin(centroid[axis]) <= bin ...
+    uint32_t first, half;                      // ... or, axis == 3, the first `half` positions of the range (balanced fallback)
 };
 struct Chunk { uint32_t slot, node, begin, end; };
 
@@ -93,18 +95,20 @@ __global__ void init_root_kernel(BuildNode* nodes, uint32_t* active, uint32_t* c
 }
 
 // ---- plan: chunk list of the level
-__global__ void plan_count_kernel(const BuildNode* nodes, const uint32_t* active, uint32_t n_active, Split* split, uint32_t* bins,
+template <typename N, int BIN_WORDS, bool ORIGIN_BINS>
+__global__ void plan_count_kernel(const N* nodes, const uint32_t* active, uint32_t n_active, Split* split, uint32_t* bins,
                                   uint32_t* counters) {
     uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot == 0) counters[kCtrNext] = 0u;
     if (slot >= n_active) return;
-    const BuildNode& n = nodes[active[slot]];
+    const N& n = nodes[active[slot]];
     Split s; memset(&s, 0, sizeof s);
     s.axis = -1; s.n_chunks = (n.count + kChunk - 1) / kChunk;
     split[slot] = s;
-    uint32_t* b = bins + (size_t)slot * kBinWords;
-    const uint32_t zero = enc(0.0f);                                    // Aabb::default(): the point box at the origin
-    for (int i = 0; i < kBinWords; ++i) b[i] = (i % 7 == 6) ? 0u : zero;
+    uint32_t* b = bins + (size_t)slot * BIN_WORDS;
+    // reference bins: Aabb::default(), the point box at the origin; accelerator bins: empty boxes
+    const uint32_t lo0 = ORIGIN_BINS ? enc(0.0f) : enc(FLT_MAX), hi0 = ORIGIN_BINS ? enc(0.0f) : enc(-FLT_MAX);
+    for (int i = 0; i < BIN_WORDS; ++i) { const int w = i % 7; b[i] = w == 6 ? 0u : (w < 3 ? lo0 : hi0); }
 }
 
 __global__ void plan_scan_kernel(Split* split, uint32_t n_active, uint32_t* counters) {     // one CTA
@@ -134,10 +138,11 @@ __global__ void plan_scan_kernel(Split* split, uint32_t n_active, uint32_t* coun
     if (threadIdx.x == 0) counters[kCtrChunks] = carry;
 }
 
-__global__ void plan_fill_kernel(const BuildNode* nodes, const uint32_t* active, uint32_t n_active, const Split* split, Chunk* chunks) {
+template <typename N>
+__global__ void plan_fill_kernel(const N* nodes, const uint32_t* active, uint32_t n_active, const Split* split, Chunk* chunks) {
     uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n_active) return;
-    const BuildNode& n = nodes[active[slot]];
+    const N& n = nodes[active[slot]];
     const Split& s = split[slot];
     for (uint32_t j = 0; j < s.n_chunks; ++j) {
         Chunk c; c.slot = slot; c.node = active[slot];
@@ -298,13 +303,46 @@ __global__ void select_kernel(const BuildNode* nodes, const uint32_t* active, ui
     s.split = (best_axis >= 0 && !(best_cost >= no_split)) ? 1u : 0u;
 }
 
-__device__ __forceinline__ bool is_left(const float* tris, uint32_t p, int axis, float pos) {
-    const float* t = tris + (size_t)p * 9;
-    return ((__ldg(t + axis) + __ldg(t + 3 + axis)) + __ldg(t + 6 + axis)) * (1.0f / 3.0f) < pos;    // bvh.rs:423
-}
+// What differs between the two builders in the partition passes: the predicate and what is moved.
+struct RefPolicy {                       // the reference's build: triangles themselves are permuted (bvh.rs:419-430)
+    const float* tris; const uint32_t* perm; float* tris_tmp; uint32_t* perm_tmp; float* tris_rw; uint32_t* perm_rw;
+    __device__ __forceinline__ bool left(uint32_t p, const Split& s) const {
+        const float* t = tris + (size_t)p * 9;
+        return ((__ldg(t + s.axis) + __ldg(t + 3 + s.axis)) + __ldg(t + 6 + s.axis)) * (1.0f / 3.0f) < s.pos;    // bvh.rs:423
+    }
+    __device__ __forceinline__ void move(uint32_t p, uint32_t dest) const {
+        float t[9]; load_tri(tris, p, t);
+        float* o = tris_tmp + (size_t)dest * 9;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) o[k] = t[k];
+        perm_tmp[dest] = perm[p];
+    }
+    __device__ __forceinline__ void copy_back(uint32_t begin, uint32_t end) const {
+        const size_t b = (size_t)begin * 9, e = (size_t)end * 9;
+        for (size_t i = b + threadIdx.x; i < e; i += kBB) tris_rw[i] = tris_tmp[i];
+        for (uint32_t p = begin + threadIdx.x; p < end; p += kBB) perm_rw[p] = perm_tmp[p];
+    }
+};
+constexpr int kSubBins = 16;
+struct SubPolicy {                       // the leaf accelerator's build: an index array is permuted, triangles stay
+    const float* tris; const uint32_t* order; uint32_t* order_tmp; uint32_t* order_rw;
+    __device__ __forceinline__ bool left(uint32_t p, const Split& s) const {
+        if (s.axis == 3) return (p - s.first) < s.half;
+        const float* t = tris + (size_t)__ldg(order + p) * 9;
+        float c = ((__ldg(t + s.axis) + __ldg(t + 3 + s.axis)) + __ldg(t + 6 + s.axis)) * (1.0f / 3.0f);
+        int bi = (int)((c - s.lo) * s.scale);
+        bi = max(0, min(kSubBins - 1, bi));
+        return bi <= s.bin;
+    }
+    __device__ __forceinline__ void move(uint32_t p, uint32_t dest) const { order_tmp[dest] = order[p]; }
+    __device__ __forceinline__ void copy_back(uint32_t begin, uint32_t end) const {
+        for (uint32_t p = begin + threadIdx.x; p < end; p += kBB) order_rw[p] = order_tmp[p];
+    }
+};
 
 // ---- partition, pass 1: left elements per chunk
-__global__ void __launch_bounds__(kBB) count_kernel(const float* __restrict__ tris, const Chunk* chunks, const Split* split,
+template <typename P>
+__global__ void __launch_bounds__(kBB) count_kernel(const P pol, const Chunk* chunks, const Split* split,
                                                    uint32_t* chunk_left, const uint32_t* counters) {
     if (blockIdx.x >= counters[kCtrChunks]) return;
     const Chunk c = chunks[blockIdx.x];
@@ -314,7 +352,7 @@ __global__ void __launch_bounds__(kBB) count_kernel(const float* __restrict__ tr
 #pragma unroll
     for (int e = 0; e < kPerThread; ++e) {
         uint32_t p = c.begin + threadIdx.x * kPerThread + e;
-        if (p < c.end && is_left(tris, p, s.axis, s.pos)) ++local;
+        if (p < c.end && pol.left(p, s)) ++local;
     }
     __shared__ uint32_t acc;
     if (threadIdx.x == 0) acc = 0u;
@@ -326,14 +364,15 @@ __global__ void __launch_bounds__(kBB) count_kernel(const float* __restrict__ tr
 }
 
 // ---- partition, pass 2: per node, prefix over its chunks; n_left, q and what sits at q   (one warp per node)
-__global__ void scan_kernel(const float* __restrict__ tris, const BuildNode* nodes, const uint32_t* active, uint32_t n_active,
+template <typename P, typename N>
+__global__ void scan_kernel(const P pol, const N* nodes, const uint32_t* active, uint32_t n_active,
                             Split* split, const uint32_t* chunk_left, uint32_t* chunk_left_before) {
     const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (slot >= n_active) return;
     Split& s = split[slot];
     if (!s.split) return;
-    const BuildNode& n = nodes[active[slot]];
+    const N& n = nodes[active[slot]];
     uint32_t carry = 0u;
     for (uint32_t base = 0; base < s.n_chunks; base += 32) {
         uint32_t j = base + lane;
@@ -346,10 +385,10 @@ __global__ void scan_kernel(const float* __restrict__ tris, const BuildNode* nod
     const uint32_t n_left = carry, q = n.first + n_left, last = n.first + n.count - 1u;
     uint32_t q_is_right = 0u, left_before_q = n_left;
     if (q <= last) {
-        q_is_right = is_left(tris, q, s.axis, s.pos) ? 0u : 1u;
+        q_is_right = pol.left(q, s) ? 0u : 1u;
         const uint32_t jq = (q - n.first) / kChunk, cb = n.first + jq * kChunk;
         uint32_t cnt = 0u;
-        for (uint32_t p = cb + lane; p < q; p += 32) cnt += is_left(tris, p, s.axis, s.pos) ? 1u : 0u;
+        for (uint32_t p = cb + lane; p < q; p += 32) cnt += pol.left(p, s) ? 1u : 0u;
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
         left_before_q = chunk_left_before[s.chunk0 + jq] + cnt;         // written by this warp above
     }
@@ -371,7 +410,8 @@ __device__ __forceinline__ uint32_t block_exclusive(uint32_t v) {
 }
 
 // ---- partition, pass 3: positions of the front's right elements (H) and the back's left elements (G)
-__global__ void __launch_bounds__(kBB) tables_kernel(const float* __restrict__ tris, const BuildNode* nodes, const Chunk* chunks,
+template <typename P, typename N>
+__global__ void __launch_bounds__(kBB) tables_kernel(const P pol, const N* nodes, const Chunk* chunks,
                                                     const Split* split, const uint32_t* chunk_left_before, uint32_t* table_h,
                                                     uint32_t* table_g, const uint32_t* counters) {
     if (blockIdx.x >= counters[kCtrChunks]) return;
@@ -383,7 +423,7 @@ __global__ void __launch_bounds__(kBB) tables_kernel(const float* __restrict__ t
 #pragma unroll
     for (int e = 0; e < kPerThread; ++e) {
         uint32_t p = c.begin + threadIdx.x * kPerThread + e;
-        left[e] = p < c.end && is_left(tris, p, s.axis, s.pos);
+        left[e] = p < c.end && pol.left(p, s);
         local += left[e] ? 1u : 0u;
     }
     uint32_t before = chunk_left_before[blockIdx.x] + block_exclusive(local);
@@ -401,10 +441,10 @@ __global__ void __launch_bounds__(kBB) tables_kernel(const float* __restrict__ t
 }
 
 // ---- partition, pass 4: move every triangle of a splitting node to its final position (into the scratch copy)
-__global__ void __launch_bounds__(kBB) scatter_kernel(const float* __restrict__ tris, const uint32_t* __restrict__ perm,
-                                                     const BuildNode* nodes, const Chunk* chunks, const Split* split,
+template <typename P, typename N>
+__global__ void __launch_bounds__(kBB) scatter_kernel(const P pol, const N* nodes, const Chunk* chunks, const Split* split,
                                                      const uint32_t* chunk_left_before, const uint32_t* table_h, const uint32_t* table_g,
-                                                     float* tris_out, uint32_t* perm_out, const uint32_t* counters) {
+                                                     const uint32_t* counters) {
     if (blockIdx.x >= counters[kCtrChunks]) return;
     const Chunk c = chunks[blockIdx.x];
     const Split s = split[c.slot];
@@ -414,7 +454,7 @@ __global__ void __launch_bounds__(kBB) scatter_kernel(const float* __restrict__ 
 #pragma unroll
     for (int e = 0; e < kPerThread; ++e) {
         uint32_t p = c.begin + threadIdx.x * kPerThread + e;
-        left[e] = p < c.end && is_left(tris, p, s.axis, s.pos);
+        left[e] = p < c.end && pol.left(p, s);
         local += left[e] ? 1u : 0u;
     }
     uint32_t before = chunk_left_before[blockIdx.x] + block_exclusive(local);
@@ -432,25 +472,18 @@ __global__ void __launch_bounds__(kBB) scatter_kernel(const float* __restrict__ 
                 if (left[e]) dest = table_h[first + (n_back_left - 1u - (before - s.left_before_q))];
                 else dest = p - 1u;
             }
-            float t[9]; load_tri(tris, p, t);
-            float* o = tris_out + (size_t)dest * 9;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) o[k] = t[k];
-            perm_out[dest] = perm[p];
+            pol.move(p, dest);
         }
         before += left[e] ? 1u : 0u;
     }
 }
 
-__global__ void __launch_bounds__(kBB) copy_back_kernel(const float* __restrict__ src, const uint32_t* __restrict__ perm_src,
-                                                       const Chunk* chunks, const Split* split, float* tris, uint32_t* perm,
-                                                       const uint32_t* counters) {
+template <typename P>
+__global__ void __launch_bounds__(kBB) copy_back_kernel(const P pol, const Chunk* chunks, const Split* split, const uint32_t* counters) {
     if (blockIdx.x >= counters[kCtrChunks]) return;
     const Chunk c = chunks[blockIdx.x];
     if (!split[c.slot].split) return;
-    const size_t b = (size_t)c.begin * 9, e = (size_t)c.end * 9;
-    for (size_t i = b + threadIdx.x; i < e; i += kBB) tris[i] = src[i];
-    for (uint32_t p = c.begin + threadIdx.x; p < c.end; p += kBB) perm[p] = perm_src[p];
+    pol.copy_back(c.begin, c.end);
 }
 
 // ---- children (bvh.rs:432-461): allocate the pair, queue both for the next level
@@ -469,6 +502,200 @@ __global__ void children_kernel(BuildNode* nodes, const uint32_t* active, uint32
     const uint32_t at = atomicAdd(&counters[kCtrNext], 2u);
     next_active[at] = left; next_active[at + 1u] = left + 1u;
     atomicMax(&counters[kCtrDepth], n.depth + 1u);
+}
+
+
+// ======================================================================================================================
+// Leaf accelerator (leaf_accel.hpp): the conservative sub-BVHs inside the reference's leaves, built on the device.
+// Same level-synchronous machinery, different policy: an INDEX array is partitioned (the reference's triangle order must
+// not change), 16 bins with empty boxes, no cost-based termination (one triangle per sub leaf), SAH splits down to
+// `sah_depth_limit`, then balanced half splits of the current arrangement (bounds the depth for the traversal stack).
+// Only the topology is produced here (child references, parents, the index array); boxes and kappa are then filled
+// bottom-up by refit_sub_nodes_kernel (upload_kernels.cu), the kernel that also runs after every vertex update.
+struct SubNode {
+    uint32_t cmin[3], cmax[3];     // encoded centroid bounds
+    uint32_t first, count;         // range in the index array
+    uint32_t depth, parent_ref;    // parent_ref = (parent << 1) | slot, 0xFFFFFFFF for the root of a reference leaf
+    uint32_t n_left;
+    uint32_t child[2];             // inner children (node ids) or kNoNode for sub leaves
+    uint32_t pad[3];
+};
+static_assert(sizeof(SubNode) == 64, "SubNode is 64 bytes");
+constexpr int kSubBinWords = 3 * kSubBins * 7;
+
+__device__ __forceinline__ void init_sub_node(SubNode& n, uint32_t first, uint32_t count, uint32_t depth, uint32_t parent_ref) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { n.cmin[k] = enc(FLT_MAX); n.cmax[k] = enc(-FLT_MAX); }
+    n.first = first; n.count = count; n.depth = depth; n.parent_ref = parent_ref; n.n_left = 0u;
+    n.child[0] = kNoNode; n.child[1] = kNoNode;
+}
+
+__global__ void sub_init_kernel(const SubRoot* roots, uint32_t n_roots, SubNode* nodes, uint32_t* active, uint32_t* order, uint32_t* counters) {
+    const uint32_t r = blockIdx.x;
+    const SubRoot root = roots[r];
+    if (threadIdx.x == 0) {
+        init_sub_node(nodes[r], root.base, root.count, 0u, kNoNode);
+        active[r] = r;
+        if (r == 0) { counters[kCtrNodes] = n_roots; counters[kCtrNext] = 0u; counters[kCtrChunks] = 0u; counters[kCtrDepth] = 0u; }
+    }
+    for (uint32_t k = threadIdx.x; k < root.count; k += blockDim.x) order[root.base + k] = root.first_prim + k;
+}
+
+__global__ void __launch_bounds__(kBB) sub_bounds_kernel(const float* __restrict__ tris, const uint32_t* __restrict__ order, SubNode* nodes,
+                                                        const Chunk* chunks, const uint32_t* counters) {
+    if (blockIdx.x >= counters[kCtrChunks]) return;
+    const Chunk c = chunks[blockIdx.x];
+    float v[6] = { FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX };
+#pragma unroll
+    for (int e = 0; e < kPerThread; ++e) {
+        uint32_t p = c.begin + threadIdx.x * kPerThread + e;
+        if (p < c.end) {
+            float t[9]; load_tri(tris, __ldg(order + p), t);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { float cen = centroid_axis(t, k); v[k] = fminf(v[k], cen); v[3 + k] = fmaxf(v[3 + k], cen); }
+        }
+    }
+    __shared__ float red[kBB / 32][6];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        for (int o = 16; o > 0; o >>= 1) {
+            float y = __shfl_xor_sync(0xFFFFFFFFu, v[k], o);
+            v[k] = k < 3 ? fminf(v[k], y) : fmaxf(v[k], y);
+        }
+        if (lane == 0) red[warp][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int k = threadIdx.x;
+        float x = red[0][k];
+        for (int w = 1; w < kBB / 32; ++w) x = k < 3 ? fminf(x, red[w][k]) : fmaxf(x, red[w][k]);
+        if (x == x) { SubNode& n = nodes[c.node]; if (k < 3) atomicMin(&n.cmin[k], enc(x)); else atomicMax(&n.cmax[k - 3], enc(x)); }
+    }
+}
+
+__global__ void __launch_bounds__(kBB) sub_bins_kernel(const float* __restrict__ tris, const uint32_t* __restrict__ order, const SubNode* nodes,
+                                                      const Chunk* chunks, uint32_t* bins, const uint32_t* counters) {
+    if (blockIdx.x >= counters[kCtrChunks]) return;
+    const Chunk c = chunks[blockIdx.x];
+    __shared__ uint32_t sb[kSubBinWords];
+    const uint32_t lo0 = enc(FLT_MAX), hi0 = enc(-FLT_MAX);
+    for (int i = threadIdx.x; i < kSubBinWords; i += kBB) { const int w = i % 7; sb[i] = w == 6 ? 0u : (w < 3 ? lo0 : hi0); }
+    float bmin[3], scale[3]; bool on[3];
+    {
+        const SubNode& n = nodes[c.node];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            bmin[a] = dec(n.cmin[a]);
+            float bmax = dec(n.cmax[a]);
+            on[a] = bmax > bmin[a];
+            scale[a] = (float)kSubBins / (bmax - bmin[a]);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < kPerThread; ++e) {
+        uint32_t p = c.begin + threadIdx.x * kPerThread + e;
+        if (p >= c.end) continue;
+        float t[9]; load_tri(tris, __ldg(order + p), t);
+        uint32_t lo[3], hi[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = enc(fminf(t[k], fminf(t[3 + k], t[6 + k])));
+            hi[k] = enc(fmaxf(t[k], fmaxf(t[3 + k], t[6 + k])));
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (!on[a]) continue;
+            int bi = (int)((centroid_axis(t, a) - bmin[a]) * scale[a]);       // must match SubPolicy::left
+            bi = max(0, min(kSubBins - 1, bi));
+            uint32_t* b = sb + (a * kSubBins + bi) * 7;
+            atomicAdd(b + 6, 1u);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { atomicMin(b + k, lo[k]); atomicMax(b + 3 + k, hi[k]); }
+        }
+    }
+    __syncthreads();
+    uint32_t* g = bins + (size_t)c.slot * kSubBinWords;
+    for (int i = threadIdx.x; i < kSubBinWords; i += kBB) {
+        const int w = i % 7;
+        if (sb[i - w + 6] == 0u) continue;
+        if (w == 6) atomicAdd(g + i, sb[i]);
+        else if (w < 3) atomicMin(g + i, sb[i]);
+        else atomicMax(g + i, sb[i]);
+    }
+}
+
+__global__ void sub_select_kernel(const SubNode* nodes, const uint32_t* active, uint32_t n_active, const uint32_t* bins, Split* split,
+                                  uint32_t sah_depth_limit) {
+    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_active) return;
+    const SubNode& n = nodes[active[slot]];
+    Split& s = split[slot];
+    int best_axis = -1, best_bin = -1; float best_cost = FLT_MAX, best_lo = 0.0f, best_scale = 0.0f;
+    if (n.depth < sah_depth_limit) {
+        for (int a = 0; a < 3; ++a) {
+            const float lo = dec(n.cmin[a]), hi = dec(n.cmax[a]);
+            if (!(hi > lo)) continue;
+            const uint32_t* b = bins + (size_t)slot * kSubBinWords + a * kSubBins * 7;
+            // right-to-left sweep first (areas + counts of the right side of every plane), then left-to-right with the cost
+            float ra[kSubBins - 1]; uint32_t rc[kSubBins - 1];
+            float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+            uint32_t cnt = 0;
+            for (int i = kSubBins - 1; i >= 1; --i) {
+                const uint32_t* bb = b + i * 7;
+                if (bb[6]) { for (int k = 0; k < 3; ++k) { mn[k] = fminf(mn[k], dec(bb[k])); mx[k] = fmaxf(mx[k], dec(bb[3 + k])); } }
+                cnt += bb[6];
+                rc[i - 1] = cnt; ra[i - 1] = cnt ? area(mn, mx) : 0.0f;
+            }
+            for (int k = 0; k < 3; ++k) { mn[k] = FLT_MAX; mx[k] = -FLT_MAX; }
+            cnt = 0;
+            for (int i = 0; i < kSubBins - 1; ++i) {
+                const uint32_t* bb = b + i * 7;
+                if (bb[6]) { for (int k = 0; k < 3; ++k) { mn[k] = fminf(mn[k], dec(bb[k])); mx[k] = fmaxf(mx[k], dec(bb[3 + k])); } }
+                cnt += bb[6];
+                if (cnt == 0u || rc[i] == 0u) continue;
+                float cost = (float)cnt * area(mn, mx) + (float)rc[i] * ra[i];
+                if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = i; best_lo = lo; best_scale = (float)kSubBins / (hi - lo); }
+            }
+        }
+    }
+    s.split = 1u;
+    if (best_axis >= 0) { s.axis = best_axis; s.lo = best_lo; s.scale = best_scale; s.bin = best_bin; }
+    else { s.axis = 3; s.first = n.first; s.half = n.count / 2u; }      // identical centroids or depth limit: balanced half split
+}
+
+__global__ void sub_children_kernel(SubNode* nodes, const uint32_t* active, uint32_t n_active, const Split* split, uint32_t* next_active,
+                                    uint32_t* counters, uint32_t max_sub_leaf) {
+    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_active) return;
+    const uint32_t id = active[slot];
+    SubNode& n = nodes[id];
+    uint32_t n_left = split[slot].n_left;
+    if (n_left == 0u || n_left >= n.count) n_left = n.count / 2u;          // cannot happen (the plane had both sides populated)
+    n.n_left = n_left;
+    const uint32_t first[2] = { n.first, n.first + n_left }, cnt[2] = { n_left, n.count - n_left };
+    for (int c = 0; c < 2; ++c) {
+        if (cnt[c] <= max_sub_leaf) continue;
+        const uint32_t child = atomicAdd(&counters[kCtrNodes], 1u);
+        init_sub_node(nodes[child], first[c], cnt[c], n.depth + 1u, (id << 1) | (uint32_t)c);
+        n.child[c] = child;
+        next_active[atomicAdd(&counters[kCtrNext], 1u)] = child;
+    }
+    atomicMax(&counters[kCtrDepth], n.depth + 1u);
+}
+
+__global__ void sub_emit_kernel(const SubNode* nodes, uint32_t n_nodes, float4* raw, uint32_t* parent) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_nodes) return;
+    const SubNode& n = nodes[id];
+    const uint32_t first[2] = { n.first, n.first + n.n_left }, cnt[2] = { n.n_left, n.count - n.n_left };
+    for (int c = 0; c < 2; ++c) {
+        uint32_t ref = n.child[c] != kNoNode ? n.child[c] : (0x80000000u | ((cnt[c] - 1u) << 28) | first[c]);
+        raw[4 * (size_t)id + 2 * c] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        raw[4 * (size_t)id + 2 * c + 1] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(ref));
+    }
+    parent[id] = n.parent_ref;
 }
 
 template <typename T> cudaError_t grow(T*& p, size_t& cap, size_t need) {
@@ -496,6 +723,8 @@ struct BuildWorkspace::Impl {
     float* tris_tmp = nullptr;    size_t tris_tmp_cap = 0;
     uint32_t* perm_tmp = nullptr; size_t perm_tmp_cap = 0;
     uint32_t* counters = nullptr; size_t counters_cap = 0;
+    SubNode* sub_nodes = nullptr; size_t sub_nodes_cap = 0;
+    SubRoot* roots = nullptr;     size_t roots_cap = 0;
 };
 
 BuildWorkspace::BuildWorkspace() : impl_(new Impl()) {}
@@ -503,7 +732,7 @@ BuildWorkspace::~BuildWorkspace() { release(); delete impl_; }
 void BuildWorkspace::release() {
     Impl& w = *impl_;
     void* ptrs[] = { w.nodes, w.active[0], w.active[1], w.split, w.bins, w.chunks, w.chunk_left, w.chunk_before, w.table_h, w.table_g,
-                     w.tris_tmp, w.perm_tmp, w.counters };
+                     w.tris_tmp, w.perm_tmp, w.counters, w.sub_nodes, w.roots };
     for (void* p : ptrs) if (p) cudaFree(p);
     *impl_ = Impl();
 }
@@ -536,18 +765,18 @@ cudaError_t device_build_reference_bvh(BuildWorkspace& ws, float* tris, uint32_t
         BVHT_BUILD_CHECK(grow(w.chunk_left, w.chunk_left_cap, ub));
         BVHT_BUILD_CHECK(grow(w.chunk_before, w.chunk_before_cap, ub));
         const unsigned gs = (n_active + 127) / 128, gc = (unsigned)ub;
-        plan_count_kernel<<<gs, 128, 0, s>>>(w.nodes, w.active[cur], n_active, w.split, w.bins, w.counters);
+        plan_count_kernel<BuildNode, kBinWords, true><<<gs, 128, 0, s>>>(w.nodes, w.active[cur], n_active, w.split, w.bins, w.counters);
         plan_scan_kernel<<<1, 1024, 0, s>>>(w.split, n_active, w.counters);
-        plan_fill_kernel<<<gs, 128, 0, s>>>(w.nodes, w.active[cur], n_active, w.split, w.chunks);
+        plan_fill_kernel<BuildNode><<<gs, 128, 0, s>>>(w.nodes, w.active[cur], n_active, w.split, w.chunks);
         bounds_kernel<<<gc, kBB, 0, s>>>(tris, w.nodes, w.chunks, w.counters);
         bins_kernel<<<gc, kBB, 0, s>>>(tris, w.nodes, w.chunks, w.bins, w.counters);
         select_kernel<<<gs, 128, 0, s>>>(w.nodes, w.active[cur], n_active, w.bins, w.split);
-        count_kernel<<<gc, kBB, 0, s>>>(tris, w.chunks, w.split, w.chunk_left, w.counters);
-        scan_kernel<<<(n_active + 3) / 4, 128, 0, s>>>(tris, w.nodes, w.active[cur], n_active, w.split, w.chunk_left, w.chunk_before);
-        tables_kernel<<<gc, kBB, 0, s>>>(tris, w.nodes, w.chunks, w.split, w.chunk_before, w.table_h, w.table_g, w.counters);
-        scatter_kernel<<<gc, kBB, 0, s>>>(tris, perm, w.nodes, w.chunks, w.split, w.chunk_before, w.table_h, w.table_g, w.tris_tmp,
-                                          w.perm_tmp, w.counters);
-        copy_back_kernel<<<gc, kBB, 0, s>>>(w.tris_tmp, w.perm_tmp, w.chunks, w.split, tris, perm, w.counters);
+        const RefPolicy pol = { tris, perm, w.tris_tmp, w.perm_tmp, tris, perm };
+        count_kernel<<<gc, kBB, 0, s>>>(pol, w.chunks, w.split, w.chunk_left, w.counters);
+        scan_kernel<<<(n_active + 3) / 4, 128, 0, s>>>(pol, w.nodes, w.active[cur], n_active, w.split, w.chunk_left, w.chunk_before);
+        tables_kernel<<<gc, kBB, 0, s>>>(pol, w.nodes, w.chunks, w.split, w.chunk_before, w.table_h, w.table_g, w.counters);
+        scatter_kernel<<<gc, kBB, 0, s>>>(pol, w.nodes, w.chunks, w.split, w.chunk_before, w.table_h, w.table_g, w.counters);
+        copy_back_kernel<<<gc, kBB, 0, s>>>(pol, w.chunks, w.split, w.counters);
         children_kernel<<<gs, 128, 0, s>>>(w.nodes, w.active[cur], n_active, w.split, w.active[cur ^ 1], w.counters);
         launches += 12;
         BVHT_BUILD_CHECK(cudaGetLastError());
@@ -585,6 +814,62 @@ cudaError_t device_build_reference_bvh(BuildWorkspace& ws, float* tris, uint32_t
         out_nodes[fi] = h;
     }
     if (stats) { stats->levels = levels; stats->launches = launches; stats->temp_nodes = ctr[kCtrNodes]; stats->max_depth = ctr[kCtrDepth]; }
+    return cudaSuccess;
+}
+
+cudaError_t device_build_leaf_accel(BuildWorkspace& ws, const float* tris, const SubRoot* roots_host, uint32_t n_roots, uint32_t n_sub,
+                                    float4* sub_raw, uint32_t* sub_parent, uint32_t* order, uint32_t max_sub_leaf, uint32_t sah_depth_limit,
+                                    cudaStream_t s, DeviceSubResult* res) {
+    BuildWorkspace::Impl& w = *ws.impl_;
+    if (res) *res = DeviceSubResult();
+    if (n_roots == 0 || n_sub == 0) return cudaSuccess;
+    const size_t n = n_sub;
+    BVHT_BUILD_CHECK(grow(w.sub_nodes, w.sub_nodes_cap, n + 1));
+    BVHT_BUILD_CHECK(grow(w.roots, w.roots_cap, (size_t)n_roots));
+    BVHT_BUILD_CHECK(grow(w.active[0], w.active_cap[0], n + 2));
+    BVHT_BUILD_CHECK(grow(w.active[1], w.active_cap[1], n + 2));
+    BVHT_BUILD_CHECK(grow(w.table_h, w.table_h_cap, n));
+    BVHT_BUILD_CHECK(grow(w.table_g, w.table_g_cap, n));
+    BVHT_BUILD_CHECK(grow(w.perm_tmp, w.perm_tmp_cap, n));
+    BVHT_BUILD_CHECK(grow(w.counters, w.counters_cap, (size_t)kCtrCount));
+    BVHT_BUILD_CHECK(cudaMemcpyAsync(w.roots, roots_host, (size_t)n_roots * sizeof(SubRoot), cudaMemcpyHostToDevice, s));
+    sub_init_kernel<<<n_roots, 128, 0, s>>>(w.roots, n_roots, w.sub_nodes, w.active[0], order, w.counters);
+    uint32_t n_active = n_roots, levels = 0, launches = 1;
+    int cur = 0;
+    const SubPolicy pol = { tris, order, w.perm_tmp, order };
+    while (n_active > 0) {
+        const size_t ub = n / kChunk + n_active + 1;
+        BVHT_BUILD_CHECK(grow(w.split, w.split_cap, (size_t)n_active));
+        BVHT_BUILD_CHECK(grow(w.bins, w.bins_cap, (size_t)n_active * kSubBinWords));
+        BVHT_BUILD_CHECK(grow(w.chunks, w.chunks_cap, ub));
+        BVHT_BUILD_CHECK(grow(w.chunk_left, w.chunk_left_cap, ub));
+        BVHT_BUILD_CHECK(grow(w.chunk_before, w.chunk_before_cap, ub));
+        const unsigned gs = (n_active + 127) / 128, gc = (unsigned)ub;
+        plan_count_kernel<SubNode, kSubBinWords, false><<<gs, 128, 0, s>>>(w.sub_nodes, w.active[cur], n_active, w.split, w.bins, w.counters);
+        plan_scan_kernel<<<1, 1024, 0, s>>>(w.split, n_active, w.counters);
+        plan_fill_kernel<SubNode><<<gs, 128, 0, s>>>(w.sub_nodes, w.active[cur], n_active, w.split, w.chunks);
+        sub_bounds_kernel<<<gc, kBB, 0, s>>>(tris, order, w.sub_nodes, w.chunks, w.counters);
+        sub_bins_kernel<<<gc, kBB, 0, s>>>(tris, order, w.sub_nodes, w.chunks, w.bins, w.counters);
+        sub_select_kernel<<<gs, 128, 0, s>>>(w.sub_nodes, w.active[cur], n_active, w.bins, w.split, sah_depth_limit);
+        count_kernel<<<gc, kBB, 0, s>>>(pol, w.chunks, w.split, w.chunk_left, w.counters);
+        scan_kernel<<<(n_active + 3) / 4, 128, 0, s>>>(pol, w.sub_nodes, w.active[cur], n_active, w.split, w.chunk_left, w.chunk_before);
+        tables_kernel<<<gc, kBB, 0, s>>>(pol, w.sub_nodes, w.chunks, w.split, w.chunk_before, w.table_h, w.table_g, w.counters);
+        scatter_kernel<<<gc, kBB, 0, s>>>(pol, w.sub_nodes, w.chunks, w.split, w.chunk_before, w.table_h, w.table_g, w.counters);
+        copy_back_kernel<<<gc, kBB, 0, s>>>(pol, w.chunks, w.split, w.counters);
+        sub_children_kernel<<<gs, 128, 0, s>>>(w.sub_nodes, w.active[cur], n_active, w.split, w.active[cur ^ 1], w.counters, max_sub_leaf);
+        launches += 12;
+        BVHT_BUILD_CHECK(cudaGetLastError());
+        uint32_t next = 0;
+        BVHT_BUILD_CHECK(cudaMemcpyAsync(&next, w.counters + kCtrNext, 4, cudaMemcpyDeviceToHost, s));
+        BVHT_BUILD_CHECK(cudaStreamSynchronize(s));
+        n_active = next; cur ^= 1; ++levels;
+    }
+    uint32_t ctr[kCtrCount];
+    BVHT_BUILD_CHECK(cudaMemcpyAsync(ctr, w.counters, sizeof ctr, cudaMemcpyDeviceToHost, s));
+    BVHT_BUILD_CHECK(cudaStreamSynchronize(s));
+    sub_emit_kernel<<<(ctr[kCtrNodes] + 127) / 128, 128, 0, s>>>(w.sub_nodes, ctr[kCtrNodes], sub_raw, sub_parent);
+    BVHT_BUILD_CHECK(cudaGetLastError());
+    if (res) { res->n_nodes = ctr[kCtrNodes]; res->max_depth = ctr[kCtrDepth]; res->levels = levels; res->launches = launches + 1; }
     return cudaSuccess;
 }
 

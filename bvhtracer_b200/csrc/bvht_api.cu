@@ -13,6 +13,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <string>
@@ -234,9 +235,79 @@ void set_useful_product(Blas& b, const ModelStats& ms, const LeafAccelConfig& cf
         b.useful_product = 1e300;
 }
 
+// The leaf accelerator built on the device (build_kernels.cu device_build_leaf_accel): topology by the level-synchronous
+// binned-SAH builder, boxes + kappa by the same bottom-up kernel that refits it after vertex updates.
+int build_accel_device(bvht_ctx* ctx, Blas& b, const LeafAccelConfig& cfg, bool& done) {
+    done = false;
+    const bool timing = getenv("BVHT_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        cudaStreamSynchronize(ctx->stream);
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bvht timing] accel %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
+    std::vector<SubRoot> roots;
+    std::vector<uint32_t> leaf_sub_root(b.nodes_used, 0xFFFFFFFFu);
+    uint64_t n_sub = 0;
+    for (uint32_t ni = 0; ni < b.nodes_used; ++ni) {
+        if (ni == 1) continue;
+        const bvht_bvh_node& n = b.h_nodes[ni];
+        if (n.prim_count == 0 || n.prim_count < cfg.min_leaf_tris || n.prim_count <= cfg.max_sub_leaf) continue;
+        if ((uint64_t)n.left_first + n.prim_count > b.n_tris) return fail(ctx, BVHT_ERR_MALFORMED_BVH, "leaf %u exceeds the primitive array", ni);
+        leaf_sub_root[ni] = (uint32_t)roots.size();
+        roots.push_back(SubRoot{ n.left_first, n.prim_count, (uint32_t)n_sub });
+        n_sub += n.prim_count;
+    }
+    if (roots.empty() || n_sub >= 0x0FFFFFFFull) return BVHT_OK;               // nothing to accelerate: the host path handles the empty case
+    ModelStats ms = compute_model_stats(b.h_tris.data(), b.n_tris);
+    b.radius = ms.radius; b.max_edge = ms.max_edge; b.model_kappa = ms.model_kappa; b.model_valid = ms.model_valid;
+    memcpy(b.model_lo, ms.model_lo, 12); memcpy(b.model_hi, ms.model_hi, 12);
+    set_useful_product(b, ms, cfg);
+    lap("roots + model stats");
+    int rc;
+    if ((rc = ensure(ctx, b.sub_raw, (size_t)n_sub * 64))) return rc;
+    if ((rc = ensure(ctx, b.sub_nodes, (size_t)n_sub * 64))) return rc;
+    if ((rc = ensure(ctx, b.sub_order, (size_t)n_sub * 4))) return rc;
+    if ((rc = ensure(ctx, b.sub_parent, (size_t)n_sub * 4))) return rc;
+    if ((rc = ensure(ctx, b.sub_counters, (size_t)n_sub * 4))) return rc;
+    if ((rc = upload_u32(ctx, b.leaf_sub_root, leaf_sub_root))) return rc;
+    DeviceSubResult res;
+    cudaError_t e = device_build_leaf_accel(ctx->build_ws, (const float*)b.tris_aos.p, roots.data(), (uint32_t)roots.size(), (uint32_t)n_sub,
+                                            (float4*)b.sub_raw.p, (uint32_t*)b.sub_parent.p, (uint32_t*)b.sub_order.p, cfg.max_sub_leaf,
+                                            28u, ctx->stream, &res);
+    if (e != cudaSuccess) return fail(ctx, BVHT_ERR_CUDA, "device leaf-accelerator build failed: %s", cudaGetErrorString(e));
+    ctx->stats.kernel_launches += res.launches;
+    lap("alloc + topology build");
+    if (timing) fprintf(stderr, "[bvht timing] accel levels %u, sub nodes %u, depth %u\n", res.levels, res.n_nodes, res.max_depth);
+    if (res.max_depth + 2 > (uint32_t)kSubStack)
+        return fail(ctx, BVHT_ERR_MALFORMED_BVH, "leaf accelerator depth %u exceeds the stack bound %d", res.max_depth, kSubStack);
+    b.n_sub = (uint32_t)n_sub;
+    b.n_sub_nodes = res.n_nodes;
+    CU(ctx, launch_refit_sub_nodes((float4*)b.sub_raw.p, (const uint32_t*)b.sub_parent.p, (unsigned int*)b.sub_counters.p,
+                                   (const float*)b.tris_aos.p, (const uint32_t*)b.sub_order.p, b.n_sub_nodes, ctx->stream));
+    if ((rc = ensure(ctx, b.stri, (size_t)b.n_sub * 48))) return rc;
+    CU(ctx, launch_repack_sub_triangles((const float*)b.tris_aos.p, (const uint32_t*)b.sub_order.p, b.n_sub, (float4*)b.stri.p, ctx->stream));
+    ctx->stats.kernel_launches += 2;
+    double d_max = b.d_max > 0.0f ? (double)b.d_max : (double)cfg.d_max;
+    double o_max = b.o_max > 0.0f ? (double)b.o_max : (double)cfg.o_max_radii * b.radius;
+    lap("boxes + repack");
+    if ((rc = bake_accel(ctx, b, d_max, o_max))) return rc;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    lap("bake");
+    done = true;
+    return BVHT_OK;
+}
+
 int build_and_upload_accel(bvht_ctx* ctx, Blas& b) {
     LeafAccelConfig cfg;
     if (const char* e = getenv("BVHT_SUB_LEAF")) { int v = atoi(e); if (v >= 1 && v <= 8) cfg.max_sub_leaf = (uint32_t)v; }   // tuning knob
+    if (cfg.max_sub_leaf == 1 && !getenv("BVHT_ACCEL_HOST_BUILD")) {       // default: build it where the triangles are
+        bool done = false;
+        int rc = build_accel_device(ctx, b, cfg, done);
+        if (rc || done) return rc;
+    }
     LeafAccelHost acc;
     if (!build_leaf_accel(b.h_tris.data(), b.n_tris, b.h_nodes.data(), b.nodes_used, cfg, acc))
         return fail(ctx, BVHT_ERR_MALFORMED_BVH, "leaf accelerator build failed");
@@ -633,6 +704,15 @@ int make_blas(bvht_ctx* ctx, const float* tris, uint32_t n_tris, const bvht_bvh_
     int rc = validate_bvh(ctx, nodes, nodes_used, n_tris, parent, depth);
     if (rc) return rc;
 
+    const bool timing = getenv("BVHT_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        cudaStreamSynchronize(ctx->stream);
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bvht timing] blas  %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
     cudaEventRecord(ctx->ev_e, ctx->stream);
     b = Blas();
     b.alive = true; b.n_tris = n_tris; b.nodes_used = nodes_used;
@@ -648,7 +728,9 @@ int make_blas(bvht_ctx* ctx, const float* tris, uint32_t n_tris, const bvht_bvh_
     auto bail = [&](int code) { free_blas(b); return code; };
     if ((rc = ensure(ctx, b.nodes, flat.size() * 4))) return bail(rc);
     if ((rc = h2d(ctx, b.nodes.p, flat.data(), flat.size() * 4))) return bail(rc);
+    lap("nodes");
     if ((rc = upload_vertices(ctx, b, tris))) return bail(rc);
+    lap("vertices");
 
     // refit plan: leaves cut into chunks, parent links, arrival counters
     std::vector<uint32_t> chunk_leaf, chunk_first, chunk_count, leaf_chunks(nodes_used, 0);
@@ -671,7 +753,9 @@ int make_blas(bvht_ctx* ctx, const float* tris, uint32_t n_tris, const bvht_bvh_
     if ((rc = ensure(ctx, b.scratch, (size_t)nodes_used * 24))) return bail(rc);
     if ((rc = ensure(ctx, b.counters, (size_t)nodes_used * 4))) return bail(rc);
 
+    lap("refit plan");
     if (accel_on(ctx)) { if ((rc = build_and_upload_accel(ctx, b))) return bail(rc); }
+    lap("leaf accelerator");
 
     cudaEventRecord(ctx->ev_f, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);

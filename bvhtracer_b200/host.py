@@ -76,6 +76,8 @@ def lib():
             "bvhx_state_hits": (_P, [_P]),
             "bvhx_renderer_render": (C.c_int64, [_P, _P, _P]),
             "bvhx_renderer_sync_scene": (C.c_int, [_P, _P]),
+            "bvhx_renderer_build_model": (_P, [_P, _P]),
+            "bvhx_renderer_rebuild_model": (C.c_int, [_P, _P]),
             "bvhx_renderer_intersect": (C.c_int, [_P, _P, _P, C.c_uint64, _P]),
         }
         for name, (res, args) in sig.items():
@@ -412,6 +414,15 @@ class Renderer:
 
     def sync_scene(self, scene):
         if lib().bvhx_renderer_sync_scene(self._h, scene._h) != 0:
+            raise _err()
+
+    def build_model(self, mesh):
+        """ModelBuilder::new().with_mesh(mesh).build() with BvhBuilder::build_for running on the device; the model is resident."""
+        return ModelInstance(lib().bvhx_renderer_build_model(self._h, mesh._h))
+
+    def rebuild_model(self, model):
+        """Rebuild the model's BVH from its current vertices on the device (the alternative to refit)."""
+        if lib().bvhx_renderer_rebuild_model(self._h, model._h) != 0:
             raise _err()
 
     def intersect(self, scene, rays):

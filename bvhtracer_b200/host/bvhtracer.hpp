@@ -697,6 +697,44 @@ public:
     CudaPathTracer& operator=(const CudaPathTracer&) = delete;
     bvht_ctx* context() const { return ctx_; }
 
+    // ModelBuilder::build (model.rs:140-144) with BvhBuilder::build_for running ON THE DEVICE (bvht_blas_build): the model
+    // comes back with the reference's node pool and its primitives reordered in place, already resident for rendering.
+    ModelInstance build_model(Mesh mesh, TextureMaterial texture = TextureMaterial()) {
+        if (mesh.primitives.empty()) throw std::runtime_error("BvhBuilder::build_for: empty mesh (the reference indexes nodes[0] and panics)");
+        auto model = std::make_shared<Model>();
+        model->mesh = std::move(mesh);
+        model->texture_ = std::move(texture);
+        const uint32_t n = (uint32_t)model->mesh.primitives.size();
+        uint32_t id = 0, n_tris = 0, used = 0;
+        check(bvht_blas_build(ctx_, (const float*)model->mesh.primitives.data(), n, &id));
+        check(bvht_blas_info(ctx_, id, &n_tris, &used));
+        model->bvh.nodes.assign(2 * (size_t)n, BvhNode());
+        model->bvh.nodes_used = used;
+        check(bvht_blas_read_nodes(ctx_, id, (bvht_bvh_node*)model->bvh.nodes.data(), used));
+        check(bvht_blas_read_triangles(ctx_, id, (float*)model->mesh.primitives.data(), n));
+        upload_attributes(*model, id);
+        uploaded_.push_back(Uploaded{ model.get(), id, model->geometry_version });
+        return model;
+    }
+
+    // The "rebuild" alternative to ModelInstance::refit (benches/bench_bvh_refit_rebuild.rs) for a model whose vertices moved
+    void rebuild_model(Model& m) {
+        Uploaded* u = find(&m);
+        if (!u) throw std::runtime_error("rebuild_model: the model is not resident on this integrator");
+        if (u->version != m.geometry_version)
+            check(bvht_blas_update_vertices(ctx_, u->blas_id, (const float*)m.primitives().data(), (uint32_t)m.primitives().size()));
+        check(bvht_blas_rebuild(ctx_, u->blas_id));
+        uint32_t n_tris = 0, used = 0;
+        check(bvht_blas_info(ctx_, u->blas_id, &n_tris, &used));
+        m.bvh.nodes.assign(2 * (size_t)n_tris, BvhNode());
+        m.bvh.nodes_used = used;
+        check(bvht_blas_read_nodes(ctx_, u->blas_id, (bvht_bvh_node*)m.bvh.nodes.data(), used));
+        check(bvht_blas_read_triangles(ctx_, u->blas_id, (float*)m.mesh.primitives.data(), n_tris));
+        m.refit_requested = false;
+        u->version = m.geometry_version;
+        scene_ = nullptr;                                                   // bounds changed: the next frame re-sends the TLAS
+    }
+
     void sync_scene(Scene& scene) {
         // (1) models
         std::vector<uint32_t> blas_ids(scene.objects().size());
@@ -709,12 +747,7 @@ public:
                 check(bvht_blas_create(ctx_, (const float*)m->primitives().data(), (uint32_t)m->primitives().size(),
                                        (const bvht_bvh_node*)m->bvh.nodes.data(), m->bvh.nodes_used, &u->blas_id));
                 u->version = m->geometry_version;
-                if (m->normals().size() == m->primitives().size())
-                    check(bvht_blas_set_normals(ctx_, u->blas_id, (const float*)m->normals().data(), (uint32_t)m->normals().size()));
-                if (m->tex_coords().size() == m->primitives().size())
-                    check(bvht_blas_set_tex_coords(ctx_, u->blas_id, (const float*)m->tex_coords().data(), (uint32_t)m->tex_coords().size()));
-                if (!m->texture().empty())
-                    check(bvht_blas_set_texture(ctx_, u->blas_id, m->texture().rgb.data(), m->texture().width, m->texture().height));
+                upload_attributes(*m, u->blas_id);
             } else if (u->version != m->geometry_version || m->refit_requested) {
                 if (u->version != m->geometry_version)
                     check(bvht_blas_update_vertices(ctx_, u->blas_id, (const float*)m->primitives().data(), (uint32_t)m->primitives().size()));
@@ -760,6 +793,14 @@ public:
     }
 private:
     struct Uploaded { Model* model; uint32_t blas_id; uint64_t version; };
+    void upload_attributes(const Model& m, uint32_t blas_id) {
+        if (m.normals().size() == m.primitives().size())
+            check(bvht_blas_set_normals(ctx_, blas_id, (const float*)m.normals().data(), (uint32_t)m.normals().size()));
+        if (m.tex_coords().size() == m.primitives().size())
+            check(bvht_blas_set_tex_coords(ctx_, blas_id, (const float*)m.tex_coords().data(), (uint32_t)m.tex_coords().size()));
+        if (!m.texture().empty())
+            check(bvht_blas_set_texture(ctx_, blas_id, m.texture().rgb.data(), m.texture().width, m.texture().height));
+    }
     Uploaded* find(Model* m) { for (auto& u : uploaded_) if (u.model == m) return &u; return nullptr; }
     void check(int rc) { if (rc != BVHT_OK) throw std::runtime_error(std::string(bvht_status_string(rc)) + ": " + bvht_last_error(ctx_)); }
     bvht_ctx* ctx_ = nullptr;

@@ -184,6 +184,14 @@ BVHX_API int64_t bvhx_renderer_render(void* renderer, void* state, void* scene) 
 BVHX_API int bvhx_renderer_sync_scene(void* renderer, void* scene) {
     return guard([&]() -> int { ((CudaPathTracer*)((Renderer*)renderer)->integrator())->sync_scene(*(Scene*)scene); return 0; }, -1);
 }
+BVHX_API void* bvhx_renderer_build_model(void* renderer, void* mesh) {
+    return guard([&]() -> void* {
+        return new ModelInstance(((CudaPathTracer*)((Renderer*)renderer)->integrator())->build_model(*(Mesh*)mesh));
+    }, nullptr);
+}
+BVHX_API int bvhx_renderer_rebuild_model(void* renderer, void* model) {
+    return guard([&]() -> int { ((CudaPathTracer*)((Renderer*)renderer)->integrator())->rebuild_model(**(ModelInstance*)model); return 0; }, -1);
+}
 BVHX_API int bvhx_renderer_intersect(void* renderer, void* scene, const bvht_ray* rays, uint64_t n, bvht_hit* out) {
     return guard([&]() -> int { ((CudaPathTracer*)((Renderer*)renderer)->integrator())->intersect(*(Scene*)scene, rays, n, out); return 0; }, -1);
 }

@@ -101,3 +101,41 @@ def test_rebuild_after_animation_matches_host_rebuild(flags):
             got = eng.trace_primary(SB.to_ffi_camera(cam), 256, 144)
             assert got.tobytes() == ref.tobytes()
             anim = examples.BigBenAnimation(rebuilt.tris)    # keep animating the reordered mesh, like the example would
+
+
+def test_host_mirror_builds_models_on_the_device():
+    # ModelBuilder::build through CudaPathTracer::build_model: same Model as the host build (nodes, reordered primitives),
+    # renders the same frames; rebuild_model after an animation step equals a host rebuild of the moved mesh.
+    from bvhtracer_b200 import host
+    spec = examples.sixteen_armadillos(3)
+    renderer = host.Renderer(flags=FLAG_STRICT | FLAG_LEAF_ACCEL)
+    mesh = host.load_asset_mesh("armadillo.tri")
+    on_device = renderer.build_model(mesh)
+    on_host = host.ModelBuilder().with_mesh(host.load_asset_mesh("armadillo.tri")).build()
+    nd, ud = on_device.nodes(); nh, uh = on_host.nodes()
+    assert ud == uh and nd[:ud].tobytes() == nh[:uh].tobytes()
+    assert on_device.primitives().tobytes() == on_host.primitives().tobytes()
+    scene, _ = host.build_scene(spec, models=[on_device])
+    w, h = 320, 180
+    state = host.RendererState(host.depth_pipeline(), w, h, keep_hits=True)
+    renderer.render(state, scene)
+    ref_scene, ref_cam = SB.oracle_scene(spec)
+    assert state.hits().tobytes() == ref_scene.render(ref_cam, w, h, threads=NTHREADS).tobytes()
+
+    # big_ben: animate, rebuild on the device, compare with the oracle's rebuild
+    bb = renderer.build_model(host.load_asset_mesh("bigben.tri"))
+    anim = examples.BigBenAnimation(bb.primitives())
+    moved = anim.animate()
+    bb.set_primitives(moved)
+    renderer.rebuild_model(bb)
+    ref = O.Blas(moved)
+    nodes, used = bb.nodes()
+    assert used == ref.nodes_used and nodes[:used].tobytes() == ref.nodes[:used].tobytes()
+    assert bb.primitives().tobytes() == ref.tris.tobytes()
+    spec5 = examples.big_ben_clock()
+    scene5, _ = host.build_scene(spec5, models=[bb])
+    state5 = host.RendererState(host.intersection_pipeline(), 256, 144, keep_hits=True)
+    renderer.render(state5, scene5)
+    _, cam5 = SB.oracle_scene(spec5)
+    ref_scene5 = O.Scene([ref], [(0, O.mat4_identity())], with_transform=False)
+    assert state5.hits().tobytes() == ref_scene5.render(cam5, 256, 144, threads=NTHREADS).tobytes()
