@@ -59,6 +59,11 @@ extern "C" {
     pub fn bvht_last_error(ctx: *const BvhtCtx) -> *const c_char;
     pub fn bvht_status_string(status: c_int) -> *const c_char;
     pub fn bvht_blas_create(ctx: *mut BvhtCtx, tris: *const f32, n_tris: u32, nodes: *const BvhtBvhNode, nodes_used: u32, out_id: *mut u32) -> c_int;
+    pub fn bvht_blas_build(ctx: *mut BvhtCtx, tris: *const f32, n_tris: u32, out_id: *mut u32) -> c_int;
+    pub fn bvht_blas_rebuild(ctx: *mut BvhtCtx, id: u32) -> c_int;
+    pub fn bvht_blas_info(ctx: *mut BvhtCtx, id: u32, n_tris: *mut u32, nodes_used: *mut u32) -> c_int;
+    pub fn bvht_blas_read_triangles(ctx: *mut BvhtCtx, id: u32, out: *mut f32, n_tris: u32) -> c_int;
+    pub fn bvht_blas_read_permutation(ctx: *mut BvhtCtx, id: u32, out: *mut u32, n_tris: u32) -> c_int;
     pub fn bvht_blas_set_normals(ctx: *mut BvhtCtx, id: u32, normals: *const f32, n_tris: u32) -> c_int;
     pub fn bvht_blas_set_tex_coords(ctx: *mut BvhtCtx, id: u32, tex_coords: *const f32, n_tris: u32) -> c_int;
     pub fn bvht_blas_set_texture(ctx: *mut BvhtCtx, id: u32, rgb: *const u8, width: u32, height: u32) -> c_int;
