@@ -32,3 +32,21 @@ for flags in (0, 2, 3):
         models2[0].refit()
         r.render(st2, scene2)
     print("flags", flags, "ok", int(st.frame_buffer().sum() % 1000), int(st2.frame_buffer().sum() % 1000))
+
+# device-side construction (K5) + textured quad + a far ray batch (re-bake path)
+r = host.Renderer(flags=2)
+m = r.build_model(host.load_asset_mesh("teapot.obj"))
+bb = r.build_model(host.load_asset_mesh("unity.tri"))
+bb.set_primitives(examples.BigBenAnimation(bb.primitives()).animate())
+r.rebuild_model(bb)
+mesh = host.Mesh.from_triangles(examples.QUAD_TRIS, examples.QUAD_NORMALS).set_tex_coords(examples.QUAD_TEX_COORDS)
+quad = host.ModelBuilder().with_mesh(mesh).with_texture(examples.brick_texture(32, 16)).build()
+scene3, _ = host.build_scene(examples.quad_example(4), models=[quad])
+st3 = host.RendererState(host.texture_pipeline(), 96, 96, keep_hits=False)
+r.render(st3, scene3)
+scene4, _ = host.build_scene(examples.trippy_teapots(2), models=[m])
+st4 = host.RendererState(host.normal_pipeline(), 128, 72, keep_hits=True)
+r.render(st4, scene4)
+far = np.array([[300, 200, -500, -0.3, -0.2, 0.5, 3.0e38], [0, 1, -5.5, 0.1, 0, 40.0, 3.0e38]], np.float32)
+r.intersect(scene4, far)
+print("device build ok", int(st3.frame_buffer().sum() % 1000), int(st4.frame_buffer().sum() % 1000))
