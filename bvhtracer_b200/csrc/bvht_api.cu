@@ -42,6 +42,7 @@ struct Blas {
     uint32_t n_tris = 0, nodes_used = 0;
     std::vector<bvht_bvh_node> h_nodes;     // host copy of the uploaded node pool (topology for validation / accel)
     std::vector<float> h_tris;              // host copy of the vertices (needed to rebuild the leaf accelerator)
+    bool global_accel = false;              // fast mode: ONE sub-BVH over the whole model instead of one per reference leaf
     std::vector<uint32_t> perm;             // device-built models: perm[i] = index, in the caller's array, of the triangle at i
     DevBuf tris_aos, nodes, tri, normals;      // normals: 3 float4 per primitive, ORIGINAL primitive order
     DevBuf tex_coords, texels;                 // 3 float2 per primitive (ORIGINAL order); Rgb<u8> texture, row-major
@@ -251,7 +252,14 @@ int build_accel_device(bvht_ctx* ctx, Blas& b, const LeafAccelConfig& cfg, bool&
     std::vector<SubRoot> roots;
     std::vector<uint32_t> leaf_sub_root(b.nodes_used, 0xFFFFFFFFu);
     uint64_t n_sub = 0;
-    for (uint32_t ni = 0; ni < b.nodes_used; ++ni) {
+    // Fast mode does not have to follow the reference's tree node by node (its bar is >= 99.99 % identical ids, t within
+    // 1e-5): ONE sub-BVH over all triangles can replace the walk through the reference's overlapping leaves; ties in t
+    // between different triangles then resolve to the lowest primitive index instead of the reference's visiting order.
+    // Measured on B200 (tools/quick_bench.py, 4K/8K): two_armadillos +14 %, sixteen_armadillos +5..9 %, trippy_teapots -5 %,
+    // big_ben_clock -25 % -- not a uniform win, so it is opt-in (BVHT_FAST_GLOBAL=1) and the default keeps one tree per leaf.
+    b.global_accel = (ctx->flags & BVHT_FLAG_FAST) != 0 && b.n_tris > cfg.max_sub_leaf && b.n_tris >= 2 && getenv("BVHT_FAST_GLOBAL");
+    if (b.global_accel) { roots.push_back(SubRoot{ 0u, b.n_tris, 0u }); n_sub = b.n_tris; }
+    for (uint32_t ni = 0; ni < b.nodes_used && !b.global_accel; ++ni) {
         if (ni == 1) continue;
         const bvht_bvh_node& n = b.h_nodes[ni];
         if (n.prim_count == 0 || n.prim_count < cfg.min_leaf_tris || n.prim_count <= cfg.max_sub_leaf) continue;
@@ -378,7 +386,7 @@ int refresh_blas_desc(bvht_ctx* ctx) {
         o.tri = (const float4*)b.tri.p;
         o.sub_nodes = (const float4*)b.sub_nodes.p;
         o.stri = (const float4*)b.stri.p;
-        o.leaf_sub_root = (const uint32_t*)b.leaf_sub_root.p;
+        o.leaf_sub_root = b.global_accel ? nullptr : (const uint32_t*)b.leaf_sub_root.p;   // null = "sub node 0 is the model's root"
         o.n_tris = b.n_tris; o.nodes_used = b.nodes_used;
         o.accel_d_max = b.d_max; o.accel_o_max = b.o_max;
     }

@@ -277,11 +277,25 @@ __device__ __forceinline__ void leaf_accel(const BlasDesc& B, uint32_t sub_root,
 template <bool ACCEL>
 __device__ __forceinline__ void blas_intersect(const BlasDesc& B, const RayM& r, float entry_t, bool use_accel,
                                                float& best_t, float& best_u, float& best_v, uint32_t& best_prim, bool& found, Stat& st) {
+    best_t = entry_t;
+    found = false;
+#ifdef BVHT_FAST_MODE
+    if (ACCEL && use_accel && B.leaf_sub_root == nullptr) {
+        // fast mode: one sub-BVH over the whole model (sub node 0), closest hit = lexicographic min (t, primitive index)
+        st.add(4);
+        leaf_accel(B, 0u, r, entry_t, best_t, best_u, best_v, best_prim, found, st);
+        if (found) {
+            const float4* tp = B.tri + 3 * (size_t)best_prim;
+            float t = best_t, u = best_u, v = best_v;
+            mt_exact_rn(ldg4(tp + 0), ldg4(tp + 1), ldg4(tp + 2), r, entry_t, t, u, v);
+            if (t < entry_t) { best_t = t; best_u = u; best_v = v; }
+        }
+        return;
+    }
+#endif
     uint32_t stack[kBlasStack];
     int sp = 0;
     uint32_t ni = 0;                       // root: its AABB is never tested (bvh.rs:243)
-    best_t = entry_t;
-    found = false;
     float4 n0 = ldg4(B.nodes + 0);
     float4 n1 = ldg4(B.nodes + 1);
     for (;;) {
