@@ -61,6 +61,8 @@ def build(force=False, verbose=False):
     extra_defs = []
     if os.environ.get("BVHT_MIN_BLOCKS"):            # tuning knob: register budget of the trace kernels
         extra_defs.append("-DBVHT_MIN_BLOCKS=" + os.environ["BVHT_MIN_BLOCKS"])
+    if os.environ.get("BVHT_GRAB"):                  # tuning knob: 32-pixel slices pulled per work-counter atomic
+        extra_defs.append("-DBVHT_GRAB=" + os.environ["BVHT_GRAB"])
     os.makedirs(LIB_DIR, exist_ok=True)
     os.makedirs(OBJ_DIR, exist_ok=True)
     objs = []
