@@ -1364,9 +1364,25 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
     CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     for (int i = 0; i < 2; ++i) CU(ctx, cudaStreamWaitEvent(ctx->aux[i], ctx->ev_fork, 0));
     CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
+    // Band shares are triangular (1, 2, 3, .., 3, 2, 1): the device->host copy of a band overlaps the tracing of the following
+    // ones, so only the FIRST band's tracing (nothing to copy yet; matters when the copy is the bottleneck, e.g. 16 B hit records)
+    // and the LAST band's copy (matters when tracing is the bottleneck) are exposed -- both are made small.
+    // BVHT_BANDS_UNIFORM=1 restores equal bands (A/B knob).
+    static const bool uniform_bands = getenv("BVHT_BANDS_UNIFORM") != nullptr;
+    std::vector<uint32_t> band_start(n_bands + 1, 0);
+    {
+        uint64_t wsum = 0, acc = 0;
+        for (uint32_t b = 0; b < n_bands; ++b) wsum += uniform_bands ? 1 : std::min(b + 1, n_bands - b);
+        for (uint32_t b = 0; b < n_bands; ++b) {
+            band_start[b] = (uint32_t)((uint64_t)tile_rows * acc / wsum);
+            acc += uniform_bands ? 1 : std::min(b + 1, n_bands - b);
+        }
+        band_start[n_bands] = tile_rows;
+    }
+    auto band_row = [&](uint32_t b) -> uint32_t { return band_start[b]; };
     for (uint32_t b = 0; b < n_bands; ++b) {
-        uint32_t r0 = ty0 + (uint32_t)((uint64_t)tile_rows * b / n_bands);
-        uint32_t r1 = ty0 + (uint32_t)((uint64_t)tile_rows * (b + 1) / n_bands);
+        uint32_t r0 = ty0 + band_row(b);
+        uint32_t r1 = ty0 + band_row(b + 1);
         bvht_rect band = { region.x0, std::max(region.y0, r0 * tile), region.x1, std::min(region.y1, r1 * tile) };
         if (band.y0 >= band.y1) continue;
         cudaStream_t cs = ctx->aux[b & 1];

@@ -25,6 +25,18 @@ def _f3(v):
     return (C.c_float * 3)(*[float(x) for x in v])
 
 
+def _release(obj, free_name):
+    """Handle destructor; at interpreter shutdown module globals may already be gone, then the OS reclaims everything."""
+    h = getattr(obj, "_h", None)
+    if not h or _lib is None:
+        return
+    try:
+        getattr(_lib, free_name)(h)
+    except Exception:
+        pass
+    obj._h = None
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -137,9 +149,10 @@ class Mesh:
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(max(n, 1), 9))[:n].copy()
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().bvhx_mesh_free(self._h)
-            self._h = None
+        try:
+            _release(self, "bvhx_mesh_free")
+        except Exception:          # interpreter shutdown: module globals already cleared
+            pass
 
 
 class TriMeshDecoder:
@@ -188,9 +201,10 @@ class ModelInstance:
         lib().bvhx_model_refit(self._h)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().bvhx_model_free(self._h)
-            self._h = None
+        try:
+            _release(self, "bvhx_model_free")
+        except Exception:          # interpreter shutdown: module globals already cleared
+            pass
 
 
 class ModelBuilder:
@@ -277,9 +291,10 @@ class Camera:
         return out
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().bvhx_camera_free(self._h)
-            self._h = None
+        try:
+            _release(self, "bvhx_camera_free")
+        except Exception:          # interpreter shutdown: module globals already cleared
+            pass
 
 
 # ------------------------------------------------------------------ scene
@@ -320,9 +335,10 @@ class Scene:
         return out
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().bvhx_scene_free(self._h)
-            self._h = None
+        try:
+            _release(self, "bvhx_scene_free")
+        except Exception:          # interpreter shutdown: module globals already cleared
+            pass
 
 
 class SceneBuilder:
@@ -368,9 +384,10 @@ class RendererState:
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(self.width * self.height * 16,)).view(HIT)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().bvhx_state_free(self._h)
-            self._h = None
+        try:
+            _release(self, "bvhx_state_free")
+        except Exception:          # interpreter shutdown: module globals already cleared
+            pass
 
 
 def depth_pipeline(scale=80.0, offset=3.0):
@@ -452,9 +469,10 @@ class Renderer:
             raise HostError(f"bvht_set_stream failed: {rc}")
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().bvhx_renderer_free(self._h)
-            self._h = None
+        try:
+            _release(self, "bvhx_renderer_free")
+        except Exception:          # interpreter shutdown: module globals already cleared
+            pass
 
 
 # ------------------------------------------------------------------ example scenes through the mirror
