@@ -139,3 +139,27 @@ def test_host_mirror_builds_models_on_the_device():
     _, cam5 = SB.oracle_scene(spec5)
     ref_scene5 = O.Scene([ref], [(0, O.mat4_identity())], with_transform=False)
     assert state5.hits().tobytes() == ref_scene5.render(cam5, 256, 144, threads=NTHREADS).tobytes()
+
+
+def test_device_build_at_the_maximum_primitive_count():
+    # 2^20 triangles: the 20-bit primitive index of InstancePrimitiveIndex is the limit of the boundary (bvht.h);
+    # 2049 chunks at the root, a 258-node tree, the leaf accelerator over 1 M triangles on top of it
+    rng = np.random.default_rng(1)
+    n = 1 << 20
+    c = rng.uniform(-30, 30, (n, 1, 3))
+    tris = (c + rng.normal(size=(n, 3, 3)) * 0.05).astype(F).reshape(n, 9)
+    with Engine(flags=FLAG_STRICT | FLAG_LEAF_ACCEL) as eng:
+        bid = eng.blas_build(tris)
+        ref = assert_same_build(eng, bid, tris)
+        assert ref.nodes_used > 100
+        # and it traces: a handful of rays against the brute-force answer of the oracle
+        scene = O.Scene([ref], [(0, O.mat4_identity())])
+        rays = np.zeros((64, 7), F)
+        rays[:, 0:3] = rng.uniform(-40, 40, (64, 3)); rays[:, 2] = -80
+        rays[:, 5] = 1.0; rays[:, 6] = O.FLT_MAX
+        SB.upload_scene(eng, scene, blas_ids=[bid])
+        got = eng.trace_rays(rays)
+        exp = scene.trace_rays(rays, threads=NTHREADS)
+        assert got.tobytes() == exp.tobytes()
+        with pytest.raises(BvhtError):
+            eng.blas_build(np.zeros((n + 1, 9), F))          # one more than the index can address
