@@ -7,25 +7,25 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np
 import torch
 
-import scene_build as SB
-from bvhtracer_b200 import Engine, FLAG_LEAF_ACCEL, FLAG_STRICT, examples
+from bvhtracer_b200 import FLAG_LEAF_ACCEL, FLAG_STRICT, examples, host
 
 
 def main():
     w, h = 3840, 2160
-    scene, cam = SB.oracle_scene(examples.sixteen_armadillos(0))
-    fcam = SB.to_ffi_camera(cam)
+    scene, _ = host.build_scene(examples.sixteen_armadillos(0))
+    fcam = scene.camera()
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    with Engine(flags=FLAG_STRICT | FLAG_LEAF_ACCEL) as eng:
-        eng.set_stream(stream.cuda_stream)
-        SB.upload_scene(eng, scene)
+    renderer = host.Renderer(flags=FLAG_STRICT | FLAG_LEAF_ACCEL)
+    renderer.set_stream(stream.cuda_stream)
+    renderer.sync_scene(scene)
+    eng = renderer.engine()
+    if True:
         dout = eng.device_alloc(w * h * 16)
         dsmall = eng.device_alloc(128 * 72 * 16)
 

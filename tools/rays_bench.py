@@ -6,12 +6,10 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np
 
-import scene_build as SB
-from bvhtracer_b200 import Engine, FLAG_LEAF_ACCEL, FLAG_STRICT, examples
+from bvhtracer_b200 import FLAG_LEAF_ACCEL, FLAG_STRICT, _ffi, examples, host
 
 F = np.float32
 
@@ -29,15 +27,17 @@ def batch(rng, n, spread, scale_dirs):
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 22
-    scene, _ = SB.oracle_scene(examples.sixteen_armadillos(0))
+    scene, _ = host.build_scene(examples.sixteen_armadillos(0))
     rng = np.random.default_rng(5)
     cases = {"near (|o|~6, unit d)": batch(rng, n, 6.0, False), "far (|o|~300, unit d)": batch(rng, n, 300.0, False),
              "far, |d| in [0.01,40]x": batch(rng, n, 300.0, True)}
     for cname, rays in cases.items():
         outs = {}
         for mname, flags in (("brute", FLAG_STRICT), ("accel", FLAG_STRICT | FLAG_LEAF_ACCEL)):
-            with Engine(flags=flags) as eng:
-                SB.upload_scene(eng, scene)
+            renderer = host.Renderer(flags=flags)
+            renderer.sync_scene(scene)
+            eng = renderer.engine()
+            if True:
                 drays = eng.device_alloc(rays.nbytes)
                 dout = eng.device_alloc(n * 16)
                 eng.memcpy_h2d(drays, rays)
@@ -46,11 +46,12 @@ def main():
                     eng.trace_rays_device(drays, n, dout)
                     eng.sync()
                     ms.append(eng.stats()["last_trace_ms"])
-                host = np.zeros(n, dtype=SB._ffi.HIT)
-                eng.memcpy_d2h(host, dout)
+                hits = np.zeros(n, dtype=_ffi.HIT)
+                eng.memcpy_d2h(hits, dout)
                 eng.device_free(drays); eng.device_free(dout)
-            outs[mname] = host
-            print(f"{cname:26s} {mname:6s} {min(ms):9.3f} ms {n / min(ms) / 1e3:10.1f} Mrays/s hits={(host['id'] != 0xFFFFFFFF).mean():.3f}", flush=True)
+            del eng, renderer
+            outs[mname] = hits
+            print(f"{cname:26s} {mname:6s} {min(ms):9.3f} ms {n / min(ms) / 1e3:10.1f} Mrays/s hits={(hits['id'] != 0xFFFFFFFF).mean():.3f}", flush=True)
         print(f"{cname:26s} accel == brute bit-for-bit: {outs['accel'].tobytes() == outs['brute'].tobytes()}", flush=True)
 
 
