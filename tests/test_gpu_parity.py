@@ -556,6 +556,37 @@ def test_fast_mode_full_size_against_strict_gpu(name, arg, size):
             assert_fast(res[label], res["strict"])
 
 
+# ------------------------------------------------------------------------------------------ full size vs the oracle, sampled
+@pytest.mark.parametrize("name,arg,size", [("two_armadillos", "canonical", (1920, 1080)), ("sixteen_armadillos", 0, (3840, 2160)),
+                                           ("sixteen_armadillos", 17, (3840, 2160)), ("trippy_teapots", 10, (3840, 2160)),
+                                           ("big_ben_clock", None, (7680, 4320))])
+def test_full_size_frames_match_the_oracle_on_sampled_tiles(name, arg, size):
+    # BASELINE.json's own resolutions: the whole frame is traced on the GPU (strict, leaf accelerator), the oracle re-traces
+    # 320 of its 8x8 tiles -- half drawn among tiles that contain hits, half anywhere -- and every record must be identical
+    spec = examples.CONFIGS[name]() if arg is None else examples.CONFIGS[name](arg)
+    scene, cam = SB.oracle_scene(spec)
+    w, h = size
+    with Engine(flags=FLAG_STRICT | FLAG_LEAF_ACCEL) as eng:
+        SB.upload_scene(eng, scene)
+        got = eng.trace_primary(SB.to_ffi_camera(cam), w, h).reshape(h, w)
+    rng = np.random.default_rng(2024)
+    tw, th = w // 8, h // 8
+    hit_tiles = np.argwhere((got["id"] != O.MISS_ID).reshape(th, 8, tw, 8).any(axis=(1, 3)))
+    assert len(hit_tiles) > 200
+    picks = [tuple(hit_tiles[i]) for i in rng.choice(len(hit_tiles), 160, replace=False)]
+    picks += [(int(rng.integers(th)), int(rng.integers(tw))) for _ in range(160)]
+    ref = np.zeros(w * h, O.HIT); ref["t"] = O.FLT_MAX; ref["id"] = O.MISS_ID
+    n_hits = 0
+    for ty, tx in picks:
+        region = (tx * 8, ty * 8, tx * 8 + 8, ty * 8 + 8)
+        scene.render(cam, w, h, region=region, out=ref)
+        a = got[ty * 8:ty * 8 + 8, tx * 8:tx * 8 + 8]
+        b = ref.reshape(h, w)[ty * 8:ty * 8 + 8, tx * 8:tx * 8 + 8]
+        assert a.tobytes() == b.tobytes(), (name, arg, tx, ty)
+        n_hits += int((b["id"] != O.MISS_ID).sum())
+    assert n_hits > 2000
+
+
 # ------------------------------------------------------------------------------------------ NormalMappingAccumulator
 @pytest.mark.parametrize("name,arg,asset", [("trippy_teapots", 6, "teapot.obj"), ("cube", None, "cube.obj")])
 def test_normal_mapping_shader_matches_oracle(name, arg, asset):
