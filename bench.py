@@ -416,7 +416,19 @@ def run_ours(args, rank, local_rank, world):
                 traffic = json.load(open(tp)).get(args.mode)
             except Exception:
                 traffic = None
+        # the same algorithmic bytes against the L2 -> SM read bandwidth measured here with the library's
+        # own streaming kernel, and the algorithmic f32 operations against the non-FMA issue peak
+        try:
+            l2_gbs = max(eng.debug_read_bandwidth(64 << 20, 50) for _ in range(2))
+        except Exception:
+            l2_gbs = None
+        fp32_peak_tops = 148 * 128 * 1.965e9 / 1e12
+        fp32_tops = f_per_ray * rays_per_launch / (kernel_ms_local * 1e-3) / 1e12
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "l2": {"peak": l2_gbs, "unit": "GB/s", "frac": (achieved / l2_gbs) if l2_gbs else None,
+                       "peak_source": "measured in this run: bvht_debug_read_bandwidth, 64 MiB buffer (L2-resident), 50 sweeps"},
+                "fp32": {"achieved": fp32_tops, "peak": fp32_peak_tops, "unit": "Tops/s (one op per add/mul/div/min/max lane, no FMA credit)",
+                         "frac": fp32_tops / fp32_peak_tops},
                 "kernel": "trace_primary_kernel", "launch_ms": kernel_ms_local, "algorithmic_bytes_per_ray": b_per_ray,
                 "algorithmic_fp32_ops_per_ray": f_per_ray, "source": src, "peak_source": peak_src,
                 "compulsory_hbm_gbs": 16.0 * rays_per_launch / (kernel_ms_local * 1e-3) / 1e9,

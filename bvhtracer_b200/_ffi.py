@@ -98,6 +98,7 @@ SYMBOLS = [
     ("bvht_ipc_open", C.c_int, [_P, _P, C.POINTER(_P)]),
     ("bvht_ipc_close", C.c_int, [_P, _P]),
     ("bvht_get_stats", C.c_int, [_P, C.POINTER(Stats)]),
+    ("bvht_debug_read_bandwidth", C.c_int, [_P, C.c_size_t, C.c_uint32, C.POINTER(C.c_double)]),
     ("bvht_debug_trace_stats", C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, Rect, _P]),
 ]
 

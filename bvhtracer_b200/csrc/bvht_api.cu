@@ -1572,6 +1572,29 @@ int bvht_ipc_close(bvht_ctx* ctx, void* device_ptr) {
     return BVHT_OK;
 }
 
+int bvht_debug_read_bandwidth(bvht_ctx* ctx, size_t bytes, uint32_t passes, double* gbs_out) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (!gbs_out || bytes < (1u << 16) || bytes % 4096 != 0 || passes == 0) return fail(ctx, BVHT_ERR_INVALID_ARG, "bad probe arguments");
+    cudaSetDevice(ctx->device);
+    void* buf = nullptr; unsigned long long* sink = nullptr;
+    CU(ctx, cudaMalloc(&buf, bytes));
+    if (cudaMalloc((void**)&sink, 8) != cudaSuccess) { cudaFree(buf); return fail(ctx, BVHT_ERR_OUT_OF_MEMORY, "probe allocation failed"); }
+    cudaMemsetAsync(buf, 1, bytes, ctx->stream); cudaMemsetAsync(sink, 0, 8, ctx->stream);
+    // each CTA reads n_vec / grid vectors per pass: `passes` full sweeps of the buffer by the grid as a whole
+    const int grid = ctx->sm_count * 8;
+    cudaError_t e = launch_read_bw(buf, bytes, 2, grid, sink, ctx->stream);           // warm-up: pulls the buffer into L2
+    cudaEventRecord(ctx->ev_e, ctx->stream);
+    if (e == cudaSuccess) e = launch_read_bw(buf, bytes, passes, grid, sink, ctx->stream);
+    cudaEventRecord(ctx->ev_f, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    float ms = 0.0f; cudaEventElapsedTime(&ms, ctx->ev_e, ctx->ev_f);
+    cudaFree(buf); cudaFree(sink);
+    ctx->stats.kernel_launches += 2;
+    if (e != cudaSuccess || e2 != cudaSuccess) return fail(ctx, BVHT_ERR_CUDA, "bandwidth probe failed");
+    *gbs_out = (double)bytes * passes / ((double)ms * 1e-3) / 1e9;
+    return BVHT_OK;
+}
+
 int bvht_debug_trace_stats(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height, uint32_t tile,
                            bvht_rect region, uint64_t counters_out[16]) {
     if (!ctx) return BVHT_ERR_BAD_HANDLE;

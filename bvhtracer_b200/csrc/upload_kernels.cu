@@ -160,7 +160,31 @@ ray_bounds_kernel(const float* __restrict__ rays, unsigned long long n, unsigned
     if ((threadIdx.x & 31) == 0) { atomicMax(out + 0, __float_as_uint(mo)); atomicMax(out + 1, __float_as_uint(md)); }
 }
 
+// Read-bandwidth probe: every CTA streams the whole buffer `iters` times with 16-byte loads.  With a buffer that fits in L2
+// this measures the L2 -> SM delivery rate the roofline of an L2-resident traversal should be compared with (SURVEY.md 8d ii);
+// with a buffer far larger than L2 it measures HBM.
+__global__ void __launch_bounds__(256)
+read_bw_kernel(const uint4* __restrict__ buf, size_t n_vec, uint32_t iters, unsigned long long* sink) {
+    unsigned int acc = 0;
+    for (uint32_t it = 0; it < iters; ++it) {
+        // rotate the start per CTA and iteration so that CTAs do not march in lock step over the same lines
+        size_t start = ((size_t)blockIdx.x * 977 + (size_t)it * 131) * 256 % n_vec;
+        for (size_t i = threadIdx.x; i < n_vec; i += 256 * (size_t)gridDim.x) {
+            size_t j = start + i + (size_t)blockIdx.x * 256;
+            j = j % n_vec;
+            uint4 v = __ldcg(buf + j);
+            acc += v.x ^ v.y ^ v.z ^ v.w;
+        }
+    }
+    if (acc == 0x9E3779B9u) atomicAdd(sink, 1ull);      // keeps the loads alive
+}
+
 } // namespace
+
+cudaError_t launch_read_bw(const void* buf, size_t bytes, uint32_t iters, int grid, unsigned long long* sink, cudaStream_t s) {
+    read_bw_kernel<<<grid, 256, 0, s>>>((const uint4*)buf, bytes / 16, iters, sink);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_ray_bounds(const float* rays, unsigned long long n, unsigned int* out2, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(out2, 0, 8, s);

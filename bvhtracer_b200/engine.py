@@ -219,6 +219,12 @@ class Engine:
     COUNTER_NAMES = ["rays", "tlas_pairs", "instance_entries", "blas_pairs", "ref_leaves", "brute_tris", "sub_pairs", "sub_tris",
                      "accel_fallbacks", "hits"]
 
+    def debug_read_bandwidth(self, nbytes, passes=20):
+        """GB/s of the library's streaming read kernel over an nbytes buffer (fits in L2 -> L2 bandwidth; >> L2 -> HBM)."""
+        g = C.c_double()
+        self._check(self._lib.bvht_debug_read_bandwidth(self._ctx, int(nbytes), int(passes), C.byref(g)))
+        return float(g.value)
+
     def debug_trace_stats(self, camera, width, height, tile=8, region=None):
         """Per-frame work counters of an instrumented strict kernel (not a product path)."""
         camera = np.ascontiguousarray(camera)

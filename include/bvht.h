@@ -280,6 +280,10 @@ BVHT_API int         bvht_get_stats(const bvht_ctx* ctx, bvht_stats* out);
  * [0] rays, [1] TLAS pair tests, [2] instance entries, [3] reference BLAS pair tests, [4] reference leaves
  * visited, [5] brute-force triangle tests, [6] sub-BVH pair tests, [7] sub-BVH triangle tests,
  * [8] accel fallbacks, [9] hits, [10..15] reserved.  Not a product path. */
+/* Measurement helper: read bandwidth (GB/s) of `passes` sweeps over a `bytes`-sized device buffer with this library's own
+ * streaming kernel -- L2 -> SM delivery when the buffer fits in L2 (e.g. 32 MiB), HBM when it is much larger (e.g. 2 GiB).
+ * bench.py records it next to MEASURED_PEAKS.json's HBM figure. */
+BVHT_API int         bvht_debug_read_bandwidth(bvht_ctx* ctx, size_t bytes, uint32_t passes, double* gbs_out);
 BVHT_API int         bvht_debug_trace_stats(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height,
                                     uint32_t tile, bvht_rect region, uint64_t counters_out[16]);
 
