@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Run one of the reference's examples (cube, two_armadillos, sixteen_armadillos, trippy_teapots, big_ben_clock)
+"""Run one of the reference's examples (cube, quad, two_armadillos, sixteen_armadillos, trippy_teapots, big_ben_clock)
 through the B200 backend and save the frame, as the reference's App would display it.
 
     python examples/run_example.py sixteen_armadillos --frames 30 --size 640 640 --out frame.png
@@ -25,7 +25,21 @@ PIPELINES = {
     "sixteen_armadillos": lambda: host.depth_pipeline(80.0, 3.0),       # sixteen_armadillos.rs:182-183
     "trippy_teapots": host.normal_pipeline,                             # trippy_teapots.rs:184-185
     "big_ben_clock": lambda: host.intersection_pipeline((255, 255, 255, 255), (0, 0, 0, 255)),   # big_ben_clock.rs:123-130
+    "quad": host.texture_pipeline,                                      # quad.rs:137-138
 }
+
+
+def build_models(spec, renderer, on_device):
+    """The example's ModelBuilder calls: on the host (C++ mirror of BvhBuilder) or on the device (CudaPathTracer::build_model)."""
+    models = []
+    for asset in spec.meshes:
+        if asset == "<quad>":                                           # quad.rs:45-92: mesh + texture coordinates + texture
+            mesh = host.Mesh.from_triangles(examples.QUAD_TRIS, examples.QUAD_NORMALS).set_tex_coords(examples.QUAD_TEX_COORDS)
+            models.append(host.ModelBuilder().with_mesh(mesh).with_texture(examples.brick_texture()).build())
+            continue
+        mesh = host.load_asset_mesh(asset)
+        models.append(renderer.build_model(mesh) if on_device else host.ModelBuilder().with_mesh(mesh).build())
+    return models
 
 
 def main():
@@ -35,19 +49,25 @@ def main():
     ap.add_argument("--size", type=int, nargs=2, default=None, help="W H (default: the example's 640 640)")
     ap.add_argument("--mode", default="strict", choices=["strict", "fast"])
     ap.add_argument("--out", default=None)
+    ap.add_argument("--device-build", action="store_true", help="run BvhBuilder::build_for on the device (bvht_blas_build)")
     args = ap.parse_args()
 
-    spec = examples.CONFIGS[args.name]()
+    spec = examples.quad_example(0) if args.name == "quad" else examples.CONFIGS[args.name]()
     w, h = args.size if args.size else spec.default_size
-    scene, models = host.build_scene(spec)
     flags = (FLAG_FAST if args.mode == "fast" else FLAG_STRICT) | FLAG_LEAF_ACCEL
     renderer = host.Renderer(flags=flags)
+    t_build = time.perf_counter()
+    scene, models = host.build_scene(spec, models=build_models(spec, renderer, args.device_build))
+    t_build = time.perf_counter() - t_build
     state = host.RendererState(PIPELINES[args.name](), w, h)
     anim = examples.GridAnimation() if args.name in ("sixteen_armadillos", "trippy_teapots") else None
     bb = examples.BigBenAnimation(models[0].primitives()) if args.name == "big_ben_clock" else None
     t0 = time.perf_counter()
     rays = renderer.render(state, scene)
-    for _ in range(args.frames):
+    for frame_no in range(1, args.frames + 1):
+        if args.name == "quad":                                          # stand-in for the rigid-body spin (examples.quad_example)
+            scene.set_transform(0, host.object_transform(examples.quad_example(frame_no).objects[0]))
+            scene.rebuild()
         if anim is not None:                                             # AppState::update (sixteen_armadillos.rs:132-163)
             anim.update()
             for i, o in enumerate(anim.objects()):
@@ -62,7 +82,8 @@ def main():
     # the bottom (lib.rs:114) -- an image file wants it as is
     frame = state.frame_buffer().reshape(h, w).copy()
     print(f"{args.name}: {args.frames + 1} frames of {w}x{h}, {rays} rays in {dt * 1e3:.1f} ms "
-          f"({rays / dt / 1e6:.0f} Mrays/s incl. host updates), last trace {renderer.stats()['last_trace_ms']:.3f} ms")
+          f"({rays / dt / 1e6:.0f} Mrays/s incl. host updates), last trace {renderer.stats()['last_trace_ms']:.3f} ms; "
+          f"scene built in {t_build * 1e3:.1f} ms ({'device' if args.device_build else 'host'} BVH build)")
     if args.out:
         rgba = frame.view(np.uint8).reshape(h, w, 4)
         if args.out.endswith(".ppm"):
