@@ -78,6 +78,8 @@ SYMBOLS = [
     ("bvht_blas_refit", C.c_int, [_P, C.c_uint32]),
     ("bvht_blas_read_nodes", C.c_int, [_P, C.c_uint32, _P, C.c_uint32]),
     ("bvht_tlas_set", C.c_int, [_P, _P, C.c_uint32, _P, C.c_uint32]),
+    ("bvht_scene_set_transforms", C.c_int, [_P, _P, _P, C.c_uint32]),
+    ("bvht_tlas_read", C.c_int, [_P, _P, C.c_uint32, C.POINTER(C.c_uint32), _P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     ("bvht_trace_primary", C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, Rect, _P]),
     ("bvht_trace_primary_device", C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, Rect, _P]),
     ("bvht_render_frame", C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, Rect, C.POINTER(ShadeParams), _P, _P]),

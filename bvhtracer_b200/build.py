@@ -30,6 +30,7 @@ UNITS = [
     ("trace_stats.cu", STRICT),
     ("upload_kernels.cu", STRICT),
     ("refit_kernels.cu", STRICT),
+    ("scene_kernels.cu", STRICT),
     ("build_kernels.cu", STRICT),
     ("bvht_api.cu", STRICT),
     ("leaf_accel.cpp", []),

@@ -80,6 +80,8 @@ struct bvht_ctx {
     DevBuf blas_desc;                                 // BlasDesc[blas.size()]
     bool blas_desc_dirty = true;
     DevBuf tlas, inst_cols, inst_blas, tlas_tight, tlas_mask;
+    DevBuf scene_in, scene_bounds;                    // K6 input (transforms, ids) and output (world boxes + status)
+    std::vector<float> h_inst_bounds;                 // SceneObject::bounds of every instance after bvht_scene_set_transforms
     uint32_t tlas_nodes_used = 0, n_inst = 0;
     std::vector<bvht_tlas_node> h_tlas;               // host copies (tight boxes are recomputed when a bake changes)
     std::vector<bvht_instance> h_inst;
@@ -890,7 +892,7 @@ void bvht_destroy(bvht_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (Blas& b : ctx->blas) free_blas(b);
     for (DevBuf* d : { &ctx->blas_desc, &ctx->tlas, &ctx->inst_cols, &ctx->inst_blas, &ctx->work_counter, &ctx->out_buf, &ctx->rays_buf,
-                       &ctx->rgba_buf, &ctx->tlas_tight, &ctx->tlas_mask })
+                       &ctx->rgba_buf, &ctx->tlas_tight, &ctx->tlas_mask, &ctx->scene_in, &ctx->scene_bounds })
         release(*d);
     for (cudaStream_t st : { ctx->aux[0], ctx->aux[1], ctx->copy_stream }) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     for (cudaEvent_t ev : { ctx->ev_fork, ctx->ev_join }) if (ev) cudaEventDestroy(ev);
@@ -1117,6 +1119,31 @@ int bvht_blas_read_nodes(bvht_ctx* ctx, uint32_t blas_id, bvht_bvh_node* out, ui
     return BVHT_OK;
 }
 
+// Walk the TLAS: indices in range, bounded depth, no cycles (node 0 is a COPY of the last merged node, tlas.rs:248)
+static int validate_tlas(bvht_ctx* ctx, const bvht_tlas_node* nodes, uint32_t nodes_used, uint32_t n_instances) {
+    std::vector<std::pair<uint32_t, uint32_t>> stack;
+    stack.push_back({ 0u, 1u });
+    uint64_t visited = 0;
+    while (!stack.empty()) {
+        auto [ni, depth] = stack.back(); stack.pop_back();
+        if (++visited > 4ull * nodes_used + 4)
+            return fail(ctx, BVHT_ERR_MALFORMED_BVH, "TLAS walk does not terminate (cycle)");
+        if (depth > (uint32_t)kTlasStack)
+            return fail(ctx, BVHT_ERR_MALFORMED_BVH, "TLAS depth exceeds the traversal stack bound %d", kTlasStack);
+        const bvht_tlas_node& n = nodes[ni];
+        if (n.left_right == 0) {
+            if (n.blas >= n_instances)
+                return fail(ctx, BVHT_ERR_MALFORMED_BVH, "TLAS leaf %u refers to instance %u of %u", ni, n.blas, n_instances);
+        } else {
+            uint32_t a = n.left_right >> 16, c = n.left_right & 0xFFFFu;
+            if (a >= nodes_used || c >= nodes_used)
+                return fail(ctx, BVHT_ERR_MALFORMED_BVH, "TLAS node %u has children %u,%u outside [0, %u)", ni, a, c, nodes_used);
+            stack.push_back({ a, depth + 1 }); stack.push_back({ c, depth + 1 });
+        }
+    }
+    return BVHT_OK;
+}
+
 int bvht_tlas_set(bvht_ctx* ctx, const bvht_tlas_node* nodes, uint32_t nodes_used, const bvht_instance* instances,
                   uint32_t n_instances) {
     if (!ctx) return BVHT_ERR_BAD_HANDLE;
@@ -1125,29 +1152,7 @@ int bvht_tlas_set(bvht_ctx* ctx, const bvht_tlas_node* nodes, uint32_t nodes_use
         return fail(ctx, BVHT_ERR_INVALID_ARG, "scene without objects (the reference's Tlas::intersect indexes blas[0] and panics, tlas.rs:130)");
     if (n_instances > 0xFFFu + 1u) return fail(ctx, BVHT_ERR_INVALID_ARG, "more than 4096 instances (12-bit instance index)");
     cudaSetDevice(ctx->device);
-    // validate: indices in range, bounded depth, no cycles (node 0 is a COPY of the last merged node, tlas.rs:248)
-    {
-        std::vector<std::pair<uint32_t, uint32_t>> stack;
-        stack.push_back({ 0u, 1u });
-        uint64_t visited = 0;
-        while (!stack.empty()) {
-            auto [ni, depth] = stack.back(); stack.pop_back();
-            if (++visited > 4ull * nodes_used + 4)
-                return fail(ctx, BVHT_ERR_MALFORMED_BVH, "TLAS walk does not terminate (cycle)");
-            if (depth > (uint32_t)kTlasStack)
-                return fail(ctx, BVHT_ERR_MALFORMED_BVH, "TLAS depth exceeds the traversal stack bound %d", kTlasStack);
-            const bvht_tlas_node& n = nodes[ni];
-            if (n.left_right == 0) {
-                if (n.blas >= n_instances)
-                    return fail(ctx, BVHT_ERR_MALFORMED_BVH, "TLAS leaf %u refers to instance %u of %u", ni, n.blas, n_instances);
-            } else {
-                uint32_t a = n.left_right >> 16, c = n.left_right & 0xFFFFu;
-                if (a >= nodes_used || c >= nodes_used)
-                    return fail(ctx, BVHT_ERR_MALFORMED_BVH, "TLAS node %u has children %u,%u outside [0, %u)", ni, a, c, nodes_used);
-                stack.push_back({ a, depth + 1 }); stack.push_back({ c, depth + 1 });
-            }
-        }
-    }
+    { int vrc = validate_tlas(ctx, nodes, nodes_used, n_instances); if (vrc) return vrc; }
     for (uint32_t i = 0; i < n_instances; ++i) {
         uint32_t id = instances[i].blas_id;
         if (id >= ctx->blas.size() || !ctx->blas[id].alive)
@@ -1181,11 +1186,120 @@ int bvht_tlas_set(bvht_ctx* ctx, const bvht_tlas_node* nodes, uint32_t nodes_use
     }
     ctx->h_tlas.assign(nodes, nodes + nodes_used);
     ctx->h_inst.assign(instances, instances + n_instances);
+    ctx->h_inst_bounds.clear();
     ctx->tlas_nodes_used = nodes_used;
     ctx->n_inst = n_instances;
     if (accel_on(ctx) && n_instances > 0) { if ((rc = recompute_tlas_tight(ctx))) return rc; }
     ctx->tlas_nodes_used = nodes_used;
     ctx->n_inst = n_instances;
+    return BVHT_OK;
+}
+
+// K6: SceneObject::set_transform x n + Tlas::rebuild on the device, then the same bookkeeping as bvht_tlas_set.
+int bvht_scene_set_transforms(bvht_ctx* ctx, const float* transforms, const uint32_t* blas_ids, uint32_t n_instances) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (!transforms || !blas_ids) return fail(ctx, BVHT_ERR_INVALID_ARG, "null transforms / blas ids");
+    if (n_instances == 0)
+        return fail(ctx, BVHT_ERR_INVALID_ARG, "scene without objects (the reference's Tlas::intersect indexes blas[0] and panics, tlas.rs:130)");
+    if (n_instances > 0xFFFu + 1u) return fail(ctx, BVHT_ERR_INVALID_ARG, "more than 4096 instances (12-bit instance index)");
+    for (uint32_t i = 0; i < n_instances; ++i) {
+        uint32_t id = blas_ids[i];
+        if (id >= ctx->blas.size() || !ctx->blas[id].alive)
+            return fail(ctx, BVHT_ERR_BAD_HANDLE, "instance %u refers to unknown blas id %u", i, id);
+    }
+    cudaSetDevice(ctx->device);
+    const uint32_t nodes_used = 2 * n_instances;
+    const size_t tl_bytes = (size_t)nodes_used * 32, ic_bytes = (size_t)n_instances * 64, ib_bytes = (size_t)n_instances * 4;
+    const size_t bd_bytes = (size_t)n_instances * 24;
+    int rc;
+    if ((rc = refresh_blas_desc(ctx))) return rc;
+    if ((rc = ensure(ctx, ctx->tlas, tl_bytes))) return rc;
+    if ((rc = ensure(ctx, ctx->inst_cols, ic_bytes))) return rc;
+    if ((rc = ensure(ctx, ctx->inst_blas, ib_bytes))) return rc;
+    if ((rc = ensure(ctx, ctx->scene_in, ic_bytes + ib_bytes))) return rc;
+    if ((rc = ensure(ctx, ctx->scene_bounds, bd_bytes + 16))) return rc;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));       // previous frame may still read the staging buffer
+    // staging: [transforms | ids] up, [tlas | inverses | bounds | status] down
+    const size_t up_bytes = ic_bytes + ib_bytes;
+    const size_t down_off = (up_bytes + 255) & ~size_t(255);
+    const size_t down_bytes = tl_bytes + ic_bytes + bd_bytes + 16;
+    if ((rc = ensure_pinned(ctx, down_off + down_bytes + 256))) return rc;
+    char* st = (char*)ctx->pinned;
+    memcpy(st, transforms, ic_bytes);
+    memcpy(st + ic_bytes, blas_ids, ib_bytes);
+    ctx->tlas_nodes_used = 0;                           // not traceable until the rebuild has been validated
+    ctx->n_inst = 0;
+    cudaEventRecord(ctx->ev_e, ctx->stream);
+    if ((rc = h2d(ctx, ctx->scene_in.p, st, up_bytes))) return rc;
+    unsigned int* status = (unsigned int*)((char*)ctx->scene_bounds.p + bd_bytes);
+    CU(ctx, cudaMemsetAsync(status, 0, 16, ctx->stream));
+    SceneRebuildParams p;
+    p.transforms = (const float*)ctx->scene_in.p;
+    p.blas_ids = (const uint32_t*)((const char*)ctx->scene_in.p + ic_bytes);
+    p.blas = (const BlasDesc*)ctx->blas_desc.p;
+    p.tlas = (float4*)ctx->tlas.p;
+    p.inst_cols = (float4*)ctx->inst_cols.p;
+    p.inst_blas = (uint32_t*)ctx->inst_blas.p;
+    p.inst_bounds = (float*)ctx->scene_bounds.p;
+    p.status = status;
+    p.n_inst = n_instances;
+    CU(ctx, launch_scene_rebuild(p, ctx->stream));
+    ctx->stats.kernel_launches += 1;
+    char* down = st + down_off;
+    CU(ctx, cudaMemcpyAsync(down, ctx->tlas.p, tl_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(down + tl_bytes, ctx->inst_cols.p, ic_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(down + tl_bytes + ic_bytes, ctx->scene_bounds.p, bd_bytes + 16, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaEventRecord(ctx->ev_f, ctx->stream);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += down_bytes;
+    { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ctx->ev_e, ctx->ev_f) == cudaSuccess) ctx->stats.last_upload_ms = ms; }
+    unsigned int st_words[4];
+    memcpy(st_words, down + tl_bytes + ic_bytes + bd_bytes, 16);
+    if (st_words[0] & 1u)
+        return fail(ctx, BVHT_ERR_INVALID_ARG, "singular transform (the reference unwraps None and panics, transform_component.rs:17-27)");
+    if (st_words[0] & 2u)
+        return fail(ctx, BVHT_ERR_INVALID_ARG, "Tlas::rebuild found no merge candidate (non-finite bounds); the reference panics at tlas.rs:184");
+    if (st_words[1] != nodes_used)
+        return fail(ctx, BVHT_ERR_CUDA, "device Tlas::rebuild produced %u nodes, expected %u", st_words[1], nodes_used);
+    ctx->h_tlas.resize(nodes_used);
+    const float* tl = (const float*)down;
+    for (uint32_t i = 0; i < nodes_used; ++i) {
+        const float* f = tl + (size_t)i * 8;
+        memcpy(ctx->h_tlas[i].aabb_min, f + 0, 12); memcpy(&ctx->h_tlas[i].left_right, f + 3, 4);
+        memcpy(ctx->h_tlas[i].aabb_max, f + 4, 12); memcpy(&ctx->h_tlas[i].blas, f + 7, 4);
+    }
+    ctx->h_inst.resize(n_instances);
+    for (uint32_t i = 0; i < n_instances; ++i) {
+        memcpy(ctx->h_inst[i].transform_inv, down + tl_bytes + (size_t)i * 64, 64);
+        ctx->h_inst[i].blas_id = blas_ids[i];
+    }
+    ctx->h_inst_bounds.assign((const float*)(down + tl_bytes + ic_bytes), (const float*)(down + tl_bytes + ic_bytes) + (size_t)n_instances * 6);
+    if ((rc = validate_tlas(ctx, ctx->h_tlas.data(), nodes_used, n_instances))) { ctx->h_tlas.clear(); ctx->h_inst.clear(); return rc; }
+    if (accel_on(ctx)) { if ((rc = recompute_tlas_tight(ctx))) return rc; }
+    ctx->tlas_nodes_used = nodes_used;
+    ctx->n_inst = n_instances;
+    return BVHT_OK;
+}
+
+int bvht_tlas_read(bvht_ctx* ctx, bvht_tlas_node* nodes_out, uint32_t max_nodes, uint32_t* nodes_used_out,
+                   bvht_instance* instances_out, float* bounds_out, uint32_t max_instances, uint32_t* n_instances_out) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (ctx->tlas_nodes_used == 0) return fail(ctx, BVHT_ERR_NOT_READY, "no TLAS has been set");
+    if (nodes_used_out) *nodes_used_out = ctx->tlas_nodes_used;
+    if (n_instances_out) *n_instances_out = ctx->n_inst;
+    if (nodes_out) {
+        if (max_nodes < ctx->tlas_nodes_used) return fail(ctx, BVHT_ERR_INVALID_ARG, "room for %u TLAS nodes, %u needed", max_nodes, ctx->tlas_nodes_used);
+        memcpy(nodes_out, ctx->h_tlas.data(), (size_t)ctx->tlas_nodes_used * sizeof(bvht_tlas_node));
+    }
+    if (instances_out || bounds_out) {
+        if (max_instances < ctx->n_inst) return fail(ctx, BVHT_ERR_INVALID_ARG, "room for %u instances, %u needed", max_instances, ctx->n_inst);
+        if (instances_out) memcpy(instances_out, ctx->h_inst.data(), (size_t)ctx->n_inst * sizeof(bvht_instance));
+        if (bounds_out) {
+            if (ctx->h_inst_bounds.size() != (size_t)ctx->n_inst * 6)
+                return fail(ctx, BVHT_ERR_NOT_READY, "instance bounds exist only after bvht_scene_set_transforms");
+            memcpy(bounds_out, ctx->h_inst_bounds.data(), (size_t)ctx->n_inst * 24);
+        }
+    }
     return BVHT_OK;
 }
 

@@ -77,6 +77,19 @@ struct PrimaryParams {
     int4      inst_rect[32];
 };
 
+// K6 (scene_kernels.cu): SceneObject::set_transform for every object + Tlas::rebuild
+struct SceneRebuildParams {
+    const float*    transforms;   // n_inst x 16, column-major FORWARD transforms (Transform3, transform.rs:24-43)
+    const uint32_t* blas_ids;     // n_inst
+    const BlasDesc* blas;
+    float4*         tlas;         // out: 2 * n_inst nodes, 2 float4 each
+    float4*         inst_cols;    // out: inverse transforms, 4 float4 per instance
+    uint32_t*       inst_blas;    // out: copy of blas_ids
+    float*          inst_bounds;  // out (may be null): world AABB per instance, 6 floats (SceneObject::bounds)
+    unsigned int*   status;       // [0]: bit 0 = singular transform, bit 1 = clustering found no candidate; [1] = nodes_used
+    uint32_t        n_inst;
+};
+
 struct RaysParams {
     SceneDev     scene;
     const float* rays;                   // n x 7 floats (o, d, t)

@@ -25,6 +25,10 @@ cudaError_t launch_refit_sub_nodes(float4* raw, const uint32_t* parent, unsigned
                                    const uint32_t* order, uint32_t n_nodes, cudaStream_t s);
 cudaError_t launch_inflate_sub_nodes(const float4* raw, float4* out, uint32_t n_nodes, float scale, float abs_, cudaStream_t s);
 
+// scene_kernels.cu
+size_t      scene_rebuild_smem_bytes(uint32_t n_inst);
+cudaError_t launch_scene_rebuild(const SceneRebuildParams& p, cudaStream_t s);
+
 // refit_kernels.cu
 struct RefitPlan {
     float4*         nodes;          // device node pool (2 float4 per node)

@@ -139,6 +139,25 @@ class Engine:
         assert nodes.dtype.itemsize == 32 and instances.dtype.itemsize == 68
         self._check(self._lib.bvht_tlas_set(self._ctx, ptr(nodes), int(nodes_used), ptr(instances), len(instances)))
 
+    def scene_set_transforms(self, transforms, blas_ids):
+        """SceneObject::set_transform for every object + Tlas::rebuild on the device (scene_object.rs:60-75, tlas.rs:204-250).
+        transforms: n x 16 f32 column-major forward matrices; blas_ids: n model ids."""
+        transforms = np.ascontiguousarray(np.asarray(transforms, "<f4").reshape(-1, 16))
+        blas_ids = np.ascontiguousarray(np.asarray(blas_ids, "<u4").reshape(-1))
+        assert transforms.shape[0] == blas_ids.shape[0]
+        self._check(self._lib.bvht_scene_set_transforms(self._ctx, ptr(transforms), ptr(blas_ids), transforms.shape[0]))
+
+    def tlas_read(self, with_bounds=False):
+        """Current TLAS nodes (reference layout), instances and, after scene_set_transforms, the objects' world bounds."""
+        used, n = C.c_uint32(0), C.c_uint32(0)
+        self._check(self._lib.bvht_tlas_read(self._ctx, None, 0, C.byref(used), None, None, 0, C.byref(n)))
+        nodes = np.zeros(used.value, TLAS_NODE)
+        inst = np.zeros(n.value, INSTANCE)
+        bounds = np.zeros((n.value, 6), "<f4") if with_bounds else None
+        self._check(self._lib.bvht_tlas_read(self._ctx, ptr(nodes), used.value, None, ptr(inst),
+                                             ptr(bounds) if with_bounds else None, n.value, None))
+        return (nodes, inst, bounds) if with_bounds else (nodes, inst)
+
     # ------------------------------------------------------------------ tracing
     def trace_primary(self, camera, width, height, tile=8, region=None, out=None):
         camera = np.ascontiguousarray(camera)

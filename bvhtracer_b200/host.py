@@ -88,6 +88,7 @@ def lib():
             "bvhx_state_hits": (_P, [_P]),
             "bvhx_renderer_render": (C.c_int64, [_P, _P, _P]),
             "bvhx_renderer_sync_scene": (C.c_int, [_P, _P]),
+            "bvhx_renderer_update_transforms": (C.c_int, [_P, _P, _P, C.c_uint32]),
             "bvhx_renderer_build_model": (_P, [_P, _P]),
             "bvhx_renderer_rebuild_model": (C.c_int, [_P, _P]),
             "bvhx_renderer_intersect": (C.c_int, [_P, _P, _P, C.c_uint64, _P]),
@@ -431,6 +432,12 @@ class Renderer:
 
     def sync_scene(self, scene):
         if lib().bvhx_renderer_sync_scene(self._h, scene._h) != 0:
+            raise _err()
+
+    def update_transforms(self, scene, transforms):
+        """set_transform for every object + scene.rebuild(), computed on the device; the host scene adopts the results."""
+        m = np.ascontiguousarray(np.stack([np.asarray(t.matrix, "<f4").reshape(16) for t in transforms]))
+        if lib().bvhx_renderer_update_transforms(self._h, scene._h, _ffi.ptr(m), m.shape[0]) != 0:
             raise _err()
 
     def build_model(self, mesh):

@@ -515,6 +515,8 @@ public:
         bounds_ = world_bounds(model_->bounds(), t);
         transform_ = t; transform_inv_ = t.inverse();
     }
+    // state computed by the device for this object (CudaPathTracer::update_transforms): same values set_transform yields
+    void adopt(const Transform3& t, const Transform3& t_inv, const Aabb& world) { transform_ = t; transform_inv_ = t_inv; bounds_ = world; }
     static Aabb world_bounds(const Aabb& ob, const Transform3& t) {
         Aabb nb = Aabb::new_empty();
         for (int i = 0; i < 8; ++i) {
@@ -606,6 +608,8 @@ public:
     const Tlas& tlas() const { return tlas_; }
     void rebuild() { tlas_.rebuild(objects_); version_++; }
     uint64_t version() const { return version_; }
+    // the device ran set_transform + Tlas::rebuild (CudaPathTracer::update_transforms): take its results
+    Tlas& tlas_mut() { version_++; return tlas_; }
 private:
     std::vector<SceneObject> objects_;
     Camera camera_;
@@ -735,8 +739,8 @@ public:
         scene_ = nullptr;                                                   // bounds changed: the next frame re-sends the TLAS
     }
 
-    void sync_scene(Scene& scene) {
-        // (1) models
+    // upload / refresh every model the scene uses; returns the blas id of each scene object
+    std::vector<uint32_t> sync_models(Scene& scene) {
         std::vector<uint32_t> blas_ids(scene.objects().size());
         for (size_t i = 0; i < scene.objects().size(); ++i) {
             Model* m = scene.objects()[i].model().get();
@@ -760,6 +764,11 @@ public:
             }
             blas_ids[i] = u->blas_id;
         }
+        return blas_ids;
+    }
+
+    void sync_scene(Scene& scene) {
+        std::vector<uint32_t> blas_ids = sync_models(scene);       // (1) models
         // (2) per-frame state
         if (scene_ != &scene || scene_version_ != scene.version() || instances_.size() != scene.objects().size()) {
             instances_.resize(scene.objects().size());
@@ -771,6 +780,34 @@ public:
                                 (uint32_t)instances_.size()));
             scene_ = &scene; scene_version_ = scene.version();
         }
+    }
+
+    // `for (i, t) in transforms { scene.get_mut_unchecked(i).set_transform(&t) }; scene.rebuild()` (sixteen_armadillos.rs:132-163)
+    // ON THE DEVICE (bvht_scene_set_transforms): inverses, world bounds and the TLAS are computed there -- from the models'
+    // CURRENT root boxes, i.e. after any pending refit -- and copied back into the host scene, which ends up in exactly the
+    // state the host loop would have produced.  The next evaluate() sends nothing but the camera.
+    void update_transforms(Scene& scene, const std::vector<Transform3>& transforms) {
+        const size_t n = scene.objects().size();
+        if (transforms.size() != n) throw std::runtime_error("update_transforms: one transform per scene object");
+        std::vector<uint32_t> blas_ids = sync_models(scene);
+        std::vector<float> fwd(n * 16);
+        for (size_t i = 0; i < n; ++i) std::memcpy(&fwd[i * 16], transforms[i].matrix.m, 64);
+        check(bvht_scene_set_transforms(ctx_, fwd.data(), blas_ids.data(), (uint32_t)n));
+        instances_.resize(n);
+        std::vector<float> bounds(n * 6);
+        Tlas& tlas = scene.tlas_mut();
+        if (tlas.nodes.size() < 2 * n) tlas.nodes.resize(2 * n);
+        uint32_t used = 0;
+        check(bvht_tlas_read(ctx_, (bvht_tlas_node*)tlas.nodes.data(), (uint32_t)tlas.nodes.size(), &used, instances_.data(), bounds.data(),
+                             (uint32_t)n, nullptr));
+        tlas.nodes_used = used;
+        for (size_t i = 0; i < n; ++i) {
+            Transform3 inv; std::memcpy(inv.matrix.m, instances_[i].transform_inv, 64);
+            Aabb b; b.bounds_min = Vector3(bounds[i * 6 + 0], bounds[i * 6 + 1], bounds[i * 6 + 2]);
+            b.bounds_max = Vector3(bounds[i * 6 + 3], bounds[i * 6 + 4], bounds[i * 6 + 5]);
+            scene.get_mut_unchecked(i).adopt(transforms[i], inv, b);
+        }
+        scene_ = &scene; scene_version_ = scene.version();
     }
 
     size_t evaluate(RendererState& state, Scene& scene) override {

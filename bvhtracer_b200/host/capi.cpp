@@ -184,6 +184,14 @@ BVHX_API int64_t bvhx_renderer_render(void* renderer, void* state, void* scene) 
 BVHX_API int bvhx_renderer_sync_scene(void* renderer, void* scene) {
     return guard([&]() -> int { ((CudaPathTracer*)((Renderer*)renderer)->integrator())->sync_scene(*(Scene*)scene); return 0; }, -1);
 }
+BVHX_API int bvhx_renderer_update_transforms(void* renderer, void* scene, const float* transforms16, uint32_t n) {
+    return guard([&]() -> int {
+        std::vector<Transform3> t(n);
+        for (uint32_t i = 0; i < n; ++i) std::memcpy(t[i].matrix.m, transforms16 + (size_t)i * 16, 64);
+        ((CudaPathTracer*)((Renderer*)renderer)->integrator())->update_transforms(*(Scene*)scene, t);
+        return 0;
+    }, -1);
+}
 BVHX_API void* bvhx_renderer_build_model(void* renderer, void* mesh) {
     return guard([&]() -> void* {
         return new ModelInstance(((CudaPathTracer*)((Renderer*)renderer)->integrator())->build_model(*(Mesh*)mesh));

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BVHT_ABI_VERSION 2
+#define BVHT_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define BVHT_API __attribute__((visibility("default")))
@@ -215,6 +215,22 @@ BVHT_API int         bvht_blas_read_nodes(bvht_ctx* ctx, uint32_t blas_id, bvht_
  * bvht_instance per SceneObject, in `Scene.objects` order (scene.rs:10-15). */
 BVHT_API int         bvht_tlas_set(bvht_ctx* ctx, const bvht_tlas_node* nodes, uint32_t nodes_used,
                           const bvht_instance* instances, uint32_t n_instances);
+
+/* The same per-frame scene state, COMPUTED ON THE DEVICE from the objects' forward transforms: for every scene object
+ * `SceneObject::set_transform` (scene_object.rs:60-75: the world AABB of the 8 transformed corners of `Model::bounds()` --
+ * the model's CURRENT root box on the device, so it follows bvht_blas_refit / bvht_blas_rebuild without a read-back -- and
+ * the cached inverse, transform_component.rs:17-27), then `Tlas::rebuild` (tlas.rs:204-250, find_best_match :179-202) with
+ * the reference's clustering order, child packing and node numbering (always 2 * n nodes).  `transforms`: n x 16 f32,
+ * column-major `Transform3` matrices, in `Scene.objects` order; `blas_ids`: the model of each object.  Replaces the host
+ * loop `for o in objects { o.set_transform(..) }; tlas.rebuild(objects)` + bvht_tlas_set; results are bit-identical to it.
+ * A singular transform, or bounds for which the clustering finds no candidate, are errors (the reference panics). */
+BVHT_API int         bvht_scene_set_transforms(bvht_ctx* ctx, const float* transforms, const uint32_t* blas_ids, uint32_t n_instances);
+
+/* The current TLAS in reference layout (`Tlas.nodes[0..nodes_used]`), the instances (cached inverses) and -- after
+ * bvht_scene_set_transforms -- `SceneObject::bounds()` of every object (6 f32 each: min, max).  Any output may be NULL;
+ * call once with NULL buffers to get the counts. */
+BVHT_API int         bvht_tlas_read(bvht_ctx* ctx, bvht_tlas_node* nodes_out, uint32_t max_nodes, uint32_t* nodes_used_out,
+                            bvht_instance* instances_out, float* bounds_out, uint32_t max_instances, uint32_t* n_instances_out);
 
 /* PathTracer::evaluate, first loop (renderer.rs:345-368): one primary ray per pixel of `region` of a
  * width x height image through Camera::get_ray_world, Scene::intersect for each, tiles of `tile` x `tile`
