@@ -84,6 +84,8 @@ struct bvht_ctx {
     std::vector<float> h_inst_bounds;                 // SceneObject::bounds of every instance after bvht_scene_set_transforms
     uint32_t tlas_nodes_used = 0, n_inst = 0;
     std::vector<bvht_tlas_node> h_tlas;               // host copies (tight boxes are recomputed when a bake changes)
+    bool tlas_nested = false;                         // every interior box contains its children's boxes (chain skipping needs it)
+    uint32_t tlas_depth = 0;                          // edges on the longest root-to-leaf path
     std::vector<bvht_instance> h_inst;
     std::vector<float> inst_tight;                    // 6 floats per instance (world lo/hi) or lo > hi when unusable
     double bake_center[3] = { 0.0, 0.0, 0.0 };        // camera origin the tight TLAS boxes' origin limit is centred on
@@ -511,6 +513,23 @@ int recompute_tlas_tight(bvht_ctx* ctx) {
         float* f = &ctx->inst_tight[(size_t)i * 6];
         if (inst_t[i].d2_max >= 0.0f && inst_t[i].o2_max >= 0.0f) { memcpy(f, inst_t[i].lo, 12); memcpy(f + 3, inst_t[i].hi, 12); }
         else { f[0] = f[1] = f[2] = 1.0f; f[3] = f[4] = f[5] = -1.0f; }       // unusable: lo > hi
+    }
+    // chain skipping (trace_kernels.cuh) replaces a run of nested box tests by the innermost one: only valid when the
+    // caller's boxes ARE nested (Tlas::rebuild's are, exactly: tlas.rs:233-234); NaNs fail the comparisons
+    ctx->tlas_nested = true;
+    for (uint32_t i = 0; i < nodes_used && ctx->tlas_nested; ++i) {
+        const bvht_tlas_node& n = ctx->h_tlas[i];
+        if (n.left_right == 0 || !done[i]) continue;
+        const uint32_t ch[2] = { n.left_right >> 16, n.left_right & 0xFFFFu };
+        for (int c = 0; c < 2; ++c)
+            for (int k = 0; k < 3; ++k)
+                if (!(n.aabb_min[k] <= ctx->h_tlas[ch[c]].aabb_min[k] && ctx->h_tlas[ch[c]].aabb_max[k] <= n.aabb_max[k])) ctx->tlas_nested = false;
+    }
+    {
+        struct Dep { static uint32_t go(const bvht_tlas_node* n, uint32_t i, uint32_t guard) {
+            if (n[i].left_right == 0 || guard == 0) return 0;
+            return 1 + std::max(go(n, n[i].left_right >> 16, guard - 1), go(n, n[i].left_right & 0xFFFFu, guard - 1)); } };
+        ctx->tlas_depth = Dep::go(ctx->h_tlas.data(), 0, 64);
     }
     // instance masks per node (only meaningful for n_inst <= 32; the kernel ignores them otherwise)
     std::vector<uint32_t> mask(nodes_used, 0xFFFFFFFFu);
@@ -1360,6 +1379,10 @@ static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvh
     p.work_counter = (unsigned int*)ctx->work_counter.p + slot;
     p.n_rect = 0;
     if (accel_on(ctx)) { uint32_t nr = 0; if (compute_instance_rects(ctx, camera, width, height, p.inst_rect, nr)) p.n_rect = nr; }
+    // chain skipping pays from three instances on (measured: pure overhead for 1-2 instances)
+    p.n_tlas_nodes = (p.n_rect >= 3 && ctx->tlas_nested && ctx->h_tlas.size() <= 64) ? (uint32_t)ctx->h_tlas.size() : 0u;
+    p.skip_rounds = 0;
+    while ((1u << p.skip_rounds) < ctx->tlas_depth) ++p.skip_rounds;
     int grid = persistent_grid(ctx, true, n_items);
     cudaError_t e = fast_on(ctx) ? launch_primary_fast(p, accel_on(ctx), grid, kTraceBlock, stream)
                                  : launch_primary_strict(p, accel_on(ctx), grid, kTraceBlock, stream);
@@ -1738,6 +1761,10 @@ int bvht_debug_trace_stats(bvht_ctx* ctx, const bvht_camera* camera, uint32_t wi
     p.work_counter = (unsigned int*)ctx->work_counter.p;
     p.stats = (unsigned long long*)cnt.p;
     if (accel_on(ctx)) { uint32_t nr = 0; if (compute_instance_rects(ctx, camera, width, height, p.inst_rect, nr)) p.n_rect = nr; }
+    // chain skipping pays from three instances on (measured: pure overhead for 1-2 instances)
+    p.n_tlas_nodes = (p.n_rect >= 3 && ctx->tlas_nested && ctx->h_tlas.size() <= 64) ? (uint32_t)ctx->h_tlas.size() : 0u;
+    p.skip_rounds = 0;
+    while ((1u << p.skip_rounds) < ctx->tlas_depth) ++p.skip_rounds;
     cudaMemsetAsync(cnt.p, 0, 16 * sizeof(uint64_t), ctx->stream);
     cudaMemsetAsync(ctx->work_counter.p, 0, 4, ctx->stream);
     int per_sm = std::max(1, blocks_per_sm_primary_stats(accel_on(ctx), kTraceBlock));

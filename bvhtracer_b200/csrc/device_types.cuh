@@ -12,6 +12,17 @@
 
 namespace bvht {
 
+// Form of the baked (inflated) sub-BVH child boxes: 0 = {lo, hi}, 1 / 2 = {centre, half extent} (trace_kernels.cuh
+// slab_test_ch; 2 keeps |f| in registers and uses three FMAs per axis).  Shared by the bake and the trace kernels.
+#ifndef BVHT_SUB_CH
+#define BVHT_SUB_CH 2
+#endif
+
+// Chain-skipping TLAS walk for blocks with a candidate mask (trace_kernels.cuh build_tlas_skip): 1 = on
+#ifndef BVHT_TLAS_PRUNE
+#define BVHT_TLAS_PRUNE 1
+#endif
+
 constexpr int kTlasStack = 64;   // validated at bvht_tlas_set (depth of the uploaded tree)
 constexpr int kBlasStack = 64;   // validated at bvht_blas_create
 constexpr int kSubStack  = 48;   // leaf sub-BVH (built by us, depth bounded at build)
@@ -74,6 +85,8 @@ struct PrimaryParams {
     // accel only: conservative screen-space rectangle (pixels, inclusive) of each instance's tight box for THIS camera;
     // n_rect == 0 disables the tile-level candidate masks
     uint32_t  n_rect;
+    uint32_t  skip_rounds;               // pointer-jumping rounds: ceil(log2(depth of the TLAS))
+    uint32_t  n_tlas_nodes;              // > 0 (and <= 64) with n_rect: chain-skipping TLAS walk (trace_kernels.cuh build_tlas_skip)
     int4      inst_rect[32];
 };
 

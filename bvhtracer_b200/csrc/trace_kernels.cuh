@@ -111,6 +111,27 @@ __device__ __forceinline__ bool slab_test_sub(const float4 lo, const float4 hi, 
     return (t_max >= t_min) && (t_min <= tcl) && (t_max >= 0.0f);
 }
 
+// The same test on a child box stored as CENTRE + HALF EXTENT (device_types.cuh BVHT_SUB_CH; inflate_sub_nodes_kernel
+// writes that form): t_centre = c * f - o * f, t_near/far = t_centre -/+ h * |f|.  No per-axis min/max: the work moves
+// from the ALU pipe (FMNMX, the busiest pipe of this kernel) to the FMA pipes.  Two more roundings than the lo/hi form
+// (eps * |t_centre| and eps * |h f|), which the bake adds to h (upload_kernels.cu).
+__device__ __forceinline__ bool slab_test_ch(const float4 c, const float4 h, const RayM& r, float tcl, float& tmin_out) {
+    float tcx = __fmaf_rn(c.x, r.fx, r.nx);
+    float tcy = __fmaf_rn(c.y, r.fy, r.ny);
+    float tcz = __fmaf_rn(c.z, r.fz, r.nz);
+#if BVHT_SUB_CH == 2
+    float ax = fabsf(r.fx), ay = fabsf(r.fy), az = fabsf(r.fz);
+    float t_min = fmaxf(fmaxf(__fmaf_rn(-h.x, ax, tcx), __fmaf_rn(-h.y, ay, tcy)), __fmaf_rn(-h.z, az, tcz));
+    float t_max = fminf(fminf(__fmaf_rn(h.x, ax, tcx), __fmaf_rn(h.y, ay, tcy)), __fmaf_rn(h.z, az, tcz));
+#else
+    float px = fabsf(__fmul_rn(h.x, r.fx)), py = fabsf(__fmul_rn(h.y, r.fy)), pz = fabsf(__fmul_rn(h.z, r.fz));
+    float t_min = fmaxf(fmaxf(__fsub_rn(tcx, px), __fsub_rn(tcy, py)), __fsub_rn(tcz, pz));
+    float t_max = fminf(fminf(__fadd_rn(tcx, px), __fadd_rn(tcy, py)), __fadd_rn(tcz, pz));
+#endif
+    tmin_out = t_min;
+    return (t_max >= t_min) && (t_min <= tcl) && (t_max >= 0.0f);
+}
+
 // geometry/triangle.rs:41-72 on the repacked triangle (v0, e1 = v1 - v0, e2 = v2 - v0), split in two so that the
 // hot loop is straight-line code with ONE rarely taken branch:
 //
@@ -251,8 +272,13 @@ __device__ __forceinline__ void leaf_accel(const BlasDesc& B, uint32_t sub_root,
             float4 d = ldg4(n + 3);   // child1 hi.xyz
             float t0, t1;
             // inclusive comparisons: a node holding a triangle with t == lt but a lower index must be visited
+#if BVHT_SUB_CH
+            bool h0 = slab_test_ch(a, b, r, lt, t0);
+            bool h1 = slab_test_ch(c, d, r, lt, t1);
+#else
             bool h0 = slab_test_sub(a, b, r, lt, t0);
             bool h1 = slab_test_sub(c, d, r, lt, t1);
+#endif
             uint32_t r0 = __float_as_uint(a.w), r1 = __float_as_uint(b.w);
             if (h0 && h1) {
                 bool swap = t1 < t0;
@@ -350,8 +376,20 @@ __device__ __forceinline__ void blas_intersect(const BlasDesc& B, const RayM& r,
 }
 
 // scene/tlas.rs:123-177 + scene_object.rs:78-89.  World ray (ox..dz, recip), initial t = tmax.
-template <bool ACCEL>
-__device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM& w, float tmax, uint32_t cand, Stat& st) {
+//
+// Chain skipping (ACCEL, `skip` != nullptr; built per pixel block by build_tlas_skip).  Under a candidate mask a TLAS
+// subtree without candidate instances is never entered, so most interior nodes have ONE relevant child -- and because
+// every .tri instance box reaches +999 (the sentinel), the reference's boxes almost never cull: the walk degenerates into
+// long chains (the clustering of sixteen_armadillos is 12-15 levels deep).  skip[x] is the node at the end of the chain
+// that starts at x: the first descendant that is a leaf or has two relevant children (x itself if it is one).  The
+// reference, having arrived at x, tests the boxes of the chain x -> c1 -> ... -> s one after the other with an unchanged
+// `closest` (nothing else is visited in between, and culled subtrees have no side effects).  Those boxes are nested
+// (a parent is the exact min/max union of its children, tlas.rs:233-234) and Aabb::intersect is monotonic in the box
+// for finite reciprocals (rounding of (b - o) * rd is monotonic in b), so "every box of the chain is hit" <=> "the
+// last one is hit": one slab test replaces the chain.  Rays with a non-finite reciprocal take the plain walk.
+template <bool ACCEL, bool PRUNE = false>
+__device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM& w, float tmax, uint32_t cand, Stat& st,
+                                                  const uint8_t* skip = nullptr) {
     // cand (ACCEL): bit i clear = instance i cannot be hit by this ray (tile-level screen rectangles); all ones = unknown
     st.add(0);
     HitRec best;
@@ -381,7 +419,37 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
         if (wd2 <= t0.w && wo2 <= t1.w && !slab_test_sub(t0, t1, wf, closest, tt)) return best;   // nothing reachable at all
         if (cand != 0xFFFFFFFFu && (__ldg(S.tlas_mask + 0) & cand) == 0u) return best;
     }
+    uint32_t cur = 0u;                     // index of the node held in n0 / n1 (chain skipping only)
+    if (ACCEL && PRUNE) {
+        if (skip && !(fabsf(w.rdx) < 3.0e38f && fabsf(w.rdy) < 3.0e38f && fabsf(w.rdz) < 3.0e38f)) skip = nullptr;
+    }
     for (;;) {
+        if (ACCEL && PRUNE) {
+            if (skip) {
+                uint32_t sn = skip[cur];
+                if (sn != cur) {
+                    // arrived at the head of a chain: only the box at its end decides (see above)
+                    st.add(1);
+                    n0 = ldg4(S.tlas + 2 * (size_t)sn);
+                    n1 = ldg4(S.tlas + 2 * (size_t)sn + 1);
+                    bool ok = true;
+                    float tt;
+                    if (__float_as_uint(n0.w) == 0u) {          // a leaf: its tight box first
+                        float4 a0 = ldg4(S.tlas_tight + 2 * (size_t)sn), a1 = ldg4(S.tlas_tight + 2 * (size_t)sn + 1);
+                        if (wd2 <= a0.w && wo2 <= a1.w) ok = slab_test_sub(a0, a1, wf, closest, tt);
+                    }
+                    if (ok) ok = slab_test(n0, n1, w, closest, tt);
+                    if (!ok) {
+                        if (sp == 0) break;
+                        cur = stack[--sp];
+                        n0 = ldg4(S.tlas + 2 * (size_t)cur);
+                        n1 = ldg4(S.tlas + 2 * (size_t)cur + 1);
+                        continue;
+                    }
+                    cur = sn;
+                }
+            }
+        }
         uint32_t lr = __float_as_uint(n0.w);
         if (lr == 0u) {
             uint32_t inst = __float_as_uint(n1.w);
@@ -427,6 +495,7 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
             }
             if (sp == 0) break;
             uint32_t ni = stack[--sp];
+            cur = ni;
             n0 = ldg4(S.tlas + 2 * (size_t)ni);
             n1 = ldg4(S.tlas + 2 * (size_t)ni + 1);
         } else {
@@ -470,17 +539,18 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
             bool far_hit = left_first ? rh : lh;
             if (near_hit) {
                 if (far_hit) stack[sp++] = left_first ? ri : li;
-                if (left_first) { n0 = l0; n1 = l1; } else { n0 = r0; n1 = r1; }
+                if (left_first) { n0 = l0; n1 = l1; cur = li; } else { n0 = r0; n1 = r1; cur = ri; }
                 continue;
             }
             if (ACCEL) {
                 if (far_hit) {             // near child dropped (or missed): the far child is next in the reference's order
-                    if (left_first) { n0 = r0; n1 = r1; } else { n0 = l0; n1 = l1; }
+                    if (left_first) { n0 = r0; n1 = r1; cur = ri; } else { n0 = l0; n1 = l1; cur = li; }
                     continue;
                 }
             }
             if (sp == 0) break;
             uint32_t ni = stack[--sp];
+            cur = ni;
             n0 = ldg4(S.tlas + 2 * (size_t)ni);
             n1 = ldg4(S.tlas + 2 * (size_t)ni + 1);
         }
@@ -604,6 +674,43 @@ __device__ __forceinline__ uint32_t shade_pixel(const PrimaryParams& P, const Hi
     return 0u;
 }
 
+// Per pixel block (one warp): skip[x] for every TLAS node under the block's candidate mask (scene_intersect, "Chain
+// skipping").  Lane j owns node j (and j + 32); `rounds` = ceil(log2(tree depth)) pointer-jumping rounds -- with shuffles
+// when the tree has at most 32 nodes (<= 16 instances), else over the byte table in shared memory.
+__device__ __forceinline__ uint32_t tlas_skip_init(const SceneDev& S, uint32_t id, uint32_t cand) {
+    uint32_t lr = __float_as_uint(__ldg(reinterpret_cast<const float*>(S.tlas + 2 * (size_t)id) + 3));
+    uint32_t sn = id;
+    if (lr != 0u) {
+        uint32_t li = lr >> 16, ri = lr & 0xFFFFu;
+        bool ml = (__ldg(S.tlas_mask + li) & cand) != 0u, mr = (__ldg(S.tlas_mask + ri) & cand) != 0u;
+        if (ml != mr) sn = ml ? li : ri;
+    }
+    return sn;
+}
+
+__device__ __forceinline__ void build_tlas_skip(const SceneDev& S, uint32_t n_nodes, uint32_t rounds, uint32_t cand, uint8_t* skip,
+                                                unsigned lane) {
+    if (n_nodes <= 32u) {
+        uint32_t sn = lane < n_nodes ? tlas_skip_init(S, lane, cand) : lane;
+        for (uint32_t r = 0; r < rounds; ++r) sn = __shfl_sync(0xFFFFFFFFu, sn, (int)sn);
+        __syncwarp();                               // the previous block's walks are over
+        skip[lane] = (uint8_t)sn;
+        __syncwarp();
+        return;
+    }
+    __syncwarp();
+    for (uint32_t id = lane; id < n_nodes; id += 32u) skip[id] = (uint8_t)tlas_skip_init(S, id, cand);
+    __syncwarp();
+    for (uint32_t r = 0; r < rounds; ++r) {
+        uint32_t a = lane < n_nodes ? skip[skip[lane]] : 0u;
+        uint32_t b = lane + 32u < n_nodes ? skip[skip[lane + 32u]] : 0u;
+        __syncwarp();
+        if (lane < n_nodes) skip[lane] = (uint8_t)a;
+        if (lane + 32u < n_nodes) skip[lane + 32u] = (uint8_t)b;
+        __syncwarp();
+    }
+}
+
 // K1: persistent, tile-pulling primary closest-hit kernel.
 // 32-pixel slices pulled per work-counter atomic.  Measured on B200 (tools/sweep_grab.sh): 2/4/8 cut the all-miss frame
 // from 0.197 to 0.148 ms (the single counter serialises in L2) but cost real frames 2 % / 6 % / 19 % through load imbalance
@@ -611,11 +718,14 @@ __device__ __forceinline__ uint32_t shade_pixel(const PrimaryParams& P, const Hi
 #ifndef BVHT_GRAB
 #define BVHT_GRAB 1
 #endif
-template <bool ACCEL>
+// PRUNE: chain-skipping TLAS walk (a separate instantiation, chosen by the host when the scene qualifies: its extra
+// registers cost single-instance scenes 2-3 % otherwise).
+template <bool ACCEL, bool PRUNE = false>
 __global__ void __launch_bounds__(128, BVHT_MIN_BLOCKS)
 trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
     const unsigned lane = threadIdx.x & 31u;
     Stat st;
+    __shared__ uint8_t s_skip[PRUNE ? 4 : 1][64];
     for (;;) {
         unsigned base = 0;
         if (lane == 0) base = atomicAdd(P.work_counter, (unsigned)BVHT_GRAB);
@@ -647,6 +757,13 @@ trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
                 cand = __ballot_sync(0xFFFFFFFFu, ov);
             }
         }
+        const uint8_t* skip = nullptr;
+        if (ACCEL && PRUNE) {
+            if (P.n_tlas_nodes != 0u && cand != 0u && cand != 0xFFFFFFFFu) {       // warp-uniform
+                build_tlas_skip(P.scene, P.n_tlas_nodes, P.skip_rounds, cand, s_skip[threadIdx.x >> 5], lane);
+                skip = s_skip[threadIdx.x >> 5];
+            }
+        }
         if (active) {
             HitRec h;
             if (ACCEL && cand == 0u) {
@@ -654,7 +771,7 @@ trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
                 st.add(0);
             } else {
                 RayM w = primary_ray(P.cam, px, py, P.width, P.height);
-                h = scene_intersect<ACCEL>(P.scene, w, FLT_MAX, cand, st);
+                h = scene_intersect<ACCEL, PRUNE>(P.scene, w, FLT_MAX, cand, st, skip);
             }
             if (P.out) {
                 uint4 o;

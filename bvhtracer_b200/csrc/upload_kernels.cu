@@ -63,8 +63,31 @@ inflate_sub_nodes_kernel(const float4* __restrict__ raw, float4* __restrict__ ou
         ohi.x = __fadd_ru(__fadd_ru(hi.x, d), __fmul_ru(fabsf(hi.x), 1e-6f));
         ohi.y = __fadd_ru(__fadd_ru(hi.y, d), __fmul_ru(fabsf(hi.y), 1e-6f));
         ohi.z = __fadd_ru(__fadd_ru(hi.z, d), __fmul_ru(fabsf(hi.z), 1e-6f));
-        // trace layout: n[0] = c0.lo | ref0, n[1] = c0.hi | ref1, n[2] = c1.lo | 0, n[3] = c1.hi | 0
+        // trace layout: n[0] = c0.lo | ref0, n[1] = c0.hi | ref1, n[2] = c1.lo | 0, n[3] = c1.hi | 0  (BVHT_SUB_CH: lo -> centre, hi -> half)
         olo.w = 0.0f; ohi.w = 0.0f;
+#if BVHT_SUB_CH
+        // centre + half extent: [c - h, c + h] contains [olo, ohi]; h also absorbs the two extra roundings of slab_test_ch
+        // (eps * |t_centre| and eps * |h f|, together < 2 eps (|o| + |c| + h) in space units: abs_ / 4 = 4 eps s_max covers it)
+        {
+            float4 ce, ha;
+            ce.x = __fmul_rn(0.5f, __fadd_rn(olo.x, ohi.x));
+            ce.y = __fmul_rn(0.5f, __fadd_rn(olo.y, ohi.y));
+            ce.z = __fmul_rn(0.5f, __fadd_rn(olo.z, ohi.z));
+            ha.x = fmaxf(__fsub_ru(ohi.x, ce.x), __fsub_ru(ce.x, olo.x));
+            ha.y = fmaxf(__fsub_ru(ohi.y, ce.y), __fsub_ru(ce.y, olo.y));
+            ha.z = fmaxf(__fsub_ru(ohi.z, ce.z), __fsub_ru(ce.z, olo.z));
+            const float extra = __fmul_ru(abs_, 0.25f);
+            ha.x = __fadd_ru(__fmul_ru(ha.x, 1.000001f), extra);
+            ha.y = __fadd_ru(__fmul_ru(ha.y, 1.000001f), extra);
+            ha.z = __fadd_ru(__fmul_ru(ha.z, 1.000001f), extra);
+            // boxes blown up to infinity (absurd ray limits): an always-hit axis instead of inf - inf = NaN
+            if (!(fabsf(ce.x) <= 1e37f) || !(ha.x <= 1e37f)) { ce.x = 0.0f; ha.x = 3.0e38f; }
+            if (!(fabsf(ce.y) <= 1e37f) || !(ha.y <= 1e37f)) { ce.y = 0.0f; ha.y = 3.0e38f; }
+            if (!(fabsf(ce.z) <= 1e37f) || !(ha.z <= 1e37f)) { ce.z = 0.0f; ha.z = 3.0e38f; }
+            ce.w = 0.0f; ha.w = 0.0f;
+            olo = ce; ohi = ha;
+        }
+#endif
         out[4 * (size_t)i + 2 * c] = olo;
         out[4 * (size_t)i + 2 * c + 1] = ohi;
     }

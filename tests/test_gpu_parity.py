@@ -788,3 +788,60 @@ def test_sharded_host_renders_fill_one_shared_frame():
         assert frame.tobytes() == full_frame.tobytes()
         assert hits.tobytes() == full_hits.tobytes()
         e0.free_pinned(frame)
+
+
+# ------------------------------------------------------------------------------------------ chain-skipping TLAS walk
+def _random_instances(rng, n, spread):
+    objs = []
+    for i in range(n):
+        s = float(rng.uniform(0.4, 1.3))
+        m = O.transform_new_rot_xz([s, s, s], rng.uniform(-spread, spread, 3), float(rng.uniform(-3, 3)), float(rng.uniform(-3, 3)))
+        objs.append((i % 2, m))
+    return objs
+
+
+@pytest.mark.parametrize("n,seed", [(3, 1), (5, 2), (9, 3), (16, 4), (17, 5), (24, 6), (32, 7)])
+def test_tlas_chain_skipping_random_scenes(n, seed):
+    # <= 32 instances: tile-level candidate masks are on and, from 3 instances, the walk skips chains of nodes with a single
+    # relevant child (trace_kernels.cuh).  Overlapping, rotated instances of two models; <= 16 instances take the shuffle
+    # build of the skip table, 17..32 the shared-memory one.  Bit-identical to the oracle's plain ordered walk.
+    rng = np.random.default_rng(seed)
+    blases = [SB.oracle_blas("teapot.obj"), SB.oracle_blas("cube.obj")]
+    scene = O.Scene(blases, _random_instances(rng, n, 2.0 + 0.07 * n))
+    cam = O.camera_symmetric_fov(90.0, 1.0, 1.0, [0.3, 0.2, -6], [0, 0, 1], [1, 0, 0], [0, 1, 0])
+    w, h = 400, 232
+    ref = scene.render(cam, w, h, threads=NTHREADS)
+    assert (ref["id"] != O.MISS_ID).mean() > 0.015
+    with Engine(flags=FLAG_STRICT | FLAG_LEAF_ACCEL) as eng:
+        SB.upload_scene(eng, scene)
+        got = eng.trace_primary(SB.to_ffi_camera(cam), w, h)
+        assert_strict(got, ref)
+        # the same scene through the region / tile variants of the launch (ragged blocks)
+        got2 = eng.trace_primary(SB.to_ffi_camera(cam), w, h, tile=5)
+        ref2 = scene.render(cam, w, h, tile=5, threads=NTHREADS)
+        assert_strict(got2, ref2)
+
+
+def test_tlas_with_boxes_that_are_not_nested_takes_the_plain_walk():
+    # bvht_tlas_set accepts any node boxes.  Chain skipping is only valid for nested boxes, so a TLAS whose interior boxes
+    # clip their children must fall back to the plain walk -- and still equal the oracle, which applies every box test.
+    rng = np.random.default_rng(11)
+    blases = [SB.oracle_blas("teapot.obj"), SB.oracle_blas("cube.obj")]
+    scene = O.Scene(blases, _random_instances(rng, 12, 2.5))
+    cam = O.camera_symmetric_fov(90.0, 1.0, 1.0, [0, 0, -6], [0, 0, 1], [1, 0, 0], [0, 1, 0])
+    w, h = 400, 232
+    nested = scene.render(cam, w, h, threads=NTHREADS)
+    n = len(scene.objects)
+    tl = scene.tlas
+    for i in range(n + 1, scene.tlas_used):          # interior nodes: pull both corners towards the centre
+        c = 0.5 * (tl["min"][i] + tl["max"][i])
+        tl["min"][i] = c + 0.8 * (tl["min"][i] - c)
+        tl["max"][i] = c + 0.8 * (tl["max"][i] - c)
+    ref = scene.render(cam, w, h, threads=NTHREADS)
+    assert (ref["id"] != O.MISS_ID).mean() > 0.05
+    assert (ref["id"] != nested["id"]).sum() > 100    # the clipped boxes do change the reference's answer
+    for flags in STRICT_MODES:
+        with Engine(flags=flags) as eng:
+            SB.upload_scene(eng, scene)
+            got = eng.trace_primary(SB.to_ffi_camera(cam), w, h)
+        assert_strict(got, ref)
