@@ -51,7 +51,7 @@ struct Blas {
     DevBuf chunk_leaf, chunk_first, chunk_count, leaf_chunks, parent, scratch, counters;
     uint32_t n_chunks = 0;
     // leaf accelerator
-    DevBuf sub_nodes, sub_raw, sub_order, stri, leaf_sub_root, sub_parent, sub_counters;
+    DevBuf sub_nodes, sub_raw, sub_lohi, sub_order, stri, leaf_sub_root, sub_parent, sub_counters;
     uint32_t n_sub = 0, n_sub_nodes = 0;
     // current bake: model-space ray limits and the whole-model tight box inflated for them
     float d_max = 0.0f, o_max = 0.0f;
@@ -152,7 +152,7 @@ int h2d(bvht_ctx* ctx, void* dst, const void* src, size_t bytes) {
 
 void free_blas(Blas& b) {
     for (DevBuf* d : { &b.tris_aos, &b.nodes, &b.tri, &b.normals, &b.tex_coords, &b.texels, &b.chunk_leaf, &b.chunk_first, &b.chunk_count,
-                       &b.leaf_chunks, &b.parent, &b.scratch, &b.counters, &b.sub_nodes, &b.sub_raw, &b.sub_order, &b.stri,
+                       &b.leaf_chunks, &b.parent, &b.scratch, &b.counters, &b.sub_nodes, &b.sub_raw, &b.sub_lohi, &b.sub_order, &b.stri,
                        &b.leaf_sub_root, &b.sub_parent, &b.sub_counters })
         release(*d);
     b = Blas();
@@ -211,7 +211,13 @@ int bake_accel(bvht_ctx* ctx, Blas& b, double d_max, double o_max) {
     accel_deltas(cfg, d_max, o_max, b.radius, b.max_edge, scale, abs_);
     float fs = (float)scale; if ((double)fs < scale) fs = std::nextafterf(fs, FLT_MAX);
     float fa = (float)abs_; if ((double)fa < abs_) fa = std::nextafterf(fa, FLT_MAX);
-    CU(ctx, launch_inflate_sub_nodes((const float4*)b.sub_raw.p, (float4*)b.sub_nodes.p, b.n_sub_nodes, fs, fa, ctx->stream));
+    {
+        int rc = ensure(ctx, b.sub_lohi, (size_t)std::max<uint32_t>(b.n_sub_nodes, 1) * 64);
+        if (rc) return rc;
+    }
+    CU(ctx, launch_bake_sub_nodes((const float4*)b.sub_raw.p, (const uint32_t*)b.sub_parent.p, (unsigned int*)b.sub_counters.p,
+                                  (const float*)b.tris_aos.p, (const uint32_t*)b.sub_order.p, b.n_sub_nodes, fs, fa,
+                                  (float4*)b.sub_lohi.p, (float4*)b.sub_nodes.p, ctx->stream));
     if (b.n_sub_nodes) ctx->stats.kernel_launches += 1;
     b.d_max = (float)d_max; if ((double)b.d_max > d_max) b.d_max = std::nextafterf(b.d_max, 0.0f);
     b.o_max = (float)o_max; if ((double)b.o_max > o_max) b.o_max = std::nextafterf(b.o_max, 0.0f);

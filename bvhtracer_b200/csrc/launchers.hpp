@@ -23,7 +23,9 @@ cudaError_t launch_read_bw(const void* buf, size_t bytes, uint32_t iters, int gr
 cudaError_t launch_ray_bounds(const float* rays, unsigned long long n, unsigned int* out2, cudaStream_t s);
 cudaError_t launch_refit_sub_nodes(float4* raw, const uint32_t* parent, unsigned int* counters, const float* tris_aos,
                                    const uint32_t* order, uint32_t n_nodes, cudaStream_t s);
-cudaError_t launch_inflate_sub_nodes(const float4* raw, float4* out, uint32_t n_nodes, float scale, float abs_, cudaStream_t s);
+cudaError_t launch_bake_sub_nodes(const float4* raw, const uint32_t* parent, unsigned int* counters, const float* tris_aos,
+                                  const uint32_t* order, uint32_t n_nodes, float scale, float abs_, float4* lohi_scratch, float4* out,
+                                  cudaStream_t s);
 
 // scene_kernels.cu
 size_t      scene_rebuild_smem_bytes(uint32_t n_inst);

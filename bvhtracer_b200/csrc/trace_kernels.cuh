@@ -28,7 +28,7 @@
 #endif
 
 #ifndef BVHT_MIN_BLOCKS
-#define BVHT_MIN_BLOCKS 6      // CTAs of 128 threads per SM the register allocation must allow (tuned on B200)
+#define BVHT_MIN_BLOCKS 8      // CTAs of 128 threads per SM the register allocation must allow: 64 registers (swept 5-10 on B200)
 #endif
 
 namespace bvht {

@@ -44,57 +44,112 @@ repack_sub_triangles_kernel(const float* __restrict__ tris, const uint32_t* __re
     out[3 * (size_t)i + 2] = make_float4(__ldg(t + 6) - ax, __ldg(t + 7) - ay, __ldg(t + 8) - az, 0.0f);
 }
 
-// Bake the sub-BVH for the current ray limits: out = raw boxes grown by delta = scale * kappa + abs (leaf_accel.hpp
-// accel_deltas), every operation rounded AWAY from the box (directed-rounding intrinsics), plus a relative 1e-6.
-// 64 B read + 64 B written per sub node; runs at upload and whenever the limits change (bvht_api.cu ensure_bake).
+// One baked child box in the form the trace kernel reads (device_types.cuh BVHT_SUB_CH): {lo, hi} or {centre, half extent}.
+// [c - h, c + h] contains [lo, hi]; h also absorbs the two extra roundings of slab_test_ch (eps * |t_centre| and
+// eps * |h f|, together < 2 eps (|o| + |c| + h) in space units: abs_ / 4 = 4 eps s_max covers it).
+__device__ __forceinline__ void store_baked_child(float4* __restrict__ out, size_t node, int slot, float4 olo, float4 ohi, float abs_,
+                                                  float w0, float w1) {
+#if BVHT_SUB_CH
+    float4 ce, ha;
+    ce.x = __fmul_rn(0.5f, __fadd_rn(olo.x, ohi.x));
+    ce.y = __fmul_rn(0.5f, __fadd_rn(olo.y, ohi.y));
+    ce.z = __fmul_rn(0.5f, __fadd_rn(olo.z, ohi.z));
+    ha.x = fmaxf(__fsub_ru(ohi.x, ce.x), __fsub_ru(ce.x, olo.x));
+    ha.y = fmaxf(__fsub_ru(ohi.y, ce.y), __fsub_ru(ce.y, olo.y));
+    ha.z = fmaxf(__fsub_ru(ohi.z, ce.z), __fsub_ru(ce.z, olo.z));
+    const float extra = __fmul_ru(abs_, 0.25f);
+    if (olo.x <= ohi.x && olo.y <= ohi.y && olo.z <= ohi.z) {
+        ha.x = __fadd_ru(__fmul_ru(ha.x, 1.000001f), extra);
+        ha.y = __fadd_ru(__fmul_ru(ha.y, 1.000001f), extra);
+        ha.z = __fadd_ru(__fmul_ru(ha.z, 1.000001f), extra);
+        // boxes blown up to infinity (absurd ray limits): an always-hit axis instead of inf - inf = NaN
+        if (!(fabsf(ce.x) <= 1e37f) || !(ha.x <= 1e37f)) { ce.x = 0.0f; ha.x = 3.0e38f; }
+        if (!(fabsf(ce.y) <= 1e37f) || !(ha.y <= 1e37f)) { ce.y = 0.0f; ha.y = 3.0e38f; }
+        if (!(fabsf(ce.z) <= 1e37f) || !(ha.z <= 1e37f)) { ce.z = 0.0f; ha.z = 3.0e38f; }
+    } else {
+        // empty box (only degenerate triangles below): a negative half extent can never be hit
+        ce.x = ce.y = ce.z = 0.0f; ha.x = ha.y = ha.z = -1.0f;
+    }
+    olo = ce; ohi = ha;
+#endif
+    olo.w = w0; ohi.w = w1;
+    out[4 * node + 2 * slot] = olo;
+    out[4 * node + 2 * slot + 1] = ohi;
+}
+
+// Bake the sub-BVH for the current ray limits, bottom-up.  Every TRIANGLE's box is grown by its own
+// delta = scale * |e1||e2| + abs (leaf_accel.hpp accel_deltas; every operation rounded AWAY from the box, plus a relative
+// 1e-6), and an inner box is the exact min/max union of its children's baked boxes -- far tighter than growing the union
+// by the largest delta below it when triangle sizes are uneven (big_ben_clock: 1.21 -> measured in DESIGN.md).  Triangles
+// with a zero edge are never accepted by Triangle::intersect (area == 0 exactly) and contribute no box: the 999-sentinel
+// of every .tri asset no longer stretches the boxes above it.  Same arrival-counter climb as refit_sub_nodes_kernel;
+// `lohi` is scratch in {lo, hi} form (the climb must not lose exactness to the centre/half conversion).
+// Runs at upload, after every vertex update and whenever the limits change (bvht_api.cu ensure_bake).
 __global__ void __launch_bounds__(kRepackBlock)
-inflate_sub_nodes_kernel(const float4* __restrict__ raw, float4* __restrict__ out, uint32_t n_nodes, float scale, float abs_) {
-    uint32_t i = blockIdx.x * kRepackBlock + threadIdx.x;
-    if (i >= n_nodes) return;
+bake_sub_nodes_kernel(const float4* __restrict__ raw, const uint32_t* __restrict__ parent, unsigned int* __restrict__ counters,
+                      const float* __restrict__ tris, const uint32_t* __restrict__ order, uint32_t n_nodes, float scale, float abs_,
+                      float4* __restrict__ lohi, float4* __restrict__ out) {
+    uint32_t node = blockIdx.x * kRepackBlock + threadIdx.x;
+    if (node >= n_nodes) return;
+    const float ref0 = __ldg(reinterpret_cast<const float*>(raw + 4 * (size_t)node + 1) + 3);
+    const float ref1 = __ldg(reinterpret_cast<const float*>(raw + 4 * (size_t)node + 3) + 3);
+    unsigned int arrivals = 0;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-        float4 lo = __ldg(raw + 4 * (size_t)i + 2 * c);        // lo.xyz, kappa
-        float4 hi = __ldg(raw + 4 * (size_t)i + 2 * c + 1);    // hi.xyz, ref
-        float d = __fmaf_ru(scale, lo.w, abs_);
-        float4 olo, ohi;
-        olo.x = __fsub_rd(__fsub_rd(lo.x, d), __fmul_ru(fabsf(lo.x), 1e-6f));
-        olo.y = __fsub_rd(__fsub_rd(lo.y, d), __fmul_ru(fabsf(lo.y), 1e-6f));
-        olo.z = __fsub_rd(__fsub_rd(lo.z, d), __fmul_ru(fabsf(lo.z), 1e-6f));
-        ohi.x = __fadd_ru(__fadd_ru(hi.x, d), __fmul_ru(fabsf(hi.x), 1e-6f));
-        ohi.y = __fadd_ru(__fadd_ru(hi.y, d), __fmul_ru(fabsf(hi.y), 1e-6f));
-        ohi.z = __fadd_ru(__fadd_ru(hi.z, d), __fmul_ru(fabsf(hi.z), 1e-6f));
-        // trace layout: n[0] = c0.lo | ref0, n[1] = c0.hi | ref1, n[2] = c1.lo | 0, n[3] = c1.hi | 0  (BVHT_SUB_CH: lo -> centre, hi -> half)
-        olo.w = 0.0f; ohi.w = 0.0f;
-#if BVHT_SUB_CH
-        // centre + half extent: [c - h, c + h] contains [olo, ohi]; h also absorbs the two extra roundings of slab_test_ch
-        // (eps * |t_centre| and eps * |h f|, together < 2 eps (|o| + |c| + h) in space units: abs_ / 4 = 4 eps s_max covers it)
-        {
-            float4 ce, ha;
-            ce.x = __fmul_rn(0.5f, __fadd_rn(olo.x, ohi.x));
-            ce.y = __fmul_rn(0.5f, __fadd_rn(olo.y, ohi.y));
-            ce.z = __fmul_rn(0.5f, __fadd_rn(olo.z, ohi.z));
-            ha.x = fmaxf(__fsub_ru(ohi.x, ce.x), __fsub_ru(ce.x, olo.x));
-            ha.y = fmaxf(__fsub_ru(ohi.y, ce.y), __fsub_ru(ce.y, olo.y));
-            ha.z = fmaxf(__fsub_ru(ohi.z, ce.z), __fsub_ru(ce.z, olo.z));
-            const float extra = __fmul_ru(abs_, 0.25f);
-            ha.x = __fadd_ru(__fmul_ru(ha.x, 1.000001f), extra);
-            ha.y = __fadd_ru(__fmul_ru(ha.y, 1.000001f), extra);
-            ha.z = __fadd_ru(__fmul_ru(ha.z, 1.000001f), extra);
-            // boxes blown up to infinity (absurd ray limits): an always-hit axis instead of inf - inf = NaN
-            if (!(fabsf(ce.x) <= 1e37f) || !(ha.x <= 1e37f)) { ce.x = 0.0f; ha.x = 3.0e38f; }
-            if (!(fabsf(ce.y) <= 1e37f) || !(ha.y <= 1e37f)) { ce.y = 0.0f; ha.y = 3.0e38f; }
-            if (!(fabsf(ce.z) <= 1e37f) || !(ha.z <= 1e37f)) { ce.z = 0.0f; ha.z = 3.0e38f; }
-            ce.w = 0.0f; ha.w = 0.0f;
-            olo = ce; ohi = ha;
+        uint32_t ref = __float_as_uint(c ? ref1 : ref0);
+        if (!(ref & 0x80000000u)) continue;
+        uint32_t first = ref & 0x0FFFFFFFu, cnt = ((ref >> 28) & 7u) + 1u;
+        float4 lo = make_float4(3.402823466e38f, 3.402823466e38f, 3.402823466e38f, 0.0f);
+        float4 hi = make_float4(-3.402823466e38f, -3.402823466e38f, -3.402823466e38f, 0.0f);
+        for (uint32_t k = 0; k < cnt; ++k) {
+            const float* t = tris + (size_t)__ldg(order + first + k) * 9;
+            float v[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) v[j] = __ldg(t + j);
+            double e1x = (double)v[3] - v[0], e1y = (double)v[4] - v[1], e1z = (double)v[5] - v[2];
+            double e2x = (double)v[6] - v[0], e2y = (double)v[7] - v[1], e2z = (double)v[8] - v[2];
+            double kp = sqrt(e1x * e1x + e1y * e1y + e1z * e1z) * sqrt(e2x * e2x + e2y * e2y + e2z * e2z);
+            if (!(kp > 0.0)) continue;                       // a zero edge: never accepted
+            float d = __fmaf_ru(scale, __double2float_ru(kp * (1.0 + 1e-12)), abs_);
+            float tl[3], th[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                tl[a] = fminf(fminf(v[a], v[3 + a]), v[6 + a]);
+                th[a] = fmaxf(fmaxf(v[a], v[3 + a]), v[6 + a]);
+                tl[a] = __fsub_rd(__fsub_rd(tl[a], d), __fmul_ru(fabsf(tl[a]), 1e-6f));
+                th[a] = __fadd_ru(__fadd_ru(th[a], d), __fmul_ru(fabsf(th[a]), 1e-6f));
+            }
+            lo.x = fminf(lo.x, tl[0]); lo.y = fminf(lo.y, tl[1]); lo.z = fminf(lo.z, tl[2]);
+            hi.x = fmaxf(hi.x, th[0]); hi.y = fmaxf(hi.y, th[1]); hi.z = fmaxf(hi.z, th[2]);
         }
-#endif
-        out[4 * (size_t)i + 2 * c] = olo;
-        out[4 * (size_t)i + 2 * c + 1] = ohi;
+        __stcg(lohi + 4 * (size_t)node + 2 * c, lo);
+        __stcg(lohi + 4 * (size_t)node + 2 * c + 1, hi);
+        store_baked_child(out, node, c, lo, hi, abs_, c ? 0.0f : ref0, c ? 0.0f : ref1);
+        arrivals++;
     }
-    // child references live in the .w of the first two float4s
-    float r0 = __ldg(raw + 4 * (size_t)i + 1).w, r1 = __ldg(raw + 4 * (size_t)i + 3).w;
-    reinterpret_cast<float*>(out + 4 * (size_t)i)[3] = r0;
-    reinterpret_cast<float*>(out + 4 * (size_t)i + 1)[3] = r1;
+    if (arrivals == 0) return;                       // both children are inner nodes: whoever completes them climbs through here
+    __threadfence();
+    unsigned int old = atomicAdd(counters + node, arrivals);
+    if (old + arrivals != 2u) return;
+    for (;;) {                                       // this thread completed `node`: climb
+        __threadfence();
+        uint32_t pp = __ldg(parent + node);
+        if (pp == 0xFFFFFFFFu) break;                // root of a sub tree: its children ARE what the trace kernel tests
+        float4 a = __ldcg(lohi + 4 * (size_t)node + 0), b = __ldcg(lohi + 4 * (size_t)node + 1);
+        float4 c = __ldcg(lohi + 4 * (size_t)node + 2), d = __ldcg(lohi + 4 * (size_t)node + 3);
+        uint32_t p = pp >> 1, slot = pp & 1u;
+        float4 plo = make_float4(fminf(a.x, c.x), fminf(a.y, c.y), fminf(a.z, c.z), 0.0f);
+        float4 phi = make_float4(fmaxf(b.x, d.x), fmaxf(b.y, d.y), fmaxf(b.z, d.z), 0.0f);
+        __stcg(lohi + 4 * (size_t)p + 2 * slot, plo);
+        __stcg(lohi + 4 * (size_t)p + 2 * slot + 1, phi);
+        const float pr0 = __ldg(reinterpret_cast<const float*>(raw + 4 * (size_t)p + 1) + 3);
+        const float pr1 = __ldg(reinterpret_cast<const float*>(raw + 4 * (size_t)p + 3) + 3);
+        store_baked_child(out, p, (int)slot, plo, phi, abs_, slot ? 0.0f : pr0, slot ? 0.0f : pr1);
+        __threadfence();
+        unsigned int o = atomicAdd(counters + p, 1u);
+        if (o + 1u != 2u) break;
+        node = p;
+    }
 }
 
 // Refit of the sub-BVHs after a vertex update (topology kept, raw boxes and kappa recomputed bottom-up): one thread per
@@ -227,10 +282,14 @@ cudaError_t launch_refit_sub_nodes(float4* raw, const uint32_t* parent, unsigned
     return cudaGetLastError();
 }
 
-cudaError_t launch_inflate_sub_nodes(const float4* raw, float4* out, uint32_t n_nodes, float scale, float abs_, cudaStream_t s) {
+cudaError_t launch_bake_sub_nodes(const float4* raw, const uint32_t* parent, unsigned int* counters, const float* tris_aos,
+                                  const uint32_t* order, uint32_t n_nodes, float scale, float abs_, float4* lohi_scratch, float4* out,
+                                  cudaStream_t s) {
     if (n_nodes == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(counters, 0, (size_t)n_nodes * 4, s);
+    if (e != cudaSuccess) return e;
     int grid = (int)((n_nodes + kRepackBlock - 1) / kRepackBlock);
-    inflate_sub_nodes_kernel<<<grid, kRepackBlock, 0, s>>>(raw, out, n_nodes, scale, abs_);
+    bake_sub_nodes_kernel<<<grid, kRepackBlock, 0, s>>>(raw, parent, counters, tris_aos, order, n_nodes, scale, abs_, lohi_scratch, out);
     return cudaGetLastError();
 }
 
