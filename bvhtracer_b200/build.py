@@ -64,7 +64,7 @@ def build(force=False, verbose=False):
         extra_defs.append("-DBVHT_MIN_BLOCKS=" + os.environ["BVHT_MIN_BLOCKS"])
     if os.environ.get("BVHT_GRAB"):                  # tuning knob: 32-pixel slices pulled per work-counter atomic
         extra_defs.append("-DBVHT_GRAB=" + os.environ["BVHT_GRAB"])
-    for knob in ("BVHT_SUB_CH", "BVHT_TLAS_PRUNE"):                    # experiment knobs passed through to every translation unit
+    for knob in ("BVHT_SUB_CH", "BVHT_TLAS_PRUNE", "BVHT_SLICE_LOG"):                    # experiment knobs passed through to every translation unit
         if os.environ.get(knob):
             extra_defs.append("-D%s=%s" % (knob, os.environ[knob]))
     os.makedirs(LIB_DIR, exist_ok=True)

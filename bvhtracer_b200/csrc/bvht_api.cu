@@ -89,7 +89,8 @@ struct bvht_ctx {
     std::vector<bvht_instance> h_inst;
     std::vector<float> inst_tight;                    // 6 floats per instance (world lo/hi) or lo > hi when unusable
     double bake_center[3] = { 0.0, 0.0, 0.0 };        // camera origin the tight TLAS boxes' origin limit is centred on
-    DevBuf work_counter;
+    DevBuf work_counter;                              // slot i: [2i] = K1's work cursor, [2i+1] = length of K0's block list
+    DevBuf work_list;                                 // K0's list of blocks that see an instance, one u32 per block of the frame
     BuildWorkspace build_ws;                   // K3 scratch (grow-only)
     DevBuf build_tris, build_perm;             // K3 input/output: triangles reordered in place + the permutation
     DevBuf out_buf, rays_buf, rgba_buf;               // device staging for the host-pointer entry points
@@ -223,12 +224,34 @@ int bake_accel(bvht_ctx* ctx, Blas& b, double d_max, double o_max) {
     b.o_max = (float)o_max; if ((double)b.o_max > o_max) b.o_max = std::nextafterf(b.o_max, 0.0f);
     b.tight_valid = b.model_valid;
     if (b.model_valid) {
-        double delta = (double)fs * b.model_kappa + (double)fa;
+        // like the sub boxes (bake_sub_nodes_kernel): every triangle grown by ITS delta = scale * |e1||e2| + abs, then the
+        // union -- one large triangle (big_ben_clock: max |e1||e2| = 0.83 against a median of 0.0014) no longer widens the
+        // whole model's box, and with it the instance's screen rectangle, by its own slack
+        double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+        const float* T = b.h_tris.data();
+        for (uint32_t i = 0; i < b.n_tris && b.h_tris.size() >= (size_t)b.n_tris * 9; ++i) {
+            const float* t = T + (size_t)i * 9;
+            double e1[3], e2[3];
+            for (int k = 0; k < 3; ++k) { e1[k] = (double)t[3 + k] - t[k]; e2[k] = (double)t[6 + k] - t[k]; }
+            double kp = std::sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]) * std::sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
+            if (!(kp > 0.0)) continue;
+            double delta = (double)fs * kp * (1.0 + 1e-9) + (double)fa;
+            for (int k = 0; k < 3; ++k) {
+                double l = std::min({ (double)t[k], (double)t[3 + k], (double)t[6 + k] }), h = std::max({ (double)t[k], (double)t[3 + k], (double)t[6 + k] });
+                lo[k] = std::min(lo[k], l - delta - std::fabs(l) * 1e-6);
+                hi[k] = std::max(hi[k], h + delta + std::fabs(h) * 1e-6);
+            }
+        }
+        if (!(lo[0] <= hi[0])) {      // no host copy of the triangles: the whole-model bound
+            double delta = (double)fs * b.model_kappa + (double)fa;
+            for (int k = 0; k < 3; ++k) {
+                lo[k] = (double)b.model_lo[k] - delta - std::fabs((double)b.model_lo[k]) * 1e-6;
+                hi[k] = (double)b.model_hi[k] + delta + std::fabs((double)b.model_hi[k]) * 1e-6;
+            }
+        }
         for (int k = 0; k < 3; ++k) {
-            double lo = (double)b.model_lo[k] - delta - std::fabs((double)b.model_lo[k]) * 1e-6;
-            double hi = (double)b.model_hi[k] + delta + std::fabs((double)b.model_hi[k]) * 1e-6;
-            float flo = (float)lo; if ((double)flo > lo) flo = std::nextafterf(flo, -FLT_MAX);
-            float fhi = (float)hi; if ((double)fhi < hi) fhi = std::nextafterf(fhi, FLT_MAX);
+            float flo = (float)lo[k]; if ((double)flo > lo[k]) flo = std::nextafterf(flo, -FLT_MAX);
+            float fhi = (float)hi[k]; if ((double)fhi < hi[k]) fhi = std::nextafterf(fhi, FLT_MAX);
             b.tight_lo[k] = flo; b.tight_hi[k] = fhi;
         }
     }
@@ -685,7 +708,7 @@ int ensure_bake(bvht_ctx* ctx, const bvht_camera* cam) {
 // Arbitrary ray batch: one small reduction kernel gives max |o_w| and max |d_w|; bake for a ball around the world origin.
 int ensure_bake_rays(bvht_ctx* ctx, const void* rays_device, uint64_t n) {
     if (!accel_on(ctx) || ctx->h_inst.empty() || n == 0) return BVHT_OK;
-    unsigned int* scratch = (unsigned int*)ctx->work_counter.p + 64;      // two words after the 64 band counters
+    unsigned int* scratch = (unsigned int*)ctx->work_counter.p + 128;     // two words after the 64 band slots (cursor + list length each)
     CU(ctx, launch_ray_bounds((const float*)rays_device, n, scratch, ctx->stream));
     ctx->stats.kernel_launches += 1;
     float m[2] = { 0.0f, 0.0f };
@@ -893,7 +916,7 @@ int bvht_create(int device, uint32_t flags, bvht_ctx** out) {
            && cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
     if (ok) {
         ctx->stream = ctx->own_stream;
-        ok = ensure(ctx, ctx->work_counter, 512) == BVHT_OK && ensure_pinned(ctx, 1 << 16) == BVHT_OK;
+        ok = ensure(ctx, ctx->work_counter, 1024) == BVHT_OK && ensure_pinned(ctx, 1 << 16) == BVHT_OK;
     }
     if (ok) {
         ok = cudaStreamCreateWithFlags(&ctx->aux[0], cudaStreamNonBlocking) == cudaSuccess
@@ -916,7 +939,7 @@ void bvht_destroy(bvht_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (Blas& b : ctx->blas) free_blas(b);
-    for (DevBuf* d : { &ctx->blas_desc, &ctx->tlas, &ctx->inst_cols, &ctx->inst_blas, &ctx->work_counter, &ctx->out_buf, &ctx->rays_buf,
+    for (DevBuf* d : { &ctx->blas_desc, &ctx->tlas, &ctx->inst_cols, &ctx->inst_blas, &ctx->work_counter, &ctx->work_list, &ctx->out_buf, &ctx->rays_buf,
                        &ctx->rgba_buf, &ctx->tlas_tight, &ctx->tlas_mask, &ctx->scene_in, &ctx->scene_bounds })
         release(*d);
     for (cudaStream_t st : { ctx->aux[0], ctx->aux[1], ctx->copy_stream }) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
@@ -1382,13 +1405,51 @@ static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvh
             p.shade_n_prims = b0.n_tris;
         }
     }
-    p.work_counter = (unsigned int*)ctx->work_counter.p + slot;
+    p.work_counter = (unsigned int*)ctx->work_counter.p + 2 * slot;
     p.n_rect = 0;
     if (accel_on(ctx)) { uint32_t nr = 0; if (compute_instance_rects(ctx, camera, width, height, p.inst_rect, nr)) p.n_rect = nr; }
     // chain skipping pays from three instances on (measured: pure overhead for 1-2 instances)
     p.n_tlas_nodes = (p.n_rect >= 3 && ctx->tlas_nested && ctx->h_tlas.size() <= 64) ? (uint32_t)ctx->h_tlas.size() : 0u;
     p.skip_rounds = 0;
     while ((1u << p.skip_rounds) < ctx->tlas_depth) ++p.skip_rounds;
+    if (const char* lp = getenv("BVHT_SLICE_LOG_PTR")) p.stats = (unsigned long long*)strtoull(lp, nullptr, 0);   // profiling build (BVHT_SLICE_LOG) only
+    // K0 pays when most blocks are empty (big_ben_clock 8K, 64 % empty: 1.11 -> 1.02 ms); when the instances' rectangles cover
+    // the frame it is a wasted pass plus one dependent load per block in K1 (trippy_teapots, all blocks listed: 0.42 -> 0.46 ms).
+    // Decide from the rectangles on a 32 x 32 grid over the launch's region.  BVHT_K0=0 / 1 forces it off / on (A/B knob).
+    const char* k0_env = getenv("BVHT_K0");
+    bool use_k0 = false;
+    if (p.n_rect) {
+        if (k0_env) use_k0 = k0_env[0] == '1';
+        else {
+            constexpr int G = 32;
+            uint32_t covered[G] = { 0 };
+            const double rw = (double)(region.x1 - region.x0) / G, rh = (double)(region.y1 - region.y0) / G;
+            for (uint32_t i = 0; i < p.n_rect; ++i) {
+                const int4 rc = p.inst_rect[i];
+                int cx0 = (int)std::floor(((double)rc.x - region.x0) / rw), cx1 = (int)std::floor(((double)rc.z - region.x0) / rw);
+                int cy0 = (int)std::floor(((double)rc.y - region.y0) / rh), cy1 = (int)std::floor(((double)rc.w - region.y0) / rh);
+                if (cx1 < 0 || cy1 < 0 || cx0 >= G || cy0 >= G || rc.z < rc.x || rc.w < rc.y) continue;
+                cx0 = std::max(cx0, 0); cy0 = std::max(cy0, 0); cx1 = std::min(cx1, G - 1); cy1 = std::min(cy1, G - 1);
+                uint32_t bits = (cx1 - cx0 == 31) ? 0xFFFFFFFFu : (((1u << (cx1 - cx0 + 1)) - 1u) << cx0);
+                for (int y = cy0; y <= cy1; ++y) covered[y] |= bits;
+            }
+            int n_cov = 0;
+            for (int y = 0; y < G; ++y) n_cov += __builtin_popcount(covered[y]);
+            use_k0 = n_cov * 2 < G * G;                  // more than half of the cells see no instance
+        }
+    }
+    if (use_k0) {
+        // K0 + work list: launches of one frame own disjoint tile rows, so each lists its blocks from its first row's offset
+        uint64_t ntx_full = ((uint64_t)width + tile - 1) / tile, nty_full = ((uint64_t)height + tile - 1) / tile;
+        uint64_t cap = ntx_full * nty_full * p.items_per_tile;
+        if (cap <= (64ull << 20)) {
+            int rc = ensure(ctx, ctx->work_list, (size_t)cap * 4);
+            if (rc) return rc;
+            p.work_list = (uint32_t*)ctx->work_list.p + (uint64_t)p.ty0 * ntx_full * p.items_per_tile;
+            p.work_count = (unsigned int*)ctx->work_counter.p + 2 * slot + 1;
+            ctx->stats.kernel_launches += 1;
+        }
+    }
     int grid = persistent_grid(ctx, true, n_items);
     cudaError_t e = fast_on(ctx) ? launch_primary_fast(p, accel_on(ctx), grid, kTraceBlock, stream)
                                  : launch_primary_strict(p, accel_on(ctx), grid, kTraceBlock, stream);
@@ -1423,7 +1484,7 @@ int bvht_render_frame_device(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
     if ((rc = fill_scene(ctx, scene))) return rc;
     ctx->stats.last_trace_rays = 0;
     if (region.x0 >= region.x1 || region.y0 >= region.y1) return BVHT_OK;     // empty region: nothing to do
-    CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, 4, ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, 8, ctx->stream));
     cudaEventRecord(ctx->ev_a, ctx->stream);
     rc = launch_primary_region(ctx, scene, camera, width, height, tile, region, shade, hits_out_device, frame_out_device,
                                ctx->stream, 0, ctx->shard_index, ctx->shard_count);
@@ -1502,7 +1563,7 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
     uint64_t rays = (uint64_t)(region.x1 - region.x0) * (region.y1 - region.y0);
     uint32_t n_bands = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(rays / (1u << 20), 1), 16);
     n_bands = std::min(n_bands, tile_rows);
-    CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, 256, ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, 512, ctx->stream));
     cudaEventRecord(ctx->ev_a, ctx->stream);
     CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     for (int i = 0; i < 2; ++i) CU(ctx, cudaStreamWaitEvent(ctx->aux[i], ctx->ev_fork, 0));

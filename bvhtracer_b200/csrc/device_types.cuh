@@ -81,6 +81,10 @@ struct PrimaryParams {
     uint32_t  tex_w, tex_h;
     float     shade_m[12];               // kind 4: columns 0..2 (xyz) + column 3 (xyz) of object 0's forward transform
     unsigned int* work_counter;          // persistent-thread work cursor
+    // accel + candidate masks: K0 (classify_fill_kernel) writes the records of the blocks no instance can be seen from and
+    // lists the others here; K1 then pulls list positions instead of block numbers.  null = K1 walks every block itself.
+    uint32_t*     work_list;
+    unsigned int* work_count;            // number of listed blocks (device counter, zeroed before K0)
     unsigned long long* stats;           // debug counters (stats build only)
     // accel only: conservative screen-space rectangle (pixels, inclusive) of each instance's tight box for THIS camera;
     // n_rect == 0 disables the tile-level candidate masks

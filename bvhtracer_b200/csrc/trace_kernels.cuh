@@ -726,15 +726,22 @@ trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
     const unsigned lane = threadIdx.x & 31u;
     Stat st;
     __shared__ uint8_t s_skip[PRUNE ? 4 : 1][64];
+    // with a work list (K0 ran first) only the listed blocks are pulled; the others already hold their miss records
+    const unsigned n_work = P.work_list ? __ldcg(P.work_count) : P.n_items;
     for (;;) {
         unsigned base = 0;
         if (lane == 0) base = atomicAdd(P.work_counter, (unsigned)BVHT_GRAB);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= P.n_items) break;
+        if (base >= n_work) break;
 #pragma unroll 1
       for (unsigned g = 0; g < (unsigned)BVHT_GRAB; ++g) {
-        const unsigned item = base + g;       // row-major order: strided permutations measured 2-15 % slower (locality, cheap tail)
-        if (item >= P.n_items) break;
+        if (base + g >= n_work) break;
+        // row-major order: strided permutations measured 2-15 % slower (locality, cheap tail)
+        const unsigned item = P.work_list ? __ldcg(P.work_list + base + g) : base + g;
+#ifdef BVHT_SLICE_LOG
+        unsigned long long log_t0 = 0;                 // profiling build only (tools/slice_timeline.py): start / end of every block
+        if (P.stats) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(log_t0));
+#endif
         uint32_t tile_idx = item / P.items_per_tile;
         uint32_t sub = item - tile_idx * P.items_per_tile;
         uint32_t tx = P.tx0 + tile_idx % P.ntx;
@@ -780,6 +787,17 @@ trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
             }
             if (P.out_rgba) P.out_rgba[(size_t)py * P.width + px] = shade_pixel(P, h);
         }
+#ifdef BVHT_SLICE_LOG
+        __syncwarp();
+        if (P.stats && lane == 0) {
+            unsigned long long log_t1;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(log_t1));
+            unsigned smid;
+            asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+            P.stats[2 * (size_t)item] = log_t0;
+            P.stats[2 * (size_t)item + 1] = (log_t1 - log_t0) | ((unsigned long long)smid << 48) | ((unsigned long long)(threadIdx.x >> 5) << 44);
+        }
+#endif
       }
     }
 #ifdef BVHT_STATS
@@ -789,6 +807,58 @@ trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
         if (lane == 0 && v) atomicAdd(P.stats + i, v);
     }
 #endif
+}
+
+// K0: classify the 32-pixel blocks of a launch and finish the empty ones.  One LANE per block: the block's pixel rectangle
+// against every instance's screen rectangle (the same test K1 makes with one lane per instance).  Blocks that see an
+// instance are appended to the work list (one atomicAdd per warp = per 32 blocks); for the others the warp writes the 32
+// miss records (and shaded pixels) right away.  K1 alone would spend one work-counter atomic on every block, and that single
+// address serialises in L2 at ~1.3 G atomics/s: an empty 4K frame costs 0.2 ms, an 8K frame 0.8 ms, of which big_ben_clock
+// (87 % empty blocks) paid most.  Streaming kernel: 16 B (+ 4 B) written per empty pixel.
+__global__ void __launch_bounds__(128)
+classify_fill_kernel(const __grid_constant__ PrimaryParams P) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned item = blockIdx.x * 128u + threadIdx.x;          // this lane's block
+    const bool valid = item < P.n_items;
+    uint32_t tile_idx = 0, sub = 0;
+    bool seen = false;
+    if (valid) {
+        tile_idx = item / P.items_per_tile;
+        sub = item - tile_idx * P.items_per_tile;
+        uint32_t tx = P.tx0 + tile_idx % P.ntx;
+        uint32_t ty = P.ty0 + (tile_idx / P.ntx) * P.row_stride;
+        int bx0 = (int)(tx * P.tile), bx1 = bx0 + (int)P.tile - 1;
+        int by0 = (int)(ty * P.tile + (sub * 32u) / P.tile), by1 = (int)(ty * P.tile + (sub * 32u + 31u) / P.tile);
+        for (uint32_t i = 0; i < P.n_rect; ++i) {
+            int4 rc = P.inst_rect[i];
+            seen |= !(rc.z < bx0 || rc.x > bx1 || rc.w < by0 || rc.y > by1);
+        }
+    }
+    const unsigned listed = __ballot_sync(0xFFFFFFFFu, valid && seen);
+    unsigned empty = __ballot_sync(0xFFFFFFFFu, valid && !seen);
+    if (listed) {
+        unsigned at = 0;
+        if (lane == 0) at = atomicAdd(P.work_count, (unsigned)__popc(listed));
+        at = __shfl_sync(0xFFFFFFFFu, at, 0);
+        if (valid && seen) P.work_list[at + __popc(listed & ((1u << lane) - 1u))] = item;
+    }
+    HitRec miss;
+    miss.t = FLT_MAX; miss.u = 0.0f; miss.v = 0.0f; miss.id = 0xFFFFFFFFu;
+    const uint32_t miss_px = P.out_rgba ? shade_pixel(P, miss) : 0u;
+    while (empty) {
+        const int src = __ffs((int)empty) - 1;
+        empty &= empty - 1u;
+        const uint32_t e_tile = __shfl_sync(0xFFFFFFFFu, tile_idx, src), e_sub = __shfl_sync(0xFFFFFFFFu, sub, src);
+        uint32_t tx = P.tx0 + e_tile % P.ntx;
+        uint32_t ty = P.ty0 + (e_tile / P.ntx) * P.row_stride;
+        uint32_t p = e_sub * 32u + lane;
+        uint32_t iu = p % P.tile, iv = p / P.tile;
+        uint32_t px = tx * P.tile + iu, py = ty * P.tile + iv;
+        if ((iv < P.tile) && px >= P.x0 && px < P.x1 && py >= P.y0 && py < P.y1) {
+            if (P.out) P.out[(size_t)py * P.width + px] = make_uint4(__float_as_uint(miss.t), 0u, 0u, miss.id);
+            if (P.out_rgba) P.out_rgba[(size_t)py * P.width + px] = miss_px;
+        }
+    }
 }
 
 // K1b: Scene::intersect(&Ray) for an arbitrary ray buffer; warps pull 32 rays at a time.

@@ -845,3 +845,37 @@ def test_tlas_with_boxes_that_are_not_nested_takes_the_plain_walk():
             SB.upload_scene(eng, scene)
             got = eng.trace_primary(SB.to_ffi_camera(cam), w, h)
         assert_strict(got, ref)
+
+
+# ------------------------------------------------------------------------------------------ K0: classify + fill
+@pytest.mark.parametrize("k0", ["0", "1"])
+def test_k0_classify_fill_equals_single_kernel(k0, monkeypatch):
+    # K0 (classify_fill_kernel) writes the records of blocks no instance can be seen from and lists the others for K1.
+    # Forced on and off (BVHT_K0): hit records AND shaded frames must equal the oracle either way -- ragged tile sizes,
+    # sub-regions, tile-row shards into one buffer.
+    monkeypatch.setenv("BVHT_K0", k0)
+    rng = np.random.default_rng(21)
+    blases = [SB.oracle_blas("teapot.obj"), SB.oracle_blas("cube.obj")]
+    scene = O.Scene(blases, _random_instances(rng, 7, 2.5))
+    cam = O.camera_symmetric_fov(90.0, 1.0, 1.0, [0.3, 0.2, -7], [0, 0, 1], [1, 0, 0], [0, 1, 0])
+    w, h = 403, 229
+    fcam = SB.to_ffi_camera(cam)
+    with Engine(flags=FLAG_STRICT | FLAG_LEAF_ACCEL) as eng:
+        SB.upload_scene(eng, scene)
+        for tile in (8, 5, 16):
+            ref = scene.render(cam, w, h, tile=tile, threads=NTHREADS)
+            assert 0.01 < (ref["id"] != O.MISS_ID).mean() < 0.5
+            assert_strict(eng.trace_primary(fcam, w, h, tile=tile), ref)
+        ref = scene.render(cam, w, h, threads=NTHREADS)
+        # a sub-region: pixels outside keep the caller's initial records
+        region = (37, 19, 301, 180)
+        got = eng.trace_primary(fcam, w, h, region=region)
+        inside = np.zeros((h, w), bool)
+        inside[region[1]:region[3], region[0]:region[2]] = True
+        inside = inside.reshape(-1)
+        assert got[inside].tobytes() == ref[inside].tobytes()
+        assert (got["id"][~inside] == O.MISS_ID).all()
+        # fused shading through render_frame (bands) and the depth shader
+        frame, hits = eng.render_frame(fcam, w, h, Engine.shade_depth(80.0, 3.0), want_hits=True)
+        assert frame.tobytes() == O.shade(1, ref, 80.0, 3.0).tobytes()
+        assert hits.tobytes() == ref.tobytes()
