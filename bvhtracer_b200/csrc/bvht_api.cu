@@ -98,6 +98,9 @@ struct bvht_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_band[64] = {};
+    // bvht_render_frame launches its bands cheapest-first, from the previous frame's per-band kernel times
+    cudaEvent_t ev_band_t[17] = {};                   // timing events: [0] = start, [i + 1] = end of the i-th launched band
+    struct BandHistory { uint32_t key[8] = { 0 }; uint32_t n = 0; float ms_per_row[16] = { 0 }; bool valid = false; } band_hist;
     void* pinned = nullptr; size_t pinned_bytes = 0;  // pinned staging for small uploads
     int sm_count = 0;
     uint32_t shard_index = 0, shard_count = 1;
@@ -925,6 +928,7 @@ int bvht_create(int device, uint32_t flags, bvht_ctx** out) {
           && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess
           && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
         for (int i = 0; ok && i < 64; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_band[i], cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; ok && i < 17; ++i) ok = cudaEventCreate(&ctx->ev_band_t[i]) == cudaSuccess;
     }
     if (!ok) { cudaGetLastError(); bvht_destroy(ctx); return BVHT_ERR_CUDA; }
     ctx->stats.sm_count = (uint32_t)ctx->sm_count;
@@ -945,6 +949,7 @@ void bvht_destroy(bvht_ctx* ctx) {
     for (cudaStream_t st : { ctx->aux[0], ctx->aux[1], ctx->copy_stream }) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     for (cudaEvent_t ev : { ctx->ev_fork, ctx->ev_join }) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : ctx->ev_band) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ctx->ev_band_t) if (ev) cudaEventDestroy(ev);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (cudaEvent_t ev : { ctx->ev_a, ctx->ev_b, ctx->ev_c, ctx->ev_d, ctx->ev_e, ctx->ev_f }) if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -1523,6 +1528,7 @@ int bvht_trace_primary_device(bvht_ctx* ctx, const bvht_camera* camera, uint32_t
 // D2H of the rows [y0, y1) x [x0, x1) of a width-pitched buffer of `elem` byte pixels.
 static int copy_rows_d2h(bvht_ctx* ctx, void* host, const void* dev, uint32_t width, bvht_rect r, size_t elem, cudaStream_t st) {
     size_t row = (size_t)width * elem;
+    if (getenv("BVHT_DEBUG_NO_D2H")) return BVHT_OK;      // timing experiment only: bands without their copies
     if (r.x0 == 0 && r.x1 == width) {
         size_t off = (size_t)r.y0 * row, len = (size_t)(r.y1 - r.y0) * row;
         CU(ctx, cudaMemcpyAsync((char*)host + off, (const char*)dev + off, len, cudaMemcpyDeviceToHost, st));
@@ -1562,36 +1568,43 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
     uint32_t tile_rows = ty1 - ty0;
     uint64_t rays = (uint64_t)(region.x1 - region.x0) * (region.y1 - region.y0);
     uint32_t n_bands = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(rays / (1u << 20), 1), 16);
+    if (const char* e = getenv("BVHT_BANDS")) { int v = atoi(e); if (v >= 1 && v <= 16) n_bands = (uint32_t)v; }      // A/B knob
     n_bands = std::min(n_bands, tile_rows);
     CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, 512, ctx->stream));
     cudaEventRecord(ctx->ev_a, ctx->stream);
     CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     for (int i = 0; i < 2; ++i) CU(ctx, cudaStreamWaitEvent(ctx->aux[i], ctx->ev_fork, 0));
     CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
-    // Band shares are triangular (1, 2, 3, .., 3, 2, 1): the device->host copy of a band overlaps the tracing of the following
-    // ones, so only the FIRST band's tracing (nothing to copy yet; matters when the copy is the bottleneck, e.g. 16 B hit records)
-    // and the LAST band's copy (matters when tracing is the bottleneck) are exposed -- both are made small.
-    // BVHT_BANDS_UNIFORM=1 restores equal bands (A/B knob).
-    static const bool uniform_bands = getenv("BVHT_BANDS_UNIFORM") != nullptr;
+    // Equal bands of whole tile rows, launched CHEAPEST FIRST.  The device->host copy of a band overlaps the tracing of the
+    // bands launched after it, so what stays exposed is the first band's tracing and whatever is still to be copied when the last
+    // kernel ends.  In image order the frames of the examples end with rows that are nearly free to trace (sixteen_armadillos:
+    // the bottom 30 % of the rows take 6 % of the time), whose copies -- 10 MB, 0.18 ms -- then had nothing left to hide behind.
+    // Ordered by the time per row the previous frame measured for each band (CUDA events), the cheap rows go first and the
+    // frame ends with its slowest band, behind which the copies keep up.  No history (first frame, other size): image order.
+    // BVHT_BANDS_IMAGE_ORDER=1 keeps image order (A/B knob).
     std::vector<uint32_t> band_start(n_bands + 1, 0);
-    {
-        uint64_t wsum = 0, acc = 0;
-        for (uint32_t b = 0; b < n_bands; ++b) wsum += uniform_bands ? 1 : std::min(b + 1, n_bands - b);
-        for (uint32_t b = 0; b < n_bands; ++b) {
-            band_start[b] = (uint32_t)((uint64_t)tile_rows * acc / wsum);
-            acc += uniform_bands ? 1 : std::min(b + 1, n_bands - b);
-        }
-        band_start[n_bands] = tile_rows;
-    }
+    for (uint32_t b = 0; b <= n_bands; ++b) band_start[b] = (uint32_t)((uint64_t)tile_rows * b / n_bands);
+    uint32_t order[16];
+    for (uint32_t b = 0; b < n_bands; ++b) order[b] = b;
+    const uint32_t hist_key[8] = { width, height, tile, region.x0, region.y0, region.x1, region.y1, n_bands };
+    bvht_ctx::BandHistory& hist = ctx->band_hist;
+    static const bool image_order = getenv("BVHT_BANDS_IMAGE_ORDER") != nullptr;
+    if (hist.valid && hist.n == n_bands && memcmp(hist.key, hist_key, sizeof hist_key) == 0 && !image_order)
+        std::stable_sort(order, order + n_bands, [&](uint32_t x, uint32_t y) { return hist.ms_per_row[x] < hist.ms_per_row[y]; });
+    cudaEventRecord(ctx->ev_band_t[0], ctx->stream);
     auto band_row = [&](uint32_t b) -> uint32_t { return band_start[b]; };
-    for (uint32_t b = 0; b < n_bands; ++b) {
+    for (uint32_t i = 0; i < n_bands; ++i) {
+        const uint32_t b = order[i];
         uint32_t r0 = ty0 + band_row(b);
         uint32_t r1 = ty0 + band_row(b + 1);
         bvht_rect band = { region.x0, std::max(region.y0, r0 * tile), region.x1, std::min(region.y1, r1 * tile) };
+        cudaStream_t cs = ctx->aux[i & 1];
+        if (band.y0 < band.y1) {
+            if ((rc = launch_primary_region(ctx, scene, camera, width, height, tile, band, shade, d_hits, d_rgba, cs, (int)b,
+                                            ctx->shard_index, ctx->shard_count))) return rc;
+        }
+        cudaEventRecord(ctx->ev_band_t[i + 1], cs);
         if (band.y0 >= band.y1) continue;
-        cudaStream_t cs = ctx->aux[b & 1];
-        if ((rc = launch_primary_region(ctx, scene, camera, width, height, tile, band, shade, d_hits, d_rgba, cs, (int)b,
-                                        ctx->shard_index, ctx->shard_count))) return rc;
         CU(ctx, cudaEventRecord(ctx->ev_band[b], cs));
         CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[b], 0));
         if (ctx->shard_count == 1) {
@@ -1631,6 +1644,20 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
     ctx->trace_timed = true;
     ctx->stats.last_trace_rays = rays / ctx->shard_count;
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    // per-band kernel times of this frame -> launch order of the next one.  The kernels of consecutive bands sit on two
+    // streams and run back to back, so the end-to-end distance of their end events is the band's share of the frame.
+    {
+        hist.valid = true; hist.n = n_bands; memcpy(hist.key, hist_key, sizeof hist_key);
+        float prev = 0.0f;
+        for (uint32_t i = 0; i < n_bands && hist.valid; ++i) {
+            float t = 0.0f;
+            if (cudaEventElapsedTime(&t, ctx->ev_band_t[0], ctx->ev_band_t[i + 1]) != cudaSuccess) { cudaGetLastError(); hist.valid = false; break; }
+            const uint32_t b = order[i];
+            const uint32_t rows = std::max(1u, band_start[b + 1] - band_start[b]);
+            hist.ms_per_row[b] = std::max(t - prev, 0.0f) / (float)rows;
+            prev = std::max(prev, t);
+        }
+    }
     return BVHT_OK;
 }
 

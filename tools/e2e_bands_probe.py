@@ -1,0 +1,28 @@
+import os, sys, time
+sys.path.insert(0, "/root/repo")
+import numpy as np
+from bvhtracer_b200 import examples, host
+anim = examples.GridAnimation()
+scene, models = host.build_scene(examples.sixteen_armadillos(0))
+r = host.Renderer(flags=2)
+eng = r.engine()
+w, h = 3840, 2160
+state = host.RendererState(host.depth_pipeline(), w, h, keep_hits=False)
+for _ in range(8):
+    anim.update()
+for bands in sys.argv[1:]:
+    os.environ["BVHT_BANDS"] = bands
+    a2 = examples.GridAnimation()
+    for _ in range(8): a2.update()
+    ts, dev = [], []
+    for f in range(24):
+        a2.update()
+        for i, o in enumerate(a2.objects()):
+            scene.set_transform(i, host.object_transform(o))
+        scene.rebuild()
+        eng.sync()
+        t0 = time.perf_counter()
+        r.render(state, scene)
+        ts.append(time.perf_counter() - t0)
+        dev.append(r.stats()["last_trace_ms"])
+    print(f"bands={bands:3s} render() wall median {np.median(ts[4:])*1e3:.3f} ms  min {min(ts[4:])*1e3:.3f}   device ev_a..ev_b median {np.median(dev[4:]):.3f} ms")
