@@ -7,7 +7,8 @@ scene, models = host.build_scene(examples.sixteen_armadillos(0))
 r = host.Renderer(flags=2)
 eng = r.engine()
 w, h = 3840, 2160
-state = host.RendererState(host.depth_pipeline(), w, h, keep_hits=False)
+keep_hits = os.environ.get("PROBE_KEEP_HITS") == "1"
+state = host.RendererState(host.depth_pipeline(), w, h, keep_hits=keep_hits)
 for _ in range(8):
     anim.update()
 for bands in sys.argv[1:]:
