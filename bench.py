@@ -12,8 +12,11 @@ One STEP = one animation frame: every primary ray of the frame traced to its clo
            (CudaPathTracer::evaluate: per-frame TLAS/instance upload from pinned memory + trace + on-device
            accumulator/pixel shader + frame buffer copied back to pinned host memory), timed with CUDA events.
 Multi-GPU (torchrun, one rank per GPU): the scene is replicated, tile rows are interleaved across ranks, every
-rank stores its pixels straight into rank 0's frame buffer over NVLink P2P (CUDA IPC mapping), no collective
-in the data path.  Scaling is WEAK: the frame grows to 3840 x (2160 * N) so per-GPU work is constant.
+rank stores its pixels (Rgba<u8>, the example's Depth accumulator + shader fused into the trace kernel) straight
+into rank 0's frame buffer over NVLink P2P (CUDA IPC mapping), no collective in the data path; the 16-byte hit
+records of a rank's rows stay in that rank's HBM, as at N = 1.  `--gather hits` assembles the 16-byte records on
+rank 0 instead (at N = 8 that saturates rank 0's NVLink ingress: 0.93 GB per step).  Scaling is WEAK: the frame
+grows to 3840 x (2160 * N) so per-GPU work is constant.
 `--impl reference` times the CPU oracle (the C restatement of the reference's Rust path; the reference itself
 cannot be compiled here: no cargo/rustc) with all host threads on a bounded sample of the same frames.
 """
@@ -224,18 +227,29 @@ def run_ours(args, rank, local_rank, world):
             scene.set_transform(i, host.object_transform(o))
         scene.rebuild()
 
-    # ---- resident output: the full frame of hit records lives in rank 0's HBM; peers map it (NVLink P2P)
-    if rank == 0:
-        d_hits = eng.device_alloc(npix * 16)
-        handle = eng.ipc_export(d_hits) if world > 1 else None
+    # ---- resident output.  N = 1: the frame of 16-byte hit records in HBM.  N > 1, --gather frame (default): the FRAME BUFFER
+    # (Rgba<u8>, DepthAccumulator + DepthMappingShader fused into the trace kernel) lives in rank 0's HBM, peers map it and
+    # store into it over NVLink P2P; the hit records of a rank's tile rows stay in that rank's HBM.  --gather hits: the 16-byte
+    # records themselves are gathered on rank 0 (at N = 8 that is 0.93 GB per 1.3 ms step into one GPU: NVLink-ingress bound).
+    gather_frame = world > 1 and args.gather == "frame"
+    d_frame = None
+    if gather_frame:
+        d_hits = eng.device_alloc(npix * 16)             # local: only this rank's tile rows are ever written
+        shared = eng.device_alloc(npix * 4) if rank == 0 else None
+    else:
+        shared = eng.device_alloc(npix * 16) if rank == 0 else None
     if world > 1:
         hb = torch.zeros(64, dtype=torch.uint8, device="cuda")
         if rank == 0:
-            hb.copy_(torch.frombuffer(bytearray(handle), dtype=torch.uint8))
+            hb.copy_(torch.frombuffer(bytearray(eng.ipc_export(shared)), dtype=torch.uint8))
         dist.broadcast(hb, 0)
         if rank != 0:
-            d_hits = eng.ipc_open(bytes(hb.cpu().numpy().tobytes()))
+            shared = eng.ipc_open(bytes(hb.cpu().numpy().tobytes()))
         eng.set_shard(rank, world)
+    if gather_frame:
+        d_frame = shared
+    else:
+        d_hits = shared
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
 
     def barrier():
@@ -249,7 +263,7 @@ def run_ours(args, rank, local_rank, world):
         flush.zero_()                                    # L2 flush between timed iterations
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        eng.render_frame_device(cam, width, height, None, tile, None, None, d_hits)
+        eng.render_frame_device(cam, width, height, shade if gather_frame else None, tile, None, d_frame, d_hits)
         e1.record(stream)
         return e0, e1
 
@@ -282,6 +296,23 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(t_resident, op=dist.ReduceOp.MAX)
     total_ms = float(t_resident.item())
     kernel_ms_local = float(np.mean(ms))
+
+    # the frame assembled in rank 0's HBM by all ranks (last timed frame) must equal the same frame rendered by rank 0 alone
+    gathered_ok = None
+    if gather_frame:
+        barrier()
+        if rank == 0:
+            got = eng.memcpy_d2h(np.zeros(npix, "<u4"), d_frame)
+            eng.set_shard(0, 1)
+            d_single = eng.device_alloc(npix * 4)
+            eng.render_frame_device(cam, width, height, shade, tile, None, d_single, None)
+            eng.sync()
+            single = eng.memcpy_d2h(np.zeros(npix, "<u4"), d_single)
+            eng.device_free(d_single)
+            eng.set_shard(rank, world)
+            gathered_ok = bool(np.array_equal(single, got))
+            del got, single
+        barrier()
 
     # ---- timed: end to end through Renderer::render (N = 1) / sharded render + rank-0 read-back (N > 1)
     e2e = None
@@ -446,11 +477,15 @@ def run_ours(args, rank, local_rank, world):
                        "frames": f"{args.warmup + 1}..{args.warmup + args.steps}", "instances": 16, "triangles_per_blas": 30001,
                        "l2": "flushed between timed iterations (256 MiB memset outside the per-step CUDA-event intervals)",
                        "timing": "sum over steps of CUDA-event intervals around the trace launch on the launching stream, max over ranks",
-                       "sharding": "tile rows interleaved over ranks, P2P stores into rank 0's buffer" if world > 1 else "single GPU",
+                       "sharding": ("single GPU" if world == 1 else
+                                    "tile rows interleaved over ranks; the Rgba<u8> frame buffer is assembled in rank 0's HBM by P2P stores over NVLink, "
+                                    "the 16-byte hit records of a rank's rows stay in its own HBM" if gather_frame else
+                                    "tile rows interleaved over ranks; the 16-byte hit records are assembled in rank 0's HBM by P2P stores over NVLink"),
                        "parity": "strict modes are bit-identical to the CPU oracle (tests/test_gpu_parity.py)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "frame_checksum": frame_checksum, "wall_s_resident_loop": wall_resident,
             "sharded_frame_equals_single_gpu": (sharded_ok if world > 1 else None),
+            "gathered_device_frame_equals_single_gpu": gathered_ok,
         }
     if world > 1:
         barrier()
@@ -463,7 +498,7 @@ def run_ours(args, rank, local_rank, world):
         except Exception:
             pass
         if rank != 0:
-            eng.ipc_close(d_hits)
+            eng.ipc_close(shared)
         barrier()
         dist.destroy_process_group()
     if rank == 0:
@@ -482,6 +517,8 @@ def main():
     ap.add_argument("--cpu-fraction", type=float, default=0.05, help="fraction of tile rows the CPU oracle renders per frame")
     ap.add_argument("--cpu-baseline-fraction", type=float, default=0.5, help="fraction of tile rows of ONE frame for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="frame", choices=["frame", "hits"],
+                    help="N > 1: what is assembled on rank 0 over NVLink P2P (frame = Rgba<u8> frame buffer, hits = the 16-byte records)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
