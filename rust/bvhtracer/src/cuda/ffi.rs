@@ -20,7 +20,7 @@ pub enum BvhtCtx {}
 pub struct BvhtBvhNode { pub aabb_min: [f32; 3], pub aabb_max: [f32; 3], pub prim_count: u32, pub left_first: u32 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct BvhtTlasNode { pub aabb_min: [f32; 3], pub aabb_max: [f32; 3], pub left_right: u32, pub blas: u32 }
-#[repr(C)] #[derive(Clone, Copy)]
+#[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct BvhtInstance { pub transform_inv: [f32; 16], pub blas_id: u32 }
 #[repr(C)] #[derive(Clone, Copy)]
 pub struct BvhtCamera { pub top_left_eye: [f32; 3], pub top_right_eye: [f32; 3], pub bottom_left_eye: [f32; 3], pub view_matrix_inv: [f32; 16] }
@@ -71,6 +71,11 @@ extern "C" {
     pub fn bvht_blas_refit(ctx: *mut BvhtCtx, id: u32) -> c_int;
     pub fn bvht_blas_read_nodes(ctx: *mut BvhtCtx, id: u32, out: *mut BvhtBvhNode, max_nodes: u32) -> c_int;
     pub fn bvht_tlas_set(ctx: *mut BvhtCtx, nodes: *const BvhtTlasNode, nodes_used: u32, inst: *const BvhtInstance, n_inst: u32) -> c_int;
+    /// `for o in objects { o.set_transform(..) }; tlas.rebuild(objects)` computed on the device (column-major `Transform3` matrices).
+    pub fn bvht_scene_set_transforms(ctx: *mut BvhtCtx, transforms: *const f32, blas_ids: *const u32, n_inst: u32) -> c_int;
+    /// The TLAS / cached inverses / world bounds the device computed, in the reference's layouts (any output may be null).
+    pub fn bvht_tlas_read(ctx: *mut BvhtCtx, nodes_out: *mut BvhtTlasNode, max_nodes: u32, nodes_used_out: *mut u32,
+                          inst_out: *mut BvhtInstance, bounds_out: *mut f32, max_inst: u32, n_inst_out: *mut u32) -> c_int;
     pub fn bvht_render_frame(ctx: *mut BvhtCtx, cam: *const BvhtCamera, width: u32, height: u32, tile: u32, region: BvhtRect,
                              shade: *const BvhtShade, frame_out: *mut u32, hits_out: *mut BvhtHit) -> c_int;
     pub fn bvht_trace_rays(ctx: *mut BvhtCtx, rays: *const BvhtRay, n: u64, out: *mut BvhtHit) -> c_int;

@@ -8,6 +8,7 @@ use crate::model::Model;
 use crate::query::{InstancePrimitiveIndex, Intersection, Ray, SurfaceInteraction};
 use crate::renderer::{Integrator, RendererState};
 use crate::scene::Scene;
+use crate::transform::Transform3;
 use cglinalg::{Matrix4x4, Vector3};
 use ffi::*;
 use std::cell::RefCell;
@@ -28,6 +29,7 @@ pub struct CudaPathTracer {
     shade: BvhtShade,
     tile: u32,
     uploaded: Vec<Uploaded>,
+    frame_state_resident: bool,         // update_transforms left this frame's TLAS / instances on the device
 }
 
 impl CudaPathTracer {
@@ -39,7 +41,7 @@ impl CudaPathTracer {
             // no CPU fallback by design: mirror the reference's unwrap() style
             panic!("bvht_create failed: {}", unsafe { CStr::from_ptr(bvht_status_string(rc)) }.to_string_lossy());
         }
-        Self { ctx, shade, tile: 8, uploaded: vec![] }
+        Self { ctx, shade, tile: 8, uploaded: vec![], frame_state_resident: false }
     }
 
     fn check(&self, rc: i32) {
@@ -85,7 +87,33 @@ impl CudaPathTracer {
         model.bvh_mut().import_bounds(&nodes);
     }
 
+    /// What the per-frame loop `for (o, t) in objects.zip(transforms) { o.set_transform(t) }; scene.rebuild()` of the animated
+    /// examples (sixteen_armadillos.rs:132-163) becomes when the scene is large: inverses, world boxes and the agglomerative
+    /// `Tlas::rebuild` (tlas.rs:179-250) run on the device, bit-identical to the host code, and the scene adopts the results
+    /// (`Scene::adopt_device_state`: cached inverse + bounds per object, `Tlas.nodes`).  Worth it from about 50 objects on.
+    pub fn update_transforms(&mut self, scene: &mut Scene, transforms: &[Transform3<f32>]) {
+        let n = scene.objects().len();
+        assert_eq!(n, transforms.len());
+        let mut mats = Vec::with_capacity(n * 16);
+        let mut ids = Vec::with_capacity(n);
+        for (object, t) in scene.objects().iter().zip(transforms.iter()) {
+            mats.extend_from_slice(&cols(&t.compute_matrix()));
+            ids.push(self.blas_id_for(&object.model().model()));
+        }
+        self.check(unsafe { bvht_scene_set_transforms(self.ctx, mats.as_ptr(), ids.as_ptr(), n as u32) });
+        let mut nodes = vec![BvhtTlasNode::default(); 2 * n.max(1)];
+        let mut inst = vec![BvhtInstance::default(); n];
+        let mut bounds = vec![0.0f32; 6 * n];
+        let (mut used, mut n_out) = (0u32, 0u32);
+        self.check(unsafe { bvht_tlas_read(self.ctx, nodes.as_mut_ptr(), nodes.len() as u32, &mut used, inst.as_mut_ptr(),
+                                           bounds.as_mut_ptr(), n as u32, &mut n_out) });
+        nodes.truncate(used as usize);
+        scene.adopt_device_state(transforms, &inst, &bounds, &nodes);
+        self.frame_state_resident = true;                       // evaluate() need not call bvht_tlas_set for this frame
+    }
+
     fn upload_frame_state(&mut self, scene: &Scene) {
+        if std::mem::take(&mut self.frame_state_resident) { return; }
         let mut inst = Vec::with_capacity(scene.objects().len());
         for object in scene.objects().iter() {
             let id = self.blas_id_for(&object.model().model());
