@@ -291,9 +291,17 @@ int build_accel_device(bvht_ctx* ctx, Blas& b, const LeafAccelConfig& cfg, bool&
     // Fast mode does not have to follow the reference's tree node by node (its bar is >= 99.99 % identical ids, t within
     // 1e-5): ONE sub-BVH over all triangles can replace the walk through the reference's overlapping leaves; ties in t
     // between different triangles then resolve to the lowest primitive index instead of the reference's visiting order.
-    // Measured on B200 (tools/quick_bench.py, 4K/8K): two_armadillos +14 %, sixteen_armadillos +5..9 %, trippy_teapots -5 %,
-    // big_ben_clock -25 % -- not a uniform win, so it is opt-in (BVHT_FAST_GLOBAL=1) and the default keeps one tree per leaf.
-    b.global_accel = (ctx->flags & BVHT_FLAG_FAST) != 0 && b.n_tris > cfg.max_sub_leaf && b.n_tris >= 2 && getenv("BVHT_FAST_GLOBAL");
+    // Measured on B200 (tools/quick_bench.py, 4K/8K, against one tree per reference leaf): two_armadillos +25 %,
+    // sixteen_armadillos +3..8 %, trippy_teapots +8 %, big_ben_clock -20 % -- the top levels of a global tree hold the
+    // model's largest triangles, and a few triangles hundreds of times larger than the typical one (Big Ben: max |e1||e2| =
+    // 115 x the mean; armadillo 6 x, teapot 3 x) drag their inflation through every box above them.  So: global tree when the
+    // largest edge product is within 32 x the mean.  BVHT_FAST_GLOBAL=0 / 1 forces it off / on.
+    ModelStats ms = compute_model_stats(b.h_tris.data(), b.n_tris);
+    {
+        bool want = ms.mean_kappa > 0.0 && ms.model_kappa <= 32.0 * ms.mean_kappa && b.n_tris >= 64;    // (a dozen triangles: brute force wins)
+        if (const char* e = getenv("BVHT_FAST_GLOBAL")) want = e[0] == '1';
+        b.global_accel = (ctx->flags & BVHT_FLAG_FAST) != 0 && b.n_tris > cfg.max_sub_leaf && b.n_tris >= 2 && want;
+    }
     if (b.global_accel) { roots.push_back(SubRoot{ 0u, b.n_tris, 0u }); n_sub = b.n_tris; }
     for (uint32_t ni = 0; ni < b.nodes_used && !b.global_accel; ++ni) {
         if (ni == 1) continue;
@@ -304,8 +312,7 @@ int build_accel_device(bvht_ctx* ctx, Blas& b, const LeafAccelConfig& cfg, bool&
         roots.push_back(SubRoot{ n.left_first, n.prim_count, (uint32_t)n_sub });
         n_sub += n.prim_count;
     }
-    if (roots.empty() || n_sub >= 0x0FFFFFFFull) return BVHT_OK;               // nothing to accelerate: the host path handles the empty case
-    ModelStats ms = compute_model_stats(b.h_tris.data(), b.n_tris);
+    if (roots.empty() || n_sub >= 0x0FFFFFFFull) { b.global_accel = false; return BVHT_OK; }      // nothing to accelerate: the host path handles the empty case
     b.radius = ms.radius; b.max_edge = ms.max_edge; b.model_kappa = ms.model_kappa; b.model_valid = ms.model_valid;
     memcpy(b.model_lo, ms.model_lo, 12); memcpy(b.model_hi, ms.model_hi, 12);
     set_useful_product(b, ms, cfg);
@@ -352,6 +359,7 @@ int build_and_upload_accel(bvht_ctx* ctx, Blas& b) {
         int rc = build_accel_device(ctx, b, cfg, done);
         if (rc || done) return rc;
     }
+    b.global_accel = false;                       // the host builder makes one tree per reference leaf
     LeafAccelHost acc;
     if (!build_leaf_accel(b.h_tris.data(), b.n_tris, b.h_nodes.data(), b.nodes_used, cfg, acc))
         return fail(ctx, BVHT_ERR_MALFORMED_BVH, "leaf accelerator build failed");

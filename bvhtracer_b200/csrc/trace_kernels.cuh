@@ -147,6 +147,53 @@ __device__ __forceinline__ bool slab_test_ch(const float4 c, const float4 h, con
 //  mt_finish  is the rest of Triangle::intersect verbatim (f, u, the u test again, q, v, t, thresholds).
 struct MtPartial { float nx, ny, nz, area, sx, sy, sz, X; };
 
+#ifdef BVHT_FAST_MODE
+// FAST build.  The filter runs with FMA contraction (that is the mode's speed-up on the 98 % of tests that end here) and, since
+// its inputs are then no longer the reference's values, with WIDENED thresholds: it only rejects what is outside by a margin
+// (|area| < 0.99e-4, u < -1e-4, u > 1 + 1e-4).  What passes is evaluated by mt_finish in the reference's arithmetic
+// (round-to-nearest intrinsics, never contracted), thresholds included -- so acceptance, (t, u, v) and every comparison
+// between candidates are the strict build's.  Ids can differ from the reference only where contraction moves u by more
+// than the margin (|area| tiny against its terms) or, with one sub-BVH per model, where two triangles tie exactly in t.
+__device__ __forceinline__ bool mt_filter(const float4 v0, const float4 e1, const float4 e2, const RayM& r, MtPartial& p) {
+    float nx = r.dy * e2.z - r.dz * e2.y;
+    float ny = r.dz * e2.x - r.dx * e2.z;
+    float nz = r.dx * e2.y - r.dy * e2.x;
+    float area = (e1.x * nx + e1.y * ny) + e1.z * nz;
+    p.sx = __fsub_rn(r.ox, v0.x); p.sy = __fsub_rn(r.oy, v0.y); p.sz = __fsub_rn(r.oz, v0.z);
+    float X = (p.sx * nx + p.sy * ny) + p.sz * nz;
+    float a = fabsf(area), x = fabsf(X);
+    bool opposite = (__float_as_int(area) ^ __float_as_int(X)) < 0;
+    bool rej_area = a < 0.000099f;
+    bool rej_neg = opposite & (x > a * 0.0001f);
+    bool rej_big = (!opposite) & (x > a * 1.0001f);
+    return !(rej_area | rej_neg | rej_big);
+}
+
+__device__ __forceinline__ bool mt_finish(const float4 e1, const float4 e2, const RayM& r, const MtPartial& p, float entry_t,
+                                          float& t_out, float& u_out, float& v_out) {
+    // geometry/triangle.rs:41-72 verbatim, one IEEE operation per source operation
+    const float threshold = 0.0001f;
+    float nx = __fsub_rn(__fmul_rn(r.dy, e2.z), __fmul_rn(r.dz, e2.y));
+    float ny = __fsub_rn(__fmul_rn(r.dz, e2.x), __fmul_rn(r.dx, e2.z));
+    float nz = __fsub_rn(__fmul_rn(r.dx, e2.y), __fmul_rn(r.dy, e2.x));
+    float area = __fadd_rn(__fadd_rn(__fmul_rn(e1.x, nx), __fmul_rn(e1.y, ny)), __fmul_rn(e1.z, nz));
+    if (fabsf(area) < threshold) return false;
+    float f = __fdiv_rn(1.0f, area);
+    float u = __fmul_rn(f, __fadd_rn(__fadd_rn(__fmul_rn(p.sx, nx), __fmul_rn(p.sy, ny)), __fmul_rn(p.sz, nz)));
+    if (u < 0.0f || u > 1.0f) return false;
+    float qx = __fsub_rn(__fmul_rn(p.sy, e1.z), __fmul_rn(p.sz, e1.y));
+    float qy = __fsub_rn(__fmul_rn(p.sz, e1.x), __fmul_rn(p.sx, e1.z));
+    float qz = __fsub_rn(__fmul_rn(p.sx, e1.y), __fmul_rn(p.sy, e1.x));
+    float v = __fmul_rn(f, __fadd_rn(__fadd_rn(__fmul_rn(r.dx, qx), __fmul_rn(r.dy, qy)), __fmul_rn(r.dz, qz)));
+    if (v < 0.0f || __fadd_rn(u, v) > 1.0f) return false;
+    float t = __fmul_rn(f, __fadd_rn(__fadd_rn(__fmul_rn(e2.x, qx), __fmul_rn(e2.y, qy)), __fmul_rn(e2.z, qz)));
+    if (!(t > threshold)) return false;
+    t_out = fminf(entry_t, t);
+    u_out = u;
+    v_out = v;
+    return true;
+}
+#else
 __device__ __forceinline__ bool mt_filter(const float4 v0, const float4 e1, const float4 e2, const RayM& r, MtPartial& p) {
     p.nx = r.dy * e2.z - r.dz * e2.y;
     p.ny = r.dz * e2.x - r.dx * e2.z;
@@ -182,27 +229,7 @@ __device__ __forceinline__ bool mt_finish(const float4 e1, const float4 e2, cons
     return true;
 }
 
-#ifdef BVHT_FAST_MODE
-// Fast build only: (t, u, v) of the WINNING triangle re-evaluated with round-to-nearest intrinsics, which nvcc never
-// contracts into FMAs -- i.e. with the reference's arithmetic.  FMA contraction may pick a different winner in a
-// near-tie (allowed: >= 99.99 % identical ids), but for the triangle it reports, t/u/v are then the reference's.
-__device__ __forceinline__ void mt_exact_rn(const float4 v0, const float4 e1, const float4 e2, const RayM& r, float entry_t,
-                                            float& t, float& u, float& v) {
-    float nx = __fsub_rn(__fmul_rn(r.dy, e2.z), __fmul_rn(r.dz, e2.y));
-    float ny = __fsub_rn(__fmul_rn(r.dz, e2.x), __fmul_rn(r.dx, e2.z));
-    float nz = __fsub_rn(__fmul_rn(r.dx, e2.y), __fmul_rn(r.dy, e2.x));
-    float area = __fadd_rn(__fadd_rn(__fmul_rn(e1.x, nx), __fmul_rn(e1.y, ny)), __fmul_rn(e1.z, nz));
-    float f = __fdiv_rn(1.0f, area);
-    float sx = __fsub_rn(r.ox, v0.x), sy = __fsub_rn(r.oy, v0.y), sz = __fsub_rn(r.oz, v0.z);
-    float uu = __fmul_rn(f, __fadd_rn(__fadd_rn(__fmul_rn(sx, nx), __fmul_rn(sy, ny)), __fmul_rn(sz, nz)));
-    float qx = __fsub_rn(__fmul_rn(sy, e1.z), __fmul_rn(sz, e1.y));
-    float qy = __fsub_rn(__fmul_rn(sz, e1.x), __fmul_rn(sx, e1.z));
-    float qz = __fsub_rn(__fmul_rn(sx, e1.y), __fmul_rn(sy, e1.x));
-    float vv = __fmul_rn(f, __fadd_rn(__fadd_rn(__fmul_rn(r.dx, qx), __fmul_rn(r.dy, qy)), __fmul_rn(r.dz, qz)));
-    float tt = __fmul_rn(f, __fadd_rn(__fadd_rn(__fmul_rn(e2.x, qx), __fmul_rn(e2.y, qy)), __fmul_rn(e2.z, qz)));
-    if (isfinite(tt) && isfinite(uu) && isfinite(vv)) { t = fminf(entry_t, tt); u = uu; v = vv; }
-}
-#endif
+#endif   // BVHT_FAST_MODE (filter / finish)
 
 // Brute-force leaf: primitives base .. base+count ascending, strict '<' against the shrinking closest t
 // (bvh.rs:250-258).  Triangles are tested against the ENTRY ray.
@@ -310,12 +337,6 @@ __device__ __forceinline__ void blas_intersect(const BlasDesc& B, const RayM& r,
         // fast mode: one sub-BVH over the whole model (sub node 0), closest hit = lexicographic min (t, primitive index)
         st.add(4);
         leaf_accel(B, 0u, r, entry_t, best_t, best_u, best_v, best_prim, found, st);
-        if (found) {
-            const float4* tp = B.tri + 3 * (size_t)best_prim;
-            float t = best_t, u = best_u, v = best_v;
-            mt_exact_rn(ldg4(tp + 0), ldg4(tp + 1), ldg4(tp + 2), r, entry_t, t, u, v);
-            if (t < entry_t) { best_t = t; best_u = u; best_v = v; }
-        }
         return;
     }
 #endif
@@ -365,14 +386,6 @@ __device__ __forceinline__ void blas_intersect(const BlasDesc& B, const RayM& r,
             n1 = ldg4(B.nodes + 2 * (size_t)ni + 1);
         }
     }
-#ifdef BVHT_FAST_MODE
-    if (found) {
-        const float4* tp = B.tri + 3 * (size_t)best_prim;
-        float t = best_t, u = best_u, v = best_v;
-        mt_exact_rn(ldg4(tp + 0), ldg4(tp + 1), ldg4(tp + 2), r, entry_t, t, u, v);
-        if (t < entry_t) { best_t = t; best_u = u; best_v = v; }      // keep the strict '<' contract of the caller
-    }
-#endif
 }
 
 // scene/tlas.rs:123-177 + scene_object.rs:78-89.  World ray (ox..dz, recip), initial t = tmax.

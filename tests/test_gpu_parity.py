@@ -310,6 +310,16 @@ def test_fast_mode_tolerance(name, frame, size, flags):
     assert_fast(got, ref)
 
 
+@pytest.mark.parametrize("flags", [FLAG_FAST, FLAG_FAST | FLAG_LEAF_ACCEL], ids=["fast-brute", "fast-accel"])
+def test_fast_mode_on_exact_ties_cube_640(flags):
+    # The axis-aligned cube view puts whole pixel columns exactly on the diagonals shared by two triangles (u + v == 1 in exact
+    # arithmetic).  The fast build filters with FMA contraction but decides every candidate that survives the (widened) filter
+    # in the reference's arithmetic, so even here the records are the strict ones.
+    got, ref = render_both(examples.cube(), 640, 640, flags)
+    r = SB.compare_hits(got, ref)
+    assert r["id_mismatch"] <= 4 and r["max_rel_t"] <= 1e-6, r
+
+
 # ------------------------------------------------------------------------------------------ error behaviour
 def test_errors_are_codes_not_crashes():
     scene, cam = SB.oracle_scene(examples.cube())
