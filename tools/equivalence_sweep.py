@@ -11,9 +11,10 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
-from bvhtracer_b200 import Engine, FLAG_LEAF_ACCEL, FLAG_STRICT, _ffi, examples, host
+from bvhtracer_b200 import Engine, FLAG_FAST, FLAG_LEAF_ACCEL, FLAG_STRICT, _ffi, examples, host
 
-quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
+quick = "quick" in sys.argv[1:]
+fast = "fast" in sys.argv[1:]          # compare the FAST build (accel) against strict-brute instead: how many records differ at all
 rng = np.random.default_rng(2026)
 total = mism = 0
 t_start = time.time()
@@ -55,7 +56,7 @@ def update_tlas(eng, scene, ids):
     eng.tlas_set(tl[:used], used, inst)
 
 
-with Engine(flags=FLAG_STRICT) as brute, Engine(flags=FLAG_STRICT | FLAG_LEAF_ACCEL) as accel:
+with Engine(flags=FLAG_STRICT) as brute, Engine(flags=(FLAG_FAST if fast else FLAG_STRICT) | FLAG_LEAF_ACCEL) as accel:
     # 1. animated frames of sixteen_armadillos and trippy_teapots at 4K / 1080p
     for name, size, frames in (("sixteen_armadillos", (3840, 2160), 12 if quick else 60), ("trippy_teapots", (3840, 2160), 6 if quick else 30)):
         anim = examples.GridAnimation()
@@ -95,5 +96,5 @@ with Engine(flags=FLAG_STRICT) as brute, Engine(flags=FLAG_STRICT | FLAG_LEAF_AC
             eng.blas_refit(bid)
         compare(f"big_ben frame {f}", brute, accel, scene.camera(), 3840, 2160)
     print(f"big_ben animated done, rays so far {total:,}, mismatches {mism}", flush=True)
-print(f"TOTAL rays {total:,}  mismatching records {mism}  c_mt={os.environ.get('BVHT_C_MT', 'shipped value (leaf_accel.hpp)')}  "
+print(f"{'FAST-accel' if fast else 'strict-accel'} vs strict-brute: TOTAL rays {total:,}  mismatching records {mism}  c_mt={os.environ.get('BVHT_C_MT', 'shipped value (leaf_accel.hpp)')}  "
       f"wall {time.time() - t_start:.0f} s")
