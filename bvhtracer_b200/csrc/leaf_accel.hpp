@@ -25,7 +25,7 @@ namespace bvht {
 struct LeafAccelHost {
     // RAW (un-inflated) sub nodes, 16 floats each: c0.lo.xyz, kappa0 | c0.hi.xyz, ref0 | c1.lo.xyz, kappa1 | c1.hi.xyz, ref1
     // kappa = max |e1| |e2| over the child's triangles.  The device inflates them for the current ray limits
-    // (inflate_sub_nodes kernel), see accel_deltas().
+    // (bake_sub_nodes_kernel, bottom-up from the triangles, per-triangle inflation), see accel_deltas().
     std::vector<float>    sub_raw;
     std::vector<uint32_t> sub_parent;     // per sub node: (parent << 1) | child slot, 0xFFFFFFFF for the root of a leaf's tree
     std::vector<uint32_t> order;          // sub position -> reference primitive index

@@ -111,7 +111,7 @@ __device__ __forceinline__ bool slab_test_sub(const float4 lo, const float4 hi, 
     return (t_max >= t_min) && (t_min <= tcl) && (t_max >= 0.0f);
 }
 
-// The same test on a child box stored as CENTRE + HALF EXTENT (device_types.cuh BVHT_SUB_CH; inflate_sub_nodes_kernel
+// The same test on a child box stored as CENTRE + HALF EXTENT (device_types.cuh BVHT_SUB_CH; bake_sub_nodes_kernel
 // writes that form): t_centre = c * f - o * f, t_near/far = t_centre -/+ h * |f|.  No per-axis min/max: the work moves
 // from the ALU pipe (FMNMX, the busiest pipe of this kernel) to the FMA pipes.  Two more roundings than the lo/hi form
 // (eps * |t_centre| and eps * |h f|), which the bake adds to h (upload_kernels.cu).
