@@ -1419,6 +1419,25 @@ static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvh
         }
     }
     p.work_counter = (unsigned int*)ctx->work_counter.p + 2 * slot;
+    p.n_origin = 0;
+    if (!ctx->h_inst.empty() && ctx->h_inst.size() <= 32 && !getenv("BVHT_NO_HOST_ORIGIN")) {
+        // BVHT_MV4 of trace_kernels.cuh, operation for operation (this file is compiled with -ffp-contract=off)
+        auto mv4 = [](float c0, float c1, float c2, float c3, float x, float y, float z, float w) -> float {
+            volatile float a = c0 * x, b = c1 * y, c = c2 * z, d = c3 * w;
+            volatile float s1 = a + b; volatile float s2 = s1 + c; volatile float s3 = s2 + d;
+            return s3;
+        };
+        const float* M = p.cam.vinv;
+        const float wx = mv4(M[0], M[4], M[8], M[12], 0.0f, 0.0f, 0.0f, 1.0f);
+        const float wy = mv4(M[1], M[5], M[9], M[13], 0.0f, 0.0f, 0.0f, 1.0f);
+        const float wz = mv4(M[2], M[6], M[10], M[14], 0.0f, 0.0f, 0.0f, 1.0f);
+        for (size_t i = 0; i < ctx->h_inst.size(); ++i) {
+            const float* c = ctx->h_inst[i].transform_inv;       // column-major: c0 = c[0..3], c1 = c[4..7], c2 = c[8..11], c3 = c[12..15]
+            p.inst_origin[i] = make_float4(mv4(c[0], c[4], c[8], c[12], wx, wy, wz, 1.0f), mv4(c[1], c[5], c[9], c[13], wx, wy, wz, 1.0f),
+                                           mv4(c[2], c[6], c[10], c[14], wx, wy, wz, 1.0f), 0.0f);
+        }
+        p.n_origin = (uint32_t)ctx->h_inst.size();
+    }
     p.n_rect = 0;
     if (accel_on(ctx)) { uint32_t nr = 0; if (compute_instance_rects(ctx, camera, width, height, p.inst_rect, nr)) p.n_rect = nr; }
     // chain skipping pays from three instances on (measured: pure overhead for 1-2 instances)

@@ -88,6 +88,10 @@ struct PrimaryParams {
     unsigned long long* stats;           // debug counters (stats build only)
     // accel only: conservative screen-space rectangle (pixels, inclusive) of each instance's tight box for THIS camera;
     // n_rect == 0 disables the tile-level candidate masks
+    // the camera origin in every instance's model space (primary rays share it): computed on the host with the kernel's own
+    // operation order (BVHT_MV4, no contraction), so the kernel need not transform the origin at every instance entry
+    uint32_t  n_origin;                  // 0 = not available (more than 32 instances)
+    float4    inst_origin[32];
     uint32_t  n_rect;
     uint32_t  skip_rounds;               // pointer-jumping rounds: ceil(log2(depth of the TLAS))
     uint32_t  n_tlas_nodes;              // > 0 (and <= 64) with n_rect: chain-skipping TLAS walk (trace_kernels.cuh build_tlas_skip)

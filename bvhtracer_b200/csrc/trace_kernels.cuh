@@ -402,7 +402,7 @@ __device__ __forceinline__ void blas_intersect(const BlasDesc& B, const RayM& r,
 // last one is hit": one slab test replaces the chain.  Rays with a non-finite reciprocal take the plain walk.
 template <bool ACCEL, bool PRUNE = false>
 __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM& w, float tmax, uint32_t cand, Stat& st,
-                                                  const uint8_t* skip = nullptr) {
+                                                  const uint8_t* skip = nullptr, const float4* origins = nullptr) {
     // cand (ACCEL): bit i clear = instance i cannot be hit by this ray (tile-level screen rectangles); all ones = unknown
     st.add(0);
     HitRec best;
@@ -471,9 +471,14 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
             RayM r;
             // transform.rs:219-234 over cglinalg Matrix4x4 * Vector4: ((c0*x + c1*y) + c2*z) + c3*w
             // (round-to-nearest intrinsics: never contracted, so the model-space ray is the reference's in BOTH builds)
-            r.ox = BVHT_MV4(c0.x, c1.x, c2.x, c3.x, w.ox, w.oy, w.oz, 1.0f);
-            r.oy = BVHT_MV4(c0.y, c1.y, c2.y, c3.y, w.ox, w.oy, w.oz, 1.0f);
-            r.oz = BVHT_MV4(c0.z, c1.z, c2.z, c3.z, w.ox, w.oy, w.oz, 1.0f);
+            if (origins) {                    // primary rays: the shared origin was transformed once per instance on the host
+                const float4 oo = origins[inst];
+                r.ox = oo.x; r.oy = oo.y; r.oz = oo.z;
+            } else {
+                r.ox = BVHT_MV4(c0.x, c1.x, c2.x, c3.x, w.ox, w.oy, w.oz, 1.0f);
+                r.oy = BVHT_MV4(c0.y, c1.y, c2.y, c3.y, w.ox, w.oy, w.oz, 1.0f);
+                r.oz = BVHT_MV4(c0.z, c1.z, c2.z, c3.z, w.ox, w.oy, w.oz, 1.0f);
+            }
             r.dx = BVHT_MV4(c0.x, c1.x, c2.x, c3.x, w.dx, w.dy, w.dz, 0.0f);
             r.dy = BVHT_MV4(c0.y, c1.y, c2.y, c3.y, w.dx, w.dy, w.dz, 0.0f);
             r.dz = BVHT_MV4(c0.z, c1.z, c2.z, c3.z, w.dx, w.dy, w.dz, 0.0f);
@@ -791,7 +796,7 @@ trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
                 st.add(0);
             } else {
                 RayM w = primary_ray(P.cam, px, py, P.width, P.height);
-                h = scene_intersect<ACCEL, PRUNE>(P.scene, w, FLT_MAX, cand, st, skip);
+                h = scene_intersect<ACCEL, PRUNE>(P.scene, w, FLT_MAX, cand, st, skip, P.n_origin ? P.inst_origin : nullptr);
             }
             if (P.out) {
                 uint4 o;
