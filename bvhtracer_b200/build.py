@@ -31,6 +31,7 @@ UNITS = [
     ("upload_kernels.cu", STRICT),
     ("refit_kernels.cu", STRICT),
     ("scene_kernels.cu", STRICT),
+    ("cover_kernels.cu", STRICT),
     ("build_kernels.cu", STRICT),
     ("bvht_api.cu", STRICT),
     ("leaf_accel.cpp", []),

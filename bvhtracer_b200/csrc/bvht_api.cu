@@ -55,6 +55,7 @@ struct Blas {
     uint32_t n_sub = 0, n_sub_nodes = 0;
     // current bake: model-space ray limits and the whole-model tight box inflated for them
     float d_max = 0.0f, o_max = 0.0f;
+    float bake_scale = 0.0f, bake_abs = 0.0f;     // delta of a triangle's box in the current bake: scale * |e1||e2| + abs
     float tight_lo[3] = { 0, 0, 0 }, tight_hi[3] = { 0, 0, 0 };
     bool tight_valid = false;
     // what the bake is computed from
@@ -90,6 +91,15 @@ struct bvht_ctx {
     std::vector<float> inst_tight;                    // 6 floats per instance (world lo/hi) or lo > hi when unusable
     double bake_center[3] = { 0.0, 0.0, 0.0 };        // camera origin the tight TLAS boxes' origin limit is centred on
     DevBuf work_counter;                              // slot i: [2i] = K1's work cursor, [2i+1] = length of K0's block list
+    DevBuf cover, cover_aux;                          // per-triangle block coverage of the current frame (cover_kernels.cu); aux: full word, big count, big list
+    bool cover_ready = false;                         // valid for the launches of the current frame only
+    // The raster pass costs 35-160 us and saves more or less than that depending on the scene (sixteen_armadillos 4K: -10..14 %
+    // of the frame; trippy_teapots, big_ben_clock: +6..10 %), so it is decided by measurement: the frame time (ev_a..ev_b) of
+    // frames traced with and without it is tracked per scene signature, the faster way is used, the other one re-probed every
+    // 64 frames.  BVHT_COVER=0 / 1 forces it off / on.
+    struct CoverPolicy { uint32_t key[4] = { 0 }; float ms[2] = { -1.0f, -1.0f }; uint32_t seen[2] = { 0, 0 }; uint32_t frames = 0; int last_mode = -1; bool pending = false; } cover_policy;
+    uint32_t cover_ntx = 0;
+    std::vector<float> inst_d2max;                    // per instance: largest |d_w|^2 its tight box / baked boxes are valid for (< 0: unusable)
     DevBuf work_list;                                 // K0's list of blocks that see an instance, one u32 per block of the frame
     BuildWorkspace build_ws;                   // K3 scratch (grow-only)
     DevBuf build_tris, build_perm;             // K3 input/output: triangles reordered in place + the permutation
@@ -224,6 +234,7 @@ int bake_accel(bvht_ctx* ctx, Blas& b, double d_max, double o_max) {
                                   (float4*)b.sub_lohi.p, (float4*)b.sub_nodes.p, ctx->stream));
     if (b.n_sub_nodes) ctx->stats.kernel_launches += 1;
     b.d_max = (float)d_max; if ((double)b.d_max > d_max) b.d_max = std::nextafterf(b.d_max, 0.0f);
+    b.bake_scale = fs; b.bake_abs = fa;
     b.o_max = (float)o_max; if ((double)b.o_max > o_max) b.o_max = std::nextafterf(b.o_max, 0.0f);
     b.tight_valid = b.model_valid;
     if (b.model_valid) {
@@ -433,6 +444,7 @@ int refresh_blas_desc(bvht_ctx* ctx) {
         o.leaf_sub_root = b.global_accel ? nullptr : (const uint32_t*)b.leaf_sub_root.p;   // null = "sub node 0 is the model's root"
         o.n_tris = b.n_tris; o.nodes_used = b.nodes_used;
         o.accel_d_max = b.d_max; o.accel_o_max = b.o_max;
+        o.bake_scale = b.bake_scale; o.bake_abs = b.bake_abs;
     }
     int rc = ensure(ctx, ctx->blas_desc, d.size() * sizeof(BlasDesc));
     if (rc) return rc;
@@ -474,8 +486,11 @@ TightBox instance_tight_box(const Blas& b, const float* inv_f, const double cent
     if (!b.tight_valid) return t;
     double inv[16], fwd[16];
     for (int i = 0; i < 16; ++i) { inv[i] = inv_f[i]; if (!std::isfinite(inv[i])) return t; }
-    // affine only: bottom row must be (0, 0, 0, 1)
-    if (inv[3] != 0.0 || inv[7] != 0.0 || inv[11] != 0.0 || inv[15] != 1.0) return t;
+    // Only rows 0..2 of the inverse ever reach a ray: Transform3::transform_point / transform_vector are Matrix4x4 * Vector4
+    // followed by contract(), without a divide (transform.rs:219-234), and the kernel computes exactly those three rows.  The
+    // f32 inverse of a ROTATED transform has a bottom row that is only approximately (0, 0, 0, 1) -- rejecting it here left
+    // every rotating instance of sixteen_armadillos without a tight box, i.e. entered by every ray of the frame.
+    inv[3] = 0.0; inv[7] = 0.0; inv[11] = 0.0; inv[15] = 1.0;
     if (!invert_d(inv, fwd)) return t;
     double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 }, maxabs = 0.0;
     for (int i = 0; i < 8; ++i) {
@@ -548,6 +563,8 @@ int recompute_tlas_tight(bvht_ctx* ctx) {
         memcpy(f + 0, node_t[i].lo, 12); f[3] = node_t[i].d2_max;
         memcpy(f + 4, node_t[i].hi, 12); f[7] = node_t[i].o2_max;
     }
+    ctx->inst_d2max.assign(n_inst, -1.0f);
+    for (uint32_t i = 0; i < n_inst; ++i) if (inst_t[i].d2_max >= 0.0f && inst_t[i].o2_max >= 0.0f) ctx->inst_d2max[i] = inst_t[i].d2_max;
     ctx->inst_tight.assign((size_t)n_inst * 6, 0.0f);
     for (uint32_t i = 0; i < n_inst; ++i) {
         float* f = &ctx->inst_tight[(size_t)i * 6];
@@ -604,14 +621,17 @@ bool compute_instance_rects(const bvht_ctx* ctx, const bvht_camera* cam, uint32_
     if (ex == 0.0 || ey == 0.0) return false;
     double vinv[16], view[16];
     for (int i = 0; i < 16; ++i) { vinv[i] = cam->view_matrix_inv[i]; if (!std::isfinite(vinv[i])) return false; }
-    if (vinv[3] != 0.0 || vinv[7] != 0.0 || vinv[11] != 0.0 || vinv[15] != 1.0) return false;
+    vinv[3] = 0.0; vinv[7] = 0.0; vinv[11] = 0.0; vinv[15] = 1.0;      // rows 0..2 are all that reaches a ray (camera.rs:1003-1008: no divide)
     if (!invert_d(vinv, view)) return false;
     double near_ = -(double)tl[2];
+    // primary rays are unit eye directions through view_inv: |d_w| <= sigma_max; a tight box baked for shorter directions is not valid for them
+    const double dw_cam = sigma_max_3x3(vinv) * (1.0 + 1e-4);
     for (uint32_t i = 0; i < n_inst; ++i) {
         const float* b = &ctx->inst_tight[(size_t)i * 6];
         int4 full = make_int4(0, 0, (int)width - 1, (int)height - 1);
         rects[i] = full;
         if (b[0] > b[3]) continue;                                    // unusable tight box
+        if (ctx->inst_d2max.size() == n_inst && !(dw_cam * dw_cam <= (double)ctx->inst_d2max[i])) continue;
         double umin = 1e300, umax = -1e300, vmin = 1e300, vmax = -1e300;
         bool behind = false;
         double scale = 0.0;
@@ -951,7 +971,7 @@ void bvht_destroy(bvht_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (Blas& b : ctx->blas) free_blas(b);
-    for (DevBuf* d : { &ctx->blas_desc, &ctx->tlas, &ctx->inst_cols, &ctx->inst_blas, &ctx->work_counter, &ctx->work_list, &ctx->out_buf, &ctx->rays_buf,
+    for (DevBuf* d : { &ctx->blas_desc, &ctx->tlas, &ctx->inst_cols, &ctx->inst_blas, &ctx->work_counter, &ctx->work_list, &ctx->cover, &ctx->cover_aux, &ctx->out_buf, &ctx->rays_buf,
                        &ctx->rgba_buf, &ctx->tlas_tight, &ctx->tlas_mask, &ctx->scene_in, &ctx->scene_bounds })
         release(*d);
     for (cudaStream_t st : { ctx->aux[0], ctx->aux[1], ctx->copy_stream }) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
@@ -1364,6 +1384,130 @@ int bvht_tlas_read(bvht_ctx* ctx, bvht_tlas_node* nodes_out, uint32_t max_nodes,
     return BVHT_OK;
 }
 
+// Before a frame's ev_a is recorded: the previous frame's time (ev_a..ev_b, complete if anything was synchronised since) goes
+// to the way that frame was traced -- with or without the coverage pass (bvht_ctx::CoverPolicy).
+static void cover_policy_observe(bvht_ctx* ctx) {
+    bvht_ctx::CoverPolicy& pol = ctx->cover_policy;
+    if (pol.pending && ctx->trace_timed && pol.last_mode >= 0 && cudaEventQuery(ctx->ev_b) == cudaSuccess) {
+        float t = 0.0f;
+        if (cudaEventElapsedTime(&t, ctx->ev_a, ctx->ev_b) == cudaSuccess) {
+            // the first frame of either way pays for its allocations inside the interval: not a sample
+            if (pol.seen[pol.last_mode]++ > 0) pol.ms[pol.last_mode] = pol.ms[pol.last_mode] < 0.0f ? t : 0.5f * (pol.ms[pol.last_mode] + t);
+        }
+    }
+    cudaGetLastError();
+    pol.pending = false;
+}
+
+// Rasterise every instance's triangles onto the 8x4-pixel blocks of the frame (cover_kernels.cu).  Once per frame, on
+// `stream`, before the frame's trace launches; they pick the result up through ctx->cover_ready.
+static int prepare_cover(bvht_ctx* ctx, const bvht_camera* cam, uint32_t width, uint32_t height, uint32_t tile, cudaStream_t stream) {
+    ctx->cover_ready = false;
+    bvht_ctx::CoverPolicy& pol = ctx->cover_policy;
+    if (getenv("BVHT_NO_COVER") || !accel_on(ctx) || tile != 8) return BVHT_OK;
+    const uint32_t n_inst = (uint32_t)ctx->h_inst.size();
+    if (n_inst == 0 || n_inst > 32 || ctx->inst_tight.size() != (size_t)n_inst * 6 || ctx->inst_d2max.size() != n_inst) return BVHT_OK;
+    {
+        uint32_t tris = 0;
+        for (const bvht_instance& in : ctx->h_inst) tris += ctx->blas[in.blas_id].n_tris;
+        const uint32_t key[4] = { width, height, n_inst, tris };
+        if (memcmp(key, pol.key, sizeof key) != 0) { memcpy(pol.key, key, sizeof key); pol.ms[0] = pol.ms[1] = -1.0f; pol.seen[0] = pol.seen[1] = 0; pol.frames = 0; }
+        int mode;
+        if (const char* e = getenv("BVHT_COVER")) mode = e[0] == '1';
+        else if (pol.ms[0] < 0.0f) mode = 0;                              // first two frames: without (the first is not a sample)
+        else if (pol.ms[1] < 0.0f) mode = 1;                              // next two: with
+        else {
+            mode = pol.ms[1] < pol.ms[0];
+            if (pol.frames % 64 == 63) mode = !mode;                      // re-probe the other way now and then
+        }
+        pol.frames += 1;
+        pol.last_mode = mode;
+        pol.pending = true;
+        if (!mode) return BVHT_OK;
+    }
+    const float* tl = cam->top_left_eye; const float* tr = cam->top_right_eye; const float* bl = cam->bottom_left_eye;
+    if (!(tl[2] < 0.0f) || tr[2] != tl[2] || bl[2] != tl[2] || tr[1] != tl[1] || bl[0] != tl[0]) return BVHT_OK;
+    const double ex = (double)tr[0] - tl[0], ey = (double)bl[1] - tl[1];
+    if (ex == 0.0 || ey == 0.0) return BVHT_OK;
+    double vinv[16], view[16];
+    for (int i = 0; i < 16; ++i) { vinv[i] = cam->view_matrix_inv[i]; if (!std::isfinite(vinv[i])) return BVHT_OK; }
+    vinv[3] = 0.0; vinv[7] = 0.0; vinv[11] = 0.0; vinv[15] = 1.0;      // rows 0..2 are all that reaches a ray
+    if (!invert_d(vinv, view)) return BVHT_OK;
+    const double dw_cam = sigma_max_3x3(vinv) * (1.0 + 1e-4);
+    int rc = refresh_blas_desc(ctx);
+    if (rc) return rc;
+    CoverParams p;
+    memset(&p, 0, sizeof p);
+    uint32_t full_init = 0, total = 0;
+    double scale_max = 1.0;
+    for (uint32_t i = 0; i < n_inst; ++i) {
+        p.tri_offset[i] = total;
+        const bvht_instance& in = ctx->h_inst[i];
+        const Blas& b = ctx->blas[in.blas_id];
+        const float* tb = &ctx->inst_tight[(size_t)i * 6];
+        double inv[16], fwd[16];
+        bool ok = tb[0] <= tb[3] && dw_cam * dw_cam <= (double)ctx->inst_d2max[i] && b.alive && b.tri.p && b.bake_scale >= 0.0f && b.tight_valid;
+        for (int k = 0; k < 16 && ok; ++k) { inv[k] = in.transform_inv[k]; ok = std::isfinite(inv[k]); }
+        if (ok) { inv[3] = 0.0; inv[7] = 0.0; inv[11] = 0.0; inv[15] = 1.0; }      // rows 0..2 are all that reaches a ray
+        ok = ok && invert_d(inv, fwd);
+        if (!ok) { full_init |= 1u << i; continue; }                 // no valid bake for this camera: visible everywhere
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 4; ++c) {
+                double v = 0.0;
+                for (int k = 0; k < 4; ++k) v += view[k * 4 + r] * fwd[c * 4 + k];       // column-major: (view * fwd)(r, c)
+                p.mv[i][r * 4 + c] = (float)v;
+                scale_max = std::max(scale_max, std::fabs(v));
+            }
+        total += b.n_tris;
+    }
+    p.tri_offset[n_inst] = total;
+    const uint32_t ntx = (width + 7) / 8, nty = (height + 7) / 8;
+    const size_t words = (size_t)ntx * nty * 2;
+    if ((rc = ensure(ctx, ctx->cover, words * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->cover_aux, 16 + (size_t)std::max(total, 1u) * 16))) return rc;
+    CU(ctx, cudaMemsetAsync(ctx->cover.p, 0, words * 4, stream));
+    const uint32_t init[4] = { full_init, 0u, 0u, 0u };
+    CU(ctx, cudaMemcpyAsync(ctx->cover_aux.p, init, 16, cudaMemcpyHostToDevice, stream));       // pageable: staged before return
+    p.cover = (uint32_t*)ctx->cover.p;
+    p.full = (uint32_t*)ctx->cover_aux.p;
+    p.big_count = (uint32_t*)ctx->cover_aux.p + 1;
+    p.big_list = (int4*)((char*)ctx->cover_aux.p + 16);
+    p.big_cap = total;
+    p.blas = (const BlasDesc*)ctx->blas_desc.p;
+    p.inst_blas = (const uint32_t*)ctx->inst_blas.p;
+    p.n_inst = n_inst;
+    p.ntx = ntx; p.width = width; p.height = height;
+    p.tlx = tl[0]; p.tly = tl[1]; p.inv_ex = (float)(1.0 / ex); p.inv_ey = (float)(1.0 / ey); p.near_ = -tl[2];
+    p.z_eps = (float)(1e-4 * (1.0 + scale_max));
+    if (total) {
+        cudaError_t e = launch_raster_cover(p, stream);
+        if (e != cudaSuccess) return fail(ctx, BVHT_ERR_CUDA, "coverage raster launch failed: %s", cudaGetErrorString(e));
+        ctx->stats.kernel_launches += 2;
+    }
+    ctx->cover_ready = true;
+    ctx->cover_ntx = ntx;
+    if (getenv("BVHT_COVER_DEBUG")) {              // diagnostics: what the raster pass produced and what it cost
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaStreamSynchronize(stream);
+        cudaMemsetAsync(ctx->cover.p, 0, words * 4, stream);
+        cudaMemcpyAsync(ctx->cover_aux.p, init, 16, cudaMemcpyHostToDevice, stream);
+        cudaEventRecord(e0, stream);
+        if (total) launch_raster_cover(p, stream);
+        cudaEventRecord(e1, stream);
+        uint32_t aux[4] = { 0 };
+        cudaMemcpyAsync(aux, ctx->cover_aux.p, 16, cudaMemcpyDeviceToHost, stream);
+        std::vector<uint32_t> cv(words);
+        cudaMemcpyAsync(cv.data(), ctx->cover.p, words * 4, cudaMemcpyDeviceToHost, stream);
+        cudaStreamSynchronize(stream);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        size_t empty = 0; for (uint32_t w : cv) empty += (w | aux[0]) == 0;
+        fprintf(stderr, "[bvht cover] %ux%u: %u triangles, raster %.3f ms, full mask 0x%08x (host preset 0x%08x), big rects %u, empty blocks %.1f %%\n",
+                width, height, total, ms, aux[0], full_init, aux[1], 100.0 * (double)empty / (double)words);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    return BVHT_OK;
+}
+
 // One persistent launch of K1 over `region` on `stream`, using work counter slot `slot`.
 static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvht_camera* camera, uint32_t width, uint32_t height,
                                  uint32_t tile, bvht_rect region, const bvht_shade_params* shade, void* hits_device,
@@ -1444,6 +1588,9 @@ static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvh
     p.n_tlas_nodes = (p.n_rect >= 3 && ctx->tlas_nested && ctx->h_tlas.size() <= 64) ? (uint32_t)ctx->h_tlas.size() : 0u;
     p.skip_rounds = 0;
     while ((1u << p.skip_rounds) < ctx->tlas_depth) ++p.skip_rounds;
+    if (ctx->cover_ready && p.n_rect && tile == 8) {
+        p.cover = (const uint32_t*)ctx->cover.p; p.cover_full = (const uint32_t*)ctx->cover_aux.p; p.cover_ntx = ctx->cover_ntx;
+    }
     if (const char* lp = getenv("BVHT_SLICE_LOG_PTR")) p.stats = (unsigned long long*)strtoull(lp, nullptr, 0);   // profiling build (BVHT_SLICE_LOG) only
     // K0 pays when most blocks are empty (big_ben_clock 8K, 64 % empty: 1.11 -> 1.02 ms); when the instances' rectangles cover
     // the frame it is a wasted pass plus one dependent load per block in K1 (trippy_teapots, all blocks listed: 0.42 -> 0.46 ms).
@@ -1452,6 +1599,7 @@ static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvh
     bool use_k0 = false;
     if (p.n_rect) {
         if (k0_env) use_k0 = k0_env[0] == '1';
+        else if (p.cover) use_k0 = true;           // with per-triangle coverage most blocks of the examples' frames are empty
         else {
             constexpr int G = 32;
             uint32_t covered[G] = { 0 };
@@ -1517,9 +1665,12 @@ int bvht_render_frame_device(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
     ctx->stats.last_trace_rays = 0;
     if (region.x0 >= region.x1 || region.y0 >= region.y1) return BVHT_OK;     // empty region: nothing to do
     CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, 8, ctx->stream));
+    cover_policy_observe(ctx);
     cudaEventRecord(ctx->ev_a, ctx->stream);
+    if ((rc = prepare_cover(ctx, camera, width, height, tile, ctx->stream))) return rc;       // inside the timed interval
     rc = launch_primary_region(ctx, scene, camera, width, height, tile, region, shade, hits_out_device, frame_out_device,
                                ctx->stream, 0, ctx->shard_index, ctx->shard_count);
+    ctx->cover_ready = false;
     cudaEventRecord(ctx->ev_b, ctx->stream);
     if (rc) return rc;
     ctx->trace_timed = true;
@@ -1598,7 +1749,9 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
     if (const char* e = getenv("BVHT_BANDS")) { int v = atoi(e); if (v >= 1 && v <= 16) n_bands = (uint32_t)v; }      // A/B knob
     n_bands = std::min(n_bands, tile_rows);
     CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, 512, ctx->stream));
+    cover_policy_observe(ctx);
     cudaEventRecord(ctx->ev_a, ctx->stream);
+    if ((rc = prepare_cover(ctx, camera, width, height, tile, ctx->stream))) return rc;       // once per frame, before the bands fork
     CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     for (int i = 0; i < 2; ++i) CU(ctx, cudaStreamWaitEvent(ctx->aux[i], ctx->ev_fork, 0));
     CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
@@ -1684,6 +1837,7 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
     cudaEventRecord(ctx->ev_b, ctx->stream);
     ctx->trace_timed = true;
     ctx->stats.last_trace_rays = rays / ctx->shard_count;
+    ctx->cover_ready = false;
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     // per-band kernel times of this frame -> launch order of the next one.  The kernels of consecutive bands sit on two
     // streams and run back to back, so the end-to-end distance of their end events is the band's share of the frame.
@@ -1722,6 +1876,7 @@ int bvht_trace_rays_device(bvht_ctx* ctx, const void* rays_device, uint64_t n, v
     if ((rc = fill_scene(ctx, p.scene))) return rc;
     p.rays = (const float*)rays_device; p.n = n; p.out = (uint4*)out_device;
     p.work_counter = (unsigned int*)ctx->work_counter.p;
+    ctx->cover_policy.pending = false;                  // ev_a / ev_b are about to time a ray batch, not a frame
     int grid = persistent_grid(ctx, false, (n + 31) / 32);
     CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, 4, ctx->stream));
     cudaEventRecord(ctx->ev_a, ctx->stream);

@@ -40,6 +40,8 @@ struct BlasDesc {
     uint32_t nodes_used;
     float    accel_d_max;     // model-space limits |d| <= d_max, |o| <= o_max under which the inflated
     float    accel_o_max;     //   sub boxes are conservative (leaf_accel.hpp); other rays use brute-force leaves
+    float    bake_scale;      // the current bake's inflation of a triangle's box: scale * |e1||e2| + abs (accel_deltas)
+    float    bake_abs;
 };
 
 struct SceneDev {
@@ -93,9 +95,31 @@ struct PrimaryParams {
     uint32_t  n_origin;                  // 0 = not available (more than 32 instances)
     float4    inst_origin[32];
     uint32_t  n_rect;
+    // per-triangle coverage of the 8x4 blocks (cover_kernels.cu; tile == 8 only): bit i of cover[(ty * cover_ntx + tx) * 2 + half]
+    // = some triangle of instance i may be seen from that block; *cover_full = instances to be treated as visible everywhere
+    const uint32_t* cover;               // null = not available
+    const uint32_t* cover_full;
+    uint32_t  cover_ntx;
     uint32_t  skip_rounds;               // pointer-jumping rounds: ceil(log2(depth of the TLAS))
     uint32_t  n_tlas_nodes;              // > 0 (and <= 64) with n_rect: chain-skipping TLAS walk (trace_kernels.cuh build_tlas_skip)
     int4      inst_rect[32];
+};
+
+// cover_kernels.cu: rasterise every instance's triangles (conservative boxes) onto the 8x4-pixel blocks of the frame
+struct CoverParams {
+    uint32_t*       cover;          // one word per block, zeroed before the launch
+    uint32_t*       full;           // one word
+    uint32_t*       big_count;      // one word, zeroed
+    int4*           big_list;       // big_cap entries: {instance, bx0 << 16 | bx1, by0 << 16 | by1, -}
+    uint32_t        big_cap;
+    const BlasDesc* blas;
+    const uint32_t* inst_blas;
+    uint32_t        n_inst;         // <= 32
+    uint32_t        tri_offset[33]; // prefix sums of the instances' triangle counts
+    uint32_t        ntx;            // tiles (= blocks) per row of the full frame
+    uint32_t        width, height;
+    float           tlx, tly, inv_ex, inv_ey, near_, z_eps;     // near-plane rectangle of the camera (eye space)
+    float           mv[32][12];     // per instance: view * object transform, rows 0..2 (row-major 3 x 4)
 };
 
 // K6 (scene_kernels.cu): SceneObject::set_transform for every object + Tlas::rebuild

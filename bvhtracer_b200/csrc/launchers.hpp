@@ -27,6 +27,9 @@ cudaError_t launch_bake_sub_nodes(const float4* raw, const uint32_t* parent, uns
                                   const uint32_t* order, uint32_t n_nodes, float scale, float abs_, float4* lohi_scratch, float4* out,
                                   cudaStream_t s);
 
+// cover_kernels.cu
+cudaError_t launch_raster_cover(const CoverParams& p, cudaStream_t s);
+
 // scene_kernels.cu
 size_t      scene_rebuild_smem_bytes(uint32_t n_inst);
 cudaError_t launch_scene_rebuild(const SceneRebuildParams& p, cudaStream_t s);

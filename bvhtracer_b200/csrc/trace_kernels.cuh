@@ -780,6 +780,8 @@ trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
                     ov = !(rc.z < bx0 || rc.x > bx1 || rc.w < by0 || rc.y > by1);
                 }
                 cand = __ballot_sync(0xFFFFFFFFu, ov);
+                // per-triangle coverage (cover_kernels.cu): instances none of whose triangles can be seen from this block
+                if (P.cover) cand &= __ldg(P.cover + ((size_t)ty * P.cover_ntx + tx) * 2u + sub) | __ldg(P.cover_full);
             }
         }
         const uint8_t* skip = nullptr;
@@ -847,10 +849,13 @@ classify_fill_kernel(const __grid_constant__ PrimaryParams P) {
         uint32_t ty = P.ty0 + (tile_idx / P.ntx) * P.row_stride;
         int bx0 = (int)(tx * P.tile), bx1 = bx0 + (int)P.tile - 1;
         int by0 = (int)(ty * P.tile + (sub * 32u) / P.tile), by1 = (int)(ty * P.tile + (sub * 32u + 31u) / P.tile);
+        uint32_t mask = 0u;
         for (uint32_t i = 0; i < P.n_rect; ++i) {
             int4 rc = P.inst_rect[i];
-            seen |= !(rc.z < bx0 || rc.x > bx1 || rc.w < by0 || rc.y > by1);
+            if (!(rc.z < bx0 || rc.x > bx1 || rc.w < by0 || rc.y > by1)) mask |= 1u << i;
         }
+        if (P.cover) mask &= __ldg(P.cover + ((size_t)ty * P.cover_ntx + tx) * 2u + sub) | __ldg(P.cover_full);
+        seen = mask != 0u;
     }
     const unsigned listed = __ballot_sync(0xFFFFFFFFu, valid && seen);
     unsigned empty = __ballot_sync(0xFFFFFFFFu, valid && !seen);

@@ -889,3 +889,35 @@ def test_k0_classify_fill_equals_single_kernel(k0, monkeypatch):
         frame, hits = eng.render_frame(fcam, w, h, Engine.shade_depth(80.0, 3.0), want_hits=True)
         assert frame.tobytes() == O.shade(1, ref, 80.0, 3.0).tobytes()
         assert hits.tobytes() == ref.tobytes()
+
+
+# ------------------------------------------------------------------------------------------ per-triangle block coverage
+@pytest.mark.parametrize("cover", ["0", "1"])
+@pytest.mark.parametrize("camera_z,n,seed", [(-7.0, 7, 31), (-2.2, 9, 32), (-0.4, 12, 33)])
+def test_coverage_raster_equals_plain_trace(cover, camera_z, n, seed, monkeypatch):
+    # cover_kernels.cu marks, per 8x4 block, the instances whose (conservatively grown) triangle boxes project onto it; the trace
+    # kernels drop the other instances from the block's candidates.  Forced on and off (BVHT_COVER): records and shaded frames
+    # equal the oracle either way -- also with the camera INSIDE the cloud of instances (boxes behind / across the eye plane
+    # make an instance "visible everywhere"), with rotated instances, sub-regions and the banded host path.
+    monkeypatch.setenv("BVHT_COVER", cover)
+    rng = np.random.default_rng(seed)
+    blases = [SB.oracle_blas("teapot.obj"), SB.oracle_blas("cube.obj")]
+    scene = O.Scene(blases, _random_instances(rng, n, 2.5))
+    cam = O.camera_symmetric_fov(90.0, 1.0, 1.0, [0.2, 0.1, camera_z], [0, 0, 1], [1, 0, 0], [0, 1, 0])
+    w, h = 416, 232
+    fcam = SB.to_ffi_camera(cam)
+    ref = scene.render(cam, w, h, threads=NTHREADS)
+    assert (ref["id"] != O.MISS_ID).mean() > 0.01
+    with Engine(flags=FLAG_STRICT | FLAG_LEAF_ACCEL) as eng:
+        SB.upload_scene(eng, scene)
+        for _ in range(2):
+            assert_strict(eng.trace_primary(fcam, w, h), ref)
+        region = (40, 24, 300, 200)
+        got = eng.trace_primary(fcam, w, h, region=region)
+        inside = np.zeros((h, w), bool)
+        inside[region[1]:region[3], region[0]:region[2]] = True
+        inside = inside.reshape(-1)
+        assert got[inside].tobytes() == ref[inside].tobytes()
+        frame, hits = eng.render_frame(fcam, w, h, Engine.shade_depth(80.0, 3.0), want_hits=True)
+        assert frame.tobytes() == O.shade(1, ref, 80.0, 3.0).tobytes()
+        assert hits.tobytes() == ref.tobytes()

@@ -44,12 +44,20 @@ def main():
         grid = eng.stats()["trace_grid"]
         log = np.zeros(n_items * 2, "<u8")
         eng.memcpy_d2h(log, dlog)
+        hits = np.zeros(w * h, dtype=[("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("id", "<u4")])
+        eng.memcpy_d2h(hits, dout)
         eng.device_free(dlog); eng.device_free(dout)
+        # per 8x4 block: does any of its rays hit?  (item = (tile_y * ntx + tile_x) * 2 + half)
+        hit_px = (hits["id"] != 0xFFFFFFFF).reshape(h // 8, 2, 4, w // 8, 8)          # ty, half, row, tx, col
+        block_hit = hit_px.any(axis=(2, 4)).transpose(0, 2, 1).reshape(-1)             # -> (ty, tx, half) flattened = item order
+        del hits, hit_px
         t0 = log[0::2].astype(np.int64)
         dur = (log[1::2] & ((1 << 44) - 1)).astype(np.int64)
         smid = (log[1::2] >> 48).astype(np.int64)
         warp = ((log[1::2] >> 44) & 15).astype(np.int64)
         ok = t0 > 0
+        miss_time = float(dur[ok & ~block_hit].sum()); all_time = float(dur[ok].sum())
+        n_miss_blocks = int((ok & ~block_hit).sum())
         t0, dur, smid, warp = t0[ok], dur[ok], smid[ok], warp[ok]
         start = t0.min(); end = (t0 + dur).max(); span = end - start
         warps = grid * 4
@@ -70,6 +78,7 @@ def main():
         print(f"    blocks in flight: mean {mean_active:.0f} of {warps} warp slots ({100 * mean_active / warps:.0f} %), plateau(p90) {plateau:.0f}")
         print(f"    in-flight >= 90 % of plateau until {100 * last_above(0.9):.0f} % of the span, >= 50 % until {100 * last_above(0.5):.0f} %")
         print(f"    block time us: median {q[0]:.1f}  p90 {q[1]:.1f}  p99 {q[2]:.1f}  max {q[3]:.1f};  sum {dur.sum() / 1e6:.1f} ms = {dur.sum() / 1e6 / warps:.3f} ms per warp slot")
+        print(f"    blocks in which no ray hits anything: {n_miss_blocks} of {len(dur)} traced, {100 * miss_time / all_time:.1f} % of the summed block time")
         per_sm = np.bincount(smid, weights=dur.astype(np.float64), minlength=148) / 1e6
         print(f"    busy time per SM (sum of its blocks' times / 32 warp slots): min {per_sm.min() / 32:.3f}  mean {per_sm.mean() / 32:.3f}  max {per_sm.max() / 32:.3f} ms")
         del eng, renderer
