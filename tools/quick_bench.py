@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Exploration helper (not the judged bench): device time of the trace kernel for every config and mode."""
+"""Exploration helper (not the judged bench): device time of the trace kernel for every config and mode.
+Eight frames per mode, best of the last three: the first five let the library settle its measured choices (coverage raster)."""
 import os
 import sys
 import time
