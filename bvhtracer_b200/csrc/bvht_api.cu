@@ -1412,6 +1412,15 @@ static int prepare_cover(bvht_ctx* ctx, const bvht_camera* cam, uint32_t width, 
         for (const bvht_instance& in : ctx->h_inst) tris += ctx->blas[in.blas_id].n_tris;
         const uint32_t key[4] = { width, height, n_inst, tris };
         if (memcmp(key, pol.key, sizeof key) != 0) { memcpy(pol.key, key, sizeof key); pol.ms[0] = pol.ms[1] = -1.0f; pol.seen[0] = pol.seen[1] = 0; pol.frames = 0; }
+        // buffers of the coverage pass and of K0's block list: allocated on the first frame of a scene signature, whichever way
+        // that frame is traced, so that no later frame pays for a cudaMalloc inside its timed interval
+        {
+            const size_t blocks = (size_t)((width + 7) / 8) * ((height + 7) / 8) * 2;
+            int rc0 = ensure(ctx, ctx->cover, blocks * 4);
+            if (!rc0) rc0 = ensure(ctx, ctx->cover_aux, 16 + (size_t)std::max(tris, 1u) * 16);
+            if (!rc0 && blocks <= (64ull << 20)) rc0 = ensure(ctx, ctx->work_list, blocks * 4);
+            if (rc0) return rc0;
+        }
         int mode;
         if (const char* e = getenv("BVHT_COVER")) mode = e[0] == '1';
         else if (pol.ms[0] < 0.0f) mode = 0;                              // first two frames: without (the first is not a sample)
