@@ -1,5 +1,8 @@
+#!/usr/bin/env python3
+"""End-to-end frame time of Renderer::render (C3 4K, frames 9..32) for given band counts: python tools/e2e_bands_probe.py 1 4 7
+(BVHT_BAND_SHAPE, BVHT_BANDS_IMAGE_ORDER, BVHT_DEBUG_NO_D2H and PROBE_KEEP_HITS=1 select what is compared)."""
 import os, sys, time
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from bvhtracer_b200 import examples, host
 anim = examples.GridAnimation()
