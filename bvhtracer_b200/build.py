@@ -56,11 +56,19 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in _deps())
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, defs=()):
+    """variant / defs: tuning builds (tools/build_variants.py): the same sources with extra -D knobs, written to
+    lib/variants/libbvht_cuda_<variant>.so; the product library is always built without them."""
+    lib_path, obj_dir = LIB_PATH, OBJ_DIR
+    if variant:
+        lib_path = os.path.join(LIB_DIR, "variants", f"libbvht_cuda_{variant}.so")
+        obj_dir = os.path.join(OBJ_DIR, "variant_" + variant)
+        os.makedirs(os.path.dirname(lib_path), exist_ok=True)
+        force = True
     if not force and not needs_build():
         return LIB_PATH
     nvcc = _nvcc()
-    extra_defs = []
+    extra_defs = ["-D" + d for d in defs]
     if os.environ.get("BVHT_MIN_BLOCKS"):            # tuning knob: register budget of the trace kernels
         extra_defs.append("-DBVHT_MIN_BLOCKS=" + os.environ["BVHT_MIN_BLOCKS"])
     if os.environ.get("BVHT_GRAB"):                  # tuning knob: 32-pixel slices pulled per work-counter atomic
@@ -69,11 +77,11 @@ def build(force=False, verbose=False):
         if os.environ.get(knob):
             extra_defs.append("-D%s=%s" % (knob, os.environ[knob]))
     os.makedirs(LIB_DIR, exist_ok=True)
-    os.makedirs(OBJ_DIR, exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
     objs = []
     procs = []
     for src, extra in UNITS:
-        obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
+        obj = os.path.join(obj_dir, os.path.splitext(src)[0] + ".o")
         cmd = [nvcc] + ARCH + COMMON + extra + extra_defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
@@ -87,11 +95,11 @@ def build(force=False, verbose=False):
             sys.stderr.write(f"[bvht build] {src}\n{out}\n")
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    tmp = LIB_PATH + ".tmp"
+    tmp = lib_path + ".tmp"
     cmd = [nvcc] + ARCH + ["-shared", "-o", tmp] + objs
     subprocess.check_call(cmd)
-    os.replace(tmp, LIB_PATH)
-    return LIB_PATH
+    os.replace(tmp, lib_path)
+    return lib_path
 
 
 HOST_DIR = os.path.join(PKG, "host")
@@ -121,6 +129,3 @@ def build_all(force=False, verbose=False):
 
 if __name__ == "__main__":
     print(build_all(force="--force" in sys.argv, verbose="-v" in sys.argv))
-    sys.exit(0)
-
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

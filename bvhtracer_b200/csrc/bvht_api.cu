@@ -68,8 +68,54 @@ struct Blas {
 
 } // namespace
 
+// Tuning / diagnostic knobs.  The product library is built WITHOUT -DBVHT_EXPERIMENT: every knob then is the constant below
+// and no environment variable is ever read (tests/test_abi_load.py checks that the release .so holds none of the names).
+// tools/build_variants.py builds the experiment flavour (lib/variants/) the probe scripts under tools/ use; there the
+// environment is read ONCE, at bvht_create.
+struct Knobs {
+    float c_mt = 0.0f;                 // > 0: constant of the Moeller-Trumbore residual bound (margin study, tools/equivalence_sweep.py)
+    bool  timing = false;              // upload / build phase times on stderr
+    int   fast_global = -1;            // fast mode, one sub-BVH per model: -1 = by triangle-size criterion, 0 / 1 = forced
+    int   sub_leaf = 0;                // > 0: triangles per sub leaf
+    bool  accel_host_build = false, accel_rebuild = false;
+    int   cover = -1;                  // per-triangle coverage raster: -1 = by rule (cover_wanted), 0 / 1 = forced
+    bool  cover_debug = false;
+    bool  no_host_origin = false;
+    unsigned long long slice_log_ptr = 0;
+    int   k0 = -1;                     // K0 (classify + fill): -1 = by rule, 0 / 1 = forced
+    bool  no_d2h = false;              // timing experiment: bands without their copies
+    int   bands = 0;                   // > 0: number of bands of bvht_render_frame
+    int   band_shape = 1;              // 0 taper, 1 uniform, 2 triangular
+    bool  bands_image_order = false;
+};
+
+static Knobs read_knobs() {
+    Knobs k;
+#ifdef BVHT_EXPERIMENT
+    auto on = [](const char* n) { return getenv(n) != nullptr; };
+    if (const char* e = getenv("BVHT_C_MT")) k.c_mt = (float)atof(e);
+    k.timing = on("BVHT_TIMING");
+    if (const char* e = getenv("BVHT_FAST_GLOBAL")) k.fast_global = e[0] == '1';
+    if (const char* e = getenv("BVHT_SUB_LEAF")) { int v = atoi(e); if (v >= 1 && v <= 8) k.sub_leaf = v; }
+    k.accel_host_build = on("BVHT_ACCEL_HOST_BUILD");
+    k.accel_rebuild = on("BVHT_ACCEL_REBUILD");
+    if (on("BVHT_NO_COVER")) k.cover = 0;
+    if (const char* e = getenv("BVHT_COVER")) k.cover = e[0] == '1';
+    k.cover_debug = on("BVHT_COVER_DEBUG");
+    k.no_host_origin = on("BVHT_NO_HOST_ORIGIN");
+    if (const char* e = getenv("BVHT_SLICE_LOG_PTR")) k.slice_log_ptr = strtoull(e, nullptr, 0);
+    if (const char* e = getenv("BVHT_K0")) k.k0 = e[0] == '1';
+    k.no_d2h = on("BVHT_DEBUG_NO_D2H");
+    if (const char* e = getenv("BVHT_BANDS")) { int v = atoi(e); if (v >= 1 && v <= 16) k.bands = v; }
+    if (const char* e = getenv("BVHT_BAND_SHAPE")) k.band_shape = e[0] == 'u' ? 1 : (e[0] == 't' && e[1] == 'r' ? 2 : 0);
+    k.bands_image_order = on("BVHT_BANDS_IMAGE_ORDER");
+#endif
+    return k;
+}
+
 struct bvht_ctx {
     int device = 0;
+    Knobs knobs;
     uint32_t flags = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -220,7 +266,7 @@ int upload_u32(bvht_ctx* ctx, DevBuf& d, const std::vector<uint32_t>& v) {
 // recompute its whole-model tight box (host, rounded outwards).
 int bake_accel(bvht_ctx* ctx, Blas& b, double d_max, double o_max) {
     LeafAccelConfig cfg;
-    if (const char* e = getenv("BVHT_C_MT")) cfg.c_mt = (float)atof(e);     // experiment knob (tools/equivalence_sweep.py): margin study only
+    if (ctx->knobs.c_mt > 0.0f) cfg.c_mt = ctx->knobs.c_mt;     // experiment builds only (Knobs)
     double scale, abs_;
     accel_deltas(cfg, d_max, o_max, b.radius, b.max_edge, scale, abs_);
     float fs = (float)scale; if ((double)fs < scale) fs = std::nextafterf(fs, FLT_MAX);
@@ -287,7 +333,7 @@ void set_useful_product(Blas& b, const ModelStats& ms, const LeafAccelConfig& cf
 // binned-SAH builder, boxes + kappa by the same bottom-up kernel that refits it after vertex updates.
 int build_accel_device(bvht_ctx* ctx, Blas& b, const LeafAccelConfig& cfg, bool& done) {
     done = false;
-    const bool timing = getenv("BVHT_TIMING") != nullptr;
+    const bool timing = ctx->knobs.timing;
     auto t0 = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) {
         if (!timing) return;
@@ -306,11 +352,11 @@ int build_accel_device(bvht_ctx* ctx, Blas& b, const LeafAccelConfig& cfg, bool&
     // sixteen_armadillos +3..8 %, trippy_teapots +8 %, big_ben_clock -20 % -- the top levels of a global tree hold the
     // model's largest triangles, and a few triangles hundreds of times larger than the typical one (Big Ben: max |e1||e2| =
     // 115 x the mean; armadillo 6 x, teapot 3 x) drag their inflation through every box above them.  So: global tree when the
-    // largest edge product is within 32 x the mean.  BVHT_FAST_GLOBAL=0 / 1 forces it off / on.
+    // largest edge product is within 32 x the mean.  Knobs::fast_global forces it off / on (experiment builds).
     ModelStats ms = compute_model_stats(b.h_tris.data(), b.n_tris);
     {
         bool want = ms.mean_kappa > 0.0 && ms.model_kappa <= 32.0 * ms.mean_kappa && b.n_tris >= 64;    // (a dozen triangles: brute force wins)
-        if (const char* e = getenv("BVHT_FAST_GLOBAL")) want = e[0] == '1';
+        if (ctx->knobs.fast_global >= 0) want = ctx->knobs.fast_global == 1;
         b.global_accel = (ctx->flags & BVHT_FLAG_FAST) != 0 && b.n_tris > cfg.max_sub_leaf && b.n_tris >= 2 && want;
     }
     if (b.global_accel) { roots.push_back(SubRoot{ 0u, b.n_tris, 0u }); n_sub = b.n_tris; }
@@ -364,8 +410,8 @@ int build_accel_device(bvht_ctx* ctx, Blas& b, const LeafAccelConfig& cfg, bool&
 
 int build_and_upload_accel(bvht_ctx* ctx, Blas& b) {
     LeafAccelConfig cfg;
-    if (const char* e = getenv("BVHT_SUB_LEAF")) { int v = atoi(e); if (v >= 1 && v <= 8) cfg.max_sub_leaf = (uint32_t)v; }   // tuning knob
-    if (cfg.max_sub_leaf == 1 && !getenv("BVHT_ACCEL_HOST_BUILD")) {       // default: build it where the triangles are
+    if (ctx->knobs.sub_leaf > 0) cfg.max_sub_leaf = (uint32_t)ctx->knobs.sub_leaf;
+    if (cfg.max_sub_leaf == 1 && !ctx->knobs.accel_host_build) {       // default: build it where the triangles are
         bool done = false;
         int rc = build_accel_device(ctx, b, cfg, done);
         if (rc || done) return rc;
@@ -404,7 +450,7 @@ int build_and_upload_accel(bvht_ctx* ctx, Blas& b) {
 // Vertex update with the leaf accelerator on: keep the sub-BVH topology, refit it on the device (raw boxes + kappa,
 // bottom-up), recompute the whole-model statistics on the host (one O(n) pass) and re-bake the inflation.
 int refit_accel(bvht_ctx* ctx, Blas& b) {
-    if (b.n_sub_nodes == 0 || !b.sub_parent.p || getenv("BVHT_ACCEL_REBUILD")) return build_and_upload_accel(ctx, b);
+    if (b.n_sub_nodes == 0 || !b.sub_parent.p || ctx->knobs.accel_rebuild) return build_and_upload_accel(ctx, b);
     CU(ctx, launch_repack_sub_triangles((const float*)b.tris_aos.p, (const uint32_t*)b.sub_order.p, b.n_sub, (float4*)b.stri.p,
                                         ctx->stream));
     CU(ctx, launch_refit_sub_nodes((float4*)b.sub_raw.p, (const uint32_t*)b.sub_parent.p, (unsigned int*)b.sub_counters.p,
@@ -793,7 +839,7 @@ int make_blas(bvht_ctx* ctx, const float* tris, uint32_t n_tris, const bvht_bvh_
     int rc = validate_bvh(ctx, nodes, nodes_used, n_tris, parent, depth);
     if (rc) return rc;
 
-    const bool timing = getenv("BVHT_TIMING") != nullptr;
+    const bool timing = ctx->knobs.timing;
     auto t0 = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) {
         if (!timing) return;
@@ -939,6 +985,7 @@ int bvht_create(int device, uint32_t flags, bvht_ctx** out) {
     memset(&ctx->stats, 0, sizeof ctx->stats);
     ctx->device = device;
     ctx->flags = flags;
+    ctx->knobs = read_knobs();
     bool ok = cudaSetDevice(device) == cudaSuccess
            && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess
            && cudaEventCreate(&ctx->ev_a) == cudaSuccess && cudaEventCreate(&ctx->ev_b) == cudaSuccess
@@ -1495,7 +1542,7 @@ static int prepare_cover(bvht_ctx* ctx, const bvht_camera* cam, uint32_t width, 
     }
     ctx->cover_ready = true;
     ctx->cover_ntx = ntx;
-    if (getenv("BVHT_COVER_DEBUG")) {              // diagnostics: what the raster pass produced and what it cost
+    if (ctx->knobs.cover_debug) {              // diagnostics: what the raster pass produced and what it cost
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaStreamSynchronize(stream);
         cudaMemsetAsync(ctx->cover.p, 0, words * 4, stream);
@@ -1573,7 +1620,7 @@ static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvh
     }
     p.work_counter = (unsigned int*)ctx->work_counter.p + 2 * slot;
     p.n_origin = 0;
-    if (!ctx->h_inst.empty() && ctx->h_inst.size() <= 32 && !getenv("BVHT_NO_HOST_ORIGIN")) {
+    if (!ctx->h_inst.empty() && ctx->h_inst.size() <= 32 && !ctx->knobs.no_host_origin) {
         // BVHT_MV4 of trace_kernels.cuh, operation for operation (this file is compiled with -ffp-contract=off)
         auto mv4 = [](float c0, float c1, float c2, float c3, float x, float y, float z, float w) -> float {
             volatile float a = c0 * x, b = c1 * y, c = c2 * z, d = c3 * w;
@@ -1600,14 +1647,13 @@ static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvh
     if (ctx->cover_ready && p.n_rect && tile == 8) {
         p.cover = (const uint32_t*)ctx->cover.p; p.cover_full = (const uint32_t*)ctx->cover_aux.p; p.cover_ntx = ctx->cover_ntx;
     }
-    if (const char* lp = getenv("BVHT_SLICE_LOG_PTR")) p.stats = (unsigned long long*)strtoull(lp, nullptr, 0);   // profiling build (BVHT_SLICE_LOG) only
+    if (ctx->knobs.slice_log_ptr) p.stats = (unsigned long long*)ctx->knobs.slice_log_ptr;   // profiling build (BVHT_SLICE_LOG + BVHT_EXPERIMENT) only
     // K0 pays when most blocks are empty (big_ben_clock 8K, 64 % empty: 1.11 -> 1.02 ms); when the instances' rectangles cover
     // the frame it is a wasted pass plus one dependent load per block in K1 (trippy_teapots, all blocks listed: 0.42 -> 0.46 ms).
-    // Decide from the rectangles on a 32 x 32 grid over the launch's region.  BVHT_K0=0 / 1 forces it off / on (A/B knob).
-    const char* k0_env = getenv("BVHT_K0");
+    // Decide from the rectangles on a 32 x 32 grid over the launch's region (Knobs::k0 forces it in experiment builds).
     bool use_k0 = false;
     if (p.n_rect) {
-        if (k0_env) use_k0 = k0_env[0] == '1';
+        if (ctx->knobs.k0 >= 0) use_k0 = ctx->knobs.k0 == 1;
         else if (p.cover) use_k0 = true;           // with per-triangle coverage most blocks of the examples' frames are empty
         else {
             constexpr int G = 32;
@@ -1715,7 +1761,7 @@ int bvht_trace_primary_device(bvht_ctx* ctx, const bvht_camera* camera, uint32_t
 // D2H of the rows [y0, y1) x [x0, x1) of a width-pitched buffer of `elem` byte pixels.
 static int copy_rows_d2h(bvht_ctx* ctx, void* host, const void* dev, uint32_t width, bvht_rect r, size_t elem, cudaStream_t st) {
     size_t row = (size_t)width * elem;
-    if (getenv("BVHT_DEBUG_NO_D2H")) return BVHT_OK;      // timing experiment only: bands without their copies
+    if (ctx->knobs.no_d2h) return BVHT_OK;      // experiment builds only: bands without their copies
     if (r.x0 == 0 && r.x1 == width) {
         size_t off = (size_t)r.y0 * row, len = (size_t)(r.y1 - r.y0) * row;
         CU(ctx, cudaMemcpyAsync((char*)host + off, (const char*)dev + off, len, cudaMemcpyDeviceToHost, st));
@@ -1755,7 +1801,7 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
     uint32_t tile_rows = ty1 - ty0;
     uint64_t rays = (uint64_t)(region.x1 - region.x0) * (region.y1 - region.y0);
     uint32_t n_bands = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(rays / (1u << 20), 1), 16);
-    if (const char* e = getenv("BVHT_BANDS")) { int v = atoi(e); if (v >= 1 && v <= 16) n_bands = (uint32_t)v; }      // A/B knob
+    if (ctx->knobs.bands > 0) n_bands = (uint32_t)ctx->knobs.bands;
     n_bands = std::min(n_bands, tile_rows);
     CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, 512, ctx->stream));
     cover_policy_observe(ctx);
@@ -1775,8 +1821,7 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
     {
         // equal shares measured best for the 4 B/pixel frame and no worse for 20 B/pixel (BVHT_BAND_SHAPE=taper|triangular: A/B knob;
         // taper = first and last band half-size, triangular = 1, 2, 3, .., 3, 2, 1)
-        const char* shape = getenv("BVHT_BAND_SHAPE");
-        const int mode = !shape ? 1 : (shape[0] == 'u' ? 1 : (shape[0] == 't' && shape[1] == 'r' ? 2 : 0));
+        const int mode = ctx->knobs.band_shape;
         auto weight = [&](uint32_t b) -> uint64_t {
             if (mode == 1) return 2;
             if (mode == 2) return 2 * std::min(b + 1, n_bands - b);
@@ -1791,7 +1836,7 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
     for (uint32_t b = 0; b < n_bands; ++b) order[b] = b;
     const uint32_t hist_key[8] = { width, height, tile, region.x0, region.y0, region.x1, region.y1, n_bands };
     bvht_ctx::BandHistory& hist = ctx->band_hist;
-    static const bool image_order = getenv("BVHT_BANDS_IMAGE_ORDER") != nullptr;
+    const bool image_order = ctx->knobs.bands_image_order;
     if (hist.valid && hist.n == n_bands && memcmp(hist.key, hist_key, sizeof hist_key) == 0 && !image_order)
         std::stable_sort(order, order + n_bands, [&](uint32_t x, uint32_t y) { return hist.ms_per_row[x] < hist.ms_per_row[y]; });
     cudaEventRecord(ctx->ev_band_t[0], ctx->stream);
