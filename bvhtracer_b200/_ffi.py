@@ -40,6 +40,8 @@ class ShadeParams(C.Structure):
                 ("hit_rgba", C.c_uint8 * 4), ("miss_rgba", C.c_uint8 * 4), ("object0_transform", C.c_float * 16)]
 
 
+OPT_COVER, OPT_K0, OPT_BANDS = 1, 2, 3
+
 SHADE_NONE, SHADE_DEPTH, SHADE_INTERSECTION, SHADE_UV, SHADE_NORMAL, SHADE_TEXTURE = 0, 1, 2, 3, 4, 5
 
 
@@ -64,6 +66,7 @@ SYMBOLS = [
     ("bvht_status_string", C.c_char_p, [C.c_int]),
     ("bvht_set_stream", C.c_int, [_P, _P]),
     ("bvht_sync", C.c_int, [_P]),
+    ("bvht_set_option", C.c_int, [_P, C.c_uint32, C.c_int32]),
     ("bvht_blas_create", C.c_int, [_P, _P, C.c_uint32, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     ("bvht_blas_destroy", C.c_int, [_P, C.c_uint32]),
     ("bvht_blas_build", C.c_int, [_P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),

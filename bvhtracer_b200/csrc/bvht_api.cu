@@ -31,6 +31,7 @@ namespace {
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr uint32_t kRefitChunkTris = 512;
 constexpr int kTraceBlock = 128;
+constexpr int kMaxBands = 16;
 
 struct DevBuf {
     void* p = nullptr;
@@ -139,11 +140,6 @@ struct bvht_ctx {
     DevBuf work_counter;                              // slot i: [2i] = K1's work cursor, [2i+1] = length of K0's block list
     DevBuf cover, cover_aux;                          // per-triangle block coverage of the current frame (cover_kernels.cu); aux: full word, big count, big list
     bool cover_ready = false;                         // valid for the launches of the current frame only
-    // The raster pass costs 35-160 us and saves more or less than that depending on the scene (sixteen_armadillos 4K: -10..14 %
-    // of the frame; trippy_teapots, big_ben_clock: +6..10 %), so it is decided by measurement: the frame time (ev_a..ev_b) of
-    // frames traced with and without it is tracked per scene signature, the faster way is used, the other one re-probed every
-    // 64 frames.  BVHT_COVER=0 / 1 forces it off / on.
-    struct CoverPolicy { uint32_t key[4] = { 0 }; float ms[2] = { -1.0f, -1.0f }; uint32_t seen[2] = { 0, 0 }; uint32_t frames = 0; int last_mode = -1; bool pending = false; } cover_policy;
     uint32_t cover_ntx = 0;
     std::vector<float> inst_d2max;                    // per instance: largest |d_w|^2 its tight box / baked boxes are valid for (< 0: unusable)
     DevBuf work_list;                                 // K0's list of blocks that see an instance, one u32 per block of the frame
@@ -159,6 +155,7 @@ struct bvht_ctx {
     struct BandHistory { uint32_t key[8] = { 0 }; uint32_t n = 0; float ms_per_row[16] = { 0 }; bool valid = false; } band_hist;
     void* pinned = nullptr; size_t pinned_bytes = 0;  // pinned staging for small uploads
     int sm_count = 0;
+    int occ_cache[3] = { 0, 0, 0 };                   // resident CTAs per SM: ray kernel, primary kernel, primary kernel with chain skipping
     uint32_t shard_index = 0, shard_count = 1;
     bvht_stats stats;
     std::string err;
@@ -637,6 +634,7 @@ int recompute_tlas_tight(bvht_ctx* ctx) {
     // instance masks per node (only meaningful for n_inst <= 32; the kernel ignores them otherwise)
     std::vector<uint32_t> mask(nodes_used, 0xFFFFFFFFu);
     if (n_inst <= 32) {
+        std::fill(mask.begin(), mask.end(), 0u);                  // slots the walk never reaches: no instance below them
         std::vector<uint8_t> mdone(nodes_used, 0);
         struct Rec { static uint32_t go(const bvht_tlas_node* n, uint32_t i, std::vector<uint32_t>& m, std::vector<uint8_t>& d) {
             if (d[i]) return m[i];
@@ -815,11 +813,16 @@ int fill_scene(bvht_ctx* ctx, SceneDev& s) {
     return BVHT_OK;
 }
 
-int persistent_grid(bvht_ctx* ctx, bool primary, uint64_t n_items) {
+int persistent_grid(bvht_ctx* ctx, bool primary, uint64_t n_items, bool prune = false) {
     bool accel = accel_on(ctx);
-    int per_sm;
-    if (fast_on(ctx)) per_sm = primary ? blocks_per_sm_primary_fast(accel, kTraceBlock) : blocks_per_sm_rays_fast(accel, kTraceBlock);
-    else              per_sm = primary ? blocks_per_sm_primary_strict(accel, kTraceBlock) : blocks_per_sm_rays_strict(accel, kTraceBlock);
+    // the occupancy query is a driver call: once per (kernel flavour) and context
+    int& cached = ctx->occ_cache[primary ? (prune ? 2 : 1) : 0];
+    int per_sm = cached;
+    if (per_sm == 0) {
+        if (fast_on(ctx)) per_sm = primary ? blocks_per_sm_primary_fast(accel, prune, kTraceBlock) : blocks_per_sm_rays_fast(accel, kTraceBlock);
+        else              per_sm = primary ? blocks_per_sm_primary_strict(accel, prune, kTraceBlock) : blocks_per_sm_rays_strict(accel, kTraceBlock);
+        cached = per_sm;
+    }
     if (per_sm < 1) per_sm = 1;
     uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)per_sm;          // a whole number of resident waves
     uint64_t warps_needed = n_items;
@@ -1019,8 +1022,9 @@ void bvht_destroy(bvht_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (Blas& b : ctx->blas) free_blas(b);
     for (DevBuf* d : { &ctx->blas_desc, &ctx->tlas, &ctx->inst_cols, &ctx->inst_blas, &ctx->work_counter, &ctx->work_list, &ctx->cover, &ctx->cover_aux, &ctx->out_buf, &ctx->rays_buf,
-                       &ctx->rgba_buf, &ctx->tlas_tight, &ctx->tlas_mask, &ctx->scene_in, &ctx->scene_bounds })
+                       &ctx->rgba_buf, &ctx->tlas_tight, &ctx->tlas_mask, &ctx->scene_in, &ctx->scene_bounds, &ctx->build_tris, &ctx->build_perm })
         release(*d);
+    ctx->build_ws.release();
     for (cudaStream_t st : { ctx->aux[0], ctx->aux[1], ctx->copy_stream }) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     for (cudaEvent_t ev : { ctx->ev_fork, ctx->ev_join }) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : ctx->ev_band) if (ev) cudaEventDestroy(ev);
@@ -1039,6 +1043,18 @@ int bvht_set_stream(bvht_ctx* ctx, void* cuda_stream) {
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return BVHT_OK;
+}
+
+int bvht_set_option(bvht_ctx* ctx, uint32_t option, int32_t value) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    switch (option) {
+        case BVHT_OPT_COVER: ctx->knobs.cover = value < 0 ? -1 : (value != 0); return BVHT_OK;
+        case BVHT_OPT_K0:    ctx->knobs.k0 = value < 0 ? -1 : (value != 0); return BVHT_OK;
+        case BVHT_OPT_BANDS:
+            if (value > kMaxBands) return fail(ctx, BVHT_ERR_INVALID_ARG, "at most %d bands (%d asked)", kMaxBands, (int)value);
+            ctx->knobs.bands = value < 0 ? 0 : value; return BVHT_OK;
+        default: return fail(ctx, BVHT_ERR_INVALID_ARG, "unknown option %u", option);
+    }
 }
 
 int bvht_sync(bvht_ctx* ctx) {
@@ -1248,12 +1264,17 @@ int bvht_blas_read_nodes(bvht_ctx* ctx, uint32_t blas_id, bvht_bvh_node* out, ui
 }
 
 // Walk the TLAS: indices in range, bounded depth, no cycles (node 0 is a COPY of the last merged node, tlas.rs:248)
-static int validate_tlas(bvht_ctx* ctx, const bvht_tlas_node* nodes, uint32_t nodes_used, uint32_t n_instances) {
+// `reached` (optional): which nodes the walk from node 0 touches.  Slots it does not touch never take part in a traversal, but the
+// device tables built per node (instance masks, chain-skip table) index through them: the caller neutralises them.
+static int validate_tlas(bvht_ctx* ctx, const bvht_tlas_node* nodes, uint32_t nodes_used, uint32_t n_instances,
+                         std::vector<uint8_t>* reached = nullptr) {
     std::vector<std::pair<uint32_t, uint32_t>> stack;
     stack.push_back({ 0u, 1u });
     uint64_t visited = 0;
+    if (reached) reached->assign(nodes_used, 0);
     while (!stack.empty()) {
         auto [ni, depth] = stack.back(); stack.pop_back();
+        if (reached) (*reached)[ni] = 1;
         if (++visited > 4ull * nodes_used + 4)
             return fail(ctx, BVHT_ERR_MALFORMED_BVH, "TLAS walk does not terminate (cycle)");
         if (depth > (uint32_t)kTlasStack)
@@ -1280,7 +1301,8 @@ int bvht_tlas_set(bvht_ctx* ctx, const bvht_tlas_node* nodes, uint32_t nodes_use
         return fail(ctx, BVHT_ERR_INVALID_ARG, "scene without objects (the reference's Tlas::intersect indexes blas[0] and panics, tlas.rs:130)");
     if (n_instances > 0xFFFu + 1u) return fail(ctx, BVHT_ERR_INVALID_ARG, "more than 4096 instances (12-bit instance index)");
     cudaSetDevice(ctx->device);
-    { int vrc = validate_tlas(ctx, nodes, nodes_used, n_instances); if (vrc) return vrc; }
+    std::vector<uint8_t> reached;
+    { int vrc = validate_tlas(ctx, nodes, nodes_used, n_instances, &reached); if (vrc) return vrc; }
     for (uint32_t i = 0; i < n_instances; ++i) {
         uint32_t id = instances[i].blas_id;
         if (id >= ctx->blas.size() || !ctx->blas[id].alive)
@@ -1298,6 +1320,7 @@ int bvht_tlas_set(bvht_ctx* ctx, const bvht_tlas_node* nodes, uint32_t nodes_use
     float* tl = (float*)st;
     for (uint32_t i = 0; i < nodes_used; ++i) {
         float* f = tl + (size_t)i * 8;
+        if (!reached[i]) { memset(f, 0, 32); continue; }       // unreachable slot (whatever it holds): a leaf of instance 0 nobody visits
         memcpy(f + 0, nodes[i].aabb_min, 12); memcpy(f + 3, &nodes[i].left_right, 4);
         memcpy(f + 4, nodes[i].aabb_max, 12); memcpy(f + 7, &nodes[i].blas, 4);
     }
@@ -1313,6 +1336,7 @@ int bvht_tlas_set(bvht_ctx* ctx, const bvht_tlas_node* nodes, uint32_t nodes_use
         if ((rc = h2d(ctx, ctx->inst_blas.p, ib, (size_t)n_instances * 4))) return rc;
     }
     ctx->h_tlas.assign(nodes, nodes + nodes_used);
+    for (uint32_t i = 0; i < nodes_used; ++i) if (!reached[i]) memset(&ctx->h_tlas[i], 0, sizeof(bvht_tlas_node));
     ctx->h_inst.assign(instances, instances + n_instances);
     ctx->h_inst_bounds.clear();
     ctx->tlas_nodes_used = nodes_used;
@@ -1431,35 +1455,46 @@ int bvht_tlas_read(bvht_ctx* ctx, bvht_tlas_node* nodes_out, uint32_t max_nodes,
     return BVHT_OK;
 }
 
-// Before a frame's ev_a is recorded: the previous frame's time (ev_a..ev_b, complete if anything was synchronised since) goes
-// to the way that frame was traced -- with or without the coverage pass (bvht_ctx::CoverPolicy).
-static void cover_policy_observe(bvht_ctx* ctx) {
-    bvht_ctx::CoverPolicy& pol = ctx->cover_policy;
-    if (pol.pending && ctx->trace_timed && pol.last_mode >= 0 && cudaEventQuery(ctx->ev_b) == cudaSuccess) {
-        float t = 0.0f;
-        if (cudaEventElapsedTime(&t, ctx->ev_a, ctx->ev_b) == cudaSuccess) {
-            // the first frame of either way pays for its allocations inside the interval: not a sample
-            if (pol.seen[pol.last_mode]++ > 0) pol.ms[pol.last_mode] = pol.ms[pol.last_mode] < 0.0f ? t : 0.5f * (pol.ms[pol.last_mode] + t);
-        }
+// Whether the per-triangle coverage raster (K7) is worth its 35-160 us for this scene and camera.  A fixed rule, not a
+// measurement, so that which kernels a frame launches depends on the scene alone.  It pays when rays would otherwise enter
+// instances they cannot hit AND entering one is expensive: several instances whose screen rectangles overlap (sixteen_armadillos
+// 4K: -10..14 % of the frame) and large models; it does not for small models (trippy_teapots: +6..10 %), for one instance
+// (big_ben_clock: K0 with the model's rectangle already removes the empty blocks) or for instances side by side.
+static bool cover_wanted(const bvht_ctx* ctx, const bvht_camera* cam, uint32_t width, uint32_t height, uint32_t n_inst, uint32_t tris) {
+    if (ctx->knobs.cover >= 0) return ctx->knobs.cover == 1;            // experiment builds only
+    if (n_inst < 2 || tris / n_inst < 8192u) return false;
+    int4 rects[32]; uint32_t nr = 0;
+    if (!compute_instance_rects(ctx, cam, width, height, rects, nr) || nr == 0) return false;
+    constexpr int G = 32;
+    uint32_t any[G] = { 0 }; uint64_t sum = 0;
+    for (uint32_t i = 0; i < nr; ++i) {
+        const int4 rc = rects[i];
+        if (rc.z < rc.x || rc.w < rc.y) continue;
+        int cx0 = std::max(0, (int)((int64_t)std::max(rc.x, 0) * G / (int64_t)width)), cx1 = std::min(G - 1, (int)((int64_t)std::max(rc.z, 0) * G / (int64_t)width));
+        int cy0 = std::max(0, (int)((int64_t)std::max(rc.y, 0) * G / (int64_t)height)), cy1 = std::min(G - 1, (int)((int64_t)std::max(rc.w, 0) * G / (int64_t)height));
+        if (cx1 < cx0 || cy1 < cy0) continue;
+        uint32_t bits = (cx1 - cx0 == 31) ? 0xFFFFFFFFu : (((1u << (cx1 - cx0 + 1)) - 1u) << cx0);
+        for (int y = cy0; y <= cy1; ++y) any[y] |= bits;
+        sum += (uint64_t)(cx1 - cx0 + 1) * (cy1 - cy0 + 1);
     }
-    cudaGetLastError();
-    pol.pending = false;
+    uint64_t uni = 0;
+    for (int y = 0; y < G; ++y) uni += __builtin_popcount(any[y]);
+    return uni > 0 && 2 * sum >= 3 * uni;                                // the rectangles cover what they cover 1.5 times over
 }
 
 // Rasterise every instance's triangles onto the 8x4-pixel blocks of the frame (cover_kernels.cu).  Once per frame, on
 // `stream`, before the frame's trace launches; they pick the result up through ctx->cover_ready.
 static int prepare_cover(bvht_ctx* ctx, const bvht_camera* cam, uint32_t width, uint32_t height, uint32_t tile, cudaStream_t stream) {
     ctx->cover_ready = false;
-    bvht_ctx::CoverPolicy& pol = ctx->cover_policy;
-    if (getenv("BVHT_NO_COVER") || !accel_on(ctx) || tile != 8) return BVHT_OK;
+    if (!accel_on(ctx) || tile != 8) return BVHT_OK;
+    // big rectangles are packed as 16-bit block bounds (cover_kernels.cu): frames beyond 65535 blocks per side go without
+    if ((width + 7) / 8 > 65535u || (height + 3) / 4 > 65535u) return BVHT_OK;
     const uint32_t n_inst = (uint32_t)ctx->h_inst.size();
     if (n_inst == 0 || n_inst > 32 || ctx->inst_tight.size() != (size_t)n_inst * 6 || ctx->inst_d2max.size() != n_inst) return BVHT_OK;
     {
         uint32_t tris = 0;
         for (const bvht_instance& in : ctx->h_inst) tris += ctx->blas[in.blas_id].n_tris;
-        const uint32_t key[4] = { width, height, n_inst, tris };
-        if (memcmp(key, pol.key, sizeof key) != 0) { memcpy(pol.key, key, sizeof key); pol.ms[0] = pol.ms[1] = -1.0f; pol.seen[0] = pol.seen[1] = 0; pol.frames = 0; }
-        // buffers of the coverage pass and of K0's block list: allocated on the first frame of a scene signature, whichever way
+        // buffers of the coverage pass and of K0's block list: allocated on the first frame of a scene, whichever way
         // that frame is traced, so that no later frame pays for a cudaMalloc inside its timed interval
         {
             const size_t blocks = (size_t)((width + 7) / 8) * ((height + 7) / 8) * 2;
@@ -1468,18 +1503,7 @@ static int prepare_cover(bvht_ctx* ctx, const bvht_camera* cam, uint32_t width, 
             if (!rc0 && blocks <= (64ull << 20)) rc0 = ensure(ctx, ctx->work_list, blocks * 4);
             if (rc0) return rc0;
         }
-        int mode;
-        if (const char* e = getenv("BVHT_COVER")) mode = e[0] == '1';
-        else if (pol.ms[0] < 0.0f) mode = 0;                              // first two frames: without (the first is not a sample)
-        else if (pol.ms[1] < 0.0f) mode = 1;                              // next two: with
-        else {
-            mode = pol.ms[1] < pol.ms[0];
-            if (pol.frames % 64 == 63) mode = !mode;                      // re-probe the other way now and then
-        }
-        pol.frames += 1;
-        pol.last_mode = mode;
-        pol.pending = true;
-        if (!mode) return BVHT_OK;
+        if (!cover_wanted(ctx, cam, width, height, n_inst, tris)) return BVHT_OK;
     }
     const float* tl = cam->top_left_eye; const float* tr = cam->top_right_eye; const float* bl = cam->bottom_left_eye;
     if (!(tl[2] < 0.0f) || tr[2] != tl[2] || bl[2] != tl[2] || tr[1] != tl[1] || bl[0] != tl[0]) return BVHT_OK;
@@ -1685,7 +1709,7 @@ static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvh
             ctx->stats.kernel_launches += 1;
         }
     }
-    int grid = persistent_grid(ctx, true, n_items);
+    int grid = persistent_grid(ctx, true, n_items, accel_on(ctx) && p.n_tlas_nodes != 0u);
     cudaError_t e = fast_on(ctx) ? launch_primary_fast(p, accel_on(ctx), grid, kTraceBlock, stream)
                                  : launch_primary_strict(p, accel_on(ctx), grid, kTraceBlock, stream);
     if (e != cudaSuccess) return fail(ctx, BVHT_ERR_CUDA, "trace_primary launch failed: %s", cudaGetErrorString(e));
@@ -1720,7 +1744,6 @@ int bvht_render_frame_device(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
     ctx->stats.last_trace_rays = 0;
     if (region.x0 >= region.x1 || region.y0 >= region.y1) return BVHT_OK;     // empty region: nothing to do
     CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, 8, ctx->stream));
-    cover_policy_observe(ctx);
     cudaEventRecord(ctx->ev_a, ctx->stream);
     if ((rc = prepare_cover(ctx, camera, width, height, tile, ctx->stream))) return rc;       // inside the timed interval
     rc = launch_primary_region(ctx, scene, camera, width, height, tile, region, shade, hits_out_device, frame_out_device,
@@ -1804,7 +1827,6 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
     if (ctx->knobs.bands > 0) n_bands = (uint32_t)ctx->knobs.bands;
     n_bands = std::min(n_bands, tile_rows);
     CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, 512, ctx->stream));
-    cover_policy_observe(ctx);
     cudaEventRecord(ctx->ev_a, ctx->stream);
     if ((rc = prepare_cover(ctx, camera, width, height, tile, ctx->stream))) return rc;       // once per frame, before the bands fork
     CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
@@ -1841,7 +1863,7 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
         std::stable_sort(order, order + n_bands, [&](uint32_t x, uint32_t y) { return hist.ms_per_row[x] < hist.ms_per_row[y]; });
     cudaEventRecord(ctx->ev_band_t[0], ctx->stream);
     auto band_row = [&](uint32_t b) -> uint32_t { return band_start[b]; };
-    for (uint32_t i = 0; i < n_bands; ++i) {
+    auto run_band = [&](uint32_t i) -> int {
         const uint32_t b = order[i];
         uint32_t r0 = ty0 + band_row(b);
         uint32_t r1 = ty0 + band_row(b + 1);
@@ -1852,7 +1874,7 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
                                             ctx->shard_index, ctx->shard_count))) return rc;
         }
         cudaEventRecord(ctx->ev_band_t[i + 1], cs);
-        if (band.y0 >= band.y1) continue;
+        if (band.y0 >= band.y1) return BVHT_OK;
         CU(ctx, cudaEventRecord(ctx->ev_band[b], cs));
         CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[b], 0));
         if (ctx->shard_count == 1) {
@@ -1884,6 +1906,17 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
                     }
                 }
             }
+        }
+        return BVHT_OK;
+    };
+    for (uint32_t i = 0; i < n_bands; ++i) {
+        if ((rc = run_band(i)) != BVHT_OK) {
+            // bands already queued on the forked streams must not outlive this call: the next one resets their work counters
+            for (cudaStream_t st : { ctx->aux[0], ctx->aux[1], ctx->copy_stream }) cudaStreamSynchronize(st);
+            cudaStreamSynchronize(ctx->stream);
+            cudaGetLastError();
+            ctx->cover_ready = false;
+            return rc;
         }
     }
     CU(ctx, cudaEventRecord(ctx->ev_join, ctx->copy_stream));
@@ -1930,7 +1963,6 @@ int bvht_trace_rays_device(bvht_ctx* ctx, const void* rays_device, uint64_t n, v
     if ((rc = fill_scene(ctx, p.scene))) return rc;
     p.rays = (const float*)rays_device; p.n = n; p.out = (uint4*)out_device;
     p.work_counter = (unsigned int*)ctx->work_counter.p;
-    ctx->cover_policy.pending = false;                  // ev_a / ev_b are about to time a ray batch, not a frame
     int grid = persistent_grid(ctx, false, (n + 31) / 32);
     CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, 4, ctx->stream));
     cudaEventRecord(ctx->ev_a, ctx->stream);
@@ -2111,7 +2143,7 @@ int bvht_debug_trace_stats(bvht_ctx* ctx, const bvht_camera* camera, uint32_t wi
     while ((1u << p.skip_rounds) < ctx->tlas_depth) ++p.skip_rounds;
     cudaMemsetAsync(cnt.p, 0, 16 * sizeof(uint64_t), ctx->stream);
     cudaMemsetAsync(ctx->work_counter.p, 0, 4, ctx->stream);
-    int per_sm = std::max(1, blocks_per_sm_primary_stats(accel_on(ctx), kTraceBlock));
+    int per_sm = std::max(1, blocks_per_sm_primary_stats(accel_on(ctx), accel_on(ctx) && p.n_tlas_nodes != 0u, kTraceBlock));
     cudaError_t e = launch_primary_stats(p, accel_on(ctx), ctx->sm_count * per_sm, kTraceBlock, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(counters_out, cnt.p, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -8,7 +8,7 @@ namespace bvht {
 #define BVHT_DECLARE_MODE(sfx)                                                                                   \
     cudaError_t launch_primary_##sfx(const PrimaryParams& p, bool accel, int grid, int block, cudaStream_t s);   \
     cudaError_t launch_rays_##sfx(const RaysParams& p, bool accel, int grid, int block, cudaStream_t s);         \
-    int blocks_per_sm_primary_##sfx(bool accel, int block);                                                      \
+    int blocks_per_sm_primary_##sfx(bool accel, bool prune, int block);                                                      \
     int blocks_per_sm_rays_##sfx(bool accel, int block);
 BVHT_DECLARE_MODE(strict)
 BVHT_DECLARE_MODE(fast)

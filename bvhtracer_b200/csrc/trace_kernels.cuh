@@ -31,96 +31,8 @@
 #define BVHT_MIN_BLOCKS 8      // CTAs of 128 threads per SM the register allocation must allow: 64 registers (swept 5-10 on B200)
 #endif
 
-// Traversal stack: the first BVHT_SMEM_STACK entries of every thread live in shared memory (one column per thread:
-// entry i of thread t at word i * 128 + t, conflict-free), deeper entries in a local-memory overflow array that the
-// examples' trees never reach (measured depth of use: TLAS + BLAS + sub-BVH <= 14).  ONE stack serves the three nested
-// walks (TLAS below, BLAS above it, leaf sub-BVH on top): an inner walk starts at the outer walk's stack pointer.
-#ifndef BVHT_SMEM_STACK
-#define BVHT_SMEM_STACK 0
-#endif
-// Leaf sub-BVH walk: triangle tests are POSTPONED and run for the lanes of a warp together (leaf_accel).  A lane that reaches
-// a leaf parks it and goes on traversing; the parked triangles are tested when at least BVHT_POSTPONE / 8 of the lanes
-// still working hold one (or none can go on).  0 = test every leaf where it is met.
-#ifndef BVHT_POSTPONE
-#define BVHT_POSTPONE 0
-#endif
-// 1: a lane with a parked leaf goes on traversing (speculatively); 0: it waits at the leaf
-#ifndef BVHT_POSTPONE_SPEC
-#define BVHT_POSTPONE_SPEC 0
-#endif
-// Sub-BVH stack entries carry the box entry distance and are dropped at pop time when the leaf's best t has passed it.
-#ifndef BVHT_POPCULL
-#define BVHT_POPCULL 0
-#endif
-// BLAS walk: every lane advances to its next reference leaf before any lane works on one (the lanes of a warp then enter
-// the leaf accelerator together).
-#ifndef BVHT_BLAS_WW
-#define BVHT_BLAS_WW 0
-#endif
-
 namespace bvht {
 namespace BVHT_MODE_NS {
-
-constexpr int kStackOverflow = kTlasStack + kBlasStack + kSubStack;
-
-struct TStack {
-#if BVHT_SMEM_STACK > 0
-    uint32_t* sm;                        // this thread's column of the CTA's shared stack
-#if BVHT_POPCULL
-    float*    smt;
-#endif
-#endif
-    uint32_t  ov[kStackOverflow];        // local memory; only entries >= BVHT_SMEM_STACK are ever touched
-#if BVHT_POPCULL
-    float     ovt[kStackOverflow];
-#endif
-    __device__ __forceinline__ void put(int i, uint32_t v) {
-#if BVHT_SMEM_STACK > 0
-        if (i < BVHT_SMEM_STACK) sm[i * 128] = v; else ov[i - BVHT_SMEM_STACK] = v;
-#else
-        ov[i] = v;
-#endif
-    }
-    __device__ __forceinline__ uint32_t get(int i) const {
-#if BVHT_SMEM_STACK > 0
-        return i < BVHT_SMEM_STACK ? sm[i * 128] : ov[i - BVHT_SMEM_STACK];
-#else
-        return ov[i];
-#endif
-    }
-#if BVHT_POPCULL
-    // box entry distance of a sub-BVH entry (same index as the entry)
-    __device__ __forceinline__ void putt(int i, float v) {
-#if BVHT_SMEM_STACK > 0
-        if (i < BVHT_SMEM_STACK) smt[i * 128] = v; else ovt[i - BVHT_SMEM_STACK] = v;
-#else
-        ovt[i] = v;
-#endif
-    }
-    __device__ __forceinline__ float gett(int i) const {
-#if BVHT_SMEM_STACK > 0
-        return i < BVHT_SMEM_STACK ? smt[i * 128] : ovt[i - BVHT_SMEM_STACK];
-#else
-        return ovt[i];
-#endif
-    }
-#endif
-};
-
-#if BVHT_SMEM_STACK > 0
-#if BVHT_POPCULL
-#define BVHT_DECLARE_STACK(S)                                              \
-    __shared__ uint32_t s_stack_[BVHT_SMEM_STACK][128];                    \
-    __shared__ float    s_stackt_[BVHT_SMEM_STACK][128];                   \
-    TStack S; S.sm = &s_stack_[0][threadIdx.x]; S.smt = &s_stackt_[0][threadIdx.x];
-#else
-#define BVHT_DECLARE_STACK(S)                                              \
-    __shared__ uint32_t s_stack_[BVHT_SMEM_STACK][128];                    \
-    TStack S; S.sm = &s_stack_[0][threadIdx.x];
-#endif
-#else
-#define BVHT_DECLARE_STACK(S) TStack S;
-#endif
 
 struct RayM {            // a ray in some space with its cached reciprocal (query/ray.rs:9-17)
     float ox, oy, oz;
@@ -340,147 +252,76 @@ __device__ __forceinline__ void leaf_brute(const BlasDesc& B, uint32_t base, uin
     }
 }
 
-__device__ __forceinline__ void sub_triangles(const BlasDesc& B, uint32_t ref, const RayM& r, float entry_t,
-                                              float& lt, float& lu, float& lv, uint32_t& lp, bool& lfound, Stat& st) {
-    // leaf ref: [30:28] = count-1, [27:0] = first triangle in sub order
-    uint32_t first = ref & 0x0FFFFFFFu;
-    uint32_t cnt = ((ref >> 28) & 7u) + 1u;
-    st.add(7, cnt);
-    const float4* tp = B.stri + 3 * (size_t)first;
-    for (uint32_t k = 0; k < cnt; ++k, tp += 3) {
-        float4 v0 = ldg4(tp + 0);
-        float4 e1 = ldg4(tp + 1);
-        float4 e2 = ldg4(tp + 2);
-        MtPartial mp;
-        if (mt_filter(v0, e1, e2, r, mp)) {
-            float t, u, v;
-            if (mt_finish(e1, e2, r, mp, entry_t, t, u, v)) {
-                uint32_t pi = __float_as_uint(v0.w);
-                if (t < lt || (t == lt && pi < lp)) { lt = t; lu = u; lv = v; lp = pi; lfound = true; }
-            }
-        }
-    }
-}
-
-constexpr uint32_t kSubDone = 0x7FFFFFFFu;      // "no node left": above every inner index, below every leaf ref (bit 31)
-
-__device__ __forceinline__ uint32_t sub_pop(TStack& S, int& sp, int sp0, float lt) {
-#if BVHT_POPCULL
-    while (sp > sp0) {
-        --sp;
-        if (S.gett(sp) <= lt) return S.get(sp);
-    }
-    return kSubDone;
-#else
-    (void)lt;
-    return sp > sp0 ? S.get(--sp) : kSubDone;
-#endif
-}
-
-// One inner step of the sub-BVH walk: test both child boxes of node `ref` against the leaf's current best t (inclusive: a
-// node holding a triangle with t == lt but a lower index must be visited), go to the nearer one, stack the other.
-__device__ __forceinline__ uint32_t sub_inner_step(const BlasDesc& B, uint32_t ref, const RayM& r, float lt, TStack& S, int& sp, int sp0, Stat& st) {
-    st.add(6);
-    const float4* n = B.sub_nodes + (size_t)ref * 4;
-    float4 a = ldg4(n + 0);   // child0 lo.xyz (or centre), child0 ref
-    float4 b = ldg4(n + 1);   // child0 hi.xyz (or half extent), child1 ref
-    float4 c = ldg4(n + 2);   // child1
-    float4 d = ldg4(n + 3);
-    float t0, t1;
-#if BVHT_SUB_CH
-    bool h0 = slab_test_ch(a, b, r, lt, t0);
-    bool h1 = slab_test_ch(c, d, r, lt, t1);
-#else
-    bool h0 = slab_test_sub(a, b, r, lt, t0);
-    bool h1 = slab_test_sub(c, d, r, lt, t1);
-#endif
-    uint32_t r0 = __float_as_uint(a.w), r1 = __float_as_uint(b.w);
-    if (h0 && h1) {
-        bool swap = t1 < t0;
-        uint32_t nearr = swap ? r1 : r0, farr = swap ? r0 : r1;
-#if BVHT_POPCULL
-        S.putt(sp, swap ? t0 : t1);
-#endif
-        S.put(sp++, farr);
-        return nearr;
-    }
-    if (h0) return r0;
-    if (h1) return r1;
-    return sub_pop(S, sp, sp0, lt);
-}
-
 // Leaf accelerator: conservative sub-BVH built by us over the triangles of one oversized reference leaf
 // (leaf_accel.hpp).  The reference's result for a leaf is the lexicographic minimum (t, primitive index)
 // over the triangles that Triangle::intersect accepts with t < closest-at-entry, because the leaf loop
 // tests against the ENTRY ray (bvh.rs:251) and accepts with strict '<' in ascending index order.  Any
 // visiting order gives that same answer as long as no accepting triangle is skipped, which the
 // pre-inflated boxes guarantee under the bound checked by the caller (DESIGN.md "Leaf accelerator").
-//
-// Because the order is free, the walk is arranged for the WARP: box steps and triangle tests are the two halves of the
-// work (profiles/: 28 % and 27 % of the kernel's instructions) and, met in one loop, they serialise -- the triangle tests
-// ran with 7 of 32 lanes.  Here a lane that reaches a leaf parks it (`pending`) and goes on with the next stack entry;
-// the parked triangles are tested together once enough lanes hold one (BVHT_POSTPONE) or nobody can go on.  Going on
-// before the parked triangle has shrunk lt can only visit MORE nodes, never fewer.
 __device__ __forceinline__ void leaf_accel(const BlasDesc& B, uint32_t sub_root, const RayM& r, float entry_t,
-                                           float& best_t, float& best_u, float& best_v, uint32_t& best_prim, bool& found, Stat& st,
-                                           TStack& S, const int sp0) {
+                                           float& best_t, float& best_u, float& best_v, uint32_t& best_prim, bool& found, Stat& st) {
     // within this leaf: lt/lu/lv/lp = lexicographic-min candidate; ties with the entry value are rejected
     // because lp starts at 0 (no index is < 0) while lt starts at the closest-at-entry value.
     float lt = best_t, lu = 0.0f, lv = 0.0f;
     uint32_t lp = 0u;
     bool lfound = false;
-    int sp = sp0;
+    uint32_t stack[kSubStack];
+    int sp = 0;
     uint32_t ref = sub_root;
-#if BVHT_POSTPONE && BVHT_POSTPONE_SPEC
-    const unsigned grp = __activemask();          // the lanes that arrived together; every exit below is uniform over them
-    uint32_t pending = 0u;                        // a parked leaf ref (bit 31 set, so never 0)
     for (;;) {
-        for (;;) {
-            if (ref < kSubDone) {
-                ref = sub_inner_step(B, ref, r, lt, S, sp, sp0, st);
-            } else if (ref != kSubDone && pending == 0u) {
-                pending = ref;
-                ref = sub_pop(S, sp, sp0, lt);
+        if (ref & 0x80000000u) {
+            // leaf ref: [30:28] = count-1, [27:0] = first triangle in sub order
+            uint32_t first = ref & 0x0FFFFFFFu;
+            uint32_t cnt = ((ref >> 28) & 7u) + 1u;
+            st.add(7, cnt);
+            const float4* tp = B.stri + 3 * (size_t)first;
+            for (uint32_t k = 0; k < cnt; ++k, tp += 3) {
+                float4 v0 = ldg4(tp + 0);
+                float4 e1 = ldg4(tp + 1);
+                float4 e2 = ldg4(tp + 2);
+                MtPartial mp;
+                if (mt_filter(v0, e1, e2, r, mp)) {
+                    float t, u, v;
+                    if (mt_finish(e1, e2, r, mp, entry_t, t, u, v)) {
+                        uint32_t pi = __float_as_uint(v0.w);
+                        if (t < lt || (t == lt && pi < lp)) { lt = t; lu = u; lv = v; lp = pi; lfound = true; }
+                    }
+                }
             }
-            const bool can = ref < kSubDone || (ref != kSubDone && pending == 0u);
-            const unsigned canm = __ballot_sync(grp, can);
-            if (canm == 0u) break;
-            const unsigned pend = __ballot_sync(grp, pending != 0u);
-            if (__popc(pend) * 8 >= __popc(canm | pend) * BVHT_POSTPONE) break;
-        }
-        if (pending != 0u) {
-            sub_triangles(B, pending, r, entry_t, lt, lu, lv, lp, lfound, st);
-            pending = 0u;
-        }
-        if (!__any_sync(grp, ref != kSubDone)) break;
-    }
-#elif BVHT_POSTPONE
-    // blocking form: a lane that reaches a leaf waits there until enough lanes wait with it
-    const unsigned grp = __activemask();
-    for (;;) {
-        for (;;) {
-            if (ref < kSubDone) ref = sub_inner_step(B, ref, r, lt, S, sp, sp0, st);
-            const unsigned canm = __ballot_sync(grp, ref < kSubDone);
-            if (canm == 0u) break;
-            const unsigned atleaf = __ballot_sync(grp, ref > kSubDone);
-            if (__popc(atleaf) * 8 >= __popc(canm | atleaf) * BVHT_POSTPONE) break;
-        }
-        if (ref > kSubDone) {
-            sub_triangles(B, ref, r, entry_t, lt, lu, lv, lp, lfound, st);
-            ref = sub_pop(S, sp, sp0, lt);
-        }
-        if (!__any_sync(grp, ref != kSubDone)) break;
-    }
+            if (sp == 0) break;
+            ref = stack[--sp];
+        } else {
+            st.add(6);
+            const float4* n = B.sub_nodes + (size_t)ref * 4;
+            float4 a = ldg4(n + 0);   // child0 lo.xyz, child0 ref
+            float4 b = ldg4(n + 1);   // child0 hi.xyz, child1 ref
+            float4 c = ldg4(n + 2);   // child1 lo.xyz
+            float4 d = ldg4(n + 3);   // child1 hi.xyz
+            float t0, t1;
+            // inclusive comparisons: a node holding a triangle with t == lt but a lower index must be visited
+#if BVHT_SUB_CH
+            bool h0 = slab_test_ch(a, b, r, lt, t0);
+            bool h1 = slab_test_ch(c, d, r, lt, t1);
 #else
-    for (;;) {
-        if (ref < kSubDone) {
-            ref = sub_inner_step(B, ref, r, lt, S, sp, sp0, st);
-        } else if (ref != kSubDone) {
-            sub_triangles(B, ref, r, entry_t, lt, lu, lv, lp, lfound, st);
-            ref = sub_pop(S, sp, sp0, lt);
-        } else break;
-    }
+            bool h0 = slab_test_sub(a, b, r, lt, t0);
+            bool h1 = slab_test_sub(c, d, r, lt, t1);
 #endif
+            uint32_t r0 = __float_as_uint(a.w), r1 = __float_as_uint(b.w);
+            if (h0 && h1) {
+                bool swap = t1 < t0;
+                uint32_t nearr = swap ? r1 : r0, farr = swap ? r0 : r1;
+                stack[sp++] = farr;
+                ref = nearr;
+            } else if (h0) {
+                ref = r0;
+            } else if (h1) {
+                ref = r1;
+            } else {
+                if (sp == 0) break;
+                ref = stack[--sp];
+            }
+        }
+    }
     if (lfound) { best_t = lt; best_u = lu; best_v = lv; best_prim = lp; found = true; }
 }
 
@@ -488,70 +329,22 @@ __device__ __forceinline__ void leaf_accel(const BlasDesc& B, uint32_t sub_root,
 // ray's current closest, scene_object.rs:87).  On return `found` says whether a strictly closer hit exists.
 template <bool ACCEL>
 __device__ __forceinline__ void blas_intersect(const BlasDesc& B, const RayM& r, float entry_t, bool use_accel,
-                                               float& best_t, float& best_u, float& best_v, uint32_t& best_prim, bool& found, Stat& st,
-                                               TStack& S, const int sp0) {
+                                               float& best_t, float& best_u, float& best_v, uint32_t& best_prim, bool& found, Stat& st) {
     best_t = entry_t;
     found = false;
 #ifdef BVHT_FAST_MODE
     if (ACCEL && use_accel && B.leaf_sub_root == nullptr) {
         // fast mode: one sub-BVH over the whole model (sub node 0), closest hit = lexicographic min (t, primitive index)
         st.add(4);
-        leaf_accel(B, 0u, r, entry_t, best_t, best_u, best_v, best_prim, found, st, S, sp0);
+        leaf_accel(B, 0u, r, entry_t, best_t, best_u, best_v, best_prim, found, st);
         return;
     }
 #endif
-    int sp = sp0;
+    uint32_t stack[kBlasStack];
+    int sp = 0;
     uint32_t ni = 0;                       // root: its AABB is never tested (bvh.rs:243)
     float4 n0 = ldg4(B.nodes + 0);
     float4 n1 = ldg4(B.nodes + 1);
-#if BVHT_BLAS_WW
-    bool live = true;
-    for (;;) {
-        // every lane walks on to its next reference leaf (or to the end of its walk) ...
-        while (live && __float_as_uint(n1.w) == 0u) {
-            uint32_t lf = __float_as_uint(n0.w);
-            st.add(3);
-            const float4* c = B.nodes + 2 * (size_t)lf;
-            float4 l0 = ldg4(c + 0), l1 = ldg4(c + 1), r0 = ldg4(c + 2), r1 = ldg4(c + 3);
-            float ld, rd;
-            bool lh = slab_test(l0, l1, r, best_t, ld);
-            bool rh = slab_test(r0, r1, r, best_t, rd);
-            float lkey = lh ? ld : FLT_MAX;
-            float rkey = rh ? rd : FLT_MAX;
-            bool left_first = lkey < rkey;         // ties and double-miss: right first (bvh.rs:271-275)
-            bool near_hit = left_first ? lh : rh;
-            bool far_hit = left_first ? rh : lh;
-            if (near_hit) {
-                if (far_hit) S.put(sp++, left_first ? lf + 1 : lf);
-                if (left_first) { ni = lf; n0 = l0; n1 = l1; } else { ni = lf + 1; n0 = r0; n1 = r1; }
-            } else if (sp > sp0) {
-                ni = S.get(--sp);
-                n0 = ldg4(B.nodes + 2 * (size_t)ni);
-                n1 = ldg4(B.nodes + 2 * (size_t)ni + 1);
-            } else live = false;
-        }
-        // ... and the lanes that found one work on their leaves together
-        if (!live) break;
-        {
-            uint32_t count = __float_as_uint(n1.w);
-            uint32_t lf = __float_as_uint(n0.w);
-            bool done = false;
-            st.add(4);
-            if (ACCEL) {
-                if (use_accel) {
-                    uint32_t sr = __ldg(B.leaf_sub_root + ni);
-                    if (sr != 0xFFFFFFFFu) { leaf_accel(B, sr, r, entry_t, best_t, best_u, best_v, best_prim, found, st, S, sp); done = true; }
-                }
-            }
-            if (!done) leaf_brute(B, lf, count, r, entry_t, best_t, best_u, best_v, best_prim, found, st);
-            if (sp > sp0) {
-                ni = S.get(--sp);
-                n0 = ldg4(B.nodes + 2 * (size_t)ni);
-                n1 = ldg4(B.nodes + 2 * (size_t)ni + 1);
-            } else break;
-        }
-    }
-#else
     for (;;) {
         uint32_t count = __float_as_uint(n1.w);
         uint32_t lf = __float_as_uint(n0.w);
@@ -561,12 +354,12 @@ __device__ __forceinline__ void blas_intersect(const BlasDesc& B, const RayM& r,
             if (ACCEL) {
                 if (use_accel) {
                     uint32_t sr = __ldg(B.leaf_sub_root + ni);
-                    if (sr != 0xFFFFFFFFu) { leaf_accel(B, sr, r, entry_t, best_t, best_u, best_v, best_prim, found, st, S, sp); done = true; }
+                    if (sr != 0xFFFFFFFFu) { leaf_accel(B, sr, r, entry_t, best_t, best_u, best_v, best_prim, found, st); done = true; }
                 }
             }
             if (!done) leaf_brute(B, lf, count, r, entry_t, best_t, best_u, best_v, best_prim, found, st);
-            if (sp == sp0) break;
-            ni = S.get(--sp);
+            if (sp == 0) break;
+            ni = stack[--sp];
             n0 = ldg4(B.nodes + 2 * (size_t)ni);
             n1 = ldg4(B.nodes + 2 * (size_t)ni + 1);
         } else {
@@ -583,17 +376,16 @@ __device__ __forceinline__ void blas_intersect(const BlasDesc& B, const RayM& r,
             bool near_hit = left_first ? lh : rh;
             bool far_hit = left_first ? rh : lh;
             if (near_hit) {
-                if (far_hit) S.put(sp++, left_first ? lf + 1 : lf);
+                if (far_hit) stack[sp++] = left_first ? lf + 1 : lf;
                 if (left_first) { ni = lf; n0 = l0; n1 = l1; } else { ni = lf + 1; n0 = r0; n1 = r1; }
                 continue;
             }
-            if (sp == sp0) break;
-            ni = S.get(--sp);
+            if (sp == 0) break;
+            ni = stack[--sp];
             n0 = ldg4(B.nodes + 2 * (size_t)ni);
             n1 = ldg4(B.nodes + 2 * (size_t)ni + 1);
         }
     }
-#endif
 }
 
 // scene/tlas.rs:123-177 + scene_object.rs:78-89.  World ray (ox..dz, recip), initial t = tmax.
@@ -609,7 +401,7 @@ __device__ __forceinline__ void blas_intersect(const BlasDesc& B, const RayM& r,
 // for finite reciprocals (rounding of (b - o) * rd is monotonic in b), so "every box of the chain is hit" <=> "the
 // last one is hit": one slab test replaces the chain.  Rays with a non-finite reciprocal take the plain walk.
 template <bool ACCEL, bool PRUNE = false>
-__device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM& w, float tmax, uint32_t cand, Stat& st, TStack& K,
+__device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM& w, float tmax, uint32_t cand, Stat& st,
                                                   const uint8_t* skip = nullptr, const float4* origins = nullptr) {
     // cand (ACCEL): bit i clear = instance i cannot be hit by this ray (tile-level screen rectangles); all ones = unknown
     st.add(0);
@@ -617,6 +409,7 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
     best.t = FLT_MAX; best.u = 0.0f; best.v = 0.0f; best.id = 0xFFFFFFFFu;
     float closest = tmax;
     bool have = false;
+    uint32_t stack[kTlasStack];
     int sp = 0;
     float4 n0 = ldg4(S.tlas + 0);
     float4 n1 = ldg4(S.tlas + 1);
@@ -661,7 +454,7 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
                     if (ok) ok = slab_test(n0, n1, w, closest, tt);
                     if (!ok) {
                         if (sp == 0) break;
-                        cur = K.get(--sp);
+                        cur = stack[--sp];
                         n0 = ldg4(S.tlas + 2 * (size_t)cur);
                         n1 = ldg4(S.tlas + 2 * (size_t)cur + 1);
                         continue;
@@ -710,7 +503,7 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
             }
             st.add(2);
             float bt, bu, bv; uint32_t bp; bool found;
-            blas_intersect<ACCEL>(B, r, closest, use_accel, bt, bu, bv, bp, found, st, K, sp);
+            blas_intersect<ACCEL>(B, r, closest, use_accel, bt, bu, bv, bp, found, st);
             if (found && bt < closest) {                                     // tlas.rs:131
                 closest = bt;
                 best.t = bt; best.u = bu; best.v = bv;
@@ -719,7 +512,7 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
                 have = true;
             }
             if (sp == 0) break;
-            uint32_t ni = K.get(--sp);
+            uint32_t ni = stack[--sp];
             cur = ni;
             n0 = ldg4(S.tlas + 2 * (size_t)ni);
             n1 = ldg4(S.tlas + 2 * (size_t)ni + 1);
@@ -763,7 +556,7 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
             bool near_hit = left_first ? lh : rh;
             bool far_hit = left_first ? rh : lh;
             if (near_hit) {
-                if (far_hit) K.put(sp++, left_first ? ri : li);
+                if (far_hit) stack[sp++] = left_first ? ri : li;
                 if (left_first) { n0 = l0; n1 = l1; cur = li; } else { n0 = r0; n1 = r1; cur = ri; }
                 continue;
             }
@@ -774,7 +567,7 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
                 }
             }
             if (sp == 0) break;
-            uint32_t ni = K.get(--sp);
+            uint32_t ni = stack[--sp];
             cur = ni;
             n0 = ldg4(S.tlas + 2 * (size_t)ni);
             n1 = ldg4(S.tlas + 2 * (size_t)ni + 1);
@@ -950,7 +743,6 @@ __global__ void __launch_bounds__(128, BVHT_MIN_BLOCKS)
 trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
     const unsigned lane = threadIdx.x & 31u;
     Stat st;
-    BVHT_DECLARE_STACK(K)
     __shared__ uint8_t s_skip[PRUNE ? 4 : 1][64];
     // with a work list (K0 ran first) only the listed blocks are pulled; the others already hold their miss records
     const unsigned n_work = P.work_list ? __ldcg(P.work_count) : P.n_items;
@@ -1006,7 +798,7 @@ trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
                 st.add(0);
             } else {
                 RayM w = primary_ray(P.cam, px, py, P.width, P.height);
-                h = scene_intersect<ACCEL, PRUNE>(P.scene, w, FLT_MAX, cand, st, K, skip, P.n_origin ? P.inst_origin : nullptr);
+                h = scene_intersect<ACCEL, PRUNE>(P.scene, w, FLT_MAX, cand, st, skip, P.n_origin ? P.inst_origin : nullptr);
             }
             if (P.out) {
                 uint4 o;
@@ -1098,7 +890,6 @@ __global__ void __launch_bounds__(128, BVHT_MIN_BLOCKS)
 trace_rays_kernel(const __grid_constant__ RaysParams P) {
     const unsigned lane = threadIdx.x & 31u;
     Stat st;
-    BVHT_DECLARE_STACK(K)
     const uint64_t n_items = (P.n + 31u) / 32u;
     for (;;) {
         unsigned item = 0;
@@ -1113,7 +904,7 @@ trace_rays_kernel(const __grid_constant__ RaysParams P) {
             w.dx = __ldg(rp + 3); w.dy = __ldg(rp + 4); w.dz = __ldg(rp + 5);
             float t = __ldg(rp + 6);
             w.rdx = __fdiv_rn(1.0f, w.dx); w.rdy = __fdiv_rn(1.0f, w.dy); w.rdz = __fdiv_rn(1.0f, w.dz);
-            HitRec h = scene_intersect<ACCEL>(P.scene, w, t, 0xFFFFFFFFu, st, K);
+            HitRec h = scene_intersect<ACCEL>(P.scene, w, t, 0xFFFFFFFFu, st);
             uint4 o;
             o.x = __float_as_uint(h.t); o.y = __float_as_uint(h.u); o.z = __float_as_uint(h.v); o.w = h.id;
             P.out[i] = o;

@@ -57,6 +57,10 @@ class Engine:
         """Only tile rows r with r % count == index are traced by the *_device entry points (multi-GPU)."""
         self._check(self._lib.bvht_set_shard(self._ctx, int(index), int(count)))
 
+    def set_option(self, option, value):
+        """bvht_set_option: scheduling overrides (coverage raster, K0, bands); value < 0 = the library's own rule."""
+        self._check(self._lib.bvht_set_option(self._ctx, int(option), int(value)))
+
     def sync(self):
         self._check(self._lib.bvht_sync(self._ctx))
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BVHT_ABI_VERSION 3
+#define BVHT_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define BVHT_API __attribute__((visibility("default")))
@@ -162,6 +162,15 @@ BVHT_API const char* bvht_status_string(int status);
 /* Use an existing CUDA stream (cudaStream_t as void*) for all work of this ctx; NULL = the ctx's own. */
 BVHT_API int         bvht_set_stream(bvht_ctx* ctx, void* cuda_stream);
 BVHT_API int         bvht_sync(bvht_ctx* ctx);
+
+/* Execution options.  None of them changes a result (tests/ force each both ways and compare with the oracle); they only
+ * override how a frame is scheduled on the device.  value < 0 restores the library's own rule.  No reference counterpart. */
+typedef enum bvht_option {
+    BVHT_OPT_COVER = 1,   /* per-triangle block coverage raster before the trace (K7): 0 off, 1 on */
+    BVHT_OPT_K0    = 2,   /* classify-and-fill pass for empty pixel blocks (K0): 0 off, 1 on */
+    BVHT_OPT_BANDS = 3    /* number of tile-row bands bvht_render_frame pipelines against its device->host copies (1..16) */
+} bvht_option;
+BVHT_API int         bvht_set_option(bvht_ctx* ctx, uint32_t option, int32_t value);
 
 /* Upload one model: the BVH-reordered triangle buffer `Mesh::primitives()` (mesh.rs:126-134; n_tris x 9 f32,
  * 36-byte stride) and the used prefix of `Bvh.nodes` (bvh.rs:228-233).  Replaces what

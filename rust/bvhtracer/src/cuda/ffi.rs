@@ -58,6 +58,8 @@ extern "C" {
     pub fn bvht_destroy(ctx: *mut BvhtCtx);
     pub fn bvht_last_error(ctx: *const BvhtCtx) -> *const c_char;
     pub fn bvht_status_string(status: c_int) -> *const c_char;
+    /// scheduling overrides (1 = coverage raster, 2 = K0, 3 = bands); never changes a result; value < 0 = the library's rule
+    pub fn bvht_set_option(ctx: *mut BvhtCtx, option: u32, value: i32) -> c_int;
     pub fn bvht_blas_create(ctx: *mut BvhtCtx, tris: *const f32, n_tris: u32, nodes: *const BvhtBvhNode, nodes_used: u32, out_id: *mut u32) -> c_int;
     pub fn bvht_blas_build(ctx: *mut BvhtCtx, tris: *const f32, n_tris: u32, out_id: *mut u32) -> c_int;
     pub fn bvht_blas_rebuild(ctx: *mut BvhtCtx, id: u32) -> c_int;

@@ -31,7 +31,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 def test_abi_version_and_struct_sizes():
     lib = _ffi.load()
-    assert lib.bvht_abi_version() == 3
+    assert lib.bvht_abi_version() == 4
     assert _ffi.BVH_NODE.itemsize == 32          # bvh.rs:720-723
     assert _ffi.TLAS_NODE.itemsize == 32
     assert _ffi.HIT.itemsize == 16               # intersection.rs:77-83
@@ -56,3 +56,22 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".inc")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle_lib" not in text and "liboracle" not in text and "bvht_oracle" not in text, f
+
+
+def test_release_library_reads_no_environment():
+    # the tuning / diagnostic knobs (Knobs in csrc/bvht_api.cu) exist only in -DBVHT_EXPERIMENT builds: the product library
+    # must hold none of their environment names, so that no variable can change what a frame computes or how it is copied back
+    blob = open(bvht_build.build(), "rb").read()
+    src = open(os.path.join(ROOT, "bvhtracer_b200", "csrc", "bvht_api.cu")).read()
+    names = sorted(set(re.findall(r'"(BVHT_[A-Z0-9_]+)"', src)))
+    assert len(names) >= 15, names
+    for n in names:
+        assert n.encode() not in blob, f"{n} is compiled into the release library"
+    for unit in ("bvht_api.cu", "cover_kernels.cu", "upload_kernels.cu", "refit_kernels.cu", "scene_kernels.cu", "build_kernels.cu",
+                 "leaf_accel.cpp", "trace_kernels.cuh"):
+        text = open(os.path.join(ROOT, "bvhtracer_b200", "csrc", unit)).read()
+        if unit != "bvht_api.cu":
+            assert "getenv" not in text, unit
+        else:
+            body = text[text.index("static Knobs read_knobs()"):]
+            assert "getenv" not in body[body.index("\n}\n"):], "getenv outside read_knobs()"

@@ -857,13 +857,49 @@ def test_tlas_with_boxes_that_are_not_nested_takes_the_plain_walk():
         assert_strict(got, ref)
 
 
+def test_tlas_garbage_in_unreachable_slots_is_ignored():
+    # Tlas::rebuild leaves a slot the walk never reaches (the last merged node is COPIED into node 0, tlas.rs:248), and a caller's
+    # pool may hold anything there.  The per-node device tables (instance masks, chain-skip table) index through every slot, so
+    # the upload neutralises unreachable ones: child indices far out of range there must neither fault nor change a record.
+    rng = np.random.default_rng(12)
+    blases = [SB.oracle_blas("teapot.obj"), SB.oracle_blas("cube.obj")]
+    for n in (5, 24):                                   # shuffle build and shared-memory build of the skip table
+        scene = O.Scene(blases, _random_instances(rng, n, 2.5))
+        cam = O.camera_symmetric_fov(90.0, 1.0, 1.0, [0, 0, -6], [0, 0, 1], [1, 0, 0], [0, 1, 0])
+        w, h = 400, 232
+        ref = scene.render(cam, w, h, threads=NTHREADS)
+        tl = scene.tlas.view(_ffi.TLAS_NODE).copy()
+        reach, todo = set(), [0]
+        while todo:
+            i = todo.pop()
+            reach.add(i)
+            lr = int(tl["left_right"][i])
+            if lr:
+                todo += [lr >> 16, lr & 0xFFFF]
+        dead = [i for i in range(scene.tlas_used) if i not in reach]
+        assert dead, "expected at least one unreachable slot"
+        for i in dead:
+            tl["left_right"][i] = 0xFFFEFFFD             # children 65534 / 65533
+            tl["blas"][i] = 0xFFFFFFFF
+            tl["aabb_min"][i] = np.nan
+        inst = np.zeros(len(scene.inst), _ffi.INSTANCE)
+        for flags in STRICT_MODES:
+            with Engine(flags=flags) as eng:
+                ids = [eng.blas_create(b.tris, b.nodes.view(_ffi.BVH_NODE), b.nodes_used) for b in scene.blases]
+                inst["transform_inv"] = scene.inst["inv"]
+                inst["blas_id"] = [ids[int(b)] for b in scene.inst["blas_id"]]
+                eng.tlas_set(tl, scene.tlas_used, inst)
+                assert_strict(eng.trace_primary(SB.to_ffi_camera(cam), w, h), ref)
+                frame, hits = eng.render_frame(SB.to_ffi_camera(cam), w, h, Engine.shade_depth(80.0, 3.0), want_hits=True)
+                assert hits.tobytes() == ref.tobytes()
+
+
 # ------------------------------------------------------------------------------------------ K0: classify + fill
-@pytest.mark.parametrize("k0", ["0", "1"])
-def test_k0_classify_fill_equals_single_kernel(k0, monkeypatch):
+@pytest.mark.parametrize("k0", [0, 1])
+def test_k0_classify_fill_equals_single_kernel(k0):
     # K0 (classify_fill_kernel) writes the records of blocks no instance can be seen from and lists the others for K1.
-    # Forced on and off (BVHT_K0): hit records AND shaded frames must equal the oracle either way -- ragged tile sizes,
+    # Forced on and off (bvht_set_option): hit records AND shaded frames must equal the oracle either way -- ragged tile sizes,
     # sub-regions, tile-row shards into one buffer.
-    monkeypatch.setenv("BVHT_K0", k0)
     rng = np.random.default_rng(21)
     blases = [SB.oracle_blas("teapot.obj"), SB.oracle_blas("cube.obj")]
     scene = O.Scene(blases, _random_instances(rng, 7, 2.5))
@@ -871,6 +907,7 @@ def test_k0_classify_fill_equals_single_kernel(k0, monkeypatch):
     w, h = 403, 229
     fcam = SB.to_ffi_camera(cam)
     with Engine(flags=FLAG_STRICT | FLAG_LEAF_ACCEL) as eng:
+        eng.set_option(_ffi.OPT_K0, k0)
         SB.upload_scene(eng, scene)
         for tile in (8, 5, 16):
             ref = scene.render(cam, w, h, tile=tile, threads=NTHREADS)
@@ -892,14 +929,13 @@ def test_k0_classify_fill_equals_single_kernel(k0, monkeypatch):
 
 
 # ------------------------------------------------------------------------------------------ per-triangle block coverage
-@pytest.mark.parametrize("cover", ["0", "1"])
+@pytest.mark.parametrize("cover", [0, 1])
 @pytest.mark.parametrize("camera_z,n,seed", [(-7.0, 7, 31), (-2.2, 9, 32), (-0.4, 12, 33)])
-def test_coverage_raster_equals_plain_trace(cover, camera_z, n, seed, monkeypatch):
+def test_coverage_raster_equals_plain_trace(cover, camera_z, n, seed):
     # cover_kernels.cu marks, per 8x4 block, the instances whose (conservatively grown) triangle boxes project onto it; the trace
-    # kernels drop the other instances from the block's candidates.  Forced on and off (BVHT_COVER): records and shaded frames
+    # kernels drop the other instances from the block's candidates.  Forced on and off (bvht_set_option): records and shaded frames
     # equal the oracle either way -- also with the camera INSIDE the cloud of instances (boxes behind / across the eye plane
     # make an instance "visible everywhere"), with rotated instances, sub-regions and the banded host path.
-    monkeypatch.setenv("BVHT_COVER", cover)
     rng = np.random.default_rng(seed)
     blases = [SB.oracle_blas("teapot.obj"), SB.oracle_blas("cube.obj")]
     scene = O.Scene(blases, _random_instances(rng, n, 2.5))
@@ -909,6 +945,7 @@ def test_coverage_raster_equals_plain_trace(cover, camera_z, n, seed, monkeypatc
     ref = scene.render(cam, w, h, threads=NTHREADS)
     assert (ref["id"] != O.MISS_ID).mean() > 0.01
     with Engine(flags=FLAG_STRICT | FLAG_LEAF_ACCEL) as eng:
+        eng.set_option(_ffi.OPT_COVER, cover)
         SB.upload_scene(eng, scene)
         for _ in range(2):
             assert_strict(eng.trace_primary(fcam, w, h), ref)

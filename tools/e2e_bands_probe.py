@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """End-to-end frame time of Renderer::render (C3 4K, frames 9..32) for given band counts: python tools/e2e_bands_probe.py 1 4 7
-(BVHT_BAND_SHAPE, BVHT_BANDS_IMAGE_ORDER, BVHT_DEBUG_NO_D2H and PROBE_KEEP_HITS=1 select what is compared)."""
+(PROBE_KEEP_HITS=1 also returns the hit records; with an experiment build of the library -- tools/build_variants.py
+exp:BVHT_EXPERIMENT -- BVHT_BAND_SHAPE, BVHT_BANDS_IMAGE_ORDER and BVHT_DEBUG_NO_D2H select what else is compared)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -15,7 +16,7 @@ state = host.RendererState(host.depth_pipeline(), w, h, keep_hits=keep_hits)
 for _ in range(8):
     anim.update()
 for bands in sys.argv[1:]:
-    os.environ["BVHT_BANDS"] = bands
+    eng.set_option(3, int(bands))      # BVHT_OPT_BANDS
     a2 = examples.GridAnimation()
     for _ in range(8): a2.update()
     ts, dev = [], []

@@ -2,7 +2,8 @@
 """Empirical backing of the leaf accelerator's equivalence claim (GPU box): strict-accel vs strict-brute on many
 frames / cameras / random rays, bit-for-bit.  python tools/equivalence_sweep.py [quick]
 
-Also usable as a margin study: BVHT_C_MT=<c> scales the Moeller-Trumbore residual term of the box inflation
+Also usable as a margin study with an EXPERIMENT build of the library (tools/build_variants.py exp:BVHT_EXPERIMENT; the
+product library reads no environment): BVHT_C_MT=<c> scales the Moeller-Trumbore residual term of the box inflation
 (shipped value 80); the number of mismatching hit records as c goes to 0 shows how much slack the bound has."""
 import os
 import sys

@@ -52,14 +52,13 @@ r.intersect(scene4, far)
 print("device build ok", int(st3.frame_buffer().sum() % 1000), int(st4.frame_buffer().sum() % 1000))
 
 # K0 (classify + fill) forced on, the chain-skipping TLAS walk, and K6 (device set_transform + Tlas::rebuild)
-os.environ["BVHT_K0"] = "1"
 anim = examples.GridAnimation()
 scene5, _ = host.build_scene(examples.sixteen_armadillos(0))
 r5 = host.Renderer(flags=2)
+r5.engine().set_option(2, 1)      # BVHT_OPT_K0 forced on
 st5 = host.RendererState(host.depth_pipeline(), 200, 120, keep_hits=True)
 for f in range(3):
     anim.update()
     r5.update_transforms(scene5, [host.object_transform(o) for o in anim.objects()])
     r5.render(st5, scene5)
-os.environ.pop("BVHT_K0")
 print("k0 + k6 ok", int(st5.frame_buffer().sum() % 1000))
