@@ -1455,31 +1455,15 @@ int bvht_tlas_read(bvht_ctx* ctx, bvht_tlas_node* nodes_out, uint32_t max_nodes,
     return BVHT_OK;
 }
 
-// Whether the per-triangle coverage raster (K7) is worth its 35-160 us for this scene and camera.  A fixed rule, not a
-// measurement, so that which kernels a frame launches depends on the scene alone.  It pays when rays would otherwise enter
-// instances they cannot hit AND entering one is expensive: several instances whose screen rectangles overlap (sixteen_armadillos
-// 4K: -10..14 % of the frame) and large models; it does not for small models (trippy_teapots: +6..10 %), for one instance
-// (big_ben_clock: K0 with the model's rectangle already removes the empty blocks) or for instances side by side.
-static bool cover_wanted(const bvht_ctx* ctx, const bvht_camera* cam, uint32_t width, uint32_t height, uint32_t n_inst, uint32_t tris) {
-    if (ctx->knobs.cover >= 0) return ctx->knobs.cover == 1;            // experiment builds only
-    if (n_inst < 2 || tris / n_inst < 8192u) return false;
-    int4 rects[32]; uint32_t nr = 0;
-    if (!compute_instance_rects(ctx, cam, width, height, rects, nr) || nr == 0) return false;
-    constexpr int G = 32;
-    uint32_t any[G] = { 0 }; uint64_t sum = 0;
-    for (uint32_t i = 0; i < nr; ++i) {
-        const int4 rc = rects[i];
-        if (rc.z < rc.x || rc.w < rc.y) continue;
-        int cx0 = std::max(0, (int)((int64_t)std::max(rc.x, 0) * G / (int64_t)width)), cx1 = std::min(G - 1, (int)((int64_t)std::max(rc.z, 0) * G / (int64_t)width));
-        int cy0 = std::max(0, (int)((int64_t)std::max(rc.y, 0) * G / (int64_t)height)), cy1 = std::min(G - 1, (int)((int64_t)std::max(rc.w, 0) * G / (int64_t)height));
-        if (cx1 < cx0 || cy1 < cy0) continue;
-        uint32_t bits = (cx1 - cx0 == 31) ? 0xFFFFFFFFu : (((1u << (cx1 - cx0 + 1)) - 1u) << cx0);
-        for (int y = cy0; y <= cy1; ++y) any[y] |= bits;
-        sum += (uint64_t)(cx1 - cx0 + 1) * (cy1 - cy0 + 1);
-    }
-    uint64_t uni = 0;
-    for (int y = 0; y < G; ++y) uni += __builtin_popcount(any[y]);
-    return uni > 0 && 2 * sum >= 3 * uni;                                // the rectangles cover what they cover 1.5 times over
+// Whether the per-triangle coverage raster (K7) is worth its 35-160 us for this scene.  A fixed rule, not a measurement, so
+// that which kernels a frame launches depends on the scene alone.  It pays when a block's rays would otherwise enter an
+// instance they cannot hit AND entering one is expensive: several instances of large models (measured on B200,
+// tools/cover_ab.py, off -> on: sixteen_armadillos 4K 0.855 -> 0.785 ms, two_armadillos 1080p 0.257 -> 0.244 ms).  It does
+// not for small models (trippy_teapots 0.262 -> 0.297 ms, cube 0.023 -> 0.058 ms) nor for a single instance, where K0 with
+// the model's screen rectangle already removes the empty blocks (big_ben_clock 8K: 1.671 -> 1.675 ms).
+static bool cover_wanted(const bvht_ctx* ctx, uint32_t n_inst, uint32_t tris) {
+    if (ctx->knobs.cover >= 0) return ctx->knobs.cover == 1;            // bvht_set_option(BVHT_OPT_COVER)
+    return n_inst >= 2 && tris / n_inst >= 8192u;
 }
 
 // Rasterise every instance's triangles onto the 8x4-pixel blocks of the frame (cover_kernels.cu).  Once per frame, on
@@ -1503,7 +1487,7 @@ static int prepare_cover(bvht_ctx* ctx, const bvht_camera* cam, uint32_t width, 
             if (!rc0 && blocks <= (64ull << 20)) rc0 = ensure(ctx, ctx->work_list, blocks * 4);
             if (rc0) return rc0;
         }
-        if (!cover_wanted(ctx, cam, width, height, n_inst, tris)) return BVHT_OK;
+        if (!cover_wanted(ctx, n_inst, tris)) return BVHT_OK;
     }
     const float* tl = cam->top_left_eye; const float* tr = cam->top_right_eye; const float* bl = cam->bottom_left_eye;
     if (!(tl[2] < 0.0f) || tr[2] != tl[2] || bl[2] != tl[2] || tr[1] != tl[1] || bl[0] != tl[0]) return BVHT_OK;
@@ -1591,7 +1575,8 @@ static int prepare_cover(bvht_ctx* ctx, const bvht_camera* cam, uint32_t width, 
 // One persistent launch of K1 over `region` on `stream`, using work counter slot `slot`.
 static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvht_camera* camera, uint32_t width, uint32_t height,
                                  uint32_t tile, bvht_rect region, const bvht_shade_params* shade, void* hits_device,
-                                 void* rgba_device, cudaStream_t stream, int slot, uint32_t shard_index = 0, uint32_t shard_count = 1) {
+                                 void* rgba_device, cudaStream_t stream, int slot, uint32_t shard_index = 0, uint32_t shard_count = 1,
+                                 unsigned long long* stats_counters = nullptr) {
     PrimaryParams p;
     memset(&p, 0, sizeof p);
     p.scene = scene;
@@ -1710,8 +1695,13 @@ static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvh
         }
     }
     int grid = persistent_grid(ctx, true, n_items, accel_on(ctx) && p.n_tlas_nodes != 0u);
-    cudaError_t e = fast_on(ctx) ? launch_primary_fast(p, accel_on(ctx), grid, kTraceBlock, stream)
-                                 : launch_primary_strict(p, accel_on(ctx), grid, kTraceBlock, stream);
+    cudaError_t e;
+    if (stats_counters) {          // bvht_debug_trace_stats: the instrumented strict build of the same kernels, same launch shape
+        p.stats = stats_counters;
+        e = launch_primary_stats(p, accel_on(ctx), grid, kTraceBlock, stream);
+    } else
+    e = fast_on(ctx) ? launch_primary_fast(p, accel_on(ctx), grid, kTraceBlock, stream)
+                     : launch_primary_strict(p, accel_on(ctx), grid, kTraceBlock, stream);
     if (e != cudaSuccess) return fail(ctx, BVHT_ERR_CUDA, "trace_primary launch failed: %s", cudaGetErrorString(e));
     ctx->stats.kernel_launches += 1;
     ctx->stats.trace_grid = (uint32_t)grid;
@@ -2118,38 +2108,27 @@ int bvht_debug_trace_stats(bvht_ctx* ctx, const bvht_camera* camera, uint32_t wi
     memset(counters_out, 0, 16 * sizeof(uint64_t));
     if (region.x0 >= region.x1 || region.y0 >= region.y1) return BVHT_OK;
     if ((rc = ensure_bake(ctx, camera))) return rc;
-    PrimaryParams p;
-    memset(&p, 0, sizeof p);
-    if ((rc = fill_scene(ctx, p.scene))) return rc;
+    SceneDev scene;
+    if ((rc = fill_scene(ctx, scene))) return rc;
     if ((rc = ensure(ctx, ctx->out_buf, (size_t)width * height * sizeof(bvht_hit)))) return rc;
     DevBuf cnt;
     if ((rc = ensure(ctx, cnt, 16 * sizeof(uint64_t)))) return rc;
-    memcpy(p.cam.tl, camera->top_left_eye, 12); memcpy(p.cam.tr, camera->top_right_eye, 12);
-    memcpy(p.cam.bl, camera->bottom_left_eye, 12); memcpy(p.cam.vinv, camera->view_matrix_inv, 64);
-    p.width = width; p.height = height; p.tile = tile;
-    p.x0 = region.x0; p.y0 = region.y0; p.x1 = region.x1; p.y1 = region.y1;
-    p.tx0 = region.x0 / tile; p.ty0 = region.y0 / tile;
-    p.ntx = (region.x1 + tile - 1) / tile - p.tx0; p.nty = (region.y1 + tile - 1) / tile - p.ty0;
-    p.row_stride = 1;
-    p.items_per_tile = (tile * tile + 31u) / 32u;
-    p.n_items = p.ntx * p.nty * p.items_per_tile;
-    p.out = (uint4*)ctx->out_buf.p;
-    p.work_counter = (unsigned int*)ctx->work_counter.p;
-    p.stats = (unsigned long long*)cnt.p;
-    if (accel_on(ctx)) { uint32_t nr = 0; if (compute_instance_rects(ctx, camera, width, height, p.inst_rect, nr)) p.n_rect = nr; }
-    // chain skipping pays from three instances on (measured: pure overhead for 1-2 instances)
-    p.n_tlas_nodes = (p.n_rect >= 3 && ctx->tlas_nested && ctx->h_tlas.size() <= 64) ? (uint32_t)ctx->h_tlas.size() : 0u;
-    p.skip_rounds = 0;
-    while ((1u << p.skip_rounds) < ctx->tlas_depth) ++p.skip_rounds;
     cudaMemsetAsync(cnt.p, 0, 16 * sizeof(uint64_t), ctx->stream);
-    cudaMemsetAsync(ctx->work_counter.p, 0, 4, ctx->stream);
-    int per_sm = std::max(1, blocks_per_sm_primary_stats(accel_on(ctx), accel_on(ctx) && p.n_tlas_nodes != 0u, kTraceBlock));
-    cudaError_t e = launch_primary_stats(p, accel_on(ctx), ctx->sm_count * per_sm, kTraceBlock, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(counters_out, cnt.p, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaMemsetAsync(ctx->work_counter.p, 0, 8, ctx->stream);
+    // exactly the frame bvht_render_frame_device launches (coverage raster, K0, kernel flavour, shard), instrumented
+    rc = prepare_cover(ctx, camera, width, height, tile, ctx->stream);
+    if (!rc) rc = launch_primary_region(ctx, scene, camera, width, height, tile, region, nullptr, ctx->out_buf.p, nullptr, ctx->stream, 0,
+                                        ctx->shard_index, ctx->shard_count, (unsigned long long*)cnt.p);
+    ctx->cover_ready = false;
+    cudaError_t e = cudaSuccess;
+    if (!rc) e = cudaMemcpyAsync(counters_out, cnt.p, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
     release(cnt);
-    if (e != cudaSuccess) return fail(ctx, BVHT_ERR_CUDA, "debug stats launch failed: %s", cudaGetErrorString(e));
-    ctx->stats.kernel_launches += 1;
+    if (rc) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess) return fail(ctx, BVHT_ERR_CUDA, "debug stats launch failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    // [0] counts the rays K1 generated; add those of blocks it never generated a ray for (K0's and its own empty blocks)
+    const uint64_t region_rays = (uint64_t)(region.x1 - region.x0) * (region.y1 - region.y0) / ctx->shard_count;
+    counters_out[15] = region_rays;
     return BVHT_OK;
 }
 

@@ -56,11 +56,13 @@ struct HitRec { float t, u, v; uint32_t id; };
 // Per-thread work counters, compiled in only for the debug entry point (BVHT_STATS); otherwise an empty type
 // whose calls vanish.  Slots: 0 rays, 1 tlas pair tests, 2 instance entries, 3 reference BLAS pair tests,
 // 4 reference leaves visited, 5 brute-force triangle tests, 6 sub-BVH pair tests, 7 sub-BVH triangle tests,
-// 8 accel fallbacks (ray outside the inflation limits), 9 hits
+// 8 accel fallbacks (ray outside the inflation limits), 9 hits, 10 mt_finish evaluations, 11 chain heads resolved by the
+// skip table, 12 rays whose block saw no instance (no ray generated), 13 pixel blocks pulled by K1, 14 skip tables built
 #ifdef BVHT_STATS
+constexpr int kStatSlots = 15;
 struct Stat {
-    unsigned long long c[10];
-    __device__ __forceinline__ Stat() { for (int i = 0; i < 10; ++i) c[i] = 0; }
+    unsigned long long c[kStatSlots];
+    __device__ __forceinline__ Stat() { for (int i = 0; i < kStatSlots; ++i) c[i] = 0; }
     __device__ __forceinline__ void add(int i, unsigned n = 1) { c[i] += n; }
 };
 #else
@@ -245,6 +247,7 @@ __device__ __forceinline__ void leaf_brute(const BlasDesc& B, uint32_t base, uin
         MtPartial mp;
         if (mt_filter(v0, e1, e2, r, mp)) {
             float t, u, v;
+            st.add(10);
             if (mt_finish(e1, e2, r, mp, entry_t, t, u, v)) {
                 if (t < best_t) { best_t = t; best_u = u; best_v = v; best_prim = pi; found = true; }
             }
@@ -282,6 +285,7 @@ __device__ __forceinline__ void leaf_accel(const BlasDesc& B, uint32_t sub_root,
                 MtPartial mp;
                 if (mt_filter(v0, e1, e2, r, mp)) {
                     float t, u, v;
+                    st.add(10);
                     if (mt_finish(e1, e2, r, mp, entry_t, t, u, v)) {
                         uint32_t pi = __float_as_uint(v0.w);
                         if (t < lt || (t == lt && pi < lp)) { lt = t; lu = u; lv = v; lp = pi; lfound = true; }
@@ -442,7 +446,7 @@ __device__ __forceinline__ HitRec scene_intersect(const SceneDev& S, const RayM&
                 uint32_t sn = skip[cur];
                 if (sn != cur) {
                     // arrived at the head of a chain: only the box at its end decides (see above)
-                    st.add(1);
+                    st.add(11);
                     n0 = ldg4(S.tlas + 2 * (size_t)sn);
                     n1 = ldg4(S.tlas + 2 * (size_t)sn + 1);
                     bool ok = true;
@@ -768,6 +772,7 @@ trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
         uint32_t iu = p % P.tile, iv = p / P.tile;
         uint32_t px = tx * P.tile + iu, py = ty * P.tile + iv;
         bool active = (iv < P.tile) && px >= P.x0 && px < P.x1 && py >= P.y0 && py < P.y1;
+        if (lane == 0) st.add(13);
         uint32_t cand = 0xFFFFFFFFu;
         if (ACCEL) {
             if (P.n_rect) {
@@ -789,13 +794,14 @@ trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
             if (P.n_tlas_nodes != 0u && cand != 0u && cand != 0xFFFFFFFFu) {       // warp-uniform
                 build_tlas_skip(P.scene, P.n_tlas_nodes, P.skip_rounds, cand, s_skip[threadIdx.x >> 5], lane);
                 skip = s_skip[threadIdx.x >> 5];
+                if (lane == 0) st.add(14);
             }
         }
         if (active) {
             HitRec h;
             if (ACCEL && cand == 0u) {
                 h.t = FLT_MAX; h.u = 0.0f; h.v = 0.0f; h.id = 0xFFFFFFFFu;      // no instance can be seen from this block
-                st.add(0);
+                st.add(12);
             } else {
                 RayM w = primary_ray(P.cam, px, py, P.width, P.height);
                 h = scene_intersect<ACCEL, PRUNE>(P.scene, w, FLT_MAX, cand, st, skip, P.n_origin ? P.inst_origin : nullptr);
@@ -821,7 +827,7 @@ trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
       }
     }
 #ifdef BVHT_STATS
-    for (int i = 0; i < 10; ++i) {
+    for (int i = 0; i < kStatSlots; ++i) {
         unsigned long long v = st.c[i];
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
         if (lane == 0 && v) atomicAdd(P.stats + i, v);

@@ -239,8 +239,9 @@ class Engine:
     def trace_rays_device(self, rays_device_ptr, n, out_device_ptr):
         self._check(self._lib.bvht_trace_rays_device(self._ctx, C.c_void_p(rays_device_ptr), int(n), C.c_void_p(out_device_ptr)))
 
-    COUNTER_NAMES = ["rays", "tlas_pairs", "instance_entries", "blas_pairs", "ref_leaves", "brute_tris", "sub_pairs", "sub_tris",
-                     "accel_fallbacks", "hits"]
+    COUNTER_NAMES = ["rays_traced", "tlas_pairs", "instance_entries", "blas_pairs", "ref_leaves", "brute_tris", "sub_pairs", "sub_tris",
+                     "accel_fallbacks", "hits", "mt_finishes", "tlas_chain_heads", "rays_in_empty_blocks", "blocks_pulled", "skip_tables",
+                     "rays"]
 
     def debug_read_bandwidth(self, nbytes, passes=20):
         """GB/s of the library's streaming read kernel over an nbytes buffer (fits in L2 -> L2 bandwidth; >> L2 -> HBM)."""
@@ -249,7 +250,8 @@ class Engine:
         return float(g.value)
 
     def debug_trace_stats(self, camera, width, height, tile=8, region=None):
-        """Per-frame work counters of an instrumented strict kernel (not a product path)."""
+        """Per-frame work counters of the instrumented strict build, launched exactly like render_frame_device (coverage raster,
+        K0, kernel flavour).  "rays" = rays of the region; "rays_traced" = those K1 generated a ray for.  Not a product path."""
         camera = np.ascontiguousarray(camera)
         out = np.zeros(16, "<u8")
         x0, y0, x1, y1 = region if region is not None else (0, 0, width, height)

@@ -83,6 +83,7 @@ def lib():
             "bvhx_renderer_ctx": (_P, [_P]),
             "bvhx_renderer_free": (None, [_P]),
             "bvhx_state_new": (_P, [C.c_uint32, C.c_float, C.c_float, _P, _P, C.c_uint32, C.c_uint32, C.c_int]),
+            "bvhx_state_new_external": (_P, [C.c_uint32, C.c_float, C.c_float, _P, _P, C.c_uint32, C.c_uint32, _P]),
             "bvhx_state_free": (None, [_P]),
             "bvhx_state_frame": (_P, [_P]),
             "bvhx_state_hits": (_P, [_P]),
@@ -366,9 +367,17 @@ class SceneBuilder:
 class RendererState:
     """renderer.rs:76-102 with the accumulator + pixel shader pair given as a device shading pipeline."""
 
-    def __init__(self, shading, width, height, keep_hits=False):
+    def __init__(self, shading, width, height, keep_hits=False, frame=None):
+        """frame: a caller-owned page-locked uint32 array of width * height pixels to render into (e.g. one frame in POSIX shared
+        memory that several single-GPU processes fill, each the tile rows its integrator is sharded to)."""
         kind, scale, offset, hit, miss = shading
         self.width, self.height, self.keep_hits = int(width), int(height), bool(keep_hits)
+        self._frame = frame
+        if frame is not None:
+            assert frame.dtype == np.uint32 and frame.size == self.width * self.height and frame.flags["C_CONTIGUOUS"]
+            self._h = _nn(lib().bvhx_state_new_external(kind, scale, offset, (C.c_uint8 * 4)(*hit), (C.c_uint8 * 4)(*miss),
+                                                        self.width, self.height, _ffi.ptr(frame)))
+            return
         self._h = _nn(lib().bvhx_state_new(kind, scale, offset, (C.c_uint8 * 4)(*hit), (C.c_uint8 * 4)(*miss),
                                            self.width, self.height, int(keep_hits)))
 

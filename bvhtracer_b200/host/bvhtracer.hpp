@@ -643,6 +643,10 @@ class RendererState {
 public:
     RendererState(const ShadingPipeline& shading, size_t width, size_t height, bool keep_hits)
         : shading_(shading), width_(width), height_(height), keep_hits_(keep_hits) {}
+    // A frame buffer the caller owns (page-locked, width * height Rgba<u8>): several processes, one per GPU, can then share ONE
+    // frame in POSIX shared memory and each fill the tile rows its integrator is sharded to (bvht_set_shard).
+    RendererState(const ShadingPipeline& shading, size_t width, size_t height, uint32_t* external_frame)
+        : shading_(shading), width_(width), height_(height), keep_hits_(false), frame_(external_frame), external_(true) {}
     ~RendererState() { release(); }
     RendererState(const RendererState&) = delete;
     RendererState& operator=(const RendererState&) = delete;
@@ -668,7 +672,7 @@ public:
     bvht_hit* hits_mut() { return hits_; }
 private:
     void release() {
-        if (frame_) bvht_host_free(nullptr, frame_);
+        if (frame_ && !external_) bvht_host_free(nullptr, frame_);
         if (hits_) bvht_host_free(nullptr, hits_);
         frame_ = nullptr; hits_ = nullptr;
     }
@@ -677,6 +681,7 @@ private:
     bool keep_hits_;
     uint32_t* frame_ = nullptr;
     bvht_hit* hits_ = nullptr;
+    bool external_ = false;
 };
 
 // renderer.rs:104-106

@@ -175,6 +175,17 @@ BVHX_API void* bvhx_state_new(uint32_t kind, float scale, float offset, const ui
         return new RendererState(s, width, height, keep_hits != 0);
     }, nullptr);
 }
+BVHX_API void* bvhx_state_new_external(uint32_t kind, float scale, float offset, const uint8_t hit[4], const uint8_t miss[4], uint32_t width,
+                                       uint32_t height, uint32_t* frame) {
+    return guard([&]() -> void* {
+        ShadingPipeline s = kind == BVHT_SHADE_DEPTH ? ShadingPipeline::depth(scale, offset)
+                          : kind == BVHT_SHADE_INTERSECTION ? ShadingPipeline::intersection(hit, miss)
+                          : kind == BVHT_SHADE_NORMAL ? ShadingPipeline::normal()
+                          : kind == BVHT_SHADE_TEXTURE ? ShadingPipeline::texture() : ShadingPipeline::uv();
+        if (!frame) throw std::runtime_error("null external frame buffer");
+        return new RendererState(s, width, height, frame);
+    }, nullptr);
+}
 BVHX_API void bvhx_state_free(void* state) { delete (RendererState*)state; }
 BVHX_API const uint32_t* bvhx_state_frame(void* state) { return ((RendererState*)state)->frame_buffer(); }
 BVHX_API const bvht_hit* bvhx_state_hits(void* state) { return ((RendererState*)state)->hits(); }

@@ -304,7 +304,10 @@ BVHT_API int         bvht_get_stats(const bvht_ctx* ctx, bvht_stats* out);
 /* Debug: trace `region` once with an instrumented strict kernel and return per-frame work counters:
  * [0] rays, [1] TLAS pair tests, [2] instance entries, [3] reference BLAS pair tests, [4] reference leaves
  * visited, [5] brute-force triangle tests, [6] sub-BVH pair tests, [7] sub-BVH triangle tests,
- * [8] accel fallbacks, [9] hits, [10..15] reserved.  Not a product path. */
+ * [8] accel fallbacks, [9] hits, [10] Moeller-Trumbore evaluations that went past the filter, [11] TLAS chains resolved by the
+ * skip table, [12] rays of blocks K1 found empty (no ray generated), [13] pixel blocks K1 pulled, [14] skip tables built,
+ * [15] rays of the region (this shard's).  The frame is launched exactly as bvht_render_frame_device launches it (coverage
+ * raster, K0, kernel flavour).  Not a product path. */
 /* Measurement helper: read bandwidth (GB/s) of `passes` sweeps over a `bytes`-sized device buffer with this library's own
  * streaming kernel -- L2 -> SM delivery when the buffer fits in L2 (e.g. 32 MiB), HBM when it is much larger (e.g. 2 GiB).
  * bench.py records it next to MEASURED_PEAKS.json's HBM figure. */

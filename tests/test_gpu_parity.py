@@ -83,6 +83,13 @@ def test_quad_viewport_640(flags):
     outside = np.ones((640, 640), bool)
     outside[160:481, 160:481] = False
     assert (g["id"][outside] == O.MISS_ID).all()
+    # the two exact-edge lines (row 160: v == 0.25, column 480: u == 0.75), ray by ray: 16 of their 642 rays miss -- in f32 no
+    # arithmetic consistent with the reference's Triangle::intersect hits them all (tests/test_quad_edge_variants.py)
+    import test_quad_edge_variants as QV
+    pinned = QV.hits_for_variant(QV.edge_rays(), "div", "lr", "plain", "f_times")
+    got_edges = np.concatenate([g["id"][160, 160:481], g["id"][160:481, 480]]) != O.MISS_ID
+    assert np.array_equal(got_edges, pinned) and int((~got_edges).sum()) == 16
+    assert (g["id"][160:481, 160] != O.MISS_ID).all() and (g["id"][480, 160:481] != O.MISS_ID).all()     # left / bottom edges: all hit
 
 
 def test_triangle_and_aabb_kats_through_abi():

@@ -352,14 +352,12 @@ def test_scene_quad_bit_exact_depths():
 def test_scene_quad_entire_viewport_mask():
     # tests/test_scene_quad.rs:355-377: 640 x 640 rays, hit iff (u, v) inside the quad's solid angle.
     #
-    # KNOWN UNPINNED POINT.  409,584 of 409,600 pixels reproduce the reference's expectation.  The other 16 lie
-    # exactly on the quad's top edge (row 160, v == 0.25) or right edge (column 480, u == 0.75), where u+v == 1 in
-    # exact arithmetic and the f32 rounding of f = 1/area decides (u+v comes out 1 ulp above 1.0 -> miss).  For
-    # those rays Moeller-Trumbore has at most two non-zero terms per dot product, so no summation order of
-    # cglinalg's dot/cross changes the outcome, and every normalize/dot order we could enumerate for the ray
-    # direction gives the same 16.  Either the reference's test fails on these 16 pixels, or cglinalg (absent
-    # here) differs in a way that cannot be inferred from the reference tree.  We pin OUR behaviour: mismatches
-    # are confined to those two edge lines and number exactly 16.
+    # 409,584 of 409,600 pixels reproduce the reference's expectation.  The other 16 lie exactly on the quad's top edge
+    # (row 160, v == 0.25) or right edge (column 480, u == 0.75), where u+v == 1 in exact arithmetic and the two roundings
+    # of f = 1/area and f * X decide (u+v comes out 1 ulp above 1.0 -> miss).  tests/test_quad_edge_variants.py enumerates
+    # every f32 variant of cglinalg's dot / cross / normalize consistent with the reference's visible source: none of the 24
+    # hits all 642 edge rays (16 or 12 misses), so the upstream expectation cannot be met by the reference's own
+    # Triangle::intersect (triangle.rs:53-62).  We pin the variant the other KATs pin: exactly these 16.
     scene, cam = quad_scene()
     uv_tl, dims = quad_test_case()
     assert uv_tl.tolist() == [0.25, 0.25] and dims.tolist() == [0.5, 0.5]
