@@ -1,4 +1,4 @@
-//! Raw bindings of `include/bvht.h` (ABI version 1).  Layouts are `#[repr(C)]` mirrors of the C structs.
+//! Raw bindings of `include/bvht.h` (ABI version 4).  Layouts are `#[repr(C)]` mirrors of the C structs.
 #![allow(non_camel_case_types, dead_code)]
 use std::os::raw::{c_char, c_int, c_void};
 
@@ -16,10 +16,9 @@ pub const BVHT_SHADE_TEXTURE: u32 = 5;
 
 pub enum BvhtCtx {}
 
-#[repr(C)] #[derive(Clone, Copy, Default)]
-pub struct BvhtBvhNode { pub aabb_min: [f32; 3], pub aabb_max: [f32; 3], pub prim_count: u32, pub left_first: u32 }
-#[repr(C)] #[derive(Clone, Copy, Default)]
-pub struct BvhtTlasNode { pub aabb_min: [f32; 3], pub aabb_max: [f32; 3], pub left_right: u32, pub blas: u32 }
+// bvht_bvh_node / bvht_tlas_node: defined next to the private node types they flatten (reference-accessors.patch)
+pub use crate::model::BvhtBvhNode;
+pub use crate::scene::BvhtTlasNode;
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct BvhtInstance { pub transform_inv: [f32; 16], pub blas_id: u32 }
 #[repr(C)] #[derive(Clone, Copy)]

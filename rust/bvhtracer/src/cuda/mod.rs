@@ -4,6 +4,7 @@
 mod ffi;
 pub use ffi::{BvhtShade, BVHT_FLAG_FAST, BVHT_FLAG_LEAF_ACCEL, BVHT_FLAG_STAMP_INSTANCE, BVHT_FLAG_STRICT};
 
+use crate::geometry::Aabb;
 use crate::model::Model;
 use crate::query::{InstancePrimitiveIndex, Intersection, Ray, SurfaceInteraction};
 use crate::renderer::{Integrator, RendererState};
@@ -67,9 +68,9 @@ impl CudaPathTracer {
         if tex_coords.len() == tris.len() {
             self.check(unsafe { bvht_blas_set_tex_coords(self.ctx, id, tex_coords.as_ptr() as *const f32, tex_coords.len() as u32) });
         }
-        let texture = model.texture().texture();               // TextureBuffer2D<Rgb<u8>, Vec<u8>> (needs a read accessor, material.rs:14-16)
+        let texture = model.texture().texture();               // TextureBuffer2D<Rgb<u8>, Vec<u8>> (reference-accessors.patch)
         if texture.width() > 0 && texture.height() > 0 {
-            self.check(unsafe { bvht_blas_set_texture(self.ctx, id, texture.as_bytes().as_ptr(), texture.width() as u32, texture.height() as u32) });
+            self.check(unsafe { bvht_blas_set_texture(self.ctx, id, texture.as_ptr() as *const u8, texture.width() as u32, texture.height() as u32) });
         }
         self.uploaded.push(Uploaded { model: key, blas_id: id, vertex_version: 0 });
         id
@@ -108,7 +109,12 @@ impl CudaPathTracer {
         self.check(unsafe { bvht_tlas_read(self.ctx, nodes.as_mut_ptr(), nodes.len() as u32, &mut used, inst.as_mut_ptr(),
                                            bounds.as_mut_ptr(), n as u32, &mut n_out) });
         nodes.truncate(used as usize);
-        scene.adopt_device_state(transforms, &inst, &bounds, &nodes);
+        let inverses: Vec<Transform3<f32>> = inst.iter().map(|i| {
+            let m = &i.transform_inv;                           // column-major, like cglinalg
+            Transform3::from_matrix(Matrix4x4::new(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], m[11], m[12], m[13], m[14], m[15]))
+        }).collect();
+        let boxes: Vec<Aabb<f32>> = bounds.chunks(6).map(|b| Aabb::new(Vector3::new(b[0], b[1], b[2]), Vector3::new(b[3], b[4], b[5]))).collect();
+        scene.adopt_device_state(transforms, &inverses, &boxes, &nodes);
         self.frame_state_resident = true;                       // evaluate() need not call bvht_tlas_set for this frame
     }
 
