@@ -40,7 +40,7 @@ class ShadeParams(C.Structure):
                 ("hit_rgba", C.c_uint8 * 4), ("miss_rgba", C.c_uint8 * 4), ("object0_transform", C.c_float * 16)]
 
 
-OPT_COVER, OPT_K0, OPT_BANDS = 1, 2, 3
+OPT_COVER, OPT_K0, OPT_BANDS, OPT_BAND_ORDER, OPT_COPY_STREAMS = 1, 2, 3, 4, 5
 
 SHADE_NONE, SHADE_DEPTH, SHADE_INTERSECTION, SHADE_UV, SHADE_NORMAL, SHADE_TEXTURE = 0, 1, 2, 3, 4, 5
 
@@ -104,6 +104,7 @@ SYMBOLS = [
     ("bvht_ipc_close", C.c_int, [_P, _P]),
     ("bvht_get_stats", C.c_int, [_P, C.POINTER(Stats)]),
     ("bvht_debug_read_bandwidth", C.c_int, [_P, C.c_size_t, C.c_uint32, C.POINTER(C.c_double)]),
+    ("bvht_debug_frame_timeline", C.c_int, [_P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     ("bvht_debug_trace_stats", C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, Rect, _P]),
 ]
 

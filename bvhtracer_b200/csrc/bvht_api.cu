@@ -31,7 +31,7 @@ namespace {
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr uint32_t kRefitChunkTris = 512;
 constexpr int kTraceBlock = 128;
-constexpr int kMaxBands = 16;
+constexpr int kMaxBands = 32;
 
 struct DevBuf {
     void* p = nullptr;
@@ -43,6 +43,7 @@ struct Blas {
     uint32_t n_tris = 0, nodes_used = 0;
     std::vector<bvht_bvh_node> h_nodes;     // host copy of the uploaded node pool (topology for validation / accel)
     std::vector<float> h_tris;              // host copy of the vertices (needed to rebuild the leaf accelerator)
+    std::vector<float> h_kappa;             // |e1||e2| per triangle, rounded up (compute_model_stats): the bake's per-triangle inflation
     bool global_accel = false;              // fast mode: ONE sub-BVH over the whole model instead of one per reference leaf
     std::vector<uint32_t> perm;             // device-built models: perm[i] = index, in the caller's array, of the triangle at i
     DevBuf tris_aos, nodes, tri, normals;      // normals: 3 float4 per primitive, ORIGINAL primitive order
@@ -86,8 +87,8 @@ struct Knobs {
     int   k0 = -1;                     // K0 (classify + fill): -1 = by rule, 0 / 1 = forced
     bool  no_d2h = false;              // timing experiment: bands without their copies
     int   bands = 0;                   // > 0: number of bands of bvht_render_frame
-    int   band_shape = 1;              // 0 taper, 1 uniform, 2 triangular
-    bool  bands_image_order = false;
+    int   band_order = -1;             // pull order of the bands: -1 = the library's rule, 0 image order, 1 cheapest first,
+                                       //   2 cheap bands (ascending), then the expensive ones (descending), 3 descending cost
 };
 
 static Knobs read_knobs() {
@@ -108,8 +109,7 @@ static Knobs read_knobs() {
     if (const char* e = getenv("BVHT_K0")) k.k0 = e[0] == '1';
     k.no_d2h = on("BVHT_DEBUG_NO_D2H");
     if (const char* e = getenv("BVHT_BANDS")) { int v = atoi(e); if (v >= 1 && v <= 16) k.bands = v; }
-    if (const char* e = getenv("BVHT_BAND_SHAPE")) k.band_shape = e[0] == 'u' ? 1 : (e[0] == 't' && e[1] == 'r' ? 2 : 0);
-    k.bands_image_order = on("BVHT_BANDS_IMAGE_ORDER");
+    if (const char* e = getenv("BVHT_BAND_ORDER")) k.band_order = atoi(e);
 #endif
     return k;
 }
@@ -137,7 +137,10 @@ struct bvht_ctx {
     std::vector<bvht_instance> h_inst;
     std::vector<float> inst_tight;                    // 6 floats per instance (world lo/hi) or lo > hi when unusable
     double bake_center[3] = { 0.0, 0.0, 0.0 };        // camera origin the tight TLAS boxes' origin limit is centred on
-    DevBuf work_counter;                              // slot i: [2i] = K1's work cursor, [2i+1] = length of K0's block list
+    DevBuf work_counter;                              // 256 words: [0] K1's work cursor | [32..63] blocks K0 listed per band | [64..95] blocks
+                                                      //   finished per band | [96..127] band completion flags (never zeroed: they carry
+                                                      //   the frame sequence number) | [128..129] scratch of the ray-bounds reduction
+    uint32_t frame_seq = 0;                           // bvht_render_frame's band flags are raised to this value
     DevBuf cover, cover_aux;                          // per-triangle block coverage of the current frame (cover_kernels.cu); aux: full word, big count, big list
     bool cover_ready = false;                         // valid for the launches of the current frame only
     uint32_t cover_ntx = 0;
@@ -148,12 +151,21 @@ struct bvht_ctx {
     DevBuf out_buf, rays_buf, rgba_buf;               // device staging for the host-pointer entry points
     cudaStream_t aux[2] = { nullptr, nullptr };       // band pipelining: two compute streams + one copy stream
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_streams[3] = { nullptr, nullptr, nullptr };   // bvht_render_frame's band copies rotate over these (copy_stream is [0])
+    cudaEvent_t ev_copy_join[3] = { nullptr, nullptr, nullptr };
+    int n_copy_streams = 2;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_band[64] = {};
-    // bvht_render_frame launches its bands cheapest-first, from the previous frame's per-band kernel times
     cudaEvent_t ev_band_t[17] = {};                   // timing events: [0] = start, [i + 1] = end of the i-th launched band
-    struct BandHistory { uint32_t key[8] = { 0 }; uint32_t n = 0; float ms_per_row[16] = { 0 }; bool valid = false; } band_hist;
-    void* pinned = nullptr; size_t pinned_bytes = 0;  // pinned staging for small uploads
+    void* pinned = nullptr; size_t pinned_bytes = 0;  // pinned staging for small uploads (synchronous users)
+    // ring of page-locked staging slots for the per-frame uploads (bvht_tlas_set): a slot is reused only after the copies queued
+    // from it have completed (its event), so an upload never has to wait for the stream to drain
+    struct Stage { void* p = nullptr; size_t bytes = 0; cudaEvent_t done = nullptr; bool used = false; } stage[4];
+    uint32_t stage_next = 0;
+    // bvht_debug_frame_timeline: events of the last bvht_render_frame ([i] = end of the i-th launched band's copy)
+    cudaEvent_t ev_copy_t[16] = {};
+    cudaEvent_t ev_cover_t = nullptr;
+    uint32_t tl_bands = 0; uint32_t tl_rows[16] = { 0 }; bool tl_valid = false;
     int sm_count = 0;
     int occ_cache[3] = { 0, 0, 0 };                   // resident CTAs per SM: ray kernel, primary kernel, primary kernel with chain skipping
     uint32_t shard_index = 0, shard_count = 1;
@@ -197,6 +209,28 @@ int ensure_pinned(bvht_ctx* ctx, size_t bytes) {
     size_t want = std::max<size_t>(bytes, 1 << 16);
     CU(ctx, cudaMallocHost(&ctx->pinned, want));
     ctx->pinned_bytes = want;
+    return BVHT_OK;
+}
+
+// Next staging slot with room for `bytes`, free to be overwritten.  After queueing the copies out of it: stage_done().
+int stage_get(bvht_ctx* ctx, size_t bytes, bvht_ctx::Stage** out) {
+    bvht_ctx::Stage& st = ctx->stage[ctx->stage_next];
+    ctx->stage_next = (ctx->stage_next + 1) % 4;
+    if (!st.done) CU(ctx, cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+    if (st.used) CU(ctx, cudaEventSynchronize(st.done));
+    if (bytes > st.bytes) {
+        if (st.p) { cudaFreeHost(st.p); st.p = nullptr; st.bytes = 0; }
+        size_t want = std::max<size_t>(bytes, 1 << 14);
+        CU(ctx, cudaMallocHost(&st.p, want));
+        st.bytes = want;
+    }
+    *out = &st;
+    return BVHT_OK;
+}
+
+int stage_done(bvht_ctx* ctx, bvht_ctx::Stage* st) {
+    CU(ctx, cudaEventRecord(st->done, ctx->stream));
+    st->used = true;
     return BVHT_OK;
 }
 
@@ -286,11 +320,16 @@ int bake_accel(bvht_ctx* ctx, Blas& b, double d_max, double o_max) {
         // whole model's box, and with it the instance's screen rectangle, by its own slack
         double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
         const float* T = b.h_tris.data();
+        const bool have_kappa = b.h_kappa.size() == b.n_tris;
         for (uint32_t i = 0; i < b.n_tris && b.h_tris.size() >= (size_t)b.n_tris * 9; ++i) {
             const float* t = T + (size_t)i * 9;
-            double e1[3], e2[3];
-            for (int k = 0; k < 3; ++k) { e1[k] = (double)t[3 + k] - t[k]; e2[k] = (double)t[6 + k] - t[k]; }
-            double kp = std::sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]) * std::sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
+            double kp;
+            if (have_kappa) kp = (double)b.h_kappa[i];
+            else {
+                double e1[3], e2[3];
+                for (int k = 0; k < 3; ++k) { e1[k] = (double)t[3 + k] - t[k]; e2[k] = (double)t[6 + k] - t[k]; }
+                kp = std::sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]) * std::sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
+            }
             if (!(kp > 0.0)) continue;
             double delta = (double)fs * kp * (1.0 + 1e-9) + (double)fa;
             for (int k = 0; k < 3; ++k) {
@@ -350,7 +389,7 @@ int build_accel_device(bvht_ctx* ctx, Blas& b, const LeafAccelConfig& cfg, bool&
     // model's largest triangles, and a few triangles hundreds of times larger than the typical one (Big Ben: max |e1||e2| =
     // 115 x the mean; armadillo 6 x, teapot 3 x) drag their inflation through every box above them.  So: global tree when the
     // largest edge product is within 32 x the mean.  Knobs::fast_global forces it off / on (experiment builds).
-    ModelStats ms = compute_model_stats(b.h_tris.data(), b.n_tris);
+    ModelStats ms = compute_model_stats(b.h_tris.data(), b.n_tris, &b.h_kappa);
     {
         bool want = ms.mean_kappa > 0.0 && ms.model_kappa <= 32.0 * ms.mean_kappa && b.n_tris >= 64;    // (a dozen triangles: brute force wins)
         if (ctx->knobs.fast_global >= 0) want = ctx->knobs.fast_global == 1;
@@ -423,7 +462,7 @@ int build_and_upload_accel(bvht_ctx* ctx, Blas& b) {
     b.n_sub_nodes = (uint32_t)(acc.sub_raw.size() / 16);
     b.radius = acc.radius; b.max_edge = acc.max_edge; b.model_kappa = acc.model_kappa; b.model_valid = acc.model_valid;
     memcpy(b.model_lo, acc.model_lo, 12); memcpy(b.model_hi, acc.model_hi, 12);
-    set_useful_product(b, compute_model_stats(b.h_tris.data(), b.n_tris), cfg);
+    set_useful_product(b, compute_model_stats(b.h_tris.data(), b.n_tris, &b.h_kappa), cfg);
     int rc;
     if ((rc = ensure(ctx, b.sub_raw, acc.sub_raw.size() * 4))) return rc;
     if ((rc = ensure(ctx, b.sub_nodes, acc.sub_raw.size() * 4))) return rc;
@@ -453,7 +492,7 @@ int refit_accel(bvht_ctx* ctx, Blas& b) {
     CU(ctx, launch_refit_sub_nodes((float4*)b.sub_raw.p, (const uint32_t*)b.sub_parent.p, (unsigned int*)b.sub_counters.p,
                                    (const float*)b.tris_aos.p, (const uint32_t*)b.sub_order.p, b.n_sub_nodes, ctx->stream));
     ctx->stats.kernel_launches += 2;
-    ModelStats ms = compute_model_stats(b.h_tris.data(), b.n_tris);
+    ModelStats ms = compute_model_stats(b.h_tris.data(), b.n_tris, &b.h_kappa);
     b.radius = ms.radius; b.max_edge = ms.max_edge; b.model_kappa = ms.model_kappa; b.model_valid = ms.model_valid;
     memcpy(b.model_lo, ms.model_lo, 12); memcpy(b.model_hi, ms.model_hi, 12);
     set_useful_product(b, ms, LeafAccelConfig());
@@ -645,8 +684,13 @@ int recompute_tlas_tight(bvht_ctx* ctx) {
     int rc = ensure(ctx, ctx->tlas_tight, flat.size() * 4);
     if (rc) return rc;
     if ((rc = ensure(ctx, ctx->tlas_mask, mask.size() * 4))) return rc;
-    if ((rc = h2d(ctx, ctx->tlas_mask.p, mask.data(), mask.size() * 4))) return rc;
-    return h2d(ctx, ctx->tlas_tight.p, flat.data(), flat.size() * 4);       // pageable: staged before return
+    bvht_ctx::Stage* stage = nullptr;
+    if ((rc = stage_get(ctx, (flat.size() + mask.size()) * 4, &stage))) return rc;
+    memcpy(stage->p, flat.data(), flat.size() * 4);
+    memcpy((char*)stage->p + flat.size() * 4, mask.data(), mask.size() * 4);
+    if ((rc = h2d(ctx, ctx->tlas_tight.p, stage->p, flat.size() * 4))) return rc;
+    if ((rc = h2d(ctx, ctx->tlas_mask.p, (char*)stage->p + flat.size() * 4, mask.size() * 4))) return rc;
+    return stage_done(ctx, stage);
 }
 
 // Conservative screen-space rectangle (inclusive pixel bounds) of every instance's tight world box for this camera.
@@ -997,16 +1041,24 @@ int bvht_create(int device, uint32_t flags, bvht_ctx** out) {
            && cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
     if (ok) {
         ctx->stream = ctx->own_stream;
-        ok = ensure(ctx, ctx->work_counter, 1024) == BVHT_OK && ensure_pinned(ctx, 1 << 16) == BVHT_OK;
+        ok = ensure(ctx, ctx->work_counter, 1024) == BVHT_OK && ensure_pinned(ctx, 1 << 16) == BVHT_OK
+          // the band completion flags live here and are compared with the frame sequence number: they must not start as garbage
+          && cudaMemset(ctx->work_counter.p, 0, 1024) == cudaSuccess;
     }
     if (ok) {
         ok = cudaStreamCreateWithFlags(&ctx->aux[0], cudaStreamNonBlocking) == cudaSuccess
           && cudaStreamCreateWithFlags(&ctx->aux[1], cudaStreamNonBlocking) == cudaSuccess
           && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess
+          && cudaStreamCreateWithFlags(&ctx->copy_streams[1], cudaStreamNonBlocking) == cudaSuccess
+          && cudaStreamCreateWithFlags(&ctx->copy_streams[2], cudaStreamNonBlocking) == cudaSuccess
           && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess
           && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
+        ctx->copy_streams[0] = ctx->copy_stream;
+        for (int i = 0; ok && i < 3; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_copy_join[i], cudaEventDisableTiming) == cudaSuccess;
         for (int i = 0; ok && i < 64; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_band[i], cudaEventDisableTiming) == cudaSuccess;
         for (int i = 0; ok && i < 17; ++i) ok = cudaEventCreate(&ctx->ev_band_t[i]) == cudaSuccess;
+        for (int i = 0; ok && i < 16; ++i) ok = cudaEventCreate(&ctx->ev_copy_t[i]) == cudaSuccess;
+        ok = ok && cudaEventCreate(&ctx->ev_cover_t) == cudaSuccess;
     }
     if (!ok) { cudaGetLastError(); bvht_destroy(ctx); return BVHT_ERR_CUDA; }
     ctx->stats.sm_count = (uint32_t)ctx->sm_count;
@@ -1025,11 +1077,15 @@ void bvht_destroy(bvht_ctx* ctx) {
                        &ctx->rgba_buf, &ctx->tlas_tight, &ctx->tlas_mask, &ctx->scene_in, &ctx->scene_bounds, &ctx->build_tris, &ctx->build_perm })
         release(*d);
     ctx->build_ws.release();
-    for (cudaStream_t st : { ctx->aux[0], ctx->aux[1], ctx->copy_stream }) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (cudaStream_t st : { ctx->aux[0], ctx->aux[1], ctx->copy_stream, ctx->copy_streams[1], ctx->copy_streams[2] }) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (cudaEvent_t ev : ctx->ev_copy_join) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : { ctx->ev_fork, ctx->ev_join }) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : ctx->ev_band) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : ctx->ev_band_t) if (ev) cudaEventDestroy(ev);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (auto& st : ctx->stage) { if (st.p) cudaFreeHost(st.p); if (st.done) cudaEventDestroy(st.done); }
+    for (cudaEvent_t ev : ctx->ev_copy_t) if (ev) cudaEventDestroy(ev);
+    if (ctx->ev_cover_t) cudaEventDestroy(ctx->ev_cover_t);
     for (cudaEvent_t ev : { ctx->ev_a, ctx->ev_b, ctx->ev_c, ctx->ev_d, ctx->ev_e, ctx->ev_f }) if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -1050,6 +1106,12 @@ int bvht_set_option(bvht_ctx* ctx, uint32_t option, int32_t value) {
     switch (option) {
         case BVHT_OPT_COVER: ctx->knobs.cover = value < 0 ? -1 : (value != 0); return BVHT_OK;
         case BVHT_OPT_K0:    ctx->knobs.k0 = value < 0 ? -1 : (value != 0); return BVHT_OK;
+        case BVHT_OPT_COPY_STREAMS:
+            if (value > 3) return fail(ctx, BVHT_ERR_INVALID_ARG, "at most 3 copy streams");
+            ctx->n_copy_streams = value < 1 ? 2 : value; return BVHT_OK;
+        case BVHT_OPT_BAND_ORDER:
+            if (value > 3) return fail(ctx, BVHT_ERR_INVALID_ARG, "unknown band order %d", (int)value);
+            ctx->knobs.band_order = value < 0 ? -1 : value; return BVHT_OK;
         case BVHT_OPT_BANDS:
             if (value > kMaxBands) return fail(ctx, BVHT_ERR_INVALID_ARG, "at most %d bands (%d asked)", kMaxBands, (int)value);
             ctx->knobs.bands = value < 0 ? 0 : value; return BVHT_OK;
@@ -1313,10 +1375,10 @@ int bvht_tlas_set(bvht_ctx* ctx, const bvht_tlas_node* nodes, uint32_t nodes_use
     if ((rc = ensure(ctx, ctx->tlas, tl_bytes))) return rc;
     if ((rc = ensure(ctx, ctx->inst_cols, ic_bytes))) return rc;
     if ((rc = ensure(ctx, ctx->inst_blas, ib_bytes))) return rc;
-    CU(ctx, cudaStreamSynchronize(ctx->stream));       // previous frame may still read the staging buffer
-    if ((rc = ensure_pinned(ctx, tl_bytes + ic_bytes + ib_bytes + 1024))) return rc;
-    // flatten into the device layouts inside the pinned buffer
-    char* st = (char*)ctx->pinned;
+    // flatten into the device layouts inside a page-locked staging slot (no wait for the stream: stage_get)
+    bvht_ctx::Stage* stage = nullptr;
+    if ((rc = stage_get(ctx, tl_bytes + ic_bytes + ib_bytes + 1024, &stage))) return rc;
+    char* st = (char*)stage->p;
     float* tl = (float*)st;
     for (uint32_t i = 0; i < nodes_used; ++i) {
         float* f = tl + (size_t)i * 8;
@@ -1335,6 +1397,7 @@ int bvht_tlas_set(bvht_ctx* ctx, const bvht_tlas_node* nodes, uint32_t nodes_use
         if ((rc = h2d(ctx, ctx->inst_cols.p, ic, (size_t)n_instances * 64))) return rc;
         if ((rc = h2d(ctx, ctx->inst_blas.p, ib, (size_t)n_instances * 4))) return rc;
     }
+    if ((rc = stage_done(ctx, stage))) return rc;
     ctx->h_tlas.assign(nodes, nodes + nodes_used);
     for (uint32_t i = 0; i < nodes_used; ++i) if (!reached[i]) memset(&ctx->h_tlas[i], 0, sizeof(bvht_tlas_node));
     ctx->h_inst.assign(instances, instances + n_instances);
@@ -1461,9 +1524,11 @@ int bvht_tlas_read(bvht_ctx* ctx, bvht_tlas_node* nodes_out, uint32_t max_nodes,
 // tools/cover_ab.py, off -> on: sixteen_armadillos 4K 0.855 -> 0.785 ms, two_armadillos 1080p 0.257 -> 0.244 ms).  It does
 // not for small models (trippy_teapots 0.262 -> 0.297 ms, cube 0.023 -> 0.058 ms) nor for a single instance, where K0 with
 // the model's screen rectangle already removes the empty blocks (big_ben_clock 8K: 1.671 -> 1.675 ms).
-static bool cover_wanted(const bvht_ctx* ctx, uint32_t n_inst, uint32_t tris) {
+// Its cost is per triangle (every GPU projects every triangle; only the marking is sharded), its gain per ray: below about two
+// million rays per GPU -- a 4K frame over 8 GPUs -- it no longer pays.
+static bool cover_wanted(const bvht_ctx* ctx, uint32_t n_inst, uint32_t tris, uint32_t width, uint32_t height) {
     if (ctx->knobs.cover >= 0) return ctx->knobs.cover == 1;            // bvht_set_option(BVHT_OPT_COVER)
-    return n_inst >= 2 && tris / n_inst >= 8192u;
+    return n_inst >= 2 && tris / n_inst >= 8192u && (uint64_t)width * height / ctx->shard_count >= 2000000ull;
 }
 
 // Rasterise every instance's triangles onto the 8x4-pixel blocks of the frame (cover_kernels.cu).  Once per frame, on
@@ -1487,7 +1552,7 @@ static int prepare_cover(bvht_ctx* ctx, const bvht_camera* cam, uint32_t width, 
             if (!rc0 && blocks <= (64ull << 20)) rc0 = ensure(ctx, ctx->work_list, blocks * 4);
             if (rc0) return rc0;
         }
-        if (!cover_wanted(ctx, n_inst, tris)) return BVHT_OK;
+        if (!cover_wanted(ctx, n_inst, tris, width, height)) return BVHT_OK;
     }
     const float* tl = cam->top_left_eye; const float* tr = cam->top_right_eye; const float* bl = cam->bottom_left_eye;
     if (!(tl[2] < 0.0f) || tr[2] != tl[2] || bl[2] != tl[2] || tr[1] != tl[1] || bl[0] != tl[0]) return BVHT_OK;
@@ -1531,7 +1596,9 @@ static int prepare_cover(bvht_ctx* ctx, const bvht_camera* cam, uint32_t width, 
     if ((rc = ensure(ctx, ctx->cover_aux, 16 + (size_t)std::max(total, 1u) * 16))) return rc;
     CU(ctx, cudaMemsetAsync(ctx->cover.p, 0, words * 4, stream));
     const uint32_t init[4] = { full_init, 0u, 0u, 0u };
-    CU(ctx, cudaMemcpyAsync(ctx->cover_aux.p, init, 16, cudaMemcpyHostToDevice, stream));       // pageable: staged before return
+    CU(ctx, cudaMemsetAsync(ctx->cover_aux.p, 0, 16, stream));
+    if (total == 0 && full_init) CU(ctx, cudaMemcpyAsync(ctx->cover_aux.p, init, 16, cudaMemcpyHostToDevice, stream));   // no raster launch to OR it in
+    p.full_init = full_init;
     p.cover = (uint32_t*)ctx->cover.p;
     p.full = (uint32_t*)ctx->cover_aux.p;
     p.big_count = (uint32_t*)ctx->cover_aux.p + 1;
@@ -1541,6 +1608,7 @@ static int prepare_cover(bvht_ctx* ctx, const bvht_camera* cam, uint32_t width, 
     p.inst_blas = (const uint32_t*)ctx->inst_blas.p;
     p.n_inst = n_inst;
     p.ntx = ntx; p.width = width; p.height = height;
+    p.shard_index = ctx->shard_index; p.shard_count = ctx->shard_count;
     p.tlx = tl[0]; p.tly = tl[1]; p.inv_ex = (float)(1.0 / ex); p.inv_ey = (float)(1.0 / ey); p.near_ = -tl[2];
     p.z_eps = (float)(1e-4 * (1.0 + scale_max));
     if (total) {
@@ -1572,11 +1640,26 @@ static int prepare_cover(bvht_ctx* ctx, const bvht_camera* cam, uint32_t width, 
     return BVHT_OK;
 }
 
-// One persistent launch of K1 over `region` on `stream`, using work counter slot `slot`.
+// How a launch's tile rows are cut into bands and in which order K1 pulls them (device_types.cuh "Bands").
+struct BandPlan {
+    uint32_t n_bands = 1;
+    uint32_t band_rows = 0;            // tile rows (of this shard) per band; 0 = all of them
+    uint8_t  order[32] = { 0 };
+    bool     flags = false;            // raise a completion flag per band (bvht_render_frame's copies wait for them)
+    uint32_t seq = 0;
+    const int4* rects = nullptr;       // the instances' screen rectangles, when the caller has computed them already
+    uint32_t n_rects = 0;
+    bool     have_rects = false;
+};
+
+constexpr uint32_t kWordBandCount = 32, kWordBandDone = 64, kWordBandFlag = 96;
+
+// One persistent launch of K1 (preceded by K0 when it pays) over `region` on `stream`.
 static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvht_camera* camera, uint32_t width, uint32_t height,
                                  uint32_t tile, bvht_rect region, const bvht_shade_params* shade, void* hits_device,
                                  void* rgba_device, cudaStream_t stream, int slot, uint32_t shard_index = 0, uint32_t shard_count = 1,
-                                 unsigned long long* stats_counters = nullptr) {
+                                 unsigned long long* stats_counters = nullptr, const BandPlan* plan = nullptr) {
+    (void)slot;
     PrimaryParams p;
     memset(&p, 0, sizeof p);
     p.scene = scene;
@@ -1627,7 +1710,20 @@ static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvh
             p.shade_n_prims = b0.n_tris;
         }
     }
-    p.work_counter = (unsigned int*)ctx->work_counter.p + 2 * slot;
+    p.work_counter = (unsigned int*)ctx->work_counter.p;
+    {
+        BandPlan single;
+        const BandPlan& bp = plan ? *plan : single;
+        const uint32_t rows = bp.band_rows ? bp.band_rows : std::max(p.nty, 1u);
+        p.n_bands = std::min<uint32_t>(std::max<uint32_t>(bp.n_bands, 1u), 32u);
+        p.band_items = rows * p.ntx * p.items_per_tile;
+        if ((uint64_t)p.band_items * p.n_bands < n_items) return fail(ctx, BVHT_ERR_INVALID_ARG, "band plan does not cover the launch");
+        memcpy(p.band_order, bp.order, 32);
+        p.band_count = (unsigned int*)ctx->work_counter.p + kWordBandCount;
+        p.band_done = bp.flags ? (unsigned int*)ctx->work_counter.p + kWordBandDone : nullptr;
+        p.band_flag = (unsigned int*)ctx->work_counter.p + kWordBandFlag;
+        p.band_seq = bp.seq;
+    }
     p.n_origin = 0;
     if (!ctx->h_inst.empty() && ctx->h_inst.size() <= 32 && !ctx->knobs.no_host_origin) {
         // BVHT_MV4 of trace_kernels.cuh, operation for operation (this file is compiled with -ffp-contract=off)
@@ -1648,7 +1744,10 @@ static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvh
         p.n_origin = (uint32_t)ctx->h_inst.size();
     }
     p.n_rect = 0;
-    if (accel_on(ctx)) { uint32_t nr = 0; if (compute_instance_rects(ctx, camera, width, height, p.inst_rect, nr)) p.n_rect = nr; }
+    if (accel_on(ctx)) {
+        if (plan && plan->have_rects) { p.n_rect = plan->n_rects; if (p.n_rect) memcpy(p.inst_rect, plan->rects, p.n_rect * sizeof(int4)); }
+        else { uint32_t nr = 0; if (compute_instance_rects(ctx, camera, width, height, p.inst_rect, nr)) p.n_rect = nr; }
+    }
     // chain skipping pays from three instances on (measured: pure overhead for 1-2 instances)
     p.n_tlas_nodes = (p.n_rect >= 3 && ctx->tlas_nested && ctx->h_tlas.size() <= 64) ? (uint32_t)ctx->h_tlas.size() : 0u;
     p.skip_rounds = 0;
@@ -1689,8 +1788,7 @@ static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvh
         if (cap <= (64ull << 20)) {
             int rc = ensure(ctx, ctx->work_list, (size_t)cap * 4);
             if (rc) return rc;
-            p.work_list = (uint32_t*)ctx->work_list.p + (uint64_t)p.ty0 * ntx_full * p.items_per_tile;
-            p.work_count = (unsigned int*)ctx->work_counter.p + 2 * slot + 1;
+            p.work_list = (uint32_t*)ctx->work_list.p;
             ctx->stats.kernel_launches += 1;
         }
     }
@@ -1733,7 +1831,7 @@ int bvht_render_frame_device(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
     if ((rc = fill_scene(ctx, scene))) return rc;
     ctx->stats.last_trace_rays = 0;
     if (region.x0 >= region.x1 || region.y0 >= region.y1) return BVHT_OK;     // empty region: nothing to do
-    CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, 8, ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, kWordBandFlag * 4, ctx->stream));
     cudaEventRecord(ctx->ev_a, ctx->stream);
     if ((rc = prepare_cover(ctx, camera, width, height, tile, ctx->stream))) return rc;       // inside the timed interval
     rc = launch_primary_region(ctx, scene, camera, width, height, tile, region, shade, hits_out_device, frame_out_device,
@@ -1789,6 +1887,21 @@ static int copy_rows_d2h(bvht_ctx* ctx, void* host, const void* dev, uint32_t wi
     return BVHT_OK;
 }
 
+// cuStreamWaitValue32 through the runtime's driver entry point lookup (no link-time dependency on libcuda)
+typedef int (*StreamWaitValue32Fn)(cudaStream_t, unsigned long long /*CUdeviceptr*/, unsigned int, unsigned int);
+static StreamWaitValue32Fn stream_wait_value32() {
+    static StreamWaitValue32Fn fn = []() -> StreamWaitValue32Fn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (StreamWaitValue32Fn)p;
+    }();
+    return fn;
+}
+
 int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height, uint32_t tile,
                       bvht_rect region, const bvht_shade_params* shade, uint32_t* frame_out_host, bvht_hit* hits_out_host) {
     if (!ctx) return BVHT_ERR_BAD_HANDLE;
@@ -1802,6 +1915,7 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
     SceneDev scene;
     if ((rc = fill_scene(ctx, scene))) return rc;
     ctx->stats.last_trace_rays = 0;
+    ctx->tl_valid = false;
     if (region.x0 >= region.x1 || region.y0 >= region.y1) return BVHT_OK;
     size_t npix = (size_t)width * height;
     if (frame_out_host && (rc = ensure(ctx, ctx->rgba_buf, npix * 4))) return rc;
@@ -1809,127 +1923,150 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
     void* d_rgba = frame_out_host ? ctx->rgba_buf.p : nullptr;
     void* d_hits = hits_out_host ? ctx->out_buf.p : nullptr;
 
-    // bands of whole tile rows, ~1 M rays each, at most 16 (and at most 64 counter slots)
-    uint32_t ty0 = region.y0 / tile, ty1 = (region.y1 + tile - 1) / tile;
-    uint32_t tile_rows = ty1 - ty0;
+    // ONE persistent launch traces the whole region; its device->host copies are pipelined against it band by band.  K1 pulls
+    // the pixel blocks band by band and raises a flag in device memory when a band's last block is done; the band's copy sits
+    // on the copy stream behind a cuStreamWaitValue32 on that flag -- no host round trip, no kernel boundary between bands
+    // (round 1 launched one kernel per band: every boundary cost ~35 us of ramp-down / ramp-up and host launch work, 0.23 ms of a
+    // 1.07 ms frame at 7 bands, profiles/r02_e2e_timeline_before.txt).  What stays exposed is the copy of the LAST band, so bands
+    // are thin (about 1.5 MB of output each, at most 32) and pulled cheapest first: the frame ends with its most expensive rows,
+    // behind which the earlier copies have long finished.  The cost of a band is estimated from the instances' screen rectangles.
+    const uint32_t shard_n = ctx->shard_count, shard_i = ctx->shard_index;
+    uint32_t first_row = region.y0 / tile, own_rows = (region.y1 + tile - 1) / tile - first_row;
+    if (shard_n > 1) bvht_shard_tile_rows(region, tile, shard_i, shard_n, &first_row, &own_rows);
     uint64_t rays = (uint64_t)(region.x1 - region.x0) * (region.y1 - region.y0);
-    uint32_t n_bands = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(rays / (1u << 20), 1), 16);
-    if (ctx->knobs.bands > 0) n_bands = (uint32_t)ctx->knobs.bands;
-    n_bands = std::min(n_bands, tile_rows);
-    CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, 512, ctx->stream));
-    cudaEventRecord(ctx->ev_a, ctx->stream);
-    if ((rc = prepare_cover(ctx, camera, width, height, tile, ctx->stream))) return rc;       // once per frame, before the bands fork
-    CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-    for (int i = 0; i < 2; ++i) CU(ctx, cudaStreamWaitEvent(ctx->aux[i], ctx->ev_fork, 0));
-    CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
-    // Equal bands of whole tile rows, launched CHEAPEST FIRST.  The device->host copy of a band overlaps the tracing of the
-    // bands launched after it, so what stays exposed is the first band's tracing and whatever is still to be copied when the last
-    // kernel ends.  In image order the frames of the examples end with rows that are nearly free to trace (sixteen_armadillos:
-    // the bottom 30 % of the rows take 6 % of the time), whose copies -- 10 MB, 0.18 ms -- then had nothing left to hide behind.
-    // Ordered by the time per row the previous frame measured for each band (CUDA events), the cheap rows go first and the
-    // frame ends with its slowest band, behind which the copies keep up.  No history (first frame, other size): image order.
-    // BVHT_BANDS_IMAGE_ORDER=1 keeps image order (A/B knob).
-    std::vector<uint32_t> band_start(n_bands + 1, 0);
+    ctx->stats.last_trace_rays = rays / shard_n;
+    if (own_rows == 0) return BVHT_OK;                                   // this shard owns no tile row of the region
+    const size_t px_bytes = (frame_out_host ? 4 : 0) + (hits_out_host ? sizeof(bvht_hit) : 0);
+    const uint64_t own_bytes = (uint64_t)own_rows * tile * (region.x1 - region.x0) * px_bytes;
+    BandPlan plan;
+    // band size: a copy of ~2.5 MB runs at ~48 of the link's ~55 GB/s and leaves a 50 us tail (B200, PCIe 5 x16; swept 1-32 bands
+    // on the 33 MB frame of sixteen_armadillos and the 8 MB one of two_armadillos, profiles/r02_e2e_timeline.txt); frames beyond
+    // 40 MB are copy-bound whatever the bands (big_ben_clock 8K: 133 MB = 2.4 ms of link time against 1.1 ms of tracing)
+    plan.n_bands = own_bytes < (512u << 10) ? 1u : own_bytes < (2u << 20) ? 2u
+                 : (uint32_t)std::min<uint64_t>(std::max<uint64_t>(own_bytes / (2560u << 10), 4), 16);
+    if (ctx->knobs.bands > 0) plan.n_bands = (uint32_t)ctx->knobs.bands;
+    plan.n_bands = std::max(1u, std::min(plan.n_bands, own_rows));
+    plan.band_rows = (own_rows + plan.n_bands - 1) / plan.n_bands;
+    plan.n_bands = (own_rows + plan.band_rows - 1) / plan.band_rows;
+    const StreamWaitValue32Fn wait_value = stream_wait_value32();
+    plan.flags = wait_value != nullptr && plan.n_bands > 1;
+    plan.seq = ++ctx->frame_seq;
+    int4 rects[32];
     {
-        // equal shares measured best for the 4 B/pixel frame and no worse for 20 B/pixel (BVHT_BAND_SHAPE=taper|triangular: A/B knob;
-        // taper = first and last band half-size, triangular = 1, 2, 3, .., 3, 2, 1)
-        const int mode = ctx->knobs.band_shape;
-        auto weight = [&](uint32_t b) -> uint64_t {
-            if (mode == 1) return 2;
-            if (mode == 2) return 2 * std::min(b + 1, n_bands - b);
-            return (b == 0 || b + 1 == n_bands) ? 1 : 2;
-        };
-        uint64_t wsum = 0, acc = 0;
-        for (uint32_t b = 0; b < n_bands; ++b) wsum += weight(b);
-        for (uint32_t b = 0; b < n_bands; ++b) { band_start[b] = (uint32_t)((uint64_t)tile_rows * acc / wsum); acc += weight(b); }
-        band_start[n_bands] = tile_rows;
-    }
-    uint32_t order[16];
-    for (uint32_t b = 0; b < n_bands; ++b) order[b] = b;
-    const uint32_t hist_key[8] = { width, height, tile, region.x0, region.y0, region.x1, region.y1, n_bands };
-    bvht_ctx::BandHistory& hist = ctx->band_hist;
-    const bool image_order = ctx->knobs.bands_image_order;
-    if (hist.valid && hist.n == n_bands && memcmp(hist.key, hist_key, sizeof hist_key) == 0 && !image_order)
-        std::stable_sort(order, order + n_bands, [&](uint32_t x, uint32_t y) { return hist.ms_per_row[x] < hist.ms_per_row[y]; });
-    cudaEventRecord(ctx->ev_band_t[0], ctx->stream);
-    auto band_row = [&](uint32_t b) -> uint32_t { return band_start[b]; };
-    auto run_band = [&](uint32_t i) -> int {
-        const uint32_t b = order[i];
-        uint32_t r0 = ty0 + band_row(b);
-        uint32_t r1 = ty0 + band_row(b + 1);
-        bvht_rect band = { region.x0, std::max(region.y0, r0 * tile), region.x1, std::min(region.y1, r1 * tile) };
-        cudaStream_t cs = ctx->aux[i & 1];
-        if (band.y0 < band.y1) {
-            if ((rc = launch_primary_region(ctx, scene, camera, width, height, tile, band, shade, d_hits, d_rgba, cs, (int)b,
-                                            ctx->shard_index, ctx->shard_count))) return rc;
+        // pull order: ascending estimated cost = pixels of instance rectangles inside the band's rows (no rectangles: image order)
+        uint64_t cost[32] = { 0 };
+        uint32_t nr = 0;
+        plan.have_rects = accel_on(ctx);
+        if (accel_on(ctx) && compute_instance_rects(ctx, camera, width, height, rects, nr)) {
+            plan.rects = rects; plan.n_rects = nr;
+            for (uint32_t k = 0; k < plan.n_bands; ++k) {
+                const uint32_t r0 = first_row + k * plan.band_rows * shard_n;
+                const uint32_t r1 = first_row + std::min(own_rows, (k + 1) * plan.band_rows) * shard_n;       // exclusive (global tile rows spanned)
+                const int y0 = (int)(r0 * tile), y1 = (int)std::min<uint64_t>((uint64_t)r1 * tile, height) - 1;
+                for (uint32_t i = 0; i < nr; ++i) {
+                    const int oy0 = std::max(y0, rects[i].y), oy1 = std::min(y1, rects[i].w);
+                    if (oy1 >= oy0 && rects[i].z >= rects[i].x) cost[k] += (uint64_t)(oy1 - oy0 + 1) * (uint64_t)(rects[i].z - rects[i].x + 1);
+                }
+            }
         }
-        cudaEventRecord(ctx->ev_band_t[i + 1], cs);
-        if (band.y0 >= band.y1) return BVHT_OK;
-        CU(ctx, cudaEventRecord(ctx->ev_band[b], cs));
-        CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[b], 0));
-        if (ctx->shard_count == 1) {
-            if (frame_out_host && (rc = copy_rows_d2h(ctx, frame_out_host, d_rgba, width, band, 4, ctx->copy_stream))) return rc;
-            if (hits_out_host && (rc = copy_rows_d2h(ctx, hits_out_host, d_hits, width, band, sizeof(bvht_hit), ctx->copy_stream))) return rc;
-        } else {
-            // sharded: only this rank's tile rows travel, and only they are written on the host (another rank fills the
-            // others, e.g. through a shared pinned mapping).  Owned rows are `tile` image rows every shard_count * tile rows:
-            // one strided 2-D copy per band (full-width regions), or one copy per owned tile row otherwise.
-            uint32_t first = 0, n_rows = 0;
-            bvht_shard_tile_rows(band, tile, ctx->shard_index, ctx->shard_count, &first, &n_rows);
-            for (int which = 0; which < 2; ++which) {
-                void* host = which == 0 ? (void*)frame_out_host : (void*)hits_out_host;
-                const void* dev = which == 0 ? d_rgba : d_hits;
-                size_t elem = which == 0 ? 4 : sizeof(bvht_hit);
-                if (!host || n_rows == 0) continue;
-                bool aligned = band.x0 == 0 && band.x1 == width && band.y0 % tile == 0 && (band.y1 % tile == 0 || band.y1 == height);
-                uint32_t last_row_end = std::min(height, (first + (n_rows - 1) * ctx->shard_count + 1) * tile);
-                if (aligned && last_row_end == (first + (n_rows - 1) * ctx->shard_count + 1) * tile) {
-                    size_t chunk = (size_t)tile * width * elem, pitch = chunk * ctx->shard_count, off = (size_t)first * tile * width * elem;
-                    CU(ctx, cudaMemcpy2DAsync((char*)host + off, pitch, (const char*)dev + off, pitch, chunk, n_rows, cudaMemcpyDeviceToHost,
-                                              ctx->copy_stream));
-                    ctx->stats.d2h_bytes += chunk * n_rows;
-                } else {
-                    for (uint32_t k = 0; k < n_rows; ++k) {
-                        uint32_t tr = first + k * ctx->shard_count;
-                        bvht_rect rr = { band.x0, std::max(band.y0, tr * tile), band.x1, std::min(band.y1, (tr + 1) * tile) };
-                        if (rr.y0 < rr.y1 && (rc = copy_rows_d2h(ctx, host, dev, width, rr, elem, ctx->copy_stream))) return rc;
-                    }
+        for (uint32_t k = 0; k < plan.n_bands; ++k) plan.order[k] = (uint8_t)k;
+        const int policy = ctx->knobs.band_order >= 0 ? ctx->knobs.band_order : 1;
+        if (policy == 1) std::stable_sort(plan.order, plan.order + plan.n_bands, [&](uint8_t x, uint8_t y) { return cost[x] < cost[y]; });
+        if (policy == 3) std::stable_sort(plan.order, plan.order + plan.n_bands, [&](uint8_t x, uint8_t y) { return cost[x] > cost[y]; });
+        if (policy == 2) {
+            // cheap bands first, cheapest first (their pixels are mostly K0's: complete almost at once, the copy engine starts on
+            // them), then the expensive ones, MOST expensive first: a heavy pixel block keeps its warp busy for ~100 us, so the
+            // heaviest rows must not be the ones the kernel ends with
+            uint64_t total = 0;
+            for (uint32_t k = 0; k < plan.n_bands; ++k) total += cost[k];
+            const uint64_t cheap_below = total / (2ull * plan.n_bands) + 1;          // under half the mean
+            std::stable_sort(plan.order, plan.order + plan.n_bands, [&](uint8_t x, uint8_t y) {
+                const bool cx = cost[x] < cheap_below, cy = cost[y] < cheap_below;
+                if (cx != cy) return cx;
+                return cx ? cost[x] < cost[y] : cost[x] > cost[y]; });
+        }
+    }
+    CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, kWordBandFlag * 4, ctx->stream));
+    cudaEventRecord(ctx->ev_a, ctx->stream);
+    if ((rc = prepare_cover(ctx, camera, width, height, tile, ctx->stream))) return rc;
+    cudaEventRecord(ctx->ev_cover_t, ctx->stream);
+    rc = launch_primary_region(ctx, scene, camera, width, height, tile, region, shade, d_hits, d_rgba, ctx->stream, 0, shard_i, shard_n,
+                               nullptr, &plan);
+    ctx->cover_ready = false;
+    if (rc) return rc;
+    CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));                 // = every kernel of the frame is done
+    cudaEventRecord(ctx->ev_band_t[0], ctx->stream);
+    if (!plan.flags) for (int c = 0; c < 3; ++c) CU(ctx, cudaStreamWaitEvent(ctx->copy_streams[c], ctx->ev_fork, 0));      // no flags: copy after the kernels
+    const unsigned long long flag_base = (unsigned long long)((unsigned int*)ctx->work_counter.p + kWordBandFlag);
+    const int n_cs = std::max(1, std::min(ctx->n_copy_streams, 3));
+    auto copy_band = [&](uint32_t k, cudaStream_t cs) -> int {
+        // tile rows of band k: own-row indices [k0, k1) = global tile rows first_row + j * shard_n
+        const uint32_t k0 = k * plan.band_rows, k1 = std::min(own_rows, (k + 1) * plan.band_rows);
+        for (int which = 0; which < 2; ++which) {
+            void* host = which == 0 ? (void*)frame_out_host : (void*)hits_out_host;
+            const void* dev = which == 0 ? d_rgba : d_hits;
+            const size_t elem = which == 0 ? 4 : sizeof(bvht_hit);
+            if (!host) continue;
+            if (shard_n == 1) {
+                bvht_rect rr = { region.x0, std::max(region.y0, (first_row + k0) * tile), region.x1, std::min(region.y1, (first_row + k1) * tile) };
+                if (rr.y0 < rr.y1 && (rc = copy_rows_d2h(ctx, host, dev, width, rr, elem, cs))) return rc;
+                continue;
+            }
+            // sharded: only this rank's tile rows travel, and only they are written on the host (another rank fills the others,
+            // e.g. through a shared pinned mapping): `tile` image rows every shard_n * tile rows -- one strided 2-D copy when the
+            // rows are whole and full width, one copy per tile row otherwise
+            const uint32_t g0 = first_row + k0 * shard_n, g_last = first_row + (k1 - 1) * shard_n;
+            const bool whole = region.x0 == 0 && region.x1 == width && g0 * tile >= region.y0 && (uint64_t)(g_last + 1) * tile <= region.y1;
+            if (whole) {
+                const size_t chunk = (size_t)tile * width * elem, pitch = chunk * shard_n, off = (size_t)g0 * tile * width * elem;
+                CU(ctx, cudaMemcpy2DAsync((char*)host + off, pitch, (const char*)dev + off, pitch, chunk, k1 - k0, cudaMemcpyDeviceToHost, cs));
+                ctx->stats.d2h_bytes += chunk * (k1 - k0);
+            } else {
+                for (uint32_t j = k0; j < k1; ++j) {
+                    const uint32_t g = first_row + j * shard_n;
+                    bvht_rect rr = { region.x0, std::max(region.y0, g * tile), region.x1, std::min(region.y1, (g + 1) * tile) };
+                    if (rr.y0 < rr.y1 && (rc = copy_rows_d2h(ctx, host, dev, width, rr, elem, cs))) return rc;
                 }
             }
         }
         return BVHT_OK;
     };
-    for (uint32_t i = 0; i < n_bands; ++i) {
-        if ((rc = run_band(i)) != BVHT_OK) {
-            // bands already queued on the forked streams must not outlive this call: the next one resets their work counters
-            for (cudaStream_t st : { ctx->aux[0], ctx->aux[1], ctx->copy_stream }) cudaStreamSynchronize(st);
+    // belt and braces: once the kernels are done every flag is raised from the stream itself, so a copy can never wait forever
+    auto raise_all_flags = [&]() -> int {
+        int rc2 = ensure_pinned(ctx, 1 << 16);
+        if (rc2) return rc2;
+        unsigned int* fill = (unsigned int*)ctx->pinned;
+        for (uint32_t j = 0; j < 32; ++j) fill[j] = plan.seq;
+        CU(ctx, cudaMemcpyAsync((unsigned int*)ctx->work_counter.p + kWordBandFlag, fill, 32 * 4, cudaMemcpyHostToDevice, ctx->stream));
+        return BVHT_OK;
+    };
+    for (uint32_t i = 0; i < plan.n_bands; ++i) {
+        const uint32_t k = plan.order[i];
+        rc = BVHT_OK;
+        cudaStream_t cs = ctx->copy_streams[i % n_cs];
+        if (plan.flags && wait_value(cs, flag_base + 4ull * k, plan.seq, 1u /* CU_STREAM_WAIT_VALUE_GEQ */) != 0)
+            rc = fail(ctx, BVHT_ERR_CUDA, "cuStreamWaitValue32 failed");
+        if (!rc) rc = copy_band(k, cs);
+        if (rc) {
+            // what is already queued must not outlive this call: let the kernels finish, then release the waiting copies
+            if (plan.flags) raise_all_flags();
             cudaStreamSynchronize(ctx->stream);
+            for (int c = 0; c < 3; ++c) cudaStreamSynchronize(ctx->copy_streams[c]);
             cudaGetLastError();
-            ctx->cover_ready = false;
             return rc;
         }
+        if (i < 16) cudaEventRecord(ctx->ev_copy_t[i], cs);
     }
-    CU(ctx, cudaEventRecord(ctx->ev_join, ctx->copy_stream));
-    CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    if (plan.flags && (rc = raise_all_flags())) return rc;     // queued after the copies: the first copy reaches its stream earlier
+    for (int c = 0; c < n_cs; ++c) {
+        CU(ctx, cudaEventRecord(ctx->ev_copy_join[c], ctx->copy_streams[c]));
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_join[c], 0));
+    }
     cudaEventRecord(ctx->ev_b, ctx->stream);
     ctx->trace_timed = true;
-    ctx->stats.last_trace_rays = rays / ctx->shard_count;
-    ctx->cover_ready = false;
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    // per-band kernel times of this frame -> launch order of the next one.  The kernels of consecutive bands sit on two
-    // streams and run back to back, so the end-to-end distance of their end events is the band's share of the frame.
-    {
-        hist.valid = true; hist.n = n_bands; memcpy(hist.key, hist_key, sizeof hist_key);
-        float prev = 0.0f;
-        for (uint32_t i = 0; i < n_bands && hist.valid; ++i) {
-            float t = 0.0f;
-            if (cudaEventElapsedTime(&t, ctx->ev_band_t[0], ctx->ev_band_t[i + 1]) != cudaSuccess) { cudaGetLastError(); hist.valid = false; break; }
-            const uint32_t b = order[i];
-            const uint32_t rows = std::max(1u, band_start[b + 1] - band_start[b]);
-            hist.ms_per_row[b] = std::max(t - prev, 0.0f) / (float)rows;
-            prev = std::max(prev, t);
-        }
-    }
+    ctx->tl_bands = std::min(plan.n_bands, 16u); ctx->tl_valid = true;
+    for (uint32_t i = 0; i < ctx->tl_bands; ++i) ctx->tl_rows[i] = std::min(own_rows, (plan.order[i] + 1u) * plan.band_rows) - plan.order[i] * plan.band_rows;
     return BVHT_OK;
 }
 
@@ -2114,7 +2251,7 @@ int bvht_debug_trace_stats(bvht_ctx* ctx, const bvht_camera* camera, uint32_t wi
     DevBuf cnt;
     if ((rc = ensure(ctx, cnt, 16 * sizeof(uint64_t)))) return rc;
     cudaMemsetAsync(cnt.p, 0, 16 * sizeof(uint64_t), ctx->stream);
-    cudaMemsetAsync(ctx->work_counter.p, 0, 8, ctx->stream);
+    cudaMemsetAsync(ctx->work_counter.p, 0, kWordBandFlag * 4, ctx->stream);
     // exactly the frame bvht_render_frame_device launches (coverage raster, K0, kernel flavour, shard), instrumented
     rc = prepare_cover(ctx, camera, width, height, tile, ctx->stream);
     if (!rc) rc = launch_primary_region(ctx, scene, camera, width, height, tile, region, nullptr, ctx->out_buf.p, nullptr, ctx->stream, 0,
@@ -2129,6 +2266,27 @@ int bvht_debug_trace_stats(bvht_ctx* ctx, const bvht_camera* camera, uint32_t wi
     // [0] counts the rays K1 generated; add those of blocks it never generated a ray for (K0's and its own empty blocks)
     const uint64_t region_rays = (uint64_t)(region.x1 - region.x0) * (region.y1 - region.y0) / ctx->shard_count;
     counters_out[15] = region_rays;
+    return BVHT_OK;
+}
+
+int bvht_debug_frame_timeline(bvht_ctx* ctx, float* ms_out, uint32_t capacity, uint32_t* n_out) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    if (!ms_out || !n_out) return fail(ctx, BVHT_ERR_INVALID_ARG, "null pointer argument");
+    *n_out = 0;
+    if (!ctx->tl_valid || !ctx->trace_timed) return fail(ctx, BVHT_ERR_NOT_READY, "no bvht_render_frame timeline recorded");
+    const uint32_t need = 2 + 3 * ctx->tl_bands;
+    if (capacity < need) return fail(ctx, BVHT_ERR_INVALID_ARG, "room for %u values, %u needed", capacity, need);
+    cudaSetDevice(ctx->device);
+    CU(ctx, cudaEventSynchronize(ctx->ev_b));
+    auto since = [&](cudaEvent_t e) { float t = -1.0f; if (cudaEventElapsedTime(&t, ctx->ev_a, e) != cudaSuccess) { cudaGetLastError(); t = -1.0f; } return t; };
+    ms_out[0] = since(ctx->ev_cover_t);
+    ms_out[1] = since(ctx->ev_b);
+    for (uint32_t i = 0; i < ctx->tl_bands; ++i) {
+        ms_out[2 + 3 * i] = since(ctx->ev_band_t[0]);          // every kernel of the frame done (one launch traces all bands)
+        ms_out[3 + 3 * i] = since(ctx->ev_copy_t[i]);
+        ms_out[4 + 3 * i] = (float)ctx->tl_rows[i];
+    }
+    *n_out = need;
     return BVHT_OK;
 }
 

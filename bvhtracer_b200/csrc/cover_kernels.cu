@@ -29,6 +29,7 @@ __device__ __forceinline__ void mark(uint32_t* cover, uint32_t ntx, int bx, int 
 __global__ void __launch_bounds__(256)
 raster_cover_kernel(const __grid_constant__ CoverParams P) {
     const uint32_t g = blockIdx.x * 256u + threadIdx.x;
+    if (g == 0u && P.full_init) atomicOr(P.full, P.full_init);
     if (g >= P.tri_offset[P.n_inst]) return;
     uint32_t i = 0;
     while (i + 1 < P.n_inst && g >= P.tri_offset[i + 1]) ++i;
@@ -81,8 +82,10 @@ raster_cover_kernel(const __grid_constant__ CoverParams P) {
     const int bx0 = px0 >> 3, bx1 = px1 >> 3, by0 = py0 >> 2, by1 = py1 >> 2;
     const uint32_t count = (uint32_t)(bx1 - bx0 + 1) * (uint32_t)(by1 - by0 + 1);
     if (count <= 64u) {
-        for (int by = by0; by <= by1; ++by)
+        for (int by = by0; by <= by1; ++by) {
+            if (P.shard_count > 1u && ((uint32_t)(by >> 1) % P.shard_count) != P.shard_index) continue;     // another GPU's tile row
             for (int bx = bx0; bx <= bx1; ++bx) mark(P.cover, P.ntx, bx, by, bit);
+        }
     } else {
         const uint32_t at = atomicAdd(P.big_count, 1u);
         if (at < P.big_cap) P.big_list[at] = make_int4((int)i, (bx0 << 16) | bx1, (by0 << 16) | by1, 0);
@@ -98,7 +101,11 @@ raster_big_kernel(const __grid_constant__ CoverParams P) {
         const uint32_t bit = 1u << r.x;
         const int bx0 = r.y >> 16, bx1 = r.y & 0xFFFF, by0 = r.z >> 16, by1 = r.z & 0xFFFF;
         const int w = bx1 - bx0 + 1, total = w * (by1 - by0 + 1);
-        for (int k = (int)threadIdx.x; k < total; k += 256) mark(P.cover, P.ntx, bx0 + k % w, by0 + k / w, bit);
+        for (int k = (int)threadIdx.x; k < total; k += 256) {
+            const int by = by0 + k / w;
+            if (P.shard_count > 1u && ((uint32_t)(by >> 1) % P.shard_count) != P.shard_index) continue;
+            mark(P.cover, P.ntx, bx0 + k % w, by, bit);
+        }
     }
 }
 

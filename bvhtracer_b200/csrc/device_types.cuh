@@ -86,7 +86,19 @@ struct PrimaryParams {
     // accel + candidate masks: K0 (classify_fill_kernel) writes the records of the blocks no instance can be seen from and
     // lists the others here; K1 then pulls list positions instead of block numbers.  null = K1 walks every block itself.
     uint32_t*     work_list;
-    unsigned int* work_count;            // number of listed blocks (device counter, zeroed before K0)
+    // Bands.  The launch's pixel blocks, in their row-major numbering, are cut into n_bands runs of band_items blocks (whole tile
+    // rows; the last run may be shorter).  K1 pulls them band by band in band_order -- the host puts the cheapest bands first,
+    // so that the frame ends with its most expensive rows and the device->host copies of the earlier bands hide behind them --
+    // and raises band_flag[b] to band_seq when the last block of band b is finished: the copy of that band's rows waits for the
+    // flag on another stream (cuStreamWaitValue32), with no host round trip and no kernel boundary between bands.
+    uint32_t      n_bands;               // 1..32
+    uint32_t      band_items;            // blocks per band = rows per band * ntx * items_per_tile
+    uint8_t       band_order[32];        // pull position -> band
+    unsigned int* band_count;            // [32] blocks K0 listed per band (zeroed before K0); with a work list, band b's entries
+                                         //   are work_list[b * band_items .. + band_count[b])
+    unsigned int* band_done;             // [32] blocks finished per band (zeroed per frame); null = no completion flags
+    unsigned int* band_flag;             // [32]
+    uint32_t      band_seq;
     unsigned long long* stats;           // debug counters (stats build only)
     // accel only: conservative screen-space rectangle (pixels, inclusive) of each instance's tight box for THIS camera;
     // n_rect == 0 disables the tile-level candidate masks
@@ -108,7 +120,8 @@ struct PrimaryParams {
 // cover_kernels.cu: rasterise every instance's triangles (conservative boxes) onto the 8x4-pixel blocks of the frame
 struct CoverParams {
     uint32_t*       cover;          // one word per block, zeroed before the launch
-    uint32_t*       full;           // one word
+    uint32_t*       full;           // one word, zeroed before the launch
+    uint32_t        full_init;      // instances the host already knows to be visible everywhere (OR-ed into *full by the kernel)
     uint32_t*       big_count;      // one word, zeroed
     int4*           big_list;       // big_cap entries: {instance, bx0 << 16 | bx1, by0 << 16 | by1, -}
     uint32_t        big_cap;
@@ -117,6 +130,7 @@ struct CoverParams {
     uint32_t        n_inst;         // <= 32
     uint32_t        tri_offset[33]; // prefix sums of the instances' triangle counts
     uint32_t        ntx;            // tiles (= blocks) per row of the full frame
+    uint32_t        shard_index, shard_count;   // multi-GPU: only the tile rows r with r % shard_count == shard_index are marked
     uint32_t        width, height;
     float           tlx, tly, inv_ex, inv_ey, near_, z_eps;     // near-plane rectangle of the camera (eye space)
     float           mv[32][12];     // per instance: view * object transform, rows 0..2 (row-major 3 x 4)

@@ -130,32 +130,39 @@ struct Builder {
 
 } // namespace
 
-ModelStats compute_model_stats(const float* tris, uint32_t n_tris) {
+// One pass, on the frame path of deforming models (bvht_blas_update_vertices): the conservative quantities (radius, longest
+// edge, largest |e1||e2|) are maxima, taken over SQUARES with one square root at the end (sqrt is monotonic: same value as the
+// maximum of the roots); only the two means, which steer a heuristic, need a root per triangle, in single precision.
+// kappa_out (optional): |e1||e2| of every triangle, rounded up, 0 for degenerate ones -- what bake_accel needs per triangle.
+ModelStats compute_model_stats(const float* tris, uint32_t n_tris, std::vector<float>* kappa_out) {
     ModelStats m;
-    double radius = 0.0, max_edge = 0.0, kmax = 0.0, sum_edge = 0.0, sum_kappa = 0.0;
+    double radius2 = 0.0, max_edge2 = 0.0, kmax2 = 0.0, sum_edge = 0.0, sum_kappa = 0.0;
     uint64_t n_good = 0;
     Box mb; mb.reset(); bool any = false;
+    if (kappa_out) kappa_out->assign(n_tris, 0.0f);
     for (uint32_t i = 0; i < n_tris; ++i) {
         const float* t = tris + (size_t)i * 9;
-        double e1[3], e2[3], e3[3];
-        for (int k = 0; k < 3; ++k) { e1[k] = (double)t[3 + k] - t[k]; e2[k] = (double)t[6 + k] - t[k]; e3[k] = (double)t[6 + k] - t[3 + k]; }
-        double l1 = std::sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
-        double l2 = std::sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
-        double l3 = std::sqrt(e3[0] * e3[0] + e3[1] * e3[1] + e3[2] * e3[2]);
-        double kappa = l1 * l2;
-        if (!(kappa > 0.0)) continue;           // degenerate (e.g. the 999 sentinel): area == 0 exactly, never accepted
-        for (int v = 0; v < 3; ++v) {
-            double n = std::sqrt((double)t[3 * v] * t[3 * v] + (double)t[3 * v + 1] * t[3 * v + 1] + (double)t[3 * v + 2] * t[3 * v + 2]);
-            radius = std::max(radius, n);
+        double l1 = 0.0, l2 = 0.0, l3 = 0.0, n0 = 0.0, n1 = 0.0, n2 = 0.0;
+        for (int k = 0; k < 3; ++k) {
+            const double a = t[k], b_ = t[3 + k], c = t[6 + k];
+            const double e1 = b_ - a, e2 = c - a, e3 = c - b_;
+            l1 += e1 * e1; l2 += e2 * e2; l3 += e3 * e3;
+            n0 += a * a; n1 += b_ * b_; n2 += c * c;
         }
-        max_edge = std::max(max_edge, std::max(l1, std::max(l2, l3)));
-        kmax = std::max(kmax, kappa);
-        sum_edge += l1; sum_kappa += kappa; ++n_good;
+        const double kappa2 = l1 * l2;
+        if (!(kappa2 > 0.0)) continue;          // degenerate (e.g. the 999 sentinel): area == 0 exactly, never accepted
+        radius2 = std::max(radius2, std::max(n0, std::max(n1, n2)));
+        max_edge2 = std::max(max_edge2, std::max(l1, std::max(l2, l3)));
+        kmax2 = std::max(kmax2, kappa2);
+        const float kf = std::sqrt((float)kappa2);
+        sum_edge += (double)std::sqrt((float)l1); sum_kappa += (double)kf; ++n_good;
+        if (kappa_out) (*kappa_out)[i] = kf * 1.000001f + 1e-37f;           // >= the exact product (float sqrt is within 1 ulp)
         mb.grow(t); mb.grow(t + 3); mb.grow(t + 6); any = true;
     }
     if (n_good) { m.mean_edge = sum_edge / (double)n_good; m.mean_kappa = sum_kappa / (double)n_good; }
+    const double radius = std::sqrt(radius2);
     m.radius = radius > 0.0 ? radius : 1.0;
-    m.max_edge = max_edge; m.model_kappa = kmax; m.model_valid = any;
+    m.max_edge = std::sqrt(max_edge2); m.model_kappa = std::sqrt(kmax2); m.model_valid = any;
     if (any) for (int k = 0; k < 3; ++k) { m.model_lo[k] = mb.lo[k]; m.model_hi[k] = mb.hi[k]; }
     return m;
 }

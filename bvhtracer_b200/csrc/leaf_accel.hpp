@@ -72,7 +72,7 @@ struct ModelStats {
     float  model_lo[3] = { 0, 0, 0 }, model_hi[3] = { 0, 0, 0 };
     bool   model_valid = false;
 };
-ModelStats compute_model_stats(const float* tris, uint32_t n_tris);
+ModelStats compute_model_stats(const float* tris, uint32_t n_tris, std::vector<float>* kappa_out = nullptr);
 
 // tris: n_tris x 9 floats in reference order; nodes: reference nodes (bvht_bvh_node layout: min[3], max[3], count, left_first)
 bool build_leaf_accel(const float* tris, uint32_t n_tris, const void* nodes, uint32_t nodes_used,

@@ -748,8 +748,34 @@ trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
     const unsigned lane = threadIdx.x & 31u;
     Stat st;
     __shared__ uint8_t s_skip[PRUNE ? 4 : 1][64];
-    // with a work list (K0 ran first) only the listed blocks are pulled; the others already hold their miss records
-    const unsigned n_work = P.work_list ? __ldcg(P.work_count) : P.n_items;
+    // Bands (device_types.cuh): s_band_end[j] = END of pull position j's run of blocks (inclusive prefix sum of the bands' block
+    // counts in pull order; shared memory, not registers: the trace below needs every one of its 64).  With a work list (K0 ran
+    // first) only the listed blocks are pulled; the others already hold their miss records.
+    __shared__ unsigned s_band_end[32];
+    __shared__ unsigned s_slot[4];
+    if (threadIdx.x < 32u) {
+        unsigned cnt = 0, band = 0;
+        if (lane < P.n_bands) {
+            band = P.band_order[lane];
+            if (P.work_list) cnt = __ldcg(P.band_count + band);
+            else {
+                const unsigned lo = band * P.band_items;
+                cnt = lo < P.n_items ? min(P.band_items, P.n_items - lo) : 0u;
+            }
+        }
+        unsigned end = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned v = __shfl_up_sync(0xFFFFFFFFu, end, off);
+            if (lane >= (unsigned)off) end += v;
+        }
+        s_band_end[lane] = end;
+        // a band without any block to trace is complete as soon as K0 is (this kernel started after it)
+        if (P.band_done && blockIdx.x == 0 && lane < P.n_bands && cnt == 0u)
+            *reinterpret_cast<volatile unsigned*>(P.band_flag + band) = P.band_seq;
+    }
+    __syncthreads();
+    const unsigned n_work = s_band_end[31];
     for (;;) {
         unsigned base = 0;
         if (lane == 0) base = atomicAdd(P.work_counter, (unsigned)BVHT_GRAB);
@@ -758,8 +784,16 @@ trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
 #pragma unroll 1
       for (unsigned g = 0; g < (unsigned)BVHT_GRAB; ++g) {
         if (base + g >= n_work) break;
-        // row-major order: strided permutations measured 2-15 % slower (locality, cheap tail)
-        const unsigned item = P.work_list ? __ldcg(P.work_list + base + g) : base + g;
+        // pull position -> band -> block (row-major inside a band: strided permutations measured 2-15 % slower)
+        const unsigned pos = base + g;
+        unsigned item;
+        {
+            const unsigned slot = (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, pos >= s_band_end[lane]));
+            const unsigned slot_begin = slot ? s_band_end[slot - 1] : 0u;
+            const unsigned in_band = (unsigned)P.band_order[slot] * P.band_items + (pos - slot_begin);
+            item = P.work_list ? __ldcg(P.work_list + in_band) : in_band;
+            if (lane == 0) s_slot[threadIdx.x >> 5] = slot;
+        }
 #ifdef BVHT_SLICE_LOG
         unsigned long long log_t0 = 0;                 // profiling build only (tools/slice_timeline.py): start / end of every block
         if (P.stats) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(log_t0));
@@ -813,6 +847,25 @@ trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
             }
             if (P.out_rgba) P.out_rgba[(size_t)py * P.width + px] = shade_pixel(P, h);
         }
+        if (P.band_done) {
+            // A block counts as finished only when its pixels are in memory.  A warp-wide __threadfence() here cost 0.09 ms of a
+            // 0.80 ms frame (profiles/r02_e2e_timeline.txt); instead the warp synchronises (the lanes' stores happen-before lane 0's
+            // next operation) and lane 0 counts the block with a RELEASE read-modify-write at GPU scope, which is cumulative over
+            // what it has observed.  Whoever counts a band's last block fences (acquire side of the chain, system scope for the
+            // copy engine) and raises the band's flag.
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned slot = s_slot[threadIdx.x >> 5];
+                const unsigned band_total = s_band_end[slot] - (slot ? s_band_end[slot - 1] : 0u);
+                const unsigned band_id = P.band_order[slot];
+                unsigned before;
+                asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(before) : "l"(P.band_done + band_id) : "memory");
+                if (before + 1u == band_total) {
+                    __threadfence_system();
+                    *reinterpret_cast<volatile unsigned*>(P.band_flag + band_id) = P.band_seq;
+                }
+            }
+        }
 #ifdef BVHT_SLICE_LOG
         __syncwarp();
         if (P.stats && lane == 0) {
@@ -865,11 +918,15 @@ classify_fill_kernel(const __grid_constant__ PrimaryParams P) {
     }
     const unsigned listed = __ballot_sync(0xFFFFFFFFu, valid && seen);
     unsigned empty = __ballot_sync(0xFFFFFFFFu, valid && !seen);
-    if (listed) {
+    if (valid && seen) {
+        // append to the block's BAND's segment of the list (device_types.cuh): the lanes of one band share one atomic
+        const unsigned band = item / P.band_items;
+        const unsigned peers = __match_any_sync(listed, band);
+        const int leader = __ffs((int)peers) - 1;
         unsigned at = 0;
-        if (lane == 0) at = atomicAdd(P.work_count, (unsigned)__popc(listed));
-        at = __shfl_sync(0xFFFFFFFFu, at, 0);
-        if (valid && seen) P.work_list[at + __popc(listed & ((1u << lane) - 1u))] = item;
+        if ((int)lane == leader) at = atomicAdd(P.band_count + band, (unsigned)__popc(peers));
+        at = __shfl_sync(peers, at, leader);
+        P.work_list[(size_t)band * P.band_items + at + __popc(peers & ((1u << lane) - 1u))] = item;
     }
     HitRec miss;
     miss.t = FLT_MAX; miss.u = 0.0f; miss.v = 0.0f; miss.id = 0xFFFFFFFFu;

@@ -249,6 +249,15 @@ class Engine:
         self._check(self._lib.bvht_debug_read_bandwidth(self._ctx, int(nbytes), int(passes), C.byref(g)))
         return float(g.value)
 
+    def debug_frame_timeline(self):
+        """Device timeline of the last render_frame (ms since its first device operation): dict with the coverage raster's end,
+        the frame's end and, per band in launch order, (kernel end, copy end, tile rows)."""
+        out = np.zeros(2 + 3 * 16, "<f4")
+        n = C.c_uint32()
+        self._check(self._lib.bvht_debug_frame_timeline(self._ctx, ptr(out), out.size, C.byref(n)))
+        bands = [(float(out[2 + 3 * i]), float(out[3 + 3 * i]), int(out[4 + 3 * i])) for i in range((n.value - 2) // 3)]
+        return {"cover_done_ms": float(out[0]), "frame_done_ms": float(out[1]), "bands": bands}
+
     def debug_trace_stats(self, camera, width, height, tile=8, region=None):
         """Per-frame work counters of the instrumented strict build, launched exactly like render_frame_device (coverage raster,
         K0, kernel flavour).  "rays" = rays of the region; "rays_traced" = those K1 generated a ray for.  Not a product path."""

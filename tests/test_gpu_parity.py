@@ -418,6 +418,54 @@ def test_render_frame_bands_full_size_equal_single_launch():
     assert np.array_equal(frame, O.shade(1, hits))
 
 
+@pytest.mark.parametrize("scene_name,size", [("sixteen_armadillos", (1283, 717)), ("cube", (333, 251))])
+def test_pipelined_host_frame_every_band_plan(scene_name, size):
+    # bvht_render_frame traces a frame with ONE launch that pulls its pixel blocks band by band and raises a flag per finished band;
+    # the device->host copies wait for the flags on other streams.  Every band count, pull order and number of copy streams must
+    # deliver the same bytes as the plain device frame -- ragged sizes, sub-regions and tile-row shards included.  (A band whose
+    # copy ran before its pixels were written would show up as stale data: the host buffers are poisoned before every call.)
+    spec = examples.sixteen_armadillos(3) if scene_name == "sixteen_armadillos" else examples.cube()
+    scene, cam = SB.oracle_scene(spec)
+    w, h = size
+    fcam = SB.to_ffi_camera(cam)
+    ref = scene.render(cam, w, h, threads=NTHREADS)
+    ref_frame = O.shade(1, ref)
+    with Engine(flags=FLAG_STRICT | FLAG_LEAF_ACCEL) as eng:
+        SB.upload_scene(eng, scene)
+        shade = eng.shade_depth()
+        frame = np.zeros(w * h, "<u4")
+        hits = np.zeros(w * h, _ffi.HIT)
+        for bands, order, streams in [(1, 0, 1), (2, 1, 1), (3, 2, 2), (7, 3, 3), (16, 1, 2), (32, 1, 3), (32, 0, 1), (-1, -1, -1)]:
+            eng.set_option(_ffi.OPT_BANDS, bands)
+            eng.set_option(_ffi.OPT_BAND_ORDER, order)
+            eng.set_option(_ffi.OPT_COPY_STREAMS, streams)
+            for k0 in (0, 1):
+                eng.set_option(_ffi.OPT_K0, k0)
+                frame[:] = 0xDEADBEEF
+                hits.view(np.uint8)[:] = 0xA5
+                eng.render_frame(fcam, w, h, shade, frame_out=frame, hits_out=hits)
+                assert hits.tobytes() == ref.tobytes(), (bands, order, streams, k0)
+                assert frame.tobytes() == ref_frame.tobytes(), (bands, order, streams, k0)
+        eng.set_option(_ffi.OPT_K0, -1)
+        # a sub-region: only its pixels are written
+        eng.set_option(_ffi.OPT_BANDS, 5)
+        region = (40, 24, w - 33, h - 19)
+        frame[:] = 0xDEADBEEF
+        eng.render_frame(fcam, w, h, shade, region=region, frame_out=frame)
+        inside = np.zeros((h, w), bool)
+        inside[region[1]:region[3], region[0]:region[2]] = True
+        inside = inside.reshape(-1)
+        assert np.array_equal(frame[inside], ref_frame[inside]) and (frame[~inside] == 0xDEADBEEF).all()
+        # three tile-row shards into ONE host frame, each with its own band plan
+        frame[:] = 0xDEADBEEF
+        for shard, bands in ((0, 4), (1, 1), (2, 9)):
+            eng.set_shard(shard, 3)
+            eng.set_option(_ffi.OPT_BANDS, bands)
+            eng.render_frame(fcam, w, h, shade, frame_out=frame)
+        eng.set_shard(0, 1)
+        assert frame.tobytes() == ref_frame.tobytes()
+
+
 # ------------------------------------------------------------------------------------------ through the host mirror
 def test_host_mirror_renderer_animated_frames():
     # Renderer::new(Box::new(CudaPathTracer::new())) + AppState::update loop of sixteen_armadillos.rs:132-163
