@@ -43,7 +43,6 @@ struct Blas {
     uint32_t n_tris = 0, nodes_used = 0;
     std::vector<bvht_bvh_node> h_nodes;     // host copy of the uploaded node pool (topology for validation / accel)
     std::vector<float> h_tris;              // host copy of the vertices (needed to rebuild the leaf accelerator)
-    std::vector<float> h_kappa;             // |e1||e2| per triangle, rounded up (compute_model_stats): the bake's per-triangle inflation
     bool global_accel = false;              // fast mode: ONE sub-BVH over the whole model instead of one per reference leaf
     std::vector<uint32_t> perm;             // device-built models: perm[i] = index, in the caller's array, of the triangle at i
     DevBuf tris_aos, nodes, tri, normals;      // normals: 3 float4 per primitive, ORIGINAL primitive order
@@ -128,6 +127,7 @@ struct bvht_ctx {
     DevBuf blas_desc;                                 // BlasDesc[blas.size()]
     bool blas_desc_dirty = true;
     DevBuf tlas, inst_cols, inst_blas, tlas_tight, tlas_mask;
+    DevBuf stats_scratch;                             // ModelStatsDev + 6 x u64 of the device statistics / tight-box reductions
     DevBuf scene_in, scene_bounds;                    // K6 input (transforms, ids) and output (world boxes + status)
     std::vector<float> h_inst_bounds;                 // SceneObject::bounds of every instance after bvht_scene_set_transforms
     uint32_t tlas_nodes_used = 0, n_inst = 0;
@@ -293,6 +293,38 @@ int upload_u32(bvht_ctx* ctx, DevBuf& d, const std::vector<uint32_t>& v) {
     return h2d(ctx, d.p, v.data(), v.size() * 4);
 }
 
+double dec_f64(unsigned long long u) {            // inverse of upload_kernels.cu enc_f64
+    unsigned long long b = (u >> 63) ? (u & 0x7FFFFFFFFFFFFFFFull) : ~u;
+    double d; memcpy(&d, &b, 8); return d;
+}
+float dec_f32(unsigned int u) {
+    unsigned int b = (u >> 31) ? (u & 0x7FFFFFFFu) : ~u;
+    float f; memcpy(&f, &b, 4); return f;
+}
+
+// compute_model_stats (leaf_accel.cpp) over the model's resident vertices, on the device: one streaming kernel + an 80-byte
+// read-back instead of a 0.25 ms host pass per frame of a deforming model.
+int device_model_stats(bvht_ctx* ctx, const Blas& b, ModelStats& m) {
+    int rc = ensure(ctx, ctx->stats_scratch, sizeof(ModelStatsDev) + 64);
+    if (rc) return rc;
+    ModelStatsDev* d = (ModelStatsDev*)ctx->stats_scratch.p;
+    CU(ctx, launch_model_stats((const float*)b.tris_aos.p, b.n_tris, d, ctx->stream));
+    ctx->stats.kernel_launches += 1;
+    ModelStatsDev h;
+    CU(ctx, cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    m = ModelStats();
+    if (h.n_good) {
+        m.mean_edge = h.sum_edge / (double)h.n_good; m.mean_kappa = h.sum_kappa / (double)h.n_good;
+        const double radius = std::sqrt(dec_f64(h.radius2));
+        m.radius = radius > 0.0 ? radius : 1.0;
+        m.max_edge = std::sqrt(dec_f64(h.max_edge2)); m.model_kappa = std::sqrt(dec_f64(h.kappa2_max));
+        m.model_valid = true;
+        for (int k = 0; k < 3; ++k) { m.model_lo[k] = dec_f32(h.lo[k]); m.model_hi[k] = dec_f32(h.hi[k]); }
+    }
+    return BVHT_OK;
+}
+
 // (Re)inflate the sub-BVH of one model for model-space rays with |d| <= d_max, |o| <= o_max (device kernel) and
 // recompute its whole-model tight box (host, rounded outwards).
 int bake_accel(bvht_ctx* ctx, Blas& b, double d_max, double o_max) {
@@ -319,24 +351,17 @@ int bake_accel(bvht_ctx* ctx, Blas& b, double d_max, double o_max) {
         // union -- one large triangle (big_ben_clock: max |e1||e2| = 0.83 against a median of 0.0014) no longer widens the
         // whole model's box, and with it the instance's screen rectangle, by its own slack
         double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
-        const float* T = b.h_tris.data();
-        const bool have_kappa = b.h_kappa.size() == b.n_tris;
-        for (uint32_t i = 0; i < b.n_tris && b.h_tris.size() >= (size_t)b.n_tris * 9; ++i) {
-            const float* t = T + (size_t)i * 9;
-            double kp;
-            if (have_kappa) kp = (double)b.h_kappa[i];
-            else {
-                double e1[3], e2[3];
-                for (int k = 0; k < 3; ++k) { e1[k] = (double)t[3 + k] - t[k]; e2[k] = (double)t[6 + k] - t[k]; }
-                kp = std::sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]) * std::sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
-            }
-            if (!(kp > 0.0)) continue;
-            double delta = (double)fs * kp * (1.0 + 1e-9) + (double)fa;
-            for (int k = 0; k < 3; ++k) {
-                double l = std::min({ (double)t[k], (double)t[3 + k], (double)t[6 + k] }), h = std::max({ (double)t[k], (double)t[3 + k], (double)t[6 + k] });
-                lo[k] = std::min(lo[k], l - delta - std::fabs(l) * 1e-6);
-                hi[k] = std::max(hi[k], h + delta + std::fabs(h) * 1e-6);
-            }
+        if (b.tris_aos.p && b.n_tris) {
+            // on the device (tight_box_kernel: the arithmetic of the host loop this replaces, in double), 48 bytes back
+            int rc = ensure(ctx, ctx->stats_scratch, sizeof(ModelStatsDev) + 64);
+            if (rc) return rc;
+            unsigned long long* d6 = (unsigned long long*)((char*)ctx->stats_scratch.p + sizeof(ModelStatsDev) + 8);
+            CU(ctx, launch_tight_box((const float*)b.tris_aos.p, b.n_tris, (double)fs, (double)fa, d6, ctx->stream));
+            ctx->stats.kernel_launches += 1;
+            unsigned long long h6[6];
+            CU(ctx, cudaMemcpyAsync(h6, d6, sizeof h6, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            if (h6[0] != ~0ull) for (int k = 0; k < 3; ++k) { lo[k] = dec_f64(h6[k]); hi[k] = dec_f64(h6[3 + k]); }
         }
         if (!(lo[0] <= hi[0])) {      // no host copy of the triangles: the whole-model bound
             double delta = (double)fs * b.model_kappa + (double)fa;
@@ -389,7 +414,7 @@ int build_accel_device(bvht_ctx* ctx, Blas& b, const LeafAccelConfig& cfg, bool&
     // model's largest triangles, and a few triangles hundreds of times larger than the typical one (Big Ben: max |e1||e2| =
     // 115 x the mean; armadillo 6 x, teapot 3 x) drag their inflation through every box above them.  So: global tree when the
     // largest edge product is within 32 x the mean.  Knobs::fast_global forces it off / on (experiment builds).
-    ModelStats ms = compute_model_stats(b.h_tris.data(), b.n_tris, &b.h_kappa);
+    ModelStats ms = compute_model_stats(b.h_tris.data(), b.n_tris);
     {
         bool want = ms.mean_kappa > 0.0 && ms.model_kappa <= 32.0 * ms.mean_kappa && b.n_tris >= 64;    // (a dozen triangles: brute force wins)
         if (ctx->knobs.fast_global >= 0) want = ctx->knobs.fast_global == 1;
@@ -462,7 +487,7 @@ int build_and_upload_accel(bvht_ctx* ctx, Blas& b) {
     b.n_sub_nodes = (uint32_t)(acc.sub_raw.size() / 16);
     b.radius = acc.radius; b.max_edge = acc.max_edge; b.model_kappa = acc.model_kappa; b.model_valid = acc.model_valid;
     memcpy(b.model_lo, acc.model_lo, 12); memcpy(b.model_hi, acc.model_hi, 12);
-    set_useful_product(b, compute_model_stats(b.h_tris.data(), b.n_tris, &b.h_kappa), cfg);
+    set_useful_product(b, compute_model_stats(b.h_tris.data(), b.n_tris), cfg);
     int rc;
     if ((rc = ensure(ctx, b.sub_raw, acc.sub_raw.size() * 4))) return rc;
     if ((rc = ensure(ctx, b.sub_nodes, acc.sub_raw.size() * 4))) return rc;
@@ -492,7 +517,8 @@ int refit_accel(bvht_ctx* ctx, Blas& b) {
     CU(ctx, launch_refit_sub_nodes((float4*)b.sub_raw.p, (const uint32_t*)b.sub_parent.p, (unsigned int*)b.sub_counters.p,
                                    (const float*)b.tris_aos.p, (const uint32_t*)b.sub_order.p, b.n_sub_nodes, ctx->stream));
     ctx->stats.kernel_launches += 2;
-    ModelStats ms = compute_model_stats(b.h_tris.data(), b.n_tris, &b.h_kappa);
+    ModelStats ms;
+    { int rc = device_model_stats(ctx, b, ms); if (rc) return rc; }
     b.radius = ms.radius; b.max_edge = ms.max_edge; b.model_kappa = ms.model_kappa; b.model_valid = ms.model_valid;
     memcpy(b.model_lo, ms.model_lo, 12); memcpy(b.model_hi, ms.model_hi, 12);
     set_useful_product(b, ms, LeafAccelConfig());
@@ -1074,7 +1100,7 @@ void bvht_destroy(bvht_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (Blas& b : ctx->blas) free_blas(b);
     for (DevBuf* d : { &ctx->blas_desc, &ctx->tlas, &ctx->inst_cols, &ctx->inst_blas, &ctx->work_counter, &ctx->work_list, &ctx->cover, &ctx->cover_aux, &ctx->out_buf, &ctx->rays_buf,
-                       &ctx->rgba_buf, &ctx->tlas_tight, &ctx->tlas_mask, &ctx->scene_in, &ctx->scene_bounds, &ctx->build_tris, &ctx->build_perm })
+                       &ctx->rgba_buf, &ctx->tlas_tight, &ctx->tlas_mask, &ctx->stats_scratch, &ctx->scene_in, &ctx->scene_bounds, &ctx->build_tris, &ctx->build_perm })
         release(*d);
     ctx->build_ws.release();
     for (cudaStream_t st : { ctx->aux[0], ctx->aux[1], ctx->copy_stream, ctx->copy_streams[1], ctx->copy_streams[2] }) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
@@ -1258,16 +1284,27 @@ int bvht_blas_update_vertices(bvht_ctx* ctx, uint32_t blas_id, const float* tris
     if (!tris && n_tris) return fail(ctx, BVHT_ERR_INVALID_ARG, "null vertex pointer");
     if (n_tris != b.n_tris) return fail(ctx, BVHT_ERR_INVALID_ARG, "vertex update with %u triangles, model has %u", n_tris, b.n_tris);
     cudaSetDevice(ctx->device);
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {              // experiment builds with BVHT_TIMING only
+        if (!ctx->knobs.timing) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bvht timing] update %-26s %8.3f ms (host)\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
     cudaEventRecord(ctx->ev_e, ctx->stream);
     int rc = upload_vertices(ctx, b, tris);
     if (rc) return rc;
+    lap("host copy + H2D + repack");
     if (accel_on(ctx)) {
         if ((rc = refit_accel(ctx, b))) return rc;
+        lap("sub refit + stats + bake");
         ctx->blas_desc_dirty = true;
         if (!ctx->h_inst.empty() && (rc = recompute_tlas_tight(ctx))) return rc;     // the model's tight box moved
+        lap("tight boxes");
     }
     cudaEventRecord(ctx->ev_f, ctx->stream);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    lap("stream sync");
     cudaEventElapsedTime(&ctx->stats.last_upload_ms, ctx->ev_e, ctx->ev_f);
     return BVHT_OK;
 }
@@ -1431,23 +1468,24 @@ int bvht_scene_set_transforms(bvht_ctx* ctx, const float* transforms, const uint
     if ((rc = ensure(ctx, ctx->tlas, tl_bytes))) return rc;
     if ((rc = ensure(ctx, ctx->inst_cols, ic_bytes))) return rc;
     if ((rc = ensure(ctx, ctx->inst_blas, ib_bytes))) return rc;
-    if ((rc = ensure(ctx, ctx->scene_in, ic_bytes + ib_bytes))) return rc;
-    if ((rc = ensure(ctx, ctx->scene_bounds, bd_bytes + 16))) return rc;
-    CU(ctx, cudaStreamSynchronize(ctx->stream));       // previous frame may still read the staging buffer
-    // staging: [transforms | ids] up, [tlas | inverses | bounds | status] down
-    const size_t up_bytes = ic_bytes + ib_bytes;
-    const size_t down_off = (up_bytes + 255) & ~size_t(255);
+    // ONE copy up, one kernel, ONE copy down (measured at the examples' n = 16: the call used to spend more time in its six
+    // small copies and their launches than in the kernel).  Up: [transforms | ids | pad | status = 0]; down: the kernel packs
+    // [tlas | inverses | bounds | status] contiguously.
+    const size_t st_off = (ic_bytes + ib_bytes + 15) & ~size_t(15);
+    const size_t up_bytes = st_off + 16;
     const size_t down_bytes = tl_bytes + ic_bytes + bd_bytes + 16;
-    if ((rc = ensure_pinned(ctx, down_off + down_bytes + 256))) return rc;
-    char* st = (char*)ctx->pinned;
+    if ((rc = ensure(ctx, ctx->scene_in, up_bytes))) return rc;
+    if ((rc = ensure(ctx, ctx->scene_bounds, bd_bytes + 64 + down_bytes))) return rc;     // bounds | pad | pack
+    bvht_ctx::Stage* stage = nullptr;
+    if ((rc = stage_get(ctx, up_bytes + 256 + down_bytes, &stage))) return rc;
+    char* st = (char*)stage->p;
     memcpy(st, transforms, ic_bytes);
     memcpy(st + ic_bytes, blas_ids, ib_bytes);
+    memset(st + ic_bytes + ib_bytes, 0, up_bytes - ic_bytes - ib_bytes);
     ctx->tlas_nodes_used = 0;                           // not traceable until the rebuild has been validated
     ctx->n_inst = 0;
     cudaEventRecord(ctx->ev_e, ctx->stream);
     if ((rc = h2d(ctx, ctx->scene_in.p, st, up_bytes))) return rc;
-    unsigned int* status = (unsigned int*)((char*)ctx->scene_bounds.p + bd_bytes);
-    CU(ctx, cudaMemsetAsync(status, 0, 16, ctx->stream));
     SceneRebuildParams p;
     p.transforms = (const float*)ctx->scene_in.p;
     p.blas_ids = (const uint32_t*)((const char*)ctx->scene_in.p + ic_bytes);
@@ -1456,16 +1494,16 @@ int bvht_scene_set_transforms(bvht_ctx* ctx, const float* transforms, const uint
     p.inst_cols = (float4*)ctx->inst_cols.p;
     p.inst_blas = (uint32_t*)ctx->inst_blas.p;
     p.inst_bounds = (float*)ctx->scene_bounds.p;
-    p.status = status;
+    p.status = (unsigned int*)((char*)ctx->scene_in.p + st_off);
+    p.pack = (char*)ctx->scene_bounds.p + ((bd_bytes + 16 + 15) & ~size_t(15));
     p.n_inst = n_instances;
     CU(ctx, launch_scene_rebuild(p, ctx->stream));
     ctx->stats.kernel_launches += 1;
-    char* down = st + down_off;
-    CU(ctx, cudaMemcpyAsync(down, ctx->tlas.p, tl_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(down + tl_bytes, ctx->inst_cols.p, ic_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(down + tl_bytes + ic_bytes, ctx->scene_bounds.p, bd_bytes + 16, cudaMemcpyDeviceToHost, ctx->stream));
+    char* down = st + ((up_bytes + 255) & ~size_t(255));
+    CU(ctx, cudaMemcpyAsync(down, p.pack, down_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     cudaEventRecord(ctx->ev_f, ctx->stream);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    stage->used = false;                                // drained: the slot may be reused without waiting
     ctx->stats.d2h_bytes += down_bytes;
     { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ctx->ev_e, ctx->ev_f) == cudaSuccess) ctx->stats.last_upload_ms = ms; }
     unsigned int st_words[4];
@@ -1521,14 +1559,15 @@ int bvht_tlas_read(bvht_ctx* ctx, bvht_tlas_node* nodes_out, uint32_t max_nodes,
 // Whether the per-triangle coverage raster (K7) is worth its 35-160 us for this scene.  A fixed rule, not a measurement, so
 // that which kernels a frame launches depends on the scene alone.  It pays when a block's rays would otherwise enter an
 // instance they cannot hit AND entering one is expensive: several instances of large models (measured on B200,
-// tools/cover_ab.py, off -> on: sixteen_armadillos 4K 0.855 -> 0.785 ms, two_armadillos 1080p 0.257 -> 0.244 ms).  It does
+// tools/cover_ab.py, off -> on: sixteen_armadillos 4K 0.855 -> 0.785 ms; two_armadillos 1080p 0.257 -> 0.244 ms on one box and
+// 0.257 -> 0.266 on another: within the noise for two instances side by side, so it needs three).  It does
 // not for small models (trippy_teapots 0.262 -> 0.297 ms, cube 0.023 -> 0.058 ms) nor for a single instance, where K0 with
 // the model's screen rectangle already removes the empty blocks (big_ben_clock 8K: 1.671 -> 1.675 ms).
-// Its cost is per triangle (every GPU projects every triangle; only the marking is sharded), its gain per ray: below about two
-// million rays per GPU -- a 4K frame over 8 GPUs -- it no longer pays.
+// Its cost is per triangle (every GPU projects every triangle; only the marking is sharded), its gain per ray: below about
+// eight rays per triangle and GPU -- the 4K frame of sixteen_armadillos (480 k triangles) over 4 or 8 GPUs -- it no longer pays.
 static bool cover_wanted(const bvht_ctx* ctx, uint32_t n_inst, uint32_t tris, uint32_t width, uint32_t height) {
     if (ctx->knobs.cover >= 0) return ctx->knobs.cover == 1;            // bvht_set_option(BVHT_OPT_COVER)
-    return n_inst >= 2 && tris / n_inst >= 8192u && (uint64_t)width * height / ctx->shard_count >= 2000000ull;
+    return n_inst >= 3 && tris / n_inst >= 8192u && (uint64_t)width * height / ctx->shard_count >= 8ull * tris;
 }
 
 // Rasterise every instance's triangles onto the 8x4-pixel blocks of the frame (cover_kernels.cu).  Once per frame, on
@@ -1817,6 +1856,46 @@ static int check_frame_args(bvht_ctx* ctx, const bvht_camera* camera, uint32_t w
     return BVHT_OK;
 }
 
+// Pull order of a plan's bands by estimated cost = pixels of instance rectangles inside the band's rows (no rectangles: image
+// order); fills plan.rects with the rectangles it computed so that the launch does not compute them again.
+static void order_bands(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height, uint32_t tile, uint32_t first_row,
+                        uint32_t own_rows, BandPlan& plan, int4 rects[32]) {
+    const uint32_t shard_n = ctx->shard_count;
+    {
+        uint64_t cost[32] = { 0 };
+        uint32_t nr = 0;
+        plan.have_rects = accel_on(ctx);
+        if (accel_on(ctx) && compute_instance_rects(ctx, camera, width, height, rects, nr)) {
+            plan.rects = rects; plan.n_rects = nr;
+            for (uint32_t k = 0; k < plan.n_bands; ++k) {
+                const uint32_t r0 = first_row + k * plan.band_rows * shard_n;
+                const uint32_t r1 = first_row + std::min(own_rows, (k + 1) * plan.band_rows) * shard_n;       // exclusive (global tile rows spanned)
+                const int y0 = (int)(r0 * tile), y1 = (int)std::min<uint64_t>((uint64_t)r1 * tile, height) - 1;
+                for (uint32_t i = 0; i < nr; ++i) {
+                    const int oy0 = std::max(y0, rects[i].y), oy1 = std::min(y1, rects[i].w);
+                    if (oy1 >= oy0 && rects[i].z >= rects[i].x) cost[k] += (uint64_t)(oy1 - oy0 + 1) * (uint64_t)(rects[i].z - rects[i].x + 1);
+                }
+            }
+        }
+        for (uint32_t k = 0; k < plan.n_bands; ++k) plan.order[k] = (uint8_t)k;
+        const int policy = ctx->knobs.band_order >= 0 ? ctx->knobs.band_order : 1;
+        if (policy == 1) std::stable_sort(plan.order, plan.order + plan.n_bands, [&](uint8_t x, uint8_t y) { return cost[x] < cost[y]; });
+        if (policy == 3) std::stable_sort(plan.order, plan.order + plan.n_bands, [&](uint8_t x, uint8_t y) { return cost[x] > cost[y]; });
+        if (policy == 2) {
+            // cheap bands first, cheapest first (their pixels are mostly K0's: complete almost at once, the copy engine starts on
+            // them), then the expensive ones, MOST expensive first: a heavy pixel block keeps its warp busy for ~100 us, so the
+            // heaviest rows must not be the ones the kernel ends with
+            uint64_t total = 0;
+            for (uint32_t k = 0; k < plan.n_bands; ++k) total += cost[k];
+            const uint64_t cheap_below = total / (2ull * plan.n_bands) + 1;          // under half the mean
+            std::stable_sort(plan.order, plan.order + plan.n_bands, [&](uint8_t x, uint8_t y) {
+                const bool cx = cost[x] < cheap_below, cy = cost[y] < cheap_below;
+                if (cx != cy) return cx;
+                return cx ? cost[x] < cost[y] : cost[x] > cost[y]; });
+        }
+    }
+}
+
 int bvht_render_frame_device(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height, uint32_t tile,
                              bvht_rect region, const bvht_shade_params* shade, void* frame_out_device, void* hits_out_device) {
     if (!ctx) return BVHT_ERR_BAD_HANDLE;
@@ -1834,8 +1913,21 @@ int bvht_render_frame_device(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
     CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, kWordBandFlag * 4, ctx->stream));
     cudaEventRecord(ctx->ev_a, ctx->stream);
     if ((rc = prepare_cover(ctx, camera, width, height, tile, ctx->stream))) return rc;       // inside the timed interval
+    // the resident frame is one band unless BVHT_OPT_BANDS asks for more (then the bands' pull order applies, without flags)
+    BandPlan plan;
+    int4 rects[32];
+    if (ctx->knobs.bands > 1) {
+        uint32_t first_row = region.y0 / tile, own_rows = (region.y1 + tile - 1) / tile - first_row;
+        if (ctx->shard_count > 1) bvht_shard_tile_rows(region, tile, ctx->shard_index, ctx->shard_count, &first_row, &own_rows);
+        if (own_rows > 0) {
+            plan.n_bands = std::min((uint32_t)ctx->knobs.bands, own_rows);
+            plan.band_rows = (own_rows + plan.n_bands - 1) / plan.n_bands;
+            plan.n_bands = (own_rows + plan.band_rows - 1) / plan.band_rows;
+            order_bands(ctx, camera, width, height, tile, first_row, own_rows, plan, rects);
+        }
+    }
     rc = launch_primary_region(ctx, scene, camera, width, height, tile, region, shade, hits_out_device, frame_out_device,
-                               ctx->stream, 0, ctx->shard_index, ctx->shard_count);
+                               ctx->stream, 0, ctx->shard_index, ctx->shard_count, nullptr, ctx->knobs.bands > 1 ? &plan : nullptr);
     ctx->cover_ready = false;
     cudaEventRecord(ctx->ev_b, ctx->stream);
     if (rc) return rc;
@@ -1952,40 +2044,7 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
     plan.flags = wait_value != nullptr && plan.n_bands > 1;
     plan.seq = ++ctx->frame_seq;
     int4 rects[32];
-    {
-        // pull order: ascending estimated cost = pixels of instance rectangles inside the band's rows (no rectangles: image order)
-        uint64_t cost[32] = { 0 };
-        uint32_t nr = 0;
-        plan.have_rects = accel_on(ctx);
-        if (accel_on(ctx) && compute_instance_rects(ctx, camera, width, height, rects, nr)) {
-            plan.rects = rects; plan.n_rects = nr;
-            for (uint32_t k = 0; k < plan.n_bands; ++k) {
-                const uint32_t r0 = first_row + k * plan.band_rows * shard_n;
-                const uint32_t r1 = first_row + std::min(own_rows, (k + 1) * plan.band_rows) * shard_n;       // exclusive (global tile rows spanned)
-                const int y0 = (int)(r0 * tile), y1 = (int)std::min<uint64_t>((uint64_t)r1 * tile, height) - 1;
-                for (uint32_t i = 0; i < nr; ++i) {
-                    const int oy0 = std::max(y0, rects[i].y), oy1 = std::min(y1, rects[i].w);
-                    if (oy1 >= oy0 && rects[i].z >= rects[i].x) cost[k] += (uint64_t)(oy1 - oy0 + 1) * (uint64_t)(rects[i].z - rects[i].x + 1);
-                }
-            }
-        }
-        for (uint32_t k = 0; k < plan.n_bands; ++k) plan.order[k] = (uint8_t)k;
-        const int policy = ctx->knobs.band_order >= 0 ? ctx->knobs.band_order : 1;
-        if (policy == 1) std::stable_sort(plan.order, plan.order + plan.n_bands, [&](uint8_t x, uint8_t y) { return cost[x] < cost[y]; });
-        if (policy == 3) std::stable_sort(plan.order, plan.order + plan.n_bands, [&](uint8_t x, uint8_t y) { return cost[x] > cost[y]; });
-        if (policy == 2) {
-            // cheap bands first, cheapest first (their pixels are mostly K0's: complete almost at once, the copy engine starts on
-            // them), then the expensive ones, MOST expensive first: a heavy pixel block keeps its warp busy for ~100 us, so the
-            // heaviest rows must not be the ones the kernel ends with
-            uint64_t total = 0;
-            for (uint32_t k = 0; k < plan.n_bands; ++k) total += cost[k];
-            const uint64_t cheap_below = total / (2ull * plan.n_bands) + 1;          // under half the mean
-            std::stable_sort(plan.order, plan.order + plan.n_bands, [&](uint8_t x, uint8_t y) {
-                const bool cx = cost[x] < cheap_below, cy = cost[y] < cheap_below;
-                if (cx != cy) return cx;
-                return cx ? cost[x] < cost[y] : cost[x] > cost[y]; });
-        }
-    }
+    order_bands(ctx, camera, width, height, tile, first_row, own_rows, plan, rects);
     CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, kWordBandFlag * 4, ctx->stream));
     cudaEventRecord(ctx->ev_a, ctx->stream);
     if ((rc = prepare_cover(ctx, camera, width, height, tile, ctx->stream))) return rc;

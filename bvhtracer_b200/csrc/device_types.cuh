@@ -146,6 +146,7 @@ struct SceneRebuildParams {
     uint32_t*       inst_blas;    // out: copy of blas_ids
     float*          inst_bounds;  // out (may be null): world AABB per instance, 6 floats (SceneObject::bounds)
     unsigned int*   status;       // [0]: bit 0 = singular transform, bit 1 = clustering found no candidate; [1] = nodes_used
+    void*           pack;         // out (may be null): tlas | inst_cols | inst_bounds | status in one contiguous block (one D2H)
     uint32_t        n_inst;
 };
 

@@ -19,6 +19,16 @@ BVHT_DECLARE_MODE(stats)
 cudaError_t launch_repack_triangles(const float* tris_aos, uint32_t n_tris, float4* out, cudaStream_t s);
 cudaError_t launch_repack_sub_triangles(const float* tris_aos, const uint32_t* sub_order, uint32_t n, float4* out, cudaStream_t s);
 
+// whole-model statistics / tight box of a model on the device (upload_kernels.cu); maxima and boxes as order-preserving integers
+struct ModelStatsDev {
+    unsigned long long radius2, max_edge2, kappa2_max;      // enc_f64 of the maxima of the SQUARES (0 = no triangle)
+    double sum_edge, sum_kappa;
+    unsigned long long n_good;
+    unsigned int lo[3], hi[3];                               // enc_f32 of the vertex box of the non-degenerate triangles
+};
+cudaError_t launch_model_stats(const float* tris_aos, uint32_t n_tris, ModelStatsDev* out, cudaStream_t s);
+cudaError_t launch_tight_box(const float* tris_aos, uint32_t n_tris, double scale, double abs_, unsigned long long* out6, cudaStream_t s);
+
 cudaError_t launch_read_bw(const void* buf, size_t bytes, uint32_t iters, int grid, unsigned long long* sink, cudaStream_t s);
 cudaError_t launch_ray_bounds(const float* rays, unsigned long long n, unsigned int* out2, cudaStream_t s);
 cudaError_t launch_refit_sub_nodes(float4* raw, const uint32_t* parent, unsigned int* counters, const float* tris_aos,

@@ -199,6 +199,19 @@ __global__ void scene_rebuild_kernel(SceneRebuildParams p) {
         p.tlas[0] = q0; p.tlas[1] = q1;
         p.status[1] = (unsigned)used;
     }
+    if (p.pack) {
+        // everything the host wants back, contiguous, so that ONE device->host copy fetches it:
+        // [tlas: 2n nodes x 2 float4 | inverse transforms: n x 4 float4 | world bounds: n x 6 floats | status: 4 words]
+        __syncthreads();
+        float4* out = reinterpret_cast<float4*>(p.pack);
+        const int n_tl = 4 * n, n_ic = 4 * n;
+        for (int i = (int)threadIdx.x; i < n_tl; i += (int)blockDim.x) out[i] = p.tlas[i];
+        for (int i = (int)threadIdx.x; i < n_ic; i += (int)blockDim.x) out[n_tl + i] = p.inst_cols[i];
+        float* fb = reinterpret_cast<float*>(out + n_tl + n_ic);
+        if (p.inst_bounds) for (int i = (int)threadIdx.x; i < 6 * n; i += (int)blockDim.x) fb[i] = p.inst_bounds[i];
+        unsigned* st = reinterpret_cast<unsigned*>(fb + 6 * n);
+        if (threadIdx.x < 4) st[threadIdx.x] = p.status[threadIdx.x];
+    }
 }
 
 } // namespace

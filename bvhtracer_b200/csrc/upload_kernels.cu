@@ -5,6 +5,7 @@
 // them once on upload is bit-identical (one IEEE subtraction either way; no FMA can form here).
 // HBM-bound streaming kernel: 36 B read + 48 B written per triangle, loads coalesced through shared memory.
 #include <algorithm>
+#include <cstring>
 #include "launchers.hpp"
 
 namespace bvht {
@@ -257,6 +258,115 @@ read_bw_kernel(const uint4* __restrict__ buf, size_t n_vec, uint32_t iters, unsi
     if (acc == 0x9E3779B9u) atomicAdd(sink, 1ull);      // keeps the loads alive
 }
 
+
+// ---- whole-model statistics and tight box of a deforming model, on the device (bvht_blas_update_vertices runs per frame for
+// big_ben_clock: the two host passes over the triangles cost 0.46 ms of a 1.9 ms frame; here they are two streaming kernels).
+// Arithmetic is the host functions' (leaf_accel.cpp compute_model_stats, bvht_api.cu bake_accel), in double: the maxima and the
+// boxes are order-independent, only the two means (a heuristic's inputs) depend on the summation order.
+__device__ __forceinline__ unsigned long long enc_f64(double d) {        // order-preserving u64 of a double
+    unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ unsigned int enc_f32(float f) {
+    unsigned int b = __float_as_uint(f);
+    return (b >> 31) ? ~b : (b | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(kRepackBlock)
+model_stats_kernel(const float* __restrict__ tris, uint32_t n_tris, ModelStatsDev* __restrict__ out) {
+    double radius2 = 0.0, edge2 = 0.0, kappa2max = 0.0, sum_edge = 0.0, sum_kappa = 0.0;
+    unsigned long long good = 0;
+    float lo[3] = { 3.402823466e38f, 3.402823466e38f, 3.402823466e38f }, hi[3] = { -3.402823466e38f, -3.402823466e38f, -3.402823466e38f };
+    for (uint32_t i = blockIdx.x * kRepackBlock + threadIdx.x; i < n_tris; i += gridDim.x * kRepackBlock) {
+        const float* t = tris + (size_t)i * 9;
+        float v[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) v[j] = __ldg(t + j);
+        double l1 = 0.0, l2 = 0.0, l3 = 0.0, n0 = 0.0, n1 = 0.0, n2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double a = v[k], b = v[3 + k], c = v[6 + k];
+            const double e1 = b - a, e2 = c - a, e3 = c - b;
+            l1 += e1 * e1; l2 += e2 * e2; l3 += e3 * e3;
+            n0 += a * a; n1 += b * b; n2 += c * c;
+        }
+        const double kappa2 = l1 * l2;
+        if (!(kappa2 > 0.0)) continue;          // degenerate (e.g. the 999 sentinel): never accepted
+        radius2 = fmax(radius2, fmax(n0, fmax(n1, n2)));
+        edge2 = fmax(edge2, fmax(l1, fmax(l2, l3)));
+        kappa2max = fmax(kappa2max, kappa2);
+        sum_edge += sqrt(l1); sum_kappa += sqrt(kappa2); ++good;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = fminf(lo[k], fminf(v[k], fminf(v[3 + k], v[6 + k])));
+            hi[k] = fmaxf(hi[k], fmaxf(v[k], fmaxf(v[3 + k], v[6 + k])));
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        radius2 = fmax(radius2, __shfl_xor_sync(0xFFFFFFFFu, radius2, off));
+        edge2 = fmax(edge2, __shfl_xor_sync(0xFFFFFFFFu, edge2, off));
+        kappa2max = fmax(kappa2max, __shfl_xor_sync(0xFFFFFFFFu, kappa2max, off));
+        sum_edge += __shfl_xor_sync(0xFFFFFFFFu, sum_edge, off);
+        sum_kappa += __shfl_xor_sync(0xFFFFFFFFu, sum_kappa, off);
+        good += __shfl_xor_sync(0xFFFFFFFFu, good, off);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xFFFFFFFFu, lo[k], off));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xFFFFFFFFu, hi[k], off));
+        }
+    }
+    if ((threadIdx.x & 31) == 0 && good) {
+        atomicMax(&out->radius2, enc_f64(radius2));
+        atomicMax(&out->max_edge2, enc_f64(edge2));
+        atomicMax(&out->kappa2_max, enc_f64(kappa2max));
+        atomicAdd(&out->sum_edge, sum_edge);
+        atomicAdd(&out->sum_kappa, sum_kappa);
+        atomicAdd(&out->n_good, good);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { atomicMin(&out->lo[k], enc_f32(lo[k])); atomicMax(&out->hi[k], enc_f32(hi[k])); }
+    }
+}
+
+// union over the non-degenerate triangles of (triangle box grown by ITS delta = scale * |e1||e2| (1 + 1e-9) + abs and 1e-6
+// relative), in double like the host loop it replaces; the host rounds the six results outwards to float
+__global__ void __launch_bounds__(kRepackBlock)
+tight_box_kernel(const float* __restrict__ tris, uint32_t n_tris, double scale, double abs_, unsigned long long* __restrict__ out6) {
+    double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+    for (uint32_t i = blockIdx.x * kRepackBlock + threadIdx.x; i < n_tris; i += gridDim.x * kRepackBlock) {
+        const float* t = tris + (size_t)i * 9;
+        float v[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) v[j] = __ldg(t + j);
+        double l1 = 0.0, l2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double e1 = (double)v[3 + k] - v[k], e2 = (double)v[6 + k] - v[k];
+            l1 += e1 * e1; l2 += e2 * e2;
+        }
+        const double kp = sqrt(l1) * sqrt(l2);
+        if (!(kp > 0.0)) continue;
+        const double delta = scale * kp * (1.0 + 1e-9) + abs_;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double l = fmin((double)v[k], fmin((double)v[3 + k], (double)v[6 + k]));
+            const double h = fmax((double)v[k], fmax((double)v[3 + k], (double)v[6 + k]));
+            lo[k] = fmin(lo[k], l - delta - fabs(l) * 1e-6);
+            hi[k] = fmax(hi[k], h + delta + fabs(h) * 1e-6);
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = fmin(lo[k], __shfl_xor_sync(0xFFFFFFFFu, lo[k], off));
+            hi[k] = fmax(hi[k], __shfl_xor_sync(0xFFFFFFFFu, hi[k], off));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { atomicMin(out6 + k, enc_f64(lo[k])); atomicMax(out6 + 3 + k, enc_f64(hi[k])); }
+    }
+}
+
 } // namespace
 
 cudaError_t launch_read_bw(const void* buf, size_t bytes, uint32_t iters, int grid, unsigned long long* sink, cudaStream_t s) {
@@ -269,6 +379,26 @@ cudaError_t launch_ray_bounds(const float* rays, unsigned long long n, unsigned 
     if (e != cudaSuccess || n == 0) return e;
     int grid = (int)std::min<unsigned long long>((n + kRepackBlock - 1) / kRepackBlock, 148ull * 8);
     ray_bounds_kernel<<<grid, kRepackBlock, 0, s>>>(rays, n, out2);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_model_stats(const float* tris_aos, uint32_t n_tris, ModelStatsDev* out, cudaStream_t s) {
+    ModelStatsDev init;
+    memset(&init, 0, sizeof init);
+    for (int k = 0; k < 3; ++k) { init.lo[k] = 0xFFFFFFFFu; init.hi[k] = 0u; }
+    cudaError_t e = cudaMemcpyAsync(out, &init, sizeof init, cudaMemcpyHostToDevice, s);        // pageable, 80 bytes: staged before return
+    if (e != cudaSuccess || n_tris == 0) return e;
+    int grid = (int)std::min<uint32_t>((n_tris + kRepackBlock - 1) / kRepackBlock, 148u * 4);
+    model_stats_kernel<<<grid, kRepackBlock, 0, s>>>(tris_aos, n_tris, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tight_box(const float* tris_aos, uint32_t n_tris, double scale, double abs_, unsigned long long* out6, cudaStream_t s) {
+    unsigned long long init[6] = { ~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull };
+    cudaError_t e = cudaMemcpyAsync(out6, init, sizeof init, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess || n_tris == 0) return e;
+    int grid = (int)std::min<uint32_t>((n_tris + kRepackBlock - 1) / kRepackBlock, 148u * 4);
+    tight_box_kernel<<<grid, kRepackBlock, 0, s>>>(tris_aos, n_tris, scale, abs_, out6);
     return cudaGetLastError();
 }
 

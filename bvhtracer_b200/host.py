@@ -492,9 +492,25 @@ class Renderer:
 
 
 # ------------------------------------------------------------------ example scenes through the mirror
+def read_mesh_file(path):
+    """`TriMeshDecoder::new(File::open(path)).read_mesh()` / `ObjMeshDecoder` by extension (mesh/decoders.rs:102-216): the text
+    asset decoded by the C++ mirror's decoders -- the ingest path of the product."""
+    text = open(path, "rb").read()
+    if path.lower().endswith(".tri"):
+        return TriMeshDecoder(text).read_mesh()
+    if path.lower().endswith(".obj"):
+        return ObjMeshDecoder(text).read_mesh()
+    raise HostError(f"unknown mesh format: {path}")
+
+
 def load_asset_mesh(name, asset_dir=None):
-    """Packed triangle soup (assets/<name>.f32; decoded from the reference's .tri/.obj by oracle/tools/pack_assets.py)."""
+    """The example asset `name` (armadillo.tri, teapot.obj, ...): the text file itself when it lies in the asset directory
+    (decoded by read_mesh_file), else its packed triangle soup assets/<name>.f32 -- the same decoders' output, written by
+    tools/pack_assets.py where the reference tree exists (the .tri / .obj texts are the reference's files and are not copied
+    into this repository; tests/test_asset_ingest.py keeps the two byte-identical)."""
     asset_dir = asset_dir or os.path.join(os.path.dirname(_ffi.PKG), "assets")
+    if os.path.exists(os.path.join(asset_dir, name)):
+        return read_mesh_file(os.path.join(asset_dir, name))
     tris = np.fromfile(os.path.join(asset_dir, name + ".f32"), dtype="<f4").reshape(-1, 9)
     npath = os.path.join(asset_dir, name + ".normals.f32")
     if os.path.exists(npath):                      # OBJ models: the `vn` normals of each face corner

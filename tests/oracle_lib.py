@@ -118,7 +118,7 @@ def triangle_centroid(tri9):
 
 # ------------------------------------------------------------------ assets
 def load_asset(name):
-    """Packed asset (assets/<name>.f32, N x 9 f32, file order; see oracle/tools/pack_assets.py)."""
+    """Packed asset (assets/<name>.f32, N x 9 f32, file order; see tools/pack_assets.py)."""
     return np.fromfile(os.path.join(ASSET_DIR, name + ".f32"), dtype="<f4").reshape(-1, 9).copy()
 
 
