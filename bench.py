@@ -534,13 +534,23 @@ def run_ours(args, rank, local_rank, world):
     if rank == 0 and weights is not None and args.mode == "strict-accel":
         frames = sorted({first_timed_frame, (first_timed_frame + last_timed_frame) // 2, last_timed_frame})
         per_frame = []
+        d_probe = eng.device_alloc(npix * 16) if world > 1 and not gather_frame else d_hits
         for f in frames:
             wl.goto(f)
             renderer.sync_scene(scene)
             c = eng.debug_trace_stats(cam, width, height, tile)
-            per_frame.append((sum(weights[k] * c[k] for k in weights), c))
-        performed = {"lane_ops_per_frame": float(np.mean([p for p, _ in per_frame])), "frames": frames,
-                     "counters_per_ray": {k: float(np.mean([c[k] / max(c["rays"], 1) for _, c in per_frame])) for k in per_frame[0][1] if k != "rays"}}
+            k1 = []
+            for _ in range(3):                           # the product frame again: duration of the trace kernel (K1) ALONE
+                eng.render_frame_device(cam, width, height, None, tile, None, None, d_probe)
+                eng.sync()
+                k1.append(renderer.stats()["last_k1_ms"])
+            per_frame.append((sum(weights[k] * c[k] for k in weights), c, float(np.mean(k1))))
+        if d_probe is not d_hits:
+            eng.device_free(d_probe)
+        performed = {"lane_ops_per_frame": float(np.mean([p for p, _, _ in per_frame])), "frames": frames,
+                     "k1_ms_per_frame": [t for _, _, t in per_frame],
+                     "lane_ops_per_ms": float(np.mean([p / t for p, _, t in per_frame])),
+                     "counters_per_ray": {k: float(np.mean([c[k] / max(c["rays"], 1) for _, c, _ in per_frame])) for k in per_frame[0][1] if k != "rays"}}
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle on the box's host cores, bounded sample of the same frame
     cpu = None
@@ -569,7 +579,9 @@ def run_ours(args, rank, local_rank, world):
                 traffic = json.load(open(tp)).get(f"{args.workload}:{args.mode}", {}).get("dram_bytes_per_frame")
             except Exception:
                 traffic = None
-        roof = {"bound": "issue", "kernel": "trace_primary_kernel", "launch_ms": kernel_ms_local, "traffic": traffic,
+        k1_ms = float(np.mean(performed["k1_ms_per_frame"])) if performed is not None else None
+        roof = {"bound": "issue", "kernel": "trace_primary_kernel", "launch_ms": k1_ms if k1_ms is not None else kernel_ms_local,
+                "frame_ms": kernel_ms_local, "traffic": traffic,
                 "unit": "T lane-instructions/s", "peak": lane_peak,
                 "peak_source": f"148 SMs x 4 schedulers x 32 lanes x {sm_mhz:.0f} MHz (SM clock sampled during the timed region); the path is "
                                "instruction-issue bound, not HBM or tensor bound (DESIGN.md 4)",
@@ -578,10 +590,12 @@ def run_ours(args, rank, local_rank, world):
                         "frac": 16.0 * rays_per_launch / (kernel_ms_local * 1e-3) / 1e9 / peak,
                         "note": "the only compulsory HBM traffic is the 16 B/ray hit record; the scene is L1/L2 resident"}}
         if performed is not None:
-            achieved = performed["lane_ops_per_frame"] / (kernel_ms_local * 1e-3) / 1e12
+            achieved = performed["lane_ops_per_ms"] * 1e3 / 1e12
             roof.update({"achieved": achieved, "frac": achieved / lane_peak, "performed": performed, "weights": weights_src,
                          "note": "achieved = lane-instructions the frame PERFORMED (work counters of the instrumented build x per-event "
-                                 "instruction counts calibrated against an ncu source-level capture, tools/lane_op_weights.py) / launch time; "
+                                 "instruction counts calibrated against an ncu source-level capture, tools/lane_op_weights.py) / duration of the "
+                                 "trace kernel alone (launch_ms: CUDA events around K1 on its stream, bvht_stats.last_k1_ms, sampled frames; "
+                                 "frame_ms adds the coverage raster and K0); "
                                  "frac = ncu's issue slots busy per ELAPSED cycle x lanes per instruction / 32 (profiles/r02_lane_op_model_validation.txt)"})
         else:
             roof.update({"achieved": None, "frac": None,

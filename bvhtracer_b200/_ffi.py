@@ -49,7 +49,8 @@ class Stats(C.Structure):
     _fields_ = [("last_trace_ms", C.c_float), ("last_refit_ms", C.c_float), ("last_upload_ms", C.c_float),
                 ("last_trace_rays", C.c_uint64), ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("sm_count", C.c_uint32), ("trace_grid", C.c_uint32),
-                ("trace_block", C.c_uint32), ("flags", C.c_uint32), ("last_build_ms", C.c_float), ("last_build_levels", C.c_uint32)]
+                ("trace_block", C.c_uint32), ("flags", C.c_uint32), ("last_build_ms", C.c_float), ("last_build_levels", C.c_uint32),
+                ("last_k1_ms", C.c_float), ("reserved_", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -120,6 +120,8 @@ struct bvht_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;       // trace timing
+    cudaEvent_t ev_k1a = nullptr, ev_k1b = nullptr;   // the trace kernel alone (bvht_stats.last_k1_ms)
+    bool k1_timed = false;
     cudaEvent_t ev_c = nullptr, ev_d = nullptr;       // refit timing
     cudaEvent_t ev_e = nullptr, ev_f = nullptr;       // upload timing
     bool trace_timed = false, refit_timed = false;
@@ -1063,6 +1065,7 @@ int bvht_create(int device, uint32_t flags, bvht_ctx** out) {
            && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess
            && cudaEventCreate(&ctx->ev_a) == cudaSuccess && cudaEventCreate(&ctx->ev_b) == cudaSuccess
            && cudaEventCreate(&ctx->ev_c) == cudaSuccess && cudaEventCreate(&ctx->ev_d) == cudaSuccess
+           && cudaEventCreate(&ctx->ev_k1a) == cudaSuccess && cudaEventCreate(&ctx->ev_k1b) == cudaSuccess
            && cudaEventCreate(&ctx->ev_e) == cudaSuccess && cudaEventCreate(&ctx->ev_f) == cudaSuccess
            && cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
     if (ok) {
@@ -1112,7 +1115,7 @@ void bvht_destroy(bvht_ctx* ctx) {
     for (auto& st : ctx->stage) { if (st.p) cudaFreeHost(st.p); if (st.done) cudaEventDestroy(st.done); }
     for (cudaEvent_t ev : ctx->ev_copy_t) if (ev) cudaEventDestroy(ev);
     if (ctx->ev_cover_t) cudaEventDestroy(ctx->ev_cover_t);
-    for (cudaEvent_t ev : { ctx->ev_a, ctx->ev_b, ctx->ev_c, ctx->ev_d, ctx->ev_e, ctx->ev_f }) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : { ctx->ev_a, ctx->ev_b, ctx->ev_c, ctx->ev_d, ctx->ev_e, ctx->ev_f, ctx->ev_k1a, ctx->ev_k1b }) if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -1626,6 +1629,7 @@ static int prepare_cover(bvht_ctx* ctx, const bvht_camera* cam, uint32_t width, 
                 p.mv[i][r * 4 + c] = (float)v;
                 scale_max = std::max(scale_max, std::fabs(v));
             }
+        p.inst_tri[i] = (const float4*)b.tri.p; p.inst_scale[i] = b.bake_scale; p.inst_abs[i] = b.bake_abs;
         total += b.n_tris;
     }
     p.tri_offset[n_inst] = total;
@@ -1837,8 +1841,9 @@ static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvh
         p.stats = stats_counters;
         e = launch_primary_stats(p, accel_on(ctx), grid, kTraceBlock, stream);
     } else
-    e = fast_on(ctx) ? launch_primary_fast(p, accel_on(ctx), grid, kTraceBlock, stream)
-                     : launch_primary_strict(p, accel_on(ctx), grid, kTraceBlock, stream);
+    e = fast_on(ctx) ? launch_primary_fast(p, accel_on(ctx), grid, kTraceBlock, stream, ctx->ev_k1a, ctx->ev_k1b)
+                     : launch_primary_strict(p, accel_on(ctx), grid, kTraceBlock, stream, ctx->ev_k1a, ctx->ev_k1b);
+    ctx->k1_timed = e == cudaSuccess;
     if (e != cudaSuccess) return fail(ctx, BVHT_ERR_CUDA, "trace_primary launch failed: %s", cudaGetErrorString(e));
     ctx->stats.kernel_launches += 1;
     ctx->stats.trace_grid = (uint32_t)grid;
@@ -2358,6 +2363,9 @@ int bvht_get_stats(const bvht_ctx* cctx, bvht_stats* out) {
     }
     if (ctx->refit_timed) {
         if (cudaEventSynchronize(ctx->ev_d) == cudaSuccess) cudaEventElapsedTime(&ctx->stats.last_refit_ms, ctx->ev_c, ctx->ev_d);
+    }
+    if (ctx->k1_timed) {
+        if (cudaEventSynchronize(ctx->ev_k1b) == cudaSuccess) cudaEventElapsedTime(&ctx->stats.last_k1_ms, ctx->ev_k1a, ctx->ev_k1b);
     }
     cudaGetLastError();
     *out = ctx->stats;

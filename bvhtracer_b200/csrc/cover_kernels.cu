@@ -35,15 +35,14 @@ raster_cover_kernel(const __grid_constant__ CoverParams P) {
     while (i + 1 < P.n_inst && g >= P.tri_offset[i + 1]) ++i;
     const uint32_t j = g - P.tri_offset[i];
     const uint32_t bit = 1u << i;
-    const BlasDesc& B = P.blas[P.inst_blas[i]];
-    const float4* tp = B.tri + 3 * (size_t)j;
+    const float4* tp = P.inst_tri[i] + 3 * (size_t)j;
     const float4 v0 = __ldg(tp + 0), e1 = __ldg(tp + 1), e2 = __ldg(tp + 2);
     const bool z1 = e1.x == 0.0f && e1.y == 0.0f && e1.z == 0.0f, z2 = e2.x == 0.0f && e2.y == 0.0f && e2.z == 0.0f;
     if (z1 || z2) return;                                   // a zero edge: area == 0 exactly, never accepted
     // |e1||e2| rounded up; NaN / inf vertices end in `full` through the projection below
     const float l1 = __fsqrt_ru(__fmaf_ru(e1.x, e1.x, __fmaf_ru(e1.y, e1.y, __fmul_ru(e1.z, e1.z))));
     const float l2 = __fsqrt_ru(__fmaf_ru(e2.x, e2.x, __fmaf_ru(e2.y, e2.y, __fmul_ru(e2.z, e2.z))));
-    const float delta = __fmaf_ru(B.bake_scale, __fmul_ru(__fmul_ru(l1, l2), 1.00001f), B.bake_abs);
+    const float delta = __fmaf_ru(P.inst_scale[i], __fmul_ru(__fmul_ru(l1, l2), 1.00001f), P.inst_abs[i]);
     float lo[3], hi[3];
     {
         const float a[3] = { v0.x, v0.y, v0.z }, b1[3] = { e1.x, e1.y, e1.z }, b2[3] = { e2.x, e2.y, e2.z };
@@ -82,9 +81,27 @@ raster_cover_kernel(const __grid_constant__ CoverParams P) {
     const int bx0 = px0 >> 3, bx1 = px1 >> 3, by0 = py0 >> 2, by1 = py1 >> 2;
     const uint32_t count = (uint32_t)(bx1 - bx0 + 1) * (uint32_t)(by1 - by0 + 1);
     if (count <= 64u) {
-        for (int by = by0; by <= by1; ++by) {
-            if (P.shard_count > 1u && ((uint32_t)(by >> 1) % P.shard_count) != P.shard_index) continue;     // another GPU's tile row
-            for (int bx = bx0; bx <= bx1; ++bx) mark(P.cover, P.ntx, bx, by, bit);
+        // The kernel is latency bound (ncu: 29 % issue slots, long-scoreboard stalls): a dependent read-then-atomic per block
+        // serialises a triangle's 4-6 marks.  So the words of up to eight blocks are READ first (independent L2 loads in flight
+        // together), and only the blocks whose bit is still clear get the atomic.
+        const int w = bx1 - bx0 + 1;
+        for (uint32_t c0 = 0; c0 < count; c0 += 8u) {
+            uint32_t* ptr[8];
+            uint32_t seen[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t c = c0 + (uint32_t)k;
+                ptr[k] = nullptr; seen[k] = bit;
+                if (c < count) {
+                    const int by = by0 + (int)(c / (uint32_t)w), bx = bx0 + (int)(c % (uint32_t)w);
+                    if (P.shard_count > 1u && ((uint32_t)(by >> 1) % P.shard_count) != P.shard_index) continue;     // another GPU's tile row
+                    ptr[k] = P.cover + ((size_t)(by >> 1) * P.ntx + (uint32_t)bx) * 2u + (uint32_t)(by & 1);
+                    seen[k] = __ldcg(ptr[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (ptr[k] && !(seen[k] & bit)) atomicOr(ptr[k], bit);
         }
     } else {
         const uint32_t at = atomicAdd(P.big_count, 1u);

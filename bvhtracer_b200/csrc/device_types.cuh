@@ -134,6 +134,9 @@ struct CoverParams {
     uint32_t        width, height;
     float           tlx, tly, inv_ex, inv_ey, near_, z_eps;     // near-plane rectangle of the camera (eye space)
     float           mv[32][12];     // per instance: view * object transform, rows 0..2 (row-major 3 x 4)
+    const float4*   inst_tri[32];   // per instance: its model's triangle records and the current bake's inflation, copied from the
+    float           inst_scale[32]; //   BLAS descriptors by the host (two dependent global loads less per thread of a kernel that is
+    float           inst_abs[32];   //   bound by exactly such latencies)
 };
 
 // K6 (scene_kernels.cu): SceneObject::set_transform for every object + Tlas::rebuild

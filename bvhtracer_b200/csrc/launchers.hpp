@@ -6,7 +6,8 @@
 namespace bvht {
 
 #define BVHT_DECLARE_MODE(sfx)                                                                                   \
-    cudaError_t launch_primary_##sfx(const PrimaryParams& p, bool accel, int grid, int block, cudaStream_t s);   \
+    cudaError_t launch_primary_##sfx(const PrimaryParams& p, bool accel, int grid, int block, cudaStream_t s,   \
+                                     cudaEvent_t k1_begin = nullptr, cudaEvent_t k1_end = nullptr);              \
     cudaError_t launch_rays_##sfx(const RaysParams& p, bool accel, int grid, int block, cudaStream_t s);         \
     int blocks_per_sm_primary_##sfx(bool accel, bool prune, int block);                                                      \
     int blocks_per_sm_rays_##sfx(bool accel, int block);

@@ -147,6 +147,8 @@ typedef struct {
     uint32_t flags;
     float    last_build_ms;          /* bvht_blas_build / bvht_blas_rebuild: upload + device build + read-back */
     uint32_t last_build_levels;      /* levels of the level-synchronous device build */
+    float    last_k1_ms;             /* the trace kernel (K1) alone of the last frame: what bench.py's roofline divides by */
+    uint32_t reserved_;
 } bvht_stats;
 
 /* ---------------------------------------------------------------------------------------------- */

@@ -2,7 +2,6 @@ cd /root/repo 2>/dev/null || cd "$GRAFT_REPO_ROOT"
 O=gpurun_out
 N=${1:-2}
 T=${2:-r02k}
-timeout 900 python -m pytest tests -m gpu -x -q > $O/${T}_pytest.txt 2>&1; tail -3 $O/${T}_pytest.txt
 for w in sixteen_armadillos big_ben_clock; do
   for n in 1 2 4 8; do
     [ $n -gt $N ] && continue

@@ -62,3 +62,16 @@ for f in range(3):
     r5.update_transforms(scene5, [host.object_transform(o) for o in anim.objects()])
     r5.render(st5, scene5)
 print("k0 + k6 ok", int(st5.frame_buffer().sum() % 1000))
+
+# the pipelined host frame: several bands, every pull order, two copy streams, coverage raster forced on, a tile-row shard
+r6 = host.Renderer(flags=2)
+e6 = r6.engine()
+st6 = host.RendererState(host.depth_pipeline(), 320, 184, keep_hits=True)
+e6.set_option(1, 1)               # BVHT_OPT_COVER
+for bands, order in ((4, 1), (7, 2), (23, 3), (2, 0)):
+    e6.set_option(3, bands)       # BVHT_OPT_BANDS
+    e6.set_option(4, order)       # BVHT_OPT_BAND_ORDER
+    r6.render(st6, scene5)
+e6.set_shard(1, 3)
+r6.render(st6, scene5)
+print("pipelined frame ok", int(st6.frame_buffer().sum() % 1000))
