@@ -50,7 +50,7 @@ class Stats(C.Structure):
                 ("last_trace_rays", C.c_uint64), ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("sm_count", C.c_uint32), ("trace_grid", C.c_uint32),
                 ("trace_block", C.c_uint32), ("flags", C.c_uint32), ("last_build_ms", C.c_float), ("last_build_levels", C.c_uint32),
-                ("last_k1_ms", C.c_float), ("reserved_", C.c_uint32)]
+                ("last_k1_ms", C.c_float), ("rebakes", C.c_uint32), ("bake_d_max", C.c_float), ("bake_o_max", C.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -53,6 +53,39 @@ __device__ __forceinline__ void ray_prepare_fma(RayM& r) {
 
 struct HitRec { float t, u, v; uint32_t id; };
 
+// Result stores.  BVHT_STORE_CS: 1 = streaming stores (evict-first) for the records / pixels K0 writes, 2 = for K1's as well.
+#ifndef BVHT_STORE_CS
+#define BVHT_STORE_CS 0
+#endif
+__device__ __forceinline__ void store_hit_k0(uint4* p, uint4 v) {
+#if BVHT_STORE_CS >= 1
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+__device__ __forceinline__ void store_px_k0(uint32_t* p, uint32_t v) {
+#if BVHT_STORE_CS >= 1
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+__device__ __forceinline__ void store_hit_k1(uint4* p, uint4 v) {
+#if BVHT_STORE_CS >= 2
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+__device__ __forceinline__ void store_px_k1(uint32_t* p, uint32_t v) {
+#if BVHT_STORE_CS >= 2
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
 // Per-thread work counters, compiled in only for the debug entry point (BVHT_STATS); otherwise an empty type
 // whose calls vanish.  Slots: 0 rays, 1 tlas pair tests, 2 instance entries, 3 reference BLAS pair tests,
 // 4 reference leaves visited, 5 brute-force triangle tests, 6 sub-BVH pair tests, 7 sub-BVH triangle tests,
@@ -843,9 +876,9 @@ trace_primary_kernel(const __grid_constant__ PrimaryParams P) {
             if (P.out) {
                 uint4 o;
                 o.x = __float_as_uint(h.t); o.y = __float_as_uint(h.u); o.z = __float_as_uint(h.v); o.w = h.id;
-                P.out[(size_t)py * P.width + px] = o;
+                store_hit_k1(P.out + (size_t)py * P.width + px, o);
             }
-            if (P.out_rgba) P.out_rgba[(size_t)py * P.width + px] = shade_pixel(P, h);
+            if (P.out_rgba) store_px_k1(P.out_rgba + (size_t)py * P.width + px, shade_pixel(P, h));
         }
         if (P.band_done) {
             // A block counts as finished only when its pixels are in memory.  A warp-wide __threadfence() here cost 0.09 ms of a
@@ -941,8 +974,8 @@ classify_fill_kernel(const __grid_constant__ PrimaryParams P) {
         uint32_t iu = p % P.tile, iv = p / P.tile;
         uint32_t px = tx * P.tile + iu, py = ty * P.tile + iv;
         if ((iv < P.tile) && px >= P.x0 && px < P.x1 && py >= P.y0 && py < P.y1) {
-            if (P.out) P.out[(size_t)py * P.width + px] = make_uint4(__float_as_uint(miss.t), 0u, 0u, miss.id);
-            if (P.out_rgba) P.out_rgba[(size_t)py * P.width + px] = miss_px;
+            if (P.out) store_hit_k0(P.out + (size_t)py * P.width + px, make_uint4(__float_as_uint(miss.t), 0u, 0u, miss.id));
+            if (P.out_rgba) store_px_k0(P.out_rgba + (size_t)py * P.width + px, miss_px);
         }
     }
 }

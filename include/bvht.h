@@ -148,7 +148,8 @@ typedef struct {
     float    last_build_ms;          /* bvht_blas_build / bvht_blas_rebuild: upload + device build + read-back */
     uint32_t last_build_levels;      /* levels of the level-synchronous device build */
     float    last_k1_ms;             /* the trace kernel (K1) alone of the last frame: what bench.py's roofline divides by */
-    uint32_t reserved_;
+    uint32_t rebakes;                /* how often the leaf accelerator's boxes were re-inflated for new ray limits */
+    float    bake_d_max, bake_o_max; /* ray limits of the last bake (model space |d|, |o|) */
 } bvht_stats;
 
 /* ---------------------------------------------------------------------------------------------- */
