@@ -25,6 +25,7 @@ intervals, max over ranks -- the same clock as N = 1.  `--scaling weak` grows th
 here: no cargo/rustc) with all host threads on a bounded sample of the same frames.
 """
 import argparse
+import collections
 import json
 import os
 import subprocess
@@ -72,8 +73,8 @@ class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region (NVML every 2 ms; nvidia-smi as fallback)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, uuid=None, index=0):
-        self.uuid, self.index = uuid, index
+    def __init__(self, uuid=None, index=0, period_s=0.002):
+        self.uuid, self.index, self.period_s = uuid, index, period_s
         self.sm, self.mask, self.sm_max = [], 0, None
         self.stop_flag = threading.Event()
         self.thread = None
@@ -100,7 +101,7 @@ class ClockSampler:
                     self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
                 except Exception:
                     pass
-                time.sleep(0.002)
+                time.sleep(self.period_s)
         except Exception as e:                                   # pragma: no cover
             self.error = repr(e)
 
@@ -115,7 +116,7 @@ class ClockSampler:
         if not self.sm:
             return self._smi_once()
         return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.sm_max, "samples": len(self.sm),
-                "reasons": sorted(n for b, n in self.REASONS.items() if self.mask & b), "source": "nvml, 2 ms period, whole timed region"}
+                "reasons": sorted(n for b, n in self.REASONS.items() if self.mask & b), "source": f"nvml, {self.period_s * 1e3:g} ms period, whole timed region"}
 
     def _smi_once(self):
         try:
@@ -269,6 +270,10 @@ class GpuWorkload:
         self.bigben = examples.BigBenAnimation(self.models[0].primitives()) if self.kind == "bigben" else None
         self.frame = 0
         self.transforms = [host.object_transform(o) for o in spec.objects]
+        self.queue = collections.deque()
+        # static scenes whose objects all carry a transform re-set them in one call per frame
+        self.static_m = (np.stack([t.matrix for t in self.transforms])
+                         if self.kind == "static" and all(o.with_transform for o in spec.objects) else None)
         self.pipeline = {"depth": host.depth_pipeline(80.0, 3.0), "normal": host.normal_pipeline(),
                          "intersection": host.intersection_pipeline()}[self.shading]
 
@@ -280,23 +285,42 @@ class GpuWorkload:
             return e.shade_intersection()
         return e.shade_normal(self.transforms[0].matrix)     # scene.get_unchecked(0).get_transform(), renderer.rs:275-278
 
+    def precompute(self, n):
+        """The next n frames' animation results (the example's own arithmetic: transforms of the grid, vertices of big_ben_clock),
+        so that a loop with frames in flight is not bound by this script's Python: advance() then only applies them to the scene."""
+        host = self.host
+        for _ in range(n):
+            if self.kind == "grid":
+                self.anim.update()
+                tr = [host.object_transform(o) for o in self.anim.objects()]
+                self.queue.append((tr, np.stack([t.matrix for t in tr])))
+            elif self.kind == "bigben":
+                self.queue.append(self.bigben.animate().copy())
+
     def advance(self):
         """AppState::update of the example, on the host (never inside a timed interval)."""
         host = self.host
         self.frame += 1
         if self.kind == "grid":                              # sixteen_armadillos.rs:132-163: 16 x set_transform + Scene::rebuild
-            self.anim.update()
-            self.transforms = [host.object_transform(o) for o in self.anim.objects()]
-            for i, t in enumerate(self.transforms):
-                self.scene.set_transform(i, t)
+            if self.queue:
+                self.transforms, m = self.queue.popleft()
+                self.scene.set_transforms(m)
+            else:
+                self.anim.update()
+                self.transforms = [host.object_transform(o) for o in self.anim.objects()]
+                for i, t in enumerate(self.transforms):
+                    self.scene.set_transform(i, t)
             self.scene.rebuild()
         elif self.kind == "bigben":                          # big_ben_clock.rs:67-103: animate() + ModelInstance::refit
-            self.models[0].set_primitives(self.bigben.animate())
+            self.models[0].set_primitives(self.queue.popleft() if self.queue else self.bigben.animate())
             self.models[0].refit()
         else:                                                # cube / two_armadillos: Scene::run re-sets the transforms and rebuilds
-            for i, t in enumerate(self.transforms):          # the TLAS every frame (scene.rs:40-50); fixed pose here (SURVEY 8d)
-                if self.spec.objects[i].with_transform:
-                    self.scene.set_transform(i, t)
+            if self.static_m is not None:                    # the TLAS every frame (scene.rs:40-50); fixed pose here (SURVEY 8d)
+                self.scene.set_transforms(self.static_m)
+            else:
+                for i, t in enumerate(self.transforms):
+                    if self.spec.objects[i].with_transform:
+                        self.scene.set_transform(i, t)
             self.scene.rebuild()
 
     def goto(self, frame):
@@ -403,7 +427,7 @@ def run_ours(args, rank, local_rank, world):
         gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
     except Exception:
         gpu_uuid = None
-    sampler = ClockSampler(gpu_uuid, local_rank)
+    sampler = ClockSampler(gpu_uuid, local_rank, args.clock_period_ms * 1e-3)
     sampler.start()
     launches0 = renderer.stats()["kernel_launches"]
     barrier()
@@ -471,6 +495,7 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     h2d0, d2h0 = renderer.stats()["h2d_bytes"], renderer.stats()["d2h_bytes"]
     ev = []
+    e2e_first_frame = wl.frame + 1
     for _ in range(args.steps):
         wl.advance()                                     # host-side scene update (not part of render(), as in the reference)
         flush.zero_()
@@ -495,6 +520,47 @@ def run_ours(args, rank, local_rank, world):
                    "; per rank: its tile rows over its own PCIe link into ONE frame in POSIX shared memory; sum of per-step CUDA-event intervals, max over ranks")}
     if world == 1:
         frame_checksum = int(np.bitwise_xor.reduce(state.frame_buffer()))
+        # the SAME frames of the animation with two in flight (Renderer::render_begin / render_end): frame n's copies run under
+        # frame n+1's kernels.  One interval around the whole loop -- scene updates, L2 flushes and the last frame's copies
+        # included -- closed after the last render_end has returned.
+        state_b = host.RendererState(wl.pipeline, width, height, keep_hits=False)
+        pair = [state, state_b]
+        wl.goto(max(e2e_first_frame - 1 - 4, 0))
+        for i in range(min(4, e2e_first_frame - 1)):
+            wl.advance()
+            renderer.render_begin(pair[i & 1], scene)
+            if i >= 1:
+                renderer.render_end()
+        renderer.render_end()
+        barrier()
+        wl.precompute(args.steps)
+        d2h1 = renderer.stats()["d2h_bytes"]
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fl = []
+        p0.record(stream)
+        for i in range(args.steps):
+            wl.advance()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(stream); flush.zero_(); f1.record(stream)
+            fl.append((f0, f1))
+            renderer.render_begin(pair[i & 1], scene)
+            if i >= 1:
+                renderer.render_end()
+        renderer.render_end()
+        p1.record(stream)
+        torch.cuda.synchronize()
+        loop_ms = p0.elapsed_time(p1)
+        flush_ms = sum(a.elapsed_time(b) for a, b in fl)
+        pipelined_checksum = int(np.bitwise_xor.reduce(pair[(args.steps - 1) & 1].frame_buffer()))
+        e2e["two_frames_in_flight"] = {
+            "value": npix * args.steps / (loop_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": loop_ms / args.steps,
+            "l2_flush_ms_per_step": flush_ms / args.steps,
+            "d2h_bytes_per_step": (renderer.stats()["d2h_bytes"] - d2h1) // args.steps,
+            "frames": [e2e_first_frame, e2e_first_frame + args.steps - 1],
+            "call": "Renderer::render_begin / render_end over two RendererStates, the frames of the e2e loop above; ONE CUDA-event "
+                    "interval around the whole loop (scene updates, the L2 flush before every frame and the last frame's copies inside it)",
+            "last_frame_checksum_xor": pipelined_checksum, "last_frame_equals_render": pipelined_checksum == frame_checksum}
+        del state_b
         if wl.kind != "bigben":
             # the same call returning the 16-byte hit records as well
             state_h = host.RendererState(wl.pipeline, width, height, keep_hits=True)
@@ -674,6 +740,7 @@ def main():
     ap.add_argument("--cpu-fraction", type=float, default=0.0, help="fraction of tile rows the CPU oracle renders per frame (0 = per-workload default)")
     ap.add_argument("--cpu-baseline-fraction", type=float, default=0.0, help="fraction of tile rows of ONE frame for the cpu_baseline leg (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-period-ms", type=float, default=2.0, help="NVML sampling period of the SM clock / throttle reasons during the timed regions")
     ap.add_argument("--gather", default="frame", choices=["frame", "hits"],
                     help="N > 1: what is assembled on rank 0 over NVLink P2P (frame = Rgba<u8> frame buffer, hits = the 16-byte records)")
     args = ap.parse_args()

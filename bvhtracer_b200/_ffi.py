@@ -87,6 +87,8 @@ SYMBOLS = [
     ("bvht_trace_primary", C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, Rect, _P]),
     ("bvht_trace_primary_device", C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, Rect, _P]),
     ("bvht_render_frame", C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, Rect, C.POINTER(ShadeParams), _P, _P]),
+    ("bvht_render_frame_begin", C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, Rect, C.POINTER(ShadeParams), _P, _P]),
+    ("bvht_render_frame_end", C.c_int, [_P]),
     ("bvht_render_frame_device", C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, Rect, C.POINTER(ShadeParams), _P, _P]),
     ("bvht_set_shard", C.c_int, [_P, C.c_uint32, C.c_uint32]),
     ("bvht_shard_tile_rows", C.c_int, [Rect, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),

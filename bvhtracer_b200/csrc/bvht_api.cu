@@ -151,6 +151,10 @@ struct bvht_ctx {
     BuildWorkspace build_ws;                   // K3 scratch (grow-only)
     DevBuf build_tris, build_perm;             // K3 input/output: triangles reordered in place + the permutation
     DevBuf out_buf, rays_buf, rgba_buf;               // device staging for the host-pointer entry points
+    DevBuf out_buf2, rgba_buf2;                       // second frame in flight (bvht_render_frame_begin): odd frames stage here
+    // frames begun and not yet ended (at most two): the events that close each copy stream's share of the frame
+    struct Flight { bool active = false; int n_cs = 0; cudaEvent_t done[3] = { nullptr, nullptr, nullptr }; } flight[2];
+    uint64_t flights_begun = 0, flights_ended = 0;
     cudaStream_t aux[2] = { nullptr, nullptr };       // band pipelining: two compute streams + one copy stream
     cudaStream_t copy_stream = nullptr;
     cudaStream_t copy_streams[3] = { nullptr, nullptr, nullptr };   // bvht_render_frame's band copies rotate over these (copy_stream is [0])
@@ -240,6 +244,27 @@ int h2d(bvht_ctx* ctx, void* dst, const void* src, size_t bytes) {
     if (bytes == 0) return BVHT_OK;
     CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.h2d_bytes += bytes;
+    return BVHT_OK;
+}
+
+// Per-frame uploads and fills through launch_small_ops (launchers.hpp): no copy engine involved, so none of them can end up
+// behind the band copies of a frame in flight.  `src` must be page-locked (a staging slot); sizes are whole words.
+struct OpsBatch { SmallOps ops; OpsBatch() { ops.n = 0; } };
+
+int ops_flush(bvht_ctx* ctx, OpsBatch& b, cudaStream_t stream) {
+    if (b.ops.n == 0) return BVHT_OK;
+    CU(ctx, launch_small_ops(b.ops, stream));
+    ctx->stats.kernel_launches += 1;
+    b.ops.n = 0;
+    return BVHT_OK;
+}
+
+int ops_add(bvht_ctx* ctx, OpsBatch& b, cudaStream_t stream, void* dst, const void* src_pinned, size_t bytes, uint32_t fill = 0) {
+    if (bytes == 0) return BVHT_OK;
+    if (bytes % 4 != 0 || bytes / 4 > 0xFFFFFFFFull) return fail(ctx, BVHT_ERR_INVALID_ARG, "small upload of %zu bytes is not a whole number of words", bytes);
+    if (b.ops.n == 8) { int rc = ops_flush(ctx, b, stream); if (rc) return rc; }
+    b.ops.op[b.ops.n++] = SmallOp{ dst, src_pinned, (uint32_t)(bytes / 4), fill };
+    if (src_pinned) ctx->stats.h2d_bytes += bytes;
     return BVHT_OK;
 }
 
@@ -717,8 +742,10 @@ int recompute_tlas_tight(bvht_ctx* ctx) {
     if ((rc = stage_get(ctx, (flat.size() + mask.size()) * 4, &stage))) return rc;
     memcpy(stage->p, flat.data(), flat.size() * 4);
     memcpy((char*)stage->p + flat.size() * 4, mask.data(), mask.size() * 4);
-    if ((rc = h2d(ctx, ctx->tlas_tight.p, stage->p, flat.size() * 4))) return rc;
-    if ((rc = h2d(ctx, ctx->tlas_mask.p, (char*)stage->p + flat.size() * 4, mask.size() * 4))) return rc;
+    OpsBatch up;
+    if ((rc = ops_add(ctx, up, ctx->stream, ctx->tlas_tight.p, stage->p, flat.size() * 4))) return rc;
+    if ((rc = ops_add(ctx, up, ctx->stream, ctx->tlas_mask.p, (char*)stage->p + flat.size() * 4, mask.size() * 4))) return rc;
+    if ((rc = ops_flush(ctx, up, ctx->stream))) return rc;
     return stage_done(ctx, stage);
 }
 
@@ -1089,6 +1116,8 @@ int bvht_create(int device, uint32_t flags, bvht_ctx** out) {
           && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
         ctx->copy_streams[0] = ctx->copy_stream;
         for (int i = 0; ok && i < 3; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_copy_join[i], cudaEventDisableTiming) == cudaSuccess;
+        for (int f = 0; f < 2; ++f)
+            for (int i = 0; ok && i < 3; ++i) ok = cudaEventCreateWithFlags(&ctx->flight[f].done[i], cudaEventDisableTiming) == cudaSuccess;
         for (int i = 0; ok && i < 64; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_band[i], cudaEventDisableTiming) == cudaSuccess;
         for (int i = 0; ok && i < 17; ++i) ok = cudaEventCreate(&ctx->ev_band_t[i]) == cudaSuccess;
         for (int i = 0; ok && i < 16; ++i) ok = cudaEventCreate(&ctx->ev_copy_t[i]) == cudaSuccess;
@@ -1106,7 +1135,10 @@ void bvht_destroy(bvht_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (cudaStream_t st : ctx->copy_streams) if (st) cudaStreamSynchronize(st);       // frames still in flight
     for (Blas& b : ctx->blas) free_blas(b);
+    for (DevBuf* d : { &ctx->out_buf2, &ctx->rgba_buf2 }) release(*d);
+    for (auto& f : ctx->flight) for (cudaEvent_t ev : f.done) if (ev) cudaEventDestroy(ev);
     for (DevBuf* d : { &ctx->blas_desc, &ctx->tlas, &ctx->inst_cols, &ctx->inst_blas, &ctx->work_counter, &ctx->work_list, &ctx->cover, &ctx->cover_aux, &ctx->out_buf, &ctx->rays_buf,
                        &ctx->rgba_buf, &ctx->tlas_tight, &ctx->tlas_mask, &ctx->stats_scratch, &ctx->scene_in, &ctx->scene_bounds, &ctx->build_tris, &ctx->build_perm })
         release(*d);
@@ -1153,11 +1185,13 @@ int bvht_set_option(bvht_ctx* ctx, uint32_t option, int32_t value) {
     }
 }
 
+static int drain_flights(bvht_ctx* ctx);
+
 int bvht_sync(bvht_ctx* ctx) {
     if (!ctx) return BVHT_ERR_BAD_HANDLE;
     cudaSetDevice(ctx->device);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    return BVHT_OK;
+    return drain_flights(ctx);                                   // frames begun and not ended complete here too
 }
 
 int bvht_blas_create(bvht_ctx* ctx, const float* tris, uint32_t n_tris, const bvht_bvh_node* nodes, uint32_t nodes_used,
@@ -1437,11 +1471,13 @@ int bvht_tlas_set(bvht_ctx* ctx, const bvht_tlas_node* nodes, uint32_t nodes_use
     size_t off2 = off + ((ic_bytes + 255) & ~size_t(255));
     uint32_t* ib = (uint32_t*)(st + off2);
     for (uint32_t i = 0; i < n_instances; ++i) ib[i] = instances[i].blas_id;
-    if ((rc = h2d(ctx, ctx->tlas.p, tl, tl_bytes))) return rc;
+    OpsBatch up;
+    if ((rc = ops_add(ctx, up, ctx->stream, ctx->tlas.p, tl, tl_bytes))) return rc;
     if (n_instances) {
-        if ((rc = h2d(ctx, ctx->inst_cols.p, ic, (size_t)n_instances * 64))) return rc;
-        if ((rc = h2d(ctx, ctx->inst_blas.p, ib, (size_t)n_instances * 4))) return rc;
+        if ((rc = ops_add(ctx, up, ctx->stream, ctx->inst_cols.p, ic, (size_t)n_instances * 64))) return rc;
+        if ((rc = ops_add(ctx, up, ctx->stream, ctx->inst_blas.p, ib, (size_t)n_instances * 4))) return rc;
     }
+    if ((rc = ops_flush(ctx, up, ctx->stream))) return rc;
     if ((rc = stage_done(ctx, stage))) return rc;
     ctx->h_tlas.assign(nodes, nodes + nodes_used);
     for (uint32_t i = 0; i < nodes_used; ++i) if (!reached[i]) memset(&ctx->h_tlas[i], 0, sizeof(bvht_tlas_node));
@@ -1642,10 +1678,17 @@ static int prepare_cover(bvht_ctx* ctx, const bvht_camera* cam, uint32_t width, 
     const size_t words = (size_t)ntx * nty * 2;
     if ((rc = ensure(ctx, ctx->cover, words * 4))) return rc;
     if ((rc = ensure(ctx, ctx->cover_aux, 16 + (size_t)std::max(total, 1u) * 16))) return rc;
-    CU(ctx, cudaMemsetAsync(ctx->cover.p, 0, words * 4, stream));
     const uint32_t init[4] = { full_init, 0u, 0u, 0u };
-    CU(ctx, cudaMemsetAsync(ctx->cover_aux.p, 0, 16, stream));
-    if (total == 0 && full_init) CU(ctx, cudaMemcpyAsync(ctx->cover_aux.p, init, 16, cudaMemcpyHostToDevice, stream));   // no raster launch to OR it in
+    {
+        OpsBatch z;
+        if ((rc = ops_add(ctx, z, stream, ctx->cover.p, nullptr, words * 4, 0u))) return rc;
+        if ((rc = ops_add(ctx, z, stream, ctx->cover_aux.p, nullptr, 16, 0u))) return rc;
+        if (total == 0 && full_init) {                               // no raster launch to OR it in
+            if ((rc = ops_flush(ctx, z, stream))) return rc;
+            if ((rc = ops_add(ctx, z, stream, ctx->cover_aux.p, nullptr, 4, full_init))) return rc;
+        }
+        if ((rc = ops_flush(ctx, z, stream))) return rc;
+    }
     p.full_init = full_init;
     p.cover = (uint32_t*)ctx->cover.p;
     p.full = (uint32_t*)ctx->cover_aux.p;
@@ -1920,7 +1963,7 @@ int bvht_render_frame_device(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
     if ((rc = fill_scene(ctx, scene))) return rc;
     ctx->stats.last_trace_rays = 0;
     if (region.x0 >= region.x1 || region.y0 >= region.y1) return BVHT_OK;     // empty region: nothing to do
-    CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, kWordBandFlag * 4, ctx->stream));
+    { OpsBatch z; if ((rc = ops_add(ctx, z, ctx->stream, ctx->work_counter.p, nullptr, kWordBandFlag * 4, 0u)) || (rc = ops_flush(ctx, z, ctx->stream))) return rc; }
     cudaEventRecord(ctx->ev_a, ctx->stream);
     if ((rc = prepare_cover(ctx, camera, width, height, tile, ctx->stream))) return rc;       // inside the timed interval
     // the resident frame is one band unless BVHT_OPT_BANDS asks for more (then the bands' pull order applies, without flags)
@@ -2004,8 +2047,28 @@ static StreamWaitValue32Fn stream_wait_value32() {
     return fn;
 }
 
-int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height, uint32_t tile,
-                      bvht_rect region, const bvht_shade_params* shade, uint32_t* frame_out_host, bvht_hit* hits_out_host) {
+// Wait for the oldest frame in flight: its pixels are in the caller's host buffers when this returns.
+static int end_oldest_flight(bvht_ctx* ctx) {
+    bvht_ctx::Flight& f = ctx->flight[ctx->flights_ended & 1u];
+    if (!f.active) return fail(ctx, BVHT_ERR_NOT_READY, "no frame in flight");
+    f.active = false;
+    ++ctx->flights_ended;
+    for (int c = 0; c < f.n_cs; ++c) CU(ctx, cudaEventSynchronize(f.done[c]));
+    return BVHT_OK;
+}
+
+static int drain_flights(bvht_ctx* ctx) {
+    int rc = BVHT_OK;
+    while (ctx->flights_ended < ctx->flights_begun) { int r = end_oldest_flight(ctx); if (r && !rc) rc = r; }
+    return rc;
+}
+
+// bvht_render_frame (in_flight = false: returns with the frame in host memory) and bvht_render_frame_begin (in_flight = true:
+// returns with everything queued; the device->host copies of this frame then overlap the NEXT frame's kernels, which write the
+// other of two device staging frames).
+static int render_frame_host(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height, uint32_t tile,
+                             bvht_rect region, const bvht_shade_params* shade, uint32_t* frame_out_host, bvht_hit* hits_out_host,
+                             bool in_flight) {
     if (!ctx) return BVHT_ERR_BAD_HANDLE;
     if (!frame_out_host && !hits_out_host) return fail(ctx, BVHT_ERR_INVALID_ARG, "no output buffer");
     if (frame_out_host && (!shade || shade->kind == BVHT_SHADE_NONE || shade->kind > BVHT_SHADE_TEXTURE))
@@ -2013,17 +2076,28 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
     int rc = check_frame_args(ctx, camera, width, height, tile, region);
     if (rc) return rc;
     cudaSetDevice(ctx->device);
+    if (!in_flight) { if ((rc = drain_flights(ctx))) return rc; }
+    else if (ctx->flights_begun - ctx->flights_ended >= 2)
+        return fail(ctx, BVHT_ERR_NOT_READY, "two frames are in flight already: bvht_render_frame_end first");
+    const uint32_t parity = in_flight ? (uint32_t)(ctx->flights_begun & 1u) : 0u;
+    DevBuf& rgba_stage = parity ? ctx->rgba_buf2 : ctx->rgba_buf;
+    DevBuf& hits_stage = parity ? ctx->out_buf2 : ctx->out_buf;
+    // a begun frame with nothing to do still pairs with one bvht_render_frame_end
+    auto nothing_to_do = [&]() -> int {
+        if (in_flight) { bvht_ctx::Flight& f = ctx->flight[parity]; f.n_cs = 0; f.active = true; ++ctx->flights_begun; }
+        return BVHT_OK;
+    };
     if ((rc = ensure_bake(ctx, camera))) return rc;
     SceneDev scene;
     if ((rc = fill_scene(ctx, scene))) return rc;
     ctx->stats.last_trace_rays = 0;
     ctx->tl_valid = false;
-    if (region.x0 >= region.x1 || region.y0 >= region.y1) return BVHT_OK;
+    if (region.x0 >= region.x1 || region.y0 >= region.y1) return nothing_to_do();
     size_t npix = (size_t)width * height;
-    if (frame_out_host && (rc = ensure(ctx, ctx->rgba_buf, npix * 4))) return rc;
-    if (hits_out_host && (rc = ensure(ctx, ctx->out_buf, npix * sizeof(bvht_hit)))) return rc;
-    void* d_rgba = frame_out_host ? ctx->rgba_buf.p : nullptr;
-    void* d_hits = hits_out_host ? ctx->out_buf.p : nullptr;
+    if (frame_out_host && (rc = ensure(ctx, rgba_stage, npix * 4))) return rc;
+    if (hits_out_host && (rc = ensure(ctx, hits_stage, npix * sizeof(bvht_hit)))) return rc;
+    void* d_rgba = frame_out_host ? rgba_stage.p : nullptr;
+    void* d_hits = hits_out_host ? hits_stage.p : nullptr;
 
     // ONE persistent launch traces the whole region; its device->host copies are pipelined against it band by band.  K1 pulls
     // the pixel blocks band by band and raises a flag in device memory when a band's last block is done; the band's copy sits
@@ -2037,7 +2111,7 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
     if (shard_n > 1) bvht_shard_tile_rows(region, tile, shard_i, shard_n, &first_row, &own_rows);
     uint64_t rays = (uint64_t)(region.x1 - region.x0) * (region.y1 - region.y0);
     ctx->stats.last_trace_rays = rays / shard_n;
-    if (own_rows == 0) return BVHT_OK;                                   // this shard owns no tile row of the region
+    if (own_rows == 0) return nothing_to_do();                                 // this shard owns no tile row of the region
     const size_t px_bytes = (frame_out_host ? 4 : 0) + (hits_out_host ? sizeof(bvht_hit) : 0);
     const uint64_t own_bytes = (uint64_t)own_rows * tile * (region.x1 - region.x0) * px_bytes;
     BandPlan plan;
@@ -2055,7 +2129,7 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
     plan.seq = ++ctx->frame_seq;
     int4 rects[32];
     order_bands(ctx, camera, width, height, tile, first_row, own_rows, plan, rects);
-    CU(ctx, cudaMemsetAsync(ctx->work_counter.p, 0, kWordBandFlag * 4, ctx->stream));
+    { OpsBatch z; if ((rc = ops_add(ctx, z, ctx->stream, ctx->work_counter.p, nullptr, kWordBandFlag * 4, 0u)) || (rc = ops_flush(ctx, z, ctx->stream))) return rc; }
     cudaEventRecord(ctx->ev_a, ctx->stream);
     if ((rc = prepare_cover(ctx, camera, width, height, tile, ctx->stream))) return rc;
     cudaEventRecord(ctx->ev_cover_t, ctx->stream);
@@ -2102,12 +2176,9 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
     };
     // belt and braces: once the kernels are done every flag is raised from the stream itself, so a copy can never wait forever
     auto raise_all_flags = [&]() -> int {
-        int rc2 = ensure_pinned(ctx, 1 << 16);
-        if (rc2) return rc2;
-        unsigned int* fill = (unsigned int*)ctx->pinned;
-        for (uint32_t j = 0; j < 32; ++j) fill[j] = plan.seq;
-        CU(ctx, cudaMemcpyAsync((unsigned int*)ctx->work_counter.p + kWordBandFlag, fill, 32 * 4, cudaMemcpyHostToDevice, ctx->stream));
-        return BVHT_OK;
+        OpsBatch f;
+        int rc2 = ops_add(ctx, f, ctx->stream, (unsigned int*)ctx->work_counter.p + kWordBandFlag, nullptr, 32 * 4, plan.seq);
+        return rc2 ? rc2 : ops_flush(ctx, f, ctx->stream);
     };
     for (uint32_t i = 0; i < plan.n_bands; ++i) {
         const uint32_t k = plan.order[i];
@@ -2124,9 +2195,19 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
             cudaGetLastError();
             return rc;
         }
-        if (i < 16) cudaEventRecord(ctx->ev_copy_t[i], cs);
+        if (i < 16 && !in_flight) cudaEventRecord(ctx->ev_copy_t[i], cs);
     }
     if (plan.flags && (rc = raise_all_flags())) return rc;     // queued after the copies: the first copy reaches its stream earlier
+    if (in_flight) {
+        // nothing joins the main stream: the next frame's kernels start behind this frame's kernels, not behind its copies
+        bvht_ctx::Flight& f = ctx->flight[parity];
+        for (int c = 0; c < n_cs; ++c) CU(ctx, cudaEventRecord(f.done[c], ctx->copy_streams[c]));
+        f.n_cs = n_cs; f.active = true;
+        ++ctx->flights_begun;
+        cudaEventRecord(ctx->ev_b, ctx->stream);                // last_trace_ms = the frame's kernels
+        ctx->trace_timed = true;
+        return BVHT_OK;
+    }
     for (int c = 0; c < n_cs; ++c) {
         CU(ctx, cudaEventRecord(ctx->ev_copy_join[c], ctx->copy_streams[c]));
         CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_join[c], 0));
@@ -2137,6 +2218,22 @@ int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, 
     ctx->tl_bands = std::min(plan.n_bands, 16u); ctx->tl_valid = true;
     for (uint32_t i = 0; i < ctx->tl_bands; ++i) ctx->tl_rows[i] = std::min(own_rows, (plan.order[i] + 1u) * plan.band_rows) - plan.order[i] * plan.band_rows;
     return BVHT_OK;
+}
+
+int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height, uint32_t tile,
+                      bvht_rect region, const bvht_shade_params* shade, uint32_t* frame_out_host, bvht_hit* hits_out_host) {
+    return render_frame_host(ctx, camera, width, height, tile, region, shade, frame_out_host, hits_out_host, false);
+}
+
+int bvht_render_frame_begin(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height, uint32_t tile,
+                            bvht_rect region, const bvht_shade_params* shade, uint32_t* frame_out_host, bvht_hit* hits_out_host) {
+    return render_frame_host(ctx, camera, width, height, tile, region, shade, frame_out_host, hits_out_host, true);
+}
+
+int bvht_render_frame_end(bvht_ctx* ctx) {
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    cudaSetDevice(ctx->device);
+    return end_oldest_flight(ctx);
 }
 
 int bvht_trace_primary(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height, uint32_t tile,

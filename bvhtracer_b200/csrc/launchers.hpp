@@ -30,6 +30,11 @@ struct ModelStatsDev {
 cudaError_t launch_model_stats(const float* tris_aos, uint32_t n_tris, ModelStatsDev* out, cudaStream_t s);
 cudaError_t launch_tight_box(const float* tris_aos, uint32_t n_tris, double scale, double abs_, unsigned long long* out6, cudaStream_t s);
 
+// up to 8 word copies (from page-locked host memory) / word fills in one launch
+struct SmallOp { void* dst; const void* src; uint32_t words; uint32_t fill; };
+struct SmallOps { SmallOp op[8]; uint32_t n; };
+cudaError_t launch_small_ops(const SmallOps& ops, cudaStream_t s);
+
 cudaError_t launch_read_bw(const void* buf, size_t bytes, uint32_t iters, int grid, unsigned long long* sink, cudaStream_t s);
 cudaError_t launch_ray_bounds(const float* rays, unsigned long long n, unsigned int* out2, cudaStream_t s);
 cudaError_t launch_refit_sub_nodes(float4* raw, const uint32_t* parent, unsigned int* counters, const float* tris_aos,

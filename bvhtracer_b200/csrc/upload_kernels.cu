@@ -367,7 +367,30 @@ tight_box_kernel(const float* __restrict__ tris, uint32_t n_tris, double scale, 
     }
 }
 
+// Small per-frame uploads and fills done by the SMs: `src` is page-locked host memory read over PCIe by the kernel itself (or
+// null: store `fill`).  A cudaMemcpyAsync of the same bytes goes through a copy engine, where it queues behind whatever large
+// device->host copy another stream has in progress -- with frames in flight that is the previous frame's band copy, ~30 us per
+// upload (tools/ce_interference_probe.py) and the next frame's kernels wait behind it.
+__global__ void __launch_bounds__(256) small_ops_kernel(SmallOps ops) {
+    for (uint32_t k = 0; k < ops.n; ++k) {
+        const SmallOp op = ops.op[k];
+        uint32_t* dst = (uint32_t*)op.dst;
+        const uint32_t* src = (const uint32_t*)op.src;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < op.words; i += gridDim.x * blockDim.x)
+            dst[i] = src ? src[i] : op.fill;
+    }
+}
+
 } // namespace
+
+cudaError_t launch_small_ops(const SmallOps& ops, cudaStream_t s) {
+    if (ops.n == 0) return cudaSuccess;
+    uint32_t most = 0;
+    for (uint32_t k = 0; k < ops.n; ++k) most = std::max(most, ops.op[k].words);
+    int grid = (int)std::min<uint32_t>(std::max<uint32_t>((most + 1023u) / 1024u, 1u), 148u);
+    small_ops_kernel<<<grid, 256, 0, s>>>(ops);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_read_bw(const void* buf, size_t bytes, uint32_t iters, int grid, unsigned long long* sink, cudaStream_t s) {
     read_bw_kernel<<<grid, 256, 0, s>>>((const uint4*)buf, bytes / 16, iters, sink);

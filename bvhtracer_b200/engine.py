@@ -221,6 +221,20 @@ class Engine:
             ptr(frame_out) if frame_out is not None else None, ptr(hits_out) if hits_out is not None else None))
         return frame_out, hits_out
 
+    def render_frame_begin(self, camera, width, height, shade, frame_out, hits_out=None, tile=8, region=None):
+        """render_frame without the wait (at most two frames in flight); frame_out / hits_out: page-locked arrays the caller keeps
+        alive and untouched until the matching render_frame_end()."""
+        camera = np.ascontiguousarray(camera)
+        x0, y0, x1, y1 = region if region is not None else (0, 0, width, height)
+        self._check(self._lib.bvht_render_frame_begin(
+            self._ctx, ptr(camera), int(width), int(height), int(tile), Rect(x0, y0, x1, y1),
+            C.byref(shade) if shade is not None else None,
+            ptr(frame_out) if frame_out is not None else None, ptr(hits_out) if hits_out is not None else None))
+
+    def render_frame_end(self):
+        """Wait for the oldest begun frame."""
+        self._check(self._lib.bvht_render_frame_end(self._ctx))
+
     def render_frame_device(self, camera, width, height, shade, tile, region, frame_dptr, hits_dptr):
         camera = np.ascontiguousarray(camera)
         x0, y0, x1, y1 = region if region is not None else (0, 0, width, height)

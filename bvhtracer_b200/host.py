@@ -74,6 +74,7 @@ def lib():
             "bvhx_scene_build": (_P, [_P]),
             "bvhx_scene_len": (C.c_uint32, [_P]),
             "bvhx_scene_set_transform": (C.c_int, [_P, C.c_uint32, _P]),
+            "bvhx_scene_set_transforms": (C.c_int, [_P, _P, C.c_uint32]),
             "bvhx_scene_rebuild": (None, [_P]),
             "bvhx_scene_tlas": (_P, [_P, C.POINTER(C.c_uint32)]),
             "bvhx_scene_instance": (None, [_P, C.c_uint32, _P, _P]),
@@ -88,6 +89,8 @@ def lib():
             "bvhx_state_frame": (_P, [_P]),
             "bvhx_state_hits": (_P, [_P]),
             "bvhx_renderer_render": (C.c_int64, [_P, _P, _P]),
+            "bvhx_renderer_render_begin": (C.c_int64, [_P, _P, _P]),
+            "bvhx_renderer_render_end": (C.c_int, [_P]),
             "bvhx_renderer_sync_scene": (C.c_int, [_P, _P]),
             "bvhx_renderer_update_transforms": (C.c_int, [_P, _P, _P, C.c_uint32]),
             "bvhx_renderer_build_model": (_P, [_P, _P]),
@@ -315,6 +318,12 @@ class Scene:
         if lib().bvhx_scene_set_transform(self._h, int(i), _ffi.ptr(transform.matrix)) != 0:
             raise _err()
 
+    def set_transforms(self, matrices):
+        """set_transform for objects 0..n-1 in one call; matrices: n x 16 f32, column-major"""
+        m = np.ascontiguousarray(matrices, "<f4").reshape(-1, 16)
+        if lib().bvhx_scene_set_transforms(self._h, _ffi.ptr(m), m.shape[0]) != 0:
+            raise _err()
+
     def rebuild(self):
         lib().bvhx_scene_rebuild(self._h)
 
@@ -438,6 +447,18 @@ class Renderer:
         if n < 0:
             raise _err()
         return int(n)
+
+    def render_begin(self, state, scene):
+        """render() without the wait: up to two frames in flight, each into its own RendererState (bvht_render_frame_begin)."""
+        n = lib().bvhx_renderer_render_begin(self._h, state._h, scene._h)
+        if n < 0:
+            raise _err()
+        return int(n)
+
+    def render_end(self):
+        """Wait for the oldest begun frame; its RendererState then holds the pixels (bvht_render_frame_end)."""
+        if lib().bvhx_renderer_render_end(self._h) != 0:
+            raise _err()
 
     def sync_scene(self, scene):
         if lib().bvhx_renderer_sync_scene(self._h, scene._h) != 0:

@@ -815,18 +815,13 @@ public:
         scene_ = &scene; scene_version_ = scene.version();
     }
 
-    size_t evaluate(RendererState& state, Scene& scene) override {
-        sync_scene(scene);
-        state.bind(ctx_);
-        bvht_camera cam = scene.active_camera().to_ffi();
-        bvht_rect region = { 0, 0, (uint32_t)state.width(), (uint32_t)state.height() };
-        bvht_shade_params shade = state.shading().params;
-        if (shade.kind == BVHT_SHADE_NORMAL && !scene.objects().empty())     // scene.get_unchecked(0).get_transform(), renderer.rs:275-278
-            std::memcpy(shade.object0_transform, scene.objects()[0].get_transform().matrix.m, 64);
-        check(bvht_render_frame(ctx_, &cam, (uint32_t)state.width(), (uint32_t)state.height(), tile_, region, &shade,
-                                state.frame_mut(), state.keep_hits() ? state.hits_mut() : nullptr));
-        return state.width() * state.height();
-    }
+    size_t evaluate(RendererState& state, Scene& scene) override { return submit(state, scene, false); }
+
+    // Two frames in flight (bvht_render_frame_begin / _end): evaluate_begin queues the frame into `state` and returns;
+    // evaluate_end waits for the oldest begun frame, whose state then holds its pixels.  Alternate two RendererStates: the
+    // copies of one frame run under the tracing of the next.  `state` must stay alive and untouched until its evaluate_end.
+    size_t evaluate_begin(RendererState& state, Scene& scene) { return submit(state, scene, true); }
+    void evaluate_end() { check(bvht_render_frame_end(ctx_)); }
 
     // Scene::intersect(&Ray) (scene.rs:32-34) for a batch of rays, on the device
     void intersect(Scene& scene, const bvht_ray* rays, uint64_t n, bvht_hit* out) {
@@ -834,6 +829,19 @@ public:
         check(bvht_trace_rays(ctx_, rays, n, out));
     }
 private:
+    size_t submit(RendererState& state, Scene& scene, bool in_flight) {
+        sync_scene(scene);
+        state.bind(ctx_);
+        bvht_camera cam = scene.active_camera().to_ffi();
+        bvht_rect region = { 0, 0, (uint32_t)state.width(), (uint32_t)state.height() };
+        bvht_shade_params shade = state.shading().params;
+        if (shade.kind == BVHT_SHADE_NORMAL && !scene.objects().empty())     // scene.get_unchecked(0).get_transform(), renderer.rs:275-278
+            std::memcpy(shade.object0_transform, scene.objects()[0].get_transform().matrix.m, 64);
+        check((in_flight ? bvht_render_frame_begin : bvht_render_frame)(ctx_, &cam, (uint32_t)state.width(), (uint32_t)state.height(), tile_,
+                                                                       region, &shade, state.frame_mut(),
+                                                                       state.keep_hits() ? state.hits_mut() : nullptr));
+        return state.width() * state.height();
+    }
     struct Uploaded { Model* model; uint32_t blas_id; uint64_t version; };
     void upload_attributes(const Model& m, uint32_t blas_id) {
         if (m.normals().size() == m.primitives().size())
@@ -858,8 +866,16 @@ class Renderer {
 public:
     explicit Renderer(std::unique_ptr<Integrator> pipeline) : integrator_(std::move(pipeline)) {}
     size_t render(RendererState& state, Scene& scene) { return integrator_->evaluate(state, scene); }
+    // render() split in two for integrators that keep frames in flight (CudaPathTracer): see evaluate_begin / evaluate_end
+    size_t render_begin(RendererState& state, Scene& scene) { return cuda().evaluate_begin(state, scene); }
+    void render_end() { cuda().evaluate_end(); }
     Integrator* integrator() { return integrator_.get(); }
 private:
+    CudaPathTracer& cuda() {
+        auto* c = dynamic_cast<CudaPathTracer*>(integrator_.get());
+        if (!c) throw std::runtime_error("render_begin / render_end: the integrator keeps no frames in flight");
+        return *c;
+    }
     std::unique_ptr<Integrator> integrator_;
 };
 

@@ -141,6 +141,18 @@ BVHX_API int bvhx_scene_set_transform(void* scene, uint32_t i, const float m[16]
         return 0;
     }, -1);
 }
+// `for (i, t) in transforms { scene.get_mut_unchecked(i).set_transform(&t) }` in one call (a binding with a per-call cost pays it once)
+BVHX_API int bvhx_scene_set_transforms(void* scene, const float* m, uint32_t n) {
+    return guard([&]() -> int {
+        Scene& s = *(Scene*)scene;
+        if (n > s.objects().size()) throw std::runtime_error("set_transforms: more transforms than scene objects");
+        for (uint32_t i = 0; i < n; ++i) {
+            Transform3 t; std::memcpy(t.matrix.m, m + 16 * (size_t)i, 64);
+            s.get_mut_unchecked(i).set_transform(t);
+        }
+        return 0;
+    }, -1);
+}
 BVHX_API void bvhx_scene_rebuild(void* scene) { ((Scene*)scene)->rebuild(); }
 BVHX_API const void* bvhx_scene_tlas(void* scene, uint32_t* nodes_used) {
     const Tlas& t = ((Scene*)scene)->tlas();
@@ -191,6 +203,12 @@ BVHX_API const uint32_t* bvhx_state_frame(void* state) { return ((RendererState*
 BVHX_API const bvht_hit* bvhx_state_hits(void* state) { return ((RendererState*)state)->hits(); }
 BVHX_API int64_t bvhx_renderer_render(void* renderer, void* state, void* scene) {
     return guard([&]() -> int64_t { return (int64_t)((Renderer*)renderer)->render(*(RendererState*)state, *(Scene*)scene); }, (int64_t)-1);
+}
+BVHX_API int64_t bvhx_renderer_render_begin(void* renderer, void* state, void* scene) {
+    return guard([&]() -> int64_t { return (int64_t)((Renderer*)renderer)->render_begin(*(RendererState*)state, *(Scene*)scene); }, (int64_t)-1);
+}
+BVHX_API int bvhx_renderer_render_end(void* renderer) {
+    return guard([&]() -> int { ((Renderer*)renderer)->render_end(); return 0; }, -1);
 }
 BVHX_API int bvhx_renderer_sync_scene(void* renderer, void* scene) {
     return guard([&]() -> int { ((CudaPathTracer*)((Renderer*)renderer)->integrator())->sync_scene(*(Scene*)scene); return 0; }, -1);

@@ -31,7 +31,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 def test_abi_version_and_struct_sizes():
     lib = _ffi.load()
-    assert lib.bvht_abi_version() == 4
+    assert lib.bvht_abi_version() == 5
     assert _ffi.BVH_NODE.itemsize == 32          # bvh.rs:720-723
     assert _ffi.TLAS_NODE.itemsize == 32
     assert _ffi.HIT.itemsize == 16               # intersection.rs:77-83

@@ -488,6 +488,90 @@ def test_host_mirror_renderer_animated_frames():
         assert state.frame_buffer().tobytes() == O.shade(1, ref).tobytes()
 
 
+def test_two_frames_in_flight_deliver_render_frames_bytes():
+    # Renderer::render_begin / render_end (bvht_render_frame_begin / _end): frame n's device->host copies run under frame n+1's
+    # kernels, out of the other of two device staging frames.  Every frame of the animation must arrive byte for byte as the
+    # oracle renders it, whatever was queued behind it (the next frame's scene update and kernels), and the begin/end pairing
+    # rules hold: a third begin and an end with nothing in flight are refused, render() drains what is in flight.
+    from bvhtracer_b200 import host
+    anim = examples.GridAnimation()
+    scene, models = host.build_scene(examples.sixteen_armadillos(0))
+    renderer = host.Renderer(flags=FLAG_STRICT | FLAG_LEAF_ACCEL)
+    w, h = 1283, 717                                                  # ragged size, several bands
+    states = [host.RendererState(host.depth_pipeline(80.0, 3.0), w, h, keep_hits=(i == 0)) for i in range(2)]
+    n_frames = 5
+    refs = []
+    for frame in range(n_frames):
+        ref_scene, ref_cam = SB.oracle_scene(examples.sixteen_armadillos(frame))
+        refs.append(ref_scene.render(ref_cam, w, h, threads=NTHREADS))
+    with pytest.raises(host.HostError):
+        renderer.render_end()                                         # nothing in flight
+    for frame in range(n_frames + 1):
+        if frame < n_frames:
+            if frame > 0:
+                anim.update()
+                for i, o in enumerate(anim.objects()):
+                    scene.set_transform(i, host.object_transform(o))
+                scene.rebuild()
+            assert renderer.render_begin(states[frame & 1], scene) == w * h
+        if frame >= 1:
+            renderer.render_end()                                     # completes frame - 1 while frame is being traced
+            done = frame - 1
+            assert states[done & 1].frame_buffer().tobytes() == O.shade(1, refs[done]).tobytes(), done
+            if (done & 1) == 0:
+                assert states[0].hits().tobytes() == refs[done].tobytes(), done
+    with pytest.raises(host.HostError):
+        renderer.render_end()
+    # two begun, a third refused; render() completes both before it renders
+    third = host.RendererState(host.depth_pipeline(80.0, 3.0), w, h, keep_hits=False)
+    renderer.render_begin(states[0], scene)
+    renderer.render_begin(states[1], scene)
+    with pytest.raises(host.HostError):
+        renderer.render_begin(third, scene)
+    renderer.render(third, scene)
+    for st in (states[0], states[1], third):
+        assert st.frame_buffer().tobytes() == O.shade(1, refs[-1]).tobytes()
+    with pytest.raises(host.HostError):
+        renderer.render_end()
+
+
+def test_frames_in_flight_with_vertex_updates_between_them():
+    # big_ben_clock: the vertices of frame n+1 are uploaded and refitted while frame n's copies are still running
+    _, cam = SB.oracle_scene(examples.big_ben_clock())
+    blas = O.Blas(O.load_asset("bigben.tri"))              # private copy: vertices get animated
+    scene = O.Scene([blas], [(0, O.mat4_identity())], with_transform=False)
+    anim = examples.BigBenAnimation(blas.tris)
+    fcam = SB.to_ffi_camera(cam)
+    w, h = 640, 360
+    with Engine(flags=FLAG_STRICT | FLAG_LEAF_ACCEL) as eng:
+        ids = SB.upload_scene(eng, scene)
+        shade = eng.shade_depth()
+        bufs = [(eng.pinned_array(w * h, "<u4"), eng.pinned_array(w * h, _ffi.HIT)) for _ in range(2)]
+        want = []
+        for frame in range(4):
+            verts = anim.animate()
+            blas.tris[:] = verts
+            blas.refit()
+            scene.refresh_blas()
+            want.append(scene.render(cam, w, h, threads=NTHREADS))
+            eng.blas_update_vertices(ids[0], verts)
+            eng.blas_refit(ids[0])
+            f, hh = bufs[frame & 1]
+            if frame >= 2:
+                eng.render_frame_end()                                # frame - 2 owned these buffers
+                assert hh.tobytes() == want[frame - 2].tobytes(), frame - 2
+            f[:] = 0xDEADBEEF
+            eng.render_frame_begin(fcam, w, h, shade, f, hh)
+        eng.sync()                                                    # completes the two still in flight
+        for frame in (2, 3):
+            f, hh = bufs[frame & 1]
+            assert hh.tobytes() == want[frame].tobytes() and f.tobytes() == O.shade(1, want[frame]).tobytes(), frame
+        with pytest.raises(BvhtError):
+            eng.render_frame_end()
+        for f, hh in bufs:
+            eng.free_pinned(f); eng.free_pinned(hh)
+
+
 def test_host_mirror_big_ben_refit_and_scene_intersect():
     # big_ben_clock.rs:67-103: animate() + ModelInstance::refit(), IntersectionAccumulator + IntersectionShader
     from bvhtracer_b200 import host
