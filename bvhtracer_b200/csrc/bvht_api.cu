@@ -179,6 +179,8 @@ struct bvht_ctx {
     std::string err;
 };
 
+constexpr uint32_t kWordBandCount = 32, kWordBandDone = 64, kWordBandFlag = 96;     // words of bvht_ctx::work_counter
+
 namespace {
 
 int fail(bvht_ctx* ctx, int status, const char* fmt, ...) {
@@ -1743,7 +1745,6 @@ struct BandPlan {
     bool     have_rects = false;
 };
 
-constexpr uint32_t kWordBandCount = 32, kWordBandDone = 64, kWordBandFlag = 96;
 
 // One persistent launch of K1 (preceded by K0 when it pays) over `region` on `stream`.
 static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvht_camera* camera, uint32_t width, uint32_t height,
@@ -2053,7 +2054,28 @@ static int end_oldest_flight(bvht_ctx* ctx) {
     if (!f.active) return fail(ctx, BVHT_ERR_NOT_READY, "no frame in flight");
     f.active = false;
     ++ctx->flights_ended;
-    for (int c = 0; c < f.n_cs; ++c) CU(ctx, cudaEventSynchronize(f.done[c]));
+    // a bounded wait: a copy that never gets its flag must surface as an error with the evidence, not as a hang
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int c = 0; c < f.n_cs; ++c) {
+        for (;;) {
+            cudaError_t e = cudaEventQuery(f.done[c]);
+            if (e == cudaSuccess) break;
+            if (e != cudaErrorNotReady) return fail(ctx, BVHT_ERR_CUDA, "frame in flight failed: %s", cudaGetErrorString(e));
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 20.0) {
+                unsigned int w[128] = { 0 };
+                cudaStream_t dbg = nullptr;
+                cudaStreamCreateWithFlags(&dbg, cudaStreamNonBlocking);
+                cudaMemcpyAsync(w, ctx->work_counter.p, sizeof w, cudaMemcpyDeviceToHost, dbg);
+                cudaStreamSynchronize(dbg);
+                cudaStreamDestroy(dbg);
+                std::string flags, done;
+                for (int k = 0; k < 16; ++k) { flags += std::to_string(w[kWordBandFlag + k]) + " "; done += std::to_string(w[kWordBandDone + k]) + " "; }
+                return fail(ctx, BVHT_ERR_CUDA, "frame in flight did not complete within 20 s (copy stream %d; frame sequence now %u; cursor %u; "
+                            "main stream %s; band flags %s; blocks done per band %s)", c, ctx->frame_seq, w[0],
+                            cudaStreamQuery(ctx->stream) == cudaSuccess ? "idle" : "busy", flags.c_str(), done.c_str());
+            }
+        }
+    }
     return BVHT_OK;
 }
 
@@ -2121,6 +2143,13 @@ static int render_frame_host(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
     plan.n_bands = own_bytes < (512u << 10) ? 1u : own_bytes < (2u << 20) ? 2u
                  : (uint32_t)std::min<uint64_t>(std::max<uint64_t>(own_bytes / (2560u << 10), 4), 16);
     if (ctx->knobs.bands > 0) plan.n_bands = (uint32_t)ctx->knobs.bands;
+    // a frame in flight is copied once its kernels are done: the copy runs under the NEXT frame's kernels anyway, and nothing of
+    // it depends on stream memory operations.  (Per-band flags as in the synchronous frame were faster here too -- C3 4K 0.93 vs
+    // 0.97 ms, C5 8K 2.74 vs 4.2 ms, because copies gated one by one leave the copy engine's queue open to the next frame's
+    // readbacks -- but with the waits of two frames queued on a stream the copy streams wedged now and then: trippy_teapots 4K,
+    // every flag raised, main stream idle, copy never issued, 6 runs of 10; profiles/r02_frames_in_flight.txt.)
+    const uint32_t copy_pieces = std::max(1u, std::min(plan.n_bands, own_rows));
+    if (in_flight) plan.n_bands = 1;
     plan.n_bands = std::max(1u, std::min(plan.n_bands, own_rows));
     plan.band_rows = (own_rows + plan.n_bands - 1) / plan.n_bands;
     plan.n_bands = (own_rows + plan.band_rows - 1) / plan.band_rows;
@@ -2142,9 +2171,8 @@ static int render_frame_host(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
     if (!plan.flags) for (int c = 0; c < 3; ++c) CU(ctx, cudaStreamWaitEvent(ctx->copy_streams[c], ctx->ev_fork, 0));      // no flags: copy after the kernels
     const unsigned long long flag_base = (unsigned long long)((unsigned int*)ctx->work_counter.p + kWordBandFlag);
     const int n_cs = std::max(1, std::min(ctx->n_copy_streams, 3));
-    auto copy_band = [&](uint32_t k, cudaStream_t cs) -> int {
-        // tile rows of band k: own-row indices [k0, k1) = global tile rows first_row + j * shard_n
-        const uint32_t k0 = k * plan.band_rows, k1 = std::min(own_rows, (k + 1) * plan.band_rows);
+    auto copy_own_rows = [&](uint32_t k0, uint32_t k1, cudaStream_t cs) -> int {
+        // own-row indices [k0, k1) = global tile rows first_row + j * shard_n
         for (int which = 0; which < 2; ++which) {
             void* host = which == 0 ? (void*)frame_out_host : (void*)hits_out_host;
             const void* dev = which == 0 ? d_rgba : d_hits;
@@ -2174,12 +2202,35 @@ static int render_frame_host(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
         }
         return BVHT_OK;
     };
+    auto copy_band = [&](uint32_t k, cudaStream_t cs) -> int {
+        return copy_own_rows(k * plan.band_rows, std::min(own_rows, (k + 1) * plan.band_rows), cs);
+    };
     // belt and braces: once the kernels are done every flag is raised from the stream itself, so a copy can never wait forever
     auto raise_all_flags = [&]() -> int {
         OpsBatch f;
         int rc2 = ops_add(ctx, f, ctx->stream, (unsigned int*)ctx->work_counter.p + kWordBandFlag, nullptr, 32 * 4, plan.seq);
         return rc2 ? rc2 : ops_flush(ctx, f, ctx->stream);
     };
+    if (in_flight) {
+        // in pieces of the band size all the same: whatever else needs the link or a copy engine meanwhile (the next frame's
+        // uploads) gets in between two pieces instead of waiting for the whole frame (big_ben_clock 8K: 133 MB = 2.4 ms)
+        const uint32_t piece_rows = (own_rows + copy_pieces - 1) / copy_pieces;
+        for (uint32_t k0 = 0; k0 < own_rows; k0 += piece_rows)
+            if ((rc = copy_own_rows(k0, std::min(own_rows, k0 + piece_rows), ctx->copy_streams[0]))) {
+                cudaStreamSynchronize(ctx->stream);
+                cudaStreamSynchronize(ctx->copy_streams[0]);
+                cudaGetLastError();
+                return rc;
+            }
+        // nothing joins the main stream: the next frame's kernels start behind this frame's kernels, not behind its copy
+        bvht_ctx::Flight& f = ctx->flight[parity];
+        CU(ctx, cudaEventRecord(f.done[0], ctx->copy_streams[0]));
+        f.n_cs = 1; f.active = true;
+        ++ctx->flights_begun;
+        cudaEventRecord(ctx->ev_b, ctx->stream);                // last_trace_ms = the frame's kernels
+        ctx->trace_timed = true;
+        return BVHT_OK;
+    }
     for (uint32_t i = 0; i < plan.n_bands; ++i) {
         const uint32_t k = plan.order[i];
         rc = BVHT_OK;
@@ -2195,19 +2246,9 @@ static int render_frame_host(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
             cudaGetLastError();
             return rc;
         }
-        if (i < 16 && !in_flight) cudaEventRecord(ctx->ev_copy_t[i], cs);
+        if (i < 16) cudaEventRecord(ctx->ev_copy_t[i], cs);
     }
     if (plan.flags && (rc = raise_all_flags())) return rc;     // queued after the copies: the first copy reaches its stream earlier
-    if (in_flight) {
-        // nothing joins the main stream: the next frame's kernels start behind this frame's kernels, not behind its copies
-        bvht_ctx::Flight& f = ctx->flight[parity];
-        for (int c = 0; c < n_cs; ++c) CU(ctx, cudaEventRecord(f.done[c], ctx->copy_streams[c]));
-        f.n_cs = n_cs; f.active = true;
-        ++ctx->flights_begun;
-        cudaEventRecord(ctx->ev_b, ctx->stream);                // last_trace_ms = the frame's kernels
-        ctx->trace_timed = true;
-        return BVHT_OK;
-    }
     for (int c = 0; c < n_cs; ++c) {
         CU(ctx, cudaEventRecord(ctx->ev_copy_join[c], ctx->copy_streams[c]));
         CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_join[c], 0));

@@ -75,3 +75,18 @@ for bands, order in ((4, 1), (7, 2), (23, 3), (2, 0)):
 e6.set_shard(1, 3)
 r6.render(st6, scene5)
 print("pipelined frame ok", int(st6.frame_buffer().sum() % 1000))
+
+# two frames in flight: band copies of one frame under the kernels of the next, scene updates queued between them
+r7 = host.Renderer(flags=2)
+pair = [host.RendererState(host.depth_pipeline(), 320, 184, keep_hits=(i == 0)) for i in range(2)]
+r7.engine().set_option(3, 5)      # BVHT_OPT_BANDS
+for f in range(5):
+    anim.update()
+    for i, o in enumerate(anim.objects()):
+        scene5.set_transform(i, host.object_transform(o))
+    scene5.rebuild()
+    r7.render_begin(pair[f & 1], scene5)
+    if f:
+        r7.render_end()
+r7.render_end()
+print("frames in flight ok", int(pair[0].frame_buffer().sum() % 1000), int(pair[1].frame_buffer().sum() % 1000))
