@@ -79,6 +79,11 @@ extern "C" {
                           inst_out: *mut BvhtInstance, bounds_out: *mut f32, max_inst: u32, n_inst_out: *mut u32) -> c_int;
     pub fn bvht_render_frame(ctx: *mut BvhtCtx, cam: *const BvhtCamera, width: u32, height: u32, tile: u32, region: BvhtRect,
                              shade: *const BvhtShade, frame_out: *mut u32, hits_out: *mut BvhtHit) -> c_int;
+    /// bvht_render_frame with up to two frames in flight: `begin` queues the frame and returns, `end` waits for the oldest one.
+    /// The host buffers must be page-locked (bvht_host_alloc) and stay untouched until the matching `end`.
+    pub fn bvht_render_frame_begin(ctx: *mut BvhtCtx, cam: *const BvhtCamera, width: u32, height: u32, tile: u32, region: BvhtRect,
+                                   shade: *const BvhtShade, frame_out: *mut u32, hits_out: *mut BvhtHit) -> c_int;
+    pub fn bvht_render_frame_end(ctx: *mut BvhtCtx) -> c_int;
     pub fn bvht_trace_rays(ctx: *mut BvhtCtx, rays: *const BvhtRay, n: u64, out: *mut BvhtHit) -> c_int;
     pub fn bvht_host_alloc(ctx: *mut BvhtCtx, bytes: usize, out: *mut *mut c_void) -> c_int;
     pub fn bvht_host_free(ctx: *mut BvhtCtx, p: *mut c_void) -> c_int;

@@ -167,6 +167,31 @@ impl Integrator for CudaPathTracer {
     }
 }
 
+impl CudaPathTracer {
+    /// `evaluate` without the wait: the frame is queued into `pixels` (page-locked, width * height Rgba<u8>, e.g. from
+    /// bvht_host_alloc; NOT the `Vec` of a `FrameBuffer`, which is pageable and may move) and the call returns.  At most two
+    /// frames may be in flight; alternate two buffers and present frame n after `evaluate_end()` while frame n + 1 is traced.
+    ///
+    /// # Safety
+    /// `pixels` must stay valid and untouched until the matching `evaluate_end`.
+    pub unsafe fn evaluate_begin(&mut self, pixels: *mut u32, width: u32, height: u32, scene: &Scene) -> usize {
+        self.upload_frame_state(scene);
+        let cam = Self::camera(scene);
+        let mut shade = self.shade;
+        if shade.kind == ffi::BVHT_SHADE_NORMAL {
+            shade.object0_transform = cols(&scene.get_unchecked(0).get_transform().compute_matrix());
+        }
+        self.check(bvht_render_frame_begin(self.ctx, &cam, width, height, self.tile, BvhtRect { x0: 0, y0: 0, x1: width, y1: height },
+                                           &shade, pixels, std::ptr::null_mut()));
+        (width * height) as usize
+    }
+
+    /// Wait for the oldest frame begun with `evaluate_begin`; its pixels are then in the buffer that was passed.
+    pub fn evaluate_end(&mut self) {
+        self.check(unsafe { bvht_render_frame_end(self.ctx) });
+    }
+}
+
 impl Drop for CudaPathTracer {
     fn drop(&mut self) { unsafe { bvht_destroy(self.ctx) } }
 }
