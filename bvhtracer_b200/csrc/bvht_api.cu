@@ -153,8 +153,22 @@ struct bvht_ctx {
     DevBuf out_buf, rays_buf, rgba_buf;               // device staging for the host-pointer entry points
     DevBuf out_buf2, rgba_buf2;                       // second frame in flight (bvht_render_frame_begin): odd frames stage here
     // frames begun and not yet ended (at most two): the events that close each copy stream's share of the frame
-    struct Flight { bool active = false; int n_cs = 0; cudaEvent_t done[3] = { nullptr, nullptr, nullptr }; } flight[2];
+    // what a band copy needs to know about its frame (bvht_render_frame and the frames in flight)
+    struct CopyJob {
+        void* host_frame = nullptr; void* host_hits = nullptr; const void* d_rgba = nullptr; const void* d_hits = nullptr;
+        uint32_t width = 0, tile = 8, first_row = 0, own_rows = 0, shard_n = 1;
+        bvht_rect region = { 0, 0, 0, 0 };
+    };
+    struct Flight {
+        bool active = false; int n_cs = 0; cudaEvent_t done[3] = { nullptr, nullptr, nullptr };
+        // the frame's band copies are issued BY THE HOST as the bands' flags come up in host-visible memory (pump_flights)
+        CopyJob job;
+        uint32_t n_bands = 0, band_rows = 0, next = 0, seq = 0;       // next = bands issued so far, in pull order
+        uint8_t order[32] = { 0 };
+        bool flags = false, closed = false;                            // closed = every copy issued, done[0] recorded
+    } flight[2];
     uint64_t flights_begun = 0, flights_ended = 0;
+    unsigned int* host_flags = nullptr;               // page-locked + mapped, 2 x 32 words: band flags of the frames in flight
     cudaStream_t aux[2] = { nullptr, nullptr };       // band pipelining: two compute streams + one copy stream
     cudaStream_t copy_stream = nullptr;
     cudaStream_t copy_streams[3] = { nullptr, nullptr, nullptr };   // bvht_render_frame's band copies rotate over these (copy_stream is [0])
@@ -180,6 +194,19 @@ struct bvht_ctx {
 };
 
 constexpr uint32_t kWordBandCount = 32, kWordBandDone = 64, kWordBandFlag = 96;     // words of bvht_ctx::work_counter
+
+extern "C" { static int pump_flights(bvht_ctx* ctx); }
+
+// cudaStreamSynchronize(ctx->stream) that keeps issuing the band copies of the frames in flight while it waits: with frames in
+// flight the main stream's tail is the previous frame's trace kernel, and its bands complete while we wait for it.
+static cudaError_t sync_stream(bvht_ctx* ctx) {
+    if (ctx->flights_begun == ctx->flights_ended) return cudaStreamSynchronize(ctx->stream);
+    for (;;) {
+        cudaError_t e = cudaStreamQuery(ctx->stream);
+        if (e != cudaErrorNotReady) return e;
+        pump_flights(ctx);
+    }
+}
 
 namespace {
 
@@ -270,6 +297,32 @@ int ops_add(bvht_ctx* ctx, OpsBatch& b, cudaStream_t stream, void* dst, const vo
     return BVHT_OK;
 }
 
+// Small device->host readback that ends with the stream drained: through small_ops_kernel into a page-locked slot (the SMs write
+// it over PCIe), not through the device->host copy engine, where it would queue behind the band copies of a frame in flight
+// (big_ben_clock 8K with two frames in flight: each of the update path's three readbacks waited for a whole frame of copies).
+int d2h_small_sync(bvht_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes) {
+    if (bytes == 0) return BVHT_OK;
+    if (bytes % 4 != 0 || bytes > (256u << 10)) {
+        CU(ctx, cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, sync_stream(ctx));
+        ctx->stats.d2h_bytes += bytes;
+        return BVHT_OK;
+    }
+    bvht_ctx::Stage* stage = nullptr;
+    int rc = stage_get(ctx, bytes, &stage);
+    if (rc) return rc;
+    SmallOps ops;
+    ops.n = 1;
+    ops.op[0] = SmallOp{ stage->p, dev_src, (uint32_t)(bytes / 4), 0u };
+    CU(ctx, launch_small_ops(ops, ctx->stream));
+    ctx->stats.kernel_launches += 1;
+    CU(ctx, sync_stream(ctx));
+    stage->used = false;                                // drained: the slot may be reused without waiting
+    memcpy(host_dst, stage->p, bytes);
+    ctx->stats.d2h_bytes += bytes;
+    return BVHT_OK;
+}
+
 void free_blas(Blas& b) {
     for (DevBuf* d : { &b.tris_aos, &b.nodes, &b.tri, &b.normals, &b.tex_coords, &b.texels, &b.chunk_leaf, &b.chunk_first, &b.chunk_count,
                        &b.leaf_chunks, &b.parent, &b.scratch, &b.counters, &b.sub_nodes, &b.sub_raw, &b.sub_lohi, &b.sub_order, &b.stri,
@@ -340,8 +393,7 @@ int device_model_stats(bvht_ctx* ctx, const Blas& b, ModelStats& m) {
     CU(ctx, launch_model_stats((const float*)b.tris_aos.p, b.n_tris, d, ctx->stream));
     ctx->stats.kernel_launches += 1;
     ModelStatsDev h;
-    CU(ctx, cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = d2h_small_sync(ctx, &h, d, sizeof h))) return rc;
     m = ModelStats();
     if (h.n_good) {
         m.mean_edge = h.sum_edge / (double)h.n_good; m.mean_kappa = h.sum_kappa / (double)h.n_good;
@@ -389,8 +441,7 @@ int bake_accel(bvht_ctx* ctx, Blas& b, double d_max, double o_max) {
             CU(ctx, launch_tight_box((const float*)b.tris_aos.p, b.n_tris, (double)fs, (double)fa, d6, ctx->stream));
             ctx->stats.kernel_launches += 1;
             unsigned long long h6[6];
-            CU(ctx, cudaMemcpyAsync(h6, d6, sizeof h6, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            if ((rc = d2h_small_sync(ctx, h6, d6, sizeof h6))) return rc;
             if (h6[0] != ~0ull) for (int k = 0; k < 3; ++k) { lo[k] = dec_f64(h6[k]); hi[k] = dec_f64(h6[3 + k]); }
         }
         if (!(lo[0] <= hi[0])) {      // no host copy of the triangles: the whole-model bound
@@ -428,7 +479,7 @@ int build_accel_device(bvht_ctx* ctx, Blas& b, const LeafAccelConfig& cfg, bool&
     auto t0 = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) {
         if (!timing) return;
-        cudaStreamSynchronize(ctx->stream);
+        sync_stream(ctx);
         auto t1 = std::chrono::steady_clock::now();
         fprintf(stderr, "[bvht timing] accel %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
         t0 = t1;
@@ -493,7 +544,7 @@ int build_accel_device(bvht_ctx* ctx, Blas& b, const LeafAccelConfig& cfg, bool&
     double o_max = b.o_max > 0.0f ? (double)b.o_max : (double)cfg.o_max_radii * b.radius;
     lap("boxes + repack");
     if ((rc = bake_accel(ctx, b, d_max, o_max))) return rc;
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     lap("bake");
     done = true;
     return BVHT_OK;
@@ -534,7 +585,7 @@ int build_and_upload_accel(bvht_ctx* ctx, Blas& b) {
     double d_max = b.d_max > 0.0f ? (double)b.d_max : (double)cfg.d_max;
     double o_max = b.o_max > 0.0f ? (double)b.o_max : (double)cfg.o_max_radii * b.radius;
     if ((rc = bake_accel(ctx, b, d_max, o_max))) return rc;
-    CU(ctx, cudaStreamSynchronize(ctx->stream));     // host vectors of `acc` die here
+    CU(ctx, sync_stream(ctx));     // host vectors of `acc` die here
     return BVHT_OK;
 }
 
@@ -587,7 +638,7 @@ int refresh_blas_desc(bvht_ctx* ctx) {
     int rc = ensure(ctx, ctx->blas_desc, d.size() * sizeof(BlasDesc));
     if (rc) return rc;
     if ((rc = h2d(ctx, ctx->blas_desc.p, d.data(), d.size() * sizeof(BlasDesc)))) return rc;
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     ctx->blas_desc_dirty = false;
     return BVHT_OK;
 }
@@ -894,7 +945,7 @@ int ensure_bake_rays(bvht_ctx* ctx, const void* rays_device, uint64_t n) {
     ctx->stats.kernel_launches += 1;
     float m[2] = { 0.0f, 0.0f };
     CU(ctx, cudaMemcpyAsync(m, scratch, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     const double zero[3] = { 0.0, 0.0, 0.0 };
     double rho = std::sqrt((double)m[0]) * (1.0 + 1e-6), dw = std::sqrt((double)m[1]) * (1.0 + 1e-6);
     if (!(dw > 0.0)) return BVHT_OK;
@@ -952,7 +1003,7 @@ int make_blas(bvht_ctx* ctx, const float* tris, uint32_t n_tris, const bvht_bvh_
     auto t0 = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) {
         if (!timing) return;
-        cudaStreamSynchronize(ctx->stream);
+        sync_stream(ctx);
         auto t1 = std::chrono::steady_clock::now();
         fprintf(stderr, "[bvht timing] blas  %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
         t0 = t1;
@@ -1002,7 +1053,7 @@ int make_blas(bvht_ctx* ctx, const float* tris, uint32_t n_tris, const bvht_bvh_
     lap("leaf accelerator");
 
     cudaEventRecord(ctx->ev_f, ctx->stream);
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = sync_stream(ctx);
     if (e != cudaSuccess) { fail(ctx, BVHT_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e)); return bail(BVHT_ERR_CUDA); }
     cudaEventElapsedTime(&ctx->stats.last_upload_ms, ctx->ev_e, ctx->ev_f);
 
@@ -1044,7 +1095,7 @@ int device_build(bvht_ctx* ctx, const float* tris_host, uint32_t n_tris, std::ve
         CU(ctx, cudaMemcpyAsync(perm_out->data(), ctx->build_perm.p, (size_t)n_tris * 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
     cudaEventRecord(ctx->ev_f, ctx->stream);
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     ctx->stats.d2h_bytes += (uint64_t)n_tris * (perm_out ? 40 : 36);
     cudaEventElapsedTime(&ctx->stats.last_build_ms, ctx->ev_e, ctx->ev_f);
     ctx->stats.last_build_levels = bs.levels;
@@ -1120,6 +1171,8 @@ int bvht_create(int device, uint32_t flags, bvht_ctx** out) {
         for (int i = 0; ok && i < 3; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_copy_join[i], cudaEventDisableTiming) == cudaSuccess;
         for (int f = 0; f < 2; ++f)
             for (int i = 0; ok && i < 3; ++i) ok = cudaEventCreateWithFlags(&ctx->flight[f].done[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaHostAlloc((void**)&ctx->host_flags, 2 * 32 * sizeof(unsigned int), cudaHostAllocMapped) == cudaSuccess;
+        if (ok) memset(ctx->host_flags, 0, 2 * 32 * sizeof(unsigned int));
         for (int i = 0; ok && i < 64; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_band[i], cudaEventDisableTiming) == cudaSuccess;
         for (int i = 0; ok && i < 17; ++i) ok = cudaEventCreate(&ctx->ev_band_t[i]) == cudaSuccess;
         for (int i = 0; ok && i < 16; ++i) ok = cudaEventCreate(&ctx->ev_copy_t[i]) == cudaSuccess;
@@ -1141,6 +1194,7 @@ void bvht_destroy(bvht_ctx* ctx) {
     for (Blas& b : ctx->blas) free_blas(b);
     for (DevBuf* d : { &ctx->out_buf2, &ctx->rgba_buf2 }) release(*d);
     for (auto& f : ctx->flight) for (cudaEvent_t ev : f.done) if (ev) cudaEventDestroy(ev);
+    if (ctx->host_flags) cudaFreeHost(ctx->host_flags);
     for (DevBuf* d : { &ctx->blas_desc, &ctx->tlas, &ctx->inst_cols, &ctx->inst_blas, &ctx->work_counter, &ctx->work_list, &ctx->cover, &ctx->cover_aux, &ctx->out_buf, &ctx->rays_buf,
                        &ctx->rgba_buf, &ctx->tlas_tight, &ctx->tlas_mask, &ctx->stats_scratch, &ctx->scene_in, &ctx->scene_bounds, &ctx->build_tris, &ctx->build_perm })
         release(*d);
@@ -1164,7 +1218,7 @@ const char* bvht_last_error(const bvht_ctx* ctx) { return ctx ? ctx->err.c_str()
 int bvht_set_stream(bvht_ctx* ctx, void* cuda_stream) {
     if (!ctx) return BVHT_ERR_BAD_HANDLE;
     cudaSetDevice(ctx->device);
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return BVHT_OK;
 }
@@ -1192,7 +1246,7 @@ static int drain_flights(bvht_ctx* ctx);
 int bvht_sync(bvht_ctx* ctx) {
     if (!ctx) return BVHT_ERR_BAD_HANDLE;
     cudaSetDevice(ctx->device);
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     return drain_flights(ctx);                                   // frames begun and not ended complete here too
 }
 
@@ -1234,7 +1288,7 @@ int bvht_blas_rebuild(bvht_ctx* ctx, uint32_t blas_id) {
     b.tex_w = old.tex_w; b.tex_h = old.tex_h;
     if (!old.perm.empty()) { for (uint32_t& p : perm) p = old.perm[p]; }       // compose with the earlier permutation
     b.perm = std::move(perm);
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     free_blas(old);
     ctx->blas[blas_id] = std::move(b);
     ctx->blas_desc_dirty = true;
@@ -1267,7 +1321,7 @@ int bvht_blas_destroy(bvht_ctx* ctx, uint32_t blas_id) {
     if (!ctx) return BVHT_ERR_BAD_HANDLE;
     if (blas_id >= ctx->blas.size() || !ctx->blas[blas_id].alive) return fail(ctx, BVHT_ERR_BAD_HANDLE, "unknown blas id %u", blas_id);
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    sync_stream(ctx);
     free_blas(ctx->blas[blas_id]);
     ctx->blas_desc_dirty = true;
     return BVHT_OK;
@@ -1286,7 +1340,7 @@ int bvht_blas_set_normals(bvht_ctx* ctx, uint32_t blas_id, const float* normals,
     int rc = ensure(ctx, b.normals, padded.size() * 4);
     if (rc) return rc;
     if ((rc = h2d(ctx, b.normals.p, padded.data(), padded.size() * 4))) return rc;
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     return BVHT_OK;
 }
 
@@ -1300,7 +1354,7 @@ int bvht_blas_set_tex_coords(bvht_ctx* ctx, uint32_t blas_id, const float* tex_c
     int rc = ensure(ctx, b.tex_coords, (size_t)n_tris * 24);
     if (rc) return rc;
     if ((rc = h2d(ctx, b.tex_coords.p, tex_coords, (size_t)n_tris * 24))) return rc;
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     return BVHT_OK;
 }
 
@@ -1316,7 +1370,7 @@ int bvht_blas_set_texture(bvht_ctx* ctx, uint32_t blas_id, const uint8_t* rgb, u
     int rc = ensure(ctx, b.texels, bytes);
     if (rc) return rc;
     if ((rc = h2d(ctx, b.texels.p, rgb, bytes))) return rc;
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     b.tex_w = width; b.tex_h = height;
     return BVHT_OK;
 }
@@ -1347,7 +1401,7 @@ int bvht_blas_update_vertices(bvht_ctx* ctx, uint32_t blas_id, const float* tris
         lap("tight boxes");
     }
     cudaEventRecord(ctx->ev_f, ctx->stream);
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     lap("stream sync");
     cudaEventElapsedTime(&ctx->stats.last_upload_ms, ctx->ev_e, ctx->ev_f);
     return BVHT_OK;
@@ -1375,7 +1429,7 @@ int bvht_blas_refit(bvht_ctx* ctx, uint32_t blas_id) {
     cudaEventRecord(ctx->ev_d, ctx->stream);
     ctx->refit_timed = true;
     ctx->stats.kernel_launches += (b.n_chunks ? 2 : 1);
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     return BVHT_OK;
 }
 
@@ -1395,9 +1449,7 @@ int bvht_blas_read_nodes(bvht_ctx* ctx, uint32_t blas_id, bvht_bvh_node* out, ui
     cudaSetDevice(ctx->device);
     uint32_t n = std::min(max_nodes, b.nodes_used);
     std::vector<float> flat((size_t)n * 8);
-    CU(ctx, cudaMemcpyAsync(flat.data(), b.nodes.p, flat.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->stats.d2h_bytes += flat.size() * 4;
+    { int rc = d2h_small_sync(ctx, flat.data(), b.nodes.p, flat.size() * 4); if (rc) return rc; }
     for (uint32_t i = 0; i < n; ++i) {
         const float* f = &flat[(size_t)i * 8];
         memcpy(out[i].aabb_min, f + 0, 12); memcpy(&out[i].left_first, f + 3, 4);
@@ -1548,7 +1600,7 @@ int bvht_scene_set_transforms(bvht_ctx* ctx, const float* transforms, const uint
     char* down = st + ((up_bytes + 255) & ~size_t(255));
     CU(ctx, cudaMemcpyAsync(down, p.pack, down_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     cudaEventRecord(ctx->ev_f, ctx->stream);
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     stage->used = false;                                // drained: the slot may be reused without waiting
     ctx->stats.d2h_bytes += down_bytes;
     { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ctx->ev_e, ctx->ev_f) == cudaSuccess) ctx->stats.last_upload_ms = ms; }
@@ -1740,6 +1792,7 @@ struct BandPlan {
     uint8_t  order[32] = { 0 };
     bool     flags = false;            // raise a completion flag per band (bvht_render_frame's copies wait for them)
     uint32_t seq = 0;
+    unsigned int* flag_words = nullptr; // where the flags live when not in the work counters (frames in flight: host-visible memory)
     const int4* rects = nullptr;       // the instances' screen rectangles, when the caller has computed them already
     uint32_t n_rects = 0;
     bool     have_rects = false;
@@ -1813,7 +1866,7 @@ static int launch_primary_region(bvht_ctx* ctx, const SceneDev& scene, const bvh
         memcpy(p.band_order, bp.order, 32);
         p.band_count = (unsigned int*)ctx->work_counter.p + kWordBandCount;
         p.band_done = bp.flags ? (unsigned int*)ctx->work_counter.p + kWordBandDone : nullptr;
-        p.band_flag = (unsigned int*)ctx->work_counter.p + kWordBandFlag;
+        p.band_flag = bp.flag_words ? bp.flag_words : (unsigned int*)ctx->work_counter.p + kWordBandFlag;
         p.band_seq = bp.seq;
     }
     p.n_origin = 0;
@@ -2048,35 +2101,90 @@ static StreamWaitValue32Fn stream_wait_value32() {
     return fn;
 }
 
-// Wait for the oldest frame in flight: its pixels are in the caller's host buffers when this returns.
-static int end_oldest_flight(bvht_ctx* ctx) {
-    bvht_ctx::Flight& f = ctx->flight[ctx->flights_ended & 1u];
-    if (!f.active) return fail(ctx, BVHT_ERR_NOT_READY, "no frame in flight");
-    f.active = false;
-    ++ctx->flights_ended;
-    // a bounded wait: a copy that never gets its flag must surface as an error with the evidence, not as a hang
-    const auto t0 = std::chrono::steady_clock::now();
-    for (int c = 0; c < f.n_cs; ++c) {
-        for (;;) {
-            cudaError_t e = cudaEventQuery(f.done[c]);
-            if (e == cudaSuccess) break;
-            if (e != cudaErrorNotReady) return fail(ctx, BVHT_ERR_CUDA, "frame in flight failed: %s", cudaGetErrorString(e));
-            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 20.0) {
-                unsigned int w[128] = { 0 };
-                cudaStream_t dbg = nullptr;
-                cudaStreamCreateWithFlags(&dbg, cudaStreamNonBlocking);
-                cudaMemcpyAsync(w, ctx->work_counter.p, sizeof w, cudaMemcpyDeviceToHost, dbg);
-                cudaStreamSynchronize(dbg);
-                cudaStreamDestroy(dbg);
-                std::string flags, done;
-                for (int k = 0; k < 16; ++k) { flags += std::to_string(w[kWordBandFlag + k]) + " "; done += std::to_string(w[kWordBandDone + k]) + " "; }
-                return fail(ctx, BVHT_ERR_CUDA, "frame in flight did not complete within 20 s (copy stream %d; frame sequence now %u; cursor %u; "
-                            "main stream %s; band flags %s; blocks done per band %s)", c, ctx->frame_seq, w[0],
-                            cudaStreamQuery(ctx->stream) == cudaSuccess ? "idle" : "busy", flags.c_str(), done.c_str());
+// D2H of the own tile rows [k0, k1) (own-row indices: global tile rows first_row + j * shard_n) of a frame's outputs.
+static int copy_own_rows(bvht_ctx* ctx, const bvht_ctx::CopyJob& j, uint32_t k0, uint32_t k1, cudaStream_t cs) {
+    int rc;
+    for (int which = 0; which < 2; ++which) {
+        void* host = which == 0 ? j.host_frame : j.host_hits;
+        const void* dev = which == 0 ? j.d_rgba : j.d_hits;
+        const size_t elem = which == 0 ? 4 : sizeof(bvht_hit);
+        if (!host) continue;
+        if (j.shard_n == 1) {
+            bvht_rect rr = { j.region.x0, std::max(j.region.y0, (j.first_row + k0) * j.tile), j.region.x1, std::min(j.region.y1, (j.first_row + k1) * j.tile) };
+            if (rr.y0 < rr.y1 && (rc = copy_rows_d2h(ctx, host, dev, j.width, rr, elem, cs))) return rc;
+            continue;
+        }
+        // sharded: only this rank's tile rows travel, and only they are written on the host (another rank fills the others,
+        // e.g. through a shared pinned mapping): `tile` image rows every shard_n * tile rows -- one strided 2-D copy when the
+        // rows are whole and full width, one copy per tile row otherwise
+        const uint32_t g0 = j.first_row + k0 * j.shard_n, g_last = j.first_row + (k1 - 1) * j.shard_n;
+        const bool whole = j.region.x0 == 0 && j.region.x1 == j.width && g0 * j.tile >= j.region.y0 && (uint64_t)(g_last + 1) * j.tile <= j.region.y1;
+        if (whole) {
+            const size_t chunk = (size_t)j.tile * j.width * elem, pitch = chunk * j.shard_n, off = (size_t)g0 * j.tile * j.width * elem;
+            CU(ctx, cudaMemcpy2DAsync((char*)host + off, pitch, (const char*)dev + off, pitch, chunk, k1 - k0, cudaMemcpyDeviceToHost, cs));
+            ctx->stats.d2h_bytes += chunk * (k1 - k0);
+        } else {
+            for (uint32_t r = k0; r < k1; ++r) {
+                const uint32_t g = j.first_row + r * j.shard_n;
+                bvht_rect rr = { j.region.x0, std::max(j.region.y0, g * j.tile), j.region.x1, std::min(j.region.y1, (g + 1) * j.tile) };
+                if (rr.y0 < rr.y1 && (rc = copy_rows_d2h(ctx, host, dev, j.width, rr, elem, cs))) return rc;
             }
         }
     }
     return BVHT_OK;
+}
+
+// Frames in flight: issue the band copies whose flags have come up (oldest frame first).  The flags live in page-locked
+// host memory; K1 raises them with a system-scope fence behind the band's pixels.  No stream memory operation is involved (the
+// waits of two frames queued on one stream wedged the copy streams, profiles/r02_frames_in_flight.txt), and a copy reaches the
+// copy engine only when it can run, so the next frame's own readbacks are not queued behind a whole frame of copies.
+static int pump_flights(bvht_ctx* ctx) {
+    for (uint64_t id = ctx->flights_ended; id < ctx->flights_begun; ++id) {
+        bvht_ctx::Flight& f = ctx->flight[id & 1u];
+        if (!f.active || f.closed) continue;
+        const volatile unsigned int* hf = ctx->host_flags + 32u * (uint32_t)(id & 1u);
+        while (f.next < f.n_bands) {
+            const uint32_t k = f.order[f.next];
+            if (f.flags && (int32_t)(hf[k] - f.seq) < 0) break;
+            int rc = copy_own_rows(ctx, f.job, k * f.band_rows, std::min(f.job.own_rows, (k + 1) * f.band_rows),
+                                   ctx->copy_streams[f.next % (uint32_t)f.n_cs]);
+            if (rc) return rc;
+            ++f.next;
+        }
+        if (f.next < f.n_bands) break;                 // a younger frame's bands cannot be ready before this one's
+        for (int c = 0; c < f.n_cs; ++c) CU(ctx, cudaEventRecord(f.done[c], ctx->copy_streams[c]));
+        f.closed = true;
+    }
+    return BVHT_OK;
+}
+
+// Wait for the oldest frame in flight: its pixels are in the caller's host buffers when this returns.
+static int end_oldest_flight(bvht_ctx* ctx) {
+    const uint32_t parity = (uint32_t)(ctx->flights_ended & 1u);
+    bvht_ctx::Flight& f = ctx->flight[parity];
+    if (!f.active) return fail(ctx, BVHT_ERR_NOT_READY, "no frame in flight");
+    // a bounded wait: a frame that never completes must surface as an error with the evidence, not as a hang
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = BVHT_OK;
+    for (;;) {
+        if ((rc = pump_flights(ctx))) break;
+        if (f.closed) {
+            cudaError_t e = cudaSuccess;
+            for (int c = 0; c < f.n_cs && e == cudaSuccess; ++c) e = cudaEventQuery(f.done[c]);
+            if (e == cudaSuccess) break;
+            if (e != cudaErrorNotReady) { rc = fail(ctx, BVHT_ERR_CUDA, "frame in flight failed: %s", cudaGetErrorString(e)); break; }
+        }
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 20.0) {
+            std::string flags;
+            for (uint32_t k = 0; k < f.n_bands; ++k) flags += std::to_string(ctx->host_flags[32u * parity + k]) + " ";
+            rc = fail(ctx, BVHT_ERR_CUDA, "frame in flight did not complete within 20 s (bands issued %u of %u; frame sequence %u; band flags %s; "
+                      "main stream %s)", f.next, f.n_bands, f.seq, flags.c_str(), cudaStreamQuery(ctx->stream) == cudaSuccess ? "idle" : "busy");
+            break;
+        }
+    }
+    f.active = false;
+    ++ctx->flights_ended;
+    return rc;
 }
 
 static int drain_flights(bvht_ctx* ctx) {
@@ -2106,7 +2214,11 @@ static int render_frame_host(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
     DevBuf& hits_stage = parity ? ctx->out_buf2 : ctx->out_buf;
     // a begun frame with nothing to do still pairs with one bvht_render_frame_end
     auto nothing_to_do = [&]() -> int {
-        if (in_flight) { bvht_ctx::Flight& f = ctx->flight[parity]; f.n_cs = 0; f.active = true; ++ctx->flights_begun; }
+        if (in_flight) {
+            bvht_ctx::Flight& f = ctx->flight[parity];
+            f.n_cs = 1; f.n_bands = 0; f.next = 0; f.flags = false; f.closed = false; f.active = true;
+            ++ctx->flights_begun;
+        }
         return BVHT_OK;
     };
     if ((rc = ensure_bake(ctx, camera))) return rc;
@@ -2143,19 +2255,16 @@ static int render_frame_host(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
     plan.n_bands = own_bytes < (512u << 10) ? 1u : own_bytes < (2u << 20) ? 2u
                  : (uint32_t)std::min<uint64_t>(std::max<uint64_t>(own_bytes / (2560u << 10), 4), 16);
     if (ctx->knobs.bands > 0) plan.n_bands = (uint32_t)ctx->knobs.bands;
-    // a frame in flight is copied once its kernels are done: the copy runs under the NEXT frame's kernels anyway, and nothing of
-    // it depends on stream memory operations.  (Per-band flags as in the synchronous frame were faster here too -- C3 4K 0.93 vs
-    // 0.97 ms, C5 8K 2.74 vs 4.2 ms, because copies gated one by one leave the copy engine's queue open to the next frame's
-    // readbacks -- but with the waits of two frames queued on a stream the copy streams wedged now and then: trippy_teapots 4K,
-    // every flag raised, main stream idle, copy never issued, 6 runs of 10; profiles/r02_frames_in_flight.txt.)
-    const uint32_t copy_pieces = std::max(1u, std::min(plan.n_bands, own_rows));
-    if (in_flight) plan.n_bands = 1;
     plan.n_bands = std::max(1u, std::min(plan.n_bands, own_rows));
     plan.band_rows = (own_rows + plan.n_bands - 1) / plan.n_bands;
     plan.n_bands = (own_rows + plan.band_rows - 1) / plan.band_rows;
     const StreamWaitValue32Fn wait_value = stream_wait_value32();
-    plan.flags = wait_value != nullptr && plan.n_bands > 1;
+    // the synchronous frame's copies wait for the band flags ON THE DEVICE (cuStreamWaitValue32); a frame in flight has them raised
+    // in host-visible memory and the host issues each copy when its flag is up (pump_flights)
+    plan.flags = (in_flight || wait_value != nullptr) && plan.n_bands > 1;
+    if (in_flight) plan.flag_words = ctx->host_flags + 32u * parity;     // page-locked + mapped: the same address on the device
     plan.seq = ++ctx->frame_seq;
+    if (in_flight && (rc = pump_flights(ctx))) return rc;                 // what the previous frame has ready goes out first
     int4 rects[32];
     order_bands(ctx, camera, width, height, tile, first_row, own_rows, plan, rects);
     { OpsBatch z; if ((rc = ops_add(ctx, z, ctx->stream, ctx->work_counter.p, nullptr, kWordBandFlag * 4, 0u)) || (rc = ops_flush(ctx, z, ctx->stream))) return rc; }
@@ -2171,65 +2280,32 @@ static int render_frame_host(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
     if (!plan.flags) for (int c = 0; c < 3; ++c) CU(ctx, cudaStreamWaitEvent(ctx->copy_streams[c], ctx->ev_fork, 0));      // no flags: copy after the kernels
     const unsigned long long flag_base = (unsigned long long)((unsigned int*)ctx->work_counter.p + kWordBandFlag);
     const int n_cs = std::max(1, std::min(ctx->n_copy_streams, 3));
-    auto copy_own_rows = [&](uint32_t k0, uint32_t k1, cudaStream_t cs) -> int {
-        // own-row indices [k0, k1) = global tile rows first_row + j * shard_n
-        for (int which = 0; which < 2; ++which) {
-            void* host = which == 0 ? (void*)frame_out_host : (void*)hits_out_host;
-            const void* dev = which == 0 ? d_rgba : d_hits;
-            const size_t elem = which == 0 ? 4 : sizeof(bvht_hit);
-            if (!host) continue;
-            if (shard_n == 1) {
-                bvht_rect rr = { region.x0, std::max(region.y0, (first_row + k0) * tile), region.x1, std::min(region.y1, (first_row + k1) * tile) };
-                if (rr.y0 < rr.y1 && (rc = copy_rows_d2h(ctx, host, dev, width, rr, elem, cs))) return rc;
-                continue;
-            }
-            // sharded: only this rank's tile rows travel, and only they are written on the host (another rank fills the others,
-            // e.g. through a shared pinned mapping): `tile` image rows every shard_n * tile rows -- one strided 2-D copy when the
-            // rows are whole and full width, one copy per tile row otherwise
-            const uint32_t g0 = first_row + k0 * shard_n, g_last = first_row + (k1 - 1) * shard_n;
-            const bool whole = region.x0 == 0 && region.x1 == width && g0 * tile >= region.y0 && (uint64_t)(g_last + 1) * tile <= region.y1;
-            if (whole) {
-                const size_t chunk = (size_t)tile * width * elem, pitch = chunk * shard_n, off = (size_t)g0 * tile * width * elem;
-                CU(ctx, cudaMemcpy2DAsync((char*)host + off, pitch, (const char*)dev + off, pitch, chunk, k1 - k0, cudaMemcpyDeviceToHost, cs));
-                ctx->stats.d2h_bytes += chunk * (k1 - k0);
-            } else {
-                for (uint32_t j = k0; j < k1; ++j) {
-                    const uint32_t g = first_row + j * shard_n;
-                    bvht_rect rr = { region.x0, std::max(region.y0, g * tile), region.x1, std::min(region.y1, (g + 1) * tile) };
-                    if (rr.y0 < rr.y1 && (rc = copy_rows_d2h(ctx, host, dev, width, rr, elem, cs))) return rc;
-                }
-            }
-        }
-        return BVHT_OK;
-    };
+    bvht_ctx::CopyJob job;
+    job.host_frame = frame_out_host; job.host_hits = hits_out_host; job.d_rgba = d_rgba; job.d_hits = d_hits;
+    job.width = width; job.tile = tile; job.first_row = first_row; job.own_rows = own_rows; job.shard_n = shard_n; job.region = region;
     auto copy_band = [&](uint32_t k, cudaStream_t cs) -> int {
-        return copy_own_rows(k * plan.band_rows, std::min(own_rows, (k + 1) * plan.band_rows), cs);
+        return copy_own_rows(ctx, job, k * plan.band_rows, std::min(own_rows, (k + 1) * plan.band_rows), cs);
     };
     // belt and braces: once the kernels are done every flag is raised from the stream itself, so a copy can never wait forever
     auto raise_all_flags = [&]() -> int {
         OpsBatch f;
-        int rc2 = ops_add(ctx, f, ctx->stream, (unsigned int*)ctx->work_counter.p + kWordBandFlag, nullptr, 32 * 4, plan.seq);
+        unsigned int* words = plan.flag_words ? plan.flag_words : (unsigned int*)ctx->work_counter.p + kWordBandFlag;
+        int rc2 = ops_add(ctx, f, ctx->stream, words, nullptr, 32 * 4, plan.seq);
         return rc2 ? rc2 : ops_flush(ctx, f, ctx->stream);
     };
     if (in_flight) {
-        // in pieces of the band size all the same: whatever else needs the link or a copy engine meanwhile (the next frame's
-        // uploads) gets in between two pieces instead of waiting for the whole frame (big_ben_clock 8K: 133 MB = 2.4 ms)
-        const uint32_t piece_rows = (own_rows + copy_pieces - 1) / copy_pieces;
-        for (uint32_t k0 = 0; k0 < own_rows; k0 += piece_rows)
-            if ((rc = copy_own_rows(k0, std::min(own_rows, k0 + piece_rows), ctx->copy_streams[0]))) {
-                cudaStreamSynchronize(ctx->stream);
-                cudaStreamSynchronize(ctx->copy_streams[0]);
-                cudaGetLastError();
-                return rc;
-            }
-        // nothing joins the main stream: the next frame's kernels start behind this frame's kernels, not behind its copy
+        // nothing joins the main stream: the next frame's kernels start behind this frame's kernels, not behind its copies
+        if (plan.flags && (rc = raise_all_flags())) { sync_stream(ctx); cudaGetLastError(); return rc; }
         bvht_ctx::Flight& f = ctx->flight[parity];
-        CU(ctx, cudaEventRecord(f.done[0], ctx->copy_streams[0]));
-        f.n_cs = 1; f.active = true;
+        f.job = job;
+        f.n_bands = plan.n_bands; f.band_rows = plan.band_rows; f.next = 0; f.seq = plan.seq; f.flags = plan.flags;
+        memcpy(f.order, plan.order, sizeof f.order);
+        f.closed = false;
+        f.n_cs = n_cs; f.active = true;
         ++ctx->flights_begun;
         cudaEventRecord(ctx->ev_b, ctx->stream);                // last_trace_ms = the frame's kernels
         ctx->trace_timed = true;
-        return BVHT_OK;
+        return pump_flights(ctx);                                // one band only: its copy is queued behind ev_fork right here
     }
     for (uint32_t i = 0; i < plan.n_bands; ++i) {
         const uint32_t k = plan.order[i];
@@ -2241,7 +2317,7 @@ static int render_frame_host(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
         if (rc) {
             // what is already queued must not outlive this call: let the kernels finish, then release the waiting copies
             if (plan.flags) raise_all_flags();
-            cudaStreamSynchronize(ctx->stream);
+            sync_stream(ctx);
             for (int c = 0; c < 3; ++c) cudaStreamSynchronize(ctx->copy_streams[c]);
             cudaGetLastError();
             return rc;
@@ -2255,7 +2331,7 @@ static int render_frame_host(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
     }
     cudaEventRecord(ctx->ev_b, ctx->stream);
     ctx->trace_timed = true;
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     ctx->tl_bands = std::min(plan.n_bands, 16u); ctx->tl_valid = true;
     for (uint32_t i = 0; i < ctx->tl_bands; ++i) ctx->tl_rows[i] = std::min(own_rows, (plan.order[i] + 1u) * plan.band_rows) - plan.order[i] * plan.band_rows;
     return BVHT_OK;
@@ -2323,7 +2399,7 @@ int bvht_trace_rays(bvht_ctx* ctx, const bvht_ray* rays, uint64_t n, bvht_hit* o
     if ((rc = bvht_trace_rays_device(ctx, ctx->rays_buf.p, n, ctx->out_buf.p))) return rc;
     CU(ctx, cudaMemcpyAsync(out_host, ctx->out_buf.p, n * sizeof(bvht_hit), cudaMemcpyDeviceToHost, ctx->stream));
     ctx->stats.d2h_bytes += n * sizeof(bvht_hit);
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     return BVHT_OK;
 }
 
@@ -2338,7 +2414,7 @@ int bvht_device_alloc(bvht_ctx* ctx, size_t bytes, void** out_device) {
 int bvht_device_free(bvht_ctx* ctx, void* device_ptr) {
     if (!ctx) return BVHT_ERR_BAD_HANDLE;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    sync_stream(ctx);
     CU(ctx, cudaFree(device_ptr));
     return BVHT_OK;
 }
@@ -2353,7 +2429,7 @@ int bvht_host_alloc(bvht_ctx* ctx, size_t bytes, void** out_host) {
 }
 
 int bvht_host_free(bvht_ctx* ctx, void* host_ptr) {
-    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    if (ctx) { cudaSetDevice(ctx->device); sync_stream(ctx); }
     cudaError_t e = cudaFreeHost(host_ptr);
     if (e != cudaSuccess) { cudaGetLastError(); return ctx ? fail(ctx, BVHT_ERR_CUDA, "cudaFreeHost: %s", cudaGetErrorString(e)) : BVHT_ERR_CUDA; }
     return BVHT_OK;
@@ -2368,7 +2444,7 @@ int bvht_host_register(bvht_ctx* ctx, void* host_ptr, size_t bytes) {
 }
 
 int bvht_host_unregister(bvht_ctx* ctx, void* host_ptr) {
-    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    if (ctx) { cudaSetDevice(ctx->device); sync_stream(ctx); }
     cudaError_t e = cudaHostUnregister(host_ptr);
     if (e != cudaSuccess) { cudaGetLastError(); return ctx ? fail(ctx, BVHT_ERR_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(e)) : BVHT_ERR_CUDA; }
     return BVHT_OK;
@@ -2379,7 +2455,7 @@ int bvht_memcpy_h2d(bvht_ctx* ctx, void* dst_device, const void* src_host, size_
     cudaSetDevice(ctx->device);
     int rc = h2d(ctx, dst_device, src_host, bytes);
     if (rc) return rc;
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     return BVHT_OK;
 }
 
@@ -2387,7 +2463,7 @@ int bvht_memcpy_d2h(bvht_ctx* ctx, void* dst_host, const void* src_device, size_
     if (!ctx) return BVHT_ERR_BAD_HANDLE;
     cudaSetDevice(ctx->device);
     CU(ctx, cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     ctx->stats.d2h_bytes += bytes;
     return BVHT_OK;
 }
@@ -2414,7 +2490,7 @@ int bvht_ipc_open(bvht_ctx* ctx, const uint8_t handle[64], void** out_device) {
 int bvht_ipc_close(bvht_ctx* ctx, void* device_ptr) {
     if (!ctx) return BVHT_ERR_BAD_HANDLE;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    sync_stream(ctx);
     CU(ctx, cudaIpcCloseMemHandle(device_ptr));
     return BVHT_OK;
 }
@@ -2433,7 +2509,7 @@ int bvht_debug_read_bandwidth(bvht_ctx* ctx, size_t bytes, uint32_t passes, doub
     cudaEventRecord(ctx->ev_e, ctx->stream);
     if (e == cudaSuccess) e = launch_read_bw(buf, bytes, passes, grid, sink, ctx->stream);
     cudaEventRecord(ctx->ev_f, ctx->stream);
-    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaError_t e2 = sync_stream(ctx);
     float ms = 0.0f; cudaEventElapsedTime(&ms, ctx->ev_e, ctx->ev_f);
     cudaFree(buf); cudaFree(sink);
     ctx->stats.kernel_launches += 2;
@@ -2466,7 +2542,7 @@ int bvht_debug_trace_stats(bvht_ctx* ctx, const bvht_camera* camera, uint32_t wi
     ctx->cover_ready = false;
     cudaError_t e = cudaSuccess;
     if (!rc) e = cudaMemcpyAsync(counters_out, cnt.p, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
-    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaError_t e2 = sync_stream(ctx);
     release(cnt);
     if (rc) return rc;
     if (e != cudaSuccess || e2 != cudaSuccess) return fail(ctx, BVHT_ERR_CUDA, "debug stats launch failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
