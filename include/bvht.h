@@ -271,9 +271,10 @@ BVHT_API int         bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera,
 /* The same frame with up to TWO frames in flight (no reference counterpart: the reference's Renderer::render returns with the
  * frame, renderer.rs:394-399; an application that presents frame n while frame n+1 is traced calls these instead).
  * bvht_render_frame_begin queues the frame and returns; bvht_render_frame_end waits for the OLDEST begun frame, whose host
- * buffers (page-locked, and not to be touched in between) are then filled.  The device->host copy of frame n runs under the
- * kernels of frame n+1: two device staging frames alternate, the copy sits on its own stream behind the frame's last kernel
- * (one piece, no bands: it is hidden anyway), and nothing makes the next frame's kernels wait for it.  Scene updates between
+ * buffers (page-locked, and not to be touched in between) are then filled.  The device->host copies of frame n run under the
+ * kernels of frame n+1: two device staging frames alternate, each band's copy is issued by the host when the band's flag comes
+ * up in page-locked memory (from _begin, _end and every wait the library does in between: call one of them to keep copies
+ * moving), and nothing makes the next frame's kernels wait for them.  Scene updates between
  * two begins (bvht_tlas_set, bvht_scene_set_transforms, bvht_blas_update_vertices / _refit) are ordered behind the kernels of
  * the frame already begun.  A third begin without an end is BVHT_ERR_NOT_READY, as is an end with nothing in flight;
  * bvht_render_frame and bvht_sync complete whatever is in flight first.  Results are those of bvht_render_frame, bit for bit. */
