@@ -40,7 +40,7 @@ class ShadeParams(C.Structure):
                 ("hit_rgba", C.c_uint8 * 4), ("miss_rgba", C.c_uint8 * 4), ("object0_transform", C.c_float * 16)]
 
 
-OPT_COVER, OPT_K0, OPT_BANDS, OPT_BAND_ORDER, OPT_COPY_STREAMS = 1, 2, 3, 4, 5
+OPT_COVER, OPT_K0, OPT_BANDS, OPT_BAND_ORDER, OPT_COPY_STREAMS, OPT_TIMELINE = 1, 2, 3, 4, 5, 6
 
 SHADE_NONE, SHADE_DEPTH, SHADE_INTERSECTION, SHADE_UV, SHADE_NORMAL, SHADE_TEXTURE = 0, 1, 2, 3, 4, 5
 

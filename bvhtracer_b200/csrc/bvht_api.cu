@@ -86,6 +86,7 @@ struct Knobs {
     int   k0 = -1;                     // K0 (classify + fill): -1 = by rule, 0 / 1 = forced
     bool  no_d2h = false;              // timing experiment: bands without their copies
     int   bands = 0;                   // > 0: number of bands of bvht_render_frame
+    bool  timeline = false;            // record the per-band events bvht_debug_frame_timeline reports (BVHT_OPT_TIMELINE)
     int   band_order = -1;             // pull order of the bands: -1 = the library's rule, 0 image order, 1 cheapest first,
                                        //   2 cheap bands (ascending), then the expensive ones (descending), 3 descending cost
 };
@@ -163,9 +164,10 @@ struct bvht_ctx {
         bool active = false; int n_cs = 0; cudaEvent_t done[3] = { nullptr, nullptr, nullptr };
         // the frame's band copies are issued BY THE HOST as the bands' flags come up in host-visible memory (pump_flights)
         CopyJob job;
-        uint32_t n_bands = 0, band_rows = 0, next = 0, seq = 0;       // next = bands issued so far, in pull order
+        uint32_t n_bands = 0, band_rows = 0, next = 0, seq = 0, issued = 0;   // next = number of bands issued, issued = which (bit i = i-th in pull order)
         uint8_t order[32] = { 0 };
-        bool flags = false, closed = false;                            // closed = every copy issued, done[0] recorded
+        bool flags = false, closed = false;                            // closed = every copy issued, done[] recorded
+        bool timeline = false;                                         // bvht_render_frame: keep the per-band events of bvht_debug_frame_timeline
     } flight[2];
     uint64_t flights_begun = 0, flights_ended = 0;
     unsigned int* host_flags = nullptr;               // page-locked + mapped, 2 x 32 words: band flags of the frames in flight
@@ -1234,6 +1236,7 @@ int bvht_set_option(bvht_ctx* ctx, uint32_t option, int32_t value) {
         case BVHT_OPT_BAND_ORDER:
             if (value > 3) return fail(ctx, BVHT_ERR_INVALID_ARG, "unknown band order %d", (int)value);
             ctx->knobs.band_order = value < 0 ? -1 : value; return BVHT_OK;
+        case BVHT_OPT_TIMELINE: ctx->knobs.timeline = value > 0; return BVHT_OK;
         case BVHT_OPT_BANDS:
             if (value > kMaxBands) return fail(ctx, BVHT_ERR_INVALID_ARG, "at most %d bands (%d asked)", kMaxBands, (int)value);
             ctx->knobs.bands = value < 0 ? 0 : value; return BVHT_OK;
@@ -2086,21 +2089,6 @@ static int copy_rows_d2h(bvht_ctx* ctx, void* host, const void* dev, uint32_t wi
     return BVHT_OK;
 }
 
-// cuStreamWaitValue32 through the runtime's driver entry point lookup (no link-time dependency on libcuda)
-typedef int (*StreamWaitValue32Fn)(cudaStream_t, unsigned long long /*CUdeviceptr*/, unsigned int, unsigned int);
-static StreamWaitValue32Fn stream_wait_value32() {
-    static StreamWaitValue32Fn fn = []() -> StreamWaitValue32Fn {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
-            cudaGetLastError();
-            return nullptr;
-        }
-        return (StreamWaitValue32Fn)p;
-    }();
-    return fn;
-}
-
 // D2H of the own tile rows [k0, k1) (own-row indices: global tile rows first_row + j * shard_n) of a frame's outputs.
 static int copy_own_rows(bvht_ctx* ctx, const bvht_ctx::CopyJob& j, uint32_t k0, uint32_t k1, cudaStream_t cs) {
     int rc;
@@ -2143,12 +2131,20 @@ static int pump_flights(bvht_ctx* ctx) {
         bvht_ctx::Flight& f = ctx->flight[id & 1u];
         if (!f.active || f.closed) continue;
         const volatile unsigned int* hf = ctx->host_flags + 32u * (uint32_t)(id & 1u);
-        while (f.next < f.n_bands) {
-            const uint32_t k = f.order[f.next];
-            if (f.flags && (int32_t)(hf[k] - f.seq) < 0) break;
+        // every band whose flag is up, in pull order but not held up by a band that is late (a heavy pixel block keeps one band
+        // open while the following ones complete: big_ben_clock 8K, +0.4 ms on such frames when issued strictly in order)
+        for (uint32_t i = 0; i < f.n_bands; ++i) {
+            if (f.issued & (1u << i)) continue;
+            const uint32_t k = f.order[i];
+            if (f.flags && (int32_t)(hf[k] - f.seq) < 0) continue;
             int rc = copy_own_rows(ctx, f.job, k * f.band_rows, std::min(f.job.own_rows, (k + 1) * f.band_rows),
                                    ctx->copy_streams[f.next % (uint32_t)f.n_cs]);
             if (rc) return rc;
+            if (f.timeline && f.next < 16) {
+                cudaEventRecord(ctx->ev_copy_t[f.next], ctx->copy_streams[f.next % (uint32_t)f.n_cs]);
+                ctx->tl_rows[f.next] = std::min(f.job.own_rows, (k + 1) * f.band_rows) - k * f.band_rows;
+            }
+            f.issued |= 1u << i;
             ++f.next;
         }
         if (f.next < f.n_bands) break;                 // a younger frame's bands cannot be ready before this one's
@@ -2193,12 +2189,22 @@ static int drain_flights(bvht_ctx* ctx) {
     return rc;
 }
 
-// bvht_render_frame (in_flight = false: returns with the frame in host memory) and bvht_render_frame_begin (in_flight = true:
-// returns with everything queued; the device->host copies of this frame then overlap the NEXT frame's kernels, which write the
-// other of two device staging frames).
+// Queue one frame whose outputs go to host memory: bvht_render_frame_begin, and the first half of bvht_render_frame
+// (`timeline`: keep the per-band events bvht_debug_frame_timeline reports).
+//
+// ONE persistent launch traces the whole region; its device->host copies are pipelined against it band by band.  K1 pulls the
+// pixel blocks band by band and, when a band's last block is done, raises the band's flag in page-locked HOST memory (a
+// system-scope fence behind the band's pixels); the host issues the band's copy when it sees the flag (pump_flights) -- no
+// kernel boundary between bands (round 1 launched one kernel per band: every boundary cost ~35 us of ramp-down / ramp-up and
+// host launch work, 0.23 ms of a 1.07 ms frame at 7 bands, profiles/r02_e2e_timeline_before.txt) and no stream memory
+// operation (until late in round 2 the flags lived in device memory and the copies sat behind cuStreamWaitValue32: 3-4 % slower
+// on every workload than the host issuing them, and with the waits of two frames queued the copy streams wedged,
+// profiles/r02_frames_in_flight.txt).  What stays exposed is the copy of the LAST band, so bands are thin (about 2.5 MB of
+// output each, at most 32) and pulled cheapest first: the frame ends with its most expensive rows, behind which the earlier
+// copies have long finished.  The cost of a band is estimated from the instances' screen rectangles.
 static int render_frame_host(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height, uint32_t tile,
                              bvht_rect region, const bvht_shade_params* shade, uint32_t* frame_out_host, bvht_hit* hits_out_host,
-                             bool in_flight) {
+                             bool timeline) {
     if (!ctx) return BVHT_ERR_BAD_HANDLE;
     if (!frame_out_host && !hits_out_host) return fail(ctx, BVHT_ERR_INVALID_ARG, "no output buffer");
     if (frame_out_host && (!shade || shade->kind == BVHT_SHADE_NONE || shade->kind > BVHT_SHADE_TEXTURE))
@@ -2206,19 +2212,16 @@ static int render_frame_host(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
     int rc = check_frame_args(ctx, camera, width, height, tile, region);
     if (rc) return rc;
     cudaSetDevice(ctx->device);
-    if (!in_flight) { if ((rc = drain_flights(ctx))) return rc; }
-    else if (ctx->flights_begun - ctx->flights_ended >= 2)
+    if (ctx->flights_begun - ctx->flights_ended >= 2)
         return fail(ctx, BVHT_ERR_NOT_READY, "two frames are in flight already: bvht_render_frame_end first");
-    const uint32_t parity = in_flight ? (uint32_t)(ctx->flights_begun & 1u) : 0u;
+    const uint32_t parity = (uint32_t)(ctx->flights_begun & 1u);
     DevBuf& rgba_stage = parity ? ctx->rgba_buf2 : ctx->rgba_buf;
     DevBuf& hits_stage = parity ? ctx->out_buf2 : ctx->out_buf;
+    bvht_ctx::Flight& f = ctx->flight[parity];
     // a begun frame with nothing to do still pairs with one bvht_render_frame_end
     auto nothing_to_do = [&]() -> int {
-        if (in_flight) {
-            bvht_ctx::Flight& f = ctx->flight[parity];
-            f.n_cs = 1; f.n_bands = 0; f.next = 0; f.flags = false; f.closed = false; f.active = true;
-            ++ctx->flights_begun;
-        }
+        f.n_cs = 1; f.n_bands = 0; f.next = 0; f.issued = 0; f.flags = false; f.closed = false; f.timeline = false; f.active = true;
+        ++ctx->flights_begun;
         return BVHT_OK;
     };
     if ((rc = ensure_bake(ctx, camera))) return rc;
@@ -2233,13 +2236,6 @@ static int render_frame_host(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
     void* d_rgba = frame_out_host ? rgba_stage.p : nullptr;
     void* d_hits = hits_out_host ? hits_stage.p : nullptr;
 
-    // ONE persistent launch traces the whole region; its device->host copies are pipelined against it band by band.  K1 pulls
-    // the pixel blocks band by band and raises a flag in device memory when a band's last block is done; the band's copy sits
-    // on the copy stream behind a cuStreamWaitValue32 on that flag -- no host round trip, no kernel boundary between bands
-    // (round 1 launched one kernel per band: every boundary cost ~35 us of ramp-down / ramp-up and host launch work, 0.23 ms of a
-    // 1.07 ms frame at 7 bands, profiles/r02_e2e_timeline_before.txt).  What stays exposed is the copy of the LAST band, so bands
-    // are thin (about 1.5 MB of output each, at most 32) and pulled cheapest first: the frame ends with its most expensive rows,
-    // behind which the earlier copies have long finished.  The cost of a band is estimated from the instances' screen rectangles.
     const uint32_t shard_n = ctx->shard_count, shard_i = ctx->shard_index;
     uint32_t first_row = region.y0 / tile, own_rows = (region.y1 + tile - 1) / tile - first_row;
     if (shard_n > 1) bvht_shard_tile_rows(region, tile, shard_i, shard_n, &first_row, &own_rows);
@@ -2251,20 +2247,17 @@ static int render_frame_host(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
     BandPlan plan;
     // band size: a copy of ~2.5 MB runs at ~48 of the link's ~55 GB/s and leaves a 50 us tail (B200, PCIe 5 x16; swept 1-32 bands
     // on the 33 MB frame of sixteen_armadillos and the 8 MB one of two_armadillos, profiles/r02_e2e_timeline.txt); frames beyond
-    // 40 MB are copy-bound whatever the bands (big_ben_clock 8K: 133 MB = 2.4 ms of link time against 1.1 ms of tracing)
+    // 40 MB are copy-bound whatever the bands (big_ben_clock 8K: 133 MB = 2.4 ms of link time against 1.6 ms of tracing)
     plan.n_bands = own_bytes < (512u << 10) ? 1u : own_bytes < (2u << 20) ? 2u
                  : (uint32_t)std::min<uint64_t>(std::max<uint64_t>(own_bytes / (2560u << 10), 4), 16);
     if (ctx->knobs.bands > 0) plan.n_bands = (uint32_t)ctx->knobs.bands;
     plan.n_bands = std::max(1u, std::min(plan.n_bands, own_rows));
     plan.band_rows = (own_rows + plan.n_bands - 1) / plan.n_bands;
     plan.n_bands = (own_rows + plan.band_rows - 1) / plan.band_rows;
-    const StreamWaitValue32Fn wait_value = stream_wait_value32();
-    // the synchronous frame's copies wait for the band flags ON THE DEVICE (cuStreamWaitValue32); a frame in flight has them raised
-    // in host-visible memory and the host issues each copy when its flag is up (pump_flights)
-    plan.flags = (in_flight || wait_value != nullptr) && plan.n_bands > 1;
-    if (in_flight) plan.flag_words = ctx->host_flags + 32u * parity;     // page-locked + mapped: the same address on the device
+    plan.flags = plan.n_bands > 1;
+    plan.flag_words = ctx->host_flags + 32u * parity;                    // page-locked + mapped: the same address on the device
     plan.seq = ++ctx->frame_seq;
-    if (in_flight && (rc = pump_flights(ctx))) return rc;                 // what the previous frame has ready goes out first
+    if ((rc = pump_flights(ctx))) return rc;                              // what the previous frame has ready goes out first
     int4 rects[32];
     order_bands(ctx, camera, width, height, tile, first_row, own_rows, plan, rects);
     { OpsBatch z; if ((rc = ops_add(ctx, z, ctx->stream, ctx->work_counter.p, nullptr, kWordBandFlag * 4, 0u)) || (rc = ops_flush(ctx, z, ctx->stream))) return rc; }
@@ -2277,74 +2270,56 @@ static int render_frame_host(bvht_ctx* ctx, const bvht_camera* camera, uint32_t 
     if (rc) return rc;
     CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));                 // = every kernel of the frame is done
     cudaEventRecord(ctx->ev_band_t[0], ctx->stream);
-    if (!plan.flags) for (int c = 0; c < 3; ++c) CU(ctx, cudaStreamWaitEvent(ctx->copy_streams[c], ctx->ev_fork, 0));      // no flags: copy after the kernels
-    const unsigned long long flag_base = (unsigned long long)((unsigned int*)ctx->work_counter.p + kWordBandFlag);
     const int n_cs = std::max(1, std::min(ctx->n_copy_streams, 3));
-    bvht_ctx::CopyJob job;
-    job.host_frame = frame_out_host; job.host_hits = hits_out_host; job.d_rgba = d_rgba; job.d_hits = d_hits;
-    job.width = width; job.tile = tile; job.first_row = first_row; job.own_rows = own_rows; job.shard_n = shard_n; job.region = region;
-    auto copy_band = [&](uint32_t k, cudaStream_t cs) -> int {
-        return copy_own_rows(ctx, job, k * plan.band_rows, std::min(own_rows, (k + 1) * plan.band_rows), cs);
-    };
-    // belt and braces: once the kernels are done every flag is raised from the stream itself, so a copy can never wait forever
-    auto raise_all_flags = [&]() -> int {
-        OpsBatch f;
-        unsigned int* words = plan.flag_words ? plan.flag_words : (unsigned int*)ctx->work_counter.p + kWordBandFlag;
-        int rc2 = ops_add(ctx, f, ctx->stream, words, nullptr, 32 * 4, plan.seq);
-        return rc2 ? rc2 : ops_flush(ctx, f, ctx->stream);
-    };
-    if (in_flight) {
-        // nothing joins the main stream: the next frame's kernels start behind this frame's kernels, not behind its copies
-        if (plan.flags && (rc = raise_all_flags())) { sync_stream(ctx); cudaGetLastError(); return rc; }
-        bvht_ctx::Flight& f = ctx->flight[parity];
-        f.job = job;
-        f.n_bands = plan.n_bands; f.band_rows = plan.band_rows; f.next = 0; f.seq = plan.seq; f.flags = plan.flags;
-        memcpy(f.order, plan.order, sizeof f.order);
-        f.closed = false;
-        f.n_cs = n_cs; f.active = true;
-        ++ctx->flights_begun;
-        cudaEventRecord(ctx->ev_b, ctx->stream);                // last_trace_ms = the frame's kernels
-        ctx->trace_timed = true;
-        return pump_flights(ctx);                                // one band only: its copy is queued behind ev_fork right here
-    }
-    for (uint32_t i = 0; i < plan.n_bands; ++i) {
-        const uint32_t k = plan.order[i];
-        rc = BVHT_OK;
-        cudaStream_t cs = ctx->copy_streams[i % n_cs];
-        if (plan.flags && wait_value(cs, flag_base + 4ull * k, plan.seq, 1u /* CU_STREAM_WAIT_VALUE_GEQ */) != 0)
-            rc = fail(ctx, BVHT_ERR_CUDA, "cuStreamWaitValue32 failed");
-        if (!rc) rc = copy_band(k, cs);
-        if (rc) {
-            // what is already queued must not outlive this call: let the kernels finish, then release the waiting copies
-            if (plan.flags) raise_all_flags();
-            sync_stream(ctx);
-            for (int c = 0; c < 3; ++c) cudaStreamSynchronize(ctx->copy_streams[c]);
-            cudaGetLastError();
+    if (!plan.flags)                                                     // one band: its copy goes out now, behind the kernels
+        for (int c = 0; c < n_cs; ++c) CU(ctx, cudaStreamWaitEvent(ctx->copy_streams[c], ctx->ev_fork, 0));
+    else {
+        // belt and braces: once the kernels are done every flag is raised from the stream itself, so a copy can never wait forever
+        OpsBatch fl;
+        if ((rc = ops_add(ctx, fl, ctx->stream, plan.flag_words, nullptr, 32 * 4, plan.seq)) || (rc = ops_flush(ctx, fl, ctx->stream))) {
+            sync_stream(ctx); cudaGetLastError();
             return rc;
         }
-        if (i < 16) cudaEventRecord(ctx->ev_copy_t[i], cs);
     }
-    if (plan.flags && (rc = raise_all_flags())) return rc;     // queued after the copies: the first copy reaches its stream earlier
-    for (int c = 0; c < n_cs; ++c) {
-        CU(ctx, cudaEventRecord(ctx->ev_copy_join[c], ctx->copy_streams[c]));
-        CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_join[c], 0));
-    }
-    cudaEventRecord(ctx->ev_b, ctx->stream);
+    // nothing joins the main stream: a next frame's kernels start behind this frame's kernels, not behind its copies
+    f.job.host_frame = frame_out_host; f.job.host_hits = hits_out_host; f.job.d_rgba = d_rgba; f.job.d_hits = d_hits;
+    f.job.width = width; f.job.tile = tile; f.job.first_row = first_row; f.job.own_rows = own_rows; f.job.shard_n = shard_n; f.job.region = region;
+    f.n_bands = plan.n_bands; f.band_rows = plan.band_rows; f.next = 0; f.issued = 0; f.seq = plan.seq; f.flags = plan.flags;
+    memcpy(f.order, plan.order, sizeof f.order);
+    f.closed = false; f.timeline = timeline;
+    f.n_cs = n_cs; f.active = true;
+    ++ctx->flights_begun;
+    cudaEventRecord(ctx->ev_b, ctx->stream);                    // frames in flight: last_trace_ms = the frame's kernels
     ctx->trace_timed = true;
-    CU(ctx, sync_stream(ctx));
-    ctx->tl_bands = std::min(plan.n_bands, 16u); ctx->tl_valid = true;
-    for (uint32_t i = 0; i < ctx->tl_bands; ++i) ctx->tl_rows[i] = std::min(own_rows, (plan.order[i] + 1u) * plan.band_rows) - plan.order[i] * plan.band_rows;
-    return BVHT_OK;
+    return pump_flights(ctx);
 }
 
 int bvht_render_frame(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height, uint32_t tile,
                       bvht_rect region, const bvht_shade_params* shade, uint32_t* frame_out_host, bvht_hit* hits_out_host) {
-    return render_frame_host(ctx, camera, width, height, tile, region, shade, frame_out_host, hits_out_host, false);
+    if (!ctx) return BVHT_ERR_BAD_HANDLE;
+    cudaSetDevice(ctx->device);
+    int rc = drain_flights(ctx);                                 // frames begun and not ended complete first
+    if (rc) return rc;
+    const uint32_t parity = (uint32_t)(ctx->flights_begun & 1u);
+    if ((rc = render_frame_host(ctx, camera, width, height, tile, region, shade, frame_out_host, hits_out_host, ctx->knobs.timeline))) return rc;
+    const bvht_ctx::Flight& f = ctx->flight[parity];
+    const bool traced = f.n_bands > 0;
+    const uint32_t n_bands = f.n_bands;
+    const int n_cs = f.n_cs;
+    if ((rc = end_oldest_flight(ctx))) return rc;
+    if (traced) {
+        // the frame's device interval ends with its last copy (bvht_stats.last_trace_ms, bvht_debug_frame_timeline)
+        // (the copies are complete: the waits are no-ops that only order the event; bvht_get_stats waits for it when asked)
+        for (int c = 0; c < n_cs; ++c) CU(ctx, cudaStreamWaitEvent(ctx->stream, f.done[c], 0));
+        cudaEventRecord(ctx->ev_b, ctx->stream);
+        ctx->tl_bands = std::min(n_bands, 16u); ctx->tl_valid = ctx->knobs.timeline;
+    }
+    return BVHT_OK;
 }
 
 int bvht_render_frame_begin(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height, uint32_t tile,
                             bvht_rect region, const bvht_shade_params* shade, uint32_t* frame_out_host, bvht_hit* hits_out_host) {
-    return render_frame_host(ctx, camera, width, height, tile, region, shade, frame_out_host, hits_out_host, true);
+    return render_frame_host(ctx, camera, width, height, tile, region, shade, frame_out_host, hits_out_host, false);
 }
 
 int bvht_render_frame_end(bvht_ctx* ctx) {

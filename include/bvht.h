@@ -173,8 +173,10 @@ typedef enum bvht_option {
     BVHT_OPT_K0    = 2,   /* classify-and-fill pass for empty pixel blocks (K0): 0 off, 1 on */
     BVHT_OPT_BANDS = 3,   /* number of tile-row bands bvht_render_frame pipelines its device->host copies in (1..32) */
     BVHT_OPT_COPY_STREAMS = 5, /* streams the band copies of bvht_render_frame rotate over (1..3) */
-    BVHT_OPT_BAND_ORDER = 4 /* order in which the bands are traced and copied: 0 image order, 1 cheapest first, 2 cheap ascending
+    BVHT_OPT_BAND_ORDER = 4, /* order in which the bands are traced and copied: 0 image order, 1 cheapest first, 2 cheap ascending
                              * then expensive descending, 3 descending cost */
+    BVHT_OPT_TIMELINE = 6   /* 1: bvht_render_frame records a timing event behind every band copy for bvht_debug_frame_timeline
+                             * (about 3 us per band on the copy streams; off by default) */
 } bvht_option;
 BVHT_API int         bvht_set_option(bvht_ctx* ctx, uint32_t option, int32_t value);
 
@@ -332,8 +334,9 @@ BVHT_API int         bvht_get_stats(const bvht_ctx* ctx, bvht_stats* out);
  * streaming kernel -- L2 -> SM delivery when the buffer fits in L2 (e.g. 32 MiB), HBM when it is much larger (e.g. 2 GiB).
  * bench.py records it next to MEASURED_PEAKS.json's HBM figure. */
 BVHT_API int         bvht_debug_read_bandwidth(bvht_ctx* ctx, size_t bytes, uint32_t passes, double* gbs_out);
-/* Debug: device timeline of the last bvht_render_frame, milliseconds since its first device operation: [0] coverage raster done,
- * [1] frame complete (last copy), then per band in pull order (the first 16): all kernels done, copy done, tile rows of the band. */
+/* Debug: device timeline of the last bvht_render_frame made with BVHT_OPT_TIMELINE on (BVHT_ERR_NOT_READY otherwise), milliseconds
+ * since its first device operation: [0] coverage raster done, [1] frame complete (last copy), then per band in the order the
+ * copies were issued (the first 16): all kernels done, copy done, tile rows of the band. */
 BVHT_API int         bvht_debug_frame_timeline(bvht_ctx* ctx, float* ms_out, uint32_t capacity, uint32_t* n_out);
 BVHT_API int         bvht_debug_trace_stats(bvht_ctx* ctx, const bvht_camera* camera, uint32_t width, uint32_t height,
                                     uint32_t tile, bvht_rect region, uint64_t counters_out[16]);

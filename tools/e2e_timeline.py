@@ -23,6 +23,7 @@ for spec in band_list:
     wl.eng.set_option(_ffi.OPT_BANDS, bands)
     wl.eng.set_option(_ffi.OPT_BAND_ORDER, policy)
     wl.eng.set_option(_ffi.OPT_COPY_STREAMS, streams)
+    wl.eng.set_option(_ffi.OPT_TIMELINE, 1)
     T = {"sync_scene (host)": [], "render (host, incl. final sync)": [], "device frame (ev_a..ev_b)": []}
     for f in range(24):
         wl.advance()

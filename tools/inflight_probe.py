@@ -11,6 +11,7 @@ wl = bench.GpuWorkload(name, bench.MODES["strict-accel"], 0)
 from bvhtracer_b200 import host
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 wl.renderer.set_stream(stream.cuda_stream)
+wl.eng.set_option(6, 1)            # BVHT_OPT_TIMELINE
 w, h = bench.frame_size(name, 1, "strong")
 states = [host.RendererState(wl.pipeline, w, h, keep_hits=False) for _ in range(2)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
