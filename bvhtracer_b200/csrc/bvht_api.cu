@@ -141,9 +141,11 @@ struct bvht_ctx {
     std::vector<float> inst_tight;                    // 6 floats per instance (world lo/hi) or lo > hi when unusable
     double bake_center[3] = { 0.0, 0.0, 0.0 };        // camera origin the tight TLAS boxes' origin limit is centred on
     DevBuf work_counter;                              // 256 words: [0] K1's work cursor | [32..63] blocks K0 listed per band | [64..95] blocks
-                                                      //   finished per band | [96..127] band completion flags (never zeroed: they carry
-                                                      //   the frame sequence number) | [128..129] scratch of the ray-bounds reduction
-    uint32_t frame_seq = 0;                           // bvht_render_frame's band flags are raised to this value
+                                                      //   finished per band | [96..127] band completion flags of launches whose flags
+                                                      //   stay on the device (host-bound frames raise theirs in host_flags; neither
+                                                      //   is zeroed: they carry the frame sequence number) | [128..129] scratch of
+                                                      //   the ray-bounds reduction
+    uint32_t frame_seq = 0;                           // a host-bound frame's band flags are raised to this value
     DevBuf cover, cover_aux;                          // per-triangle block coverage of the current frame (cover_kernels.cu); aux: full word, big count, big list
     bool cover_ready = false;                         // valid for the launches of the current frame only
     uint32_t cover_ntx = 0;
@@ -171,13 +173,10 @@ struct bvht_ctx {
     } flight[2];
     uint64_t flights_begun = 0, flights_ended = 0;
     unsigned int* host_flags = nullptr;               // page-locked + mapped, 2 x 32 words: band flags of the frames in flight
-    cudaStream_t aux[2] = { nullptr, nullptr };       // band pipelining: two compute streams + one copy stream
     cudaStream_t copy_stream = nullptr;
     cudaStream_t copy_streams[3] = { nullptr, nullptr, nullptr };   // bvht_render_frame's band copies rotate over these (copy_stream is [0])
-    cudaEvent_t ev_copy_join[3] = { nullptr, nullptr, nullptr };
     int n_copy_streams = 2;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    cudaEvent_t ev_band[64] = {};
+    cudaEvent_t ev_fork = nullptr;                    // every kernel of the frame is done
     cudaEvent_t ev_band_t[17] = {};                   // timing events: [0] = start, [i + 1] = end of the i-th launched band
     void* pinned = nullptr; size_t pinned_bytes = 0;  // pinned staging for small uploads (synchronous users)
     // ring of page-locked staging slots for the per-frame uploads (bvht_tlas_set): a slot is reused only after the copies queued
@@ -1162,20 +1161,15 @@ int bvht_create(int device, uint32_t flags, bvht_ctx** out) {
           && cudaMemset(ctx->work_counter.p, 0, 1024) == cudaSuccess;
     }
     if (ok) {
-        ok = cudaStreamCreateWithFlags(&ctx->aux[0], cudaStreamNonBlocking) == cudaSuccess
-          && cudaStreamCreateWithFlags(&ctx->aux[1], cudaStreamNonBlocking) == cudaSuccess
-          && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess
+        ok = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess
           && cudaStreamCreateWithFlags(&ctx->copy_streams[1], cudaStreamNonBlocking) == cudaSuccess
           && cudaStreamCreateWithFlags(&ctx->copy_streams[2], cudaStreamNonBlocking) == cudaSuccess
-          && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess
-          && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
+          && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
         ctx->copy_streams[0] = ctx->copy_stream;
-        for (int i = 0; ok && i < 3; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_copy_join[i], cudaEventDisableTiming) == cudaSuccess;
         for (int f = 0; f < 2; ++f)
             for (int i = 0; ok && i < 3; ++i) ok = cudaEventCreateWithFlags(&ctx->flight[f].done[i], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaHostAlloc((void**)&ctx->host_flags, 2 * 32 * sizeof(unsigned int), cudaHostAllocMapped) == cudaSuccess;
         if (ok) memset(ctx->host_flags, 0, 2 * 32 * sizeof(unsigned int));
-        for (int i = 0; ok && i < 64; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_band[i], cudaEventDisableTiming) == cudaSuccess;
         for (int i = 0; ok && i < 17; ++i) ok = cudaEventCreate(&ctx->ev_band_t[i]) == cudaSuccess;
         for (int i = 0; ok && i < 16; ++i) ok = cudaEventCreate(&ctx->ev_copy_t[i]) == cudaSuccess;
         ok = ok && cudaEventCreate(&ctx->ev_cover_t) == cudaSuccess;
@@ -1201,10 +1195,8 @@ void bvht_destroy(bvht_ctx* ctx) {
                        &ctx->rgba_buf, &ctx->tlas_tight, &ctx->tlas_mask, &ctx->stats_scratch, &ctx->scene_in, &ctx->scene_bounds, &ctx->build_tris, &ctx->build_perm })
         release(*d);
     ctx->build_ws.release();
-    for (cudaStream_t st : { ctx->aux[0], ctx->aux[1], ctx->copy_stream, ctx->copy_streams[1], ctx->copy_streams[2] }) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
-    for (cudaEvent_t ev : ctx->ev_copy_join) if (ev) cudaEventDestroy(ev);
-    for (cudaEvent_t ev : { ctx->ev_fork, ctx->ev_join }) if (ev) cudaEventDestroy(ev);
-    for (cudaEvent_t ev : ctx->ev_band) if (ev) cudaEventDestroy(ev);
+    for (cudaStream_t st : { ctx->copy_stream, ctx->copy_streams[1], ctx->copy_streams[2] }) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (cudaEvent_t ev : ctx->ev_band_t) if (ev) cudaEventDestroy(ev);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (auto& st : ctx->stage) { if (st.p) cudaFreeHost(st.p); if (st.done) cudaEventDestroy(st.done); }

@@ -89,8 +89,9 @@ struct PrimaryParams {
     // Bands.  The launch's pixel blocks, in their row-major numbering, are cut into n_bands runs of band_items blocks (whole tile
     // rows; the last run may be shorter).  K1 pulls them band by band in band_order -- the host puts the cheapest bands first,
     // so that the frame ends with its most expensive rows and the device->host copies of the earlier bands hide behind them --
-    // and raises band_flag[b] to band_seq when the last block of band b is finished: the copy of that band's rows waits for the
-    // flag on another stream (cuStreamWaitValue32), with no host round trip and no kernel boundary between bands.
+    // and raises band_flag[b] to band_seq when the last block of band b is finished (system-scope fence first: the flags of a
+    // host-bound frame live in page-locked host memory, and the host issues the copy of that band's rows when it sees the flag;
+    // bvht_api.cu pump_flights), with no kernel boundary between bands.
     uint32_t      n_bands;               // 1..32
     uint32_t      band_items;            // blocks per band = rows per band * ntx * items_per_tile
     uint8_t       band_order[32];        // pull position -> band
