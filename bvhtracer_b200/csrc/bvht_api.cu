@@ -2151,8 +2151,10 @@ static int end_oldest_flight(bvht_ctx* ctx) {
     const uint32_t parity = (uint32_t)(ctx->flights_ended & 1u);
     bvht_ctx::Flight& f = ctx->flight[parity];
     if (!f.active) return fail(ctx, BVHT_ERR_NOT_READY, "no frame in flight");
-    // a bounded wait: a frame that never completes must surface as an error with the evidence, not as a hang
-    const auto t0 = std::chrono::steady_clock::now();
+    // a bounded wait: a frame that never completes must surface as an error with the evidence, not as a hang.  The clock only
+    // runs while the main stream is idle (every kernel of the frame done, every flag raised): from then on all that is left are
+    // the copies, milliseconds of work however long the kernels took.
+    auto t0 = std::chrono::steady_clock::now();
     int rc = BVHT_OK;
     for (;;) {
         if ((rc = pump_flights(ctx))) break;
@@ -2162,10 +2164,13 @@ static int end_oldest_flight(bvht_ctx* ctx) {
             if (e == cudaSuccess) break;
             if (e != cudaErrorNotReady) { rc = fail(ctx, BVHT_ERR_CUDA, "frame in flight failed: %s", cudaGetErrorString(e)); break; }
         }
-        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 20.0) {
+        const auto now = std::chrono::steady_clock::now();
+        const double waited = std::chrono::duration<double>(now - t0).count();
+        if (waited > 1.0 && waited <= 20.0 && cudaStreamQuery(ctx->stream) == cudaErrorNotReady) t0 = now;     // kernels still running
+        else if (waited > 20.0) {
             std::string flags;
             for (uint32_t k = 0; k < f.n_bands; ++k) flags += std::to_string(ctx->host_flags[32u * parity + k]) + " ";
-            rc = fail(ctx, BVHT_ERR_CUDA, "frame in flight did not complete within 20 s (bands issued %u of %u; frame sequence %u; band flags %s; "
+            rc = fail(ctx, BVHT_ERR_CUDA, "frame in flight did not complete within 20 s of its last kernel (bands issued %u of %u; frame sequence %u; band flags %s; "
                       "main stream %s)", f.next, f.n_bands, f.seq, flags.c_str(), cudaStreamQuery(ctx->stream) == cudaSuccess ? "idle" : "busy");
             break;
         }
