@@ -39,6 +39,27 @@ def test_abi_version_and_struct_sizes():
     assert lib.bvht_status_string(-2).decode().startswith("no CUDA device")
 
 
+def test_python_constants_match_the_header():
+    # bvht_option, flags and status codes are spelled twice (include/bvht.h and bvhtracer_b200/_ffi.py): keep them equal
+    text = open(os.path.join(ROOT, "include", "bvht.h")).read()
+    enum = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"\b(BVHT_[A-Z0-9_]+)\s*=\s*(-?(?:0x[0-9a-fA-F]+|\d+))\b", text)}
+    for name in ("COVER", "K0", "BANDS", "BAND_ORDER", "COPY_STREAMS", "TIMELINE"):
+        assert getattr(_ffi, "OPT_" + name) == enum["BVHT_OPT_" + name], name
+    assert len({enum[k] for k in enum if k.startswith("BVHT_OPT_")}) == 6          # no two options share a number
+    assert _ffi.ERR_NO_DEVICE == enum["BVHT_ERR_NO_DEVICE"]
+    for name in ("DEPTH", "UV", "NORMAL", "TEXTURE"):
+        assert getattr(_ffi, "SHADE_" + name) == enum["BVHT_SHADE_" + name], name
+
+
+def test_host_mirror_exports_the_frames_in_flight_calls():
+    # Renderer::render_begin / render_end and the batched set_transform of the C++ mirror (no device needed to load it)
+    from bvhtracer_b200 import host
+    L = host.lib()
+    for name in ("bvhx_renderer_render", "bvhx_renderer_render_begin", "bvhx_renderer_render_end", "bvhx_scene_set_transforms"):
+        assert hasattr(L, name), name
+    assert callable(host.Renderer.render_begin) and callable(host.Renderer.render_end)
+
+
 def test_no_device_is_an_error_not_a_fallback():
     lib = _ffi.load()
     if lib.bvht_device_count() > 0:

@@ -72,6 +72,27 @@ def test_scene_update_and_rebuild_match_oracle():
             assert scene.instance(i)[0].tobytes() == ref_scene.inst["inv"][i].tobytes()
 
 
+def test_batched_set_transforms_is_the_per_object_loop():
+    # Scene.set_transforms (one binding call) = set_transform(i, t) for i in 0..n-1: same TLAS, same inverses after rebuild
+    anim = examples.GridAnimation()
+    spec = examples.sixteen_armadillos(0)
+    one, _ = host.build_scene(spec)
+    batched, _ = host.build_scene(spec)
+    for frame in range(3):
+        anim.update()
+        transforms = [host.object_transform(o) for o in anim.objects()]
+        for i, t in enumerate(transforms):
+            one.set_transform(i, t)
+        batched.set_transforms(np.stack([t.matrix for t in transforms]))
+        one.rebuild(); batched.rebuild()
+        (ta, ua), (tb, ub) = one.tlas(), batched.tlas()
+        assert ua == ub and ta[:ua].tobytes() == tb[:ub].tobytes()
+        for i in range(16):
+            assert one.instance(i)[0].tobytes() == batched.instance(i)[0].tobytes()
+    with pytest.raises(host.HostError):
+        batched.set_transforms(np.zeros((17, 16), "<f4"))             # more transforms than objects
+
+
 def test_transform_matches_oracle():
     rng = np.random.default_rng(5)
     for _ in range(50):
