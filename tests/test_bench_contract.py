@@ -37,3 +37,25 @@ def test_gpu_arm_has_no_cpu_fallback():
     r = _run("--steps", "1", "--warmup", "3")
     assert r.returncode != 0
     assert "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_committed_bench_lines_carry_the_contract():
+    # the bench lines kept under profiles/ (what DESIGN.md's tables are printed from) hold every key of the contract
+    import glob
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r02f_bench_*_n1.json")))
+    assert len(paths) == 5
+    for p in paths:
+        d = json.loads(open(p).read().strip().splitlines()[-1])
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                    "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+            assert key in d, (p, key)
+        assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0 and d["vs_baseline"] is None
+        r = d["roofline"]
+        assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(r) and 0.0 < r["frac"] <= 1.0
+        e = d["e2e"]
+        assert e["d2h_bytes_per_step"] >= d["config"]["width"] * d["config"]["height"] * 4 and e["value"] < d["value"]
+        assert e["two_frames_in_flight"]["last_frame_equals_render"] is True
+        c = d["clocks"]
+        assert not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        cb = d["cpu_baseline"]
+        assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0
