@@ -16,6 +16,8 @@ AppState::update), then every primary ray of the frame traced to its closest hit
   e2e    : the same frame through the reference-facing plugin call `Renderer::render` of the C++ host mirror
            (CudaPathTracer::evaluate: model / TLAS / instance uploads from host memory + refit + trace + on-device accumulator and
            pixel shader + Rgba<u8> frame buffer copied back to page-locked host memory), CUDA events around the call.
+           e2e.two_frames_in_flight (N = 1): the same frames through Renderer::render_begin / render_end over two frame buffers
+           (frame n copied back under frame n+1's kernels), ONE interval around the whole loop, L2 flushes inside it.
 Multi-GPU (torchrun, one rank per GPU), STRONG scaling by default: the frame is fixed, the scene replicated, tile rows
 interleaved over the ranks.  value: every rank stores its shaded pixels straight into rank 0's frame buffer over NVLink P2P (CUDA
 IPC mapping), no collective in the data path; hit records stay in the rank's own HBM.  e2e: every rank's `Renderer::render`
