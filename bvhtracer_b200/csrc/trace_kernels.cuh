@@ -53,7 +53,8 @@ __device__ __forceinline__ void ray_prepare_fma(RayM& r) {
 
 struct HitRec { float t, u, v; uint32_t id; };
 
-// Result stores.  BVHT_STORE_CS: 1 = streaming stores (evict-first) for the records / pixels K0 writes, 2 = for K1's as well.
+// Result stores.  BVHT_STORE_CS: 1 = streaming stores (evict-first) for the records / pixels K0 writes, 2 = for K1's as well
+// (measured on C3 4K and C5 8K, resident and end to end: no difference either way, so plain stores stay the default).
 #ifndef BVHT_STORE_CS
 #define BVHT_STORE_CS 0
 #endif
